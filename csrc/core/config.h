@@ -1,0 +1,46 @@
+// Configuration structs shared by C++, the pybind layer and the Python kwargs/argparse
+// surface.  Field names of the first block of each struct are the reference's
+// (src/config.h:13-32); the second block is the B200 fabric extension.
+#pragma once
+
+#include <cstddef>
+#include <string>
+#include <vector>
+
+namespace istore {
+
+struct ServerConfig {
+    int service_port = 0;
+    std::string log_level = "warning";
+    std::string dev_name = "mlx5_1";  // accepted and ignored on the NVLink fabric
+    size_t prealloc_size = 16;        // GB
+    int ib_port = 1;                  // accepted and ignored
+    std::string link_type = "IB";     // accepted and ignored
+    int minimal_allocate_size = 64;   // KB (allocation granule)
+    int num_stream = 1;               // deprecated in the reference; ignored
+    bool auto_increase = false;
+
+    // --- fabric extension
+    std::string host = "0.0.0.0";          // listen address (the reference parses but ignores it)
+    std::string pool_backend = "auto";     // auto | hbm | host
+    std::vector<int> pool_devices;         // CUDA ordinals hosting pool segments (default {0})
+    size_t extend_size = 10;               // GB added per auto-increase step
+    size_t prealloc_bytes = 0;             // if non-zero overrides prealloc_size (tests)
+    size_t index_slots = 0;                // device-index entries per segment (0 = auto)
+};
+
+struct ClientConfig {
+    int service_port = 0;
+    std::string log_level = "warning";
+    std::string dev_name = "mlx5_1";
+    std::string host_addr;
+    int ib_port = 1;
+    std::string link_type = "IB";
+
+    // --- fabric extension
+    int device = -1;          // CUDA ordinal the client launches kernels on (-1: decide per tensor)
+    int timeout_ms = 10000;   // per-request deadline on the control plane
+    int pool_hint = -1;       // preferred pool segment device for allocations (-1 = any)
+};
+
+}  // namespace istore

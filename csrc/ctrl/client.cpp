@@ -1,0 +1,1069 @@
+#include "client.h"
+
+#include <arpa/inet.h>
+#include <cuda_runtime_api.h>
+#include <netdb.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <sys/socket.h>
+#include <sys/time.h>
+#include <sys/uio.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cstring>
+
+#include "../core/log.h"
+#include "../kernels/kernels.h"
+#include "../wire/messages.h"
+
+namespace istore {
+
+namespace {
+
+constexpr size_t kBlobPayload = ~size_t(0);
+constexpr size_t kRingBytes = 16u << 20;     // pinned, mapped staging ring per device
+constexpr size_t kScratchBytes = 8u << 20;   // device scratch per device
+constexpr size_t kZeroBytes = 2u << 20;      // self-cleaning zeroed counters per device
+constexpr size_t kMaxBatch = 65536;          // blocks per kernel launch
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (dev >= 0 && dev != prev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+bool send_all(int fd, const iovec* iov_in, int iovcnt) {
+    iovec iov[4];
+    for (int i = 0; i < iovcnt; ++i) iov[i] = iov_in[i];
+    int first = 0;
+    while (first < iovcnt) {
+        msghdr mh{};
+        mh.msg_iov = iov + first;
+        mh.msg_iovlen = size_t(iovcnt - first);
+        ssize_t n = sendmsg(fd, &mh, MSG_NOSIGNAL);
+        if (n < 0) {
+            if (errno == EINTR) continue;
+            return false;
+        }
+        while (n > 0 && first < iovcnt) {
+            if (size_t(n) >= iov[first].iov_len) {
+                n -= ssize_t(iov[first].iov_len);
+                ++first;
+            } else {
+                iov[first].iov_base = static_cast<uint8_t*>(iov[first].iov_base) + n;
+                iov[first].iov_len -= size_t(n);
+                n = 0;
+            }
+        }
+        while (first < iovcnt && iov[first].iov_len == 0) ++first;
+    }
+    return true;
+}
+
+bool recv_all(int fd, void* buf, size_t len) {
+    uint8_t* p = static_cast<uint8_t*>(buf);
+    while (len) {
+        const ssize_t n = recv(fd, p, len, 0);
+        if (n == 0) return false;
+        if (n < 0) {
+            if (errno == EINTR) continue;
+            return false;
+        }
+        p += n;
+        len -= size_t(n);
+    }
+    return true;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
+
+}  // namespace
+
+// Per-device data-plane state.
+struct Connection::DevCtx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    std::vector<std::shared_ptr<fabric::Mapping>> maps;  // by segment id
+    uint8_t* ring_h = nullptr;  // pinned + mapped: descriptors, publish records, key bytes
+    uint8_t* ring_d = nullptr;
+    size_t ring_head = 0;
+    uint8_t* scratch = nullptr;  // device memory: descriptors built by the lookup kernel
+    size_t scratch_head = 0;
+    uint8_t* zeros = nullptr;    // device memory kept zero between launches (counters/tickets)
+    size_t zeros_head = 0;
+    uint32_t* status_h = nullptr;
+    uint32_t* status_d = nullptr;
+    std::vector<std::pair<cudaStream_t, cudaEvent_t>> events;  // last launch per stream
+    bool dirty = false;
+
+    ~DevCtx() {
+        DeviceGuard g(device);
+        for (auto& e : events) {
+            cudaEventSynchronize(e.second);
+            cudaEventDestroy(e.second);
+        }
+        if (stream) {
+            cudaStreamSynchronize(stream);
+            cudaStreamDestroy(stream);
+        }
+        maps.clear();
+        if (ring_h) cudaFreeHost(ring_h);
+        if (status_h) cudaFreeHost(status_h);
+        if (scratch) cudaFree(scratch);
+        if (zeros) cudaFree(zeros);
+    }
+
+    void wait_all() {
+        DeviceGuard g(device);
+        for (auto& e : events) cudaEventSynchronize(e.second);
+        dirty = false;
+    }
+    void mark(cudaStream_t s) {
+        for (auto& e : events)
+            if (e.first == s) {
+                cudaEventRecord(e.second, s);
+                dirty = true;
+                return;
+            }
+        cudaEvent_t ev;
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        cudaEventRecord(ev, s);
+        events.emplace_back(s, ev);
+        dirty = true;
+    }
+    // Bump allocators.  When a region wraps, everything launched from it must be done.
+    size_t ring_alloc(size_t bytes) {
+        bytes = align_up(bytes, 64);
+        if (ring_head + bytes > kRingBytes) {
+            wait_all();
+            ring_head = 0;
+        }
+        const size_t at = ring_head;
+        ring_head += bytes;
+        return at;
+    }
+    size_t scratch_alloc(size_t bytes) {
+        bytes = align_up(bytes, 256);
+        if (scratch_head + bytes > kScratchBytes) {
+            wait_all();
+            scratch_head = 0;
+        }
+        const size_t at = scratch_head;
+        scratch_head += bytes;
+        return at;
+    }
+    size_t zeros_alloc(size_t bytes) {
+        bytes = align_up(bytes, 256);
+        if (zeros_head + bytes > kZeroBytes) {
+            wait_all();
+            zeros_head = 0;
+        }
+        const size_t at = zeros_head;
+        zeros_head += bytes;
+        return at;
+    }
+};
+
+struct Connection::Task {
+    enum Kind { kAllocate, kWaitEvent, kStop } kind = kWaitEvent;
+    // allocate
+    std::vector<std::string> keys;
+    int block_size = 0;
+    std::function<void(std::vector<RemoteBlock>)> alloc_cb;
+    // wait for device work, then commit + callback
+    int device = -1;
+    cudaEvent_t event = nullptr;
+    int status = 0;
+    bool commit = false;
+    std::function<void(int)> done_cb;
+};
+
+Connection::Connection() {}
+
+Connection::~Connection() { close(); }
+
+void Connection::fail(const std::string& msg) {
+    last_error_ = msg;
+    LOG_ERROR("%s", msg.c_str());
+}
+
+ClientStats Connection::stats() const { return stats_; }
+
+// ---------------------------------------------------------------- control plane
+
+int Connection::init_connection(const ClientConfig& cfg) {
+    cfg_ = cfg;
+    if (fd_ >= 0) return 0;
+    addrinfo hints{};
+    hints.ai_family = AF_INET;
+    hints.ai_socktype = SOCK_STREAM;
+    addrinfo* res = nullptr;
+    const std::string port = std::to_string(cfg.service_port);
+    if (getaddrinfo(cfg.host_addr.c_str(), port.c_str(), &hints, &res) != 0 || !res) {
+        fail("cannot resolve " + cfg.host_addr);
+        return -1;
+    }
+    int fd = -1;
+    for (addrinfo* ai = res; ai; ai = ai->ai_next) {
+        fd = socket(ai->ai_family, ai->ai_socktype | SOCK_CLOEXEC, ai->ai_protocol);
+        if (fd < 0) continue;
+        if (connect(fd, ai->ai_addr, ai->ai_addrlen) == 0) break;
+        ::close(fd);
+        fd = -1;
+    }
+    freeaddrinfo(res);
+    if (fd < 0) {
+        fail("cannot connect to " + cfg.host_addr + ":" + port + ": " + std::strerror(errno));
+        return -1;
+    }
+    int one = 1;
+    setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+    timeval tv{};
+    tv.tv_sec = cfg.timeout_ms / 1000;
+    tv.tv_usec = (cfg.timeout_ms % 1000) * 1000;
+    setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+    setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof(tv));
+    fd_ = fd;
+
+    ConnInfo me{};
+    me.qpn = uint32_t(getpid());
+    me.psn = cfg.device >= 0 ? uint32_t(cfg.device) : 0xffffffffu;
+    std::memcpy(me.gid, fabric::process_uuid(), 16);
+    me.lid = fabric::cuda_available() ? 1 : 0;
+    me.mtu = kFabricVersion;
+    int32_t code = 0;
+    std::vector<uint8_t> payload;
+    if (transact(kOpExchange, &me, sizeof(me), &code, &payload, sizeof(ConnInfo)) != 0 ||
+        code != kFinish) {
+        fail("fabric exchange with the server failed");
+        close();
+        return -1;
+    }
+    ConnInfo srv{};
+    std::memcpy(&srv, payload.data(), sizeof(srv));
+    if (srv.mtu != kFabricVersion) {
+        fail("server speaks fabric protocol v" + std::to_string(srv.mtu));
+        close();
+        return -1;
+    }
+    server_cuda_ = srv.lid & 1;
+    server_hbm_ = srv.lid & 2;
+    std::memcpy(server_uuid_, srv.gid, 16);
+    if (!worker_.joinable()) {
+        stop_ = false;
+        worker_ = std::thread([this] { worker(); });
+    }
+    return 0;
+}
+
+int Connection::setup_rdma(const ClientConfig&) {
+    if (fd_ < 0) return -1;
+    // The HBM pool is the fast path: look keys up on the GPU unless told otherwise.
+    device_lookup_ = false;
+    return refresh_pool_map();
+}
+
+void Connection::close() {
+    if (worker_.joinable()) {
+        {
+            std::lock_guard<std::mutex> lk(q_mu_);
+            stop_ = true;
+            Task t;
+            t.kind = Task::kStop;
+            queue_.push_back(std::move(t));
+        }
+        q_cv_.notify_all();
+        worker_.join();
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto& kv : devs_) kv.second->wait_all();
+        devs_.clear();
+        host_maps_.clear();
+        for (auto& kv : host_regs_)
+            if (kv.second.registered) cudaHostUnregister(reinterpret_cast<void*>(kv.first));
+        host_regs_.clear();
+    }
+    if (fd_ >= 0) {
+        ::close(fd_);
+        fd_ = -1;
+    }
+}
+
+// One request/response exchange.  fixed_payload: bytes following the code on success, or
+// kBlobPayload for "u32 length + blob".
+int Connection::transact(char op, const void* body, size_t len, int32_t* code,
+                         std::vector<uint8_t>* payload, size_t fixed_payload) {
+    std::lock_guard<std::mutex> lk(sock_mu_);
+    if (fd_ < 0) return -1;
+    Header h{kMagic, op, uint32_t(len)};
+    iovec iov[2] = {{&h, sizeof(h)}, {const_cast<void*>(body), len}};
+    if (!send_all(fd_, iov, len ? 2 : 1)) {
+        fail(std::string("send ") + op_name(op) + ": " + std::strerror(errno));
+        return -1;
+    }
+    stats_.ctrl_requests++;
+    if (!recv_all(fd_, code, sizeof(*code))) {
+        fail(std::string("no reply to ") + op_name(op) + " (timeout or connection closed)");
+        return -1;
+    }
+    if (payload) payload->clear();
+    if (*code != kFinish && *code != kTaskAccepted) return 0;  // error replies carry no payload
+    if (fixed_payload == kBlobPayload) {
+        uint32_t n = 0;
+        if (!recv_all(fd_, &n, sizeof(n)) || n > kMaxBody + 4096) return -1;
+        payload->resize(n);
+        if (n && !recv_all(fd_, payload->data(), n)) return -1;
+    } else if (fixed_payload) {
+        payload->resize(fixed_payload);
+        if (!recv_all(fd_, payload->data(), fixed_payload)) return -1;
+    }
+    return 0;
+}
+
+int Connection::send_only(char op, const void* body, size_t len) {
+    std::lock_guard<std::mutex> lk(sock_mu_);
+    if (fd_ < 0) return -1;
+    Header h{kMagic, op, uint32_t(len)};
+    iovec iov[2] = {{&h, sizeof(h)}, {const_cast<void*>(body), len}};
+    if (!send_all(fd_, iov, len ? 2 : 1)) return -1;
+    stats_.ctrl_requests++;
+    return 0;
+}
+
+int Connection::refresh_pool_map() {
+    const uint32_t first = uint32_t(segs_.size());
+    int32_t code = 0;
+    std::vector<uint8_t> blob;
+    if (transact(kOpPoolMap, &first, sizeof(first), &code, &blob, kBlobPayload) != 0 ||
+        code != kFinish || blob.size() < 4)
+        return -1;
+    uint32_t count = 0;
+    std::memcpy(&count, blob.data(), 4);
+    if (blob.size() != 4 + size_t(count) * sizeof(SegmentInfo)) return -1;
+    for (uint32_t i = 0; i < count; ++i) {
+        SegmentInfo s;
+        std::memcpy(&s, blob.data() + 4 + size_t(i) * sizeof(SegmentInfo), sizeof(s));
+        segs_.push_back(s);
+    }
+    return 0;
+}
+
+int Connection::check_exist(const std::string& key) {
+    if (device_lookup_ && server_hbm_) {
+        const int r = match_via_device_index({key}, true);
+        if (r >= -1) return r == 0 ? 0 : 1;
+    }
+    int32_t code = 0;
+    std::vector<uint8_t> p;
+    if (transact(kOpCheckExist, key.data(), key.size(), &code, &p, sizeof(int32_t)) != 0 ||
+        code != kFinish)
+        return -1;
+    int32_t v;
+    std::memcpy(&v, p.data(), sizeof(v));
+    return v;
+}
+
+int Connection::get_match_last_index(const std::vector<std::string>& keys) {
+    if (keys.empty()) return -1;
+    if (device_lookup_ && server_hbm_) {
+        const int r = match_via_device_index(keys, false);
+        if (r >= -1) return r;
+    }
+    std::vector<std::string_view> kv(keys.begin(), keys.end());
+    std::vector<uint8_t> buf(remote_meta_bound(kv, 0));
+    fb::Builder b(buf.data(), buf.size());
+    encode_match_request(b, kv);
+    int32_t code = 0;
+    std::vector<uint8_t> p;
+    if (transact(kOpMatchLastIdx, b.data(), b.size(), &code, &p, sizeof(int32_t)) != 0 ||
+        code != kFinish)
+        return -2;
+    int32_t v;
+    std::memcpy(&v, p.data(), sizeof(v));
+    return v;
+}
+
+int Connection::sync_local() {
+    if (drain_devices() != 0) return -1;
+    if (flush_commits() != 0) return -1;
+    int32_t code = 0;
+    std::vector<uint8_t> p;
+    if (transact(kOpSync, nullptr, 0, &code, &p, sizeof(uint32_t)) != 0 || code != kFinish)
+        return -1;
+    uint32_t remain;
+    std::memcpy(&remain, p.data(), sizeof(remain));
+    return int(remain);
+}
+
+int Connection::sync_rdma() {
+    {  // async operations first: their completions append to the commit list
+        std::unique_lock<std::mutex> lk(q_mu_);
+        if (!idle_cv_.wait_for(lk, std::chrono::milliseconds(cfg_.timeout_ms),
+                               [this] { return inflight_async_ == 0; })) {
+            fail("sync: timed out waiting for asynchronous operations");
+            return -1;
+        }
+    }
+    const int r = sync_local();
+    return r < 0 ? r : 0;
+}
+
+int Connection::flush_commits() {
+    std::vector<uint64_t> addrs;
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        addrs.swap(pending_commit_);
+    }
+    if (addrs.empty()) return 0;
+    // chunk so that one message stays far below the body cap
+    constexpr size_t kChunk = 256 * 1024;
+    for (size_t at = 0; at < addrs.size(); at += kChunk) {
+        const size_t n = std::min(kChunk, addrs.size() - at);
+        std::vector<uint8_t> buf(align_up(n * 8 + 128, 8));
+        fb::Builder b(buf.data(), buf.size());
+        encode_remote_meta(b, {}, 0, 0, addrs.data() + at, n, kOpCommit);
+        if (send_only(kOpCommit, b.data(), b.size()) != 0) {
+            fail("commit: send failed");
+            return -1;
+        }
+    }
+    return 0;
+}
+
+int Connection::allocate(const std::vector<std::string>& keys, int block_size,
+                         std::vector<RemoteBlock>& out) {
+    out.clear();
+    if (keys.empty() || block_size <= 0) return -1;
+    std::vector<std::string_view> kv(keys.begin(), keys.end());
+    std::vector<uint8_t> buf(remote_meta_bound(kv, 0));
+    if (buf.size() > kMaxBody) {
+        fail("allocate: too many keys for one request");
+        return -1;
+    }
+    fb::Builder b(buf.data(), buf.size());
+    encode_remote_meta(b, kv, block_size, 0, nullptr, 0, kOpAllocate, cfg_.pool_hint);
+    int32_t code = 0;
+    std::vector<uint8_t> p;
+    if (transact(kOpAllocate, b.data(), b.size(), &code, &p, kBlobPayload) != 0) return -1;
+    if (code != kFinish) {
+        fail("allocate: server returned " + std::to_string(code));
+        return -code;
+    }
+    try {
+        out = decode_allocate_response(p.data(), p.size());
+    } catch (const std::exception& e) {
+        fail(std::string("allocate: bad reply: ") + e.what());
+        return -1;
+    }
+    if (out.size() != keys.size()) return -1;
+    if (server_hbm_) {  // remember fingerprints: the write kernel publishes them in-band
+        std::lock_guard<std::mutex> lk(mu_);
+        for (size_t i = 0; i < keys.size(); ++i) {
+            if (is_fake_block(out[i])) continue;
+            pending_hash_[out[i].remote_addr] =
+                hash_key(reinterpret_cast<const uint8_t*>(keys[i].data()), keys[i].size());
+        }
+    }
+    return 0;
+}
+
+int Connection::lookup_blocks(char op, const std::vector<KeyOffset>& blocks, int block_size,
+                              std::vector<RemoteBlock>& out) {
+    int32_t code = 0;
+    std::vector<uint8_t> p;
+    if (op == kOpLocalRead || op == kOpLocalWrite) {
+        std::vector<LocalBlock> lb(blocks.size());
+        for (size_t i = 0; i < blocks.size(); ++i) lb[i] = LocalBlock{blocks[i].key, blocks[i].offset};
+        std::vector<uint8_t> buf(local_meta_bound(lb));
+        fb::Builder b(buf.data(), buf.size());
+        encode_local_meta(b, std::max(default_device_, 0), std::string_view(), block_size, lb);
+        if (transact(op, b.data(), b.size(), &code, &p, kBlobPayload) != 0) return -1;
+    } else {
+        std::vector<std::string_view> kv;
+        kv.reserve(blocks.size());
+        for (auto& kb : blocks) kv.push_back(kb.key);
+        std::vector<uint8_t> buf(remote_meta_bound(kv, 0));
+        fb::Builder b(buf.data(), buf.size());
+        encode_remote_meta(b, kv, block_size, 0, nullptr, 0, op, cfg_.pool_hint);
+        if (transact(op, b.data(), b.size(), &code, &p, kBlobPayload) != 0) return -1;
+    }
+    if (code != kFinish && code != kTaskAccepted) {
+        last_error_ = std::string(op_name(op)) + ": server returned " + std::to_string(code);
+        return -code;
+    }
+    try {
+        out = decode_allocate_response(p.data(), p.size());
+    } catch (const std::exception& e) {
+        fail(std::string("bad reply: ") + e.what());
+        return -1;
+    }
+    return out.size() == blocks.size() ? 0 : -1;
+}
+
+// ---------------------------------------------------------------- data plane
+
+Connection::DevCtx* Connection::dev_ctx(int device) {
+    auto it = devs_.find(device);
+    if (it != devs_.end()) return it->second.get();
+    if (device < 0 || device >= fabric::cuda_device_count()) {
+        fail("no such CUDA device: " + std::to_string(device));
+        return nullptr;
+    }
+    DeviceGuard g(device);
+    auto ctx = std::make_unique<DevCtx>();
+    ctx->device = device;
+    void* dp = nullptr;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc(reinterpret_cast<void**>(&ctx->ring_h), kRingBytes,
+                      cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+        cudaHostGetDevicePointer(&dp, ctx->ring_h, 0) != cudaSuccess) {
+        fail(std::string("device context: ") + cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    ctx->ring_d = static_cast<uint8_t*>(dp);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->status_h), 256,
+                      cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+        cudaHostGetDevicePointer(&dp, ctx->status_h, 0) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&ctx->scratch), kScratchBytes) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&ctx->zeros), kZeroBytes) != cudaSuccess ||
+        cudaMemset(ctx->zeros, 0, kZeroBytes) != cudaSuccess) {
+        fail(std::string("device context: ") + cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    ctx->status_d = static_cast<uint32_t*>(dp);
+    std::memset(ctx->status_h, 0, 256);
+    if (default_device_ < 0) default_device_ = device;
+    DevCtx* raw = ctx.get();
+    devs_[device] = std::move(ctx);
+    return raw;
+}
+
+std::shared_ptr<fabric::Mapping> Connection::mapping(uint32_t seg, int device) {
+    if (seg >= segs_.size() && refresh_pool_map() != 0) return nullptr;
+    if (seg >= segs_.size()) {
+        fail("server referenced unknown pool segment " + std::to_string(seg));
+        return nullptr;
+    }
+    if (device >= 0) {
+        DevCtx* ctx = dev_ctx(device);
+        if (!ctx) return nullptr;
+        if (ctx->maps.size() <= seg) ctx->maps.resize(seg + 1);
+        if (!ctx->maps[seg]) {
+            std::string err;
+            ctx->maps[seg] = fabric::map_segment(segs_[seg], device, &err);
+            if (!ctx->maps[seg]) fail("cannot map pool segment: " + err);
+        }
+        return ctx->maps[seg];
+    }
+    // host-only mapping (CPU tensors against a host pool)
+    if (host_maps_.size() <= seg) host_maps_.resize(seg + 1);
+    if (!host_maps_[seg]) {
+        std::string err;
+        host_maps_[seg] = fabric::map_segment(segs_[seg], -1, &err);
+        if (!host_maps_[seg]) fail("cannot map pool segment: " + err);
+    }
+    return host_maps_[seg];
+}
+
+int Connection::ensure_host_registered(uint64_t ptr, size_t bytes, int device) {
+    auto it = host_regs_.upper_bound(ptr);
+    if (it != host_regs_.begin()) {
+        --it;
+        if (ptr >= it->first && ptr + bytes <= it->first + it->second.bytes &&
+            it->second.registered)
+            return 0;
+    }
+    DeviceGuard g(device);
+    const cudaError_t e = cudaHostRegister(reinterpret_cast<void*>(ptr), bytes,
+                                           cudaHostRegisterMapped | cudaHostRegisterPortable);
+    if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered) {
+        (void)cudaGetLastError();
+        return -1;
+    }
+    (void)cudaGetLastError();
+    host_regs_[ptr] = HostReg{bytes, e == cudaSuccess};
+    return 0;
+}
+
+int Connection::register_mr(uint64_t ptr, size_t size, int device) {
+    std::lock_guard<std::mutex> lk(mu_);
+    mrs_[ptr] = size;  // re-registering the same base replaces the old entry
+    if (device < 0 && fabric::cuda_available() && server_hbm_) {
+        // Pin + map host memory so that kernels can stream it over PCIe (the role
+        // ibv_reg_mr plays for CPU tensors in the reference).
+        const int kd = cfg_.device >= 0 ? cfg_.device : std::max(default_device_, 0);
+        if (ensure_host_registered(ptr, size, kd) != 0)
+            LOG_WARN("register_mr: could not pin host memory, falling back to staged copies");
+    }
+    if (device >= 0 && !dev_ctx(device)) return -1;
+    return 1;
+}
+
+// Move n blocks between the caller's tensor and the pool.
+int Connection::move_blocks(bool write, const uint64_t* local_off, const RemoteBlock* blocks,
+                            size_t n, int block_size, uint64_t base_ptr, int device,
+                            uint64_t stream_in) {
+    std::lock_guard<std::mutex> lk(mu_);
+    // --- classify
+    bool all_host_segs = true;
+    size_t live = 0;
+    uint64_t max_off = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (write && is_fake_block(blocks[i])) continue;  // dedup: first writer wins
+        const uint32_t seg = addr_seg(blocks[i].remote_addr);
+        if (seg >= segs_.size() && refresh_pool_map() != 0) return -1;
+        if (seg >= segs_.size()) {
+            fail("block refers to unknown segment");
+            return -1;
+        }
+        if (segs_[seg].kind != kSegHostShm) all_host_segs = false;
+        max_off = std::max(max_off, local_off[i]);
+        ++live;
+    }
+    if (live == 0) return 0;
+
+    // --- pure host path: CPU tensor <-> host pool
+    if (device < 0 && all_host_segs) {
+        for (size_t i = 0; i < n; ++i) {
+            if (write && is_fake_block(blocks[i])) continue;
+            auto m = mapping(addr_seg(blocks[i].remote_addr), -1);
+            if (!m || !m->host_ptr) return -1;
+            uint8_t* pool = m->host_ptr + addr_off(blocks[i].remote_addr);
+            uint8_t* local = reinterpret_cast<uint8_t*>(base_ptr + local_off[i]);
+            if (write)
+                std::memcpy(pool, local, size_t(block_size));
+            else
+                std::memcpy(local, pool, size_t(block_size));
+            if (write) pending_commit_.push_back(blocks[i].remote_addr);
+            stats_.host_copies++;
+        }
+        (write ? stats_.bytes_written : stats_.bytes_read) += live * uint64_t(block_size);
+        return 0;
+    }
+
+    // --- kernel path on `kd`
+    if (!fabric::cuda_available()) {
+        fail("a CUDA device is required to reach an HBM pool");
+        return -1;
+    }
+    int kd = device;
+    if (kd < 0) {
+        kd = cfg_.device >= 0 ? cfg_.device : std::max(default_device_, 0);
+        // make the host tensor addressable by the kernel
+        auto mr = mrs_.find(base_ptr);
+        const size_t span = mr != mrs_.end() ? mr->second : size_t(max_off) + size_t(block_size);
+        if (ensure_host_registered(base_ptr, span, kd) != 0) {
+            fail("cannot pin the host tensor for the GPU data path");
+            return -1;
+        }
+    }
+    DevCtx* ctx = dev_ctx(kd);
+    if (!ctx) return -1;
+    DeviceGuard g(kd);
+    cudaStream_t stream = stream_in ? reinterpret_cast<cudaStream_t>(stream_in) : ctx->stream;
+
+    size_t i = 0;
+    while (i < n) {
+        // gather up to kMaxBatch live blocks
+        const size_t batch_cap = std::min(kMaxBatch, n - i);
+        const size_t at_desc = ctx->ring_alloc(batch_cap * sizeof(kernels::CopyDesc));
+        auto* descs = reinterpret_cast<kernels::CopyDesc*>(ctx->ring_h + at_desc);
+        const bool publish = write;
+        size_t at_rec = 0;
+        kernels::IndexEntry* recs = nullptr;
+        if (publish) {
+            at_rec = ctx->ring_alloc(batch_cap * sizeof(kernels::IndexEntry));
+            recs = reinterpret_cast<kernels::IndexEntry*>(ctx->ring_h + at_rec);
+        }
+        uint32_t m = 0;
+        bool can_publish = publish;
+        const fabric::Mapping* index_map = nullptr;
+        for (; i < n && m < batch_cap; ++i) {
+            if (write && is_fake_block(blocks[i])) continue;
+            const uint32_t seg = addr_seg(blocks[i].remote_addr);
+            auto mp = mapping(seg, kd);
+            if (!mp || !mp->dev_ptr) {
+                fail("pool segment is not addressable from device " + std::to_string(kd));
+                return -1;
+            }
+            const uint64_t pool = reinterpret_cast<uint64_t>(mp->dev_ptr) +
+                                  addr_off(blocks[i].remote_addr);
+            const uint64_t local = base_ptr + local_off[i];
+            descs[m] = write ? kernels::CopyDesc{local, pool} : kernels::CopyDesc{pool, local};
+            if (publish) {
+                auto h = pending_hash_.find(blocks[i].remote_addr);
+                if (h == pending_hash_.end()) {
+                    can_publish = false;
+                } else {
+                    recs[m] = kernels::IndexEntry{h->second.h1, h->second.h2,
+                                                  blocks[i].remote_addr, blocks[i].gen,
+                                                  uint32_t(block_size)};
+                    pending_hash_.erase(h);
+                }
+                pending_commit_.push_back(blocks[i].remote_addr);
+            }
+            ++m;
+        }
+        if (m == 0) break;
+        kernels::CopyLaunch L;
+        L.descs = reinterpret_cast<const kernels::CopyDesc*>(ctx->ring_d + at_desc);
+        L.n = m;
+        L.bytes = uint32_t(block_size);
+        L.status = ctx->status_d;
+        L.variant = copy_variant_;
+        L.max_ctas = max_ctas_;
+        if (can_publish) {
+            // the device index lives in segment 0
+            auto m0 = mapping(0, kd);
+            if (m0 && m0->dev_ptr && m0->info.index_slots) {
+                index_map = m0.get();
+                L.recs = reinterpret_cast<const kernels::IndexEntry*>(ctx->ring_d + at_rec);
+                L.table = reinterpret_cast<kernels::IndexEntry*>(index_map->dev_ptr +
+                                                                 index_map->info.index_off);
+                L.table_mask = index_map->info.index_slots - 1;
+                L.done = reinterpret_cast<uint32_t*>(ctx->zeros + ctx->zeros_alloc(m * 4));
+            }
+        }
+        const cudaError_t e = kernels::launch_kv_copy(L, stream);
+        if (e != cudaSuccess) {
+            fail(std::string("kv_copy launch failed: ") + cudaGetErrorString(e));
+            return -1;
+        }
+        ctx->mark(stream);
+        stats_.kernel_launches++;
+        (write ? stats_.bytes_written : stats_.bytes_read) += uint64_t(m) * uint64_t(block_size);
+    }
+    return 0;
+}
+
+int Connection::w_rdma(const std::vector<uint64_t>& offsets, int block_size,
+                       const RemoteBlock* blocks, size_t nblocks, uint64_t base_ptr, int device,
+                       uint64_t stream) {
+    if (offsets.size() != nblocks) {
+        fail("w_rdma: offsets and remote blocks differ in length");
+        return -1;
+    }
+    {
+        // C10: the tensor must be the one that was registered (lookup by base pointer)
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!mrs_.count(base_ptr)) LOG_DEBUG("w_rdma on an unregistered base pointer");
+    }
+    return move_blocks(true, offsets.data(), blocks, nblocks, block_size, base_ptr, device, stream);
+}
+
+int Connection::r_rdma(const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr,
+                       int device, uint64_t stream) {
+    if (blocks.empty()) return 0;
+    if (device_lookup_ && server_hbm_ && device >= 0)
+        return read_via_device_index(blocks, block_size, base_ptr, device, stream);
+    std::vector<RemoteBlock> rb;
+    const int r = lookup_blocks(kOpReadLookup, blocks, block_size, rb);
+    if (r != 0) return r;
+    std::vector<uint64_t> offs(blocks.size());
+    for (size_t i = 0; i < blocks.size(); ++i) offs[i] = blocks[i].offset;
+    return move_blocks(false, offs.data(), rb.data(), rb.size(), block_size, base_ptr, device,
+                       stream);
+}
+
+int Connection::rw_local(char op, const std::vector<KeyOffset>& blocks, int block_size,
+                         uint64_t base_ptr, int device, uint64_t stream) {
+    if (blocks.empty()) return 0;
+    if (op != kOpLocalRead && op != kOpLocalWrite) return -1;
+    if (op == kOpLocalRead && device_lookup_ && server_hbm_ && device >= 0)
+        return read_via_device_index(blocks, block_size, base_ptr, device, stream);
+    std::vector<RemoteBlock> rb;
+    const int r = lookup_blocks(op, blocks, block_size, rb);
+    if (r != 0) return r;
+    if (op == kOpLocalWrite && server_hbm_) {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (size_t i = 0; i < blocks.size(); ++i) {
+            if (is_fake_block(rb[i])) continue;
+            pending_hash_[rb[i].remote_addr] = hash_key(
+                reinterpret_cast<const uint8_t*>(blocks[i].key.data()), blocks[i].key.size());
+        }
+    }
+    std::vector<uint64_t> offs(blocks.size());
+    for (size_t i = 0; i < blocks.size(); ++i) offs[i] = blocks[i].offset;
+    return move_blocks(op == kOpLocalWrite, offs.data(), rb.data(), rb.size(), block_size,
+                       base_ptr, device, stream);
+}
+
+// Pack keys into the pinned ring so that the lookup kernel can hash them: each key starts
+// on an 8-byte boundary and is zero padded to a multiple of 8.
+static size_t pack_keys(const std::string* const* keys, size_t n, uint8_t* bytes, uint32_t* off,
+                        uint32_t* len) {
+    size_t at = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const std::string& k = *keys[i];
+        off[i] = uint32_t(at);
+        len[i] = uint32_t(k.size());
+        const size_t padded = align_up(k.size() ? k.size() : 1, 8);
+        std::memcpy(bytes + at, k.data(), k.size());
+        std::memset(bytes + at + k.size(), 0, padded - k.size());
+        at += padded;
+    }
+    return at;
+}
+
+int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int block_size,
+                                      uint64_t base_ptr, int device, uint64_t stream_in) {
+    std::lock_guard<std::mutex> lk(mu_);
+    DevCtx* ctx = dev_ctx(device);
+    if (!ctx) return -1;
+    auto m0 = mapping(0, device);
+    if (!m0 || !m0->dev_ptr || !m0->info.index_slots) {
+        fail("the server exposes no device index");
+        return -1;
+    }
+    DeviceGuard g(device);
+    cudaStream_t stream = stream_in ? reinterpret_cast<cudaStream_t>(stream_in) : ctx->stream;
+    for (size_t base = 0; base < blocks.size(); base += kMaxBatch) {
+        const size_t n = std::min(kMaxBatch, blocks.size() - base);
+        size_t key_bytes = 0;
+        std::vector<const std::string*> kp(n);
+        for (size_t i = 0; i < n; ++i) {
+            kp[i] = &blocks[base + i].key;
+            key_bytes += align_up(std::max<size_t>(kp[i]->size(), 1), 8);
+        }
+        const size_t at_bytes = ctx->ring_alloc(key_bytes);
+        const size_t at_off = ctx->ring_alloc(n * 4);
+        const size_t at_len = ctx->ring_alloc(n * 4);
+        const size_t at_dst = ctx->ring_alloc(n * 8);
+        pack_keys(kp.data(), n, ctx->ring_h + at_bytes,
+                  reinterpret_cast<uint32_t*>(ctx->ring_h + at_off),
+                  reinterpret_cast<uint32_t*>(ctx->ring_h + at_len));
+        auto* dst = reinterpret_cast<uint64_t*>(ctx->ring_h + at_dst);
+        for (size_t i = 0; i < n; ++i) dst[i] = blocks[base + i].offset;
+
+        kernels::LookupLaunch Q;
+        Q.key_bytes = ctx->ring_d + at_bytes;
+        Q.key_off = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_off);
+        Q.key_len = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_len);
+        Q.n = uint32_t(n);
+        Q.table = reinterpret_cast<const kernels::IndexEntry*>(m0->dev_ptr + m0->info.index_off);
+        Q.table_mask = m0->info.index_slots - 1;
+        Q.nsegs = uint32_t(std::min<size_t>(segs_.size(), kernels::LookupLaunch::kMaxSegs));
+        for (uint32_t s = 0; s < Q.nsegs; ++s) {
+            auto mp = mapping(s, device);
+            Q.seg_base[s] = mp && mp->dev_ptr ? reinterpret_cast<uint64_t>(mp->dev_ptr) : 0;
+        }
+        auto* out = reinterpret_cast<kernels::CopyDesc*>(
+            ctx->scratch + ctx->scratch_alloc(n * sizeof(kernels::CopyDesc)));
+        Q.out_descs = out;
+        Q.dst_off = reinterpret_cast<const uint64_t*>(ctx->ring_d + at_dst);
+        Q.dst_base = base_ptr;
+        Q.need_bytes = uint32_t(block_size);
+        Q.status = ctx->status_d;
+        cudaError_t e = kernels::launch_index_lookup(Q, stream);
+        if (e == cudaSuccess) {
+            kernels::CopyLaunch L;
+            L.descs = out;
+            L.n = uint32_t(n);
+            L.bytes = uint32_t(block_size);
+            L.status = ctx->status_d;
+            L.variant = copy_variant_;
+            L.max_ctas = max_ctas_;
+            e = kernels::launch_kv_copy(L, stream);
+        }
+        if (e != cudaSuccess) {
+            fail(std::string("device-index read failed to launch: ") + cudaGetErrorString(e));
+            return -1;
+        }
+        ctx->mark(stream);
+        stats_.kernel_launches += 2;
+        stats_.bytes_read += uint64_t(n) * uint64_t(block_size);
+    }
+    return 0;
+}
+
+int Connection::match_via_device_index(const std::vector<std::string>& keys, bool exist_only) {
+    std::lock_guard<std::mutex> lk(mu_);
+    const int device = cfg_.device >= 0 ? cfg_.device : std::max(default_device_, 0);
+    DevCtx* ctx = dev_ctx(device);
+    if (!ctx) return -3;
+    auto m0 = mapping(0, device);
+    if (!m0 || !m0->dev_ptr || !m0->info.index_slots) return -3;
+    const size_t n = keys.size();
+    size_t key_bytes = 0;
+    std::vector<const std::string*> kp(n);
+    for (size_t i = 0; i < n; ++i) {
+        kp[i] = &keys[i];
+        key_bytes += align_up(std::max<size_t>(keys[i].size(), 1), 8);
+    }
+    if (key_bytes + n * 8 + 4096 > kRingBytes / 2) return -3;  // too large: use the control plane
+    DeviceGuard g(device);
+    const size_t at_bytes = ctx->ring_alloc(key_bytes);
+    const size_t at_off = ctx->ring_alloc(n * 4);
+    const size_t at_len = ctx->ring_alloc(n * 4);
+    pack_keys(kp.data(), n, ctx->ring_h + at_bytes,
+              reinterpret_cast<uint32_t*>(ctx->ring_h + at_off),
+              reinterpret_cast<uint32_t*>(ctx->ring_h + at_len));
+    kernels::LookupLaunch Q;
+    Q.key_bytes = ctx->ring_d + at_bytes;
+    Q.key_off = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_off);
+    Q.key_len = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_len);
+    Q.n = uint32_t(n);
+    Q.table = reinterpret_cast<const kernels::IndexEntry*>(m0->dev_ptr + m0->info.index_off);
+    Q.table_mask = m0->info.index_slots - 1;
+    const size_t words = (n + 31) / 32;
+    Q.present = reinterpret_cast<uint32_t*>(ctx->scratch + ctx->scratch_alloc(words * 4));
+    Q.ticket = reinterpret_cast<uint32_t*>(ctx->zeros + ctx->zeros_alloc(4));
+    Q.status = ctx->status_d;
+    Q.want_match = true;
+    // The launch is ordered after this connection's writes on the same stream, so keys
+    // written just before (even without sync) are visible, as in the reference.
+    cudaStream_t stream = ctx->stream;
+    cudaMemsetAsync(Q.present, 0, words * 4, stream);
+    const cudaError_t e = kernels::launch_index_lookup(Q, stream);
+    if (e != cudaSuccess) {
+        fail(std::string("match kernel failed to launch: ") + cudaGetErrorString(e));
+        return -3;
+    }
+    stats_.kernel_launches++;
+    // external streams may hold this connection's writes: wait for them too
+    ctx->mark(stream);
+    ctx->wait_all();
+    const int32_t result = int32_t(ctx->status_h[kernels::kStatMatch]);
+    (void)exist_only;
+    return result;
+}
+
+int Connection::drain_devices() {
+    std::lock_guard<std::mutex> lk(mu_);
+    int rc = 0;
+    for (auto& kv : devs_) {
+        DevCtx& ctx = *kv.second;
+        if (!ctx.dirty) continue;
+        ctx.wait_all();
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            fail(std::string("device error during transfer: ") + cudaGetErrorString(e));
+            rc = -1;
+        }
+        if (ctx.status_h[kernels::kStatMiss]) {
+            fail("read: " + std::to_string(ctx.status_h[kernels::kStatMiss]) +
+                 " key(s) not found in the device index");
+            ctx.status_h[kernels::kStatMiss] = 0;
+            rc = -kKeyNotFound;
+        }
+        if (ctx.status_h[kernels::kStatPublishFail]) {
+            LOG_WARN("device index is full: %u block(s) are only reachable through the server",
+                     ctx.status_h[kernels::kStatPublishFail]);
+            ctx.status_h[kernels::kStatPublishFail] = 0;
+        }
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------- async API
+
+void Connection::post(Task&& t) {
+    {
+        std::lock_guard<std::mutex> lk(q_mu_);
+        queue_.push_back(std::move(t));
+        ++inflight_async_;
+    }
+    q_cv_.notify_one();
+}
+
+void Connection::worker() {
+    for (;;) {
+        Task t;
+        {
+            std::unique_lock<std::mutex> lk(q_mu_);
+            q_cv_.wait(lk, [this] { return !queue_.empty(); });
+            t = std::move(queue_.front());
+            queue_.pop_front();
+        }
+        if (t.kind == Task::kStop) return;
+        if (t.kind == Task::kAllocate) {
+            std::vector<RemoteBlock> out;
+            if (allocate(t.keys, t.block_size, out) != 0) out.clear();
+            if (t.alloc_cb) t.alloc_cb(std::move(out));
+        } else {
+            int status = t.status;
+            if (t.event) {
+                DeviceGuard g(t.device);
+                if (cudaEventSynchronize(t.event) != cudaSuccess) status = -1;
+                cudaEventDestroy(t.event);
+            }
+            if (status == 0 && t.commit && flush_commits() != 0) status = -1;
+            if (t.done_cb) t.done_cb(status);
+        }
+        {
+            std::lock_guard<std::mutex> lk(q_mu_);
+            --inflight_async_;
+        }
+        idle_cv_.notify_all();
+    }
+}
+
+int Connection::allocate_async(const std::vector<std::string>& keys, int block_size,
+                               std::function<void(std::vector<RemoteBlock>)> cb) {
+    Task t;
+    t.kind = Task::kAllocate;
+    t.keys = keys;
+    t.block_size = block_size;
+    t.alloc_cb = std::move(cb);
+    post(std::move(t));
+    return 0;
+}
+
+int Connection::w_rdma_async(const std::vector<uint64_t>& offsets, int block_size,
+                             const RemoteBlock* blocks, size_t nblocks, uint64_t base_ptr,
+                             int device, uint64_t stream, std::function<void(int)> cb) {
+    const int r = w_rdma(offsets, block_size, blocks, nblocks, base_ptr, device, stream);
+    Task t;
+    t.kind = Task::kWaitEvent;
+    t.status = r;
+    t.commit = true;
+    t.done_cb = std::move(cb);
+    const int kd = device >= 0 ? device : (cfg_.device >= 0 ? cfg_.device : default_device_);
+    if (r == 0 && kd >= 0 && fabric::cuda_available()) {
+        std::lock_guard<std::mutex> lk(mu_);
+        auto it = devs_.find(kd);
+        if (it != devs_.end() && it->second->dirty) {
+            DeviceGuard g(kd);
+            cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : it->second->stream;
+            cudaEventCreateWithFlags(&t.event, cudaEventDisableTiming);
+            cudaEventRecord(t.event, s);
+            t.device = kd;
+        }
+    }
+    post(std::move(t));
+    return r;
+}
+
+int Connection::r_rdma_async(const std::vector<KeyOffset>& blocks, int block_size,
+                             uint64_t base_ptr, int device, uint64_t stream,
+                             std::function<void(int)> cb) {
+    const int r = r_rdma(blocks, block_size, base_ptr, device, stream);
+    Task t;
+    t.kind = Task::kWaitEvent;
+    t.status = r;
+    t.done_cb = std::move(cb);
+    const int kd = device >= 0 ? device : (cfg_.device >= 0 ? cfg_.device : default_device_);
+    if (r == 0 && kd >= 0 && fabric::cuda_available()) {
+        std::lock_guard<std::mutex> lk(mu_);
+        auto it = devs_.find(kd);
+        if (it != devs_.end() && it->second->dirty) {
+            DeviceGuard g(kd);
+            cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : it->second->stream;
+            cudaEventCreateWithFlags(&t.event, cudaEventDisableTiming);
+            cudaEventRecord(t.event, s);
+            t.device = kd;
+        }
+    }
+    post(std::move(t));
+    return r;
+}
+
+}  // namespace istore

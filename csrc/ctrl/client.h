@@ -1,0 +1,160 @@
+// Client connection: blocking control-plane socket + client-driven data plane.
+//
+// Capability parity with the reference's `Connection` (src/libinfinistore.h:34-122):
+// init_connection, the fabric set-up that replaces setup_rdma, register_mr,
+// allocate[_async], w_rdma[_async], r_rdma[_async], rw_local, sync_local, sync_rdma,
+// check_exist, get_match_last_index.
+//
+// The data plane is redesigned for an NVSwitch box: instead of posting RDMA work requests
+// to a NIC (reference: src/libinfinistore.cpp:860-1099) the client maps the server's HBM
+// pool segments into its own address space and launches sm_100a kernels on ITS GPU that
+// move a whole batch of pages with peer loads/stores over NVLink and publish the commit
+// in-band (kernels/kv_copy.cu).  The server CPU only allocates and indexes.
+#pragma once
+
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../core/config.h"
+#include "../core/hash.h"
+#include "../fabric/segment.h"
+#include "../wire/protocol.h"
+
+namespace istore {
+
+struct KeyOffset {
+    std::string key;
+    uint64_t offset;  // bytes from the tensor base
+};
+
+struct ClientStats {
+    uint64_t kernel_launches = 0;   // data-plane kernels launched by this connection
+    uint64_t bytes_written = 0;
+    uint64_t bytes_read = 0;
+    uint64_t ctrl_requests = 0;
+    uint64_t host_copies = 0;       // blocks moved with memcpy (CPU tensors / host pool)
+};
+
+class Connection {
+   public:
+    Connection();
+    ~Connection();
+    Connection(const Connection&) = delete;
+    Connection& operator=(const Connection&) = delete;
+
+    // --- connection management
+    int init_connection(const ClientConfig& cfg);  // TCP connect + 'E' exchange
+    int setup_rdma(const ClientConfig& cfg);       // fetch the pool map (fabric set-up)
+    void close();
+    bool connected() const { return fd_ >= 0; }
+    bool server_has_hbm() const { return server_hbm_; }
+
+    // --- metadata
+    int check_exist(const std::string& key);  // 0 = exists & committed, 1 = not, <0 error
+    int get_match_last_index(const std::vector<std::string>& keys);  // index, -1 none, <-1 error
+    int sync_local();  // remaining server-side tasks (always 0 here) or <0
+    int sync_rdma();   // drain kernels + async ops, commit, control-plane barrier
+
+    // --- data plane.  `device` is the CUDA ordinal owning base_ptr, -1 for host memory;
+    //     `stream` is a cudaStream_t to order after (0 = the connection's own stream).
+    int register_mr(uint64_t ptr, size_t size, int device);
+    int allocate(const std::vector<std::string>& keys, int block_size,
+                 std::vector<RemoteBlock>& out);
+    int w_rdma(const std::vector<uint64_t>& offsets, int block_size, const RemoteBlock* blocks,
+               size_t nblocks, uint64_t base_ptr, int device, uint64_t stream);
+    int r_rdma(const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr, int device,
+               uint64_t stream);
+    int rw_local(char op, const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr,
+                 int device, uint64_t stream);
+
+    // --- async flavours: the callback runs on the connection's completion thread
+    int allocate_async(const std::vector<std::string>& keys, int block_size,
+                       std::function<void(std::vector<RemoteBlock>)> cb);
+    int w_rdma_async(const std::vector<uint64_t>& offsets, int block_size,
+                     const RemoteBlock* blocks, size_t nblocks, uint64_t base_ptr, int device,
+                     uint64_t stream, std::function<void(int)> cb);
+    int r_rdma_async(const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr,
+                     int device, uint64_t stream, std::function<void(int)> cb);
+
+    // --- tuning / introspection
+    void set_copy_variant(int v) { copy_variant_ = v; }
+    void set_max_ctas(int n) { max_ctas_ = n; }
+    void set_device_lookup(bool on) { device_lookup_ = on; }
+    bool device_lookup() const { return device_lookup_; }
+    ClientStats stats() const;
+    std::vector<SegmentInfo> segments() const { return segs_; }
+    const std::string& last_error() const { return last_error_; }
+
+   private:
+    struct DevCtx;
+    struct Task;
+
+    // control plane
+    int transact(char op, const void* body, size_t len, int32_t* code,
+                 std::vector<uint8_t>* payload, size_t fixed_payload);
+    int send_only(char op, const void* body, size_t len);
+    int refresh_pool_map();
+    int lookup_blocks(char op, const std::vector<KeyOffset>& blocks, int block_size,
+                      std::vector<RemoteBlock>& out);
+    int flush_commits();
+
+    // data plane
+    DevCtx* dev_ctx(int device);
+    std::shared_ptr<fabric::Mapping> mapping(uint32_t seg, int device);
+    int move_blocks(bool write, const uint64_t* local_off, const RemoteBlock* blocks, size_t n,
+                    int block_size, uint64_t base_ptr, int device, uint64_t stream);
+    int read_via_device_index(const std::vector<KeyOffset>& blocks, int block_size,
+                              uint64_t base_ptr, int device, uint64_t stream);
+    int match_via_device_index(const std::vector<std::string>& keys, bool exist_only);
+    int ensure_host_registered(uint64_t ptr, size_t bytes, int device);
+    int drain_devices();
+    void fail(const std::string& msg);
+
+    // completion thread
+    void worker();
+    void post(Task&& t);
+
+    ClientConfig cfg_;
+    int fd_ = -1;
+    std::mutex sock_mu_;  // one request/response transaction at a time
+    bool server_cuda_ = false;
+    bool server_hbm_ = false;
+    uint8_t server_uuid_[16] = {0};
+    std::vector<SegmentInfo> segs_;
+
+    std::mutex mu_;  // guards the data-plane state below
+    std::map<int, std::unique_ptr<DevCtx>> devs_;
+    std::vector<std::shared_ptr<fabric::Mapping>> host_maps_;  // CPU view of host segments
+    std::unordered_map<uint64_t, KeyHash> pending_hash_;  // allocated addr -> key fingerprint
+    std::vector<uint64_t> pending_commit_;
+    struct HostReg {
+        size_t bytes;
+        bool registered;
+    };
+    std::map<uint64_t, HostReg> host_regs_;  // register_mr'ed host ranges by base pointer
+    std::map<uint64_t, size_t> mrs_;         // registered regions by base pointer (C10)
+    int copy_variant_ = 0;
+    int max_ctas_ = 0;
+    bool device_lookup_ = false;
+    int default_device_ = -1;
+    ClientStats stats_;
+    std::string last_error_;
+
+    std::thread worker_;
+    std::mutex q_mu_;
+    std::condition_variable q_cv_, idle_cv_;
+    std::deque<Task> queue_;
+    size_t inflight_async_ = 0;
+    bool stop_ = false;
+};
+
+}  // namespace istore

@@ -1,0 +1,611 @@
+#include "server.h"
+
+#include <arpa/inet.h>
+#include <fcntl.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <sys/epoll.h>
+#include <sys/eventfd.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+#include <cerrno>
+#include <chrono>
+#include <cstring>
+
+#include "../core/log.h"
+#include "../wire/messages.h"
+
+namespace istore {
+
+struct Server::Conn {
+    int fd = -1;
+    uint64_t id = 0;
+    enum State { kHeader, kBody } state = kHeader;
+    uint8_t hdr_buf[sizeof(Header)];
+    size_t hdr_got = 0;
+    Header hdr{};
+    std::vector<uint8_t> body;
+    size_t body_got = 0;
+    std::vector<uint8_t> out;
+    size_t out_off = 0;
+    bool want_write = false;
+    bool closing = false;  // flush pending output, then close
+    ConnInfo peer{};
+    std::vector<BlockPtr> leases;  // blocks pinned for this client's in-flight reads
+    std::string addr;
+};
+
+namespace {
+bool set_nonblock(int fd) {
+    const int fl = fcntl(fd, F_GETFL, 0);
+    return fl >= 0 && fcntl(fd, F_SETFL, fl | O_NONBLOCK) == 0;
+}
+size_t next_pow2(size_t v) {
+    size_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+}  // namespace
+
+Server::Server(const ServerConfig& cfg) : cfg_(cfg) {
+    store_ = std::make_unique<KVStore>(&mm_);
+    scratch_.resize(64 << 10);
+}
+
+Server::~Server() { stop(); }
+
+bool Server::add_segment(std::string* err) {
+    const uint32_t id = uint32_t(segs_.size());
+    const bool first_round = id < std::max<size_t>(1, cfg_.pool_devices.size());
+    size_t bytes = cfg_.prealloc_bytes ? cfg_.prealloc_bytes
+                                       : (first_round ? cfg_.prealloc_size : cfg_.extend_size) << 30;
+    const uint32_t granule = uint32_t(cfg_.minimal_allocate_size) * 1024u;
+    bytes = bytes / granule * granule;
+    if (bytes == 0) {
+        if (err) *err = "pool size is smaller than one allocation granule";
+        return false;
+    }
+    std::unique_ptr<fabric::SegmentOwner> seg;
+    int device = -1;
+    if (use_hbm_) {
+        device = cfg_.pool_devices.empty()
+                     ? 0
+                     : cfg_.pool_devices[next_pool_dev_++ % cfg_.pool_devices.size()];
+        size_t slots = cfg_.index_slots ? next_pow2(cfg_.index_slots)
+                                        : next_pow2(std::max<size_t>(1024, 2 * (bytes / granule)));
+        seg = fabric::SegmentOwner::create_device(id, device, bytes, granule, slots, err);
+    } else {
+        seg = fabric::SegmentOwner::create_host(id, bytes, granule, port_, err);
+    }
+    if (!seg) return false;
+    mm_.add_pool(bytes, granule, device);
+    LOG_INFO("pool segment %u: %s, %.2f GiB, granule %u KiB, device %d", id,
+             use_hbm_ ? "HBM" : "host shm", double(bytes) / double(1ull << 30), granule / 1024,
+             device);
+    segs_.push_back(std::move(seg));
+    return true;
+}
+
+bool Server::maybe_extend() {
+    if (!cfg_.auto_increase) return false;
+    std::string err;
+    // Done inline on the reactor thread: creating a segment is an allocation, not a
+    // multi-second pin+register as in the reference, and it keeps the pool vector
+    // single-threaded (the reference mutates it from a worker thread).
+    if (!add_segment(&err)) {
+        LOG_WARN("pool auto-increase failed: %s", err.c_str());
+        return false;
+    }
+    LOG_INFO("pool extended to %zu segments", segs_.size());
+    return true;
+}
+
+int Server::start(std::string* err) {
+    if (running_.load()) return 0;
+    port_ = cfg_.service_port;
+    if (cfg_.pool_backend == "hbm")
+        use_hbm_ = true;
+    else if (cfg_.pool_backend == "host")
+        use_hbm_ = false;
+    else
+        use_hbm_ = fabric::cuda_available();
+    if (use_hbm_ && !fabric::cuda_available()) {
+        if (err) *err = "pool backend 'hbm' requested but no CUDA device is usable";
+        return -1;
+    }
+
+    listen_fd_ = socket(AF_INET, SOCK_STREAM | SOCK_CLOEXEC, 0);
+    if (listen_fd_ < 0) {
+        if (err) *err = std::string("socket: ") + std::strerror(errno);
+        return -1;
+    }
+    int one = 1;
+    setsockopt(listen_fd_, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+    sockaddr_in sa{};
+    sa.sin_family = AF_INET;
+    sa.sin_port = htons(uint16_t(cfg_.service_port));
+    const std::string host = cfg_.host.empty() ? "0.0.0.0" : cfg_.host;
+    if (inet_pton(AF_INET, host == "localhost" ? "127.0.0.1" : host.c_str(), &sa.sin_addr) != 1) {
+        if (err) *err = "invalid listen address: " + host;
+        close(listen_fd_);
+        listen_fd_ = -1;
+        return -1;
+    }
+    if (bind(listen_fd_, reinterpret_cast<sockaddr*>(&sa), sizeof(sa)) != 0 ||
+        listen(listen_fd_, 128) != 0) {
+        if (err)
+            *err = "bind/listen on " + host + ":" + std::to_string(cfg_.service_port) + ": " +
+                   std::strerror(errno);
+        close(listen_fd_);
+        listen_fd_ = -1;
+        return -1;
+    }
+    if (cfg_.service_port == 0) {  // ephemeral port (tests)
+        socklen_t sl = sizeof(sa);
+        getsockname(listen_fd_, reinterpret_cast<sockaddr*>(&sa), &sl);
+        port_ = ntohs(sa.sin_port);
+    }
+    set_nonblock(listen_fd_);
+
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        const size_t initial = std::max<size_t>(1, use_hbm_ ? cfg_.pool_devices.size() : 1);
+        for (size_t i = 0; i < initial; ++i) {
+            if (!add_segment(err)) {
+                close(listen_fd_);
+                listen_fd_ = -1;
+                segs_.clear();
+                return -1;
+            }
+        }
+    }
+
+    epoll_fd_ = epoll_create1(EPOLL_CLOEXEC);
+    wake_fd_ = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);
+    epoll_event ev{};
+    ev.events = EPOLLIN;
+    ev.data.fd = listen_fd_;
+    epoll_ctl(epoll_fd_, EPOLL_CTL_ADD, listen_fd_, &ev);
+    ev.data.fd = wake_fd_;
+    epoll_ctl(epoll_fd_, EPOLL_CTL_ADD, wake_fd_, &ev);
+
+    stop_.store(false);
+    running_.store(true);
+    thread_ = std::thread([this] { loop(); });
+    LOG_INFO("control plane listening on %s:%d (%s pool)", host.c_str(), port_,
+             use_hbm_ ? "HBM" : "host");
+    return 0;
+}
+
+void Server::stop() {
+    if (!running_.exchange(false)) return;
+    stop_.store(true);
+    uint64_t one = 1;
+    (void)!write(wake_fd_, &one, sizeof(one));
+    if (thread_.joinable()) thread_.join();
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto& kv : conns_) close(kv.second->fd);
+    conns_.clear();
+    if (listen_fd_ >= 0) close(listen_fd_);
+    if (epoll_fd_ >= 0) close(epoll_fd_);
+    if (wake_fd_ >= 0) close(wake_fd_);
+    listen_fd_ = epoll_fd_ = wake_fd_ = -1;
+    store_->purge();
+    segs_.clear();
+}
+
+size_t Server::kvmap_len() {
+    std::lock_guard<std::mutex> lk(mu_);
+    return store_->size();
+}
+
+size_t Server::purge() {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto& kv : conns_) kv.second->leases.clear();
+    const size_t n = store_->purge();
+    for (auto& s : segs_) s->clear_index();
+    return n;
+}
+
+ServerStats Server::stats() {
+    std::lock_guard<std::mutex> lk(mu_);
+    ServerStats s = stats_;
+    s.connections = conns_.size();
+    s.keys = store_->size();
+    s.inflight = store_->inflight();
+    s.pool_bytes = mm_.total_bytes();
+    s.used_bytes = mm_.used_bytes();
+    s.segments = segs_.size();
+    return s;
+}
+
+std::vector<SegmentInfo> Server::segments() {
+    std::lock_guard<std::mutex> lk(mu_);
+    std::vector<SegmentInfo> v;
+    for (auto& s : segs_) v.push_back(s->info());
+    return v;
+}
+
+// ---------------------------------------------------------------- reactor
+
+void Server::loop() {
+    constexpr int kMaxEvents = 64;
+    epoll_event evs[kMaxEvents];
+    while (!stop_.load(std::memory_order_relaxed)) {
+        const int n = epoll_wait(epoll_fd_, evs, kMaxEvents, 500);
+        if (n < 0) {
+            if (errno == EINTR) continue;
+            LOG_ERROR("epoll_wait: %s", std::strerror(errno));
+            break;
+        }
+        for (int i = 0; i < n; ++i) {
+            const int fd = evs[i].data.fd;
+            if (fd == wake_fd_) {
+                uint64_t v;
+                (void)!read(wake_fd_, &v, sizeof(v));
+                continue;
+            }
+            if (fd == listen_fd_) {
+                on_accept();
+                continue;
+            }
+            std::lock_guard<std::mutex> lk(mu_);
+            auto it = conns_.find(fd);
+            if (it == conns_.end()) continue;
+            Conn* c = it->second.get();
+            if (evs[i].events & (EPOLLERR | EPOLLHUP)) {
+                close_conn(c);
+                continue;
+            }
+            if (evs[i].events & EPOLLOUT) on_writable(c);
+            if (conns_.count(fd) && (evs[i].events & EPOLLIN)) on_readable(c);
+        }
+    }
+}
+
+void Server::on_accept() {
+    for (;;) {
+        sockaddr_in sa{};
+        socklen_t sl = sizeof(sa);
+        const int fd = accept4(listen_fd_, reinterpret_cast<sockaddr*>(&sa), &sl,
+                               SOCK_NONBLOCK | SOCK_CLOEXEC);
+        if (fd < 0) {
+            if (errno != EAGAIN && errno != EWOULDBLOCK && errno != EINTR)
+                LOG_WARN("accept: %s", std::strerror(errno));
+            return;
+        }
+        int one = 1;
+        setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+        auto c = std::make_unique<Conn>();
+        c->fd = fd;
+        char ip[INET_ADDRSTRLEN] = {0};
+        inet_ntop(AF_INET, &sa.sin_addr, ip, sizeof(ip));
+        c->addr = std::string(ip) + ":" + std::to_string(ntohs(sa.sin_port));
+        epoll_event ev{};
+        ev.events = EPOLLIN;
+        ev.data.fd = fd;
+        std::lock_guard<std::mutex> lk(mu_);
+        c->id = next_conn_id_++;
+        if (epoll_ctl(epoll_fd_, EPOLL_CTL_ADD, fd, &ev) != 0) {
+            close(fd);
+            continue;
+        }
+        LOG_DEBUG("connection %llu from %s", (unsigned long long)c->id, c->addr.c_str());
+        stats_.accepted++;
+        conns_[fd] = std::move(c);
+    }
+}
+
+void Server::close_conn(Conn* c) {
+    const size_t dropped = store_->drop_uncommitted(c->id);
+    if (dropped)
+        LOG_WARN("connection %llu closed with %zu uncommitted blocks: released",
+                 (unsigned long long)c->id, dropped);
+    LOG_DEBUG("connection %llu closed", (unsigned long long)c->id);
+    epoll_ctl(epoll_fd_, EPOLL_CTL_DEL, c->fd, nullptr);
+    close(c->fd);
+    conns_.erase(c->fd);  // destroys c (and its leases)
+}
+
+void Server::on_writable(Conn* c) {
+    while (c->out_off < c->out.size()) {
+        const ssize_t n =
+            send(c->fd, c->out.data() + c->out_off, c->out.size() - c->out_off, MSG_NOSIGNAL);
+        if (n > 0) {
+            c->out_off += size_t(n);
+        } else if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) {
+            break;
+        } else if (n < 0 && errno == EINTR) {
+            continue;
+        } else {
+            close_conn(c);
+            return;
+        }
+    }
+    const bool pending = c->out_off < c->out.size();
+    if (!pending) {
+        c->out.clear();
+        c->out_off = 0;
+        if (c->closing) {
+            close_conn(c);
+            return;
+        }
+    }
+    if (pending != c->want_write) {
+        epoll_event ev{};
+        ev.events = EPOLLIN | (pending ? EPOLLOUT : 0);
+        ev.data.fd = c->fd;
+        epoll_ctl(epoll_fd_, EPOLL_CTL_MOD, c->fd, &ev);
+        c->want_write = pending;
+    }
+}
+
+void Server::reply(Conn* c, int32_t code, const void* payload, size_t len) {
+    const size_t at = c->out.size();
+    c->out.resize(at + sizeof(code) + len);
+    std::memcpy(c->out.data() + at, &code, sizeof(code));
+    if (len) std::memcpy(c->out.data() + at + sizeof(code), payload, len);
+}
+
+void Server::reply_blob(Conn* c, int32_t code, const void* blob, size_t len) {
+    const size_t at = c->out.size();
+    const uint32_t l32 = uint32_t(len);
+    c->out.resize(at + sizeof(code) + sizeof(l32) + len);
+    std::memcpy(c->out.data() + at, &code, sizeof(code));
+    std::memcpy(c->out.data() + at + sizeof(code), &l32, sizeof(l32));
+    if (len) std::memcpy(c->out.data() + at + sizeof(code) + sizeof(l32), blob, len);
+}
+
+// Stream parser: READ_HEADER (9 bytes) -> READ_BODY (body_size bytes) -> dispatch.
+void Server::on_readable(Conn* c) {
+    const int fd = c->fd;
+    for (int budget = 0; budget < 256; ++budget) {
+        if (c->closing) break;
+        ssize_t n;
+        if (c->state == Conn::kHeader) {
+            n = recv(fd, c->hdr_buf + c->hdr_got, sizeof(Header) - c->hdr_got, 0);
+        } else {
+            n = recv(fd, c->body.data() + c->body_got, c->body.size() - c->body_got, 0);
+        }
+        if (n == 0) {
+            close_conn(c);
+            return;
+        }
+        if (n < 0) {
+            if (errno == EAGAIN || errno == EWOULDBLOCK) break;
+            if (errno == EINTR) continue;
+            close_conn(c);
+            return;
+        }
+        bool complete = false;
+        if (c->state == Conn::kHeader) {
+            c->hdr_got += size_t(n);
+            if (c->hdr_got < sizeof(Header)) continue;
+            std::memcpy(&c->hdr, c->hdr_buf, sizeof(Header));
+            c->hdr_got = 0;
+            if (c->hdr.magic != kMagic) {
+                LOG_WARN("bad magic 0x%08x from %s: closing", c->hdr.magic, c->addr.c_str());
+                stats_.bad_requests++;
+                close_conn(c);
+                return;
+            }
+            if (!op_known(c->hdr.op)) {
+                LOG_WARN("unknown op 0x%02x from %s: 400 and close", (unsigned)(uint8_t)c->hdr.op,
+                         c->addr.c_str());
+                stats_.bad_requests++;
+                reply(c, kInvalidReq);
+                c->closing = true;
+                break;
+            }
+            if (!op_has_body(c->hdr.op)) {
+                // the reference client leaves body_size uninitialised for SYNC: ignore it
+                c->body.clear();
+                complete = true;
+            } else if (c->hdr.body_size > kMaxBody) {
+                LOG_WARN("body of %u bytes exceeds the %u byte cap: 400 and close",
+                         c->hdr.body_size, kMaxBody);
+                stats_.bad_requests++;
+                reply(c, kInvalidReq);
+                c->closing = true;
+                break;
+            } else if (c->hdr.body_size == 0) {
+                c->body.clear();
+                complete = true;
+            } else {
+                c->body.resize(c->hdr.body_size);
+                c->body_got = 0;
+                c->state = Conn::kBody;
+            }
+        } else {
+            c->body_got += size_t(n);
+            if (c->body_got == c->body.size()) {
+                c->state = Conn::kHeader;
+                complete = true;
+            }
+        }
+        if (complete) {
+            stats_.requests++;
+            stats_.ops[uint8_t(c->hdr.op) & 127]++;
+            const uint64_t d = drop_after_.load();
+            if (d && drop_after_.fetch_sub(1) == 1) {  // fault injection
+                close_conn(c);
+                return;
+            }
+            if (!dispatch(c)) {
+                c->closing = true;
+                break;
+            }
+        }
+    }
+    if (conns_.count(fd)) on_writable(c);  // flush replies (may close when `closing`)
+}
+
+bool Server::dispatch(Conn* c) {
+    const auto t0 = std::chrono::steady_clock::now();
+    int code = kInvalidReq;
+    try {
+        switch (c->hdr.op) {
+            case kOpExchange: code = handle_exchange(c); break;
+            case kOpPoolMap: code = handle_pool_map(c); break;
+            case kOpAllocate: code = handle_allocate(c, false); break;
+            case kOpLocalWrite: code = handle_allocate(c, true); break;
+            case kOpReadLookup: code = handle_lookup(c, false); break;
+            case kOpLocalRead: code = handle_lookup(c, true); break;
+            case kOpCommit: code = handle_commit(c); break;
+            case kOpCheckExist: code = handle_check_exist(c); break;
+            case kOpMatchLastIdx: code = handle_match(c); break;
+            case kOpSync: {
+                c->leases.clear();  // the client's reads have completed
+                const uint32_t remain = 0;  // no server-side transfers exist in this design
+                reply(c, kFinish, &remain, sizeof(remain));
+                code = kFinish;
+                break;
+            }
+            default: break;
+        }
+    } catch (const fb::Malformed& e) {
+        LOG_WARN("malformed %s request from %s: %s", op_name(c->hdr.op), c->addr.c_str(),
+                 e.what());
+        code = kInvalidReq;
+        if (c->hdr.op != kOpCommit) reply(c, kInvalidReq);
+    } catch (const std::exception& e) {
+        LOG_ERROR("%s request failed: %s", op_name(c->hdr.op), e.what());
+        code = kInternalError;
+        if (c->hdr.op != kOpCommit) reply(c, kInternalError);
+    }
+    if (code >= 400) stats_.bad_requests++;
+    const auto us = std::chrono::duration_cast<std::chrono::microseconds>(
+                        std::chrono::steady_clock::now() - t0)
+                        .count();
+    LOG_DEBUG("%s from conn %llu -> %d in %lld us", op_name(c->hdr.op),
+              (unsigned long long)c->id, code, (long long)us);
+    // A malformed request leaves the stream position well defined (the body was consumed),
+    // so the connection stays usable; only protocol-level violations close it.
+    return true;
+}
+
+int Server::handle_exchange(Conn* c) {
+    if (c->body.size() != sizeof(ConnInfo)) {
+        reply(c, kInvalidReq);
+        return kInvalidReq;
+    }
+    std::memcpy(&c->peer, c->body.data(), sizeof(ConnInfo));
+    ConnInfo me{};
+    me.qpn = uint32_t(getpid());
+    me.psn = uint32_t(segs_.size());
+    std::memcpy(me.gid, fabric::process_uuid(), 16);
+    me.lid = uint16_t((fabric::cuda_available() ? 1 : 0) | (use_hbm_ ? 2 : 0));
+    me.mtu = kFabricVersion;
+    reply(c, kFinish, &me, sizeof(me));
+    return kFinish;
+}
+
+int Server::handle_pool_map(Conn* c) {
+    uint32_t first = 0;
+    if (c->body.size() >= sizeof(first)) std::memcpy(&first, c->body.data(), sizeof(first));
+    std::vector<uint8_t> blob(sizeof(uint32_t));
+    uint32_t count = 0;
+    for (size_t i = first; i < segs_.size(); ++i) {
+        const SegmentInfo& info = segs_[i]->info();
+        const size_t at = blob.size();
+        blob.resize(at + sizeof(SegmentInfo));
+        std::memcpy(blob.data() + at, &info, sizeof(SegmentInfo));
+        ++count;
+    }
+    std::memcpy(blob.data(), &count, sizeof(count));
+    reply_blob(c, kFinish, blob.data(), blob.size());
+    return kFinish;
+}
+
+int Server::handle_allocate(Conn* c, bool local) {
+    std::vector<std::string_view> keys;
+    int32_t block_size = 0;
+    int hint = -1;
+    if (local) {
+        LocalMetaRequest req = decode_local_meta(c->body.data(), c->body.size());
+        block_size = req.block_size;
+        keys.reserve(req.blocks.size());
+        for (auto& b : req.blocks) keys.push_back(b.key);
+        hint = -1;
+    } else {
+        RemoteMetaRequest req = decode_remote_meta(c->body.data(), c->body.size());
+        block_size = req.block_size;
+        keys = std::move(req.keys);
+        hint = req.hint;
+    }
+    if (block_size <= 0 || keys.empty()) {
+        reply(c, kInvalidReq);
+        return kInvalidReq;
+    }
+    std::vector<RemoteBlock> blocks;
+    int code = store_->reserve(keys, size_t(block_size), hint, c->id, blocks);
+    while (code == kOutOfMemory && maybe_extend())
+        code = store_->reserve(keys, size_t(block_size), hint, c->id, blocks);
+    if (code != kFinish) {
+        LOG_WARN("allocate of %zu x %d bytes failed: pool exhausted (%zu/%zu MiB used)",
+                 keys.size(), block_size, mm_.used_bytes() >> 20, mm_.total_bytes() >> 20);
+        reply(c, code);
+        return code;
+    }
+    if (cfg_.auto_increase && mm_.need_extend()) maybe_extend();
+    const size_t need = blocks.size() * sizeof(RemoteBlock) + 64;
+    if (scratch_.size() < need) scratch_.resize((need + 7) & ~size_t(7));
+    fb::Builder b(scratch_.data(), scratch_.size() & ~size_t(7));
+    encode_allocate_response(b, blocks.data(), blocks.size());
+    reply_blob(c, local ? kTaskAccepted : kFinish, b.data(), b.size());
+    return kFinish;
+}
+
+int Server::handle_lookup(Conn* c, bool local) {
+    std::vector<std::string_view> keys;
+    int32_t block_size = 0;
+    if (local) {
+        LocalMetaRequest req = decode_local_meta(c->body.data(), c->body.size());
+        block_size = req.block_size;
+        keys.reserve(req.blocks.size());
+        for (auto& b : req.blocks) keys.push_back(b.key);
+    } else {
+        RemoteMetaRequest req = decode_remote_meta(c->body.data(), c->body.size());
+        block_size = req.block_size;
+        keys = std::move(req.keys);
+    }
+    if (block_size <= 0 || keys.empty()) {
+        reply(c, kInvalidReq);
+        return kInvalidReq;
+    }
+    std::vector<RemoteBlock> blocks;
+    const int code = store_->lookup(keys, size_t(block_size), blocks, &c->leases);
+    if (code != kFinish) {
+        reply(c, code);  // explicit error reply (the reference's RDMA path stays silent)
+        return code;
+    }
+    const size_t need = blocks.size() * sizeof(RemoteBlock) + 64;
+    if (scratch_.size() < need) scratch_.resize((need + 7) & ~size_t(7));
+    fb::Builder b(scratch_.data(), scratch_.size() & ~size_t(7));
+    encode_allocate_response(b, blocks.data(), blocks.size());
+    reply_blob(c, local ? kTaskAccepted : kFinish, b.data(), b.size());
+    return kFinish;
+}
+
+int Server::handle_commit(Conn* c) {
+    RemoteMetaRequest req = decode_remote_meta(c->body.data(), c->body.size());
+    store_->commit(req.remote_addrs.data(), req.remote_addrs.size());
+    return kFinish;  // no reply: ordered before the client's next SYNC on this connection
+}
+
+int Server::handle_check_exist(Conn* c) {
+    const std::string_view key(reinterpret_cast<const char*>(c->body.data()), c->body.size());
+    const int32_t v = store_->exists_committed(key) ? 0 : 1;
+    reply(c, kFinish, &v, sizeof(v));
+    return kFinish;
+}
+
+int Server::handle_match(Conn* c) {
+    std::vector<std::string_view> keys = decode_match_request(c->body.data(), c->body.size());
+    const int32_t idx = store_->match_last_index(keys);
+    reply(c, kFinish, &idx, sizeof(idx));
+    return kFinish;
+}
+
+}  // namespace istore

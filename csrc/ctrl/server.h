@@ -1,0 +1,109 @@
+// Control-plane server: an epoll reactor on its own thread that owns the allocator, the
+// key index and the pool segments.
+//
+// Role parity with the reference's libuv front-end + server bootstrap
+// (src/infinistore.cpp:1113-1298): accept, 2-state header/body stream parser tolerant of
+// arbitrary TCP segmentation, per-op dispatch, replies of `int code + payload`.  It is
+// NOT a libuv port: libuv headers do not exist on the target image, and the B200 design
+// moves all data movement to client-side kernels, so the server never touches CUDA on a
+// request path (no per-request stream/event/IPC-open as in the reference's local path).
+//
+// Hardening relative to the reference: body_size is capped, an
+// unknown op is answered with 400 and the connection is closed instead of spinning,
+// every flatbuffer is verified, the exchange body must be exactly 30 bytes, the listen
+// address is honoured, and uncommitted reservations of a dead client are released.
+#pragma once
+
+#include <atomic>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../core/config.h"
+#include "../core/kv_store.h"
+#include "../core/mempool.h"
+#include "../fabric/segment.h"
+
+namespace istore {
+
+struct ServerStats {
+    uint64_t connections = 0;       // currently open
+    uint64_t accepted = 0;          // total accepted
+    uint64_t requests = 0;
+    uint64_t bad_requests = 0;
+    uint64_t keys = 0;
+    uint64_t inflight = 0;
+    uint64_t pool_bytes = 0;
+    uint64_t used_bytes = 0;
+    uint64_t segments = 0;
+    uint64_t ops[128] = {0};        // per opcode
+};
+
+class Server {
+   public:
+    explicit Server(const ServerConfig& cfg);
+    ~Server();
+
+    // Creates the pool, binds and starts the reactor thread.  0 on success.
+    int start(std::string* err);
+    void stop();
+    bool running() const { return running_.load(); }
+    int port() const { return port_; }
+
+    size_t kvmap_len();
+    size_t purge();
+    ServerStats stats();
+    std::vector<SegmentInfo> segments();
+
+    // Fault injection for tests: close a connection instead of answering the n-th request
+    // from now (0 = off).
+    void inject_drop_after(uint64_t n) { drop_after_.store(n); }
+
+   private:
+    struct Conn;
+    void loop();
+    void on_accept();
+    void on_readable(Conn* c);
+    void on_writable(Conn* c);
+    void close_conn(Conn* c);
+    bool dispatch(Conn* c);  // false => close the connection
+    void reply(Conn* c, int32_t code, const void* payload = nullptr, size_t len = 0);
+    void reply_blob(Conn* c, int32_t code, const void* blob, size_t len);
+    bool add_segment(std::string* err);
+    bool maybe_extend();
+
+    int handle_exchange(Conn* c);
+    int handle_pool_map(Conn* c);
+    int handle_allocate(Conn* c, bool local);
+    int handle_lookup(Conn* c, bool local);
+    int handle_commit(Conn* c);
+    int handle_check_exist(Conn* c);
+    int handle_match(Conn* c);
+
+    ServerConfig cfg_;
+    int port_ = 0;
+    int listen_fd_ = -1;
+    int epoll_fd_ = -1;
+    int wake_fd_ = -1;
+    std::thread thread_;
+    std::atomic<bool> running_{false};
+    std::atomic<bool> stop_{false};
+    std::atomic<uint64_t> drop_after_{0};
+
+    std::mutex mu_;  // guards everything below (reactor thread vs. manage-plane callers)
+    MM mm_;
+    std::unique_ptr<KVStore> store_;
+    std::vector<std::unique_ptr<fabric::SegmentOwner>> segs_;
+    std::map<int, std::unique_ptr<Conn>> conns_;
+    uint64_t next_conn_id_ = 1;
+    size_t next_pool_dev_ = 0;
+    bool use_hbm_ = false;
+    ServerStats stats_;
+    std::vector<uint8_t> scratch_;  // reply serialisation buffer
+};
+
+}  // namespace istore

@@ -1,0 +1,128 @@
+// Host-callable launchers of the sm_100a data-plane kernels.
+//
+// These kernels replace every byte-moving / lookup call site of the reference, which has
+// no device code at all: per-block cudaMemcpyAsync (src/infinistore.cpp:
+// 623-624,747-748), ibv_post_send RDMA_WRITE chains (src/libinfinistore.cpp:916-981,
+// src/infinistore.cpp:471-501), the COMMIT message (src/libinfinistore.cpp:362-395) and
+// the get_match_last_index / check_key CPU probes (src/infinistore.cpp:1077-1108).
+#pragma once
+
+#include <cuda_runtime_api.h>
+
+#include <cstdint>
+
+namespace istore::kernels {
+
+// One block to move: absolute, device-addressable source and destination.  For a write
+// `dst` is a peer-mapped pool address, for a read `src` is.  src == 0 marks a block the
+// device lookup did not find: it is skipped and counted in status[kStatMiss].
+struct CopyDesc {
+    uint64_t src;
+    uint64_t dst;
+};
+
+// Entry of the HBM-resident key index == record a writer publishes once the block's data
+// is visible system-wide.  Open addressing, linear probing, slot = h1 & mask.
+//   h1   : claimed with a 64-bit CAS (0 = empty slot)
+//   tag  : allocation generation, written last with release.sys; 0 = not yet committed
+struct IndexEntry {
+    uint64_t h1;
+    uint64_t h2;
+    uint64_t addr;  // global block address: (segment+1) << 44 | offset
+    uint32_t tag;
+    uint32_t size;
+};
+static_assert(sizeof(IndexEntry) == 32, "index entries are 32 bytes");
+
+enum Status : int {
+    kStatMiss = 0,         // blocks skipped by a read because the key was not in the index
+    kStatPublishFail = 1,  // index insertions that found the table full
+    kStatMatch = 2,        // result of the last match_last_index launch (int32)
+    kStatWords = 8,
+};
+
+enum CopyVariant : int {
+    kCopyAuto = 0,
+    kCopyLdSt = 1,  // 128-bit ld/st, all threads: LDG.128 / STG.128 on (peer) global memory
+    kCopyTma = 2,   // 1-D bulk async copies through an SMEM ring: UBLKCP.S.G / UBLKCP.G.S
+    kCopyLdSt256 = 3,  // 256-bit ld/st (LDG.E.ENL2.256 / STG.E.ENL2.256)
+};
+
+struct CopyLaunch {
+    const CopyDesc* descs = nullptr;  // device-addressable (device memory or mapped pinned host)
+    uint32_t n = 0;                   // blocks
+    uint32_t bytes = 0;               // bytes per block
+    uint64_t align_or = 0;            // OR of every local address (pool blocks are granule aligned)
+    // optional in-band commit (writes): publish recs[i] once block i has landed
+    const IndexEntry* recs = nullptr;
+    IndexEntry* table = nullptr;
+    uint64_t table_mask = 0;
+    uint32_t* done = nullptr;         // n zeroed u32 counters in client-local device memory
+    uint32_t* status = nullptr;       // kStatWords u32, device-addressable
+    int variant = kCopyAuto;
+    int max_ctas = 0;                 // 0 = pick from the problem size
+};
+cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream);
+
+// fp8 (e4m3) fused variants: the write converts bf16 pages to e4m3 with one fp32 scale
+// per `group` elements (the head_dim row) and stores payload + scales into the pool block;
+// the read dequantises back to bf16 while scattering into the paged KV cache.
+struct Fp8Launch {
+    const CopyDesc* descs = nullptr;
+    uint32_t n = 0;
+    uint32_t elems = 0;   // bf16 elements per page
+    uint32_t group = 128; // elements sharing one scale
+    const IndexEntry* recs = nullptr;
+    IndexEntry* table = nullptr;
+    uint64_t table_mask = 0;
+    uint32_t* done = nullptr;
+    uint32_t* status = nullptr;
+    int max_ctas = 0;
+};
+// bytes a quantised page occupies in the pool: elems (e4m3) + 4 * elems/group (scales)
+inline uint32_t fp8_block_bytes(uint32_t elems, uint32_t group) {
+    return elems + 4u * (elems / group);
+}
+cudaError_t launch_kv_write_fp8(const Fp8Launch& a, cudaStream_t stream);
+cudaError_t launch_kv_read_fp8(const Fp8Launch& a, cudaStream_t stream);
+
+// Device-side key lookup: hash the packed key bytes, probe the index, and either build
+// copy descriptors for a following kv_copy (read path) or produce a presence bitmap and
+// replay the reference's binary search (get_match_last_index / check_exist).
+struct LookupLaunch {
+    const uint8_t* key_bytes = nullptr;  // every key starts 8-byte aligned, zero padded
+    const uint32_t* key_off = nullptr;   // n byte offsets into key_bytes
+    const uint32_t* key_len = nullptr;   // n lengths
+    uint32_t n = 0;
+    const IndexEntry* table = nullptr;
+    uint64_t table_mask = 0;
+    // segment id -> mapped base pointer on the launching device
+    static constexpr int kMaxSegs = 16;
+    uint64_t seg_base[kMaxSegs] = {0};
+    uint32_t nsegs = 0;
+    // read path: out_descs[i] = {pool pointer or 0, dst_base + dst_off[i]}
+    CopyDesc* out_descs = nullptr;
+    const uint64_t* dst_off = nullptr;
+    uint64_t dst_base = 0;
+    uint32_t need_bytes = 0;             // a hit must hold at least this many bytes
+    // match path: presence bitmap (n bits, device memory) + replayed binary search
+    uint32_t* present = nullptr;         // ceil(n/32) words, zeroed by the kernel's caller
+    uint32_t* status = nullptr;          // status[kStatMatch] receives the int32 result
+    uint32_t* ticket = nullptr;          // zeroed u32 used to elect the last CTA
+    bool want_match = false;
+};
+cudaError_t launch_index_lookup(const LookupLaunch& a, cudaStream_t stream);
+
+// One writer -> all readers replication through an NVLS multicast mapping (multimem.st).
+struct BcastLaunch {
+    const CopyDesc* descs = nullptr;  // dst = address inside the multicast mapping
+    uint32_t n = 0;
+    uint32_t bytes = 0;
+    int max_ctas = 0;
+};
+cudaError_t launch_kv_bcast_nvls(const BcastLaunch& a, cudaStream_t stream);
+
+// Number of SMs of the current device (cached per device).
+int sm_count();
+
+}  // namespace istore::kernels

@@ -1,0 +1,261 @@
+// kv_copy: the batched page mover behind write_cache (client GPU -> pool HBM) and
+// read_cache (pool HBM -> client GPU).
+//
+// One launch moves a whole batch of pages (a layer's worth) described by a descriptor
+// array; either side of every descriptor may be a peer-mapped address, so the bytes cross
+// NVLink 5 / NVSwitch from inside the kernel.  This replaces, for one batch,
+//   * N cudaMemcpyAsync calls on a fresh stream + event (reference local path,
+//     src/infinistore.cpp:623-624,747-748),
+//   * N RDMA_WRITE work requests chained 32 at a time (src/libinfinistore.cpp:905-970,
+//     src/infinistore.cpp:456-530), and
+//   * the COMMIT message round (src/libinfinistore.cpp:362-395 -> src/infinistore.cpp:
+//     255-271): the kernel publishes each block in the HBM-resident index itself, with
+//     release semantics at system scope, once the block's bytes have landed.
+//
+// Two data paths, selected per launch (measured, not guessed — see profiles/):
+//   kCopyLdSt : every thread streams 128-bit (or 256-bit) vectors, 4 in flight per thread;
+//   kCopyTma  : one elected thread per CTA drives an SMEM ring with 1-D bulk async copies
+//               (cp.async.bulk, mbarrier completion in, bulk-group completion out).  A few
+//               CTAs of one warp each keep megabytes in flight, leaving the SMs to the
+//               model's own kernels when the transfer overlaps prefill.
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "publish.cuh"
+
+namespace istore::kernels {
+
+namespace {
+
+using namespace dev;
+
+constexpr int kLdStThreads = 256;
+constexpr uint32_t kLdStChunk = 32u << 10;  // work item of the ld/st path
+constexpr int kTmaStages = 8;
+constexpr uint32_t kTmaChunk = 16u << 10;   // bytes per bulk copy / ring stage
+
+// ---------------------------------------------------------------- ld/st path
+template <int VEC>
+__device__ __forceinline__ void copy_span(uint8_t* dst, const uint8_t* src, uint32_t len) {
+    constexpr int U = 4;
+    const uint32_t nvec = len / VEC;
+    const uint32_t tid = threadIdx.x;
+    uint32_t i = tid;
+    for (; i + (U - 1) * kLdStThreads < nvec; i += U * kLdStThreads) {
+        if constexpr (VEC == 16) {
+            uint4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = ld_stream_v4(src + size_t(i + u * kLdStThreads) * 16);
+#pragma unroll
+            for (int u = 0; u < U; ++u) st_v4(dst + size_t(i + u * kLdStThreads) * 16, v[u]);
+        } else {
+            u32x8 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = ld_v8(src + size_t(i + u * kLdStThreads) * 32);
+#pragma unroll
+            for (int u = 0; u < U; ++u) st_v8(dst + size_t(i + u * kLdStThreads) * 32, v[u]);
+        }
+    }
+    for (; i < nvec; i += kLdStThreads) {
+        if constexpr (VEC == 16)
+            st_v4(dst + size_t(i) * 16, ld_stream_v4(src + size_t(i) * 16));
+        else
+            st_v8(dst + size_t(i) * 32, ld_v8(src + size_t(i) * 32));
+    }
+    for (uint32_t b = nvec * VEC + tid; b < len; b += kLdStThreads) dst[b] = src[b];
+}
+
+// VEC = 16 / 32: vector width; VEC = 1: byte fallback for unaligned tensors.
+template <int VEC>
+__global__ void __launch_bounds__(kLdStThreads)
+    kv_copy_ldst_kernel(const CopyDesc* __restrict__ descs, uint32_t n, uint32_t bytes,
+                        uint32_t chunk, uint32_t cpb, Publish pub) {
+    const uint32_t total = n * cpb;
+    uint32_t handled = 0;
+    uint32_t item = blockIdx.x;
+    CopyDesc next = item < total ? descs[item / cpb] : CopyDesc{0, 0};
+    for (; item < total; item += gridDim.x) {
+        const CopyDesc d = next;
+        const uint32_t nxt = item + gridDim.x;
+        if (nxt < total) next = descs[nxt / cpb];  // prefetch: descriptors may sit in host memory
+        ++handled;
+        if (d.src == 0) {  // key not found by the device lookup
+            if (threadIdx.x == 0 && item % cpb == 0 && pub.status)
+                atomicAdd(pub.status + kStatMiss, 1u);
+            continue;
+        }
+        const uint32_t off = (item % cpb) * chunk;
+        const uint32_t len = min(chunk, bytes - off);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(d.dst) + off;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(d.src) + off;
+        if constexpr (VEC == 1) {
+            for (uint32_t b = threadIdx.x; b < len; b += kLdStThreads) dst[b] = src[b];
+        } else {
+            copy_span<VEC>(dst, src, len);
+        }
+    }
+    if (pub.recs) publish_done_blocks(pub, blockIdx.x, handled, gridDim.x, cpb);
+}
+
+// ---------------------------------------------------------------- bulk-async (TMA) path
+// One warp per CTA.  Lane 0 runs the pipeline; all lanes prefetch descriptors (32 at a
+// time, one coalesced read even when they live in mapped host memory) and take part in
+// the publish step.
+__global__ void __launch_bounds__(32)
+    kv_copy_tma_kernel(const CopyDesc* __restrict__ descs, uint32_t n, uint32_t bytes,
+                       uint32_t cpb, Publish pub) {
+    extern __shared__ __align__(128) uint8_t ring[];
+    __shared__ __align__(8) uint64_t full[kTmaStages];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t total = n * cpb;
+    const uint32_t grid = gridDim.x;
+    const uint32_t nitems = blockIdx.x < total ? (total - blockIdx.x + grid - 1) / grid : 0;
+
+    if (lane == 0) {
+        for (int s = 0; s < kTmaStages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    // item k of this CTA -> global item blockIdx.x + k * grid
+    auto fetch = [&](uint32_t k0) -> CopyDesc {  // lane l gets the descriptor of item k0 + l
+        const uint32_t k = k0 + lane;
+        if (k >= nitems) return CopyDesc{0, 0};
+        return descs[(blockIdx.x + k * grid) / cpb];
+    };
+    // The descriptors of items [w, w+32) live in `cur`, of [w+32, w+64) in `nxt`.
+    CopyDesc cur = fetch(0), nxt = fetch(32);
+    uint32_t window = 0;
+    auto desc_of = [&](uint32_t k) -> CopyDesc {  // warp-uniform k in [window, window + 64)
+        const bool in_cur = k < window + 32;
+        const uint32_t l = (k - window) & 31;
+        CopyDesc r;
+        r.src = __shfl_sync(0xffffffffu, in_cur ? cur.src : nxt.src, l);
+        r.dst = __shfl_sync(0xffffffffu, in_cur ? cur.dst : nxt.dst, l);
+        return r;
+    };
+    auto issue_load = [&](uint32_t k, const CopyDesc& d) {
+        const uint32_t s = k % kTmaStages;
+        const uint32_t off = ((blockIdx.x + k * grid) % cpb) * kTmaChunk;
+        const uint32_t len = min(kTmaChunk, bytes - off);
+        if (lane == 0 && d.src != 0) {
+            mbar_expect_tx(&full[s], len);
+            bulk_g2s(ring + size_t(s) * kTmaChunk, reinterpret_cast<const uint8_t*>(d.src) + off,
+                     len, &full[s]);
+        }
+    };
+
+    const uint32_t prologue = min(uint32_t(kTmaStages - 1), nitems);
+    for (uint32_t k = 0; k < prologue; ++k) issue_load(k, desc_of(k));
+
+    for (uint32_t k = 0; k < nitems; ++k) {
+        if (k >= window + 32) {  // slide the descriptor window
+            window += 32;
+            cur = nxt;
+            nxt = fetch(window + 32);
+        }
+        const CopyDesc d = desc_of(k);
+        const uint32_t s = k % kTmaStages;
+        const uint32_t item = blockIdx.x + k * grid;
+        const uint32_t off = (item % cpb) * kTmaChunk;
+        const uint32_t len = min(kTmaChunk, bytes - off);
+        if (lane == 0) {
+            if (d.src != 0) {
+                mbar_wait(&full[s], (k / kTmaStages) & 1);
+                bulk_s2g(reinterpret_cast<uint8_t*>(d.dst) + off, ring + size_t(s) * kTmaChunk, len);
+            } else if (off == 0 && pub.status) {
+                atomicAdd(pub.status + kStatMiss, 1u);
+            }
+            bulk_commit();  // one group per item keeps wait_group arithmetic simple
+        }
+        const uint32_t kn = k + kTmaStages - 1;
+        if (kn < nitems) {
+            // stage kn % S was last read by the store of item k-1: wait until that store
+            // has drained its shared-memory source (all but the newest group)
+            if (lane == 0 && k >= 1) bulk_wait_read<1>();
+            // kn = k + S - 1 < window + 64 always holds (S - 1 < 32)
+            issue_load(kn, desc_of(kn));
+        }
+    }
+    if (lane == 0) {
+        bulk_wait<0>();        // every bulk store of this CTA has completed its writes
+        fence_proxy_async();   // order async-proxy writes before the generic-proxy publish
+    }
+    __syncwarp();
+    if (pub.recs) publish_done_blocks(pub, blockIdx.x, nitems, grid, cpb);
+}
+
+std::mutex g_attr_mu;
+bool g_tma_attr_set[64] = {false};
+
+}  // namespace
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream) {
+    if (a.n == 0 || a.bytes == 0) return cudaSuccess;
+    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status};
+    if (!a.table || !a.done) pub.recs = nullptr;
+    const int sms = sm_count();
+
+    int variant = a.variant;
+    // Alignment: bulk copies need 16-byte aligned addresses and sizes.  Descriptors that
+    // live in mapped host memory can be inspected here; device-resident ones (built by the
+    // lookup kernel) always point at granule-aligned pool blocks and the caller's offsets.
+    const bool aligned16 = (a.bytes % 16) == 0 && (a.align_or & 15) == 0;
+    const bool aligned32 = (a.bytes % 32) == 0 && (a.align_or & 31) == 0;
+    if (variant == kCopyAuto) variant = kCopyLdSt;  // default picked from profiles/ sweeps
+    if (!aligned16 && (variant == kCopyTma || variant == kCopyLdSt256)) variant = kCopyLdSt;
+
+    if (variant == kCopyTma) {
+        const uint32_t cpb = (a.bytes + kTmaChunk - 1) / kTmaChunk;
+        const uint64_t total = uint64_t(a.n) * cpb;
+        int ctas = a.max_ctas > 0 ? a.max_ctas : 2 * sms;
+        ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
+        const size_t smem = size_t(kTmaStages) * kTmaChunk;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> lk(g_attr_mu);
+            if (dev >= 0 && dev < 64 && !g_tma_attr_set[dev]) {
+                cudaError_t e = cudaFuncSetAttribute(
+                    kv_copy_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+                if (e != cudaSuccess) return e;
+                g_tma_attr_set[dev] = true;
+            }
+        }
+        kv_copy_tma_kernel<<<ctas, 32, smem, stream>>>(a.descs, a.n, a.bytes, cpb, pub);
+        return cudaGetLastError();
+    }
+
+    const uint32_t chunk = std::min(a.bytes, kLdStChunk);
+    const uint32_t cpb = (a.bytes + chunk - 1) / chunk;
+    const uint64_t total = uint64_t(a.n) * cpb;
+    int ctas = a.max_ctas > 0 ? a.max_ctas : 8 * sms;
+    ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
+    if (!aligned16)
+        kv_copy_ldst_kernel<1><<<ctas, kLdStThreads, 0, stream>>>(a.descs, a.n, a.bytes, chunk,
+                                                                   cpb, pub);
+    else if (variant == kCopyLdSt256 && aligned32)
+        kv_copy_ldst_kernel<32><<<ctas, kLdStThreads, 0, stream>>>(a.descs, a.n, a.bytes, chunk,
+                                                                    cpb, pub);
+    else
+        kv_copy_ldst_kernel<16><<<ctas, kLdStThreads, 0, stream>>>(a.descs, a.n, a.bytes, chunk,
+                                                                    cpb, pub);
+    return cudaGetLastError();
+}
+
+}  // namespace istore::kernels

@@ -1,0 +1,175 @@
+// fp8 KV path: the quantisation is fused into the page mover.
+//
+//   kv_write_fp8 : bf16 page in the client's paged KV cache -> e4m3 payload + one fp32 scale
+//                  per 128-element row (head_dim) written straight into the (peer) pool
+//                  block, then the in-band commit.  Half the NVLink bytes of a bf16 write and
+//                  no separate cast kernel / staging buffer.
+//   kv_read_fp8  : pool block -> dequantised bf16 scattered into the destination pages.
+// The reference moves raw bytes only (dtype-agnostic, infinistore/lib.py:377-379); this is
+// the "write fused with fp8 cast / read fused with gather" item of the north star.
+//
+// Pool block layout: [elems x e4m3][elems/128 x fp32 scale].
+// A warp owns one 128-element row per step (lane l: elements 4l..4l+3, one 8-byte load),
+// reduces |x| max with shuffles, and emits 4 bytes per lane (one coalesced 128-byte store
+// per row).  Four rows are in flight per warp to cover the NVLink / HBM latency.
+// There is no direct bf16<->e4m3 cvt on sm_100a: quantise via f32, dequantise via f16x2.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "publish.cuh"
+
+namespace istore::kernels {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr uint32_t kRow = 128;                 // elements sharing a scale
+constexpr int kRowsInFlight = 4;
+constexpr uint32_t kChunkElems = 8192;         // CTA work item: 64 rows
+constexpr float kE4m3Max = 448.f;
+
+__device__ __forceinline__ uint2 ld_u2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_u1(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint16_t cvt_e4m3x2(float hi, float lo) {  // F2FP.SATFINITE.E4M3.F32
+    uint16_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t cvt_f16x2_e4m3x2(uint16_t v) {  // F2FP.F16.E4M3.UNPACK_B
+    uint32_t r;
+    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(r) : "h"(v));
+    return r;
+}
+__device__ __forceinline__ float2 bf16x2_to_f2(uint32_t v) {
+    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&b);
+}
+
+__global__ void __launch_bounds__(kThreads)
+    kv_write_fp8_kernel(const CopyDesc* __restrict__ descs, uint32_t n, uint32_t elems,
+                        uint32_t cpb, Publish pub) {
+    const uint32_t total = n * cpb;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t handled = 0;
+    for (uint32_t item = blockIdx.x; item < total; item += gridDim.x, ++handled) {
+        const CopyDesc d = descs[item / cpb];
+        const uint32_t e0 = (item % cpb) * kChunkElems;
+        const uint32_t rows = (min(kChunkElems, elems - e0)) / kRow;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(d.src);  // bf16 page
+        uint8_t* q = reinterpret_cast<uint8_t*>(d.dst);                // e4m3 payload
+        float* scales = reinterpret_cast<float*>(q + elems);
+        for (uint32_t r0 = warp * kRowsInFlight; r0 < rows; r0 += kWarps * kRowsInFlight) {
+            uint2 v[kRowsInFlight];
+#pragma unroll
+            for (int u = 0; u < kRowsInFlight; ++u) {
+                const uint32_t row = e0 / kRow + r0 + u;
+                if (r0 + u < rows) v[u] = ld_u2(src + (size_t(row) * kRow + lane * 4) * 2);
+            }
+#pragma unroll
+            for (int u = 0; u < kRowsInFlight; ++u) {
+                if (r0 + u >= rows) break;
+                const uint32_t row = e0 / kRow + r0 + u;
+                const float2 a = bf16x2_to_f2(v[u].x), b = bf16x2_to_f2(v[u].y);
+                float amax = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y)));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+                const float scale = amax > 0.f ? amax * (1.f / kE4m3Max) : 1.f;
+                const float inv = 1.f / scale;
+                const uint32_t lo = cvt_e4m3x2(a.y * inv, a.x * inv);
+                const uint32_t hi = cvt_e4m3x2(b.y * inv, b.x * inv);
+                *reinterpret_cast<uint32_t*>(q + size_t(row) * kRow + lane * 4) = lo | (hi << 16);
+                if (lane == 0) scales[row] = scale;
+            }
+        }
+    }
+    if (pub.recs) publish_done_blocks(pub, blockIdx.x, handled, gridDim.x, cpb);
+}
+
+__global__ void __launch_bounds__(kThreads)
+    kv_read_fp8_kernel(const CopyDesc* __restrict__ descs, uint32_t n, uint32_t elems,
+                       uint32_t cpb, uint32_t* status) {
+    const uint32_t total = n * cpb;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t item = blockIdx.x; item < total; item += gridDim.x) {
+        const CopyDesc d = descs[item / cpb];
+        if (d.src == 0) {
+            if (threadIdx.x == 0 && item % cpb == 0 && status) atomicAdd(status + kStatMiss, 1u);
+            continue;
+        }
+        const uint32_t e0 = (item % cpb) * kChunkElems;
+        const uint32_t rows = (min(kChunkElems, elems - e0)) / kRow;
+        const uint8_t* q = reinterpret_cast<const uint8_t*>(d.src);
+        const float* scales = reinterpret_cast<const float*>(q + elems);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(d.dst);
+        for (uint32_t r0 = warp * kRowsInFlight; r0 < rows; r0 += kWarps * kRowsInFlight) {
+            uint32_t v[kRowsInFlight];
+            float sc[kRowsInFlight];
+#pragma unroll
+            for (int u = 0; u < kRowsInFlight; ++u) {
+                const uint32_t row = e0 / kRow + r0 + u;
+                if (r0 + u < rows) {
+                    v[u] = ld_u1(q + size_t(row) * kRow + lane * 4);
+                    sc[u] = __uint_as_float(ld_u1(scales + row));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kRowsInFlight; ++u) {
+                if (r0 + u >= rows) break;
+                const uint32_t row = e0 / kRow + r0 + u;
+                const uint32_t h01 = cvt_f16x2_e4m3x2(uint16_t(v[u] & 0xffffu));
+                const uint32_t h23 = cvt_f16x2_e4m3x2(uint16_t(v[u] >> 16));
+                const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+                const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+                uint2 out;
+                out.x = f2_to_bf16x2(f01.x * sc[u], f01.y * sc[u]);
+                out.y = f2_to_bf16x2(f23.x * sc[u], f23.y * sc[u]);
+                *reinterpret_cast<uint2*>(dst + (size_t(row) * kRow + lane * 4) * 2) = out;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_kv_write_fp8(const Fp8Launch& a, cudaStream_t stream) {
+    if (a.n == 0 || a.elems == 0) return cudaSuccess;
+    if (a.group != kRow || a.elems % kRow != 0) return cudaErrorInvalidValue;
+    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status};
+    if (!a.table || !a.done) pub.recs = nullptr;
+    const uint32_t cpb = (a.elems + kChunkElems - 1) / kChunkElems;
+    const uint64_t total = uint64_t(a.n) * cpb;
+    int ctas = a.max_ctas > 0 ? a.max_ctas : 8 * sm_count();
+    ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
+    kv_write_fp8_kernel<<<ctas, kThreads, 0, stream>>>(a.descs, a.n, a.elems, cpb, pub);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kv_read_fp8(const Fp8Launch& a, cudaStream_t stream) {
+    if (a.n == 0 || a.elems == 0) return cudaSuccess;
+    if (a.group != kRow || a.elems % kRow != 0) return cudaErrorInvalidValue;
+    const uint32_t cpb = (a.elems + kChunkElems - 1) / kChunkElems;
+    const uint64_t total = uint64_t(a.n) * cpb;
+    int ctas = a.max_ctas > 0 ? a.max_ctas : 8 * sm_count();
+    ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
+    kv_read_fp8_kernel<<<ctas, kThreads, 0, stream>>>(a.descs, a.n, a.elems, cpb, a.status);
+    return cudaGetLastError();
+}
+
+}  // namespace istore::kernels

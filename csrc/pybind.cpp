@@ -1,0 +1,607 @@
+// Python binding: module infinistore_b200._infinistore.
+//
+// Surface parity with the reference's pybind module (src/pybind.cpp:36-210): ClientConfig,
+// ServerConfig, Connection, register_server, purge_kv_map, get_kvmap_len, log_msg,
+// set_log_level; allocate results are a zero-copy numpy structured array with rkey:u4 @0
+// and remote_addr:u8 @8 (itemsize 16).  Every blocking call releases the GIL; callbacks
+// of the async API re-acquire it on the connection's completion thread.
+// Extras: a Server class (several servers per process, SPMD ranks hosting pool shards),
+// introspection (stats, segments), and raw launchers of the sm_100a kernels plus the wire
+// codec / allocator for unit tests.
+#include <pybind11/functional.h>
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <cuda_runtime_api.h>
+
+#include <memory>
+#include <mutex>
+
+#include "core/config.h"
+#include "core/hash.h"
+#include "core/kv_store.h"
+#include "core/log.h"
+#include "core/mempool.h"
+#include "ctrl/client.h"
+#include "ctrl/server.h"
+#include "fabric/nvls.h"
+#include "fabric/segment.h"
+#include "kernels/kernels.h"
+#include "wire/messages.h"
+
+namespace py = pybind11;
+using namespace istore;
+
+namespace {
+
+std::mutex g_server_mu;
+std::unique_ptr<Server> g_server;
+
+py::array_t<RemoteBlock> blocks_to_array(std::vector<RemoteBlock>&& v) {
+    auto* heap = new std::vector<RemoteBlock>(std::move(v));
+    py::capsule owner(heap, [](void* p) { delete static_cast<std::vector<RemoteBlock>*>(p); });
+    return py::array_t<RemoteBlock>(heap->size(), heap->data(), owner);
+}
+
+// remote blocks arrive as the structured array returned by allocate (possibly sliced)
+std::vector<RemoteBlock> blocks_from_py(const py::object& obj) {
+    std::vector<RemoteBlock> out;
+    if (py::isinstance<py::array>(obj)) {
+        py::array arr = py::array::ensure(obj);
+        if (arr.itemsize() == sizeof(RemoteBlock)) {
+            auto a = py::array_t<RemoteBlock, py::array::c_style | py::array::forcecast>(arr);
+            auto r = a.unchecked<1>();
+            out.resize(size_t(r.shape(0)));
+            for (py::ssize_t i = 0; i < r.shape(0); ++i) out[size_t(i)] = r(i);
+            return out;
+        }
+    }
+    for (auto item : obj) {  // list of (rkey, remote_addr) or (rkey, gen, remote_addr)
+        py::tuple t = py::cast<py::tuple>(item);
+        RemoteBlock b{};
+        if (t.size() == 2) {
+            b.rkey = t[0].cast<uint32_t>();
+            b.remote_addr = t[1].cast<uint64_t>();
+        } else {
+            b.rkey = t[0].cast<uint32_t>();
+            b.gen = t[1].cast<uint32_t>();
+            b.remote_addr = t[2].cast<uint64_t>();
+        }
+        out.push_back(b);
+    }
+    return out;
+}
+
+std::vector<KeyOffset> key_offsets(const std::vector<std::pair<std::string, uint64_t>>& v) {
+    std::vector<KeyOffset> out;
+    out.reserve(v.size());
+    for (auto& p : v) out.push_back(KeyOffset{p.first, p.second});
+    return out;
+}
+
+py::dict segment_dict(const SegmentInfo& s) {
+    py::dict d;
+    d["id"] = s.id;
+    d["kind"] = s.kind == kSegDeviceIpc ? "hbm" : "host";
+    d["device"] = s.device;
+    d["granule"] = s.granule;
+    d["bytes"] = s.bytes;
+    d["index_slots"] = s.index_slots;
+    d["map_bytes"] = s.map_bytes;
+    return d;
+}
+
+py::dict stats_dict(const ServerStats& s) {
+    py::dict d;
+    d["connections"] = s.connections;
+    d["accepted"] = s.accepted;
+    d["requests"] = s.requests;
+    d["bad_requests"] = s.bad_requests;
+    d["keys"] = s.keys;
+    d["inflight"] = s.inflight;
+    d["pool_bytes"] = s.pool_bytes;
+    d["used_bytes"] = s.used_bytes;
+    d["segments"] = s.segments;
+    py::dict ops;
+    for (int i = 0; i < 128; ++i)
+        if (s.ops[i]) ops[py::str(op_name(char(i)))] = s.ops[i];
+    d["ops"] = ops;
+    return d;
+}
+
+template <typename T>
+T* as_ptr(uint64_t p) {
+    return reinterpret_cast<T*>(p);
+}
+
+}  // namespace
+
+PYBIND11_MODULE(_infinistore, m) {
+    m.doc() = "B200-native KV-cache store: control plane, fabric and sm_100a kernels";
+
+    PYBIND11_NUMPY_DTYPE(RemoteBlock, rkey, gen, remote_addr);
+
+    py::class_<ClientConfig>(m, "ClientConfig")
+        .def(py::init<>())
+        .def_readwrite("service_port", &ClientConfig::service_port)
+        .def_readwrite("log_level", &ClientConfig::log_level)
+        .def_readwrite("dev_name", &ClientConfig::dev_name)
+        .def_readwrite("host_addr", &ClientConfig::host_addr)
+        .def_readwrite("ib_port", &ClientConfig::ib_port)
+        .def_readwrite("link_type", &ClientConfig::link_type)
+        .def_readwrite("device", &ClientConfig::device)
+        .def_readwrite("timeout_ms", &ClientConfig::timeout_ms)
+        .def_readwrite("pool_hint", &ClientConfig::pool_hint);
+
+    py::class_<ServerConfig>(m, "ServerConfig")
+        .def(py::init<>())
+        .def_readwrite("service_port", &ServerConfig::service_port)
+        .def_readwrite("log_level", &ServerConfig::log_level)
+        .def_readwrite("dev_name", &ServerConfig::dev_name)
+        .def_readwrite("prealloc_size", &ServerConfig::prealloc_size)
+        .def_readwrite("ib_port", &ServerConfig::ib_port)
+        .def_readwrite("link_type", &ServerConfig::link_type)
+        .def_readwrite("minimal_allocate_size", &ServerConfig::minimal_allocate_size)
+        .def_readwrite("num_stream", &ServerConfig::num_stream)
+        .def_readwrite("auto_increase", &ServerConfig::auto_increase)
+        .def_readwrite("host", &ServerConfig::host)
+        .def_readwrite("pool_backend", &ServerConfig::pool_backend)
+        .def_readwrite("pool_devices", &ServerConfig::pool_devices)
+        .def_readwrite("extend_size", &ServerConfig::extend_size)
+        .def_readwrite("prealloc_bytes", &ServerConfig::prealloc_bytes)
+        .def_readwrite("index_slots", &ServerConfig::index_slots);
+
+    // ------------------------------------------------------------ client
+    py::class_<Connection, std::shared_ptr<Connection>>(m, "Connection")
+        .def(py::init<>())
+        .def("close", &Connection::close, py::call_guard<py::gil_scoped_release>())
+        .def("init_connection", &Connection::init_connection,
+             py::call_guard<py::gil_scoped_release>())
+        .def("setup_rdma", &Connection::setup_rdma, py::call_guard<py::gil_scoped_release>())
+        .def("check_exist", &Connection::check_exist, py::call_guard<py::gil_scoped_release>())
+        .def("get_match_last_index", &Connection::get_match_last_index,
+             py::call_guard<py::gil_scoped_release>())
+        .def("sync_local", &Connection::sync_local, py::call_guard<py::gil_scoped_release>())
+        .def("sync_rdma", &Connection::sync_rdma, py::call_guard<py::gil_scoped_release>())
+        .def("register_mr", &Connection::register_mr, py::arg("ptr"), py::arg("size"),
+             py::arg("device") = -1, py::call_guard<py::gil_scoped_release>())
+        .def(
+            "allocate_rdma",
+            [](Connection& c, const std::vector<std::string>& keys, int block_size) {
+                std::vector<RemoteBlock> out;
+                {
+                    py::gil_scoped_release rel;
+                    if (c.allocate(keys, block_size, out) != 0) out.clear();
+                }
+                return blocks_to_array(std::move(out));
+            },
+            "Reserve pool blocks for keys; returns a structured array (rkey, gen, remote_addr), "
+            "empty on failure")
+        .def(
+            "allocate_rdma_async",
+            [](Connection& c, const std::vector<std::string>& keys, int block_size,
+               py::function cb) {
+                auto holder = std::make_shared<py::function>(std::move(cb));
+                c.allocate_async(keys, block_size, [holder](std::vector<RemoteBlock> v) {
+                    py::gil_scoped_acquire acq;
+                    (*holder)(blocks_to_array(std::move(v)));
+                    holder->release().dec_ref();
+                });
+            })
+        .def(
+            "w_rdma",
+            [](Connection& c, const std::vector<uint64_t>& offsets, int block_size,
+               const py::object& remote_blocks, uint64_t base_ptr, int device, uint64_t stream) {
+                std::vector<RemoteBlock> rb = blocks_from_py(remote_blocks);
+                py::gil_scoped_release rel;
+                return c.w_rdma(offsets, block_size, rb.data(), rb.size(), base_ptr, device,
+                                stream);
+            },
+            py::arg("offsets"), py::arg("block_size"), py::arg("remote_blocks"),
+            py::arg("base_ptr"), py::arg("device") = -1, py::arg("stream") = 0)
+        .def(
+            "w_rdma_async",
+            [](Connection& c, const std::vector<uint64_t>& offsets, int block_size,
+               const py::object& remote_blocks, uint64_t base_ptr, py::function cb, int device,
+               uint64_t stream) {
+                std::vector<RemoteBlock> rb = blocks_from_py(remote_blocks);
+                auto holder = std::make_shared<py::function>(std::move(cb));
+                py::gil_scoped_release rel;
+                return c.w_rdma_async(offsets, block_size, rb.data(), rb.size(), base_ptr, device,
+                                      stream, [holder](int status) {
+                                          py::gil_scoped_acquire acq;
+                                          (*holder)(status);
+                                          holder->release().dec_ref();
+                                      });
+            },
+            py::arg("offsets"), py::arg("block_size"), py::arg("remote_blocks"),
+            py::arg("base_ptr"), py::arg("callback"), py::arg("device") = -1,
+            py::arg("stream") = 0)
+        .def(
+            "r_rdma",
+            [](Connection& c, const std::vector<std::pair<std::string, uint64_t>>& blocks,
+               int block_size, uint64_t base_ptr, int device, uint64_t stream) {
+                py::gil_scoped_release rel;
+                return c.r_rdma(key_offsets(blocks), block_size, base_ptr, device, stream);
+            },
+            py::arg("blocks"), py::arg("block_size"), py::arg("base_ptr"),
+            py::arg("device") = -1, py::arg("stream") = 0)
+        .def(
+            "r_rdma_async",
+            [](Connection& c, const std::vector<std::pair<std::string, uint64_t>>& blocks,
+               int block_size, uint64_t base_ptr, py::function cb, int device, uint64_t stream) {
+                auto holder = std::make_shared<py::function>(std::move(cb));
+                py::gil_scoped_release rel;
+                return c.r_rdma_async(key_offsets(blocks), block_size, base_ptr, device, stream,
+                                      [holder](int status) {
+                                          py::gil_scoped_acquire acq;
+                                          (*holder)(status);
+                                          holder->release().dec_ref();
+                                      });
+            },
+            py::arg("blocks"), py::arg("block_size"), py::arg("base_ptr"), py::arg("callback"),
+            py::arg("device") = -1, py::arg("stream") = 0)
+        .def(
+            "rw_local",
+            [](Connection& c, const std::string& op,
+               const std::vector<std::pair<std::string, uint64_t>>& blocks, int block_size,
+               uint64_t base_ptr, int device, uint64_t stream) {
+                py::gil_scoped_release rel;
+                return c.rw_local(op.empty() ? 0 : op[0], key_offsets(blocks), block_size,
+                                  base_ptr, device, stream);
+            },
+            py::arg("op"), py::arg("blocks"), py::arg("block_size"), py::arg("base_ptr"),
+            py::arg("device") = -1, py::arg("stream") = 0)
+        .def("set_copy_variant", &Connection::set_copy_variant)
+        .def("set_max_ctas", &Connection::set_max_ctas)
+        .def("set_device_lookup", &Connection::set_device_lookup)
+        .def("device_lookup", &Connection::device_lookup)
+        .def("server_has_hbm", &Connection::server_has_hbm)
+        .def("last_error", &Connection::last_error)
+        .def("segments",
+             [](Connection& c) {
+                 py::list l;
+                 for (auto& s : c.segments()) l.append(segment_dict(s));
+                 return l;
+             })
+        .def("stats", [](Connection& c) {
+            const ClientStats s = c.stats();
+            py::dict d;
+            d["kernel_launches"] = s.kernel_launches;
+            d["bytes_written"] = s.bytes_written;
+            d["bytes_read"] = s.bytes_read;
+            d["ctrl_requests"] = s.ctrl_requests;
+            d["host_copies"] = s.host_copies;
+            return d;
+        });
+
+    // ------------------------------------------------------------ server
+    py::class_<Server, std::shared_ptr<Server>>(m, "Server")
+        .def(py::init<const ServerConfig&>())
+        .def(
+            "start",
+            [](Server& s) {
+                std::string err;
+                int rc;
+                {
+                    py::gil_scoped_release rel;
+                    rc = s.start(&err);
+                }
+                if (rc != 0) throw std::runtime_error("server start failed: " + err);
+                return s.port();
+            })
+        .def("stop", &Server::stop, py::call_guard<py::gil_scoped_release>())
+        .def("port", &Server::port)
+        .def("running", &Server::running)
+        .def("kvmap_len", &Server::kvmap_len, py::call_guard<py::gil_scoped_release>())
+        .def("purge", &Server::purge, py::call_guard<py::gil_scoped_release>())
+        .def("inject_drop_after", &Server::inject_drop_after)
+        .def("stats", [](Server& s) { return stats_dict(s.stats()); })
+        .def("segments", [](Server& s) {
+            py::list l;
+            for (auto& i : s.segments()) l.append(segment_dict(i));
+            return l;
+        });
+
+    m.def(
+        "register_server",
+        [](uint64_t /*loop_ptr*/, const ServerConfig& cfg) {
+            std::lock_guard<std::mutex> lk(g_server_mu);
+            if (g_server && g_server->running()) return 0;
+            g_server = std::make_unique<Server>(cfg);
+            std::string err;
+            int rc;
+            {
+                py::gil_scoped_release rel;
+                rc = g_server->start(&err);
+            }
+            if (rc != 0) {
+                LOG_ERROR("register_server: %s", err.c_str());
+                g_server.reset();
+                return -1;
+            }
+            return 0;
+        },
+        "Start the process-wide store server (reactor thread); the event-loop pointer of the "
+        "reference API is accepted and ignored");
+    m.def("stop_server", [] {
+        std::lock_guard<std::mutex> lk(g_server_mu);
+        if (g_server) {
+            py::gil_scoped_release rel;
+            g_server->stop();
+        }
+        g_server.reset();
+    });
+    m.def("purge_kv_map", [] {
+        std::lock_guard<std::mutex> lk(g_server_mu);
+        if (g_server) g_server->purge();
+    });
+    m.def("get_kvmap_len", [] {
+        std::lock_guard<std::mutex> lk(g_server_mu);
+        return g_server ? g_server->kvmap_len() : size_t(0);
+    });
+    m.def("server_stats", [] {
+        std::lock_guard<std::mutex> lk(g_server_mu);
+        return g_server ? stats_dict(g_server->stats()) : py::dict();
+    });
+    m.def("server_port", [] {
+        std::lock_guard<std::mutex> lk(g_server_mu);
+        return g_server ? g_server->port() : 0;
+    });
+
+    m.def("log_msg", &log_msg);
+    m.def("set_log_level", [](const std::string& l) { set_log_level(l); });
+    m.def("cuda_available", &fabric::cuda_available);
+    m.def("cuda_device_count", &fabric::cuda_device_count);
+
+    // ------------------------------------------------------------ fabric (NVLS)
+    py::class_<fabric::NvlsProbe>(m, "NvlsProbe")
+        .def_readonly("driver_ok", &fabric::NvlsProbe::driver_ok)
+        .def_readonly("multicast_supported", &fabric::NvlsProbe::multicast_supported)
+        .def_readonly("vmm_supported", &fabric::NvlsProbe::vmm_supported)
+        .def_readonly("posix_fd_supported", &fabric::NvlsProbe::posix_fd_supported)
+        .def_readonly("fabric_handle_supported", &fabric::NvlsProbe::fabric_handle_supported)
+        .def_readonly("granularity", &fabric::NvlsProbe::granularity)
+        .def_readonly("detail", &fabric::NvlsProbe::detail);
+    m.def("nvls_probe", &fabric::nvls_probe, py::arg("device") = 0);
+    py::class_<fabric::NvlsGroup, std::shared_ptr<fabric::NvlsGroup>>(m, "NvlsGroup")
+        .def_static(
+            "create",
+            [](const std::vector<int>& devices, size_t bytes) {
+                std::string err;
+                auto g = fabric::NvlsGroup::create(devices, bytes, &err);
+                if (!g) throw std::runtime_error("NVLS group: " + err);
+                return g;
+            },
+            "Single-process multicast group over `devices` with `bytes` of replica per GPU")
+        .def("mc_ptr", &fabric::NvlsGroup::mc_ptr, "multicast VA as seen from devices[i]")
+        .def("uc_ptr", &fabric::NvlsGroup::uc_ptr, "local replica VA on devices[i]")
+        .def("bytes", &fabric::NvlsGroup::bytes)
+        .def("size", &fabric::NvlsGroup::size);
+
+    // ------------------------------------------------------------ raw kernel launchers
+    py::module_ k = m.def_submodule("kernels", "raw launchers of the sm_100a kernels");
+    k.attr("COPY_AUTO") = int(kernels::kCopyAuto);
+    k.attr("COPY_LDST") = int(kernels::kCopyLdSt);
+    k.attr("COPY_TMA") = int(kernels::kCopyTma);
+    k.attr("COPY_LDST256") = int(kernels::kCopyLdSt256);
+    k.attr("STAT_MISS") = int(kernels::kStatMiss);
+    k.attr("STAT_PUBLISH_FAIL") = int(kernels::kStatPublishFail);
+    k.attr("STAT_MATCH") = int(kernels::kStatMatch);
+    k.attr("STAT_WORDS") = int(kernels::kStatWords);
+    k.def(
+        "kv_copy",
+        [](uint64_t descs, uint32_t n, uint32_t bytes, int variant, int max_ctas, uint64_t stream,
+           uint64_t recs, uint64_t table, uint64_t table_mask, uint64_t done, uint64_t status,
+           uint64_t align_or) {
+            kernels::CopyLaunch L;
+            L.descs = as_ptr<const kernels::CopyDesc>(descs);
+            L.n = n;
+            L.bytes = bytes;
+            L.align_or = align_or;
+            L.recs = as_ptr<const kernels::IndexEntry>(recs);
+            L.table = as_ptr<kernels::IndexEntry>(table);
+            L.table_mask = table_mask;
+            L.done = as_ptr<uint32_t>(done);
+            L.status = as_ptr<uint32_t>(status);
+            L.variant = variant;
+            L.max_ctas = max_ctas;
+            const cudaError_t e = kernels::launch_kv_copy(L, as_ptr<CUstream_st>(stream));
+            if (e != cudaSuccess) throw std::runtime_error(cudaGetErrorString(e));
+        },
+        py::arg("descs"), py::arg("n"), py::arg("bytes"), py::arg("variant") = 0,
+        py::arg("max_ctas") = 0, py::arg("stream") = 0, py::arg("recs") = 0,
+        py::arg("table") = 0, py::arg("table_mask") = 0, py::arg("done") = 0,
+        py::arg("status") = 0, py::arg("align_or") = 0);
+    k.def(
+        "index_lookup",
+        [](uint64_t key_bytes, uint64_t key_off, uint64_t key_len, uint32_t n, uint64_t table,
+           uint64_t table_mask, const std::vector<uint64_t>& seg_base, uint64_t out_descs,
+           uint64_t dst_off, uint64_t dst_base, uint32_t need_bytes, uint64_t present,
+           uint64_t status, uint64_t ticket, bool want_match, uint64_t stream) {
+            kernels::LookupLaunch Q;
+            Q.key_bytes = as_ptr<const uint8_t>(key_bytes);
+            Q.key_off = as_ptr<const uint32_t>(key_off);
+            Q.key_len = as_ptr<const uint32_t>(key_len);
+            Q.n = n;
+            Q.table = as_ptr<const kernels::IndexEntry>(table);
+            Q.table_mask = table_mask;
+            Q.nsegs = uint32_t(std::min<size_t>(seg_base.size(), kernels::LookupLaunch::kMaxSegs));
+            for (uint32_t i = 0; i < Q.nsegs; ++i) Q.seg_base[i] = seg_base[i];
+            Q.out_descs = as_ptr<kernels::CopyDesc>(out_descs);
+            Q.dst_off = as_ptr<const uint64_t>(dst_off);
+            Q.dst_base = dst_base;
+            Q.need_bytes = need_bytes;
+            Q.present = as_ptr<uint32_t>(present);
+            Q.status = as_ptr<uint32_t>(status);
+            Q.ticket = as_ptr<uint32_t>(ticket);
+            Q.want_match = want_match;
+            const cudaError_t e = kernels::launch_index_lookup(Q, as_ptr<CUstream_st>(stream));
+            if (e != cudaSuccess) throw std::runtime_error(cudaGetErrorString(e));
+        },
+        py::arg("key_bytes"), py::arg("key_off"), py::arg("key_len"), py::arg("n"),
+        py::arg("table"), py::arg("table_mask"), py::arg("seg_base") = std::vector<uint64_t>(),
+        py::arg("out_descs") = 0, py::arg("dst_off") = 0, py::arg("dst_base") = 0,
+        py::arg("need_bytes") = 0, py::arg("present") = 0, py::arg("status") = 0,
+        py::arg("ticket") = 0, py::arg("want_match") = false, py::arg("stream") = 0);
+    auto fp8 = [](bool write) {
+        return [write](uint64_t descs, uint32_t n, uint32_t elems, uint32_t group, int max_ctas,
+                       uint64_t stream, uint64_t recs, uint64_t table, uint64_t table_mask,
+                       uint64_t done, uint64_t status) {
+            kernels::Fp8Launch L;
+            L.descs = as_ptr<const kernels::CopyDesc>(descs);
+            L.n = n;
+            L.elems = elems;
+            L.group = group;
+            L.recs = as_ptr<const kernels::IndexEntry>(recs);
+            L.table = as_ptr<kernels::IndexEntry>(table);
+            L.table_mask = table_mask;
+            L.done = as_ptr<uint32_t>(done);
+            L.status = as_ptr<uint32_t>(status);
+            L.max_ctas = max_ctas;
+            const cudaError_t e = write
+                                      ? kernels::launch_kv_write_fp8(L, as_ptr<CUstream_st>(stream))
+                                      : kernels::launch_kv_read_fp8(L, as_ptr<CUstream_st>(stream));
+            if (e != cudaSuccess) throw std::runtime_error(cudaGetErrorString(e));
+        };
+    };
+    k.def("kv_write_fp8", fp8(true), py::arg("descs"), py::arg("n"), py::arg("elems"),
+          py::arg("group") = 128, py::arg("max_ctas") = 0, py::arg("stream") = 0,
+          py::arg("recs") = 0, py::arg("table") = 0, py::arg("table_mask") = 0,
+          py::arg("done") = 0, py::arg("status") = 0);
+    k.def("kv_read_fp8", fp8(false), py::arg("descs"), py::arg("n"), py::arg("elems"),
+          py::arg("group") = 128, py::arg("max_ctas") = 0, py::arg("stream") = 0,
+          py::arg("recs") = 0, py::arg("table") = 0, py::arg("table_mask") = 0,
+          py::arg("done") = 0, py::arg("status") = 0);
+    k.def("fp8_block_bytes", &kernels::fp8_block_bytes);
+    k.def(
+        "kv_bcast_nvls",
+        [](uint64_t descs, uint32_t n, uint32_t bytes, int max_ctas, uint64_t stream) {
+            kernels::BcastLaunch L;
+            L.descs = as_ptr<const kernels::CopyDesc>(descs);
+            L.n = n;
+            L.bytes = bytes;
+            L.max_ctas = max_ctas;
+            const cudaError_t e = kernels::launch_kv_bcast_nvls(L, as_ptr<CUstream_st>(stream));
+            if (e != cudaSuccess) throw std::runtime_error(cudaGetErrorString(e));
+        },
+        py::arg("descs"), py::arg("n"), py::arg("bytes"), py::arg("max_ctas") = 0,
+        py::arg("stream") = 0);
+
+    // ------------------------------------------------------------ unit-test access to the core
+    py::module_ t = m.def_submodule("testing", "wire codec, allocator and hash for unit tests");
+    t.def("hash_key", [](py::bytes key) {
+        const std::string s = key;
+        const KeyHash h = hash_key(reinterpret_cast<const uint8_t*>(s.data()), s.size());
+        return py::make_tuple(h.h1, h.h2);
+    });
+    t.def("header_size", [] { return sizeof(Header); });
+    t.def("conn_info_size", [] { return sizeof(ConnInfo); });
+    t.def("segment_info_size", [] { return sizeof(SegmentInfo); });
+    t.def("encode_remote_meta",
+          [](const std::vector<std::string>& keys, int block_size, uint32_t rkey,
+             const std::vector<uint64_t>& addrs, const std::string& op, int hint) {
+              std::vector<std::string_view> kv(keys.begin(), keys.end());
+              std::vector<uint8_t> buf(remote_meta_bound(kv, addrs.size()));
+              fb::Builder b(buf.data(), buf.size());
+              encode_remote_meta(b, kv, block_size, rkey, addrs.data(), addrs.size(),
+                                 op.empty() ? 0 : op[0], hint);
+              return py::bytes(reinterpret_cast<const char*>(b.data()), b.size());
+          },
+          py::arg("keys"), py::arg("block_size"), py::arg("rkey"), py::arg("addrs"),
+          py::arg("op"), py::arg("hint") = -1);
+    t.def("decode_remote_meta", [](py::bytes data) {
+        const std::string s = data;
+        RemoteMetaRequest r = decode_remote_meta(s.data(), s.size());
+        py::dict d;
+        py::list keys;
+        for (auto k : r.keys) keys.append(py::bytes(k.data(), k.size()));
+        d["keys"] = keys;
+        d["block_size"] = r.block_size;
+        d["rkey"] = r.rkey;
+        d["remote_addrs"] = r.remote_addrs;
+        d["op"] = std::string(1, char(r.op));
+        d["hint"] = r.hint;
+        return d;
+    });
+    t.def("encode_allocate_response", [](const std::vector<std::tuple<uint32_t, uint32_t, uint64_t>>& blocks) {
+        std::vector<RemoteBlock> rb;
+        for (auto& b : blocks) rb.push_back(RemoteBlock{std::get<0>(b), std::get<1>(b), std::get<2>(b)});
+        std::vector<uint8_t> buf((rb.size() * 16 + 64 + 7) & ~size_t(7));
+        fb::Builder b(buf.data(), buf.size());
+        encode_allocate_response(b, rb.data(), rb.size());
+        return py::bytes(reinterpret_cast<const char*>(b.data()), b.size());
+    });
+    t.def("decode_allocate_response", [](py::bytes data) {
+        const std::string s = data;
+        return blocks_to_array(decode_allocate_response(s.data(), s.size()));
+    });
+    t.def("encode_local_meta",
+          [](int device, py::bytes ipc, int block_size,
+             const std::vector<std::pair<std::string, uint64_t>>& blocks) {
+              const std::string ipc_s = ipc;
+              std::vector<LocalBlock> lb;
+              for (auto& b : blocks) lb.push_back(LocalBlock{b.first, b.second});
+              std::vector<uint8_t> buf(local_meta_bound(lb) + ((ipc_s.size() + 15) & ~size_t(7)));
+              fb::Builder b(buf.data(), buf.size());
+              encode_local_meta(b, device, ipc_s, block_size, lb);
+              return py::bytes(reinterpret_cast<const char*>(b.data()), b.size());
+          });
+    t.def("decode_local_meta", [](py::bytes data) {
+        const std::string s = data;
+        LocalMetaRequest r = decode_local_meta(s.data(), s.size());
+        py::dict d;
+        d["device"] = r.device;
+        d["ipc_handle"] = py::bytes(r.ipc_handle.data(), r.ipc_handle.size());
+        d["block_size"] = r.block_size;
+        py::list blocks;
+        for (auto& b : r.blocks)
+            blocks.append(py::make_tuple(py::bytes(b.key.data(), b.key.size()), b.offset));
+        d["blocks"] = blocks;
+        return d;
+    });
+    t.def("encode_match_request", [](const std::vector<std::string>& keys) {
+        std::vector<std::string_view> kv(keys.begin(), keys.end());
+        std::vector<uint8_t> buf(remote_meta_bound(kv, 0));
+        fb::Builder b(buf.data(), buf.size());
+        encode_match_request(b, kv);
+        return py::bytes(reinterpret_cast<const char*>(b.data()), b.size());
+    });
+    t.def("decode_match_request", [](py::bytes data) {
+        const std::string s = data;
+        py::list keys;
+        for (auto k : decode_match_request(s.data(), s.size())) keys.append(py::bytes(k.data(), k.size()));
+        return keys;
+    });
+
+    py::class_<MemoryPool>(t, "MemoryPool")
+        .def(py::init<size_t, size_t, int>(), py::arg("pool_bytes"), py::arg("granule"),
+             py::arg("device") = -1)
+        .def("allocate", &MemoryPool::allocate)
+        .def("allocate_n",
+             [](MemoryPool& p, size_t size, size_t n) -> py::object {
+                 std::vector<uint64_t> out;
+                 if (!p.allocate_n(size, n, out)) return py::none();
+                 return py::cast(out);
+             })
+        .def("deallocate", &MemoryPool::deallocate)
+        .def("used_blocks", &MemoryPool::used_blocks)
+        .def("total_blocks", &MemoryPool::total_blocks)
+        .def("usage", &MemoryPool::usage);
+    py::class_<MM>(t, "MM")
+        .def(py::init<>())
+        .def("add_pool", &MM::add_pool)
+        .def("allocate",
+             [](MM& mm, size_t size, size_t n, int hint) -> py::object {
+                 std::vector<Allocation> out;
+                 if (!mm.allocate(size, n, hint, out)) return py::none();
+                 py::list l;
+                 for (auto& a : out) l.append(py::make_tuple(a.seg, a.offset));
+                 return l;
+             })
+        .def("deallocate", &MM::deallocate)
+        .def("need_extend", &MM::need_extend)
+        .def("used_bytes", &MM::used_bytes)
+        .def("total_bytes", &MM::total_bytes);
+}
