@@ -353,6 +353,20 @@ PYBIND11_MODULE(_infinistore, m) {
     m.def("log_msg", &log_msg);
     m.def("set_log_level", [](const std::string& l) { set_log_level(l); });
     m.def("cuda_available", &fabric::cuda_available);
+    m.def(
+        "enable_peer_access",
+        [](int device, int peer) {
+            int prev = -1, can = 0;
+            cudaGetDevice(&prev);
+            cudaDeviceCanAccessPeer(&can, device, peer);
+            if (!can) return false;
+            cudaSetDevice(device);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+            (void)cudaGetLastError();
+            if (prev >= 0) cudaSetDevice(prev);
+            return e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
+        },
+        "Let kernels running on `device` address memory of `peer` (single-process use)");
     m.def("cuda_device_count", &fabric::cuda_device_count);
 
     // ------------------------------------------------------------ fabric (NVLS)

@@ -1,0 +1,6 @@
+"""Alias of infinistore_b200.server (see infinistore/__init__.py)."""
+from infinistore_b200.server import *  # noqa: F401,F403
+from infinistore_b200.server import main  # noqa: F401
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,561 @@
+"""Python API of the B200-native KV-cache store.
+
+Public names and call signatures follow the reference package so that callers can switch
+packages without code changes (reference: infinistore/lib.py:21-707): ``ClientConfig``,
+``ServerConfig``, ``InfinityConnection`` (``connect``, ``register_mr``, ``allocate_rdma``,
+``rdma_write_cache``, ``read_cache`` / ``rdma_read_cache``, ``local_gpu_write_cache``,
+``sync``, ``check_exist``, ``get_match_last_index`` and the ``*_async`` variants),
+``Logger``, ``DisableTorchCaching``, ``check_supported``, ``register_server``,
+``purge_kv_map``, ``get_kvmap_len``.
+
+What differs is the substrate.  ``TYPE_RDMA`` here means "one-sided remote access over the
+NVLink fabric": the server's block pool is HBM on a pool GPU, mapped into the client
+process, and ``rdma_write_cache`` / ``read_cache`` launch sm_100a kernels on the client's
+GPU that move the whole batch of pages with peer loads/stores and publish the commit
+in-band.  ``dev_name`` / ``ib_port`` / ``link_type`` are accepted for compatibility and
+ignored.  Units are the reference's: offsets and page sizes in ELEMENTS for the
+read/write calls, BYTES for ``allocate_rdma`` (reference: infinistore/lib.py:379,685-707).
+"""
+from __future__ import annotations
+
+import asyncio
+import os
+import time
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _infinistore
+
+# connection types (reference: infinistore/lib.py:13-18)
+TYPE_LOCAL_GPU = "LOCAL_GPU"
+TYPE_RDMA = "RDMA"
+LINK_ETHERNET = "Ethernet"
+LINK_IB = "IB"
+
+_LOG_LEVELS = ("error", "debug", "info", "warning")
+_CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy handle: torch's default stream has handle 0
+
+
+class ClientConfig(_infinistore.ClientConfig):
+    """Client configuration.
+
+    Reference kwargs (infinistore/lib.py:21-56): connection_type, host_addr, dev_name,
+    ib_port, link_type, service_port, log_level (env INFINISTORE_LOG_LEVEL overrides).
+    Fabric extensions: ``device`` (CUDA ordinal used when a host tensor has to be moved by a
+    kernel; default: first GPU touched), ``timeout_ms`` (control-plane deadline),
+    ``pool_hint`` (preferred pool GPU for allocations), ``device_lookup`` (resolve keys in
+    the HBM index with a kernel instead of asking the server), ``copy_variant``
+    ("auto" | "ldst" | "tma" | "ldst256") and ``max_ctas`` (cap on the copy grid).
+    """
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.connection_type = kwargs.get("connection_type", None)
+        self.host_addr = kwargs.get("host_addr", None) or ""
+        self.dev_name = kwargs.get("dev_name", "mlx5_1")
+        self.ib_port = kwargs.get("ib_port", 1)
+        self.link_type = kwargs.get("link_type", "IB")
+        self.service_port = kwargs.get("service_port", None) or 0
+        if "INFINISTORE_LOG_LEVEL" in os.environ:
+            self.log_level = os.environ["INFINISTORE_LOG_LEVEL"]
+        else:
+            self.log_level = kwargs.get("log_level", "warning")
+        self.device = kwargs.get("device", -1)
+        self.timeout_ms = kwargs.get("timeout_ms", 10000)
+        self.pool_hint = kwargs.get("pool_hint", -1)
+        self.device_lookup = kwargs.get("device_lookup", False)
+        self.copy_variant = kwargs.get("copy_variant", "auto")
+        self.max_ctas = kwargs.get("max_ctas", 0)
+
+    def __repr__(self):
+        return (
+            f"ClientConfig(service_port={self.service_port}, log_level='{self.log_level}', "
+            f"host_addr='{self.host_addr}', connection_type='{self.connection_type}', "
+            f"dev_name='{self.dev_name}', ib_port={self.ib_port}, link_type='{self.link_type}', "
+            f"device={self.device}, device_lookup={self.device_lookup})"
+        )
+
+    def verify(self):
+        if self.connection_type not in [TYPE_LOCAL_GPU, TYPE_RDMA]:
+            raise Exception("Invalid connection type")
+        if self.host_addr == "":
+            raise Exception("Host address is empty")
+        if self.service_port == 0:
+            raise Exception("Service port is 0")
+        if not 0 < self.service_port < 65536:
+            raise Exception("Service port must be in 1..65535")
+        if self.log_level not in _LOG_LEVELS:
+            raise Exception("log level should be error, debug, info or warning")
+        if self.ib_port < 1:
+            raise Exception("ib port of device should be greater than 0")
+        if self.connection_type == TYPE_RDMA and self.link_type not in ["IB", "Ethernet"]:
+            raise Exception("link type should be IB or Ethernet for RDMA connection")
+        if self.copy_variant not in _COPY_VARIANTS:
+            raise Exception(f"copy_variant should be one of {sorted(_COPY_VARIANTS)}")
+
+
+_COPY_VARIANTS = {
+    "auto": _infinistore.kernels.COPY_AUTO,
+    "ldst": _infinistore.kernels.COPY_LDST,
+    "tma": _infinistore.kernels.COPY_TMA,
+    "ldst256": _infinistore.kernels.COPY_LDST256,
+}
+
+
+class ServerConfig(_infinistore.ServerConfig):
+    """Server configuration.
+
+    Reference kwargs (infinistore/lib.py:76-128): manage_port, service_port, log_level,
+    dev_name, ib_port, link_type, prealloc_size (GB), minimal_allocate_size (KB),
+    num_stream (deprecated), auto_increase.  Fabric extensions: ``host`` (listen address,
+    honoured here), ``pool_backend`` ("auto" | "hbm" | "host"), ``pool_devices`` (CUDA
+    ordinals that each host one pool segment), ``extend_size`` (GB per auto-increase step),
+    ``prealloc_bytes`` (exact pool size, for tests), ``index_slots``.
+    """
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.manage_port = kwargs.get("manage_port", 0)
+        self.service_port = kwargs.get("service_port", 0)
+        self.log_level = kwargs.get("log_level", "warning")
+        self.dev_name = kwargs.get("dev_name", "mlx5_1")
+        self.ib_port = kwargs.get("ib_port", 1)
+        self.link_type = kwargs.get("link_type", "IB")
+        self.prealloc_size = kwargs.get("prealloc_size", 16)
+        self.minimal_allocate_size = kwargs.get("minimal_allocate_size", 64)
+        self.num_stream = kwargs.get("num_stream", 1)
+        self.auto_increase = kwargs.get("auto_increase", False)
+        self.host = kwargs.get("host", "0.0.0.0")
+        self.pool_backend = kwargs.get("pool_backend", "auto")
+        self.pool_devices = list(kwargs.get("pool_devices", []) or [])
+        self.extend_size = kwargs.get("extend_size", 10)
+        self.prealloc_bytes = kwargs.get("prealloc_bytes", 0)
+        self.index_slots = kwargs.get("index_slots", 0)
+
+    def __repr__(self):
+        return (
+            f"ServerConfig: service_port={self.service_port}, manage_port={self.manage_port}, "
+            f"log_level='{self.log_level}', dev_name='{self.dev_name}', ib_port={self.ib_port}, "
+            f"link_type='{self.link_type}', prealloc_size={self.prealloc_size}, "
+            f"minimal_allocate_size={self.minimal_allocate_size}, num_stream={self.num_stream}, "
+            f"auto_increase={self.auto_increase}, host='{self.host}', "
+            f"pool_backend='{self.pool_backend}', pool_devices={list(self.pool_devices)}"
+        )
+
+    def verify(self):
+        if self.service_port == 0:
+            raise Exception("Service port is 0")
+        if self.manage_port == 0:
+            raise Exception("Manage port is 0")
+        if not 0 < self.service_port < 65536 or not 0 < self.manage_port < 65536:
+            raise Exception("ports must be in 1..65535")
+        if self.log_level not in _LOG_LEVELS:
+            raise Exception("log level should be error, debug, info or warning")
+        if self.ib_port < 1:
+            raise Exception("ib port of device should be greater than 0")
+        if self.link_type not in ["IB", "Ethernet"]:
+            raise Exception("link type should be IB or Ethernet")
+        if self.minimal_allocate_size < 16:
+            raise Exception("minimal allocate size should be greater than 16")
+        if self.pool_backend not in ("auto", "hbm", "host"):
+            raise Exception("pool backend should be auto, hbm or host")
+
+
+class Logger:
+    """Thin wrappers over the native logger (reference: infinistore/lib.py:131-150)."""
+
+    @staticmethod
+    def info(msg):
+        _infinistore.log_msg("info", str(msg))
+
+    @staticmethod
+    def debug(msg):
+        _infinistore.log_msg("debug", str(msg))
+
+    @staticmethod
+    def error(msg):
+        _infinistore.log_msg("error", str(msg))
+
+    @staticmethod
+    def warn(msg):
+        _infinistore.log_msg("warning", str(msg))
+
+    @staticmethod
+    def set_log_level(level):
+        _infinistore.set_log_level(level)
+
+
+def get_kvmap_len():
+    """Number of keys in the in-process server's index (reference: lib.py:153-165)."""
+    return _infinistore.get_kvmap_len()
+
+
+def purge_kv_map():
+    """Drop every key of the in-process server; pool space returns once the last
+    in-flight reference is gone (reference: lib.py:167-178)."""
+    return _infinistore.purge_kv_map()
+
+
+def register_server(loop, config: ServerConfig):
+    """Start the store server inside this process.
+
+    The reference hands the uvloop ``uv_loop_t*`` to its C++ libuv server
+    (infinistore/lib.py:179-205).  Here the control plane is an epoll reactor on its own
+    native thread, so ``loop`` is accepted for signature compatibility and not used; the
+    call returns once the pool exists and the port is listening.
+    """
+    if _infinistore.register_server(0, config) < 0:
+        raise Exception("Failed to register server")
+
+
+def stop_server():
+    _infinistore.stop_server()
+
+
+def server_stats():
+    return _infinistore.server_stats()
+
+
+def _kernel_modules():
+    modules = set()
+    try:
+        with open("/proc/modules", "r") as f:
+            for line in f:
+                modules.add(line.split(" ", 1)[0])
+    except IOError:
+        pass
+    return modules
+
+
+def check_supported(raise_on_missing_gpu: bool = False):
+    """Environment check.
+
+    The reference verifies ``nv_peer_mem`` and an active ibverbs port
+    (infinistore/lib.py:208-251).  The NVLink fabric needs neither; what matters is CUDA,
+    peer access between the GPUs and (for broadcast) NVLS multicast.  Returns a dict.
+    """
+    info = {"cuda": _infinistore.cuda_available(), "devices": _infinistore.cuda_device_count(),
+            "p2p_missing": [], "nvls": False}
+    if not info["cuda"]:
+        msg = "no CUDA device visible: the store will use the host-memory pool backend"
+        if raise_on_missing_gpu:
+            raise Exception(msg)
+        Logger.warn(msg)
+        return info
+    n = info["devices"]
+    for i in range(n):
+        for j in range(n):
+            if i != j and not torch.cuda.can_device_access_peer(i, j):
+                info["p2p_missing"].append((i, j))
+    if info["p2p_missing"]:
+        Logger.warn(f"peer access NOT supported between {info['p2p_missing']}")
+    try:
+        probe = _infinistore.nvls_probe(0)
+        info["nvls"] = bool(probe.multicast_supported)
+        info["vmm"] = bool(probe.vmm_supported)
+    except Exception:  # pragma: no cover
+        pass
+    return info
+
+
+class DisableTorchCaching:
+    """Context manager setting PYTORCH_NO_CUDA_MEMORY_CACHING=1.
+
+    The reference needs it for LOCAL_GPU because its server maps the client's allocation
+    through a CUDA IPC handle, which covers whole cudaMalloc allocations
+    (infinistore/lib.py:254-274).  Here the CLIENT maps the SERVER's pool, so caller
+    tensors can come from the caching allocator; the class is kept (and harmless) for
+    source compatibility.
+    """
+
+    def __enter__(self):
+        self._prev = os.environ.get("PYTORCH_NO_CUDA_MEMORY_CACHING")
+        os.environ["PYTORCH_NO_CUDA_MEMORY_CACHING"] = "1"
+        return self
+
+    def __exit__(self, exc_type, exc_value, traceback):
+        if self._prev is None:
+            os.environ.pop("PYTORCH_NO_CUDA_MEMORY_CACHING", None)
+        else:
+            os.environ["PYTORCH_NO_CUDA_MEMORY_CACHING"] = self._prev
+        return
+
+
+def _device_of(cache: torch.Tensor) -> int:
+    return cache.device.index if cache.device.type == "cuda" else -1
+
+
+def _stream_of(cache: torch.Tensor, stream) -> int:
+    """cudaStream_t handle to launch on.  "current" = torch's current stream of the tensor's
+    device (kernels are ordered after the work that produced the pages); None = the
+    connection's own stream (for overlap with the model, as in the layer-wise demo)."""
+    if cache.device.type != "cuda" or stream is None:
+        return 0
+    if stream == "current":
+        handle = torch.cuda.current_stream(cache.device).cuda_stream
+    elif isinstance(stream, torch.cuda.Stream):
+        handle = stream.cuda_stream
+    else:
+        handle = int(stream)
+    return handle if handle != 0 else _CUDA_STREAM_LEGACY
+
+
+class InfinityConnection:
+    """Connection to a store server (reference: infinistore/lib.py:277-707)."""
+
+    OP_R = "R"
+    OP_W = "W"
+    OP_SYNC = "S"
+    OP_RDMA_READ = "A"
+
+    def __init__(self, config: ClientConfig):
+        config.verify()
+        self.conn = _infinistore.Connection()
+        self.local_connected = False
+        self.rdma_connected = False
+        self.config = config
+        Logger.set_log_level(config.log_level)
+
+    # ------------------------------------------------------------------ connect
+    def _apply_options(self):
+        self.conn.set_copy_variant(_COPY_VARIANTS[self.config.copy_variant])
+        self.conn.set_max_ctas(int(self.config.max_ctas))
+        self.conn.set_device_lookup(bool(self.config.device_lookup) and self.conn.server_has_hbm())
+
+    async def connect_async(self):
+        """Connect without blocking the event loop (RDMA type only, as in the reference)."""
+        if self.config.connection_type == TYPE_LOCAL_GPU:
+            raise Exception("Local GPU connection is not supported in async mode")
+        loop = asyncio.get_running_loop()
+
+        def blocking_connect():
+            if self.conn.init_connection(self.config) < 0:
+                raise Exception("Failed to initialize remote connection")
+            if self.conn.setup_rdma(self.config) < 0:
+                raise Exception("Failed to setup RDMA connection")
+            self._apply_options()
+            self.rdma_connected = True
+
+        await loop.run_in_executor(None, blocking_connect)
+
+    def connect(self):
+        if self.local_connected:
+            raise Exception("Already connected to local instance")
+        if self.rdma_connected:
+            raise Exception("Already connected to remote instance")
+        if self.config.connection_type == TYPE_LOCAL_GPU and self.config.host_addr not in (
+            "127.0.0.1",
+            "localhost",
+        ):
+            raise Exception("Local GPU connection must be to localhost")
+        if self.conn.init_connection(self.config) < 0:
+            raise Exception("Failed to initialize remote connection")
+        if self.conn.setup_rdma(self.config) < 0:
+            raise Exception("Failed to setup RDMA connection")
+        self._apply_options()
+        if self.config.connection_type == TYPE_LOCAL_GPU:
+            self.local_connected = True
+        else:
+            self.rdma_connected = True
+
+    def close(self):
+        self.conn.close()
+        self.local_connected = False
+        self.rdma_connected = False
+
+    # ------------------------------------------------------------------ writes
+    def local_gpu_write_cache(self, cache: torch.Tensor, blocks: List[Tuple[str, int]],
+                              page_size: int, stream="current"):
+        """Allocate + write + commit pages of a CUDA tensor in one call.
+
+        ``blocks`` is a list of (key, offset_in_elements); ``page_size`` is in elements.
+        Returns once the kernel is enqueued; ``sync()`` is the completion barrier.
+        """
+        self._verify(cache)
+        assert self.local_connected
+        es = cache.element_size()
+        blocks_in_bytes = [(key, offset * es) for key, offset in blocks]
+        ret = self.conn.rw_local(self.OP_W, blocks_in_bytes, page_size * es, cache.data_ptr(),
+                                 _device_of(cache), _stream_of(cache, stream))
+        if ret < 0:
+            raise Exception(f"Failed to write to infinistore, ret = {ret}")
+        return 0
+
+    def rdma_write_cache(self, cache: torch.Tensor, offsets: List[int], page_size,
+                         remote_blocks, stream="current"):
+        """Write pages of ``cache`` into previously allocated remote blocks.
+
+        ``offsets`` / ``page_size`` in elements; ``remote_blocks`` is (a slice of) what
+        ``allocate_rdma`` returned.  Blocks the server marked as already existing are
+        skipped (first writer wins).
+        """
+        assert self.rdma_connected
+        self._verify(cache)
+        es = cache.element_size()
+        ret = self.conn.w_rdma([o * es for o in offsets], page_size * es, remote_blocks,
+                               cache.data_ptr(), _device_of(cache), _stream_of(cache, stream))
+        if ret < 0:
+            raise Exception(f"Failed to write to infinistore, ret = {ret}")
+        return 0
+
+    async def rdma_write_cache_async(self, cache: torch.Tensor, offsets: List[int], page_size,
+                                     remote_blocks, stream="current"):
+        if not self.rdma_connected:
+            raise Exception("this function is only valid for connected rdma")
+        self._verify(cache)
+        es = cache.element_size()
+        loop = asyncio.get_running_loop()
+        future = loop.create_future()
+
+        def _callback(status):
+            # runs on the connection's completion thread
+            loop.call_soon_threadsafe(future.set_result, status)
+
+        ret = self.conn.w_rdma_async([o * es for o in offsets], page_size * es, remote_blocks,
+                                     cache.data_ptr(), _callback, _device_of(cache),
+                                     _stream_of(cache, stream))
+        status = await future
+        if ret < 0 or status < 0:
+            raise Exception(f"Failed to write to infinistore, ret = {min(ret, status)}")
+        return 0
+
+    # ------------------------------------------------------------------ reads
+    def read_cache(self, cache: torch.Tensor, blocks: List[Tuple[str, int]], page_size: int,
+                   stream="current"):
+        """Read pages into ``cache``.  ``blocks`` = [(key, offset_in_elements)].
+
+        Raises if a key is missing or not committed (with ``device_lookup`` the miss is
+        detected on the GPU and reported by ``sync()``).
+        """
+        self._verify(cache)
+        es = cache.element_size()
+        blocks_in_bytes = [(key, offset * es) for key, offset in blocks]
+        if self.local_connected:
+            ret = self.conn.rw_local(self.OP_R, blocks_in_bytes, page_size * es, cache.data_ptr(),
+                                     _device_of(cache), _stream_of(cache, stream))
+        elif self.rdma_connected:
+            ret = self.conn.r_rdma(blocks_in_bytes, page_size * es, cache.data_ptr(),
+                                   _device_of(cache), _stream_of(cache, stream))
+        else:
+            raise Exception("Not connected to any instance")
+        if ret < 0:
+            raise Exception(f"Failed to read to infinistore, ret = {ret}")
+
+    async def read_cache_async(self, cache: torch.Tensor, blocks: List[Tuple[str, int]],
+                               page_size: int, stream="current"):
+        if not self.rdma_connected:
+            raise Exception("this function is only valid for connected rdma")
+        self._verify(cache)
+        es = cache.element_size()
+        blocks_in_bytes = [(key, offset * es) for key, offset in blocks]
+        loop = asyncio.get_running_loop()
+        future = loop.create_future()
+
+        def _callback(status):
+            loop.call_soon_threadsafe(future.set_result, status)
+
+        ret = self.conn.r_rdma_async(blocks_in_bytes, page_size * es, cache.data_ptr(), _callback,
+                                     _device_of(cache), _stream_of(cache, stream))
+        status = await future
+        if ret < 0 or status < 0:
+            raise Exception(f"Failed to read to infinistore, ret = {min(ret, status)}")
+        return 0
+
+    # the north-star API list names the read entry points rdma_read_cache*: same functions
+    rdma_read_cache = read_cache
+    rdma_read_cache_async = read_cache_async
+
+    # ------------------------------------------------------------------ barrier / metadata
+    def sync(self):
+        """Completion barrier: every enqueued kernel has finished, commits have reached the
+        server and have been applied (fixes the reference's commit/visibility race)."""
+        if self.local_connected:
+            deadline = time.monotonic() + max(self.config.timeout_ms, 1000) / 1000.0
+            while True:
+                ret = self.conn.sync_local()
+                if ret < 0:
+                    raise Exception(f"Failed to sync to infinistore, ret = {ret}: "
+                                    f"{self.conn.last_error()}")
+                if ret == 0:
+                    return
+                if time.monotonic() > deadline:
+                    raise Exception("Timeout waiting for inflight requests")
+                time.sleep(min(ret * 0.0005, 0.01))
+        elif self.rdma_connected:
+            ret = self.conn.sync_rdma()
+        else:
+            raise Exception("Not connected to any instance")
+        if ret < 0:
+            raise Exception(f"Failed to sync to infinistore, ret = {ret}: "
+                            f"{self.conn.last_error()}")
+        return
+
+    def _verify(self, cache: torch.Tensor):
+        if (not self.rdma_connected) and cache.device.type != "cuda":
+            raise Exception("Tensor must be on CUDA device for local GPU connection")
+        if cache.is_contiguous() is False:
+            raise Exception("Tensor must be contiguous")
+
+    def check_exist(self, key: str):
+        ret = self.conn.check_exist(key)
+        if ret < 0:
+            raise Exception("Failed to check if this key exists")
+        return True if ret == 0 else False
+
+    def get_match_last_index(self, keys: List[str]):
+        """Index of the last key of the longest matching prefix, computed with the
+        reference's exact binary search (src/infinistore.cpp:1092-1108).  Raises when
+        nothing matches."""
+        ret = self.conn.get_match_last_index(keys)
+        if ret < 0:
+            raise Exception("can't find a match")
+        return ret
+
+    def register_mr(self, cache: torch.Tensor):
+        """Register the KV-cache tensor once; pages are then addressed by element offset.
+
+        For CUDA tensors this prepares the per-device launch context; for CPU tensors it
+        pins and maps the memory so kernels can stream it over PCIe.
+        """
+        self._verify(cache)
+        if not self.rdma_connected:
+            raise Exception("this function is only valid for connected rdma")
+        ret = self.conn.register_mr(cache.data_ptr(), cache.numel() * cache.element_size(),
+                                    _device_of(cache))
+        if ret < 0:
+            raise Exception("register memory region failed")
+        return ret
+
+    async def allocate_rdma_async(self, keys: List[str], page_size_in_bytes: int):
+        if not self.rdma_connected:
+            raise Exception("this function is only valid for connected rdma")
+        loop = asyncio.get_running_loop()
+        future = loop.create_future()
+
+        def _callback(remote_addrs):
+            loop.call_soon_threadsafe(future.set_result, remote_addrs)
+
+        self.conn.allocate_rdma_async(keys, page_size_in_bytes, _callback)
+        blocks = await future
+        if len(blocks) == 0:
+            raise Exception("allocate memory failed")
+        return blocks
+
+    def allocate_rdma(self, keys: List[str], page_size_in_bytes: int):
+        """Reserve one pool block per key.  Returns a numpy structured array with fields
+        ``rkey`` (u4 @0), ``gen`` (u4 @4) and ``remote_addr`` (u8 @8), itemsize 16; a
+        (0, 0) entry marks a key that already exists."""
+        if not self.rdma_connected:
+            raise Exception("this function is only valid for connected rdma")
+        ret = self.conn.allocate_rdma(keys, page_size_in_bytes)
+        if len(ret) == 0:
+            raise Exception("allocate memory failed")
+        return ret
+
+    # ------------------------------------------------------------------ introspection
+    def stats(self):
+        return self.conn.stats()
+
+    def segments(self):
+        return self.conn.segments()

@@ -1,0 +1,187 @@
+"""Tensor-level wrappers over the raw sm_100a kernel launchers.
+
+The store's hot path (``InfinityConnection``) drives the kernels from C++; these wrappers
+exist for unit tests, the micro-benchmarks under ``bench/`` and for users who want the
+page movers without the control plane (e.g. moving pages between two paged KV caches).
+All functions launch on the current torch stream of the descriptor tensor's device.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _infinistore
+
+K = _infinistore.kernels
+
+VARIANTS = {"auto": K.COPY_AUTO, "ldst": K.COPY_LDST, "tma": K.COPY_TMA, "ldst256": K.COPY_LDST256}
+INDEX_ENTRY_BYTES = 32
+
+
+def _stream(device) -> int:
+    h = torch.cuda.current_stream(device).cuda_stream
+    return h if h != 0 else 1  # 1 == cudaStreamLegacy
+
+
+def make_descs(src_ptrs: Sequence[int], dst_ptrs: Sequence[int], device) -> torch.Tensor:
+    """(n, 2) int64 tensor of absolute {src, dst} addresses on `device`."""
+    a = np.empty((len(src_ptrs), 2), dtype=np.uint64)
+    a[:, 0] = np.asarray(src_ptrs, dtype=np.uint64)
+    a[:, 1] = np.asarray(dst_ptrs, dtype=np.uint64)
+    return torch.from_numpy(a.view(np.int64)).to(device)
+
+
+def kv_copy(descs: torch.Tensor, nbytes: int, variant: str = "auto", max_ctas: int = 0,
+            publish: Optional["PublishArgs"] = None, status: Optional[torch.Tensor] = None,
+            align_or: int = 0) -> None:
+    """Move descs.shape[0] blocks of `nbytes` bytes.  See csrc/kernels/kv_copy.cu."""
+    assert descs.is_cuda and descs.dtype == torch.int64 and descs.is_contiguous()
+    n = descs.shape[0]
+    with torch.cuda.device(descs.device):
+        K.kv_copy(descs.data_ptr(), n, nbytes, VARIANTS[variant], max_ctas, _stream(descs.device),
+                  publish.recs.data_ptr() if publish else 0,
+                  publish.table.data_ptr() if publish else 0,
+                  publish.mask if publish else 0,
+                  publish.done.data_ptr() if publish else 0,
+                  status.data_ptr() if status is not None else 0, align_or)
+
+
+class PublishArgs:
+    """Index records to publish with a write: one 32-byte entry per block."""
+
+    def __init__(self, table: torch.Tensor, keys: Sequence[bytes], addrs: Sequence[int],
+                 gens: Sequence[int], size: int):
+        dev = table.device
+        rec = np.zeros((len(keys), 4), dtype=np.uint64)
+        for i, k in enumerate(keys):
+            h1, h2 = _infinistore.testing.hash_key(k)
+            rec[i, 0], rec[i, 1], rec[i, 2] = h1, h2, addrs[i]
+            rec[i, 3] = (int(gens[i]) & 0xFFFFFFFF) | (int(size) << 32)
+        self.recs = torch.from_numpy(rec.view(np.int64)).to(dev)
+        self.table = table
+        self.mask = table.numel() * table.element_size() // INDEX_ENTRY_BYTES - 1
+        self.done = torch.zeros(len(keys), dtype=torch.int32, device=dev)
+
+
+def new_index_table(slots: int, device) -> torch.Tensor:
+    assert slots & (slots - 1) == 0, "slots must be a power of two"
+    return torch.zeros(slots * 4, dtype=torch.int64, device=device)
+
+
+def pack_keys(keys: Sequence[bytes], device) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Key bytes packed the way the lookup kernel expects: every key starts on an 8-byte
+    boundary and is zero padded to a multiple of 8."""
+    off, ln, chunks, at = [], [], [], 0
+    for k in keys:
+        padded = max((len(k) + 7) // 8 * 8, 8)
+        off.append(at)
+        ln.append(len(k))
+        chunks.append(k + b"\0" * (padded - len(k)))
+        at += padded
+    raw = np.frombuffer(b"".join(chunks), dtype=np.uint8).copy()
+    return (torch.from_numpy(raw).to(device),
+            torch.tensor(off, dtype=torch.int32, device=device),
+            torch.tensor(ln, dtype=torch.int32, device=device))
+
+
+def index_lookup(table: torch.Tensor, keys: Sequence[bytes], seg_base: Sequence[int] = (),
+                 dst_base: int = 0, dst_off: Optional[Sequence[int]] = None, need_bytes: int = 0,
+                 want_match: bool = False):
+    """Probe `table` for `keys`.  Returns (descs | None, present bitmap, match index | None)."""
+    dev = table.device
+    kb, ko, kl = pack_keys(keys, dev)
+    n = len(keys)
+    mask = table.numel() * table.element_size() // INDEX_ENTRY_BYTES - 1
+    descs = torch.zeros((n, 2), dtype=torch.int64, device=dev) if dst_off is not None else None
+    doff = (torch.tensor(list(dst_off), dtype=torch.int64, device=dev)
+            if dst_off is not None else None)
+    present = torch.zeros((n + 31) // 32, dtype=torch.int32, device=dev)
+    status = torch.zeros(K.STAT_WORDS, dtype=torch.int32, device=dev)
+    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        K.index_lookup(kb.data_ptr(), ko.data_ptr(), kl.data_ptr(), n, table.data_ptr(), mask,
+                       list(seg_base), descs.data_ptr() if descs is not None else 0,
+                       doff.data_ptr() if doff is not None else 0, dst_base, need_bytes,
+                       present.data_ptr(), status.data_ptr(), ticket.data_ptr(), want_match,
+                       _stream(dev))
+    match = None
+    if want_match:
+        torch.cuda.synchronize(dev)
+        match = int(np.int32(status[K.STAT_MATCH].item()))
+    return descs, present, match
+
+
+def presence_bits(present: torch.Tensor, n: int) -> List[bool]:
+    words = present.cpu().numpy().view(np.uint32)
+    return [bool((words[i >> 5] >> (i & 31)) & 1) for i in range(n)]
+
+
+def reference_match_last_index(present: Sequence[bool]) -> int:
+    """The reference's binary search (src/infinistore.cpp:1092-1108) over a presence list."""
+    left, right = 0, len(present)
+    while left < right:
+        mid = left + (right - left) // 2
+        if present[mid]:
+            left = mid + 1
+        else:
+            right = mid
+    return left - 1
+
+
+# ------------------------------------------------------------------------------ fp8
+def fp8_block_bytes(elems: int, group: int = 128) -> int:
+    return K.fp8_block_bytes(elems, group)
+
+
+def kv_write_fp8(descs: torch.Tensor, elems: int, max_ctas: int = 0,
+                 publish: Optional[PublishArgs] = None) -> None:
+    """bf16 pages (desc.src) -> e4m3 payload + per-128 scales (desc.dst)."""
+    with torch.cuda.device(descs.device):
+        K.kv_write_fp8(descs.data_ptr(), descs.shape[0], elems, 128, max_ctas,
+                       _stream(descs.device),
+                       publish.recs.data_ptr() if publish else 0,
+                       publish.table.data_ptr() if publish else 0,
+                       publish.mask if publish else 0,
+                       publish.done.data_ptr() if publish else 0, 0)
+
+
+def kv_read_fp8(descs: torch.Tensor, elems: int, max_ctas: int = 0,
+                status: Optional[torch.Tensor] = None) -> None:
+    """e4m3 payload + scales (desc.src) -> bf16 pages (desc.dst)."""
+    with torch.cuda.device(descs.device):
+        K.kv_read_fp8(descs.data_ptr(), descs.shape[0], elems, 128, max_ctas,
+                      _stream(descs.device), 0, 0, 0, 0,
+                      status.data_ptr() if status is not None else 0)
+
+
+def fp8_reference(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Plain PyTorch fp32 reference of the fused quantiser: per-128 amax scale, e4m3
+    round-to-nearest with saturation.  Returns (dequantised fp32, scales, payload)."""
+    xf = x.float().reshape(-1, 128)
+    amax = xf.abs().amax(dim=1, keepdim=True)
+    scale = torch.where(amax > 0, amax * (1.0 / 448.0), torch.ones_like(amax))
+    q = (xf * (1.0 / scale)).clamp(-448, 448).to(torch.float8_e4m3fn)
+    return (q.float() * scale).reshape(x.shape), scale.reshape(-1), q.reshape(-1)
+
+
+def fp8_roundtrip_check(device, pages: int = 8, elems: int = 16384) -> float:
+    """Quantise `pages` bf16 pages into a pool buffer and read them back; compares against
+    the fp32 reference.  Returns the max abs error vs the reference dequantisation."""
+    x = (torch.randn(pages, elems, device=device) * 3).to(torch.bfloat16)
+    bb = fp8_block_bytes(elems)
+    pool = torch.zeros(pages, (bb + 255) // 256 * 256, dtype=torch.uint8, device=device)
+    out = torch.zeros_like(x)
+    wd = make_descs([x[i].data_ptr() for i in range(pages)],
+                    [pool[i].data_ptr() for i in range(pages)], device)
+    rd = make_descs([pool[i].data_ptr() for i in range(pages)],
+                    [out[i].data_ptr() for i in range(pages)], device)
+    kv_write_fp8(wd, elems)
+    kv_read_fp8(rd, elems)
+    torch.cuda.synchronize(device)
+    ref, _, _ = fp8_reference(x)
+    err = (out.float() - ref.to(torch.bfloat16).float()).abs().max().item()
+    tol = float(x.float().abs().max()) * 2 ** -7  # one bf16 ulp of the largest value
+    assert err <= tol, f"fp8 round trip error {err} > {tol}"
+    return err

@@ -1,0 +1,217 @@
+"""Numerics of the sm_100a kernels against plain PyTorch references (run on the B200 box)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _ops():
+    from infinistore_b200 import ops
+
+    return ops
+
+
+@pytest.mark.parametrize("variant", ["ldst", "tma", "ldst256"])
+@pytest.mark.parametrize("nbytes", [4096, 16384, 65536, 131072, 1 << 20, 48 * 1024 + 16])
+def test_kv_copy_matches_torch_gather_scatter(variant, nbytes):
+    ops = _ops()
+    n = 37
+    g = torch.Generator(device=DEV).manual_seed(nbytes)
+    stride = (nbytes + 255) // 256 * 256
+    src = torch.randint(0, 255, (n * 2, stride), dtype=torch.uint8, device=DEV, generator=g)
+    dst = torch.zeros((n * 2, stride), dtype=torch.uint8, device=DEV)
+    perm_s = torch.randperm(n * 2, generator=torch.Generator().manual_seed(1))[:n].tolist()
+    perm_d = torch.randperm(n * 2, generator=torch.Generator().manual_seed(2))[:n].tolist()
+    descs = ops.make_descs([src[i].data_ptr() for i in perm_s],
+                           [dst[i].data_ptr() for i in perm_d], DEV)
+    ops.kv_copy(descs, nbytes, variant=variant)
+    torch.cuda.synchronize()
+    ref = torch.zeros_like(dst)
+    for s, d in zip(perm_s, perm_d):
+        ref[d, :nbytes] = src[s, :nbytes]
+    assert torch.equal(dst, ref)
+
+
+@pytest.mark.parametrize("variant", ["ldst", "tma"])
+def test_kv_copy_small_grid_and_many_blocks(variant):
+    ops = _ops()
+    n, nbytes = 3000, 8192
+    src = torch.randint(0, 255, (n, nbytes), dtype=torch.uint8, device=DEV)
+    dst = torch.zeros_like(src)
+    descs = ops.make_descs([src[i].data_ptr() for i in range(n)],
+                           [dst[n - 1 - i].data_ptr() for i in range(n)], DEV)
+    ops.kv_copy(descs, nbytes, variant=variant, max_ctas=5)
+    torch.cuda.synchronize()
+    assert torch.equal(dst, src.flip(0))
+
+
+def test_kv_copy_unaligned_falls_back_to_bytes():
+    ops = _ops()
+    n, nbytes = 9, 1000  # not a multiple of 16, odd addresses
+    src = torch.randint(0, 255, (n, 2048), dtype=torch.uint8, device=DEV)
+    dst = torch.zeros_like(src)
+    descs = ops.make_descs([src[i].data_ptr() + 3 for i in range(n)],
+                           [dst[i].data_ptr() + 5 for i in range(n)], DEV)
+    ops.kv_copy(descs, nbytes, variant="tma", align_or=3)
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:, 5:1005], src[:, 3:1003])
+    assert int(dst[:, :5].sum()) == 0 and int(dst[:, 1005:].sum()) == 0
+
+
+@pytest.mark.parametrize("variant", ["ldst", "tma"])
+def test_publish_then_lookup_and_read(variant):
+    """Write with in-band commit, then resolve the keys on the GPU and read them back."""
+    ops = _ops()
+    n, nbytes = 257, 32768
+    keys = [b"layer3/tp0/block-%05d" % i for i in range(n)]
+    pool = torch.zeros((n, nbytes), dtype=torch.uint8, device=DEV)
+    src = torch.randint(0, 255, (n, nbytes), dtype=torch.uint8, device=DEV)
+    dst = torch.zeros_like(src)
+    table = ops.new_index_table(1024, DEV)
+    seg_base = pool.data_ptr()
+    addrs = [(1 << 44) | (i * nbytes) for i in range(n)]  # segment 0, offset i*nbytes
+    pub = ops.PublishArgs(table, keys, addrs, gens=list(range(1, n + 1)), size=nbytes)
+    status = torch.zeros(8, dtype=torch.int32, device=DEV)
+    wd = ops.make_descs([src[i].data_ptr() for i in range(n)],
+                        [pool[i].data_ptr() for i in range(n)], DEV)
+    ops.kv_copy(wd, nbytes, variant=variant, publish=pub, status=status)
+    torch.cuda.synchronize()
+    assert int(pub.done.abs().sum()) == 0  # counters are left zeroed
+    assert int(status[1]) == 0
+
+    order = list(range(n))[::-1]
+    query = [keys[i] for i in order] + [b"missing-1", b"missing-2"]
+    dst_off = [i * nbytes for i in order] + [0, 0]
+    descs, present, _ = ops.index_lookup(table, query, seg_base=[seg_base],
+                                         dst_base=dst.data_ptr(), dst_off=dst_off,
+                                         need_bytes=nbytes)
+    bits = ops.presence_bits(present, len(query))
+    assert bits == [True] * n + [False, False]
+    d = descs.cpu().numpy().view(np.uint64)
+    assert d[n, 0] == 0 and d[n + 1, 0] == 0
+    ops.kv_copy(descs, nbytes, variant=variant, status=status)
+    torch.cuda.synchronize()
+    assert int(status[0]) == 2  # two misses counted, not copied
+    assert torch.equal(dst, src)
+    # a reader asking for more than was written gets a miss, not an overrun
+    descs2, _, _ = ops.index_lookup(table, query[:4], seg_base=[seg_base],
+                                    dst_base=dst.data_ptr(), dst_off=dst_off[:4],
+                                    need_bytes=nbytes + 1)
+    assert (descs2.cpu().numpy().view(np.uint64)[:, 0] == 0).all()
+
+
+def test_match_last_index_replays_reference_search_bit_exact():
+    ops = _ops()
+    rng = np.random.default_rng(7)
+    table = ops.new_index_table(4096, DEV)
+    stored = [b"key-%04d" % i for i in range(1500)]
+    pool = torch.zeros((1, 64), dtype=torch.uint8, device=DEV)
+    src = torch.zeros((1, 64), dtype=torch.uint8, device=DEV)
+    pub = ops.PublishArgs(table, stored, [(1 << 44)] * len(stored),
+                          gens=list(range(1, len(stored) + 1)), size=64)
+    wd = ops.make_descs([src.data_ptr()] * len(stored), [pool.data_ptr()] * len(stored), DEV)
+    ops.kv_copy(wd, 64, variant="ldst", publish=pub)
+    torch.cuda.synchronize()
+    stored_set = set(stored)
+    # the reference's own example: non-monotone presence
+    q = [b"A", b"B", b"C", b"key-0001", b"D", b"E"]
+    _, present, match = ops.index_lookup(table, q, want_match=True)
+    assert match == 3 == ops.reference_match_last_index([k in stored_set for k in q])
+    for trial in range(25):
+        n = int(rng.integers(1, 700))
+        if trial % 3 == 0:  # prefix-monotone (the real use: chained token-block hashes)
+            hit = int(rng.integers(0, n + 1))
+            q = [stored[i] if i < hit else b"miss-%d" % i for i in range(n)]
+        else:               # arbitrary presence pattern
+            q = [stored[int(rng.integers(0, len(stored)))] if rng.random() < 0.5
+                 else b"miss-%d-%d" % (trial, i) for i in range(n)]
+        _, present, match = ops.index_lookup(table, q, want_match=True)
+        want = [k in stored_set for k in q]
+        assert ops.presence_bits(present, n) == want
+        assert match == ops.reference_match_last_index(want)
+
+
+def test_device_hash_equals_host_hash():
+    """Keys of every length 0..70 are found, i.e. the kernel's hash == core/hash.h on host."""
+    ops = _ops()
+    keys = [bytes((i * 7 + j) % 251 for j in range(i)) for i in range(71)]
+    table = ops.new_index_table(256, DEV)
+    pool = torch.zeros(64, dtype=torch.uint8, device=DEV)
+    pub = ops.PublishArgs(table, keys, [(1 << 44)] * len(keys),
+                          gens=list(range(1, len(keys) + 1)), size=64)
+    wd = ops.make_descs([pool.data_ptr()] * len(keys), [pool.data_ptr()] * len(keys), DEV)
+    ops.kv_copy(wd, 64, publish=pub)
+    _, present, _ = ops.index_lookup(table, keys)
+    torch.cuda.synchronize()
+    assert all(ops.presence_bits(present, len(keys)))
+
+
+def test_index_full_is_reported_not_hung():
+    ops = _ops()
+    table = ops.new_index_table(16, DEV)
+    keys = [b"k%d" % i for i in range(40)]
+    pool = torch.zeros(64, dtype=torch.uint8, device=DEV)
+    pub = ops.PublishArgs(table, keys, [(1 << 44)] * 40, gens=list(range(1, 41)), size=64)
+    status = torch.zeros(8, dtype=torch.int32, device=DEV)
+    wd = ops.make_descs([pool.data_ptr()] * 40, [pool.data_ptr()] * 40, DEV)
+    ops.kv_copy(wd, 64, publish=pub, status=status)
+    torch.cuda.synchronize()
+    assert int(status[1]) == 40 - 16
+
+
+def test_first_writer_wins_in_the_device_index():
+    ops = _ops()
+    table = ops.new_index_table(64, DEV)
+    pool = torch.zeros(64, dtype=torch.uint8, device=DEV)
+    wd = ops.make_descs([pool.data_ptr()], [pool.data_ptr()], DEV)
+    ops.kv_copy(wd, 64, publish=ops.PublishArgs(table, [b"dup"], [(1 << 44) | 4096], [5], 64))
+    ops.kv_copy(wd, 64, publish=ops.PublishArgs(table, [b"dup"], [(1 << 44) | 8192], [6], 64))
+    descs, present, _ = ops.index_lookup(table, [b"dup"], seg_base=[0x1000000], dst_base=0,
+                                         dst_off=[0], need_bytes=1)
+    torch.cuda.synchronize()
+    assert int(descs.cpu().numpy().view(np.uint64)[0, 0]) == 0x1000000 + 4096
+
+
+@pytest.mark.parametrize("elems", [128, 8192, 16384, 65536, 8192 + 128 * 5])
+def test_fp8_write_matches_fp32_reference(elems):
+    ops = _ops()
+    pages = 11
+    g = torch.Generator(device=DEV).manual_seed(elems)
+    x = (torch.randn(pages, elems, device=DEV, generator=g) * 4).to(torch.bfloat16)
+    x[0, :128] = 0  # an all-zero row must not divide by zero
+    x[1, 5] = 30000.0  # outlier row
+    bb = ops.fp8_block_bytes(elems)
+    assert bb == elems + 4 * (elems // 128)
+    stride = (bb + 255) // 256 * 256
+    pool = torch.zeros(pages, stride, dtype=torch.uint8, device=DEV)
+    wd = ops.make_descs([x[i].data_ptr() for i in range(pages)],
+                        [pool[i].data_ptr() for i in range(pages)], DEV)
+    ops.kv_write_fp8(wd, elems)
+    torch.cuda.synchronize()
+    ref_deq, ref_scale, ref_q = ops.fp8_reference(x)
+    payload = pool[:, :elems].contiguous().view(torch.float8_e4m3fn)
+    scales = pool[:, elems:bb].contiguous().view(torch.float32)
+    assert torch.allclose(scales.reshape(-1), ref_scale, rtol=1e-6, atol=0)
+    # identical up to round-to-nearest ties of x * (1/scale): compare dequantised values
+    got = payload.float().reshape(pages, -1, 128) * scales.reshape(pages, -1, 1)
+    step = ref_scale.reshape(pages, -1, 1) * 32.0  # one e4m3 ulp at the top binade
+    assert ((got - ref_deq.reshape(pages, -1, 128)).abs() <= step).all()
+    assert (payload.float() == ref_q.float().reshape(pages, -1)).float().mean() > 0.999
+
+    out = torch.zeros_like(x)
+    rd = ops.make_descs([pool[i].data_ptr() for i in range(pages)],
+                        [out[i].data_ptr() for i in range(pages)], DEV)
+    ops.kv_read_fp8(rd, elems)
+    torch.cuda.synchronize()
+    assert torch.equal(out, got.reshape(pages, elems).to(torch.bfloat16))
+    # quantisation error bound: half an e4m3 ulp relative to the row maximum (2^-4)
+    rel = (out.float() - x.float()).abs().reshape(pages, -1, 128).amax(2) / \
+        x.float().abs().reshape(pages, -1, 128).amax(2).clamp_min(1e-30)
+    assert float(rel.max()) <= 2 ** -4 + 2 ** -8
+
+
+def test_fp8_roundtrip_helper():
+    _ops().fp8_roundtrip_check(torch.device(DEV))

@@ -1,0 +1,246 @@
+"""End-to-end store on an HBM pool (run on the B200 box): ports of the reference's
+integration tests (infinistore/test_infinistore.py) onto the NVLink fabric."""
+import asyncio
+import multiprocessing as mp
+import random
+import string
+
+import pytest
+import torch
+
+import infinistore_b200 as ist
+from conftest import make_conn
+
+pytestmark = pytest.mark.gpu
+
+
+def rand_key(n=10):
+    return "".join(random.choice(string.ascii_letters + string.digits) for _ in range(n))
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("new_connection", [True, False])
+@pytest.mark.parametrize("local", [True, False])
+@pytest.mark.parametrize("device_lookup", [False, True])
+def test_basic_read_write_cache(hbm_server, dtype, new_connection, local, device_lookup):
+    _, port = hbm_server
+    ctype = ist.TYPE_LOCAL_GPU if local else ist.TYPE_RDMA
+    conn = make_conn(port, ctype, device_lookup=device_lookup)
+    key = rand_key()
+    src = torch.arange(4096, device="cuda:0").to(dtype)
+    if local:
+        conn.local_gpu_write_cache(src, [(key, 0)], 4096)
+    else:
+        conn.register_mr(src)
+        conn.rdma_write_cache(src, [0], 4096, conn.allocate_rdma([key], 4096 * src.element_size()))
+    conn.sync()
+    if new_connection:
+        conn = make_conn(port, ctype, device_lookup=device_lookup)
+    dst = torch.zeros(4096, device="cuda:0", dtype=dtype)
+    if not local:
+        conn.register_mr(dst)
+    conn.read_cache(dst, [(key, 0)], 4096)
+    conn.sync()
+    assert torch.equal(src, dst)
+    assert conn.stats()["kernel_launches"] >= 1
+
+
+@pytest.mark.parametrize("variant", ["ldst", "tma", "ldst256"])
+@pytest.mark.parametrize("separated_gpu", [False, True])
+def test_batch_read_write_cache(hbm_server, variant, separated_gpu):
+    if separated_gpu and torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _, port = hbm_server
+    src_dev, dst_dev = ("cuda:0", "cuda:1") if separated_gpu else ("cuda:0", "cuda:0")
+    conn = make_conn(port, copy_variant=variant, device_lookup=True)
+    nblocks, bs = 64, 32768
+    src = torch.randn(nblocks * bs, device=src_dev)
+    conn.register_mr(src)
+    for _ in range(3):
+        keys = [rand_key(12) for _ in range(nblocks)]
+        blocks = [(keys[i], i * bs) for i in range(nblocks)]
+        remote = conn.allocate_rdma(keys, bs * 4)
+        conn.rdma_write_cache(src, [i * bs for i in range(nblocks)], bs, remote)
+        conn.sync()
+        dst = torch.zeros(nblocks * bs, device=dst_dev)
+        conn.register_mr(dst)
+        conn.read_cache(dst, blocks, bs)
+        conn.sync()
+        assert torch.equal(src.cpu(), dst.cpu())
+
+
+def _client_proc(port, local, q):
+    try:
+        torch.cuda.set_device(0)
+        ctype = ist.TYPE_LOCAL_GPU if local else ist.TYPE_RDMA
+        conn = make_conn(port, ctype, device_lookup=True)
+        key = rand_key()
+        src = torch.arange(4096, device="cuda:0", dtype=torch.float32)
+        if local:
+            conn.local_gpu_write_cache(src, [(key, 0)], 4096)
+        else:
+            conn.register_mr(src)
+            conn.rdma_write_cache(src, [0], 4096, conn.allocate_rdma([key], 4096 * 4))
+        conn.sync()
+        conn = make_conn(port, ctype)  # host-mediated lookup on the second connection
+        dst = torch.zeros(4096, device="cuda:0")
+        conn.read_cache(dst, [(key, 0)], 4096)
+        conn.sync()
+        q.put(bool(torch.equal(src, dst)))
+    except Exception as e:  # pragma: no cover
+        q.put(repr(e))
+
+
+@pytest.mark.parametrize("local", [True, False])
+def test_multiple_client_processes_map_the_pool_over_cuda_ipc(hbm_server, local):
+    """Separate client processes: the pool is reached through a CUDA IPC mapping."""
+    _, port = hbm_server
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_client_proc, args=(port, local, q)) for _ in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert results == [True, True]
+
+
+def test_key_check_and_match_on_device(hbm_server):
+    _, port = hbm_server
+    conn = make_conn(port, device_lookup=True)
+    src = torch.randn(4096, device="cuda:0")
+    conn.register_mr(src)
+    remote = conn.allocate_rdma(["key1", "key2", "key3"], 1024 * 4)
+    conn.rdma_write_cache(src, [0, 1024, 2048], 1024, remote)
+    # no sync: the match kernel is stream-ordered after the write kernel
+    assert conn.get_match_last_index(["A", "B", "C", "key1", "D", "E"]) == 3
+    assert conn.get_match_last_index(["key1", "key2", "key3", "X"]) == 2
+    with pytest.raises(Exception):
+        conn.get_match_last_index(["nope"])
+    conn.sync()
+    assert conn.check_exist("key2") and not conn.check_exist("key9")
+    # host path answers the same
+    conn2 = make_conn(port)
+    assert conn2.get_match_last_index(["A", "B", "C", "key1", "D", "E"]) == 3
+    assert conn2.check_exist("key2")
+
+
+def test_key_not_found(hbm_server):
+    _, port = hbm_server
+    conn = make_conn(port, ist.TYPE_LOCAL_GPU)
+    dst = torch.zeros(4096, device="cuda:0")
+    with pytest.raises(Exception):
+        conn.read_cache(dst, [("not_exist_key", 0)], 4096)
+    # with the device index the miss is found by the kernel and surfaces at sync()
+    conn = make_conn(port, ist.TYPE_LOCAL_GPU, device_lookup=True)
+    conn.read_cache(dst, [("not_exist_key", 0)], 4096)
+    with pytest.raises(Exception, match="404|not found"):
+        conn.sync()
+    conn.sync()  # the error is reported once
+
+
+def test_upload_cpu_download_gpu(hbm_server):
+    """CPU tensor in over the fabric connection, GPU tensor out over LOCAL_GPU: both paths
+    share one store (reference: test_infinistore.py:296-326)."""
+    _, port = hbm_server
+    up = make_conn(port, ist.TYPE_RDMA)
+    key = rand_key(5)
+    src = torch.randn(4096)
+    up.register_mr(src)
+    up.rdma_write_cache(src, [0], 4096, up.allocate_rdma([key], 4096 * 4))
+    up.sync()
+    down = make_conn(port, ist.TYPE_LOCAL_GPU)
+    dst = torch.zeros(4096, device="cuda:0")
+    down.read_cache(dst, [(key, 0)], 4096)
+    down.sync()
+    assert torch.equal(src, dst.cpu())
+    # and back out to a CPU tensor
+    back = torch.zeros(4096)
+    up.register_mr(back)
+    up.read_cache(back, [(key, 0)], 4096)
+    up.sync()
+    assert torch.equal(src, back)
+
+
+def test_deduplicate(hbm_server):
+    srv, port = hbm_server
+    conn = make_conn(port, device_lookup=True)
+    key = "duplicate_key"
+    src = torch.arange(4096, device="cuda:0", dtype=torch.float32)
+    conn.register_mr(src)
+    conn.rdma_write_cache(src, [0], 4096, conn.allocate_rdma([key], 4096 * 4))
+    conn.sync()
+    src2 = torch.randn(4096, device="cuda:0")
+    conn.register_mr(src2)
+    conn.rdma_write_cache(src2, [0], 4096, conn.allocate_rdma([key], 4096 * 4))
+    conn.sync()
+    dst = torch.zeros(4096)
+    conn.register_mr(dst)
+    conn.read_cache(dst, [(key, 0)], 4096)
+    conn.sync()
+    assert torch.equal(src.cpu(), dst) and not torch.equal(src2.cpu(), dst)
+
+
+def test_async_api(hbm_server):
+    _, port = hbm_server
+    conn = ist.InfinityConnection(ist.ClientConfig(
+        host_addr="127.0.0.1", service_port=port, connection_type=ist.TYPE_RDMA))
+
+    async def run():
+        await conn.connect_async()
+        key = rand_key(5)
+        src = torch.randn(4096, device="cuda:0")
+        dst = torch.zeros(4096, device="cuda:0")
+        await asyncio.to_thread(lambda: (conn.register_mr(src), conn.register_mr(dst)))
+        remote = await conn.allocate_rdma_async([key], 4096 * 4)
+        await conn.rdma_write_cache_async(src, [0], 4096, remote)
+        await conn.read_cache_async(dst, [(key, 0)], 4096)
+        assert torch.equal(src, dst)
+
+    asyncio.run(asyncio.wait_for(run(), 60))
+
+
+def test_purge_clears_the_device_index(hbm_server):
+    srv, port = hbm_server
+    conn = make_conn(port, device_lookup=True)
+    src = torch.randn(4096, device="cuda:0")
+    conn.register_mr(src)
+    conn.rdma_write_cache(src, [0], 4096, conn.allocate_rdma(["p"], 16384))
+    conn.sync()
+    assert conn.check_exist("p")
+    assert srv.purge() == 1
+    assert not conn.check_exist("p")
+    conn.rdma_write_cache(src, [0], 4096, conn.allocate_rdma(["p"], 16384))
+    conn.sync()
+    assert conn.check_exist("p")
+
+
+def test_warmup_and_selftest(hbm_server):
+    from infinistore_b200 import server as srvmod, warmup
+
+    _, port = hbm_server
+
+    class A:
+        service_port = port
+        start_delay = 0
+
+    assert warmup.warm_up(A) >= 1
+    assert asyncio.run(srvmod.run_selftest(port)) == {"status": "ok"}
+
+
+def test_benchmark_module(hbm_server):
+    from infinistore_b200 import benchmark
+
+    _, port = hbm_server
+    for extra in ([], ["--rdma"], ["--rdma", "--device-lookup", "--variant", "tma"]):
+        args = benchmark.parse_args(["--service-port", str(port), "--size", "64", "--block-size",
+                                     "32", "--iteration", "2", "--steps", "8"] + extra)
+        r = benchmark.run(args)
+        assert r["write_mb_s"] > 0 and r["read_mb_s"] > 0
+
+
+def test_smoke_entry():
+    import __graft_entry__
+
+    __graft_entry__.smoke()

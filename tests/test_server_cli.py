@@ -1,0 +1,89 @@
+"""`python -m infinistore.server` as a subprocess + the HTTP manage plane, on CPU."""
+import json
+import os
+import signal
+import subprocess
+import sys
+import time
+import urllib.request
+
+import pytest
+import torch
+
+from conftest import ROOT, free_port, make_conn
+
+
+@pytest.fixture(scope="module")
+def cli_server():
+    sport, mport = free_port(), free_port()
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    proc = subprocess.Popen(
+        [sys.executable, "-m", "infinistore.server", "--service-port", str(sport),
+         "--manage-port", str(mport), "--host", "127.0.0.1", "--pool-backend", "host",
+         "--prealloc-size", "1", "--minimal-allocate-size", "16", "--log-level", "warning",
+         "--dev-name", "mlx5_2", "--link-type", "Ethernet"],
+        env=env, cwd=ROOT)
+    deadline = time.time() + 60
+    while time.time() < deadline:
+        try:
+            urllib.request.urlopen(f"http://127.0.0.1:{mport}/kvmap_len", timeout=1).read()
+            break
+        except Exception:
+            if proc.poll() is not None:
+                raise RuntimeError("server exited early")
+            time.sleep(0.2)
+    yield sport, mport
+    os.kill(proc.pid, signal.SIGINT)
+    try:
+        proc.wait(20)
+    except subprocess.TimeoutExpired:
+        proc.kill()
+
+
+def _http(method, url):
+    req = urllib.request.Request(url, method=method)
+    return json.loads(urllib.request.urlopen(req, timeout=30).read())
+
+
+def test_manage_plane_and_selftest(cli_server):
+    sport, mport = cli_server
+    base = f"http://127.0.0.1:{mport}"
+    assert _http("GET", base + "/kvmap_len") == {"len": 0}
+    conn = make_conn(sport)
+    src = torch.randn(8 * 1024)
+    conn.register_mr(src)
+    keys = [f"cli-{i}" for i in range(8)]
+    conn.rdma_write_cache(src, [i * 1024 for i in range(8)], 1024, conn.allocate_rdma(keys, 4096))
+    conn.sync()
+    assert _http("GET", base + "/kvmap_len") == {"len": 8}
+    assert _http("POST", base + f"/selftest/{sport}") == {"status": "ok"}
+    stats = _http("GET", base + "/stats")
+    assert stats["keys"] == 11 and stats["ops"]["ALLOCATE"] >= 2
+    text = urllib.request.urlopen(base + "/metrics", timeout=10).read().decode()
+    assert "infinistore_keys 11" in text and 'infinistore_op_total{op="COMMIT"}' in text
+    assert _http("POST", base + "/purge") == {"status": "ok", "num": 11}
+    assert _http("GET", base + "/kvmap_len") == {"len": 0}
+    assert not conn.check_exist("cli-0")
+
+
+def test_cpu_benchmark_against_cli_server(cli_server):
+    sport, _ = cli_server
+    from infinistore_b200 import benchmark
+
+    args = benchmark.parse_args(["--service-port", str(sport), "--size", "4", "--block-size", "4",
+                                 "--iteration", "2", "--rdma", "--cpu", "--steps", "4"])
+    r = benchmark.run(args)
+    assert r["write_mb_s"] > 0 and r["read_mb_s"] > 0
+
+
+def test_arg_defaults_match_reference():
+    from infinistore_b200 import server
+
+    a = server.parse_args([])
+    assert (a.manage_port, a.service_port, a.prealloc_size, a.minimal_allocate_size) == \
+        (18080, 22345, 16, 64)
+    assert (a.log_level, a.dev_name, a.ib_port, a.link_type, a.num_stream) == \
+        ("info", "mlx5_1", 1, "IB", 1)
+    assert a.auto_increase is False and a.warmup is False and a.host == "0.0.0.0"
+    cfg = server.config_from_args(server.parse_args(["--pool-devices", "0,2", "--auto-increase"]))
+    assert list(cfg.pool_devices) == [0, 2] and cfg.auto_increase

@@ -1,0 +1,468 @@
+"""End-to-end store semantics on CPU loop-back (host-memory pool, no GPU).
+
+Ports the behaviour the reference's integration tests assert
+(infinistore/test_infinistore.py:61-417) to the CPU plumbing configuration of BASELINE.json
+("server + client write/read 16 keys x 4 KB on CPU loopback"), plus the contract items of
+SURVEY §2.5 and the reference defects that must NOT be reproduced (D1-D5, D10-D12).
+"""
+import asyncio
+import multiprocessing as mp
+import random
+import socket
+import string
+import struct
+import time
+
+import numpy as np
+import pytest
+import torch
+
+import infinistore_b200 as ist
+from conftest import make_conn
+
+
+def rand_key(n=10):
+    return "".join(random.choice(string.ascii_letters + string.digits) for _ in range(n))
+
+
+# ------------------------------------------------------------------ reference test ports
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("new_connection", [True, False])
+def test_basic_read_write_cache(host_server, dtype, new_connection):
+    _, port = host_server
+    conn = make_conn(port)
+    key = rand_key()
+    src = torch.arange(4096).to(dtype)
+    conn.register_mr(src)
+    blocks = conn.allocate_rdma([key], 4096 * src.element_size())
+    conn.rdma_write_cache(src, [0], 4096, blocks)
+    conn.sync()
+    if new_connection:
+        conn = make_conn(port)
+    dst = torch.zeros(4096, dtype=dtype)
+    conn.register_mr(dst)
+    conn.read_cache(dst, [(key, 0)], 4096)
+    conn.sync()
+    assert torch.equal(src, dst)
+
+
+def test_plumbing_config_16_keys_x_4kb(host_server):
+    """BASELINE.json config 1."""
+    _, port = host_server
+    conn = make_conn(port)
+    keys = [rand_key() for _ in range(16)]
+    src = torch.randn(16 * 1024)  # 16 x 4 KB of fp32
+    dst = torch.zeros_like(src)
+    conn.register_mr(src)
+    conn.register_mr(dst)
+    blocks = conn.allocate_rdma(keys, 4096)
+    conn.rdma_write_cache(src, [i * 1024 for i in range(16)], 1024, blocks)
+    conn.sync()
+    conn.read_cache(dst, [(k, i * 1024) for i, k in enumerate(keys)], 1024)
+    conn.sync()
+    assert torch.equal(src, dst)
+    assert conn.stats()["host_copies"] == 32
+
+
+def test_batch_read_write_cache(host_server):
+    _, port = host_server
+    conn = make_conn(port)
+    nblocks, bs = 10, 4096
+    src = torch.arange(nblocks * bs, dtype=torch.float32)
+    conn.register_mr(src)
+    for _ in range(3):
+        keys = [rand_key() for _ in range(nblocks)]
+        blocks = [(keys[i], i * bs) for i in range(nblocks)]
+        remote = conn.allocate_rdma(keys, bs * 4)
+        conn.rdma_write_cache(src, [i * bs for i in range(nblocks)], bs, remote)
+        conn.sync()
+        dst = torch.zeros(nblocks * bs, dtype=torch.float32)
+        conn.register_mr(dst)
+        conn.read_cache(dst, blocks, bs)
+        conn.sync()
+        assert torch.equal(src, dst)
+
+
+def _client_proc(port, q):
+    try:
+        conn = make_conn(port)
+        key = rand_key()
+        src = torch.arange(4096, dtype=torch.float32)
+        conn.register_mr(src)
+        blocks = conn.allocate_rdma([key], 4096 * 4)
+        conn.rdma_write_cache(src, [0], 4096, blocks)
+        conn.sync()
+        conn = make_conn(port)
+        dst = torch.zeros(4096, dtype=torch.float32)
+        conn.read_cache(dst, [(key, 0)], 4096)
+        conn.sync()
+        q.put(bool(torch.equal(src, dst)))
+    except Exception as e:  # pragma: no cover
+        q.put(repr(e))
+
+
+def test_multiple_clients(host_server):
+    _, port = host_server
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_client_proc, args=(port, q)) for _ in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(30)
+    assert results == [True, True]
+
+
+def test_key_check(host_server):
+    _, port = host_server
+    conn = make_conn(port)
+    key = rand_key(5)
+    src = torch.randn(4096)
+    conn.register_mr(src)
+    blocks = conn.allocate_rdma([key], 4096 * 4)
+    assert not conn.check_exist(key)  # reserved but not committed (C3)
+    conn.rdma_write_cache(src, [0], 4096, blocks)
+    conn.sync()
+    assert conn.check_exist(key)
+    assert not conn.check_exist("never-written")
+
+
+def test_get_match_last_index(host_server):
+    _, port = host_server
+    conn = make_conn(port)
+    src = torch.randn(4096)
+    conn.register_mr(src)
+    blocks = conn.allocate_rdma(["key1", "key2", "key3"], 1024 * 4)
+    conn.rdma_write_cache(src, [0, 1024, 2048], 1024, blocks)
+    # no sync on purpose: match does not require `committed` (C3), and the non-monotone
+    # input must give exactly what the reference's binary search gives (C7)
+    assert conn.get_match_last_index(["A", "B", "C", "key1", "D", "E"]) == 3
+    assert conn.get_match_last_index(["key1", "key2", "key3", "X"]) == 2
+    assert conn.get_match_last_index(["key1"]) == 0
+    with pytest.raises(Exception, match="can't find a match"):
+        conn.get_match_last_index(["A", "B"])
+
+
+def test_key_not_found(host_server):
+    _, port = host_server
+    conn = make_conn(port)
+    dst = torch.zeros(4096)
+    with pytest.raises(Exception):
+        conn.read_cache(dst, [("not_exist_key", 0)], 4096)
+    # a reserved-but-uncommitted key is not readable either
+    conn.allocate_rdma(["pending"], 4096 * 4)
+    with pytest.raises(Exception):
+        conn.read_cache(dst, [("pending", 0)], 4096)
+
+
+def test_deduplicate_first_writer_wins(host_server):
+    srv, port = host_server
+    conn = make_conn(port)
+    key = "duplicate_key"
+    src = torch.arange(4096, dtype=torch.float32)
+    conn.register_mr(src)
+    conn.rdma_write_cache(src, [0], 4096, conn.allocate_rdma([key], 4096 * 4))
+    conn.sync()
+    used = srv.stats()["used_bytes"]
+    src2 = torch.randn(4096)
+    conn.register_mr(src2)
+    again = conn.allocate_rdma([key], 4096 * 4)
+    assert again["rkey"][0] == 0 and again["remote_addr"][0] == 0  # fake block sentinel
+    conn.rdma_write_cache(src2, [0], 4096, again)  # silently skipped
+    conn.sync()
+    assert srv.stats()["used_bytes"] == used  # dedup does not leak pool space (ref. defect D1)
+    dst = torch.zeros(4096)
+    conn.read_cache(dst, [(key, 0)], 4096)
+    conn.sync()
+    assert torch.equal(src, dst) and not torch.equal(src2, dst)
+
+
+def test_partial_dedup_batch_completes(host_server):
+    """Reference defect D2: a batch whose LAST block is a duplicate must still complete."""
+    _, port = host_server
+    conn = make_conn(port)
+    src = torch.randn(2 * 1024)
+    conn.register_mr(src)
+    conn.rdma_write_cache(src, [1024], 1024, conn.allocate_rdma(["tail"], 4096))
+    conn.sync()
+    blocks = conn.allocate_rdma(["head", "tail"], 4096)
+    assert blocks["rkey"].tolist()[1] == 0
+
+    async def run():
+        await conn.rdma_write_cache_async(src, [0, 1024], 1024, blocks)
+
+    asyncio.run(asyncio.wait_for(run(), 10))
+    conn.sync()
+    assert conn.check_exist("head")
+
+
+def test_async_api(host_server):
+    _, port = host_server
+    cfg = ist.ClientConfig(host_addr="127.0.0.1", service_port=port,
+                           connection_type=ist.TYPE_RDMA)
+    conn = ist.InfinityConnection(cfg)
+
+    async def run():
+        await conn.connect_async()
+        key = rand_key(5)
+        src = torch.randn(4096)
+        dst = torch.zeros(4096)
+        await asyncio.to_thread(lambda: (conn.register_mr(src), conn.register_mr(dst)))
+        remote = await conn.allocate_rdma_async([key], 4096 * 4)
+        await conn.rdma_write_cache_async(src, [0], 4096, remote)
+        await conn.read_cache_async(dst, [(key, 0)], 4096)
+        assert torch.equal(src, dst)
+
+    asyncio.run(asyncio.wait_for(run(), 20))
+
+
+def test_local_connection_requires_cuda_tensor_and_localhost(host_server):
+    _, port = host_server
+    conn = make_conn(port, connection_type=ist.TYPE_LOCAL_GPU)
+    with pytest.raises(Exception, match="CUDA"):
+        conn.local_gpu_write_cache(torch.zeros(16), [("k", 0)], 16)
+    cfg = ist.ClientConfig(host_addr="10.1.2.3", service_port=port,
+                           connection_type=ist.TYPE_LOCAL_GPU)
+    with pytest.raises(Exception, match="localhost"):
+        ist.InfinityConnection(cfg).connect()
+
+
+def test_config_verify_matches_reference_rules():
+    with pytest.raises(Exception):
+        ist.ClientConfig(host_addr="127.0.0.1", service_port=1).verify()  # no connection type
+    with pytest.raises(Exception):
+        ist.ClientConfig(connection_type=ist.TYPE_RDMA, host_addr="", service_port=1).verify()
+    with pytest.raises(Exception):
+        ist.ClientConfig(connection_type=ist.TYPE_RDMA, host_addr="h", service_port=0).verify()
+    with pytest.raises(Exception):  # the reference's own tests use ports > 65535 (defect D8)
+        ist.ClientConfig(connection_type=ist.TYPE_RDMA, host_addr="h", service_port=92345).verify()
+    with pytest.raises(Exception):
+        ist.ClientConfig(connection_type=ist.TYPE_RDMA, host_addr="h", service_port=1,
+                         link_type="foo").verify()
+    with pytest.raises(Exception):
+        ist.ServerConfig(service_port=1, manage_port=2, minimal_allocate_size=8).verify()
+    with pytest.raises(Exception):
+        ist.ServerConfig(service_port=1, manage_port=0).verify()
+    ist.ServerConfig(service_port=1, manage_port=2).verify()
+    c = ist.ServerConfig()
+    assert (c.prealloc_size, c.minimal_allocate_size, c.num_stream, c.auto_increase) == \
+        (16, 64, 1, False)
+
+
+def test_noncontiguous_tensor_rejected(host_server):
+    _, port = host_server
+    conn = make_conn(port)
+    t = torch.zeros(64, 64).t()
+    with pytest.raises(Exception, match="contiguous"):
+        conn.register_mr(t)
+
+
+# ------------------------------------------------------------------ pool behaviour
+def _server(**kw):
+    from infinistore_b200 import _infinistore as m
+
+    cfg = m.ServerConfig()
+    cfg.service_port = 0
+    cfg.host = "127.0.0.1"
+    cfg.pool_backend = "host"
+    cfg.minimal_allocate_size = 16
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    srv = m.Server(cfg)
+    return srv, srv.start()
+
+
+def test_out_of_memory_is_reported_and_nothing_is_half_allocated():
+    srv, port = _server(prealloc_bytes=8 * 16384)
+    try:
+        conn = make_conn(port)
+        with pytest.raises(Exception):
+            conn.allocate_rdma([f"k{i}" for i in range(9)], 16384)  # 507, not a timeout (D3)
+        assert srv.kvmap_len() == 0 and srv.stats()["used_bytes"] == 0  # (D4)
+        ok = conn.allocate_rdma([f"k{i}" for i in range(8)], 16384)
+        assert len(ok) == 8
+        with pytest.raises(Exception):
+            conn.allocate_rdma(["one-more"], 16384)
+        assert srv.purge() == 8
+        assert len(conn.allocate_rdma(["one-more"], 16384)) == 1  # purge returns the space (D10)
+    finally:
+        srv.stop()
+
+
+def test_auto_increase_adds_segments_and_clients_map_them():
+    srv, port = _server(prealloc_bytes=8 * 16384, auto_increase=True)
+    try:
+        conn = make_conn(port)
+        src = torch.randn(20 * 4096)
+        dst = torch.zeros_like(src)
+        conn.register_mr(src)
+        keys = [f"k{i}" for i in range(20)]
+        blocks = conn.allocate_rdma(keys, 16384)
+        assert srv.stats()["segments"] >= 3
+        assert len(set(blocks["rkey"].tolist())) >= 3
+        conn.rdma_write_cache(src, [i * 4096 for i in range(20)], 4096, blocks)
+        conn.sync()
+        conn.read_cache(dst, [(k, i * 4096) for i, k in enumerate(keys)], 4096)
+        conn.sync()
+        assert torch.equal(src, dst)
+    finally:
+        srv.stop()
+
+
+def test_block_spanning_several_granules_and_short_reads():
+    srv, port = _server(prealloc_bytes=64 * 16384)
+    try:
+        conn = make_conn(port)
+        src = torch.randn(40000 // 4)
+        conn.register_mr(src)
+        b = conn.allocate_rdma(["big"], 40000)  # 3 granules
+        assert srv.stats()["used_bytes"] == 3 * 16384
+        conn.rdma_write_cache(src, [0], 10000, b)
+        conn.sync()
+        dst = torch.zeros(10000)
+        conn.read_cache(dst, [("big", 0)], 10000)
+        conn.sync()
+        assert torch.equal(src, dst)
+        with pytest.raises(Exception):  # never read past what was written
+            conn.read_cache(torch.zeros(20000), [("big", 0)], 20000)
+    finally:
+        srv.stop()
+
+
+def test_dead_writer_does_not_leave_reserved_keys(host_server):
+    srv, port = host_server
+    conn = make_conn(port)
+    conn.allocate_rdma(["orphan"], 4096)
+    assert srv.kvmap_len() == 1
+    conn.close()
+    deadline = time.time() + 5
+    while srv.kvmap_len() and time.time() < deadline:
+        time.sleep(0.01)
+    assert srv.kvmap_len() == 0 and srv.stats()["used_bytes"] == 0
+    conn2 = make_conn(port)
+    assert len(conn2.allocate_rdma(["orphan"], 4096)) == 1  # writable again
+
+
+def test_purge_while_reader_holds_lease(host_server):
+    srv, port = host_server
+    conn = make_conn(port)
+    src = torch.randn(4096)
+    conn.register_mr(src)
+    conn.rdma_write_cache(src, [0], 4096, conn.allocate_rdma(["p"], 16384))
+    conn.sync()
+    dst = torch.zeros(4096)
+    conn.read_cache(dst, [("p", 0)], 4096)  # lookup pins the block until the next sync
+    assert srv.purge() == 1
+    conn.sync()
+    assert srv.stats()["used_bytes"] == 0
+    assert not conn.check_exist("p")
+
+
+# ------------------------------------------------------------------ protocol hardening
+def _raw(port):
+    s = socket.create_connection(("127.0.0.1", port), timeout=5)
+    return s
+
+
+def _closed(s):
+    """True when the peer closed the connection (orderly EOF or reset)."""
+    try:
+        return s.recv(1) == b""
+    except (ConnectionResetError, BrokenPipeError):
+        return True
+
+
+def test_unknown_op_gets_400_and_server_survives(host_server):
+    srv, port = host_server
+    s = _raw(port)
+    s.sendall(struct.pack("<IcI", 0xDEADBEEF, b"Z", 0))
+    assert struct.unpack("<i", s.recv(4))[0] == 400
+    assert _closed(s)
+    # the reactor is not stuck (reference defect D11 spins forever here)
+    conn = make_conn(port)
+    assert not conn.check_exist("x")
+
+
+def test_bad_magic_closes_connection(host_server):
+    _, port = host_server
+    s = _raw(port)
+    s.sendall(struct.pack("<IcI", 0x12345678, b"C", 1) + b"x")
+    assert _closed(s)
+
+
+def test_oversized_body_is_refused(host_server):
+    _, port = host_server
+    s = _raw(port)
+    s.sendall(struct.pack("<IcI", 0xDEADBEEF, b"M", 0x7FFFFFFF))
+    assert struct.unpack("<i", s.recv(4))[0] == 400
+    assert _closed(s)
+
+
+def test_exchange_body_must_be_30_bytes(host_server):
+    _, port = host_server
+    s = _raw(port)
+    s.sendall(struct.pack("<IcI", 0xDEADBEEF, b"E", 64) + b"\0" * 64)
+    assert struct.unpack("<i", s.recv(4))[0] == 400
+
+
+def test_garbage_flatbuffer_gets_400_and_connection_stays_usable(host_server):
+    _, port = host_server
+    s = _raw(port)
+    junk = b"\xff" * 40
+    s.sendall(struct.pack("<IcI", 0xDEADBEEF, b"D", len(junk)) + junk)
+    assert struct.unpack("<i", s.recv(4))[0] == 400
+    s.sendall(struct.pack("<IcI", 0xDEADBEEF, b"C", 3) + b"abc")
+    code, val = struct.unpack("<ii", s.recv(8))
+    assert (code, val) == (200, 1)
+
+
+def test_request_split_across_tcp_segments(host_server):
+    from infinistore_b200 import _infinistore as m
+
+    _, port = host_server
+    s = _raw(port)
+    s.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+    body = m.testing.encode_match_request(["a", "b", "c"])
+    msg = struct.pack("<IcI", 0xDEADBEEF, b"M", len(body)) + body
+    for i in range(len(msg)):  # one byte per segment
+        s.sendall(msg[i:i + 1])
+        if i % 7 == 0:
+            time.sleep(0.001)
+    code, idx = struct.unpack("<ii", s.recv(8))
+    assert (code, idx) == (200, -1)
+    # two requests in one segment + SYNC with an uninitialised body_size (as the
+    # reference client sends it)
+    s.sendall(msg + struct.pack("<IcI", 0xDEADBEEF, b"S", 0xCCCCCCCC))
+    data = b""
+    while len(data) < 16:
+        data += s.recv(16 - len(data))
+    assert struct.unpack("<iiiI", data) == (200, -1, 200, 0)
+
+
+def test_fault_injection_dropped_request_surfaces_as_error(host_server):
+    srv, port = host_server
+    conn = make_conn(port, timeout_ms=2000)
+    srv.inject_drop_after(1)
+    with pytest.raises(Exception):
+        conn.check_exist("k")
+    conn2 = make_conn(port)
+    assert not conn2.check_exist("k")
+
+
+def test_many_keys_single_request(host_server):
+    _, port = host_server
+    conn = make_conn(port)
+    n = 2000
+    keys = [f"{i:08d}-" + rand_key(27) for i in range(n)]
+    src = torch.randn(n * 64)
+    dst = torch.zeros_like(src)
+    conn.register_mr(src)
+    blocks = conn.allocate_rdma(keys, 256)
+    assert len(set(blocks["remote_addr"].tolist())) == n
+    conn.rdma_write_cache(src, [i * 64 for i in range(n)], 64, blocks)
+    conn.sync()
+    conn.read_cache(dst, [(k, i * 64) for i, k in enumerate(keys)], 64)
+    conn.sync()
+    assert torch.equal(src, dst)
+    assert conn.get_match_last_index(keys) == n - 1
