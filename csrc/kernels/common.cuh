@@ -95,18 +95,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { 
                  "r"(bytes)
                  : "memory");
 }
+// Waits for the phase with the given parity.  try_wait suspends the thread in hardware for a
+// bounded time per attempt; a watchdog turns a lost completion (a bug) into a trap instead
+// of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {  // SYNCS.PHASECHK..TRYWAIT
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    long long start = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spins == 64) start = clock64();
+        if (spins > 64 && (spins & 1023) == 0 && clock64() - start > 8000000000ll) __trap();
+    }
 }
 // global -> shared, completion signalled on an mbarrier                      UBLKCP.S.G
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes,
