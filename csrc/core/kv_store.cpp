@@ -1,37 +1,49 @@
 #include "kv_store.h"
 
+#include <algorithm>
+
 #include "log.h"
 
 namespace istore {
 
+Block*& KVStore::inflight_slot(uint32_t seg, uint64_t offset) {
+    if (inflight_.size() <= seg) inflight_.resize(seg + 1);
+    std::vector<Block*>& v = inflight_[seg];
+    const MemoryPool& pool = mm_->pool(seg);
+    if (v.size() != pool.total_blocks()) v.assign(pool.total_blocks(), nullptr);
+    return v[offset / pool.granule()];
+}
+
 int KVStore::reserve(const std::vector<std::string_view>& keys, size_t size, int device_hint,
                      uint64_t conn, std::vector<RemoteBlock>& out) {
     out.assign(keys.size(), RemoteBlock{0, 0, 0});
-    // Decide about duplicates first (also duplicates inside the batch), then allocate
-    // exactly what is needed: nothing leaks for deduplicated keys.
-    std::vector<size_t> fresh;
+    // Decide about duplicates first, then allocate exactly what is needed: nothing leaks for
+    // deduplicated keys.  A placeholder entry per fresh key also catches duplicates inside
+    // the batch (the second occurrence finds the placeholder).
+    using Iter = decltype(map_)::iterator;
+    std::vector<std::pair<size_t, Iter>> fresh;
     fresh.reserve(keys.size());
-    {
-        std::unordered_map<std::string_view, size_t, StrHash, StrEq> seen;
-        seen.reserve(keys.size());
-        for (size_t i = 0; i < keys.size(); ++i) {
-            if (map_.find(keys[i]) != map_.end()) continue;
-            if (!seen.emplace(keys[i], i).second) continue;
-            fresh.push_back(i);
-        }
+    for (size_t i = 0; i < keys.size(); ++i) {
+        if (map_.find(keys[i]) != map_.end()) continue;
+        fresh.emplace_back(i, map_.emplace(std::string(keys[i]), nullptr).first);
     }
     std::vector<Allocation> allocs;
     allocs.reserve(fresh.size());
-    if (!mm_->allocate(size, fresh.size(), device_hint, allocs)) return kOutOfMemory;
+    if (!mm_->allocate(size, fresh.size(), device_hint, allocs)) {
+        for (auto& f : fresh) map_.erase(f.second);
+        return kOutOfMemory;
+    }
     for (size_t j = 0; j < fresh.size(); ++j) {
-        const size_t i = fresh[j];
+        const size_t i = fresh[j].first;
         uint32_t gen = next_gen_++;
         if (next_gen_ == 0) next_gen_ = 1;  // 0 means "not committed" in the device index
         auto blk = std::make_shared<Block>(mm_, allocs[j].seg, allocs[j].offset, uint32_t(size),
                                            gen, conn);
-        auto it = map_.emplace(std::string(keys[i]), blk).first;
-        inflight_[blk->addr()] = {blk, &it->first};
+        blk->key = &fresh[j].second->first;
+        inflight_slot(allocs[j].seg, allocs[j].offset) = blk.get();
+        ++inflight_count_;
         out[i] = RemoteBlock{allocs[j].seg + 1, gen, blk->addr()};
+        fresh[j].second->second = std::move(blk);
     }
     return kFinish;
 }
@@ -39,11 +51,16 @@ int KVStore::reserve(const std::vector<std::string_view>& keys, size_t size, int
 size_t KVStore::commit(const uint64_t* addrs, size_t n) {
     size_t done = 0;
     for (size_t i = 0; i < n; ++i) {
-        auto it = inflight_.find(addrs[i]);
-        if (it == inflight_.end()) continue;
-        it->second.first->committed = true;
-        it->second.first->owner = 0;
-        inflight_.erase(it);
+        const uint32_t seg = addr_seg(addrs[i]);
+        const uint64_t off = addr_off(addrs[i]);
+        if (seg >= mm_->num_pools() || off >= mm_->pool(seg).bytes()) continue;
+        Block*& slot = inflight_slot(seg, off);
+        Block* b = slot;
+        if (!b || b->offset != off) continue;  // unknown / already committed: ignored
+        b->committed = true;
+        b->owner = 0;
+        slot = nullptr;
+        --inflight_count_;
         ++done;
     }
     return done;
@@ -91,15 +108,17 @@ int KVStore::match_last_index(const std::vector<std::string_view>& keys) const {
 }
 
 size_t KVStore::drop_uncommitted(uint64_t conn) {
+    if (inflight_count_ == 0) return 0;
     size_t n = 0;
-    for (auto it = inflight_.begin(); it != inflight_.end();) {
-        if (it->second.first->owner == conn) {
-            const std::string key = *it->second.second;
-            it = inflight_.erase(it);
-            map_.erase(key);
+    for (auto& seg : inflight_) {
+        for (Block*& slot : seg) {
+            Block* b = slot;
+            if (!b || b->owner != conn) continue;
+            slot = nullptr;
+            --inflight_count_;
             ++n;
-        } else {
-            ++it;
+            const std::string key = *b->key;  // copy: erasing frees the node that owns it
+            map_.erase(key);
         }
     }
     return n;
@@ -107,7 +126,8 @@ size_t KVStore::drop_uncommitted(uint64_t conn) {
 
 size_t KVStore::purge() {
     const size_t n = map_.size();
-    inflight_.clear();
+    for (auto& seg : inflight_) std::fill(seg.begin(), seg.end(), nullptr);
+    inflight_count_ = 0;
     map_.clear();
     return n;
 }

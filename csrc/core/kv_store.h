@@ -33,6 +33,7 @@ struct Block {
     uint32_t gen;
     bool committed = false;
     uint64_t owner = 0;  // connection id that reserved it (0 once committed)
+    const std::string* key = nullptr;  // the map node's key (node addresses are stable)
     Block(MM* m, uint32_t s, uint64_t o, uint32_t sz, uint32_t g, uint64_t own)
         : mm(m), seg(s), offset(o), size(sz), gen(g), owner(own) {}
     ~Block() { mm->deallocate(seg, offset, size); }
@@ -77,13 +78,18 @@ class KVStore {
     size_t drop_uncommitted(uint64_t conn);
     size_t purge();
     size_t size() const { return map_.size(); }
-    size_t inflight() const { return inflight_.size(); }
+    size_t inflight() const { return inflight_count_; }
 
    private:
+    // In-flight (reserved, uncommitted) blocks are found by address in O(1): one slot per
+    // allocation granule of every pool, holding the block that starts there.
+    Block*& inflight_slot(uint32_t seg, uint64_t offset);
+
     MM* mm_;
     uint32_t next_gen_ = 1;
     std::unordered_map<std::string, BlockPtr, StrHash, StrEq> map_;
-    std::unordered_map<uint64_t, std::pair<BlockPtr, const std::string*>> inflight_;  // by addr
+    std::vector<std::vector<Block*>> inflight_;  // [segment][granule]
+    size_t inflight_count_ = 0;
 };
 
 }  // namespace istore

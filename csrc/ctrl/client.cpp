@@ -86,11 +86,56 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
 
 }  // namespace
 
+void PendingHashes::grow() {
+    std::vector<Slot> old;
+    old.swap(slots_);
+    slots_.assign(old.empty() ? 1024 : old.size() * 2, Slot{});
+    count_ = 0;
+    for (auto& sl : old)
+        if (sl.addr) put(sl.addr, sl.h);
+}
+
+void PendingHashes::put(uint64_t addr, const KeyHash& h) {
+    if ((count_ + 1) * 2 > slots_.size()) grow();
+    const size_t mask = slots_.size() - 1;
+    size_t i = mix(addr) & mask;
+    while (slots_[i].addr && slots_[i].addr != addr) i = (i + 1) & mask;
+    if (!slots_[i].addr) ++count_;
+    slots_[i].addr = addr;
+    slots_[i].h = h;
+}
+
+bool PendingHashes::take(uint64_t addr, KeyHash* out) {
+    if (slots_.empty()) return false;
+    const size_t mask = slots_.size() - 1;
+    size_t i = mix(addr) & mask;
+    while (slots_[i].addr != addr) {
+        if (!slots_[i].addr) return false;
+        i = (i + 1) & mask;
+    }
+    *out = slots_[i].h;
+    // backward-shift deletion keeps probe sequences intact without tombstones
+    size_t j = i;
+    for (;;) {
+        j = (j + 1) & mask;
+        if (!slots_[j].addr) break;
+        const size_t home = mix(slots_[j].addr) & mask;
+        if ((i <= j) ? (home <= i || home > j) : (home <= i && home > j)) {
+            slots_[i] = slots_[j];
+            i = j;
+        }
+    }
+    slots_[i].addr = 0;
+    --count_;
+    return true;
+}
+
 // Per-device data-plane state.
 struct Connection::DevCtx {
     int device = -1;
     cudaStream_t stream = nullptr;
     std::vector<std::shared_ptr<fabric::Mapping>> maps;  // by segment id
+    std::vector<uint8_t*> seg_ptr;  // maps[i]->dev_ptr, cached for the per-block hot loop
     uint8_t* ring_h = nullptr;  // pinned + mapped: descriptors, publish records, key bytes
     uint8_t* ring_d = nullptr;
     size_t ring_head = 0;
@@ -100,15 +145,12 @@ struct Connection::DevCtx {
     size_t zeros_head = 0;
     uint32_t* status_h = nullptr;
     uint32_t* status_d = nullptr;
-    std::vector<std::pair<cudaStream_t, cudaEvent_t>> events;  // last launch per stream
+    std::vector<cudaStream_t> busy;  // streams with launches since the last wait_all()
     bool dirty = false;
 
     ~DevCtx() {
         DeviceGuard g(device);
-        for (auto& e : events) {
-            cudaEventSynchronize(e.second);
-            cudaEventDestroy(e.second);
-        }
+        wait_all();
         if (stream) {
             cudaStreamSynchronize(stream);
             cudaStreamDestroy(stream);
@@ -122,21 +164,15 @@ struct Connection::DevCtx {
 
     void wait_all() {
         DeviceGuard g(device);
-        for (auto& e : events) cudaEventSynchronize(e.second);
+        for (cudaStream_t s : busy) cudaStreamSynchronize(s);
+        busy.clear();
         dirty = false;
     }
     void mark(cudaStream_t s) {
-        for (auto& e : events)
-            if (e.first == s) {
-                cudaEventRecord(e.second, s);
-                dirty = true;
-                return;
-            }
-        cudaEvent_t ev;
-        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-        cudaEventRecord(ev, s);
-        events.emplace_back(s, ev);
         dirty = true;
+        for (cudaStream_t b : busy)
+            if (b == s) return;
+        busy.push_back(s);
     }
     // Bump allocators.  When a region wraps, everything launched from it must be done.
     size_t ring_alloc(size_t bytes) {
@@ -358,7 +394,7 @@ int Connection::refresh_pool_map() {
 
 int Connection::check_exist(const std::string& key) {
     if (device_lookup_ && server_hbm_) {
-        const int r = match_via_device_index({key}, true);
+        const int r = match_via_device_index({std::string_view(key)}, true);
         if (r >= -1) return r == 0 ? 0 : 1;
     }
     int32_t code = 0;
@@ -371,13 +407,13 @@ int Connection::check_exist(const std::string& key) {
     return v;
 }
 
-int Connection::get_match_last_index(const std::vector<std::string>& keys) {
+int Connection::get_match_last_index(const std::vector<std::string_view>& keys) {
     if (keys.empty()) return -1;
     if (device_lookup_ && server_hbm_) {
         const int r = match_via_device_index(keys, false);
         if (r >= -1) return r;
     }
-    std::vector<std::string_view> kv(keys.begin(), keys.end());
+    const std::vector<std::string_view>& kv = keys;
     std::vector<uint8_t> buf(remote_meta_bound(kv, 0));
     fb::Builder b(buf.data(), buf.size());
     encode_match_request(b, kv);
@@ -438,11 +474,11 @@ int Connection::flush_commits() {
     return 0;
 }
 
-int Connection::allocate(const std::vector<std::string>& keys, int block_size,
+int Connection::allocate(const std::vector<std::string_view>& keys, int block_size,
                          std::vector<RemoteBlock>& out) {
     out.clear();
     if (keys.empty() || block_size <= 0) return -1;
-    std::vector<std::string_view> kv(keys.begin(), keys.end());
+    const std::vector<std::string_view>& kv = keys;
     std::vector<uint8_t> buf(remote_meta_bound(kv, 0));
     if (buf.size() > kMaxBody) {
         fail("allocate: too many keys for one request");
@@ -468,8 +504,9 @@ int Connection::allocate(const std::vector<std::string>& keys, int block_size,
         std::lock_guard<std::mutex> lk(mu_);
         for (size_t i = 0; i < keys.size(); ++i) {
             if (is_fake_block(out[i])) continue;
-            pending_hash_[out[i].remote_addr] =
-                hash_key(reinterpret_cast<const uint8_t*>(keys[i].data()), keys[i].size());
+            pending_hash_.put(out[i].remote_addr,
+                              hash_key(reinterpret_cast<const uint8_t*>(keys[i].data()),
+                                       keys[i].size()));
         }
     }
     return 0;
@@ -607,57 +644,69 @@ int Connection::register_mr(uint64_t ptr, size_t size, int device) {
     return 1;
 }
 
-// Move n blocks between the caller's tensor and the pool.
-int Connection::move_blocks(bool write, const uint64_t* local_off, const RemoteBlock* blocks,
-                            size_t n, int block_size, uint64_t base_ptr, int device,
-                            uint64_t stream_in) {
+// Resolve the device pointer of a pool segment for `ctx` (slow path: map it first).
+uint8_t* Connection::seg_dev_ptr(DevCtx* ctx, uint32_t seg) {
+    if (seg < ctx->seg_ptr.size() && ctx->seg_ptr[seg]) return ctx->seg_ptr[seg];
+    auto mp = mapping(seg, ctx->device);
+    if (!mp || !mp->dev_ptr) {
+        fail("pool segment " + std::to_string(seg) + " is not addressable from device " +
+             std::to_string(ctx->device));
+        return nullptr;
+    }
+    if (ctx->seg_ptr.size() <= seg) ctx->seg_ptr.resize(seg + 1, nullptr);
+    ctx->seg_ptr[seg] = mp->dev_ptr;
+    return mp->dev_ptr;
+}
+
+// Move n blocks between the caller's tensor and the pool.  local_off[i] * scale is the
+// byte offset of block i from base_ptr.
+int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scale,
+                            const RemoteBlock* blocks, size_t n, int block_size,
+                            uint64_t base_ptr, int device, uint64_t stream_in) {
     std::lock_guard<std::mutex> lk(mu_);
-    // --- classify
-    bool all_host_segs = true;
-    size_t live = 0;
-    uint64_t max_off = 0;
-    for (size_t i = 0; i < n; ++i) {
-        if (write && is_fake_block(blocks[i])) continue;  // dedup: first writer wins
-        const uint32_t seg = addr_seg(blocks[i].remote_addr);
-        if (seg >= segs_.size() && refresh_pool_map() != 0) return -1;
-        if (seg >= segs_.size()) {
-            fail("block refers to unknown segment");
+    if (n == 0) return 0;
+    int kd = device;
+    if (device < 0) {
+        // host tensor: memcpy when every target segment is host memory, else a kernel on
+        // the connection's default device reads / writes the (pinned) host tensor
+        bool all_host_segs = true;
+        size_t live = 0;
+        uint64_t max_off = 0;
+        for (size_t i = 0; i < n; ++i) {
+            if (write && is_fake_block(blocks[i])) continue;  // dedup: first writer wins
+            const uint32_t seg = addr_seg(blocks[i].remote_addr);
+            if (seg >= segs_.size() && refresh_pool_map() != 0) return -1;
+            if (seg >= segs_.size()) {
+                fail("block refers to unknown segment");
+                return -1;
+            }
+            if (segs_[seg].kind != kSegHostShm) all_host_segs = false;
+            max_off = std::max(max_off, local_off[i] * scale);
+            ++live;
+        }
+        if (live == 0) return 0;
+        if (all_host_segs) {
+            for (size_t i = 0; i < n; ++i) {
+                if (write && is_fake_block(blocks[i])) continue;
+                auto m = mapping(addr_seg(blocks[i].remote_addr), -1);
+                if (!m || !m->host_ptr) return -1;
+                uint8_t* pool = m->host_ptr + addr_off(blocks[i].remote_addr);
+                uint8_t* local = reinterpret_cast<uint8_t*>(base_ptr + local_off[i] * scale);
+                if (write)
+                    std::memcpy(pool, local, size_t(block_size));
+                else
+                    std::memcpy(local, pool, size_t(block_size));
+                if (write) pending_commit_.push_back(blocks[i].remote_addr);
+                stats_.host_copies++;
+            }
+            (write ? stats_.bytes_written : stats_.bytes_read) += live * uint64_t(block_size);
+            return 0;
+        }
+        if (!fabric::cuda_available()) {
+            fail("a CUDA device is required to reach an HBM pool");
             return -1;
         }
-        if (segs_[seg].kind != kSegHostShm) all_host_segs = false;
-        max_off = std::max(max_off, local_off[i]);
-        ++live;
-    }
-    if (live == 0) return 0;
-
-    // --- pure host path: CPU tensor <-> host pool
-    if (device < 0 && all_host_segs) {
-        for (size_t i = 0; i < n; ++i) {
-            if (write && is_fake_block(blocks[i])) continue;
-            auto m = mapping(addr_seg(blocks[i].remote_addr), -1);
-            if (!m || !m->host_ptr) return -1;
-            uint8_t* pool = m->host_ptr + addr_off(blocks[i].remote_addr);
-            uint8_t* local = reinterpret_cast<uint8_t*>(base_ptr + local_off[i]);
-            if (write)
-                std::memcpy(pool, local, size_t(block_size));
-            else
-                std::memcpy(local, pool, size_t(block_size));
-            if (write) pending_commit_.push_back(blocks[i].remote_addr);
-            stats_.host_copies++;
-        }
-        (write ? stats_.bytes_written : stats_.bytes_read) += live * uint64_t(block_size);
-        return 0;
-    }
-
-    // --- kernel path on `kd`
-    if (!fabric::cuda_available()) {
-        fail("a CUDA device is required to reach an HBM pool");
-        return -1;
-    }
-    int kd = device;
-    if (kd < 0) {
         kd = cfg_.device >= 0 ? cfg_.device : std::max(default_device_, 0);
-        // make the host tensor addressable by the kernel
         auto mr = mrs_.find(base_ptr);
         const size_t span = mr != mrs_.end() ? mr->second : size_t(max_off) + size_t(block_size);
         if (ensure_host_registered(base_ptr, span, kd) != 0) {
@@ -665,50 +714,64 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, const RemoteB
             return -1;
         }
     }
+
+    // --- kernel path on `kd`
     DevCtx* ctx = dev_ctx(kd);
     if (!ctx) return -1;
     DeviceGuard g(kd);
     cudaStream_t stream = stream_in ? reinterpret_cast<cudaStream_t>(stream_in) : ctx->stream;
 
+    // the device index lives in segment 0
+    kernels::IndexEntry* table = nullptr;
+    uint64_t table_mask = 0;
+    if (write && !segs_.empty() && segs_[0].index_slots) {
+        if (uint8_t* p0 = seg_dev_ptr(ctx, 0)) {
+            table = reinterpret_cast<kernels::IndexEntry*>(p0 + segs_[0].index_off);
+            table_mask = segs_[0].index_slots - 1;
+        }
+    }
+
     size_t i = 0;
     while (i < n) {
-        // gather up to kMaxBatch live blocks
         const size_t batch_cap = std::min(kMaxBatch, n - i);
         const size_t at_desc = ctx->ring_alloc(batch_cap * sizeof(kernels::CopyDesc));
         auto* descs = reinterpret_cast<kernels::CopyDesc*>(ctx->ring_h + at_desc);
-        const bool publish = write;
         size_t at_rec = 0;
         kernels::IndexEntry* recs = nullptr;
-        if (publish) {
+        if (table) {
             at_rec = ctx->ring_alloc(batch_cap * sizeof(kernels::IndexEntry));
             recs = reinterpret_cast<kernels::IndexEntry*>(ctx->ring_h + at_rec);
         }
         uint32_t m = 0;
-        bool can_publish = publish;
-        const fabric::Mapping* index_map = nullptr;
+        bool can_publish = table != nullptr;
+        uint64_t align_or = 0;
+        const size_t nseg = ctx->seg_ptr.size();
+        uint8_t* const* seg_ptr = ctx->seg_ptr.data();
         for (; i < n && m < batch_cap; ++i) {
-            if (write && is_fake_block(blocks[i])) continue;
-            const uint32_t seg = addr_seg(blocks[i].remote_addr);
-            auto mp = mapping(seg, kd);
-            if (!mp || !mp->dev_ptr) {
-                fail("pool segment is not addressable from device " + std::to_string(kd));
-                return -1;
+            const RemoteBlock& rb = blocks[i];
+            if (write && is_fake_block(rb)) continue;
+            const uint32_t seg = addr_seg(rb.remote_addr);
+            uint8_t* segbase = seg < nseg ? seg_ptr[seg] : nullptr;
+            if (!segbase) {
+                segbase = seg_dev_ptr(ctx, seg);
+                if (!segbase) return -1;
+                seg_ptr = ctx->seg_ptr.data();
             }
-            const uint64_t pool = reinterpret_cast<uint64_t>(mp->dev_ptr) +
-                                  addr_off(blocks[i].remote_addr);
-            const uint64_t local = base_ptr + local_off[i];
-            descs[m] = write ? kernels::CopyDesc{local, pool} : kernels::CopyDesc{pool, local};
-            if (publish) {
-                auto h = pending_hash_.find(blocks[i].remote_addr);
-                if (h == pending_hash_.end()) {
-                    can_publish = false;
-                } else {
-                    recs[m] = kernels::IndexEntry{h->second.h1, h->second.h2,
-                                                  blocks[i].remote_addr, blocks[i].gen,
-                                                  uint32_t(block_size)};
-                    pending_hash_.erase(h);
+            const uint64_t pool = reinterpret_cast<uint64_t>(segbase) + addr_off(rb.remote_addr);
+            const uint64_t local = base_ptr + local_off[i] * scale;
+            align_or |= local;
+            descs[m].src = write ? local : pool;
+            descs[m].dst = write ? pool : local;
+            if (write) {
+                if (recs) {
+                    KeyHash kh;
+                    if (pending_hash_.take(rb.remote_addr, &kh))
+                        recs[m] = kernels::IndexEntry{kh.h1, kh.h2, rb.remote_addr, rb.gen,
+                                                      uint32_t(block_size)};
+                    else
+                        can_publish = false;  // not allocated through this connection
                 }
-                pending_commit_.push_back(blocks[i].remote_addr);
+                pending_commit_.push_back(rb.remote_addr);
             }
             ++m;
         }
@@ -717,20 +780,15 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, const RemoteB
         L.descs = reinterpret_cast<const kernels::CopyDesc*>(ctx->ring_d + at_desc);
         L.n = m;
         L.bytes = uint32_t(block_size);
+        L.align_or = align_or;
         L.status = ctx->status_d;
         L.variant = copy_variant_;
         L.max_ctas = max_ctas_;
         if (can_publish) {
-            // the device index lives in segment 0
-            auto m0 = mapping(0, kd);
-            if (m0 && m0->dev_ptr && m0->info.index_slots) {
-                index_map = m0.get();
-                L.recs = reinterpret_cast<const kernels::IndexEntry*>(ctx->ring_d + at_rec);
-                L.table = reinterpret_cast<kernels::IndexEntry*>(index_map->dev_ptr +
-                                                                 index_map->info.index_off);
-                L.table_mask = index_map->info.index_slots - 1;
-                L.done = reinterpret_cast<uint32_t*>(ctx->zeros + ctx->zeros_alloc(m * 4));
-            }
+            L.recs = reinterpret_cast<const kernels::IndexEntry*>(ctx->ring_d + at_rec);
+            L.table = table;
+            L.table_mask = table_mask;
+            L.done = reinterpret_cast<uint32_t*>(ctx->zeros + ctx->zeros_alloc(size_t(m) * 4));
         }
         const cudaError_t e = kernels::launch_kv_copy(L, stream);
         if (e != cudaSuccess) {
@@ -744,19 +802,15 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, const RemoteB
     return 0;
 }
 
-int Connection::w_rdma(const std::vector<uint64_t>& offsets, int block_size,
+int Connection::w_rdma(const uint64_t* offsets, size_t noffsets, uint64_t scale, int block_size,
                        const RemoteBlock* blocks, size_t nblocks, uint64_t base_ptr, int device,
                        uint64_t stream) {
-    if (offsets.size() != nblocks) {
+    if (noffsets != nblocks) {
         fail("w_rdma: offsets and remote blocks differ in length");
         return -1;
     }
-    {
-        // C10: the tensor must be the one that was registered (lookup by base pointer)
-        std::lock_guard<std::mutex> lk(mu_);
-        if (!mrs_.count(base_ptr)) LOG_DEBUG("w_rdma on an unregistered base pointer");
-    }
-    return move_blocks(true, offsets.data(), blocks, nblocks, block_size, base_ptr, device, stream);
+    return move_blocks(true, offsets, scale, blocks, nblocks, block_size, base_ptr, device,
+                       stream);
 }
 
 int Connection::r_rdma(const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr,
@@ -769,7 +823,7 @@ int Connection::r_rdma(const std::vector<KeyOffset>& blocks, int block_size, uin
     if (r != 0) return r;
     std::vector<uint64_t> offs(blocks.size());
     for (size_t i = 0; i < blocks.size(); ++i) offs[i] = blocks[i].offset;
-    return move_blocks(false, offs.data(), rb.data(), rb.size(), block_size, base_ptr, device,
+    return move_blocks(false, offs.data(), 1, rb.data(), rb.size(), block_size, base_ptr, device,
                        stream);
 }
 
@@ -786,23 +840,24 @@ int Connection::rw_local(char op, const std::vector<KeyOffset>& blocks, int bloc
         std::lock_guard<std::mutex> lk(mu_);
         for (size_t i = 0; i < blocks.size(); ++i) {
             if (is_fake_block(rb[i])) continue;
-            pending_hash_[rb[i].remote_addr] = hash_key(
-                reinterpret_cast<const uint8_t*>(blocks[i].key.data()), blocks[i].key.size());
+            pending_hash_.put(rb[i].remote_addr,
+                              hash_key(reinterpret_cast<const uint8_t*>(blocks[i].key.data()),
+                                       blocks[i].key.size()));
         }
     }
     std::vector<uint64_t> offs(blocks.size());
     for (size_t i = 0; i < blocks.size(); ++i) offs[i] = blocks[i].offset;
-    return move_blocks(op == kOpLocalWrite, offs.data(), rb.data(), rb.size(), block_size,
+    return move_blocks(op == kOpLocalWrite, offs.data(), 1, rb.data(), rb.size(), block_size,
                        base_ptr, device, stream);
 }
 
 // Pack keys into the pinned ring so that the lookup kernel can hash them: each key starts
 // on an 8-byte boundary and is zero padded to a multiple of 8.
-static size_t pack_keys(const std::string* const* keys, size_t n, uint8_t* bytes, uint32_t* off,
+static size_t pack_keys(const std::string_view* keys, size_t n, uint8_t* bytes, uint32_t* off,
                         uint32_t* len) {
     size_t at = 0;
     for (size_t i = 0; i < n; ++i) {
-        const std::string& k = *keys[i];
+        const std::string_view k = keys[i];
         off[i] = uint32_t(at);
         len[i] = uint32_t(k.size());
         const size_t padded = align_up(k.size() ? k.size() : 1, 8);
@@ -828,10 +883,10 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
     for (size_t base = 0; base < blocks.size(); base += kMaxBatch) {
         const size_t n = std::min(kMaxBatch, blocks.size() - base);
         size_t key_bytes = 0;
-        std::vector<const std::string*> kp(n);
+        std::vector<std::string_view> kp(n);
         for (size_t i = 0; i < n; ++i) {
-            kp[i] = &blocks[base + i].key;
-            key_bytes += align_up(std::max<size_t>(kp[i]->size(), 1), 8);
+            kp[i] = blocks[base + i].key;
+            key_bytes += align_up(std::max<size_t>(kp[i].size(), 1), 8);
         }
         const size_t at_bytes = ctx->ring_alloc(key_bytes);
         const size_t at_off = ctx->ring_alloc(n * 4);
@@ -851,10 +906,8 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
         Q.table = reinterpret_cast<const kernels::IndexEntry*>(m0->dev_ptr + m0->info.index_off);
         Q.table_mask = m0->info.index_slots - 1;
         Q.nsegs = uint32_t(std::min<size_t>(segs_.size(), kernels::LookupLaunch::kMaxSegs));
-        for (uint32_t s = 0; s < Q.nsegs; ++s) {
-            auto mp = mapping(s, device);
-            Q.seg_base[s] = mp && mp->dev_ptr ? reinterpret_cast<uint64_t>(mp->dev_ptr) : 0;
-        }
+        for (uint32_t s = 0; s < Q.nsegs; ++s)
+            Q.seg_base[s] = reinterpret_cast<uint64_t>(seg_dev_ptr(ctx, s));
         auto* out = reinterpret_cast<kernels::CopyDesc*>(
             ctx->scratch + ctx->scratch_alloc(n * sizeof(kernels::CopyDesc)));
         Q.out_descs = out;
@@ -884,7 +937,7 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
     return 0;
 }
 
-int Connection::match_via_device_index(const std::vector<std::string>& keys, bool exist_only) {
+int Connection::match_via_device_index(const std::vector<std::string_view>& keys, bool exist_only) {
     std::lock_guard<std::mutex> lk(mu_);
     const int device = cfg_.device >= 0 ? cfg_.device : std::max(default_device_, 0);
     DevCtx* ctx = dev_ctx(device);
@@ -893,9 +946,9 @@ int Connection::match_via_device_index(const std::vector<std::string>& keys, boo
     if (!m0 || !m0->dev_ptr || !m0->info.index_slots) return -3;
     const size_t n = keys.size();
     size_t key_bytes = 0;
-    std::vector<const std::string*> kp(n);
+    std::vector<std::string_view> kp(n);
     for (size_t i = 0; i < n; ++i) {
-        kp[i] = &keys[i];
+        kp[i] = keys[i];
         key_bytes += align_up(std::max<size_t>(keys[i].size(), 1), 8);
     }
     if (key_bytes + n * 8 + 4096 > kRingBytes / 2) return -3;  // too large: use the control plane
@@ -986,7 +1039,8 @@ void Connection::worker() {
         if (t.kind == Task::kStop) return;
         if (t.kind == Task::kAllocate) {
             std::vector<RemoteBlock> out;
-            if (allocate(t.keys, t.block_size, out) != 0) out.clear();
+            std::vector<std::string_view> kv(t.keys.begin(), t.keys.end());
+            if (allocate(kv, t.block_size, out) != 0) out.clear();
             if (t.alloc_cb) t.alloc_cb(std::move(out));
         } else {
             int status = t.status;
@@ -1020,7 +1074,8 @@ int Connection::allocate_async(const std::vector<std::string>& keys, int block_s
 int Connection::w_rdma_async(const std::vector<uint64_t>& offsets, int block_size,
                              const RemoteBlock* blocks, size_t nblocks, uint64_t base_ptr,
                              int device, uint64_t stream, std::function<void(int)> cb) {
-    const int r = w_rdma(offsets, block_size, blocks, nblocks, base_ptr, device, stream);
+    const int r = w_rdma(offsets.data(), offsets.size(), 1, block_size, blocks, nblocks, base_ptr,
+                         device, stream);
     Task t;
     t.kind = Task::kWaitEvent;
     t.status = r;

@@ -20,6 +20,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <string_view>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -31,9 +32,30 @@
 
 namespace istore {
 
+// Non-owning: the key bytes must stay valid for the duration of the call.
 struct KeyOffset {
-    std::string key;
+    std::string_view key;
     uint64_t offset;  // bytes from the tensor base
+};
+
+// addr -> key fingerprint of blocks that were allocated but not written yet.  Open
+// addressing with backward-shift deletion: entries live for microseconds (allocate ->
+// write), and the write path looks one up per block, so this must be a few ns per op.
+class PendingHashes {
+   public:
+    void put(uint64_t addr, const KeyHash& h);
+    bool take(uint64_t addr, KeyHash* out);  // find + erase
+    size_t size() const { return count_; }
+
+   private:
+    struct Slot {
+        uint64_t addr = 0;  // 0 = empty (block addresses are never 0)
+        KeyHash h{};
+    };
+    void grow();
+    static size_t mix(uint64_t a) { return size_t((a * 0x9e3779b97f4a7c15ull) >> 20); }
+    std::vector<Slot> slots_;
+    size_t count_ = 0;
 };
 
 struct ClientStats {
@@ -60,17 +82,19 @@ class Connection {
 
     // --- metadata
     int check_exist(const std::string& key);  // 0 = exists & committed, 1 = not, <0 error
-    int get_match_last_index(const std::vector<std::string>& keys);  // index, -1 none, <-1 error
+    int get_match_last_index(const std::vector<std::string_view>& keys);  // index, -1 none, <-1 error
     int sync_local();  // remaining server-side tasks (always 0 here) or <0
     int sync_rdma();   // drain kernels + async ops, commit, control-plane barrier
 
     // --- data plane.  `device` is the CUDA ordinal owning base_ptr, -1 for host memory;
     //     `stream` is a cudaStream_t to order after (0 = the connection's own stream).
     int register_mr(uint64_t ptr, size_t size, int device);
-    int allocate(const std::vector<std::string>& keys, int block_size,
+    int allocate(const std::vector<std::string_view>& keys, int block_size,
                  std::vector<RemoteBlock>& out);
-    int w_rdma(const std::vector<uint64_t>& offsets, int block_size, const RemoteBlock* blocks,
-               size_t nblocks, uint64_t base_ptr, int device, uint64_t stream);
+    // offsets[i] * scale = byte offset of block i (scale lets callers pass element offsets)
+    int w_rdma(const uint64_t* offsets, size_t noffsets, uint64_t scale, int block_size,
+               const RemoteBlock* blocks, size_t nblocks, uint64_t base_ptr, int device,
+               uint64_t stream);
     int r_rdma(const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr, int device,
                uint64_t stream);
     int rw_local(char op, const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr,
@@ -110,11 +134,13 @@ class Connection {
     // data plane
     DevCtx* dev_ctx(int device);
     std::shared_ptr<fabric::Mapping> mapping(uint32_t seg, int device);
-    int move_blocks(bool write, const uint64_t* local_off, const RemoteBlock* blocks, size_t n,
-                    int block_size, uint64_t base_ptr, int device, uint64_t stream);
+    int move_blocks(bool write, const uint64_t* local_off, uint64_t scale,
+                    const RemoteBlock* blocks, size_t n, int block_size, uint64_t base_ptr,
+                    int device, uint64_t stream);
+    uint8_t* seg_dev_ptr(DevCtx* ctx, uint32_t seg);
     int read_via_device_index(const std::vector<KeyOffset>& blocks, int block_size,
                               uint64_t base_ptr, int device, uint64_t stream);
-    int match_via_device_index(const std::vector<std::string>& keys, bool exist_only);
+    int match_via_device_index(const std::vector<std::string_view>& keys, bool exist_only);
     int ensure_host_registered(uint64_t ptr, size_t bytes, int device);
     int drain_devices();
     void fail(const std::string& msg);
@@ -134,7 +160,7 @@ class Connection {
     std::mutex mu_;  // guards the data-plane state below
     std::map<int, std::unique_ptr<DevCtx>> devs_;
     std::vector<std::shared_ptr<fabric::Mapping>> host_maps_;  // CPU view of host segments
-    std::unordered_map<uint64_t, KeyHash> pending_hash_;  // allocated addr -> key fingerprint
+    PendingHashes pending_hash_;  // allocated addr -> key fingerprint
     std::vector<uint64_t> pending_commit_;
     struct HostReg {
         size_t bytes;

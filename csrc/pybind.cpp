@@ -15,8 +15,10 @@
 
 #include <cuda_runtime_api.h>
 
+#include <cstring>
 #include <memory>
 #include <mutex>
+#include <string_view>
 
 #include "core/config.h"
 #include "core/hash.h"
@@ -44,17 +46,32 @@ py::array_t<RemoteBlock> blocks_to_array(std::vector<RemoteBlock>&& v) {
     return py::array_t<RemoteBlock>(heap->size(), heap->data(), owner);
 }
 
-// remote blocks arrive as the structured array returned by allocate (possibly sliced)
-std::vector<RemoteBlock> blocks_from_py(const py::object& obj) {
-    std::vector<RemoteBlock> out;
+// Remote blocks arrive as the structured array returned by allocate (possibly sliced):
+// used in place when contiguous; otherwise converted into `tmp`.
+struct BlockSpan {
+    const RemoteBlock* data = nullptr;
+    size_t n = 0;
+    std::vector<RemoteBlock> tmp;
+    py::object keep;
+};
+
+void blocks_from_py(const py::object& obj, BlockSpan& out) {
     if (py::isinstance<py::array>(obj)) {
-        py::array arr = py::array::ensure(obj);
-        if (arr.itemsize() == sizeof(RemoteBlock)) {
-            auto a = py::array_t<RemoteBlock, py::array::c_style | py::array::forcecast>(arr);
-            auto r = a.unchecked<1>();
-            out.resize(size_t(r.shape(0)));
-            for (py::ssize_t i = 0; i < r.shape(0); ++i) out[size_t(i)] = r(i);
-            return out;
+        py::array arr = py::reinterpret_borrow<py::array>(obj);
+        if (arr.itemsize() == sizeof(RemoteBlock) && arr.ndim() == 1) {
+            if (arr.strides(0) == py::ssize_t(sizeof(RemoteBlock))) {
+                out.data = static_cast<const RemoteBlock*>(arr.data());
+                out.n = size_t(arr.shape(0));
+                out.keep = arr;
+                return;
+            }
+            out.tmp.resize(size_t(arr.shape(0)));
+            const char* base = static_cast<const char*>(arr.data());
+            for (py::ssize_t i = 0; i < arr.shape(0); ++i)
+                std::memcpy(&out.tmp[size_t(i)], base + i * arr.strides(0), sizeof(RemoteBlock));
+            out.data = out.tmp.data();
+            out.n = out.tmp.size();
+            return;
         }
     }
     for (auto item : obj) {  // list of (rkey, remote_addr) or (rkey, gen, remote_addr)
@@ -68,16 +85,136 @@ std::vector<RemoteBlock> blocks_from_py(const py::object& obj) {
             b.gen = t[1].cast<uint32_t>();
             b.remote_addr = t[2].cast<uint64_t>();
         }
-        out.push_back(b);
+        out.tmp.push_back(b);
     }
-    return out;
+    out.data = out.tmp.data();
+    out.n = out.tmp.size();
 }
 
-std::vector<KeyOffset> key_offsets(const std::vector<std::pair<std::string, uint64_t>>& v) {
-    std::vector<KeyOffset> out;
-    out.reserve(v.size());
-    for (auto& p : v) out.push_back(KeyOffset{p.first, p.second});
-    return out;
+// Offsets: a contiguous int64/uint64 numpy array is used in place, anything else is
+// converted element by element with the C API.
+struct OffsetSpan {
+    const uint64_t* data = nullptr;
+    size_t n = 0;
+    std::vector<uint64_t> tmp;
+    py::object keep;
+};
+
+void offsets_from_py(const py::object& obj, OffsetSpan& out) {
+    if (py::isinstance<py::array>(obj)) {
+        py::array arr = py::reinterpret_borrow<py::array>(obj);
+        const char kind = arr.dtype().kind();
+        if ((kind == 'i' || kind == 'u') && arr.itemsize() == 8 && arr.ndim() == 1 &&
+            arr.strides(0) == 8) {
+            out.data = static_cast<const uint64_t*>(arr.data());
+            out.n = size_t(arr.shape(0));
+            out.keep = arr;
+            return;
+        }
+    }
+    PyObject* seq = PySequence_Fast(obj.ptr(), "offsets must be a sequence of integers");
+    if (!seq) throw py::error_already_set();
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);
+    out.tmp.resize(size_t(n));
+    for (Py_ssize_t i = 0; i < n; ++i) {
+        const unsigned long long v = PyLong_AsUnsignedLongLong(PySequence_Fast_GET_ITEM(seq, i));
+        if (v == (unsigned long long)-1 && PyErr_Occurred()) {
+            Py_DECREF(seq);
+            throw py::error_already_set();
+        }
+        out.tmp[size_t(i)] = v;
+    }
+    Py_DECREF(seq);
+    out.data = out.tmp.data();
+    out.n = out.tmp.size();
+}
+
+// Keys are copied once into a per-thread arena while the GIL is held; the views stay valid
+// after the GIL is released for the (possibly blocking) native call.
+struct KeyArena {
+    std::vector<char> bytes;
+    std::vector<std::pair<size_t, size_t>> spans;  // offset, length
+    void clear() {
+        bytes.clear();
+        spans.clear();
+    }
+    void add(PyObject* o) {
+        const char* p = nullptr;
+        Py_ssize_t n = 0;
+        if (PyUnicode_Check(o)) {
+            p = PyUnicode_AsUTF8AndSize(o, &n);
+            if (!p) throw py::error_already_set();
+        } else if (PyBytes_Check(o)) {
+            p = PyBytes_AS_STRING(o);
+            n = PyBytes_GET_SIZE(o);
+        } else {
+            throw py::type_error("keys must be str or bytes");
+        }
+        spans.emplace_back(bytes.size(), size_t(n));
+        bytes.insert(bytes.end(), p, p + n);
+    }
+    std::string_view view(size_t i) const {
+        return std::string_view(bytes.data() + spans[i].first, spans[i].second);
+    }
+};
+
+thread_local KeyArena t_arena;
+
+// [(key, offset), ...] -> KeyOffset views (offset * scale bytes)
+void blocks_list_from_py(const py::object& obj, uint64_t scale, std::vector<KeyOffset>& out) {
+    KeyArena& a = t_arena;
+    a.clear();
+    PyObject* seq = PySequence_Fast(obj.ptr(), "blocks must be a sequence of (key, offset)");
+    if (!seq) throw py::error_already_set();
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);
+    std::vector<uint64_t> offs;
+    offs.resize(size_t(n));
+    for (Py_ssize_t i = 0; i < n; ++i) {
+        PyObject* item = PySequence_Fast_GET_ITEM(seq, i);
+        PyObject *k, *o;
+        if (PyTuple_Check(item) && PyTuple_GET_SIZE(item) == 2) {
+            k = PyTuple_GET_ITEM(item, 0);
+            o = PyTuple_GET_ITEM(item, 1);
+        } else if (PyList_Check(item) && PyList_GET_SIZE(item) == 2) {
+            k = PyList_GET_ITEM(item, 0);
+            o = PyList_GET_ITEM(item, 1);
+        } else {
+            Py_DECREF(seq);
+            throw py::type_error("each block must be a (key, offset) pair");
+        }
+        const unsigned long long v = PyLong_AsUnsignedLongLong(o);
+        if (v == (unsigned long long)-1 && PyErr_Occurred()) {
+            Py_DECREF(seq);
+            throw py::error_already_set();
+        }
+        try {
+            a.add(k);
+        } catch (...) {
+            Py_DECREF(seq);
+            throw;
+        }
+        offs[size_t(i)] = v * scale;
+    }
+    Py_DECREF(seq);
+    out.resize(size_t(n));
+    for (size_t i = 0; i < size_t(n); ++i) out[i] = KeyOffset{a.view(i), offs[i]};
+}
+
+void keys_from_py(const py::object& obj, std::vector<std::string_view>& out) {
+    KeyArena& a = t_arena;
+    a.clear();
+    PyObject* seq = PySequence_Fast(obj.ptr(), "keys must be a sequence of str");
+    if (!seq) throw py::error_already_set();
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);
+    try {
+        for (Py_ssize_t i = 0; i < n; ++i) a.add(PySequence_Fast_GET_ITEM(seq, i));
+    } catch (...) {
+        Py_DECREF(seq);
+        throw;
+    }
+    Py_DECREF(seq);
+    out.resize(size_t(n));
+    for (size_t i = 0; i < size_t(n); ++i) out[i] = a.view(i);
 }
 
 py::dict segment_dict(const SegmentInfo& s) {
@@ -160,19 +297,26 @@ PYBIND11_MODULE(_infinistore, m) {
              py::call_guard<py::gil_scoped_release>())
         .def("setup_rdma", &Connection::setup_rdma, py::call_guard<py::gil_scoped_release>())
         .def("check_exist", &Connection::check_exist, py::call_guard<py::gil_scoped_release>())
-        .def("get_match_last_index", &Connection::get_match_last_index,
-             py::call_guard<py::gil_scoped_release>())
+        .def("get_match_last_index",
+             [](Connection& c, const py::object& keys) {
+                 std::vector<std::string_view> kv;
+                 keys_from_py(keys, kv);
+                 py::gil_scoped_release rel;
+                 return c.get_match_last_index(kv);
+             })
         .def("sync_local", &Connection::sync_local, py::call_guard<py::gil_scoped_release>())
         .def("sync_rdma", &Connection::sync_rdma, py::call_guard<py::gil_scoped_release>())
         .def("register_mr", &Connection::register_mr, py::arg("ptr"), py::arg("size"),
              py::arg("device") = -1, py::call_guard<py::gil_scoped_release>())
         .def(
             "allocate_rdma",
-            [](Connection& c, const std::vector<std::string>& keys, int block_size) {
+            [](Connection& c, const py::object& keys, int block_size) {
+                std::vector<std::string_view> kv;
+                keys_from_py(keys, kv);
                 std::vector<RemoteBlock> out;
                 {
                     py::gil_scoped_release rel;
-                    if (c.allocate(keys, block_size, out) != 0) out.clear();
+                    if (c.allocate(kv, block_size, out) != 0) out.clear();
                 }
                 return blocks_to_array(std::move(out));
             },
@@ -191,25 +335,35 @@ PYBIND11_MODULE(_infinistore, m) {
             })
         .def(
             "w_rdma",
-            [](Connection& c, const std::vector<uint64_t>& offsets, int block_size,
-               const py::object& remote_blocks, uint64_t base_ptr, int device, uint64_t stream) {
-                std::vector<RemoteBlock> rb = blocks_from_py(remote_blocks);
+            [](Connection& c, const py::object& offsets, int block_size,
+               const py::object& remote_blocks, uint64_t base_ptr, int device, uint64_t stream,
+               uint64_t scale) {
+                BlockSpan rb;
+                OffsetSpan off;
+                blocks_from_py(remote_blocks, rb);
+                offsets_from_py(offsets, off);
                 py::gil_scoped_release rel;
-                return c.w_rdma(offsets, block_size, rb.data(), rb.size(), base_ptr, device,
-                                stream);
+                return c.w_rdma(off.data, off.n, scale, block_size, rb.data, rb.n, base_ptr,
+                                device, stream);
             },
             py::arg("offsets"), py::arg("block_size"), py::arg("remote_blocks"),
-            py::arg("base_ptr"), py::arg("device") = -1, py::arg("stream") = 0)
+            py::arg("base_ptr"), py::arg("device") = -1, py::arg("stream") = 0,
+            py::arg("scale") = 1)
         .def(
             "w_rdma_async",
-            [](Connection& c, const std::vector<uint64_t>& offsets, int block_size,
+            [](Connection& c, const py::object& offsets, int block_size,
                const py::object& remote_blocks, uint64_t base_ptr, py::function cb, int device,
-               uint64_t stream) {
-                std::vector<RemoteBlock> rb = blocks_from_py(remote_blocks);
+               uint64_t stream, uint64_t scale) {
+                BlockSpan rb;
+                OffsetSpan off;
+                blocks_from_py(remote_blocks, rb);
+                offsets_from_py(offsets, off);
+                std::vector<uint64_t> bytes(off.n);
+                for (size_t i = 0; i < off.n; ++i) bytes[i] = off.data[i] * scale;
                 auto holder = std::make_shared<py::function>(std::move(cb));
                 py::gil_scoped_release rel;
-                return c.w_rdma_async(offsets, block_size, rb.data(), rb.size(), base_ptr, device,
-                                      stream, [holder](int status) {
+                return c.w_rdma_async(bytes, block_size, rb.data, rb.n, base_ptr, device, stream,
+                                      [holder](int status) {
                                           py::gil_scoped_acquire acq;
                                           (*holder)(status);
                                           holder->release().dec_ref();
@@ -217,23 +371,27 @@ PYBIND11_MODULE(_infinistore, m) {
             },
             py::arg("offsets"), py::arg("block_size"), py::arg("remote_blocks"),
             py::arg("base_ptr"), py::arg("callback"), py::arg("device") = -1,
-            py::arg("stream") = 0)
+            py::arg("stream") = 0, py::arg("scale") = 1)
         .def(
             "r_rdma",
-            [](Connection& c, const std::vector<std::pair<std::string, uint64_t>>& blocks,
-               int block_size, uint64_t base_ptr, int device, uint64_t stream) {
+            [](Connection& c, const py::object& blocks, int block_size, uint64_t base_ptr,
+               int device, uint64_t stream, uint64_t scale) {
+                std::vector<KeyOffset> kb;
+                blocks_list_from_py(blocks, scale, kb);
                 py::gil_scoped_release rel;
-                return c.r_rdma(key_offsets(blocks), block_size, base_ptr, device, stream);
+                return c.r_rdma(kb, block_size, base_ptr, device, stream);
             },
             py::arg("blocks"), py::arg("block_size"), py::arg("base_ptr"),
-            py::arg("device") = -1, py::arg("stream") = 0)
+            py::arg("device") = -1, py::arg("stream") = 0, py::arg("scale") = 1)
         .def(
             "r_rdma_async",
-            [](Connection& c, const std::vector<std::pair<std::string, uint64_t>>& blocks,
-               int block_size, uint64_t base_ptr, py::function cb, int device, uint64_t stream) {
+            [](Connection& c, const py::object& blocks, int block_size, uint64_t base_ptr,
+               py::function cb, int device, uint64_t stream, uint64_t scale) {
+                std::vector<KeyOffset> kb;
+                blocks_list_from_py(blocks, scale, kb);
                 auto holder = std::make_shared<py::function>(std::move(cb));
                 py::gil_scoped_release rel;
-                return c.r_rdma_async(key_offsets(blocks), block_size, base_ptr, device, stream,
+                return c.r_rdma_async(kb, block_size, base_ptr, device, stream,
                                       [holder](int status) {
                                           py::gil_scoped_acquire acq;
                                           (*holder)(status);
@@ -241,18 +399,19 @@ PYBIND11_MODULE(_infinistore, m) {
                                       });
             },
             py::arg("blocks"), py::arg("block_size"), py::arg("base_ptr"), py::arg("callback"),
-            py::arg("device") = -1, py::arg("stream") = 0)
+            py::arg("device") = -1, py::arg("stream") = 0, py::arg("scale") = 1)
         .def(
             "rw_local",
-            [](Connection& c, const std::string& op,
-               const std::vector<std::pair<std::string, uint64_t>>& blocks, int block_size,
-               uint64_t base_ptr, int device, uint64_t stream) {
+            [](Connection& c, const std::string& op, const py::object& blocks, int block_size,
+               uint64_t base_ptr, int device, uint64_t stream, uint64_t scale) {
+                std::vector<KeyOffset> kb;
+                blocks_list_from_py(blocks, scale, kb);
                 py::gil_scoped_release rel;
-                return c.rw_local(op.empty() ? 0 : op[0], key_offsets(blocks), block_size,
-                                  base_ptr, device, stream);
+                return c.rw_local(op.empty() ? 0 : op[0], kb, block_size, base_ptr, device,
+                                  stream);
             },
             py::arg("op"), py::arg("blocks"), py::arg("block_size"), py::arg("base_ptr"),
-            py::arg("device") = -1, py::arg("stream") = 0)
+            py::arg("device") = -1, py::arg("stream") = 0, py::arg("scale") = 1)
         .def("set_copy_variant", &Connection::set_copy_variant)
         .def("set_max_ctas", &Connection::set_max_ctas)
         .def("set_device_lookup", &Connection::set_device_lookup)

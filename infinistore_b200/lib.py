@@ -375,9 +375,8 @@ class InfinityConnection:
         self._verify(cache)
         assert self.local_connected
         es = cache.element_size()
-        blocks_in_bytes = [(key, offset * es) for key, offset in blocks]
-        ret = self.conn.rw_local(self.OP_W, blocks_in_bytes, page_size * es, cache.data_ptr(),
-                                 _device_of(cache), _stream_of(cache, stream))
+        ret = self.conn.rw_local(self.OP_W, blocks, page_size * es, cache.data_ptr(),
+                                 _device_of(cache), _stream_of(cache, stream), es)
         if ret < 0:
             raise Exception(f"Failed to write to infinistore, ret = {ret}")
         return 0
@@ -393,8 +392,8 @@ class InfinityConnection:
         assert self.rdma_connected
         self._verify(cache)
         es = cache.element_size()
-        ret = self.conn.w_rdma([o * es for o in offsets], page_size * es, remote_blocks,
-                               cache.data_ptr(), _device_of(cache), _stream_of(cache, stream))
+        ret = self.conn.w_rdma(offsets, page_size * es, remote_blocks, cache.data_ptr(),
+                               _device_of(cache), _stream_of(cache, stream), es)
         if ret < 0:
             raise Exception(f"Failed to write to infinistore, ret = {ret}")
         return 0
@@ -412,9 +411,8 @@ class InfinityConnection:
             # runs on the connection's completion thread
             loop.call_soon_threadsafe(future.set_result, status)
 
-        ret = self.conn.w_rdma_async([o * es for o in offsets], page_size * es, remote_blocks,
-                                     cache.data_ptr(), _callback, _device_of(cache),
-                                     _stream_of(cache, stream))
+        ret = self.conn.w_rdma_async(offsets, page_size * es, remote_blocks, cache.data_ptr(),
+                                     _callback, _device_of(cache), _stream_of(cache, stream), es)
         status = await future
         if ret < 0 or status < 0:
             raise Exception(f"Failed to write to infinistore, ret = {min(ret, status)}")
@@ -430,13 +428,12 @@ class InfinityConnection:
         """
         self._verify(cache)
         es = cache.element_size()
-        blocks_in_bytes = [(key, offset * es) for key, offset in blocks]
         if self.local_connected:
-            ret = self.conn.rw_local(self.OP_R, blocks_in_bytes, page_size * es, cache.data_ptr(),
-                                     _device_of(cache), _stream_of(cache, stream))
+            ret = self.conn.rw_local(self.OP_R, blocks, page_size * es, cache.data_ptr(),
+                                     _device_of(cache), _stream_of(cache, stream), es)
         elif self.rdma_connected:
-            ret = self.conn.r_rdma(blocks_in_bytes, page_size * es, cache.data_ptr(),
-                                   _device_of(cache), _stream_of(cache, stream))
+            ret = self.conn.r_rdma(blocks, page_size * es, cache.data_ptr(),
+                                   _device_of(cache), _stream_of(cache, stream), es)
         else:
             raise Exception("Not connected to any instance")
         if ret < 0:
@@ -448,15 +445,14 @@ class InfinityConnection:
             raise Exception("this function is only valid for connected rdma")
         self._verify(cache)
         es = cache.element_size()
-        blocks_in_bytes = [(key, offset * es) for key, offset in blocks]
         loop = asyncio.get_running_loop()
         future = loop.create_future()
 
         def _callback(status):
             loop.call_soon_threadsafe(future.set_result, status)
 
-        ret = self.conn.r_rdma_async(blocks_in_bytes, page_size * es, cache.data_ptr(), _callback,
-                                     _device_of(cache), _stream_of(cache, stream))
+        ret = self.conn.r_rdma_async(blocks, page_size * es, cache.data_ptr(), _callback,
+                                     _device_of(cache), _stream_of(cache, stream), es)
         status = await future
         if ret < 0 or status < 0:
             raise Exception(f"Failed to read to infinistore, ret = {min(ret, status)}")
