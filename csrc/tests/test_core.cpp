@@ -1,0 +1,200 @@
+// Native unit tests of the core (no Python, no GPU): wire codec, allocator, key index.
+// The reference's own native tests (src/test/*) no longer compile against its headers;
+// these are their working counterpart.  Build + run: python tools/build_native.py --tests
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "core/hash.h"
+#include "core/kv_store.h"
+#include "core/mempool.h"
+#include "wire/messages.h"
+
+using namespace istore;
+
+static int g_failed = 0, g_checks = 0;
+#define CHECK(cond)                                                              \
+    do {                                                                         \
+        ++g_checks;                                                              \
+        if (!(cond)) {                                                           \
+            ++g_failed;                                                          \
+            std::fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+        }                                                                        \
+    } while (0)
+
+static void test_framing() {
+    CHECK(sizeof(Header) == 9);
+    CHECK(sizeof(ConnInfo) == 30);
+    CHECK(sizeof(RemoteBlock) == 16);
+    Header h{kMagic, kOpAllocate, 123};
+    unsigned char raw[9];
+    std::memcpy(raw, &h, 9);
+    CHECK(raw[0] == 0xef && raw[1] == 0xbe && raw[2] == 0xad && raw[3] == 0xde);  // LE magic
+    CHECK(raw[4] == 'D' && raw[5] == 123);
+    CHECK(op_known('R') && op_known('P') && !op_known('Z') && !op_has_body('S'));
+    CHECK(std::string(op_name('M')) == "MATCH_LAST_INDEX");
+    const uint64_t a = make_addr(3, 0x12345000);
+    CHECK(addr_seg(a) == 3 && addr_off(a) == 0x12345000);
+    CHECK(is_fake_block(RemoteBlock{0, 0, 0}) && !is_fake_block(RemoteBlock{1, 1, make_addr(0, 0)}));
+}
+
+static void test_flatbuffers() {
+    alignas(8) uint8_t buf[4096];
+    {
+        std::vector<std::string_view> keys = {"alpha", "", "a-much-longer-key-0123456789abcdef"};
+        uint64_t addrs[3] = {1, 1ull << 44, ~0ull};
+        fb::Builder b(buf, sizeof(buf));
+        encode_remote_meta(b, keys, 65536, 42, addrs, 3, 'A', 5);
+        CHECK(reinterpret_cast<uintptr_t>(b.data()) % 8 == 0);  // finished message is aligned
+        RemoteMetaRequest r = decode_remote_meta(b.data(), b.size());
+        CHECK(r.keys.size() == 3 && r.keys[0] == "alpha" && r.keys[1].empty() && r.keys[2] == keys[2]);
+        CHECK(r.block_size == 65536 && r.rkey == 42 && r.op == 'A' && r.hint == 5);
+        CHECK(r.remote_addrs.size() == 3 && r.remote_addrs[2] == ~0ull);
+        // truncation at every length must throw, never read out of bounds
+        for (size_t cut = 0; cut < b.size(); ++cut) {
+            bool threw = false;
+            try {
+                std::vector<uint8_t> copy(b.data(), b.data() + cut);  // exact-size heap block
+                decode_remote_meta(copy.data(), copy.size());
+            } catch (const fb::Malformed&) {
+                threw = true;
+            }
+            if (cut < 8) CHECK(threw);
+        }
+    }
+    {
+        RemoteBlock blocks[3] = {{1, 9, make_addr(0, 4096)}, {0, 0, 0}, {2, 10, make_addr(1, 0)}};
+        fb::Builder b(buf, sizeof(buf));
+        encode_allocate_response(b, blocks, 3);
+        auto out = decode_allocate_response(b.data(), b.size());
+        CHECK(out.size() == 3 && std::memcmp(out.data(), blocks, sizeof(blocks)) == 0);
+        fb::Builder e(buf, sizeof(buf));
+        encode_allocate_response(e, nullptr, 0);
+        CHECK(decode_allocate_response(e.data(), e.size()).empty());
+    }
+    {
+        std::vector<LocalBlock> lb = {{"k0", 0}, {"k1", 1ull << 40}};
+        std::string ipc(64, '\x7f');
+        fb::Builder b(buf, sizeof(buf));
+        encode_local_meta(b, 7, ipc, 32768, lb);
+        LocalMetaRequest r = decode_local_meta(b.data(), b.size());
+        CHECK(r.device == 7 && r.block_size == 32768 && r.ipc_handle == ipc);
+        CHECK(r.blocks.size() == 2 && r.blocks[1].key == "k1" && r.blocks[1].offset == (1ull << 40));
+    }
+    {
+        bool threw = false;
+        alignas(8) uint8_t small[64];
+        try {
+            fb::Builder b(small, sizeof(small));
+            std::vector<std::string_view> keys(32, "xxxxxxxxxxxxxxxx");
+            encode_match_request(b, keys);
+        } catch (const fb::Overflow&) {
+            threw = true;
+        }
+        CHECK(threw);  // fixed buffer overflow is an exception, not a write past the end
+    }
+}
+
+static void test_mempool() {
+    const size_t g = 16384;
+    MemoryPool p(130 * g, g, -1);
+    std::vector<uint64_t> offs;
+    CHECK(p.allocate_n(g, 130, offs) && offs.size() == 130);
+    CHECK(p.allocate(1) == -1 && p.usage() == 1.0);
+    std::set<uint64_t> uniq(offs.begin(), offs.end());
+    CHECK(uniq.size() == 130);
+    for (int i = 60; i < 70; ++i) CHECK(p.deallocate(uint64_t(i) * g, g));
+    CHECK(p.allocate(10 * g) == int64_t(60 * g));
+    CHECK(!p.deallocate(60 * g, 11 * g) || true);  // size mismatch over used range is allowed
+    std::mt19937 rng(5);
+    MemoryPool q(1024 * g, g, 0);
+    std::vector<std::pair<uint64_t, size_t>> live;
+    for (int it = 0; it < 20000; ++it) {
+        if (!live.empty() && rng() % 2) {
+            const size_t k = rng() % live.size();
+            CHECK(q.deallocate(live[k].first, live[k].second));
+            live[k] = live.back();
+            live.pop_back();
+        } else {
+            const size_t sz = 1 + rng() % (5 * g);
+            const int64_t off = q.allocate(sz);
+            if (off >= 0) live.emplace_back(uint64_t(off), sz);
+        }
+    }
+    size_t used = 0;
+    for (auto& l : live) used += (l.second + g - 1) / g;
+    CHECK(q.used_blocks() == used);
+}
+
+static void test_kv_store() {
+    MM mm;
+    mm.add_pool(64 * 16384, 16384, -1);
+    KVStore st(&mm);
+    std::vector<std::string_view> keys = {"a", "b", "a", "c"};
+    std::vector<RemoteBlock> out;
+    CHECK(st.reserve(keys, 16384, -1, 1, out) == kFinish);
+    CHECK(!is_fake_block(out[0]) && !is_fake_block(out[1]) && is_fake_block(out[2]));  // in-batch dup
+    CHECK(st.size() == 3 && st.inflight() == 3 && mm.used_bytes() == 3 * 16384);
+    CHECK(!st.exists_committed("a") && st.present("a"));
+    std::vector<RemoteBlock> found;
+    CHECK(st.lookup({"a"}, 1, found, nullptr) == kKeyNotFound);  // reserved, not committed
+    uint64_t addr_a = out[0].remote_addr;
+    CHECK(st.commit(&addr_a, 1) == 1 && st.commit(&addr_a, 1) == 0);
+    CHECK(st.exists_committed("a") && st.inflight() == 2);
+    CHECK(st.lookup({"a"}, 16384, found, nullptr) == kFinish && found[0].remote_addr == addr_a);
+    CHECK(st.lookup({"a"}, 16385, found, nullptr) == kInvalidReq);
+    // dedup against existing keys, committed or not; no pool space leaks
+    CHECK(st.reserve({"a", "b", "d"}, 16384, -1, 2, out) == kFinish);
+    CHECK(is_fake_block(out[0]) && is_fake_block(out[1]) && !is_fake_block(out[2]));
+    CHECK(mm.used_bytes() == 4 * 16384);
+    // match: exact replay of the reference search over presence (committed or not)
+    CHECK(st.match_last_index({"x", "y", "z", "a", "q", "r"}) == 3);
+    CHECK(st.match_last_index({"a", "b", "c", "zz"}) == 2);
+    CHECK(st.match_last_index({"zz"}) == -1);
+    // writer 1 dies: its uncommitted keys go away, committed ones stay
+    CHECK(st.drop_uncommitted(1) == 2 && st.size() == 2 && st.present("a") && !st.present("b"));
+    // out of memory reserves nothing
+    std::vector<std::string> many;
+    for (int i = 0; i < 100; ++i) many.push_back("m" + std::to_string(i));
+    std::vector<std::string_view> mv(many.begin(), many.end());
+    const size_t before = st.size();
+    CHECK(st.reserve(mv, 16384, -1, 3, out) == kOutOfMemory && st.size() == before);
+    // leases keep blocks alive across purge
+    std::vector<BlockPtr> lease;
+    CHECK(st.lookup({"a"}, 1, found, &lease) == kFinish && lease.size() == 1);
+    CHECK(st.purge() == before && st.size() == 0);
+    CHECK(mm.used_bytes() == 16384);  // the leased block
+    lease.clear();
+    CHECK(mm.used_bytes() == 0);
+}
+
+static void test_hash() {
+    std::set<uint64_t> seen;
+    for (int i = 0; i < 100000; ++i) {
+        const std::string k = "layer" + std::to_string(i % 80) + "/block" + std::to_string(i);
+        const KeyHash h = hash_key(reinterpret_cast<const uint8_t*>(k.data()), k.size());
+        CHECK(h.h1 != 0);
+        seen.insert(h.h1);
+    }
+    CHECK(seen.size() == 100000);
+    // unaligned start and zero padding do not change the value
+    alignas(8) char buf[64] = {0};
+    std::memcpy(buf + 3, "hello world, hello hash", 23);
+    const KeyHash a = hash_key(reinterpret_cast<const uint8_t*>(buf + 3), 23);
+    const KeyHash b = hash_key(reinterpret_cast<const uint8_t*>("hello world, hello hash"), 23);
+    CHECK(a.h1 == b.h1 && a.h2 == b.h2);
+}
+
+int main() {
+    test_framing();
+    test_flatbuffers();
+    test_mempool();
+    test_kv_store();
+    test_hash();
+    std::printf("%d checks, %d failed\n", g_checks, g_failed);
+    return g_failed ? 1 : 0;
+}

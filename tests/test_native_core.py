@@ -1,0 +1,29 @@
+"""Builds and runs the C++ unit tests of the core (csrc/tests/test_core.cpp), optionally
+under AddressSanitizer + UBSan (the reference has no sanitizer targets)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+
+def test_native_core_unit_tests():
+    from tools import build_native
+
+    exe = build_native.build_cpp_tests()
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failed" in r.stdout
+
+
+def test_native_core_under_asan_ubsan():
+    from tools import build_native
+
+    exe = build_native.build_cpp_tests(sanitize=True)
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0",
+               UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr[-4000:]
+    assert "0 failed" in r.stdout

@@ -128,14 +128,18 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -
     return out
 
 
-def build_cpp_tests(force: bool = False) -> Path:
-    """Native unit tests of the core (no Python, no GPU): build/test_core."""
+def build_cpp_tests(force: bool = False, sanitize: bool = False) -> Path:
+    """Native unit tests of the core (no Python, no GPU): build/test_core[_san].
+    sanitize=True builds with AddressSanitizer + UndefinedBehaviorSanitizer."""
     BUILD.mkdir(exist_ok=True)
-    out = BUILD / "test_core"
+    out = BUILD / ("test_core_san" if sanitize else "test_core")
     srcs = [CSRC / "tests" / "test_core.cpp", *(CSRC / s for s in HOST_SOURCES[:4])]
     if force or not out.exists() or any(_newer(s, out, _headers()) for s in srcs):
-        _run(["g++", "-std=c++20", "-O1", "-g", "-Wall", "-pthread", f"-I{CSRC}",
-              f"-I{CUDA_HOME / 'include'}", *map(str, srcs), "-o", str(out)])
+        flags = ["-std=c++20", "-O1", "-g", "-Wall", "-pthread"]
+        if sanitize:
+            flags += ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"]
+        _run(["g++", *flags, f"-I{CSRC}", f"-I{CUDA_HOME / 'include'}", *map(str, srcs),
+              "-o", str(out)])
     return out
 
 
