@@ -76,7 +76,9 @@ def reference_arm(args):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons of one GPU while the timed region runs."""
+    """Samples SM clocks / throttle reasons of one GPU while the timed region runs.  Uses
+    NVML in-process (a `nvidia-smi` subprocess every 200 ms takes driver-wide locks long
+    enough to perturb a launch-latency-sensitive loop); falls back to nvidia-smi."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -89,31 +91,63 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.max_mhz = 0
         self._stop_ev = threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            idx = index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            if vis:
+                idx = int(vis.split(",")[index])
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self._nvml = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        self.samples.append(int(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        for name, bit in (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown),
+                          ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown),
+                          ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(
+            ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+             "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5
+        ).stdout.strip().split(",")
+        if len(out) >= 6:
+            self.samples.append(int(float(out[0])))
+            self.max_mhz = int(float(out[1]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown",
+                                "sw_thermal_slowdown", "sw_power_cap"), out[2:6]):
+                if v.strip().lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
         while not self._stop_ev.is_set():
             try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5
-                ).stdout.strip().split(",")
-                if len(out) >= 6:
-                    self.samples.append(int(float(out[0])))
-                    self.max_mhz = int(float(out[1]))
-                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown",
-                                        "sw_thermal_slowdown", "sw_power_cap"), out[2:6]):
-                        if v.strip().lower().startswith("active"):
-                            self.reasons.add(name)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:  # noqa: BLE001
                 pass
-            self._stop_ev.wait(0.2)
+            self._stop_ev.wait(0.1 if self._nvml is not None else 0.5)
 
     def stop(self):
         self._stop_ev.set()
         self.join(timeout=5)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz or None,
-                "reasons": sorted(self.reasons)}
+                "reasons": sorted(self.reasons), "samples": len(s),
+                "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 def main():
@@ -209,17 +243,46 @@ def main():
         remote = conn.allocate_rdma(keys, block_bytes)
         return keys, remote
 
-    def run_step(keys, remote):
-        for l in range(layers):
-            a, b = l * per_layer, (l + 1) * per_layer
-            conn.rdma_write_cache(src, offsets[a:b], elems, remote[a:b])
-        conn.sync()
-        for l in range(layers):
-            a, b = l * per_layer, (l + 1) * per_layer
-            conn.read_cache(dst, list(zip(keys[a:b], offsets[a:b])), elems)
-        conn.sync()
+    host_t = {"issue_write": 0.0, "sync_write": 0.0, "issue_read": 0.0, "sync_read": 0.0}
+    phase_events = []
 
-    prepared = [fresh_step() for _ in range(total_steps)]  # allocation is outside the timing
+    def run_step(keys, remote, blocks, record=False):
+        t0 = time.perf_counter()
+        if record:
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            e[0].record(stream)
+        for l in range(layers):
+            a, b = l * per_layer, (l + 1) * per_layer
+            conn.rdma_write_cache(src, offsets_np[a:b], elems, remote[a:b])
+        if record:
+            e[1].record(stream)
+        t1 = time.perf_counter()
+        conn.sync()
+        t2 = time.perf_counter()
+        if record:
+            e[2].record(stream)
+        for l in range(layers):
+            a, b = l * per_layer, (l + 1) * per_layer
+            conn.read_cache(dst, blocks[a:b], elems)
+        if record:
+            e[3].record(stream)
+            phase_events.append(e)
+        t3 = time.perf_counter()
+        conn.sync()
+        t4 = time.perf_counter()
+        if record:
+            host_t["issue_write"] += t1 - t0
+            host_t["sync_write"] += t2 - t1
+            host_t["issue_read"] += t3 - t2
+            host_t["sync_read"] += t4 - t3
+
+    offsets_np = np.asarray(offsets, dtype=np.int64)
+
+    def fresh_prepared():
+        keys, remote = fresh_step()
+        return keys, remote, list(zip(keys, offsets))  # (key, offset) list built like the reference
+
+    prepared = [fresh_prepared() for _ in range(total_steps)]  # allocation is outside the timing
 
     with torch.cuda.stream(stream):
         for s in range(args.warmup):
@@ -236,13 +299,20 @@ def main():
         ev1 = torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
         for s in range(args.warmup, total_steps):
-            run_step(*prepared[s])
+            run_step(*prepared[s], record=True)
         ev1.record(stream)
         torch.cuda.synchronize()
         barrier()
         clocks = sampler.stop()
         ms = ev0.elapsed_time(ev1)
         launches = conn.stats()["kernel_launches"] - launches0
+        gpu_w = sum(e[0].elapsed_time(e[1]) for e in phase_events) / args.steps
+        gpu_r = sum(e[2].elapsed_time(e[3]) for e in phase_events) / args.steps
+        breakdown = {"gpu_write_phase_ms": round(gpu_w, 3), "gpu_read_phase_ms": round(gpu_r, 3),
+                     "write_phase_GBps": round(nblocks * block_bytes / gpu_w / 1e6, 1),
+                     "read_phase_GBps": round(nblocks * block_bytes / gpu_r / 1e6, 1),
+                     **{"host_" + k + "_ms": round(v / args.steps * 1e3, 3) for k, v in host_t.items()},
+                     "cpus": os.cpu_count()}
     ok = bool(torch.equal(src, dst))
 
     ms_max = allmax(ms)
@@ -257,20 +327,20 @@ def main():
         host_src = torch.empty(nblocks * elems, dtype=torch.bfloat16).pin_memory()
         host_src.copy_(src.cpu())
         host_out = torch.empty(elems + 1, dtype=torch.bfloat16).pin_memory()
-        e2e_prepared = [fresh_step() for _ in range(e2e_steps + 1)]
+        e2e_prepared = [fresh_prepared() for _ in range(e2e_steps + 1)]
         h2d_bytes = nblocks * block_bytes
         d2h_bytes = (elems + 1) * 2
 
-        def e2e_step(keys, remote):
+        def e2e_step(keys, remote, blocks):
             with torch.cuda.stream(stream):
                 for l in range(layers):
                     a, b = l * per_layer, (l + 1) * per_layer
                     src[a * elems:b * elems].copy_(host_src[a * elems:b * elems], non_blocking=True)
-                    conn.rdma_write_cache(src, offsets[a:b], elems, remote[a:b])
+                    conn.rdma_write_cache(src, offsets_np[a:b], elems, remote[a:b])
                 conn.sync()
                 for l in range(layers):
                     a, b = l * per_layer, (l + 1) * per_layer
-                    conn.read_cache(dst, list(zip(keys[a:b], offsets[a:b])), elems)
+                    conn.read_cache(dst, blocks[a:b], elems)
                 conn.sync()
                 same = (dst[-elems:] == src[-elems:]).all().to(torch.bfloat16).reshape(1)
                 host_out[:elems].copy_(dst[:elems], non_blocking=True)
@@ -327,6 +397,7 @@ def main():
             "roofline": {"gbps": round(roof, 1), "what": roof_name,
                          "fraction": round(value / roof, 3)},
             "clocks": clocks, "gpu_launches": total_launches, "e2e": e2e,
+            "breakdown": breakdown,
         }
         print(json.dumps(out))
     if dist is not None:

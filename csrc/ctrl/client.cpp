@@ -662,10 +662,14 @@ uint8_t* Connection::seg_dev_ptr(DevCtx* ctx, uint32_t seg) {
 // byte offset of block i from base_ptr.
 int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scale,
                             const RemoteBlock* blocks, size_t n, int block_size,
-                            uint64_t base_ptr, int device, uint64_t stream_in) {
+                            uint64_t base_ptr, int device, uint64_t stream_in, int fp8_elems) {
     std::lock_guard<std::mutex> lk(mu_);
     if (n == 0) return 0;
     int kd = device;
+    if (device < 0 && fp8_elems) {
+        fail("the fp8 KV path needs a CUDA tensor");
+        return -1;
+    }
     if (device < 0) {
         // host tensor: memcpy when every target segment is host memory, else a kernel on
         // the connection's default device reads / writes the (pinned) host tensor
@@ -790,9 +794,24 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             L.table_mask = table_mask;
             L.done = reinterpret_cast<uint32_t*>(ctx->zeros + ctx->zeros_alloc(size_t(m) * 4));
         }
-        const cudaError_t e = kernels::launch_kv_copy(L, stream);
+        cudaError_t e;
+        if (fp8_elems) {
+            kernels::Fp8Launch F;
+            F.descs = L.descs;
+            F.n = m;
+            F.elems = uint32_t(fp8_elems);
+            F.recs = L.recs;
+            F.table = L.table;
+            F.table_mask = L.table_mask;
+            F.done = L.done;
+            F.status = L.status;
+            F.max_ctas = max_ctas_;
+            e = write ? kernels::launch_kv_write_fp8(F, stream) : kernels::launch_kv_read_fp8(F, stream);
+        } else {
+            e = kernels::launch_kv_copy(L, stream);
+        }
         if (e != cudaSuccess) {
-            fail(std::string("kv_copy launch failed: ") + cudaGetErrorString(e));
+            fail(std::string("page mover launch failed: ") + cudaGetErrorString(e));
             return -1;
         }
         ctx->mark(stream);
@@ -811,6 +830,37 @@ int Connection::w_rdma(const uint64_t* offsets, size_t noffsets, uint64_t scale,
     }
     return move_blocks(true, offsets, scale, blocks, nblocks, block_size, base_ptr, device,
                        stream);
+}
+
+int Connection::w_rdma_fp8(const uint64_t* offsets, size_t noffsets, uint64_t scale, int elems,
+                           const RemoteBlock* blocks, size_t nblocks, uint64_t base_ptr,
+                           int device, uint64_t stream) {
+    if (noffsets != nblocks || elems <= 0 || elems % 128) {
+        fail("w_rdma_fp8: page size must be a positive multiple of 128 elements");
+        return -1;
+    }
+    return move_blocks(true, offsets, scale, blocks, nblocks,
+                       int(kernels::fp8_block_bytes(uint32_t(elems), 128)), base_ptr, device,
+                       stream, elems);
+}
+
+int Connection::r_rdma_fp8(const std::vector<KeyOffset>& blocks, int elems, uint64_t base_ptr,
+                           int device, uint64_t stream) {
+    if (blocks.empty()) return 0;
+    if (elems <= 0 || elems % 128 || device < 0) {
+        fail("r_rdma_fp8: needs a CUDA tensor and pages of a multiple of 128 elements");
+        return -1;
+    }
+    const int bytes = int(kernels::fp8_block_bytes(uint32_t(elems), 128));
+    if (device_lookup_ && server_hbm_)
+        return read_via_device_index(blocks, bytes, base_ptr, device, stream, elems);
+    std::vector<RemoteBlock> rb;
+    const int r = lookup_blocks(kOpReadLookup, blocks, bytes, rb);
+    if (r != 0) return r;
+    std::vector<uint64_t> offs(blocks.size());
+    for (size_t i = 0; i < blocks.size(); ++i) offs[i] = blocks[i].offset;
+    return move_blocks(false, offs.data(), 1, rb.data(), rb.size(), bytes, base_ptr, device,
+                       stream, elems);
 }
 
 int Connection::r_rdma(const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr,
@@ -869,7 +919,8 @@ static size_t pack_keys(const std::string_view* keys, size_t n, uint8_t* bytes, 
 }
 
 int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int block_size,
-                                      uint64_t base_ptr, int device, uint64_t stream_in) {
+                                      uint64_t base_ptr, int device, uint64_t stream_in,
+                                      int fp8_elems) {
     std::lock_guard<std::mutex> lk(mu_);
     DevCtx* ctx = dev_ctx(device);
     if (!ctx) return -1;
@@ -916,11 +967,22 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
         Q.need_bytes = uint32_t(block_size);
         Q.status = ctx->status_d;
         cudaError_t e = kernels::launch_index_lookup(Q, stream);
-        if (e == cudaSuccess) {
+        if (e == cudaSuccess && fp8_elems) {
+            kernels::Fp8Launch F;
+            F.descs = out;
+            F.n = uint32_t(n);
+            F.elems = uint32_t(fp8_elems);
+            F.status = ctx->status_d;
+            F.max_ctas = max_ctas_;
+            e = kernels::launch_kv_read_fp8(F, stream);
+        } else if (e == cudaSuccess) {
+            uint64_t align_or = base_ptr;
+            for (size_t i = 0; i < n; ++i) align_or |= blocks[base + i].offset;
             kernels::CopyLaunch L;
             L.descs = out;
             L.n = uint32_t(n);
             L.bytes = uint32_t(block_size);
+            L.align_or = align_or;
             L.status = ctx->status_d;
             L.variant = copy_variant_;
             L.max_ctas = max_ctas_;

@@ -99,6 +99,14 @@ class Connection {
                uint64_t stream);
     int rw_local(char op, const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr,
                  int device, uint64_t stream);
+    // fp8 KV path: pages are bf16 in the caller's tensor (`elems` elements each) and
+    // e4m3 + per-128 fp32 scales in the pool (kernels::fp8_block_bytes(elems) bytes, which is
+    // the size to allocate).  The cast is fused into the page mover.
+    int w_rdma_fp8(const uint64_t* offsets, size_t noffsets, uint64_t scale, int elems,
+                   const RemoteBlock* blocks, size_t nblocks, uint64_t base_ptr, int device,
+                   uint64_t stream);
+    int r_rdma_fp8(const std::vector<KeyOffset>& blocks, int elems, uint64_t base_ptr, int device,
+                   uint64_t stream);
 
     // --- async flavours: the callback runs on the connection's completion thread
     int allocate_async(const std::vector<std::string>& keys, int block_size,
@@ -136,10 +144,10 @@ class Connection {
     std::shared_ptr<fabric::Mapping> mapping(uint32_t seg, int device);
     int move_blocks(bool write, const uint64_t* local_off, uint64_t scale,
                     const RemoteBlock* blocks, size_t n, int block_size, uint64_t base_ptr,
-                    int device, uint64_t stream);
+                    int device, uint64_t stream, int fp8_elems = 0);
     uint8_t* seg_dev_ptr(DevCtx* ctx, uint32_t seg);
     int read_via_device_index(const std::vector<KeyOffset>& blocks, int block_size,
-                              uint64_t base_ptr, int device, uint64_t stream);
+                              uint64_t base_ptr, int device, uint64_t stream, int fp8_elems = 0);
     int match_via_device_index(const std::vector<std::string_view>& keys, bool exist_only);
     int ensure_host_registered(uint64_t ptr, size_t bytes, int device);
     int drain_devices();

@@ -401,6 +401,31 @@ PYBIND11_MODULE(_infinistore, m) {
             py::arg("blocks"), py::arg("block_size"), py::arg("base_ptr"), py::arg("callback"),
             py::arg("device") = -1, py::arg("stream") = 0, py::arg("scale") = 1)
         .def(
+            "w_rdma_fp8",
+            [](Connection& c, const py::object& offsets, int elems, const py::object& remote_blocks,
+               uint64_t base_ptr, int device, uint64_t stream, uint64_t scale) {
+                BlockSpan rb;
+                OffsetSpan off;
+                blocks_from_py(remote_blocks, rb);
+                offsets_from_py(offsets, off);
+                py::gil_scoped_release rel;
+                return c.w_rdma_fp8(off.data, off.n, scale, elems, rb.data, rb.n, base_ptr, device,
+                                    stream);
+            },
+            py::arg("offsets"), py::arg("elems"), py::arg("remote_blocks"), py::arg("base_ptr"),
+            py::arg("device") = -1, py::arg("stream") = 0, py::arg("scale") = 1)
+        .def(
+            "r_rdma_fp8",
+            [](Connection& c, const py::object& blocks, int elems, uint64_t base_ptr, int device,
+               uint64_t stream, uint64_t scale) {
+                std::vector<KeyOffset> kb;
+                blocks_list_from_py(blocks, scale, kb);
+                py::gil_scoped_release rel;
+                return c.r_rdma_fp8(kb, elems, base_ptr, device, stream);
+            },
+            py::arg("blocks"), py::arg("elems"), py::arg("base_ptr"), py::arg("device") = -1,
+            py::arg("stream") = 0, py::arg("scale") = 1)
+        .def(
             "rw_local",
             [](Connection& c, const std::string& op, const py::object& blocks, int block_size,
                uint64_t base_ptr, int device, uint64_t stream, uint64_t scale) {

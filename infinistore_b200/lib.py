@@ -458,6 +458,40 @@ class InfinityConnection:
             raise Exception(f"Failed to read to infinistore, ret = {min(ret, status)}")
         return 0
 
+    # ------------------------------------------------------------------ fp8 KV path
+    @staticmethod
+    def fp8_page_bytes(page_size: int) -> int:
+        """Pool bytes of one quantised page of `page_size` bf16 elements (what to pass to
+        ``allocate_rdma``): e4m3 payload + one fp32 scale per 128 elements."""
+        return _infinistore.kernels.fp8_block_bytes(page_size, 128)
+
+    def rdma_write_cache_fp8(self, cache: torch.Tensor, offsets, page_size: int, remote_blocks,
+                             stream="current"):
+        """Like ``rdma_write_cache`` for a bf16 CUDA tensor, but the pages are quantised to
+        e4m3 (per-128-element scales) inside the write kernel: half the NVLink bytes, no
+        separate cast kernel.  Blocks must have been allocated with ``fp8_page_bytes``."""
+        assert self.rdma_connected
+        self._verify(cache)
+        if cache.dtype != torch.bfloat16 or cache.device.type != "cuda":
+            raise Exception("the fp8 KV path takes bf16 CUDA tensors")
+        ret = self.conn.w_rdma_fp8(offsets, page_size, remote_blocks, cache.data_ptr(),
+                                   _device_of(cache), _stream_of(cache, stream), 2)
+        if ret < 0:
+            raise Exception(f"Failed to write to infinistore, ret = {ret}")
+        return 0
+
+    def read_cache_fp8(self, cache: torch.Tensor, blocks: List[Tuple[str, int]], page_size: int,
+                       stream="current"):
+        """Read pages written by ``rdma_write_cache_fp8`` back into a bf16 CUDA tensor; the
+        dequantisation is fused into the read kernel."""
+        self._verify(cache)
+        if cache.dtype != torch.bfloat16 or cache.device.type != "cuda":
+            raise Exception("the fp8 KV path takes bf16 CUDA tensors")
+        ret = self.conn.r_rdma_fp8(blocks, page_size, cache.data_ptr(), _device_of(cache),
+                                   _stream_of(cache, stream), 2)
+        if ret < 0:
+            raise Exception(f"Failed to read to infinistore, ret = {ret}")
+
     # the north-star API list names the read entry points rdma_read_cache*: same functions
     rdma_read_cache = read_cache
     rdma_read_cache_async = read_cache_async
