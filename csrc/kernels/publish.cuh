@@ -50,17 +50,25 @@ __device__ inline void publish_entry(const Publish& pub, const IndexEntry& rec) 
 
 // Called by every thread of the CTA after its last data store.  `first`, `count`, `stride`
 // enumerate the work items this CTA handled; an item belongs to block item / cpb.
+//
+// Ordering: bar.sync makes every thread's data stores visible to warp 0 at CTA scope; each
+// lane of warp 0 then issues ONE fence.acq_rel.sys, which is cumulative, so the stores of
+// the whole CTA are performed system-wide before that lane's counter increment.  (One
+// fence per lane of one warp instead of one per thread: MEMBAR.SYS is the expensive part
+// of the epilogue and 256 of them per CTA serialise in the memory system.)
 __device__ inline void publish_done_blocks(const Publish& pub, uint32_t first, uint32_t count,
-                                    uint32_t stride, uint32_t cpb) {
-    fence_sys();      // this thread's data stores are performed system-wide ...
-    __syncthreads();  // ... for every thread of the CTA
-    fence_sys();      // cumulative: covers the stores the barrier made visible to us
-    for (uint32_t k = threadIdx.x; k < count; k += blockDim.x) {
+                                           uint32_t stride, uint32_t cpb) {
+    __syncthreads();
+    if (threadIdx.x >= 32 || threadIdx.x >= count) return;
+    fence_sys();
+    for (uint32_t k = threadIdx.x; k < count; k += 32) {
         const uint32_t block = (first + k * stride) / cpb;
-        const uint32_t arrived = atomicAdd(pub.done + block, 1u) + 1;
+        const uint32_t arrived = cpb == 1 ? 1 : atomicAdd(pub.done + block, 1u) + 1;
         if (arrived == cpb) {  // last chunk of this block, chip-wide
-            fence_sys();
-            pub.done[block] = 0;  // leave the counter area zeroed for the next launch
+            if (cpb != 1) {
+                fence_sys();          // acquire side: other CTAs' stores happen-before us
+                pub.done[block] = 0;  // leave the counter area zeroed for the next launch
+            }
             publish_entry(pub, pub.recs[block]);
         }
     }
