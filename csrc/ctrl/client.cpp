@@ -782,6 +782,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
         if (m == 0) break;
         kernels::CopyLaunch L;
         L.descs = reinterpret_cast<const kernels::CopyDesc*>(ctx->ring_d + at_desc);
+        L.descs_host = descs;
         L.n = m;
         L.bytes = uint32_t(block_size);
         L.align_or = align_or;
@@ -792,7 +793,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             L.recs = reinterpret_cast<const kernels::IndexEntry*>(ctx->ring_d + at_rec);
             L.table = table;
             L.table_mask = table_mask;
-            L.done = reinterpret_cast<uint32_t*>(ctx->zeros + ctx->zeros_alloc(size_t(m) * 4));
+            L.done = reinterpret_cast<uint32_t*>(ctx->zeros + ctx->zeros_alloc(size_t(m) * 12));
         }
         cudaError_t e;
         if (fp8_elems) {

@@ -50,6 +50,8 @@ enum CopyVariant : int {
 
 struct CopyLaunch {
     const CopyDesc* descs = nullptr;  // device-addressable (device memory or mapped pinned host)
+    const CopyDesc* descs_host = nullptr;  // same array as seen by the CPU, if it is host memory:
+                                           // small batches are then passed as kernel parameters
     uint32_t n = 0;                   // blocks
     uint32_t bytes = 0;               // bytes per block
     uint64_t align_or = 0;            // OR of every local address (pool blocks are granule aligned)
@@ -57,7 +59,7 @@ struct CopyLaunch {
     const IndexEntry* recs = nullptr;
     IndexEntry* table = nullptr;
     uint64_t table_mask = 0;
-    uint32_t* done = nullptr;         // n zeroed u32 counters in client-local device memory
+    uint32_t* done = nullptr;         // 3*n zeroed u32 of client-local device scratch
     uint32_t* status = nullptr;       // kStatWords u32, device-addressable
     int variant = kCopyAuto;
     int max_ctas = 0;                 // 0 = pick from the problem size

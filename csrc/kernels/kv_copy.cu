@@ -19,6 +19,7 @@
 //               CTAs of one warp each keep megabytes in flight, leaving the SMs to the
 //               model's own kernels when the transfer overlaps prefill.
 #include <algorithm>
+#include <cstring>
 #include <mutex>
 
 #include "common.cuh"
@@ -67,20 +68,42 @@ __device__ __forceinline__ void copy_span(uint8_t* dst, const uint8_t* src, uint
     for (uint32_t b = nvec * VEC + tid; b < len; b += kLdStThreads) dst[b] = src[b];
 }
 
+// Descriptors of small batches travel in the kernel parameters (constant bank): reading
+// them from the pinned host ring costs a PCIe round trip at the start of every launch
+// (+3-4 us of 18 on a 32 MB launch, profiles/r1_launch_overhead_v1.json).
+constexpr int kParamDescs = 256;
+template <int N>
+struct DescParam {
+    CopyDesc d[N];
+};
+
 // VEC = 16 / 32: vector width; VEC = 1: byte fallback for unaligned tensors.
-template <int VEC>
-__global__ void __launch_bounds__(kLdStThreads)
-    kv_copy_ldst_kernel(const CopyDesc* __restrict__ descs, uint32_t n, uint32_t bytes,
-                        uint32_t chunk, uint32_t cpb, Publish pub) {
+// Threads [0, 256) copy; warp 8 is the control warp (in-band commit, publish.cuh).
+template <int VEC, bool PARAM>
+__global__ void __launch_bounds__(kLdStThreads + 32)
+    kv_copy_ldst_kernel(const CopyDesc* __restrict__ descs,
+                        const __grid_constant__ DescParam<PARAM ? kParamDescs : 1> pd, uint32_t n,
+                        uint32_t bytes, uint32_t chunk, uint32_t cpb, Publish pub) {
     const uint32_t total = n * cpb;
-    uint32_t handled = 0;
+    if (threadIdx.x >= kLdStThreads) {
+        if (!pub.recs) return;
+        const uint32_t count = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        control_warp(pub, threadIdx.x - kLdStThreads, blockIdx.x, count, gridDim.x, cpb,
+                     kLdStThreads + 32);
+        return;
+    }
+    auto desc_at = [&](uint32_t block) -> CopyDesc {
+        if constexpr (PARAM)
+            return pd.d[block];
+        else
+            return descs[block];
+    };
     uint32_t item = blockIdx.x;
-    CopyDesc next = item < total ? descs[item / cpb] : CopyDesc{0, 0};
+    CopyDesc next = item < total ? desc_at(item / cpb) : CopyDesc{0, 0};
     for (; item < total; item += gridDim.x) {
         const CopyDesc d = next;
         const uint32_t nxt = item + gridDim.x;
-        if (nxt < total) next = descs[nxt / cpb];  // prefetch: descriptors may sit in host memory
-        ++handled;
+        if (nxt < total) next = desc_at(nxt / cpb);  // prefetch: descriptors may sit in host memory
         if (d.src == 0) {  // key not found by the device lookup
             if (threadIdx.x == 0 && item % cpb == 0 && pub.status)
                 atomicAdd(pub.status + kStatMiss, 1u);
@@ -96,22 +119,28 @@ __global__ void __launch_bounds__(kLdStThreads)
             copy_span<VEC>(dst, src, len);
         }
     }
-    if (pub.recs) publish_done_blocks(pub, blockIdx.x, handled, gridDim.x, cpb);
+    if (pub.recs) ctrl_barrier_arrive(kLdStThreads + 32);
 }
 
 // ---------------------------------------------------------------- bulk-async (TMA) path
-// One warp per CTA.  Lane 0 runs the pipeline; all lanes prefetch descriptors (32 at a
-// time, one coalesced read even when they live in mapped host memory) and take part in
-// the publish step.
-__global__ void __launch_bounds__(32)
-    kv_copy_tma_kernel(const CopyDesc* __restrict__ descs, uint32_t n, uint32_t bytes,
-                       uint32_t cpb, Publish pub) {
+// Two warps per CTA.  Warp 0: lane 0 runs the pipeline; all lanes prefetch descriptors (32 at
+// a time, one coalesced read even when they live in mapped host memory).  Warp 1 is the
+// control warp (in-band commit).
+template <bool PARAM>
+__global__ void __launch_bounds__(64)
+    kv_copy_tma_kernel(const CopyDesc* __restrict__ descs,
+                       const __grid_constant__ DescParam<PARAM ? kParamDescs : 1> pd, uint32_t n,
+                       uint32_t bytes, uint32_t cpb, Publish pub) {
     extern __shared__ __align__(128) uint8_t ring[];
     __shared__ __align__(8) uint64_t full[kTmaStages];
-    const uint32_t lane = threadIdx.x;
     const uint32_t total = n * cpb;
     const uint32_t grid = gridDim.x;
     const uint32_t nitems = blockIdx.x < total ? (total - blockIdx.x + grid - 1) / grid : 0;
+    if (threadIdx.x >= 32) {
+        if (pub.recs) control_warp(pub, threadIdx.x - 32, blockIdx.x, nitems, grid, cpb, 64);
+        return;
+    }
+    const uint32_t lane = threadIdx.x;
 
     if (lane == 0) {
         for (int s = 0; s < kTmaStages; ++s) mbar_init(&full[s], 1);
@@ -123,7 +152,11 @@ __global__ void __launch_bounds__(32)
     auto fetch = [&](uint32_t k0) -> CopyDesc {  // lane l gets the descriptor of item k0 + l
         const uint32_t k = k0 + lane;
         if (k >= nitems) return CopyDesc{0, 0};
-        return descs[(blockIdx.x + k * grid) / cpb];
+        const uint32_t block = (blockIdx.x + k * grid) / cpb;
+        if constexpr (PARAM)
+            return pd.d[block];
+        else
+            return descs[block];
     };
     // The descriptors of items [w, w+32) live in `cur`, of [w+32, w+64) in `nxt`.
     CopyDesc cur = fetch(0), nxt = fetch(32);
@@ -181,10 +214,10 @@ __global__ void __launch_bounds__(32)
     }
     if (lane == 0) {
         bulk_wait<0>();        // every bulk store of this CTA has completed its writes
-        fence_proxy_async();   // order async-proxy writes before the generic-proxy publish
+        fence_proxy_async();   // order async-proxy writes before the generic-proxy commit
     }
     __syncwarp();
-    if (pub.recs) publish_done_blocks(pub, blockIdx.x, nitems, grid, cpb);
+    if (pub.recs) ctrl_barrier_arrive(64);
 }
 
 std::mutex g_attr_mu;
@@ -207,18 +240,24 @@ int sm_count() {
 
 cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream) {
     if (a.n == 0 || a.bytes == 0) return cudaSuccess;
-    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status};
+    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n};
     if (!a.table || !a.done) pub.recs = nullptr;
     const int sms = sm_count();
 
     int variant = a.variant;
-    // Alignment: bulk copies need 16-byte aligned addresses and sizes.  Descriptors that
-    // live in mapped host memory can be inspected here; device-resident ones (built by the
-    // lookup kernel) always point at granule-aligned pool blocks and the caller's offsets.
+    // Alignment: bulk copies need 16-byte aligned addresses and sizes (the caller ORs every
+    // local address into align_or; pool blocks are granule aligned).
     const bool aligned16 = (a.bytes % 16) == 0 && (a.align_or & 15) == 0;
     const bool aligned32 = (a.bytes % 32) == 0 && (a.align_or & 31) == 0;
-    if (variant == kCopyAuto) variant = kCopyLdSt;  // default picked from profiles/ sweeps
+    if (variant == kCopyAuto) variant = aligned32 ? kCopyLdSt256 : kCopyLdSt;
     if (!aligned16 && (variant == kCopyTma || variant == kCopyLdSt256)) variant = kCopyLdSt;
+    if (variant == kCopyLdSt256 && !aligned32) variant = kCopyLdSt;
+
+    // small batches: descriptors ride in the kernel parameters
+    const bool param = a.descs_host != nullptr && a.n <= uint32_t(kParamDescs) && aligned16;
+    DescParam<kParamDescs> pd;
+    if (param) std::memcpy(pd.d, a.descs_host, size_t(a.n) * sizeof(CopyDesc));
+    const DescParam<1> none{};
 
     if (variant == kCopyTma) {
         const uint32_t cpb = (a.bytes + kTmaChunk - 1) / kTmaChunk;
@@ -232,29 +271,37 @@ cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream) {
             std::lock_guard<std::mutex> lk(g_attr_mu);
             if (dev >= 0 && dev < 64 && !g_tma_attr_set[dev]) {
                 cudaError_t e = cudaFuncSetAttribute(
-                    kv_copy_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+                    kv_copy_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+                if (e == cudaSuccess)
+                    e = cudaFuncSetAttribute(kv_copy_tma_kernel<true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
                 if (e != cudaSuccess) return e;
                 g_tma_attr_set[dev] = true;
             }
         }
-        kv_copy_tma_kernel<<<ctas, 32, smem, stream>>>(a.descs, a.n, a.bytes, cpb, pub);
+        if (param)
+            kv_copy_tma_kernel<true><<<ctas, 64, smem, stream>>>(a.descs, pd, a.n, a.bytes, cpb, pub);
+        else
+            kv_copy_tma_kernel<false><<<ctas, 64, smem, stream>>>(a.descs, none, a.n, a.bytes, cpb, pub);
         return cudaGetLastError();
     }
 
     const uint32_t chunk = std::min(a.bytes, kLdStChunk);
     const uint32_t cpb = (a.bytes + chunk - 1) / chunk;
     const uint64_t total = uint64_t(a.n) * cpb;
-    int ctas = a.max_ctas > 0 ? a.max_ctas : 8 * sms;
+    int ctas = a.max_ctas > 0 ? a.max_ctas : 7 * sms;  // 7 x 288 threads fit one SM
     ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
+    constexpr int T = kLdStThreads + 32;
     if (!aligned16)
-        kv_copy_ldst_kernel<1><<<ctas, kLdStThreads, 0, stream>>>(a.descs, a.n, a.bytes, chunk,
-                                                                   cpb, pub);
-    else if (variant == kCopyLdSt256 && aligned32)
-        kv_copy_ldst_kernel<32><<<ctas, kLdStThreads, 0, stream>>>(a.descs, a.n, a.bytes, chunk,
-                                                                    cpb, pub);
+        kv_copy_ldst_kernel<1, false><<<ctas, T, 0, stream>>>(a.descs, none, a.n, a.bytes, chunk, cpb, pub);
+    else if (variant == kCopyLdSt256 && param)
+        kv_copy_ldst_kernel<32, true><<<ctas, T, 0, stream>>>(a.descs, pd, a.n, a.bytes, chunk, cpb, pub);
+    else if (variant == kCopyLdSt256)
+        kv_copy_ldst_kernel<32, false><<<ctas, T, 0, stream>>>(a.descs, none, a.n, a.bytes, chunk, cpb, pub);
+    else if (param)
+        kv_copy_ldst_kernel<16, true><<<ctas, T, 0, stream>>>(a.descs, pd, a.n, a.bytes, chunk, cpb, pub);
     else
-        kv_copy_ldst_kernel<16><<<ctas, kLdStThreads, 0, stream>>>(a.descs, a.n, a.bytes, chunk,
-                                                                    cpb, pub);
+        kv_copy_ldst_kernel<16, false><<<ctas, T, 0, stream>>>(a.descs, none, a.n, a.bytes, chunk, cpb, pub);
     return cudaGetLastError();
 }
 

@@ -61,13 +61,19 @@ __device__ __forceinline__ uint32_t f2_to_bf16x2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&b);
 }
 
-__global__ void __launch_bounds__(kThreads)
+// Threads [0, 256) quantise + store; warp 8 is the control warp (in-band commit).
+__global__ void __launch_bounds__(kThreads + 32)
     kv_write_fp8_kernel(const CopyDesc* __restrict__ descs, uint32_t n, uint32_t elems,
                         uint32_t cpb, Publish pub) {
     const uint32_t total = n * cpb;
+    if (threadIdx.x >= kThreads) {
+        if (!pub.recs) return;
+        const uint32_t count = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        control_warp(pub, threadIdx.x - kThreads, blockIdx.x, count, gridDim.x, cpb, kThreads + 32);
+        return;
+    }
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t handled = 0;
-    for (uint32_t item = blockIdx.x; item < total; item += gridDim.x, ++handled) {
+    for (uint32_t item = blockIdx.x; item < total; item += gridDim.x) {
         const CopyDesc d = descs[item / cpb];
         const uint32_t e0 = (item % cpb) * kChunkElems;
         const uint32_t rows = (min(kChunkElems, elems - e0)) / kRow;
@@ -99,7 +105,7 @@ __global__ void __launch_bounds__(kThreads)
             }
         }
     }
-    if (pub.recs) publish_done_blocks(pub, blockIdx.x, handled, gridDim.x, cpb);
+    if (pub.recs) ctrl_barrier_arrive(kThreads + 32);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -151,13 +157,13 @@ __global__ void __launch_bounds__(kThreads)
 cudaError_t launch_kv_write_fp8(const Fp8Launch& a, cudaStream_t stream) {
     if (a.n == 0 || a.elems == 0) return cudaSuccess;
     if (a.group != kRow || a.elems % kRow != 0) return cudaErrorInvalidValue;
-    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status};
+    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n};
     if (!a.table || !a.done) pub.recs = nullptr;
     const uint32_t cpb = (a.elems + kChunkElems - 1) / kChunkElems;
     const uint64_t total = uint64_t(a.n) * cpb;
-    int ctas = a.max_ctas > 0 ? a.max_ctas : 8 * sm_count();
+    int ctas = a.max_ctas > 0 ? a.max_ctas : 7 * sm_count();
     ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
-    kv_write_fp8_kernel<<<ctas, kThreads, 0, stream>>>(a.descs, a.n, a.elems, cpb, pub);
+    kv_write_fp8_kernel<<<ctas, kThreads + 32, 0, stream>>>(a.descs, a.n, a.elems, cpb, pub);
     return cudaGetLastError();
 }
 

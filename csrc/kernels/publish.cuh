@@ -4,6 +4,15 @@
 // src/libinfinistore.cpp:362-395; server flips `committed`, src/infinistore.cpp:255-271)
 // with a release-ordered publication from the kernel that moved the data: a reader on any
 // GPU that observes the entry's tag (ld.acquire.sys) is guaranteed to observe the block.
+//
+// Two phases, run by a dedicated CONTROL WARP of every CTA so that the copy warps never
+// wait on a fabric round trip (measured: doing the whole insertion after the data cost
+// +30 us per 32 MB launch over NVLink, profiles/r1_launch_overhead_v1.json):
+//   claim  (kernel start, overlaps the copy): CAS the slot's h1 from 0 (one NVLink round
+//          trip), fill h2/addr/size with posted stores; tag stays 0 = invisible.
+//   commit (after the block's last chunk has landed): one posted st.release.sys of the tag.
+// Chunks of one block may be moved by several CTAs: completion is counted with
+// client-local atomics; slot and tag travel through client-local scratch.
 #pragma once
 
 #include "common.cuh"
@@ -14,63 +23,99 @@ namespace istore::kernels {
 using namespace dev;
 
 struct Publish {
-    const IndexEntry* recs;
+    const IndexEntry* recs;  // one record per block (device-addressable, may be host memory)
     IndexEntry* table;
     uint64_t mask;
-    uint32_t* done;
+    uint32_t* scratch;  // 3*n zeroed u32 in client-local device memory: done | slot+1 | tag
     uint32_t* status;
+    uint32_t n;
 };
 
-// Insert `rec` into the open-addressing table.  The slot is claimed with a 64-bit CAS on
-// h1 (works on peer memory over NVLink); the tag is written last with release.sys, which
-// is what makes the block visible to readers on any GPU.
-__device__ inline void publish_entry(const Publish& pub, const IndexEntry& rec) {
+// Reserve a slot for `rec`.  Returns slot + 1, or 0 when nothing is to be committed (the
+// key is already published - first writer wins - or the table is full).
+__device__ inline uint32_t claim_entry(const Publish& pub, const IndexEntry& rec) {
     uint64_t slot = rec.h1 & pub.mask;
     for (uint64_t probe = 0; probe <= pub.mask; ++probe) {
         IndexEntry* e = pub.table + slot;
-        uint64_t cur = ld_relaxed_sys_u64(&e->h1);
-        if (cur == 0) cur = cas_relaxed_sys_u64(&e->h1, 0, rec.h1);
-        if (cur == 0) {  // slot is ours
+        const uint64_t cur = cas_relaxed_sys_u64(&e->h1, 0, rec.h1);
+        if (cur == 0) {  // slot is ours; fields are posted stores, tag stays 0
             st_relaxed_sys_u64(&e->h2, rec.h2);
             st_relaxed_sys_u64(&e->addr, rec.addr);
             e->size = rec.size;
-            st_release_sys(&e->tag, rec.tag);
-            return;
+            return uint32_t(slot) + 1;
         }
         if (cur == rec.h1) {
-            // Same key already present (first writer wins) or a 64-bit collision with a
-            // different key; either way the authoritative copy is the server's map.
+            // same key already present, or a 64-bit collision with another key; either way
+            // the authoritative copy is the server's map
             const uint32_t tag = ld_acquire_sys(&e->tag);
-            if (tag != 0 && e->h2 == rec.h2) return;
+            if (tag != 0 && e->h2 == rec.h2) return 0;
         }
         slot = (slot + 1) & pub.mask;
     }
     if (pub.status) atomicAdd(pub.status + kStatPublishFail, 1u);
+    return 0;
 }
 
-// Called by every thread of the CTA after its last data store.  `first`, `count`, `stride`
-// enumerate the work items this CTA handled; an item belongs to block item / cpb.
-//
-// Ordering: bar.sync makes every thread's data stores visible to warp 0 at CTA scope; each
-// lane of warp 0 then issues ONE fence.acq_rel.sys, which is cumulative, so the stores of
-// the whole CTA are performed system-wide before that lane's counter increment.  (One
-// fence per lane of one warp instead of one per thread: MEMBAR.SYS is the expensive part
-// of the epilogue and 256 of them per CTA serialise in the memory system.)
-__device__ inline void publish_done_blocks(const Publish& pub, uint32_t first, uint32_t count,
-                                           uint32_t stride, uint32_t cpb) {
-    __syncthreads();
-    if (threadIdx.x >= 32 || threadIdx.x >= count) return;
-    fence_sys();
-    for (uint32_t k = threadIdx.x; k < count; k += 32) {
-        const uint32_t block = (first + k * stride) / cpb;
-        const uint32_t arrived = cpb == 1 ? 1 : atomicAdd(pub.done + block, 1u) + 1;
-        if (arrived == cpb) {  // last chunk of this block, chip-wide
-            if (cpb != 1) {
-                fence_sys();          // acquire side: other CTAs' stores happen-before us
-                pub.done[block] = 0;  // leave the counter area zeroed for the next launch
-            }
-            publish_entry(pub, pub.recs[block]);
+__device__ inline void commit_entry(const Publish& pub, uint32_t slot_plus1, uint32_t tag) {
+    if (slot_plus1) st_release_sys(&pub.table[slot_plus1 - 1].tag, tag);
+}
+
+constexpr int kCtrlBarrier = 1;  // named barrier shared by the copy warps and the control warp
+
+__device__ inline void ctrl_barrier_arrive(uint32_t threads) {
+    asm volatile("bar.arrive %0, %1;" ::"n"(kCtrlBarrier), "r"(threads) : "memory");
+}
+__device__ inline void ctrl_barrier_sync(uint32_t threads) {
+    asm volatile("bar.sync %0, %1;" ::"n"(kCtrlBarrier), "r"(threads) : "memory");
+}
+
+// Body of the control warp.  The CTA moves items first, first+stride, ... (count of them);
+// item i is chunk i % cpb of block i / cpb.  `cta_threads` = copy threads + 32.
+// Ordering: the copy threads' bar.arrive orders their data stores before the control warp's
+// bar.sync at CTA scope; each lane then issues ONE cumulative fence.acq_rel.sys before its
+// counter increments, so the whole CTA's stores are performed system-wide first (one fence
+// per lane of one warp, not one per copy thread: MEMBAR.SYS is the expensive part).
+__device__ inline void control_warp(const Publish& pub, uint32_t lane, uint32_t first,
+                                    uint32_t count, uint32_t stride, uint32_t cpb,
+                                    uint32_t cta_threads) {
+    uint32_t* done = pub.scratch;
+    uint32_t* slot_of = pub.scratch + pub.n;
+    uint32_t* tag_of = pub.scratch + 2 * size_t(pub.n);
+    // ---- claim (overlaps the copy)
+    uint32_t my_slot = 0, my_tag = 0;  // valid for this lane's first claimed item (cpb == 1 path)
+    for (uint32_t k = lane; k < count; k += 32) {
+        const uint32_t item = first + k * stride;
+        if (item % cpb) continue;
+        const uint32_t block = item / cpb;
+        const IndexEntry rec = pub.recs[block];
+        const uint32_t s = claim_entry(pub, rec);
+        if (cpb == 1 && count <= 32) {
+            my_slot = s;
+            my_tag = rec.tag;
+        } else {
+            slot_of[block] = s;
+            tag_of[block] = rec.tag;
         }
+    }
+    // ---- wait until every copy thread of this CTA has issued its last store
+    ctrl_barrier_sync(cta_threads);
+    fence_sys();
+    // ---- commit
+    if (cpb == 1 && count <= 32) {
+        if (lane < count) commit_entry(pub, my_slot, my_tag);
+        return;
+    }
+    for (uint32_t k = lane; k < count; k += 32) {
+        const uint32_t block = (first + k * stride) / cpb;
+        const uint32_t arrived = cpb == 1 ? 1 : atomicAdd(done + block, 1u) + 1;
+        if (arrived != cpb) continue;
+        if (cpb != 1) fence_sys();  // other CTAs' stores and scratch writes happen-before us
+        const uint32_t s = __ldcg(slot_of + block);
+        const uint32_t t = __ldcg(tag_of + block);
+        done[block] = 0;  // leave the scratch zeroed for the next launch
+        slot_of[block] = 0;
+        tag_of[block] = 0;
+        commit_entry(pub, s, t);
     }
 }
 

@@ -62,7 +62,7 @@ class PublishArgs:
         self.recs = torch.from_numpy(rec.view(np.int64)).to(dev)
         self.table = table
         self.mask = table.numel() * table.element_size() // INDEX_ENTRY_BYTES - 1
-        self.done = torch.zeros(len(keys), dtype=torch.int32, device=dev)
+        self.done = torch.zeros(3 * len(keys), dtype=torch.int32, device=dev)  # done | slot | tag
 
 
 def new_index_table(slots: int, device) -> torch.Tensor:
