@@ -148,9 +148,63 @@ struct Connection::DevCtx {
     std::vector<cudaStream_t> busy;  // streams with launches since the last wait_all()
     bool dirty = false;
 
+    // Launch streams.  Back-to-back page-mover kernels of one connection are independent of
+    // each other, but in a single stream the fixed head (launch, descriptor fetch) and tail
+    // (store acks, fence, commit) of every kernel are exposed: +5..30 us on a 45 us NVLink
+    // launch (profiles/r1_launch_overhead_*.json).  Round-robin over a few internal streams
+    // lets the tail of one kernel overlap the body of the next.  Ordering: every launch
+    // waits for the caller's stream (the pages are ready); reads / lookups additionally wait
+    // for earlier writes of this connection; completion is established by sync().
+    static constexpr int kMaxStreams = 8;
+    cudaStream_t pool[kMaxStreams] = {nullptr};
+    cudaEvent_t pool_ev[kMaxStreams] = {nullptr};
+    uint64_t last_write[kMaxStreams] = {0};
+    uint64_t joined[kMaxStreams] = {0};
+    uint64_t write_epoch = 0;
+    cudaEvent_t user_ev = nullptr;
+    int nstreams = 0;
+    int rr = 0;
+
+    // Stream for the next launch.  nstreams == 0: the caller's stream itself (in-stream
+    // semantics, CUDA-graph capturable).
+    cudaStream_t pick(cudaStream_t user, bool is_write, int want_streams) {
+        if (want_streams <= 0) return user ? user : stream;
+        if (nstreams < want_streams) {
+            for (int i = nstreams; i < want_streams && i < kMaxStreams; ++i) {
+                cudaStreamCreateWithFlags(&pool[i], cudaStreamNonBlocking);
+                cudaEventCreateWithFlags(&pool_ev[i], cudaEventDisableTiming);
+            }
+            nstreams = std::min(want_streams, int(kMaxStreams));
+            if (!user_ev) cudaEventCreateWithFlags(&user_ev, cudaEventDisableTiming);
+        }
+        const int i = rr++ % nstreams;
+        cudaStream_t s = pool[i];
+        if (user) {  // run after whatever produced the pages
+            cudaEventRecord(user_ev, user);
+            cudaStreamWaitEvent(s, user_ev, 0);
+        }
+        if (is_write) {
+            last_write[i] = ++write_epoch;
+        } else if (joined[i] < write_epoch) {  // reads see this connection's earlier writes
+            for (int w = 0; w < nstreams; ++w) {
+                if (w == i || last_write[w] <= joined[i]) continue;
+                cudaEventRecord(pool_ev[w], pool[w]);
+                cudaStreamWaitEvent(s, pool_ev[w], 0);
+            }
+            joined[i] = write_epoch;
+        }
+        return s;
+    }
+
     ~DevCtx() {
         DeviceGuard g(device);
         wait_all();
+        for (int i = 0; i < nstreams; ++i) {
+            cudaStreamSynchronize(pool[i]);
+            cudaStreamDestroy(pool[i]);
+            cudaEventDestroy(pool_ev[i]);
+        }
+        if (user_ev) cudaEventDestroy(user_ev);
         if (stream) {
             cudaStreamSynchronize(stream);
             cudaStreamDestroy(stream);
@@ -168,8 +222,10 @@ struct Connection::DevCtx {
         busy.clear();
         dirty = false;
     }
+    cudaStream_t last = nullptr;  // stream of the most recent launch
     void mark(cudaStream_t s) {
         dirty = true;
+        last = s;
         for (cudaStream_t b : busy)
             if (b == s) return;
         busy.push_back(s);
@@ -723,7 +779,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
     DevCtx* ctx = dev_ctx(kd);
     if (!ctx) return -1;
     DeviceGuard g(kd);
-    cudaStream_t stream = stream_in ? reinterpret_cast<cudaStream_t>(stream_in) : ctx->stream;
+    cudaStream_t stream = ctx->pick(reinterpret_cast<cudaStream_t>(stream_in), write, streams_);
 
     // the device index lives in segment 0
     kernels::IndexEntry* table = nullptr;
@@ -931,7 +987,7 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
         return -1;
     }
     DeviceGuard g(device);
-    cudaStream_t stream = stream_in ? reinterpret_cast<cudaStream_t>(stream_in) : ctx->stream;
+    cudaStream_t stream = ctx->pick(reinterpret_cast<cudaStream_t>(stream_in), false, streams_);
     for (size_t base = 0; base < blocks.size(); base += kMaxBatch) {
         const size_t n = std::min(kMaxBatch, blocks.size() - base);
         size_t key_bytes = 0;
@@ -1036,8 +1092,7 @@ int Connection::match_via_device_index(const std::vector<std::string_view>& keys
     Q.want_match = true;
     // The launch is ordered after this connection's writes on the same stream, so keys
     // written just before (even without sync) are visible, as in the reference.
-    cudaStream_t stream = ctx->stream;
-    cudaMemsetAsync(Q.present, 0, words * 4, stream);
+    cudaStream_t stream = ctx->pick(nullptr, false, std::max(streams_, 1));
     const cudaError_t e = kernels::launch_index_lookup(Q, stream);
     if (e != cudaSuccess) {
         fail(std::string("match kernel failed to launch: ") + cudaGetErrorString(e));
@@ -1150,9 +1205,8 @@ int Connection::w_rdma_async(const std::vector<uint64_t>& offsets, int block_siz
         auto it = devs_.find(kd);
         if (it != devs_.end() && it->second->dirty) {
             DeviceGuard g(kd);
-            cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : it->second->stream;
             cudaEventCreateWithFlags(&t.event, cudaEventDisableTiming);
-            cudaEventRecord(t.event, s);
+            cudaEventRecord(t.event, it->second->last);
             t.device = kd;
         }
     }
@@ -1174,9 +1228,8 @@ int Connection::r_rdma_async(const std::vector<KeyOffset>& blocks, int block_siz
         auto it = devs_.find(kd);
         if (it != devs_.end() && it->second->dirty) {
             DeviceGuard g(kd);
-            cudaStream_t s = stream ? reinterpret_cast<cudaStream_t>(stream) : it->second->stream;
             cudaEventCreateWithFlags(&t.event, cudaEventDisableTiming);
-            cudaEventRecord(t.event, s);
+            cudaEventRecord(t.event, it->second->last);
             t.device = kd;
         }
     }

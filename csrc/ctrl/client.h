@@ -121,6 +121,9 @@ class Connection {
     void set_copy_variant(int v) { copy_variant_ = v; }
     void set_max_ctas(int n) { max_ctas_ = n; }
     void set_device_lookup(bool on) { device_lookup_ = on; }
+    // 0: launch in the caller's stream; n >= 1: round-robin over n internal streams that
+    // wait for the caller's stream (kernels of successive calls overlap)
+    void set_streams(int n) { streams_ = n < 0 ? 0 : (n > 8 ? 8 : n); }
     bool device_lookup() const { return device_lookup_; }
     ClientStats stats() const;
     std::vector<SegmentInfo> segments() const { return segs_; }
@@ -179,6 +182,7 @@ class Connection {
     int copy_variant_ = 0;
     int max_ctas_ = 0;
     bool device_lookup_ = false;
+    int streams_ = 4;
     int default_device_ = -1;
     ClientStats stats_;
     std::string last_error_;

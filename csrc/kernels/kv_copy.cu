@@ -289,9 +289,20 @@ cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream) {
     const uint32_t chunk = std::min(a.bytes, kLdStChunk);
     const uint32_t cpb = (a.bytes + chunk - 1) / chunk;
     const uint64_t total = uint64_t(a.n) * cpb;
-    int ctas = a.max_ctas > 0 ? a.max_ctas : 7 * sms;  // 7 x 288 threads fit one SM
-    ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
     constexpr int T = kLdStThreads + 32;
+    // One wave: every CTA is resident and loops over its items, so the commit epilogue
+    // (fence + release) runs once per CTA instead of once per item and per wave.
+    static int resident16 = 0, resident32 = 0;
+    if (!resident16) {
+        int b16 = 0, b32 = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b16, kv_copy_ldst_kernel<16, false>, T, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b32, kv_copy_ldst_kernel<32, false>, T, 0);
+        resident16 = std::max(b16, 1);
+        resident32 = std::max(b32, 1);
+    }
+    const int per_sm = (variant == kCopyLdSt256) ? resident32 : resident16;
+    int ctas = a.max_ctas > 0 ? a.max_ctas : per_sm * sms;
+    ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
     if (!aligned16)
         kv_copy_ldst_kernel<1, false><<<ctas, T, 0, stream>>>(a.descs, none, a.n, a.bytes, chunk, cpb, pub);
     else if (variant == kCopyLdSt256 && param)

@@ -440,6 +440,7 @@ PYBIND11_MODULE(_infinistore, m) {
         .def("set_copy_variant", &Connection::set_copy_variant)
         .def("set_max_ctas", &Connection::set_max_ctas)
         .def("set_device_lookup", &Connection::set_device_lookup)
+        .def("set_streams", &Connection::set_streams)
         .def("device_lookup", &Connection::device_lookup)
         .def("server_has_hbm", &Connection::server_has_hbm)
         .def("last_error", &Connection::last_error)

@@ -46,7 +46,12 @@ class ClientConfig(_infinistore.ClientConfig):
     kernel; default: first GPU touched), ``timeout_ms`` (control-plane deadline),
     ``pool_hint`` (preferred pool GPU for allocations), ``device_lookup`` (resolve keys in
     the HBM index with a kernel instead of asking the server), ``copy_variant``
-    ("auto" | "ldst" | "tma" | "ldst256") and ``max_ctas`` (cap on the copy grid).
+    ("auto" | "ldst" | "tma" | "ldst256"), ``max_ctas`` (cap on the copy grid) and
+    ``streams`` (n >= 1: kernels of successive calls run on n internal streams that wait
+    for the caller's stream, so their fixed head/tail latencies overlap; completion is
+    established by ``sync()`` as in the reference.  0: launch in the caller's stream
+    itself, e.g. for CUDA-graph capture or when later work on that stream must see the
+    result without a ``sync()``).
     """
 
     def __init__(self, **kwargs):
@@ -67,6 +72,7 @@ class ClientConfig(_infinistore.ClientConfig):
         self.device_lookup = kwargs.get("device_lookup", False)
         self.copy_variant = kwargs.get("copy_variant", "auto")
         self.max_ctas = kwargs.get("max_ctas", 0)
+        self.streams = kwargs.get("streams", 4)
 
     def __repr__(self):
         return (
@@ -321,6 +327,7 @@ class InfinityConnection:
     def _apply_options(self):
         self.conn.set_copy_variant(_COPY_VARIANTS[self.config.copy_variant])
         self.conn.set_max_ctas(int(self.config.max_ctas))
+        self.conn.set_streams(int(self.config.streams))
         self.conn.set_device_lookup(bool(self.config.device_lookup) and self.conn.server_has_hbm())
 
     async def connect_async(self):
