@@ -136,6 +136,7 @@ struct Connection::DevCtx {
     cudaStream_t stream = nullptr;
     std::vector<std::shared_ptr<fabric::Mapping>> maps;  // by segment id
     std::vector<uint8_t*> seg_ptr;  // maps[i]->dev_ptr, cached for the per-block hot loop
+    std::vector<uint8_t> seg_remote;  // 1 when the segment is not in this device's own HBM
     uint8_t* ring_h = nullptr;  // pinned + mapped: descriptors, publish records, key bytes
     uint8_t* ring_d = nullptr;
     size_t ring_head = 0;
@@ -709,8 +710,19 @@ uint8_t* Connection::seg_dev_ptr(DevCtx* ctx, uint32_t seg) {
              std::to_string(ctx->device));
         return nullptr;
     }
-    if (ctx->seg_ptr.size() <= seg) ctx->seg_ptr.resize(seg + 1, nullptr);
+    if (ctx->seg_ptr.size() <= seg) {
+        ctx->seg_ptr.resize(seg + 1, nullptr);
+        ctx->seg_remote.resize(seg + 1, 1);
+    }
     ctx->seg_ptr[seg] = mp->dev_ptr;
+    // NVLink (or PCIe) on the path?  Such transfers are link-bound: a small grid saturates
+    // them and leaves the SMs to whatever else runs on this GPU.
+    cudaPointerAttributes attr{};
+    bool local = false;
+    if (cudaPointerGetAttributes(&attr, mp->dev_ptr) == cudaSuccess)
+        local = attr.type == cudaMemoryTypeDevice && attr.device == ctx->device;
+    (void)cudaGetLastError();
+    ctx->seg_remote[seg] = local ? 0 : 1;
     return mp->dev_ptr;
 }
 
@@ -804,6 +816,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
         }
         uint32_t m = 0;
         bool can_publish = table != nullptr;
+        bool all_remote = true;
         uint64_t align_or = 0;
         const size_t nseg = ctx->seg_ptr.size();
         uint8_t* const* seg_ptr = ctx->seg_ptr.data();
@@ -819,6 +832,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             }
             const uint64_t pool = reinterpret_cast<uint64_t>(segbase) + addr_off(rb.remote_addr);
             const uint64_t local = base_ptr + local_off[i] * scale;
+            all_remote = all_remote && ctx->seg_remote[seg];
             align_or |= local;
             descs[m].src = write ? local : pool;
             descs[m].dst = write ? pool : local;
@@ -844,7 +858,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
         L.align_or = align_or;
         L.status = ctx->status_d;
         L.variant = copy_variant_;
-        L.max_ctas = max_ctas_;
+        L.max_ctas = max_ctas_ ? max_ctas_ : (all_remote ? 2 * kernels::sm_count() : 0);
         if (can_publish) {
             L.recs = reinterpret_cast<const kernels::IndexEntry*>(ctx->ring_d + at_rec);
             L.table = table;
@@ -862,7 +876,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             F.table_mask = L.table_mask;
             F.done = L.done;
             F.status = L.status;
-            F.max_ctas = max_ctas_;
+            F.max_ctas = L.max_ctas;
             e = write ? kernels::launch_kv_write_fp8(F, stream) : kernels::launch_kv_read_fp8(F, stream);
         } else {
             e = kernels::launch_kv_copy(L, stream);
@@ -1006,51 +1020,81 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
         auto* dst = reinterpret_cast<uint64_t*>(ctx->ring_h + at_dst);
         for (size_t i = 0; i < n; ++i) dst[i] = blocks[base + i].offset;
 
-        kernels::LookupLaunch Q;
-        Q.key_bytes = ctx->ring_d + at_bytes;
-        Q.key_off = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_off);
-        Q.key_len = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_len);
-        Q.n = uint32_t(n);
-        Q.table = reinterpret_cast<const kernels::IndexEntry*>(m0->dev_ptr + m0->info.index_off);
-        Q.table_mask = m0->info.index_slots - 1;
-        Q.nsegs = uint32_t(std::min<size_t>(segs_.size(), kernels::LookupLaunch::kMaxSegs));
-        for (uint32_t s = 0; s < Q.nsegs; ++s)
-            Q.seg_base[s] = reinterpret_cast<uint64_t>(seg_dev_ptr(ctx, s));
-        auto* out = reinterpret_cast<kernels::CopyDesc*>(
-            ctx->scratch + ctx->scratch_alloc(n * sizeof(kernels::CopyDesc)));
-        Q.out_descs = out;
-        Q.dst_off = reinterpret_cast<const uint64_t*>(ctx->ring_d + at_dst);
-        Q.dst_base = base_ptr;
-        Q.need_bytes = uint32_t(block_size);
-        Q.status = ctx->status_d;
-        cudaError_t e = kernels::launch_index_lookup(Q, stream);
-        if (e == cudaSuccess && fp8_elems) {
-            kernels::Fp8Launch F;
-            F.descs = out;
-            F.n = uint32_t(n);
-            F.elems = uint32_t(fp8_elems);
-            F.status = ctx->status_d;
-            F.max_ctas = max_ctas_;
-            e = kernels::launch_kv_read_fp8(F, stream);
-        } else if (e == cudaSuccess) {
-            uint64_t align_or = base_ptr;
-            for (size_t i = 0; i < n; ++i) align_or |= blocks[base + i].offset;
-            kernels::CopyLaunch L;
-            L.descs = out;
-            L.n = uint32_t(n);
-            L.bytes = uint32_t(block_size);
-            L.align_or = align_or;
-            L.status = ctx->status_d;
-            L.variant = copy_variant_;
-            L.max_ctas = max_ctas_;
-            e = kernels::launch_kv_copy(L, stream);
+        const uint32_t nsegs =
+            uint32_t(std::min<size_t>(segs_.size(), kernels::LookupLaunch::kMaxSegs));
+        uint64_t seg_base[kernels::LookupLaunch::kMaxSegs] = {0};
+        bool all_remote = true;
+        for (uint32_t s = 0; s < nsegs; ++s) {
+            seg_base[s] = reinterpret_cast<uint64_t>(seg_dev_ptr(ctx, s));
+            all_remote = all_remote && ctx->seg_remote[s];
+        }
+        const int grid_cap = max_ctas_ ? max_ctas_ : (all_remote ? 2 * kernels::sm_count() : 0);
+        uint64_t align_or = base_ptr;
+        for (size_t i = 0; i < n; ++i) align_or |= blocks[base + i].offset;
+        cudaError_t e;
+        if (!fp8_elems && copy_variant_ != kernels::kCopyTma) {
+            // one kernel: hash + probe + move
+            kernels::ReadFusedLaunch R;
+            R.key_bytes = ctx->ring_d + at_bytes;
+            R.key_off = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_off);
+            R.key_len = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_len);
+            R.dst_off = reinterpret_cast<const uint64_t*>(ctx->ring_d + at_dst);
+            R.dst_base = base_ptr;
+            R.n = uint32_t(n);
+            R.bytes = uint32_t(block_size);
+            R.align_or = copy_variant_ == kernels::kCopyLdSt ? (align_or | 16) : align_or;
+            R.table = reinterpret_cast<const kernels::IndexEntry*>(m0->dev_ptr + m0->info.index_off);
+            R.table_mask = m0->info.index_slots - 1;
+            R.nsegs = nsegs;
+            for (uint32_t s = 0; s < nsegs; ++s) R.seg_base[s] = seg_base[s];
+            R.status = ctx->status_d;
+            R.max_ctas = grid_cap;
+            e = kernels::launch_kv_read_fused(R, stream);
+            stats_.kernel_launches += 1;
+        } else {
+            kernels::LookupLaunch Q;
+            Q.key_bytes = ctx->ring_d + at_bytes;
+            Q.key_off = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_off);
+            Q.key_len = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_len);
+            Q.n = uint32_t(n);
+            Q.table = reinterpret_cast<const kernels::IndexEntry*>(m0->dev_ptr + m0->info.index_off);
+            Q.table_mask = m0->info.index_slots - 1;
+            Q.nsegs = nsegs;
+            for (uint32_t s = 0; s < nsegs; ++s) Q.seg_base[s] = seg_base[s];
+            auto* out = reinterpret_cast<kernels::CopyDesc*>(
+                ctx->scratch + ctx->scratch_alloc(n * sizeof(kernels::CopyDesc)));
+            Q.out_descs = out;
+            Q.dst_off = reinterpret_cast<const uint64_t*>(ctx->ring_d + at_dst);
+            Q.dst_base = base_ptr;
+            Q.need_bytes = uint32_t(block_size);
+            Q.status = ctx->status_d;
+            e = kernels::launch_index_lookup(Q, stream);
+            if (e == cudaSuccess && fp8_elems) {
+                kernels::Fp8Launch F;
+                F.descs = out;
+                F.n = uint32_t(n);
+                F.elems = uint32_t(fp8_elems);
+                F.status = ctx->status_d;
+                F.max_ctas = grid_cap;
+                e = kernels::launch_kv_read_fp8(F, stream);
+            } else if (e == cudaSuccess) {
+                kernels::CopyLaunch L;
+                L.descs = out;
+                L.n = uint32_t(n);
+                L.bytes = uint32_t(block_size);
+                L.align_or = align_or;
+                L.status = ctx->status_d;
+                L.variant = copy_variant_;
+                L.max_ctas = grid_cap;
+                e = kernels::launch_kv_copy(L, stream);
+            }
+            stats_.kernel_launches += 2;
         }
         if (e != cudaSuccess) {
             fail(std::string("device-index read failed to launch: ") + cudaGetErrorString(e));
             return -1;
         }
         ctx->mark(stream);
-        stats_.kernel_launches += 2;
         stats_.bytes_read += uint64_t(n) * uint64_t(block_size);
     }
     return 0;

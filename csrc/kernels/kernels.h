@@ -115,6 +115,26 @@ struct LookupLaunch {
 };
 cudaError_t launch_index_lookup(const LookupLaunch& a, cudaStream_t stream);
 
+// read_cache in one kernel: resolve the keys in the HBM index and move the pages.
+struct ReadFusedLaunch {
+    const uint8_t* key_bytes = nullptr;  // packed as for LookupLaunch
+    const uint32_t* key_off = nullptr;
+    const uint32_t* key_len = nullptr;
+    const uint64_t* dst_off = nullptr;   // byte offset of every page from dst_base
+    uint64_t dst_base = 0;
+    uint32_t n = 0;
+    uint32_t bytes = 0;                  // bytes per page; an index hit must hold at least this
+    uint64_t align_or = 0;               // OR of every destination address
+    const IndexEntry* table = nullptr;
+    uint64_t table_mask = 0;
+    static constexpr int kMaxSegs = 16;
+    uint64_t seg_base[kMaxSegs] = {0};
+    uint32_t nsegs = 0;
+    uint32_t* status = nullptr;          // status[kStatMiss] counts keys that were not found
+    int max_ctas = 0;
+};
+cudaError_t launch_kv_read_fused(const ReadFusedLaunch& a, cudaStream_t stream);
+
 // One writer -> all readers replication through an NVLS multicast mapping (multimem.st).
 struct BcastLaunch {
     const CopyDesc* descs = nullptr;  // dst = address inside the multicast mapping

@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "copy_span.cuh"
 #include "publish.cuh"
 
 namespace istore::kernels {
@@ -32,42 +33,11 @@ namespace {
 
 using namespace dev;
 
-constexpr int kLdStThreads = 256;
 constexpr uint32_t kLdStChunk = 32u << 10;  // work item of the ld/st path
 constexpr int kTmaStages = 8;
 constexpr uint32_t kTmaChunk = 16u << 10;   // bytes per bulk copy / ring stage
 
-// ---------------------------------------------------------------- ld/st path
-template <int VEC>
-__device__ __forceinline__ void copy_span(uint8_t* dst, const uint8_t* src, uint32_t len) {
-    constexpr int U = 4;
-    const uint32_t nvec = len / VEC;
-    const uint32_t tid = threadIdx.x;
-    uint32_t i = tid;
-    for (; i + (U - 1) * kLdStThreads < nvec; i += U * kLdStThreads) {
-        if constexpr (VEC == 16) {
-            uint4 v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) v[u] = ld_stream_v4(src + size_t(i + u * kLdStThreads) * 16);
-#pragma unroll
-            for (int u = 0; u < U; ++u) st_v4(dst + size_t(i + u * kLdStThreads) * 16, v[u]);
-        } else {
-            u32x8 v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) v[u] = ld_v8(src + size_t(i + u * kLdStThreads) * 32);
-#pragma unroll
-            for (int u = 0; u < U; ++u) st_v8(dst + size_t(i + u * kLdStThreads) * 32, v[u]);
-        }
-    }
-    for (; i < nvec; i += kLdStThreads) {
-        if constexpr (VEC == 16)
-            st_v4(dst + size_t(i) * 16, ld_stream_v4(src + size_t(i) * 16));
-        else
-            st_v8(dst + size_t(i) * 32, ld_v8(src + size_t(i) * 32));
-    }
-    for (uint32_t b = nvec * VEC + tid; b < len; b += kLdStThreads) dst[b] = src[b];
-}
-
+// ---------------------------------------------------------------- ld/st path (copy_span.cuh)
 // Descriptors of small batches travel in the kernel parameters (constant bank): reading
 // them from the pinned host ring costs a PCIe round trip at the start of every launch
 // (+3-4 us of 18 on a 32 MB launch, profiles/r1_launch_overhead_v1.json).

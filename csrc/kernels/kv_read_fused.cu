@@ -1,0 +1,134 @@
+// kv_read_fused: read_cache in ONE kernel — hash the keys, probe the HBM-resident index
+// over NVLink, and move the pages, with no server round trip and no separate lookup launch.
+//
+// This is the "read fused with the lookup/gather" end of the north star: the reference
+// answers a read by a CPU hash-map probe per key on the server followed by RDMA_WRITE work
+// requests pushed towards the client (src/infinistore.cpp:424-533).  Here every CTA has a
+// RESOLVER warp that runs ahead of the copy warps: lane l hashes the key of the CTA's l-th
+// work item (core/hash.h), probes the index (ld.acquire.sys on peer memory) and hands the
+// pool address to the 256 copy threads through shared memory, double-buffered in rounds of
+// 32 items with named barriers.  The lookup latency (2-3 NVLink round trips) is paid once
+// per CTA, overlapped with the copies of other CTAs and of kernels in other streams.
+#include <algorithm>
+
+#include "../core/hash.h"
+#include "copy_span.cuh"
+#include "kernels.h"
+
+namespace istore::kernels {
+
+namespace {
+
+constexpr uint64_t kMaxProbe = 4096;
+constexpr int kRound = 32;
+// named barriers: full[p] (resolver -> copy warps), empty[p] (copy warps -> resolver)
+constexpr int kBarFull0 = 2, kBarEmpty0 = 4;
+constexpr int kThreads = kLdStThreads + 32;
+
+__device__ __forceinline__ void bar_sync(int id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kThreads) : "memory");
+}
+
+__device__ uint64_t resolve(const ReadFusedLaunch& a, uint32_t block) {
+    const KeyHash kh = hash_key(a.key_bytes + a.key_off[block], a.key_len[block]);
+    uint64_t slot = kh.h1 & a.table_mask;
+    const uint64_t limit = a.table_mask + 1 < kMaxProbe ? a.table_mask + 1 : kMaxProbe;
+    for (uint64_t p = 0; p < limit; ++p) {
+        const IndexEntry* e = a.table + slot;
+        const uint64_t h1 = ld_relaxed_sys_u64(&e->h1);
+        if (h1 == 0) return 0;
+        if (h1 == kh.h1) {
+            const uint32_t tag = ld_acquire_sys(&e->tag);
+            if (tag == 0) return 0;  // reserved, not committed
+            if (e->h2 == kh.h2) {
+                const uint64_t addr = e->addr;
+                const uint32_t seg = uint32_t(addr >> 44) - 1;
+                if (e->size < a.bytes || seg >= a.nsegs || !a.seg_base[seg]) return 0;
+                return a.seg_base[seg] + (addr & ((1ull << 44) - 1));
+            }
+        }
+        slot = (slot + 1) & a.table_mask;
+    }
+    return 0;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+    kv_read_fused_kernel(const __grid_constant__ ReadFusedLaunch a, uint32_t chunk, uint32_t cpb) {
+    __shared__ uint64_t src_of[2][kRound];
+    const uint32_t total = a.n * cpb;
+    const uint32_t count = blockIdx.x < total ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t rounds = (count + kRound - 1) / kRound;
+
+    if (threadIdx.x >= kLdStThreads) {  // ---- resolver warp
+        const uint32_t lane = threadIdx.x - kLdStThreads;
+        for (uint32_t r = 0; r < rounds; ++r) {
+            const uint32_t p = r & 1;
+            if (r >= 2) bar_sync(kBarEmpty0 + p);  // copy warps are done with this buffer
+            const uint32_t k = r * kRound + lane;
+            if (k < count) {
+                const uint32_t item = blockIdx.x + k * gridDim.x;
+                const uint64_t src = resolve(a, item / cpb);
+                src_of[p][lane] = src;
+                if (src == 0 && item % cpb == 0 && a.status) atomicAdd(a.status + kStatMiss, 1u);
+            }
+            bar_arrive(kBarFull0 + p);
+        }
+        return;
+    }
+    // ---- copy warps
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t p = r & 1;
+        bar_sync(kBarFull0 + p);
+        const uint32_t kend = min(count, (r + 1) * kRound);
+        for (uint32_t k = r * kRound; k < kend; ++k) {
+            const uint64_t base = src_of[p][k - r * kRound];
+            if (base == 0) continue;  // key not found: counted by the resolver
+            const uint32_t item = blockIdx.x + k * gridDim.x;
+            const uint32_t off = (item % cpb) * chunk;
+            const uint32_t len = min(chunk, a.bytes - off);
+            uint8_t* dst = reinterpret_cast<uint8_t*>(a.dst_base + a.dst_off[item / cpb]) + off;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(base) + off;
+            if constexpr (VEC == 1) {
+                for (uint32_t b = threadIdx.x; b < len; b += kLdStThreads) dst[b] = src[b];
+            } else {
+                copy_span<VEC>(dst, src, len);
+            }
+        }
+        if (r + 2 < rounds) bar_arrive(kBarEmpty0 + p);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_kv_read_fused(const ReadFusedLaunch& a, cudaStream_t stream) {
+    if (a.n == 0 || a.bytes == 0) return cudaSuccess;
+    const uint32_t chunk = std::min(a.bytes, 32u << 10);
+    const uint32_t cpb = (a.bytes + chunk - 1) / chunk;
+    const uint64_t total = uint64_t(a.n) * cpb;
+    const bool aligned16 = (a.bytes % 16) == 0 && (a.align_or & 15) == 0;
+    const bool aligned32 = (a.bytes % 32) == 0 && (a.align_or & 31) == 0;
+    static int resident16 = 0, resident32 = 0;
+    if (!resident16) {
+        int b16 = 0, b32 = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b16, kv_read_fused_kernel<16>, kThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b32, kv_read_fused_kernel<32>, kThreads, 0);
+        resident16 = std::max(b16, 1);
+        resident32 = std::max(b32, 1);
+    }
+    const int per_sm = aligned32 ? resident32 : resident16;
+    int ctas = a.max_ctas > 0 ? a.max_ctas : per_sm * sm_count();
+    ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
+    if (!aligned16)
+        kv_read_fused_kernel<1><<<ctas, kThreads, 0, stream>>>(a, chunk, cpb);
+    else if (aligned32)
+        kv_read_fused_kernel<32><<<ctas, kThreads, 0, stream>>>(a, chunk, cpb);
+    else
+        kv_read_fused_kernel<16><<<ctas, kThreads, 0, stream>>>(a, chunk, cpb);
+    return cudaGetLastError();
+}
+
+}  // namespace istore::kernels
