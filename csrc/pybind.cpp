@@ -688,6 +688,44 @@ PYBIND11_MODULE(_infinistore, m) {
         py::arg("descs"), py::arg("n"), py::arg("bytes"), py::arg("max_ctas") = 0,
         py::arg("stream") = 0);
 
+    // ------------------------------------------------------------ comparison baselines
+    // The reference's data-movement pattern, reproduced for bench/ only (never on the
+    // product path): one cudaMemcpyAsync per block on a stream + event created for the
+    // request and destroyed after it (reference: src/infinistore.cpp:581-586,623-624,
+    // 667-681,723-729,747-748).
+    py::module_ bl = m.def_submodule("baseline", "library-call baselines for bench/");
+    bl.def(
+        "memcpy_blocks",
+        [](const std::vector<uint64_t>& dst, const std::vector<uint64_t>& src, size_t bytes,
+           bool fresh_stream, int device) {
+            py::gil_scoped_release rel;
+            int prev = -1;
+            cudaGetDevice(&prev);
+            if (device >= 0) cudaSetDevice(device);
+            cudaStream_t st = nullptr;
+            cudaEvent_t ev = nullptr;
+            if (fresh_stream) {
+                cudaStreamCreate(&st);
+                cudaEventCreate(&ev);
+            }
+            cudaError_t e = cudaSuccess;
+            for (size_t i = 0; i < dst.size() && e == cudaSuccess; ++i)
+                e = cudaMemcpyAsync(as_ptr<void>(dst[i]), as_ptr<void>(src[i]), bytes,
+                                    cudaMemcpyDefault, st);
+            if (fresh_stream) {
+                cudaEventRecord(ev, st);
+                cudaEventSynchronize(ev);
+                cudaEventDestroy(ev);
+                cudaStreamDestroy(st);
+            } else {
+                cudaStreamSynchronize(st);
+            }
+            if (prev >= 0) cudaSetDevice(prev);
+            if (e != cudaSuccess) throw std::runtime_error(cudaGetErrorString(e));
+        },
+        py::arg("dst"), py::arg("src"), py::arg("bytes"), py::arg("fresh_stream") = true,
+        py::arg("device") = -1);
+
     // ------------------------------------------------------------ unit-test access to the core
     py::module_ t = m.def_submodule("testing", "wire codec, allocator and hash for unit tests");
     t.def("hash_key", [](py::bytes key) {

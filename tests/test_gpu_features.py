@@ -1,0 +1,168 @@
+"""GPU tests of the B200-only features: fp8 KV path through the store, the fused read
+kernel's corner cases, sharded HBM pools, the paged KV cache and NVLS broadcast."""
+import random
+import string
+
+import numpy as np
+import pytest
+import torch
+
+import infinistore_b200 as ist
+from infinistore_b200 import _infinistore as native
+from infinistore_b200 import ops
+from infinistore_b200.models import PagedKVCache, KVLayout, chain_hashes
+from infinistore_b200.parallel import (PrefixBroadcaster, ShardedConnection, nvls_available,
+                                       start_shard_server)
+from conftest import make_conn
+
+pytestmark = pytest.mark.gpu
+
+
+def rk(n=12):
+    return "".join(random.choice(string.ascii_letters) for _ in range(n))
+
+
+@pytest.mark.parametrize("device_lookup", [False, True])
+def test_fp8_kv_path_through_the_store(hbm_server, device_lookup):
+    srv, port = hbm_server
+    conn = make_conn(port, device_lookup=device_lookup)
+    n, elems = 24, 16384
+    x = (torch.randn(n, elems, device="cuda:0") * 2).to(torch.bfloat16)
+    out = torch.zeros_like(x)
+    conn.register_mr(x)
+    conn.register_mr(out)
+    keys = [rk() for _ in range(n)]
+    nbytes = conn.fp8_page_bytes(elems)
+    assert nbytes == elems + 4 * elems // 128
+    blocks = conn.allocate_rdma(keys, nbytes)
+    conn.rdma_write_cache_fp8(x, [i * elems for i in range(n)], elems, blocks)
+    conn.sync()
+    assert srv.stats()["used_bytes"] < n * elems * 2  # fp8 pages occupy about half
+    conn.read_cache_fp8(out, [(k, i * elems) for i, k in enumerate(keys)], elems)
+    conn.sync()
+    ref, _, _ = ops.fp8_reference(x)
+    assert (out.float() - ref.to(torch.bfloat16).float()).abs().max().item() <= \
+        float(x.float().abs().max()) * 2 ** -7
+    # a bf16-sized read of an fp8-sized block is refused, never an overrun
+    with pytest.raises(Exception):
+        conn.read_cache(out, [(keys[0], 0)], elems)
+        conn.sync()
+
+
+def test_fused_read_many_rounds_and_misses(hbm_server):
+    """Few CTAs, many items per CTA (several resolver rounds), misses in the middle."""
+    _, port = hbm_server
+    conn = make_conn(port, device_lookup=True, max_ctas=3)
+    n, elems = 400, 2048  # 400 items over 3 CTAs -> 134 items per CTA = 5 rounds of 32
+    src = torch.randn(n * elems, device="cuda:0")
+    dst = torch.zeros_like(src)
+    conn.register_mr(src)
+    keys = [f"fr-{i}-{rk(6)}" for i in range(n)]
+    conn.rdma_write_cache(src, [i * elems for i in range(n)], elems,
+                          conn.allocate_rdma(keys, elems * 4))
+    conn.sync()
+    conn.read_cache(dst, [(k, i * elems) for i, k in enumerate(keys)], elems)
+    conn.sync()
+    assert torch.equal(src, dst)
+    dst.zero_()
+    q = [(k, i * elems) for i, k in enumerate(keys)]
+    q[7] = ("missing-a", 7 * elems)
+    q[250] = ("missing-b", 250 * elems)
+    conn.read_cache(dst, q, elems)
+    with pytest.raises(Exception, match="2 key"):
+        conn.sync()
+    got = dst.view(n, elems)
+    want = src.view(n, elems).clone()
+    want[7] = 0
+    want[250] = 0
+    assert torch.equal(got, want)
+
+
+def test_in_stream_mode_orders_with_the_callers_stream(hbm_server):
+    """streams=0: kernels run in the caller's stream, so later work on that stream sees the
+    data without sync() (the mode to use under CUDA-graph capture)."""
+    _, port = hbm_server
+    conn = make_conn(port, device_lookup=True, streams=0)
+    n, elems = 64, 32768
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        src = torch.randn(n * elems, device="cuda:0")
+        dst = torch.zeros_like(src)
+        keys = [rk() for _ in range(n)]
+        conn.register_mr(src)
+        blocks = conn.allocate_rdma(keys, elems * 4)
+        conn.rdma_write_cache(src, [i * elems for i in range(n)], elems, blocks)
+        conn.read_cache(dst, [(k, i * elems) for i, k in enumerate(keys)], elems)
+        same = torch.equal(src, dst)  # enqueued on the same stream: no conn.sync() needed
+    assert same
+    conn.sync()
+
+
+def test_sharded_hbm_pools_two_servers():
+    devs = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    servers = [start_shard_server(d, 0, 256 << 20, granule_kb=16) for d in devs]
+    try:
+        cfgs = [ist.ClientConfig(host_addr="127.0.0.1", service_port=s.port(),
+                                 connection_type=ist.TYPE_RDMA, device_lookup=True)
+                for s in servers]
+        conn = ShardedConnection(cfgs)
+        conn.connect()
+        n, page = 200, 8192
+        keys = [rk(16) for _ in range(n)]
+        src = torch.randn(n * page, device="cuda:0")
+        dst = torch.zeros_like(src)
+        conn.register_mr(src)
+        blocks = conn.allocate_rdma(keys, page * 4)
+        conn.rdma_write_cache(src, np.arange(n) * page, page, blocks)
+        conn.sync()
+        assert all(s.kvmap_len() > 0 for s in servers)
+        conn.read_cache(dst, [(k, i * page) for i, k in enumerate(keys)], page)
+        conn.sync()
+        assert torch.equal(src, dst)
+        conn.close()
+    finally:
+        for s in servers:
+            s.stop()
+
+
+@pytest.mark.parametrize("fp8", [False, True])
+def test_paged_kv_cache_on_gpu(hbm_server, fp8):
+    _, port = hbm_server
+    layout = KVLayout("tiny-gpu", layers=4, kv_heads=2, head_dim=128, page_tokens=16)
+    a = PagedKVCache(layout, num_pages=8, device="cuda:0")
+    b = PagedKVCache(layout, num_pages=8, device="cuda:0")
+    a.data.normal_()
+    ca = make_conn(port, device_lookup=True)
+    cb = make_conn(port, device_lookup=True)
+    hashes = chain_hashes(list(range(16 * 5)), 16, salt=f"fp8={fp8}")
+    pages, dst_pages = [7, 2, 5, 0, 3], [1, 0, 4, 6, 2]
+    for layer in range(layout.layers):
+        a.write_layer(ca, layer, pages, hashes, fp8=fp8)
+    ca.sync()
+    assert b.cached_prefix_pages(cb, hashes) == 5
+    for layer in range(layout.layers):
+        b.read_layer(cb, layer, dst_pages, hashes, fp8=fp8)
+    cb.sync()
+    for s, d in zip(pages, dst_pages):
+        x, y = a.data[:, :, s].float(), b.data[:, :, d].float()
+        if fp8:
+            assert (x - y).abs().max().item() <= x.abs().max().item() * 2 ** -4
+        else:
+            assert torch.equal(x, y)
+
+
+def test_nvls_prefix_broadcast():
+    if torch.cuda.device_count() < 2 or not nvls_available():
+        pytest.skip("needs >= 2 GPUs with NVLS multicast")
+    ndev = torch.cuda.device_count()
+    bc = PrefixBroadcaster(list(range(ndev)), 64 << 20)
+    nblk, bs = 24, 1 << 20
+    src = torch.randint(0, 255, (nblk * bs,), dtype=torch.uint8, device="cuda:0")
+    slots = [((i * 7) % nblk) * bs for i in range(nblk)]  # scattered slots in the replica
+    bc.broadcast(src, [i * bs for i in range(nblk)], slots, bs)
+    torch.cuda.synchronize(0)
+    for d in range(ndev):
+        rep = bc.replica(d)
+        torch.cuda.synchronize(d)
+        for i in (0, 5, nblk - 1):
+            assert torch.equal(rep[slots[i]:slots[i] + bs].cpu(), src[i * bs:(i + 1) * bs].cpu())
