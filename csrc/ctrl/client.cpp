@@ -996,7 +996,7 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
     DevCtx* ctx = dev_ctx(device);
     if (!ctx) return -1;
     auto m0 = mapping(0, device);
-    if (!m0 || !m0->dev_ptr || !m0->info.index_slots) {
+    if (!m0 || !m0->dev_ptr || !segs_[0].index_slots) {
         fail("the server exposes no device index");
         return -1;
     }
@@ -1043,8 +1043,8 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             R.n = uint32_t(n);
             R.bytes = uint32_t(block_size);
             R.align_or = copy_variant_ == kernels::kCopyLdSt ? (align_or | 16) : align_or;
-            R.table = reinterpret_cast<const kernels::IndexEntry*>(m0->dev_ptr + m0->info.index_off);
-            R.table_mask = m0->info.index_slots - 1;
+            R.table = reinterpret_cast<const kernels::IndexEntry*>(m0->dev_ptr + segs_[0].index_off);
+            R.table_mask = segs_[0].index_slots - 1;
             R.nsegs = nsegs;
             for (uint32_t s = 0; s < nsegs; ++s) R.seg_base[s] = seg_base[s];
             R.status = ctx->status_d;
@@ -1057,8 +1057,8 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             Q.key_off = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_off);
             Q.key_len = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_len);
             Q.n = uint32_t(n);
-            Q.table = reinterpret_cast<const kernels::IndexEntry*>(m0->dev_ptr + m0->info.index_off);
-            Q.table_mask = m0->info.index_slots - 1;
+            Q.table = reinterpret_cast<const kernels::IndexEntry*>(m0->dev_ptr + segs_[0].index_off);
+            Q.table_mask = segs_[0].index_slots - 1;
             Q.nsegs = nsegs;
             for (uint32_t s = 0; s < nsegs; ++s) Q.seg_base[s] = seg_base[s];
             auto* out = reinterpret_cast<kernels::CopyDesc*>(
@@ -1106,7 +1106,7 @@ int Connection::match_via_device_index(const std::vector<std::string_view>& keys
     DevCtx* ctx = dev_ctx(device);
     if (!ctx) return -3;
     auto m0 = mapping(0, device);
-    if (!m0 || !m0->dev_ptr || !m0->info.index_slots) return -3;
+    if (!m0 || !m0->dev_ptr || !segs_[0].index_slots) return -3;
     const size_t n = keys.size();
     size_t key_bytes = 0;
     std::vector<std::string_view> kp(n);
@@ -1127,8 +1127,8 @@ int Connection::match_via_device_index(const std::vector<std::string_view>& keys
     Q.key_off = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_off);
     Q.key_len = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_len);
     Q.n = uint32_t(n);
-    Q.table = reinterpret_cast<const kernels::IndexEntry*>(m0->dev_ptr + m0->info.index_off);
-    Q.table_mask = m0->info.index_slots - 1;
+    Q.table = reinterpret_cast<const kernels::IndexEntry*>(m0->dev_ptr + segs_[0].index_off);
+    Q.table_mask = segs_[0].index_slots - 1;
     const size_t words = (n + 31) / 32;
     Q.present = reinterpret_cast<uint32_t*>(ctx->scratch + ctx->scratch_alloc(words * 4));
     Q.ticket = reinterpret_cast<uint32_t*>(ctx->zeros + ctx->zeros_alloc(4));

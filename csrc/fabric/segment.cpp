@@ -240,16 +240,21 @@ std::shared_ptr<Mapping> map_segment(const SegmentInfo& info, int device, std::s
     key.id = info.id;
     key.device = device;
     key.owner_ptr = info.owner_ptr;
+    const bool same_process = std::memcmp(info.owner, process_uuid(), 16) == 0;
     std::lock_guard<std::mutex> lk(g_map_mu);
-    auto it = g_maps.find(key);
-    if (it != g_maps.end()) {
-        if (auto sp = it->second.lock()) return sp;
-        g_maps.erase(it);
+    // Only real mappings are cached (an IPC handle can be opened once per context).  A
+    // segment of this very process is used through its own pointer; caching that would let
+    // a mapping of a stopped server alias a new segment that reuses the address.
+    if (!same_process) {
+        auto it = g_maps.find(key);
+        if (it != g_maps.end()) {
+            if (auto sp = it->second.lock()) return sp;
+            g_maps.erase(it);
+        }
     }
     auto m = std::make_shared<Mapping>();
     m->info = info;
     m->device = device;
-    const bool same_process = std::memcmp(info.owner, process_uuid(), 16) == 0;
 
     if (info.kind == kSegHostShm) {
         if (same_process) {
@@ -324,7 +329,7 @@ std::shared_ptr<Mapping> map_segment(const SegmentInfo& info, int device, std::s
             m->ipc_opened = true;
         }
     }
-    g_maps[key] = m;
+    if (!same_process) g_maps[key] = m;
     return m;
 }
 

@@ -26,7 +26,7 @@ def rk(n=12):
 def test_fp8_kv_path_through_the_store(hbm_server, device_lookup):
     srv, port = hbm_server
     conn = make_conn(port, device_lookup=device_lookup)
-    n, elems = 24, 16384
+    n, elems = 24, 65536
     x = (torch.randn(n, elems, device="cuda:0") * 2).to(torch.bfloat16)
     out = torch.zeros_like(x)
     conn.register_mr(x)
