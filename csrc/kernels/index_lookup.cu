@@ -36,10 +36,12 @@ __device__ Hit probe(const IndexEntry* table, uint64_t mask, const KeyHash& kh) 
     const uint64_t limit = mask + 1 < kMaxProbe ? mask + 1 : kMaxProbe;
     for (uint64_t p = 0; p < limit; ++p) {
         const IndexEntry* e = table + slot;
+        // h1 and tag are fetched together (the acquire load does not depend on h1): a hit
+        // costs two fabric round trips, not three
         const uint64_t h1 = ld_relaxed_sys_u64(&e->h1);
+        const uint32_t tag = ld_acquire_sys(&e->tag);
         if (h1 == 0) break;  // empty slot terminates the probe sequence
         if (h1 == kh.h1) {
-            const uint32_t tag = ld_acquire_sys(&e->tag);
             if (tag == 0) break;  // reserved by a writer that has not committed yet
             if (e->h2 == kh.h2) return Hit{true, e->addr, e->size};
         }

@@ -38,10 +38,12 @@ __device__ uint64_t resolve(const ReadFusedLaunch& a, uint32_t block) {
     const uint64_t limit = a.table_mask + 1 < kMaxProbe ? a.table_mask + 1 : kMaxProbe;
     for (uint64_t p = 0; p < limit; ++p) {
         const IndexEntry* e = a.table + slot;
+        // h1 and tag are fetched together (the acquire load does not depend on h1): a hit
+        // costs two fabric round trips, not three
         const uint64_t h1 = ld_relaxed_sys_u64(&e->h1);
+        const uint32_t tag = ld_acquire_sys(&e->tag);
         if (h1 == 0) return 0;
         if (h1 == kh.h1) {
-            const uint32_t tag = ld_acquire_sys(&e->tag);
             if (tag == 0) return 0;  // reserved, not committed
             if (e->h2 == kh.h2) {
                 const uint64_t addr = e->addr;

@@ -56,8 +56,14 @@ __device__ inline uint32_t claim_entry(const Publish& pub, const IndexEntry& rec
     return 0;
 }
 
+// The caller has just executed fence.acq_rel.sys; fence + relaxed store is a release
+// pattern, so the tag needs no second MEMBAR.SYS/ERRBAR (the most expensive instruction of
+// the epilogue, profiles/r1_ncu_kv_copy_*.txt).
 __device__ inline void commit_entry(const Publish& pub, uint32_t slot_plus1, uint32_t tag) {
-    if (slot_plus1) st_release_sys(&pub.table[slot_plus1 - 1].tag, tag);
+    if (slot_plus1)
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(&pub.table[slot_plus1 - 1].tag),
+                     "r"(tag)
+                     : "memory");
 }
 
 constexpr int kCtrlBarrier = 1;  // named barrier shared by the copy warps and the control warp
@@ -109,7 +115,9 @@ __device__ inline void control_warp(const Publish& pub, uint32_t lane, uint32_t 
         const uint32_t block = (first + k * stride) / cpb;
         const uint32_t arrived = cpb == 1 ? 1 : atomicAdd(done + block, 1u) + 1;
         if (arrived != cpb) continue;
-        if (cpb != 1) fence_sys();  // other CTAs' stores and scratch writes happen-before us
+        // acquire side of the counter (other CTAs' stores and scratch writes happen-before
+        // us) and release side of the tag store below, in one fence
+        if (cpb != 1) fence_sys();
         const uint32_t s = __ldcg(slot_of + block);
         const uint32_t t = __ldcg(tag_of + block);
         done[block] = 0;  // leave the scratch zeroed for the next launch
