@@ -50,6 +50,9 @@ def parse_args():
                    help="resolve read keys through the server instead of the HBM index")
     p.add_argument("--base-port", type=int, default=0)
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--pool-gb", type=int, default=48,
+                   help="HBM pool per GPU; steps beyond its capacity run in further epochs "
+                        "(purge + re-allocate outside the timed region)")
     return p.parse_args()
 
 
@@ -215,7 +218,9 @@ def main():
     scfg.pool_backend = "hbm"
     scfg.pool_devices = [local_rank]
     scfg.minimal_allocate_size = max(16, min(args.block_kb, 64))
-    scfg.prealloc_bytes = (total_steps + e2e_steps + 2) * size_bytes + (64 << 20)
+    epoch_cap = max(1, ((args.pool_gb << 30) - (64 << 20)) // size_bytes - 1)
+    pool_steps = min(max(total_steps, e2e_steps + 1), epoch_cap)
+    scfg.prealloc_bytes = (pool_steps + 1) * size_bytes + (64 << 20)
     scfg.log_level = "warning"
     server = native.Server(scfg)
     server.start()
@@ -282,29 +287,45 @@ def main():
         keys, remote = fresh_step()
         return keys, remote, list(zip(keys, offsets))  # (key, offset) list built like the reference
 
-    prepared = [fresh_prepared() for _ in range(total_steps)]  # allocation is outside the timing
+    def new_epoch(nsteps):
+        """Empty this rank's pool shard and reserve blocks for `nsteps` steps (untimed)."""
+        barrier()          # nobody is still reading the shard we are about to purge
+        server.purge()
+        barrier()
+        return [fresh_prepared() for _ in range(nsteps)]  # allocation is outside the timing
+
+    def run_epochs(nsteps, record):
+        """Run `nsteps` steps; returns the device time (ms) of the timed regions: each epoch
+        is bracketed by barrier + synchronize on both sides and timed with CUDA events."""
+        total_ms = 0.0
+        remaining = nsteps
+        while remaining > 0:
+            n_ep = min(remaining, epoch_cap)
+            prepared = new_epoch(n_ep)
+            dst.zero_()
+            torch.cuda.synchronize()
+            barrier()
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            for s in range(n_ep):
+                run_step(*prepared[s], record=record)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            barrier()
+            total_ms += ev0.elapsed_time(ev1)
+            remaining -= n_ep
+        return total_ms
 
     with torch.cuda.stream(stream):
-        for s in range(args.warmup):
-            run_step(*prepared[s])
+        run_epochs(args.warmup, record=False)
         torch.cuda.synchronize()
-        assert torch.equal(src, dst), "read-back mismatch after warm-up"
-        dst.zero_()
+        assert args.warmup == 0 or torch.equal(src, dst), "read-back mismatch after warm-up"
         launches0 = conn.stats()["kernel_launches"]
-
         sampler = ClockSampler(local_rank)
         sampler.start()
-        barrier()
-        ev0 = torch.cuda.Event(enable_timing=True)
-        ev1 = torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        for s in range(args.warmup, total_steps):
-            run_step(*prepared[s], record=True)
-        ev1.record(stream)
-        torch.cuda.synchronize()
-        barrier()
+        ms = run_epochs(args.steps, record=True)
         clocks = sampler.stop()
-        ms = ev0.elapsed_time(ev1)
         launches = conn.stats()["kernel_launches"] - launches0
         # phase wall time = issue + sync (kernels run on the connection's internal streams)
         w_ms = (host_t["issue_write"] + host_t["sync_write"]) / args.steps * 1e3
@@ -313,7 +334,7 @@ def main():
                      "write_phase_GBps": round(nblocks * block_bytes / w_ms / 1e6, 1),
                      "read_phase_GBps": round(nblocks * block_bytes / r_ms / 1e6, 1),
                      **{"host_" + k + "_ms": round(v / args.steps * 1e3, 3) for k, v in host_t.items()},
-                     "cpus": os.cpu_count()}
+                     "cpus": os.cpu_count(), "epochs": -(-args.steps // epoch_cap)}
     ok = bool(torch.equal(src, dst))
 
     ms_max = allmax(ms)
@@ -328,7 +349,8 @@ def main():
         host_src = torch.empty(nblocks * elems, dtype=torch.bfloat16).pin_memory()
         host_src.copy_(src.cpu())
         host_out = torch.empty(elems + 1, dtype=torch.bfloat16).pin_memory()
-        e2e_prepared = [fresh_prepared() for _ in range(e2e_steps + 1)]
+        e2e_steps = min(e2e_steps, epoch_cap - 1) if epoch_cap > 1 else 1
+        e2e_prepared = new_epoch(e2e_steps + 1)
         h2d_bytes = nblocks * block_bytes
         d2h_bytes = (elems + 1) * 2
 
