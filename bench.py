@@ -46,6 +46,7 @@ def parse_args():
     p.add_argument("--layers", type=int, default=32, help="batches per phase (reference --steps)")
     p.add_argument("--variant", default="auto", choices=["auto", "ldst", "tma", "ldst256"])
     p.add_argument("--max-ctas", type=int, default=0)
+    p.add_argument("--streams", type=int, default=4, help="internal launch streams per connection")
     p.add_argument("--host-lookup", action="store_true",
                    help="resolve read keys through the server instead of the HBM index")
     p.add_argument("--base-port", type=int, default=0)
@@ -230,7 +231,8 @@ def main():
     ccfg = ist.ClientConfig(host_addr="127.0.0.1", service_port=base_port + peer,
                             connection_type=ist.TYPE_RDMA, log_level="warning",
                             device=local_rank, device_lookup=not args.host_lookup,
-                            copy_variant=args.variant, max_ctas=args.max_ctas)
+                            copy_variant=args.variant, max_ctas=args.max_ctas,
+                            streams=args.streams)
     conn = ist.InfinityConnection(ccfg)
     conn.connect()
 
@@ -415,7 +417,7 @@ def main():
                        "seq_len": None, "layers_per_phase": layers,
                        "parallelism": f"{world} pool shards, ring placement (rank r -> GPU (r+1)%N)",
                        "l2": "working set 2 GiB per GPU per step >> 126 MB L2 (no flush needed)",
-                       "variant": args.variant, "lookup": "host" if args.host_lookup else "device-index",
+                       "variant": args.variant, "streams": args.streams, "lookup": "host" if args.host_lookup else "device-index",
                        "phase_sync": True},
             "roofline": {"gbps": round(roof, 1), "what": roof_name,
                          "fraction": round(value / roof, 3)},

@@ -817,6 +817,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
         uint32_t m = 0;
         bool can_publish = table != nullptr;
         bool all_remote = true;
+        bool all_local = !ctx->seg_remote.empty() && !ctx->seg_remote[0];  // index table (segment 0)
         uint64_t align_or = 0;
         const size_t nseg = ctx->seg_ptr.size();
         uint8_t* const* seg_ptr = ctx->seg_ptr.data();
@@ -833,6 +834,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             const uint64_t pool = reinterpret_cast<uint64_t>(segbase) + addr_off(rb.remote_addr);
             const uint64_t local = base_ptr + local_off[i] * scale;
             all_remote = all_remote && ctx->seg_remote[seg];
+            all_local = all_local && !ctx->seg_remote[seg];
             align_or |= local;
             descs[m].src = write ? local : pool;
             descs[m].dst = write ? pool : local;
@@ -859,6 +861,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
         L.status = ctx->status_d;
         L.variant = copy_variant_;
         L.max_ctas = max_ctas_ ? max_ctas_ : (all_remote ? 2 * kernels::sm_count() : 0);
+        L.all_local = all_local;
         if (can_publish) {
             L.recs = reinterpret_cast<const kernels::IndexEntry*>(ctx->ring_d + at_rec);
             L.table = table;
@@ -877,6 +880,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             F.done = L.done;
             F.status = L.status;
             F.max_ctas = L.max_ctas;
+            F.all_local = all_local;
             e = write ? kernels::launch_kv_write_fp8(F, stream) : kernels::launch_kv_read_fp8(F, stream);
         } else {
             e = kernels::launch_kv_copy(L, stream);

@@ -55,6 +55,14 @@ __device__ __forceinline__ void st_v8(void* p, const u32x8& r) {  // STG.E.ENL2.
 
 // ---------------------------------------------------------------- system-scope sync
 __device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// counter increment that releases this thread's earlier (fenced) work and acquires the
+// other arrivers'; gpu scope: the counters live in this GPU's own memory
+__device__ __forceinline__ uint32_t atom_add_acq_rel_gpu(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {  // LDG.E.STRONG.SYS
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -74,6 +82,15 @@ __device__ __forceinline__ void st_relaxed_sys_u64(uint64_t* p, uint64_t v) {
 __device__ __forceinline__ uint64_t cas_relaxed_sys_u64(uint64_t* p, uint64_t cmp, uint64_t val) {
     uint64_t old;
     asm volatile("atom.relaxed.sys.global.cas.b64 %0, [%1], %2, %3;"
+                 : "=l"(old)
+                 : "l"(p), "l"(cmp), "l"(val)
+                 : "memory");
+    return old;
+}
+
+__device__ __forceinline__ uint64_t cas_relaxed_gpu_u64(uint64_t* p, uint64_t cmp, uint64_t val) {
+    uint64_t old;
+    asm volatile("atom.relaxed.gpu.global.cas.b64 %0, [%1], %2, %3;"
                  : "=l"(old)
                  : "l"(p), "l"(cmp), "l"(val)
                  : "memory");

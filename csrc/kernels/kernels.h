@@ -63,6 +63,8 @@ struct CopyLaunch {
     uint32_t* status = nullptr;       // kStatWords u32, device-addressable
     int variant = kCopyAuto;
     int max_ctas = 0;                 // 0 = pick from the problem size
+    unsigned long long* trace = nullptr;  // optional per-CTA %globaltimer stamps (bench only)
+    bool all_local = false;  // every destination and the index table are in this GPU's own HBM
 };
 cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream);
 
@@ -80,6 +82,7 @@ struct Fp8Launch {
     uint32_t* done = nullptr;
     uint32_t* status = nullptr;
     int max_ctas = 0;
+    bool all_local = false;
 };
 // bytes a quantised page occupies in the pool: elems (e4m3) + 4 * elems/group (scales)
 inline uint32_t fp8_block_bytes(uint32_t elems, uint32_t group) {

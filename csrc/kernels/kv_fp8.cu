@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kThreads)
 cudaError_t launch_kv_write_fp8(const Fp8Launch& a, cudaStream_t stream) {
     if (a.n == 0 || a.elems == 0) return cudaSuccess;
     if (a.group != kRow || a.elems % kRow != 0) return cudaErrorInvalidValue;
-    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n};
+    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n, nullptr, !a.all_local};
     if (!a.table || !a.done) pub.recs = nullptr;
     const uint32_t cpb = (a.elems + kChunkElems - 1) / kChunkElems;
     const uint64_t total = uint64_t(a.n) * cpb;

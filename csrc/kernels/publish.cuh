@@ -29,7 +29,19 @@ struct Publish {
     uint32_t* scratch;  // 3*n zeroed u32 in client-local device memory: done | slot+1 | tag
     uint32_t* status;
     uint32_t n;
+    unsigned long long* trace = nullptr;  // optional: 8 %globaltimer stamps per CTA (bench only)
+    // true: some destination (pool block or index table) is NOT in this GPU's own HBM, so
+    // "performed" must mean acknowledged across NVLink: fence.acq_rel.sys (MEMBAR.SYS +
+    // ERRBAR, ~10 us).  false: everything is local; the local L2 is the point of coherence
+    // for local memory, also for peers reading it over NVLink, so gpu scope suffices.
+    bool sys = true;
 };
+
+__device__ inline unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // Reserve a slot for `rec`.  Returns slot + 1, or 0 when nothing is to be committed (the
 // key is already published - first writer wins - or the table is full).
@@ -37,10 +49,13 @@ __device__ inline uint32_t claim_entry(const Publish& pub, const IndexEntry& rec
     uint64_t slot = rec.h1 & pub.mask;
     for (uint64_t probe = 0; probe <= pub.mask; ++probe) {
         IndexEntry* e = pub.table + slot;
-        const uint64_t cur = cas_relaxed_sys_u64(&e->h1, 0, rec.h1);
+        // Atomics on one address are serialised at the L2 that owns it whatever the scope
+        // qualifier, so a local table may be claimed at gpu scope even if peers claim too.
+        const uint64_t cur = pub.sys ? cas_relaxed_sys_u64(&e->h1, 0, rec.h1)
+                                     : cas_relaxed_gpu_u64(&e->h1, 0, rec.h1);
         if (cur == 0) {  // slot is ours; fields are posted stores, tag stays 0
-            st_relaxed_sys_u64(&e->h2, rec.h2);
-            st_relaxed_sys_u64(&e->addr, rec.addr);
+            e->h2 = rec.h2;
+            e->addr = rec.addr;
             e->size = rec.size;
             return uint32_t(slot) + 1;
         }
@@ -60,10 +75,12 @@ __device__ inline uint32_t claim_entry(const Publish& pub, const IndexEntry& rec
 // pattern, so the tag needs no second MEMBAR.SYS/ERRBAR (the most expensive instruction of
 // the epilogue, profiles/r1_ncu_kv_copy_*.txt).
 __device__ inline void commit_entry(const Publish& pub, uint32_t slot_plus1, uint32_t tag) {
-    if (slot_plus1)
-        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(&pub.table[slot_plus1 - 1].tag),
-                     "r"(tag)
-                     : "memory");
+    if (!slot_plus1) return;
+    uint32_t* p = &pub.table[slot_plus1 - 1].tag;
+    if (pub.sys)
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(tag) : "memory");
+    else
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(tag) : "memory");
 }
 
 constexpr int kCtrlBarrier = 1;  // named barrier shared by the copy warps and the control warp
@@ -84,6 +101,8 @@ __device__ inline void ctrl_barrier_sync(uint32_t threads) {
 __device__ inline void control_warp(const Publish& pub, uint32_t lane, uint32_t first,
                                     uint32_t count, uint32_t stride, uint32_t cpb,
                                     uint32_t cta_threads) {
+    unsigned long long* tr = pub.trace && lane == 0 ? pub.trace + size_t(blockIdx.x) * 8 : nullptr;
+    if (tr) tr[0] = globaltimer_ns();
     uint32_t* done = pub.scratch;
     uint32_t* slot_of = pub.scratch + pub.n;
     uint32_t* tag_of = pub.scratch + 2 * size_t(pub.n);
@@ -103,21 +122,31 @@ __device__ inline void control_warp(const Publish& pub, uint32_t lane, uint32_t 
             tag_of[block] = rec.tag;
         }
     }
+    if (tr) tr[1] = globaltimer_ns();  // claims done
     // ---- wait until every copy thread of this CTA has issued its last store
     ctrl_barrier_sync(cta_threads);
-    fence_sys();
+    if (tr) tr[2] = globaltimer_ns();  // copy warps done issuing
+    // The ONE expensive fence of the epilogue: when it completes, every data store of this
+    // CTA (and the claim's field stores) has been performed where its readers will look.
+    if (pub.sys)
+        fence_sys();
+    else
+        fence_gpu();
+    if (tr) tr[3] = globaltimer_ns();  // stores performed
     // ---- commit
     if (cpb == 1 && count <= 32) {
         if (lane < count) commit_entry(pub, my_slot, my_tag);
+        if (tr) tr[4] = globaltimer_ns();
         return;
     }
     for (uint32_t k = lane; k < count; k += 32) {
         const uint32_t block = (first + k * stride) / cpb;
-        const uint32_t arrived = cpb == 1 ? 1 : atomicAdd(done + block, 1u) + 1;
+        // acq_rel counter in local memory: every arriver fenced its stores BEFORE its
+        // increment, so when the last arriver observes the full count all chunks of the block
+        // are already performed; its tag store is issued after that in program order
+        // (no second MEMBAR.SYS: profiles/r1_trace_write_epilogue_v1.json, +10 us each).
+        const uint32_t arrived = cpb == 1 ? 1 : atom_add_acq_rel_gpu(done + block, 1u) + 1;
         if (arrived != cpb) continue;
-        // acquire side of the counter (other CTAs' stores and scratch writes happen-before
-        // us) and release side of the tag store below, in one fence
-        if (cpb != 1) fence_sys();
         const uint32_t s = __ldcg(slot_of + block);
         const uint32_t t = __ldcg(tag_of + block);
         done[block] = 0;  // leave the scratch zeroed for the next launch
@@ -125,6 +154,7 @@ __device__ inline void control_warp(const Publish& pub, uint32_t lane, uint32_t 
         tag_of[block] = 0;
         commit_entry(pub, s, t);
     }
+    if (tr) tr[4] = globaltimer_ns();
 }
 
 }  // namespace istore::kernels
