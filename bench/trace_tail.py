@@ -13,7 +13,7 @@ from infinistore_b200 import _infinistore as native  # noqa: E402
 from infinistore_b200 import ops  # noqa: E402
 
 
-def run(pool_dev, label, nblk=256, bs=128 << 10, ctas=0, all_local=False):
+def run(pool_dev, label, nblk=256, bs=128 << 10, ctas=0, all_local=False, debug=0):
     dev = "cuda:0"
     src = torch.empty(nblk * bs, dtype=torch.uint8, device=dev).random_(0, 255)
     pool = torch.empty(nblk * bs, dtype=torch.uint8, device=pool_dev)
@@ -34,7 +34,7 @@ def run(pool_dev, label, nblk=256, bs=128 << 10, ctas=0, all_local=False):
             native.kernels.kv_copy(d.data_ptr(), nblk, bs, ops.VARIANTS["ldst256"], ctas,
                                    ops._stream(torch.device(dev)), p.recs.data_ptr(),
                                    p.table.data_ptr(), p.mask, p.done.data_ptr(), 0, 0,
-                                   trace.data_ptr(), all_local)
+                                   trace.data_ptr(), all_local, debug)
             e1.record()
             e1.synchronize()
         t = trace.cpu().numpy().reshape(-1, 8)
@@ -49,14 +49,17 @@ def run(pool_dev, label, nblk=256, bs=128 << 10, ctas=0, all_local=False):
                "fence_cost_med": np.median(rel[:, 3] - rel[:, 2]),
                "fence_cost_max": (rel[:, 3] - rel[:, 2]).max()}
     out = {k: (round(float(v), 2) if not isinstance(v, int) else v) for k, v in out.items()}
-    print(label, json.dumps(out), flush=True)
+    print(label, {a: b for a, b in out.items() if a in ("event_us", "fence_done_max", "commit_max", "claim_done_max", "copy_done_max")}, flush=True)
     return out
 
 
 res = {"local": run("cuda:0", "local-sys"), "local_gpu_scope": run("cuda:0", "local-gpu", all_local=True)}
+for dbg in (1, 2, 4, 7):
+    res[f"local_gpu_dbg{dbg}"] = run("cuda:0", f"local-gpu dbg={dbg}", all_local=True, debug=dbg)
 if torch.cuda.device_count() >= 2:
     native.enable_peer_access(0, 1)
     res["peer"] = run("cuda:1", "peer ")
-    res["peer_296"] = run("cuda:1", "peer296", ctas=296)
+    for dbg in (1, 2, 4, 7):
+        res[f"peer_dbg{dbg}"] = run("cuda:1", f"peer dbg={dbg}", debug=dbg)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/trace_tail.json", "w"), indent=1)

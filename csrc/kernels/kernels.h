@@ -65,6 +65,7 @@ struct CopyLaunch {
     int max_ctas = 0;                 // 0 = pick from the problem size
     unsigned long long* trace = nullptr;  // optional per-CTA %globaltimer stamps (bench only)
     bool all_local = false;  // every destination and the index table are in this GPU's own HBM
+    uint32_t debug = 0;      // bench only, see publish.cuh
 };
 cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream);
 

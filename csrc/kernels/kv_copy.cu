@@ -210,7 +210,7 @@ int sm_count() {
 
 cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream) {
     if (a.n == 0 || a.bytes == 0) return cudaSuccess;
-    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n, a.trace, !a.all_local};
+    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n, a.trace, !a.all_local, a.debug};
     if (!a.table || !a.done) pub.recs = nullptr;
     const int sms = sm_count();
 
@@ -256,7 +256,11 @@ cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream) {
         return cudaGetLastError();
     }
 
-    const uint32_t chunk = std::min(a.bytes, kLdStChunk);
+    // Work item = one 32 KB chunk, or - when there are at least as many blocks as SMs - one
+    // whole block: then a block is moved by a single CTA, its commit needs no cross-CTA
+    // counter (claim, one fence, one store) and a reader resolves every key exactly once.
+    uint32_t chunk = std::min(a.bytes, kLdStChunk);
+    if (a.n >= uint32_t(sms) && a.bytes <= (1u << 20)) chunk = a.bytes;
     const uint32_t cpb = (a.bytes + chunk - 1) / chunk;
     const uint64_t total = uint64_t(a.n) * cpb;
     constexpr int T = kLdStThreads + 32;

@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(kThreads)
 
 cudaError_t launch_kv_read_fused(const ReadFusedLaunch& a, cudaStream_t stream) {
     if (a.n == 0 || a.bytes == 0) return cudaSuccess;
-    const uint32_t chunk = std::min(a.bytes, 32u << 10);
+    uint32_t chunk = std::min(a.bytes, 32u << 10);
+    if (a.n >= uint32_t(sm_count()) && a.bytes <= (1u << 20)) chunk = a.bytes;  // see kv_copy.cu
     const uint32_t cpb = (a.bytes + chunk - 1) / chunk;
     const uint64_t total = uint64_t(a.n) * cpb;
     const bool aligned16 = (a.bytes % 16) == 0 && (a.align_or & 15) == 0;

@@ -35,6 +35,7 @@ struct Publish {
     // ERRBAR, ~10 us).  false: everything is local; the local L2 is the point of coherence
     // for local memory, also for peers reading it over NVLink, so gpu scope suffices.
     bool sys = true;
+    uint32_t debug = 0;  // bench only: 1 = skip claim, 2 = skip fence, 4 = skip commit store
 };
 
 __device__ inline unsigned long long globaltimer_ns() {
@@ -75,7 +76,7 @@ __device__ inline uint32_t claim_entry(const Publish& pub, const IndexEntry& rec
 // pattern, so the tag needs no second MEMBAR.SYS/ERRBAR (the most expensive instruction of
 // the epilogue, profiles/r1_ncu_kv_copy_*.txt).
 __device__ inline void commit_entry(const Publish& pub, uint32_t slot_plus1, uint32_t tag) {
-    if (!slot_plus1) return;
+    if (!slot_plus1 || (pub.debug & 4)) return;
     uint32_t* p = &pub.table[slot_plus1 - 1].tag;
     if (pub.sys)
         asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(tag) : "memory");
@@ -113,7 +114,7 @@ __device__ inline void control_warp(const Publish& pub, uint32_t lane, uint32_t 
         if (item % cpb) continue;
         const uint32_t block = item / cpb;
         const IndexEntry rec = pub.recs[block];
-        const uint32_t s = claim_entry(pub, rec);
+        const uint32_t s = (pub.debug & 1) ? uint32_t(rec.h1 & pub.mask) + 1 : claim_entry(pub, rec);
         if (cpb == 1 && count <= 32) {
             my_slot = s;
             my_tag = rec.tag;
@@ -128,7 +129,8 @@ __device__ inline void control_warp(const Publish& pub, uint32_t lane, uint32_t 
     if (tr) tr[2] = globaltimer_ns();  // copy warps done issuing
     // The ONE expensive fence of the epilogue: when it completes, every data store of this
     // CTA (and the claim's field stores) has been performed where its readers will look.
-    if (pub.sys)
+    if (pub.debug & 2) {
+    } else if (pub.sys)
         fence_sys();
     else
         fence_gpu();

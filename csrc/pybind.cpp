@@ -593,7 +593,7 @@ PYBIND11_MODULE(_infinistore, m) {
         "kv_copy",
         [](uint64_t descs, uint32_t n, uint32_t bytes, int variant, int max_ctas, uint64_t stream,
            uint64_t recs, uint64_t table, uint64_t table_mask, uint64_t done, uint64_t status,
-           uint64_t align_or, uint64_t trace, bool all_local) {
+           uint64_t align_or, uint64_t trace, bool all_local, uint32_t debug) {
             kernels::CopyLaunch L;
             L.descs = as_ptr<const kernels::CopyDesc>(descs);
             L.n = n;
@@ -608,6 +608,7 @@ PYBIND11_MODULE(_infinistore, m) {
             L.max_ctas = max_ctas;
             L.trace = as_ptr<unsigned long long>(trace);
             L.all_local = all_local;
+            L.debug = debug;
             const cudaError_t e = kernels::launch_kv_copy(L, as_ptr<CUstream_st>(stream));
             if (e != cudaSuccess) throw std::runtime_error(cudaGetErrorString(e));
         },
@@ -615,7 +616,7 @@ PYBIND11_MODULE(_infinistore, m) {
         py::arg("max_ctas") = 0, py::arg("stream") = 0, py::arg("recs") = 0,
         py::arg("table") = 0, py::arg("table_mask") = 0, py::arg("done") = 0,
         py::arg("status") = 0, py::arg("align_or") = 0, py::arg("trace") = 0,
-        py::arg("all_local") = false);
+        py::arg("all_local") = false, py::arg("debug") = 0);
     k.def(
         "index_lookup",
         [](uint64_t key_bytes, uint64_t key_off, uint64_t key_len, uint32_t n, uint64_t table,
