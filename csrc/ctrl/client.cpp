@@ -206,7 +206,6 @@ struct Connection::DevCtx {
             cudaEventDestroy(pool_ev[i]);
         }
         if (user_ev) cudaEventDestroy(user_ev);
-        for (cudaEvent_t e : ev_free) cudaEventDestroy(e);
         if (stream) {
             cudaStreamSynchronize(stream);
             cudaStreamDestroy(stream);
@@ -223,25 +222,6 @@ struct Connection::DevCtx {
         for (cudaStream_t s : busy) cudaStreamSynchronize(s);
         busy.clear();
         dirty = false;
-    }
-    std::mutex ev_mu;
-    std::vector<cudaEvent_t> ev_free;  // recycled completion events (taken/returned by 2 threads)
-    cudaEvent_t take_event() {
-        {
-            std::lock_guard<std::mutex> lk(ev_mu);
-            if (!ev_free.empty()) {
-                cudaEvent_t e = ev_free.back();
-                ev_free.pop_back();
-                return e;
-            }
-        }
-        cudaEvent_t e = nullptr;
-        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-        return e;
-    }
-    void give_event(cudaEvent_t e) {
-        std::lock_guard<std::mutex> lk(ev_mu);
-        ev_free.push_back(e);
     }
     cudaStream_t last = nullptr;  // stream of the most recent launch
     void mark(cudaStream_t s) {
@@ -293,8 +273,6 @@ struct Connection::Task {
     // wait for device work, then commit + callback
     int device = -1;
     cudaEvent_t event = nullptr;
-    bool recycle_event = false;        // event belongs to the device context's pool
-    std::vector<uint64_t> commit_addrs;  // blocks to commit once `event` has completed
     int status = 0;
     bool commit = false;
     std::function<void(int)> done_cb;
@@ -507,17 +485,7 @@ int Connection::get_match_last_index(const std::vector<std::string_view>& keys) 
 }
 
 int Connection::sync_local() {
-    const int drained = drain_devices();
-    if (drained != 0) return drained;
-    // eager commits (and async operations) are sent by the completion thread
-    if (!wait_async_idle()) {
-        fail("sync: timed out waiting for the completion thread");
-        return -1;
-    }
-    if (async_error_.exchange(false)) {
-        fail("sync: a transfer or its commit failed");
-        return -1;
-    }
+    if (drain_devices() != 0) return -1;
     if (flush_commits() != 0) return -1;
     int32_t code = 0;
     std::vector<uint8_t> p;
@@ -529,24 +497,16 @@ int Connection::sync_local() {
 }
 
 int Connection::sync_rdma() {
-    const int r = sync_local();
-    return r < 0 ? r : 0;
-}
-
-int Connection::send_commit(const uint64_t* addrs, size_t count) {
-    // chunk so that one message stays far below the body cap
-    constexpr size_t kChunk = 256 * 1024;
-    for (size_t at = 0; at < count; at += kChunk) {
-        const size_t n = std::min(kChunk, count - at);
-        std::vector<uint8_t> buf(align_up(n * 8 + 128, 8));
-        fb::Builder b(buf.data(), buf.size());
-        encode_remote_meta(b, {}, 0, 0, addrs + at, n, kOpCommit);
-        if (send_only(kOpCommit, b.data(), b.size()) != 0) {
-            fail("commit: send failed");
+    {  // async operations first: their completions append to the commit list
+        std::unique_lock<std::mutex> lk(q_mu_);
+        if (!idle_cv_.wait_for(lk, std::chrono::milliseconds(cfg_.timeout_ms),
+                               [this] { return inflight_async_ == 0; })) {
+            fail("sync: timed out waiting for asynchronous operations");
             return -1;
         }
     }
-    return 0;
+    const int r = sync_local();
+    return r < 0 ? r : 0;
 }
 
 int Connection::flush_commits() {
@@ -556,13 +516,19 @@ int Connection::flush_commits() {
         addrs.swap(pending_commit_);
     }
     if (addrs.empty()) return 0;
-    return send_commit(addrs.data(), addrs.size());
-}
-
-bool Connection::wait_async_idle() {
-    std::unique_lock<std::mutex> lk(q_mu_);
-    return idle_cv_.wait_for(lk, std::chrono::milliseconds(cfg_.timeout_ms),
-                             [this] { return inflight_async_ == 0; });
+    // chunk so that one message stays far below the body cap
+    constexpr size_t kChunk = 256 * 1024;
+    for (size_t at = 0; at < addrs.size(); at += kChunk) {
+        const size_t n = std::min(kChunk, addrs.size() - at);
+        std::vector<uint8_t> buf(align_up(n * 8 + 128, 8));
+        fb::Builder b(buf.data(), buf.size());
+        encode_remote_meta(b, {}, 0, 0, addrs.data() + at, n, kOpCommit);
+        if (send_only(kOpCommit, b.data(), b.size()) != 0) {
+            fail("commit: send failed");
+            return -1;
+        }
+    }
+    return 0;
 }
 
 int Connection::allocate(const std::vector<std::string_view>& keys, int block_size,
@@ -849,8 +815,6 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             recs = reinterpret_cast<kernels::IndexEntry*>(ctx->ring_h + at_rec);
         }
         uint32_t m = 0;
-        std::vector<uint64_t> batch_addrs;
-        if (write) batch_addrs.reserve(batch_cap);
         bool can_publish = table != nullptr;
         bool all_remote = true;
         bool all_local = !ctx->seg_remote.empty() && !ctx->seg_remote[0];  // index table (segment 0)
@@ -883,7 +847,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
                     else
                         can_publish = false;  // not allocated through this connection
                 }
-                batch_addrs.push_back(rb.remote_addr);
+                pending_commit_.push_back(rb.remote_addr);
             }
             ++m;
         }
@@ -928,19 +892,6 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
         ctx->mark(stream);
         stats_.kernel_launches++;
         (write ? stats_.bytes_written : stats_.bytes_read) += uint64_t(m) * uint64_t(block_size);
-        if (write) {
-            // Eager commit: the completion thread waits for this launch and sends the COMMIT
-            // while later layers are still being moved, so sync() finds (almost) nothing left
-            // to send and the server applies commits concurrently with the transfer.
-            Task t;
-            t.kind = Task::kWaitEvent;
-            t.device = kd;
-            t.event = ctx->take_event();
-            t.recycle_event = true;
-            cudaEventRecord(t.event, stream);
-            t.commit_addrs = std::move(batch_addrs);
-            post(std::move(t));
-        }
     }
     return 0;
 }
@@ -1262,22 +1213,9 @@ void Connection::worker() {
             if (t.event) {
                 DeviceGuard g(t.device);
                 if (cudaEventSynchronize(t.event) != cudaSuccess) status = -1;
-                if (t.recycle_event) {
-                    std::lock_guard<std::mutex> lk(mu_);
-                    auto it = devs_.find(t.device);
-                    if (it != devs_.end())
-                        it->second->give_event(t.event);
-                    else
-                        cudaEventDestroy(t.event);
-                } else {
-                    cudaEventDestroy(t.event);
-                }
+                cudaEventDestroy(t.event);
             }
-            if (status == 0 && !t.commit_addrs.empty() &&
-                send_commit(t.commit_addrs.data(), t.commit_addrs.size()) != 0)
-                status = -1;
             if (status == 0 && t.commit && flush_commits() != 0) status = -1;
-            if (status != 0) async_error_.store(true);
             if (t.done_cb) t.done_cb(status);
         }
         {

@@ -141,8 +141,6 @@ class Connection {
     int lookup_blocks(char op, const std::vector<KeyOffset>& blocks, int block_size,
                       std::vector<RemoteBlock>& out);
     int flush_commits();
-    int send_commit(const uint64_t* addrs, size_t count);
-    bool wait_async_idle();
 
     // data plane
     DevCtx* dev_ctx(int device);
@@ -195,7 +193,6 @@ class Connection {
     std::deque<Task> queue_;
     size_t inflight_async_ = 0;
     bool stop_ = false;
-    std::atomic<bool> async_error_{false};
 };
 
 }  // namespace istore
