@@ -68,11 +68,15 @@ def main():
             conn.sync()
             t_sync_r = time.perf_counter() - t0
             assert torch.equal(src, dst)
+            st = conn.stats()
             med = lambda v: sorted(v)[len(v) // 2]  # noqa: E731
             row = {"alloc_us_per_key": t_alloc / n * 1e6, "write_call_us": med(tw) * 1e6,
                    "write_ns_per_block": med(tw) / per_call * 1e9, "read_call_us": med(tr) * 1e6,
                    "read_ns_per_block": med(tr) / per_call * 1e9, "sync_after_write_us": t_sync_w * 1e6,
-                   "sync_after_read_us": t_sync_r * 1e6}
+                   "sync_after_read_us": t_sync_r * 1e6,
+                   "cxx_build_us_per_call": st["ns_build"] / max(st["calls"], 1) / 1e3,
+                   "cxx_streams_us_per_call": st["ns_streams"] / max(st["calls"], 1) / 1e3,
+                   "cxx_launch_us_per_call": st["ns_launch"] / max(st["calls"], 1) / 1e3}
             out[f"lookup={'device' if lookup else 'host'} blocks/call={per_call}"] = {
                 k: round(v, 2) for k, v in row.items()}
             print(lookup, per_call, out[f"lookup={'device' if lookup else 'host'} blocks/call={per_call}"], flush=True)

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cerrno>
+#include <chrono>
 #include <cstring>
 
 #include "../core/log.h"
@@ -83,6 +84,12 @@ bool recv_all(int fd, void* buf, size_t len) {
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) & ~(a - 1); }
+
+inline uint64_t now_ns() {
+    return uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(
+                        std::chrono::steady_clock::now().time_since_epoch())
+                        .count());
+}
 
 }  // namespace
 
@@ -791,7 +798,10 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
     DevCtx* ctx = dev_ctx(kd);
     if (!ctx) return -1;
     DeviceGuard g(kd);
+    const uint64_t t_pick0 = now_ns();
     cudaStream_t stream = ctx->pick(reinterpret_cast<cudaStream_t>(stream_in), write, streams_);
+    stats_.ns_streams += now_ns() - t_pick0;
+    stats_.calls++;
 
     // the device index lives in segment 0
     kernels::IndexEntry* table = nullptr;
@@ -805,6 +815,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
 
     size_t i = 0;
     while (i < n) {
+        const uint64_t t_build0 = now_ns();
         const size_t batch_cap = std::min(kMaxBatch, n - i);
         const size_t at_desc = ctx->ring_alloc(batch_cap * sizeof(kernels::CopyDesc));
         auto* descs = reinterpret_cast<kernels::CopyDesc*>(ctx->ring_h + at_desc);
@@ -868,6 +879,8 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             L.table_mask = table_mask;
             L.done = reinterpret_cast<uint32_t*>(ctx->zeros + ctx->zeros_alloc(size_t(m) * 12));
         }
+        const uint64_t t_launch0 = now_ns();
+        stats_.ns_build += t_launch0 - t_build0;
         cudaError_t e;
         if (fp8_elems) {
             kernels::Fp8Launch F;
@@ -885,6 +898,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
         } else {
             e = kernels::launch_kv_copy(L, stream);
         }
+        stats_.ns_launch += now_ns() - t_launch0;
         if (e != cudaSuccess) {
             fail(std::string("page mover launch failed: ") + cudaGetErrorString(e));
             return -1;
@@ -1005,8 +1019,12 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
         return -1;
     }
     DeviceGuard g(device);
+    const uint64_t t_pick0 = now_ns();
     cudaStream_t stream = ctx->pick(reinterpret_cast<cudaStream_t>(stream_in), false, streams_);
+    stats_.ns_streams += now_ns() - t_pick0;
+    stats_.calls++;
     for (size_t base = 0; base < blocks.size(); base += kMaxBatch) {
+        const uint64_t t_build0 = now_ns();
         const size_t n = std::min(kMaxBatch, blocks.size() - base);
         size_t key_bytes = 0;
         std::vector<std::string_view> kp(n);
@@ -1035,6 +1053,8 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
         const int grid_cap = max_ctas_ ? max_ctas_ : (all_remote ? 2 * kernels::sm_count() : 0);
         uint64_t align_or = base_ptr;
         for (size_t i = 0; i < n; ++i) align_or |= blocks[base + i].offset;
+        const uint64_t t_launch0 = now_ns();
+        stats_.ns_build += t_launch0 - t_build0;
         cudaError_t e;
         if (!fp8_elems && copy_variant_ != kernels::kCopyTma) {
             // one kernel: hash + probe + move
@@ -1094,6 +1114,7 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             }
             stats_.kernel_launches += 2;
         }
+        stats_.ns_launch += now_ns() - t_launch0;
         if (e != cudaSuccess) {
             fail(std::string("device-index read failed to launch: ") + cudaGetErrorString(e));
             return -1;

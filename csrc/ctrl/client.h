@@ -64,6 +64,11 @@ struct ClientStats {
     uint64_t bytes_read = 0;
     uint64_t ctrl_requests = 0;
     uint64_t host_copies = 0;       // blocks moved with memcpy (CPU tensors / host pool)
+    // host-side time of the data-plane calls, nanoseconds (tracing aid, see docs/design.md)
+    uint64_t ns_build = 0;    // descriptor / record / key packing loops
+    uint64_t ns_streams = 0;  // stream selection + cross-stream event dependencies
+    uint64_t ns_launch = 0;   // cudaLaunchKernel and friends
+    uint64_t calls = 0;
 };
 
 class Connection {

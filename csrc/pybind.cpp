@@ -458,6 +458,10 @@ PYBIND11_MODULE(_infinistore, m) {
             d["bytes_read"] = s.bytes_read;
             d["ctrl_requests"] = s.ctrl_requests;
             d["host_copies"] = s.host_copies;
+            d["ns_build"] = s.ns_build;
+            d["ns_streams"] = s.ns_streams;
+            d["ns_launch"] = s.ns_launch;
+            d["calls"] = s.calls;
             return d;
         });
 

@@ -292,6 +292,27 @@ def _device_of(cache: torch.Tensor) -> int:
     return cache.device.index if cache.device.type == "cuda" else -1
 
 
+try:  # raw handle of torch's current stream without building a Stream object (~0.2 us)
+    _raw_current_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:  # pragma: no cover
+    _raw_current_stream = None
+
+
+class _TensorInfo:
+    """Per-tensor facts the hot path needs, computed once (the KV cache tensor is registered
+    once and then addressed by offsets, reference calling convention C10)."""
+
+    __slots__ = ("ptr", "es", "dev", "ref")
+
+    def __init__(self, cache: torch.Tensor):
+        import weakref
+
+        self.ptr = cache.data_ptr()
+        self.es = cache.element_size()
+        self.dev = _device_of(cache)
+        self.ref = weakref.ref(cache)
+
+
 def _stream_of(cache: torch.Tensor, stream) -> int:
     """cudaStream_t handle to launch on.  "current" = torch's current stream of the tensor's
     device (kernels are ordered after the work that produced the pages); None = the
@@ -321,7 +342,29 @@ class InfinityConnection:
         self.local_connected = False
         self.rdma_connected = False
         self.config = config
+        self._tinfo = {}
         Logger.set_log_level(config.log_level)
+
+    def _info(self, cache: torch.Tensor) -> "_TensorInfo":
+        """Validated facts about `cache` (contiguous, device rule), cached per tensor object."""
+        info = self._tinfo.get(id(cache))
+        if info is not None and info.ref() is cache and info.ptr == cache.data_ptr():
+            return info
+        self._verify(cache)
+        if len(self._tinfo) > 64:
+            self._tinfo = {k: v for k, v in self._tinfo.items() if v.ref() is not None}
+        info = _TensorInfo(cache)
+        self._tinfo[id(cache)] = info
+        return info
+
+    @staticmethod
+    def _stream(info: "_TensorInfo", cache: torch.Tensor, stream) -> int:
+        if info.dev < 0 or stream is None:
+            return 0
+        if stream == "current" and _raw_current_stream is not None:
+            handle = _raw_current_stream(info.dev)
+            return handle if handle != 0 else _CUDA_STREAM_LEGACY
+        return _stream_of(cache, stream)
 
     # ------------------------------------------------------------------ connect
     def _apply_options(self):
@@ -379,11 +422,11 @@ class InfinityConnection:
         ``blocks`` is a list of (key, offset_in_elements); ``page_size`` is in elements.
         Returns once the kernel is enqueued; ``sync()`` is the completion barrier.
         """
-        self._verify(cache)
+        info = self._info(cache)
         assert self.local_connected
-        es = cache.element_size()
-        ret = self.conn.rw_local(self.OP_W, blocks, page_size * es, cache.data_ptr(),
-                                 _device_of(cache), _stream_of(cache, stream), es)
+        es = info.es
+        ret = self.conn.rw_local(self.OP_W, blocks, page_size * es, info.ptr, info.dev,
+                                 self._stream(info, cache, stream), es)
         if ret < 0:
             raise Exception(f"Failed to write to infinistore, ret = {ret}")
         return 0
@@ -397,10 +440,9 @@ class InfinityConnection:
         skipped (first writer wins).
         """
         assert self.rdma_connected
-        self._verify(cache)
-        es = cache.element_size()
-        ret = self.conn.w_rdma(offsets, page_size * es, remote_blocks, cache.data_ptr(),
-                               _device_of(cache), _stream_of(cache, stream), es)
+        info = self._info(cache)
+        ret = self.conn.w_rdma(offsets, page_size * info.es, remote_blocks, info.ptr, info.dev,
+                               self._stream(info, cache, stream), info.es)
         if ret < 0:
             raise Exception(f"Failed to write to infinistore, ret = {ret}")
         return 0
@@ -433,14 +475,14 @@ class InfinityConnection:
         Raises if a key is missing or not committed (with ``device_lookup`` the miss is
         detected on the GPU and reported by ``sync()``).
         """
-        self._verify(cache)
-        es = cache.element_size()
+        info = self._info(cache)
+        es = info.es
         if self.local_connected:
-            ret = self.conn.rw_local(self.OP_R, blocks, page_size * es, cache.data_ptr(),
-                                     _device_of(cache), _stream_of(cache, stream), es)
+            ret = self.conn.rw_local(self.OP_R, blocks, page_size * es, info.ptr, info.dev,
+                                     self._stream(info, cache, stream), es)
         elif self.rdma_connected:
-            ret = self.conn.r_rdma(blocks, page_size * es, cache.data_ptr(),
-                                   _device_of(cache), _stream_of(cache, stream), es)
+            ret = self.conn.r_rdma(blocks, page_size * es, info.ptr, info.dev,
+                                   self._stream(info, cache, stream), es)
         else:
             raise Exception("Not connected to any instance")
         if ret < 0:
