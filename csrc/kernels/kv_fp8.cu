@@ -9,9 +9,10 @@
 // the "write fused with fp8 cast / read fused with gather" item of the north star.
 //
 // Pool block layout: [elems x e4m3][elems/128 x fp32 scale].
-// A warp owns one 128-element row per step (lane l: elements 4l..4l+3, one 8-byte load),
-// reduces |x| max with shuffles, and emits 4 bytes per lane (one coalesced 128-byte store
-// per row).  Four rows are in flight per warp to cover the NVLink / HBM latency.
+// A half-warp owns one 128-element row per step (lane l: elements 8l..8l+7, one 16-byte
+// load), reduces |x| max with shuffles inside the half, and emits 8 bytes per lane (one
+// coalesced 128-byte store per row).  Eight rows are in flight per warp to cover the
+// NVLink / HBM latency.
 // There is no direct bf16<->e4m3 cvt on sm_100a: quantise via f32, dequantise via f16x2.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -29,7 +30,6 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr uint32_t kRow = 128;                 // elements sharing a scale
-constexpr int kRowsInFlight = 4;
 constexpr uint32_t kChunkElems = 8192;         // CTA work item: 64 rows
 constexpr float kE4m3Max = 448.f;
 
@@ -61,10 +61,22 @@ __device__ __forceinline__ uint32_t f2_to_bf16x2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&b);
 }
 
+// A half-warp owns one 128-element row per step (lane l of the half: elements 8l..8l+7, one
+// 16-byte load), so a warp instruction covers two rows; kRowPairs such steps are in flight.
+constexpr int kRowPairs = 4;  // 8 rows = 2 KB of bf16 in flight per warp
+
+__device__ __forceinline__ uint4 ld_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
 // Threads [0, 256) quantise + store; warp 8 is the control warp (in-band commit).
 __global__ void __launch_bounds__(kThreads + 32)
     kv_write_fp8_kernel(const CopyDesc* __restrict__ descs, uint32_t n, uint32_t elems,
-                        uint32_t cpb, Publish pub) {
+                        uint32_t chunk, uint32_t cpb, Publish pub) {
     const uint32_t total = n * cpb;
     if (threadIdx.x >= kThreads) {
         if (!pub.recs) return;
@@ -73,35 +85,50 @@ __global__ void __launch_bounds__(kThreads + 32)
         return;
     }
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t half = lane >> 4, hl = lane & 15;
+    constexpr uint32_t kStep = 2 * kRowPairs;  // rows per warp iteration
     for (uint32_t item = blockIdx.x; item < total; item += gridDim.x) {
         const CopyDesc d = descs[item / cpb];
-        const uint32_t e0 = (item % cpb) * kChunkElems;
-        const uint32_t rows = (min(kChunkElems, elems - e0)) / kRow;
+        const uint32_t e0 = (item % cpb) * chunk;
+        const uint32_t rows = min(chunk, elems - e0) / kRow;
+        const uint32_t row0 = e0 / kRow;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(d.src);  // bf16 page
         uint8_t* q = reinterpret_cast<uint8_t*>(d.dst);                // e4m3 payload
         float* scales = reinterpret_cast<float*>(q + elems);
-        for (uint32_t r0 = warp * kRowsInFlight; r0 < rows; r0 += kWarps * kRowsInFlight) {
-            uint2 v[kRowsInFlight];
+        for (uint32_t r0 = warp * kStep; r0 < rows; r0 += kWarps * kStep) {
+            uint4 v[kRowPairs];
 #pragma unroll
-            for (int u = 0; u < kRowsInFlight; ++u) {
-                const uint32_t row = e0 / kRow + r0 + u;
-                if (r0 + u < rows) v[u] = ld_u2(src + (size_t(row) * kRow + lane * 4) * 2);
+            for (int u = 0; u < kRowPairs; ++u) {
+                const uint32_t r = r0 + 2 * u + half;
+                if (r < rows) v[u] = ld_u4(src + (size_t(row0 + r) * kRow + hl * 8) * 2);
             }
 #pragma unroll
-            for (int u = 0; u < kRowsInFlight; ++u) {
-                if (r0 + u >= rows) break;
-                const uint32_t row = e0 / kRow + r0 + u;
-                const float2 a = bf16x2_to_f2(v[u].x), b = bf16x2_to_f2(v[u].y);
-                float amax = fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y)));
+            for (int u = 0; u < kRowPairs; ++u) {
+                const uint32_t r = r0 + 2 * u + half;
+                const bool live = r < rows;
+                float2 f[4];
+                f[0] = bf16x2_to_f2(v[u].x);
+                f[1] = bf16x2_to_f2(v[u].y);
+                f[2] = bf16x2_to_f2(v[u].z);
+                f[3] = bf16x2_to_f2(v[u].w);
+                float amax = 0.f;
+                if (live) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
+                    for (int j = 0; j < 4; ++j) amax = fmaxf(amax, fmaxf(fabsf(f[j].x), fabsf(f[j].y)));
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1)  // reduce within the half-warp that owns the row
                     amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+                if (!live) continue;
                 const float scale = amax > 0.f ? amax * (1.f / kE4m3Max) : 1.f;
                 const float inv = 1.f / scale;
-                const uint32_t lo = cvt_e4m3x2(a.y * inv, a.x * inv);
-                const uint32_t hi = cvt_e4m3x2(b.y * inv, b.x * inv);
-                *reinterpret_cast<uint32_t*>(q + size_t(row) * kRow + lane * 4) = lo | (hi << 16);
-                if (lane == 0) scales[row] = scale;
+                uint2 out;
+                out.x = uint32_t(cvt_e4m3x2(f[0].y * inv, f[0].x * inv)) |
+                        (uint32_t(cvt_e4m3x2(f[1].y * inv, f[1].x * inv)) << 16);
+                out.y = uint32_t(cvt_e4m3x2(f[2].y * inv, f[2].x * inv)) |
+                        (uint32_t(cvt_e4m3x2(f[3].y * inv, f[3].x * inv)) << 16);
+                *reinterpret_cast<uint2*>(q + size_t(row0 + r) * kRow + hl * 8) = out;
+                if (hl == 0) scales[row0 + r] = scale;
             }
         }
     }
@@ -110,43 +137,51 @@ __global__ void __launch_bounds__(kThreads + 32)
 
 __global__ void __launch_bounds__(kThreads)
     kv_read_fp8_kernel(const CopyDesc* __restrict__ descs, uint32_t n, uint32_t elems,
-                       uint32_t cpb, uint32_t* status) {
+                       uint32_t chunk, uint32_t cpb, uint32_t* status) {
     const uint32_t total = n * cpb;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t half = lane >> 4, hl = lane & 15;
+    constexpr uint32_t kStep = 2 * kRowPairs;
     for (uint32_t item = blockIdx.x; item < total; item += gridDim.x) {
         const CopyDesc d = descs[item / cpb];
         if (d.src == 0) {
             if (threadIdx.x == 0 && item % cpb == 0 && status) atomicAdd(status + kStatMiss, 1u);
             continue;
         }
-        const uint32_t e0 = (item % cpb) * kChunkElems;
-        const uint32_t rows = (min(kChunkElems, elems - e0)) / kRow;
+        const uint32_t e0 = (item % cpb) * chunk;
+        const uint32_t rows = min(chunk, elems - e0) / kRow;
+        const uint32_t row0 = e0 / kRow;
         const uint8_t* q = reinterpret_cast<const uint8_t*>(d.src);
         const float* scales = reinterpret_cast<const float*>(q + elems);
         uint8_t* dst = reinterpret_cast<uint8_t*>(d.dst);
-        for (uint32_t r0 = warp * kRowsInFlight; r0 < rows; r0 += kWarps * kRowsInFlight) {
-            uint32_t v[kRowsInFlight];
-            float sc[kRowsInFlight];
+        for (uint32_t r0 = warp * kStep; r0 < rows; r0 += kWarps * kStep) {
+            uint2 v[kRowPairs];
+            float sc[kRowPairs];
 #pragma unroll
-            for (int u = 0; u < kRowsInFlight; ++u) {
-                const uint32_t row = e0 / kRow + r0 + u;
-                if (r0 + u < rows) {
-                    v[u] = ld_u1(q + size_t(row) * kRow + lane * 4);
-                    sc[u] = __uint_as_float(ld_u1(scales + row));
+            for (int u = 0; u < kRowPairs; ++u) {
+                const uint32_t r = r0 + 2 * u + half;
+                if (r < rows) {
+                    v[u] = ld_u2(q + size_t(row0 + r) * kRow + hl * 8);
+                    sc[u] = __uint_as_float(ld_u1(scales + row0 + r));
                 }
             }
 #pragma unroll
-            for (int u = 0; u < kRowsInFlight; ++u) {
-                if (r0 + u >= rows) break;
-                const uint32_t row = e0 / kRow + r0 + u;
-                const uint32_t h01 = cvt_f16x2_e4m3x2(uint16_t(v[u] & 0xffffu));
-                const uint32_t h23 = cvt_f16x2_e4m3x2(uint16_t(v[u] >> 16));
-                const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
-                const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
-                uint2 out;
-                out.x = f2_to_bf16x2(f01.x * sc[u], f01.y * sc[u]);
-                out.y = f2_to_bf16x2(f23.x * sc[u], f23.y * sc[u]);
-                *reinterpret_cast<uint2*>(dst + (size_t(row) * kRow + lane * 4) * 2) = out;
+            for (int u = 0; u < kRowPairs; ++u) {
+                const uint32_t r = r0 + 2 * u + half;
+                if (r >= rows) continue;
+                const uint32_t w[2] = {v[u].x, v[u].y};
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t h01 = cvt_f16x2_e4m3x2(uint16_t(w[j] & 0xffffu));
+                    const uint32_t h23 = cvt_f16x2_e4m3x2(uint16_t(w[j] >> 16));
+                    const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+                    const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+                    o[2 * j] = f2_to_bf16x2(f01.x * sc[u], f01.y * sc[u]);
+                    o[2 * j + 1] = f2_to_bf16x2(f23.x * sc[u], f23.y * sc[u]);
+                }
+                *reinterpret_cast<uint4*>(dst + (size_t(row0 + r) * kRow + hl * 8) * 2) =
+                    make_uint4(o[0], o[1], o[2], o[3]);
             }
         }
     }
@@ -159,22 +194,27 @@ cudaError_t launch_kv_write_fp8(const Fp8Launch& a, cudaStream_t stream) {
     if (a.group != kRow || a.elems % kRow != 0) return cudaErrorInvalidValue;
     Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n, nullptr, !a.all_local};
     if (!a.table || !a.done) pub.recs = nullptr;
-    const uint32_t cpb = (a.elems + kChunkElems - 1) / kChunkElems;
+    // whole pages per CTA when there are enough of them (single-CTA commit, see kv_copy.cu)
+    uint32_t chunk = kChunkElems;
+    if (a.n >= uint32_t(sm_count()) && a.elems <= (1u << 19)) chunk = a.elems;
+    const uint32_t cpb = (a.elems + chunk - 1) / chunk;
     const uint64_t total = uint64_t(a.n) * cpb;
-    int ctas = a.max_ctas > 0 ? a.max_ctas : 7 * sm_count();
+    int ctas = a.max_ctas > 0 ? a.max_ctas : 6 * sm_count();
     ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
-    kv_write_fp8_kernel<<<ctas, kThreads + 32, 0, stream>>>(a.descs, a.n, a.elems, cpb, pub);
+    kv_write_fp8_kernel<<<ctas, kThreads + 32, 0, stream>>>(a.descs, a.n, a.elems, chunk, cpb, pub);
     return cudaGetLastError();
 }
 
 cudaError_t launch_kv_read_fp8(const Fp8Launch& a, cudaStream_t stream) {
     if (a.n == 0 || a.elems == 0) return cudaSuccess;
     if (a.group != kRow || a.elems % kRow != 0) return cudaErrorInvalidValue;
-    const uint32_t cpb = (a.elems + kChunkElems - 1) / kChunkElems;
+    uint32_t chunk = kChunkElems;
+    if (a.n >= uint32_t(sm_count()) && a.elems <= (1u << 19)) chunk = a.elems;
+    const uint32_t cpb = (a.elems + chunk - 1) / chunk;
     const uint64_t total = uint64_t(a.n) * cpb;
-    int ctas = a.max_ctas > 0 ? a.max_ctas : 8 * sm_count();
+    int ctas = a.max_ctas > 0 ? a.max_ctas : 6 * sm_count();
     ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
-    kv_read_fp8_kernel<<<ctas, kThreads, 0, stream>>>(a.descs, a.n, a.elems, cpb, a.status);
+    kv_read_fp8_kernel<<<ctas, kThreads, 0, stream>>>(a.descs, a.n, a.elems, chunk, cpb, a.status);
     return cudaGetLastError();
 }
 
