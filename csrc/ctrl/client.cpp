@@ -456,8 +456,15 @@ int Connection::refresh_pool_map() {
     return 0;
 }
 
+// The kernels resolve at most kMaxSegs segment bases; a pool that auto-increased beyond that
+// is served through the control plane (authoritative anyway).
+bool Connection::device_index_usable() {
+    if (segs_.empty() || !segs_[0].index_slots) return false;
+    return segs_.size() <= size_t(kernels::LookupLaunch::kMaxSegs);
+}
+
 int Connection::check_exist(const std::string& key) {
-    if (device_lookup_ && server_hbm_) {
+    if (device_lookup_ && server_hbm_ && device_index_usable()) {
         const int r = match_via_device_index({std::string_view(key)}, true);
         if (r >= -1) return r == 0 ? 0 : 1;
     }
@@ -473,7 +480,7 @@ int Connection::check_exist(const std::string& key) {
 
 int Connection::get_match_last_index(const std::vector<std::string_view>& keys) {
     if (keys.empty()) return -1;
-    if (device_lookup_ && server_hbm_) {
+    if (device_lookup_ && server_hbm_ && device_index_usable()) {
         const int r = match_via_device_index(keys, false);
         if (r >= -1) return r;
     }
@@ -941,7 +948,7 @@ int Connection::r_rdma_fp8(const std::vector<KeyOffset>& blocks, int elems, uint
         return -1;
     }
     const int bytes = int(kernels::fp8_block_bytes(uint32_t(elems), 128));
-    if (device_lookup_ && server_hbm_)
+    if (device_lookup_ && server_hbm_ && device_index_usable())
         return read_via_device_index(blocks, bytes, base_ptr, device, stream, elems);
     std::vector<RemoteBlock> rb;
     const int r = lookup_blocks(kOpReadLookup, blocks, bytes, rb);
@@ -955,7 +962,7 @@ int Connection::r_rdma_fp8(const std::vector<KeyOffset>& blocks, int elems, uint
 int Connection::r_rdma(const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr,
                        int device, uint64_t stream) {
     if (blocks.empty()) return 0;
-    if (device_lookup_ && server_hbm_ && device >= 0)
+    if (device_lookup_ && server_hbm_ && device >= 0 && device_index_usable())
         return read_via_device_index(blocks, block_size, base_ptr, device, stream);
     std::vector<RemoteBlock> rb;
     const int r = lookup_blocks(kOpReadLookup, blocks, block_size, rb);
@@ -970,7 +977,7 @@ int Connection::rw_local(char op, const std::vector<KeyOffset>& blocks, int bloc
                          uint64_t base_ptr, int device, uint64_t stream) {
     if (blocks.empty()) return 0;
     if (op != kOpLocalRead && op != kOpLocalWrite) return -1;
-    if (op == kOpLocalRead && device_lookup_ && server_hbm_ && device >= 0)
+    if (op == kOpLocalRead && device_lookup_ && server_hbm_ && device >= 0 && device_index_usable())
         return read_via_device_index(blocks, block_size, base_ptr, device, stream);
     std::vector<RemoteBlock> rb;
     const int r = lookup_blocks(op, blocks, block_size, rb);

@@ -159,6 +159,7 @@ class Connection {
     int match_via_device_index(const std::vector<std::string_view>& keys, bool exist_only);
     int ensure_host_registered(uint64_t ptr, size_t bytes, int device);
     int drain_devices();
+    bool device_index_usable();
     void fail(const std::string& msg);
 
     // completion thread

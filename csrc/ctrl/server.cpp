@@ -72,8 +72,13 @@ bool Server::add_segment(std::string* err) {
         device = cfg_.pool_devices.empty()
                      ? 0
                      : cfg_.pool_devices[next_pool_dev_++ % cfg_.pool_devices.size()];
-        size_t slots = cfg_.index_slots ? next_pow2(cfg_.index_slots)
-                                        : next_pow2(std::max<size_t>(1024, 2 * (bytes / granule)));
+        // 2 slots per block keeps linear probing short; the table (segment 0 only) must also
+        // cover the blocks of segments added later by --auto-increase
+        const size_t growth = cfg_.auto_increase ? 8 : 1;
+        size_t slots = cfg_.index_slots
+                           ? next_pow2(cfg_.index_slots)
+                           : next_pow2(std::max<size_t>(1024, 2 * growth * (bytes / granule)));
+        if (id != 0) slots = 0;
         seg = fabric::SegmentOwner::create_device(id, device, bytes, granule, slots, err);
     } else {
         seg = fabric::SegmentOwner::create_host(id, bytes, granule, port_, err);
