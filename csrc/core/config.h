@@ -27,6 +27,8 @@ struct ServerConfig {
     size_t extend_size = 10;               // GB added per auto-increase step
     size_t prealloc_bytes = 0;             // if non-zero overrides prealloc_size (tests)
     size_t index_slots = 0;                // device-index entries per segment (0 = auto)
+    size_t replica_bytes = 0;              // NVLS-replicated region per GPU (0 = none)
+    std::vector<int> replica_devices;      // GPUs holding a replica (default: all visible)
 };
 
 struct ClientConfig {

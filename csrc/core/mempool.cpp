@@ -136,12 +136,22 @@ bool MM::allocate(size_t size, size_t n, int device_hint, std::vector<Allocation
     const size_t mark_at = out.size();
     size_t remaining = n;
     // pools on the hinted device first, then the rest in creation order
+    // The NVLS-replicated region (device -2) is a separate address space: it serves exactly
+    // the requests that ask for it and is never used as overflow for ordinary blocks.
+    constexpr int kReplica = -2;
     std::vector<size_t> order;
     order.reserve(pools_.size());
-    for (size_t p = 0; p < pools_.size(); ++p)
-        if (device_hint >= 0 && pools_[p]->device() == device_hint) order.push_back(p);
-    for (size_t p = 0; p < pools_.size(); ++p)
-        if (!(device_hint >= 0 && pools_[p]->device() == device_hint)) order.push_back(p);
+    if (device_hint == kReplica) {
+        for (size_t p = 0; p < pools_.size(); ++p)
+            if (pools_[p]->device() == kReplica) order.push_back(p);
+    } else {
+        for (size_t p = 0; p < pools_.size(); ++p)
+            if (device_hint >= 0 && pools_[p]->device() == device_hint) order.push_back(p);
+        for (size_t p = 0; p < pools_.size(); ++p)
+            if (!(device_hint >= 0 && pools_[p]->device() == device_hint) &&
+                pools_[p]->device() != kReplica)
+                order.push_back(p);
+    }
 
     std::vector<uint64_t> offs;
     for (size_t p : order) {
@@ -174,7 +184,9 @@ bool MM::deallocate(uint32_t seg, uint64_t offset, size_t size) {
 }
 
 bool MM::need_extend() const {
-    return !pools_.empty() && pools_.back()->usage() > kExtendUsageRatio;
+    for (size_t p = pools_.size(); p > 0; --p)  // last ordinary pool
+        if (pools_[p - 1]->device() != -2) return pools_[p - 1]->usage() > kExtendUsageRatio;
+    return false;
 }
 
 size_t MM::used_bytes() const {

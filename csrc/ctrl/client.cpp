@@ -144,6 +144,7 @@ struct Connection::DevCtx {
     std::vector<std::shared_ptr<fabric::Mapping>> maps;  // by segment id
     std::vector<uint8_t*> seg_ptr;  // maps[i]->dev_ptr, cached for the per-block hot loop
     std::vector<uint8_t> seg_remote;  // 1 when the segment is not in this device's own HBM
+    std::vector<uint8_t*> seg_mc;     // NVLS replica segments: multicast base (writes)
     uint8_t* ring_h = nullptr;  // pinned + mapped: descriptors, publish records, key bytes
     uint8_t* ring_d = nullptr;
     size_t ring_head = 0;
@@ -546,7 +547,7 @@ int Connection::flush_commits() {
 }
 
 int Connection::allocate(const std::vector<std::string_view>& keys, int block_size,
-                         std::vector<RemoteBlock>& out) {
+                         std::vector<RemoteBlock>& out, int hint) {
     out.clear();
     if (keys.empty() || block_size <= 0) return -1;
     const std::vector<std::string_view>& kv = keys;
@@ -556,7 +557,8 @@ int Connection::allocate(const std::vector<std::string_view>& keys, int block_si
         return -1;
     }
     fb::Builder b(buf.data(), buf.size());
-    encode_remote_meta(b, kv, block_size, 0, nullptr, 0, kOpAllocate, cfg_.pool_hint);
+    encode_remote_meta(b, kv, block_size, 0, nullptr, 0, kOpAllocate,
+                       hint == kHintDefault ? cfg_.pool_hint : hint);
     int32_t code = 0;
     std::vector<uint8_t> p;
     if (transact(kOpAllocate, b.data(), b.size(), &code, &p, kBlobPayload) != 0) return -1;
@@ -719,7 +721,7 @@ int Connection::register_mr(uint64_t ptr, size_t size, int device) {
 uint8_t* Connection::seg_dev_ptr(DevCtx* ctx, uint32_t seg) {
     if (seg < ctx->seg_ptr.size() && ctx->seg_ptr[seg]) return ctx->seg_ptr[seg];
     auto mp = mapping(seg, ctx->device);
-    if (!mp || !mp->dev_ptr) {
+    if (!mp || (!mp->dev_ptr && !mp->mc_ptr)) {
         fail("pool segment " + std::to_string(seg) + " is not addressable from device " +
              std::to_string(ctx->device));
         return nullptr;
@@ -727,8 +729,10 @@ uint8_t* Connection::seg_dev_ptr(DevCtx* ctx, uint32_t seg) {
     if (ctx->seg_ptr.size() <= seg) {
         ctx->seg_ptr.resize(seg + 1, nullptr);
         ctx->seg_remote.resize(seg + 1, 1);
+        ctx->seg_mc.resize(seg + 1, nullptr);
     }
     ctx->seg_ptr[seg] = mp->dev_ptr;
+    ctx->seg_mc[seg] = mp->mc_ptr;
     // NVLink (or PCIe) on the path?  Such transfers are link-bound: a small grid saturates
     // them and leaves the SMs to whatever else runs on this GPU.
     cudaPointerAttributes attr{};
@@ -833,6 +837,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             recs = reinterpret_cast<kernels::IndexEntry*>(ctx->ring_h + at_rec);
         }
         uint32_t m = 0;
+        uint32_t n_mc = 0;  // blocks of this batch that live in the NVLS-replicated region
         bool can_publish = table != nullptr;
         bool all_remote = true;
         bool all_local = !ctx->seg_remote.empty() && !ctx->seg_remote[0];  // index table (segment 0)
@@ -846,8 +851,15 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             uint8_t* segbase = seg < nseg ? seg_ptr[seg] : nullptr;
             if (!segbase) {
                 segbase = seg_dev_ptr(ctx, seg);
-                if (!segbase) return -1;
+                if (!segbase && !(seg < ctx->seg_mc.size() && ctx->seg_mc[seg])) return -1;
                 seg_ptr = ctx->seg_ptr.data();
+            }
+            if (write && seg < ctx->seg_mc.size() && ctx->seg_mc[seg]) {
+                segbase = ctx->seg_mc[seg];  // replicated block: write through the multicast VA
+                ++n_mc;
+            } else if (!segbase) {
+                fail("no local replica of the NVLS region on device " + std::to_string(kd));
+                return -1;
             }
             const uint64_t pool = reinterpret_cast<uint64_t>(segbase) + addr_off(rb.remote_addr);
             const uint64_t local = base_ptr + local_off[i] * scale;
@@ -870,7 +882,12 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             ++m;
         }
         if (m == 0) break;
+        if (n_mc && n_mc != m) {
+            fail("a write batch must not mix replicated and ordinary blocks");
+            return -1;
+        }
         kernels::CopyLaunch L;
+        L.multicast = n_mc != 0;
         L.descs = reinterpret_cast<const kernels::CopyDesc*>(ctx->ring_d + at_desc);
         L.descs_host = descs;
         L.n = m;
@@ -879,7 +896,11 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
         L.status = ctx->status_d;
         L.variant = copy_variant_;
         L.max_ctas = max_ctas_ ? max_ctas_ : (all_remote ? 2 * kernels::sm_count() : 0);
-        L.all_local = all_local;
+        L.all_local = all_local && !L.multicast;
+        if (L.multicast && fp8_elems) {
+            fail("the fp8 path does not write to the replicated region");
+            return -1;
+        }
         if (can_publish) {
             L.recs = reinterpret_cast<const kernels::IndexEntry*>(ctx->ring_d + at_rec);
             L.table = table;

@@ -94,8 +94,11 @@ class Connection {
     // --- data plane.  `device` is the CUDA ordinal owning base_ptr, -1 for host memory;
     //     `stream` is a cudaStream_t to order after (0 = the connection's own stream).
     int register_mr(uint64_t ptr, size_t size, int device);
+    // hint: pool device to prefer, kReplicaDevice (-2) for the NVLS-replicated region,
+    // kHintDefault for the connection's configured pool_hint
+    static constexpr int kHintDefault = -1000;
     int allocate(const std::vector<std::string_view>& keys, int block_size,
-                 std::vector<RemoteBlock>& out);
+                 std::vector<RemoteBlock>& out, int hint = kHintDefault);
     // offsets[i] * scale = byte offset of block i (scale lets callers pass element offsets)
     int w_rdma(const uint64_t* offsets, size_t noffsets, uint64_t scale, int block_size,
                const RemoteBlock* blocks, size_t nblocks, uint64_t base_ptr, int device,

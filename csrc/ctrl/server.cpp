@@ -166,6 +166,26 @@ int Server::start(std::string* err) {
         }
     }
 
+    if (use_hbm_ && cfg_.replica_bytes) {
+        // NVLS-replicated region for one-writer / many-reader blocks (shared prompt prefixes)
+        std::lock_guard<std::mutex> lk(mu_);
+        std::vector<int> devs = cfg_.replica_devices;
+        if (devs.empty())
+            for (int d = 0; d < fabric::cuda_device_count(); ++d) devs.push_back(d);
+        const uint32_t granule = uint32_t(cfg_.minimal_allocate_size) * 1024u;
+        std::string rerr;
+        auto seg = fabric::SegmentOwner::create_replica(uint32_t(segs_.size()), devs,
+                                                        cfg_.replica_bytes, granule, port_, &rerr);
+        if (seg) {
+            mm_.add_pool(seg->info().bytes, granule, kReplicaDevice);
+            LOG_INFO("NVLS replica segment %zu: %.2f GiB on %zu GPUs", segs_.size(),
+                     double(seg->info().bytes) / double(1ull << 30), devs.size());
+            segs_.push_back(std::move(seg));
+        } else {
+            LOG_WARN("no NVLS-replicated region: %s", rerr.c_str());
+        }
+    }
+
     epoll_fd_ = epoll_create1(EPOLL_CLOEXEC);
     wake_fd_ = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);
     epoll_event ev{};

@@ -38,6 +38,10 @@ struct Driver {
     CUresult (*MulticastUnbind)(CUmemGenericAllocationHandle, CUdevice, size_t, size_t) = nullptr;
     CUresult (*MulticastGetGranularity)(size_t*, const CUmulticastObjectProp*,
                                         CUmulticastGranularity_flags) = nullptr;
+    CUresult (*MemExportToShareableHandle)(void*, CUmemGenericAllocationHandle,
+                                           CUmemAllocationHandleType, unsigned long long) = nullptr;
+    CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle*, void*,
+                                             CUmemAllocationHandleType) = nullptr;
 };
 
 template <typename F>
@@ -73,7 +77,9 @@ const Driver& driver() {
                   resolve("cuMemAddressFree", r.MemAddressFree, r.why) &&
                   resolve("cuMemMap", r.MemMap, r.why) && resolve("cuMemUnmap", r.MemUnmap, r.why) &&
                   resolve("cuMemSetAccess", r.MemSetAccess, r.why) &&
-                  resolve("cuMemGetAllocationGranularity", r.MemGetAllocationGranularity, r.why);
+                  resolve("cuMemGetAllocationGranularity", r.MemGetAllocationGranularity, r.why) &&
+                  resolve("cuMemExportToShareableHandle", r.MemExportToShareableHandle, r.why) &&
+                  resolve("cuMemImportFromShareableHandle", r.MemImportFromShareableHandle, r.why);
         if (ok) {
             // multicast entry points are optional (absent before driver 535)
             std::string w;
@@ -158,7 +164,7 @@ std::shared_ptr<NvlsGroup> NvlsGroup::create(const std::vector<int>& devices, si
 
     CUmulticastObjectProp mprop{};
     mprop.numDevices = unsigned(devices.size());
-    mprop.handleTypes = 0;
+    mprop.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;  // shareable with clients
     size_t gran = 0;
     mprop.size = bytes;
     if (d.MulticastGetGranularity(&gran, &mprop, CU_MULTICAST_GRANULARITY_RECOMMENDED) !=
@@ -197,6 +203,7 @@ std::shared_ptr<NvlsGroup> NvlsGroup::create(const std::vector<int>& devices, si
         prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
         prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
         prop.location.id = devices[i];
+        prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
         CUmemGenericAllocationHandle mem = 0;
         if ((r = d.MemCreate(&mem, size, &prop, 0)) != CUDA_SUCCESS) {
             if (prev >= 0) cudaSetDevice(prev);
@@ -228,6 +235,81 @@ std::shared_ptr<NvlsGroup> NvlsGroup::create(const std::vector<int>& devices, si
     if (prev >= 0) cudaSetDevice(prev);
     LOG_INFO("NVLS group over %zu GPUs, %zu MiB replica each", devices.size(), size >> 20);
     return g;
+}
+
+int NvlsGroup::index_of_device(int device) const {
+    for (size_t i = 0; i < devs_.size(); ++i)
+        if (devs_[i] == device) return int(i);
+    return -1;
+}
+
+static int export_fd(uint64_t handle) {
+    const Driver& d = driver();
+    if (!d.ok || !handle) return -1;
+    int fd = -1;
+    if (d.MemExportToShareableHandle(&fd, CUmemGenericAllocationHandle(handle),
+                                     CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS)
+        return -1;
+    return fd;
+}
+
+int NvlsGroup::export_mc_fd() const { return export_fd(mc_handle_); }
+
+int NvlsGroup::export_mem_fd(size_t i) const {
+    return i < mem_handles_.size() ? export_fd(mem_handles_[i]) : -1;
+}
+
+std::shared_ptr<NvlsImport> NvlsImport::import(int mc_fd, int mem_fd, size_t bytes, int device,
+                                               std::string* err) {
+    auto fail = [&](const std::string& m) -> std::shared_ptr<NvlsImport> {
+        if (err) *err = m;
+        return nullptr;
+    };
+    const Driver& d = driver();
+    if (!d.ok) return fail(d.why);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    cudaFree(nullptr);
+    std::shared_ptr<NvlsImport> im(new NvlsImport());
+    im->bytes_ = bytes;
+    CUmemAccessDesc access{};
+    access.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    access.location.id = device;
+    access.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    CUresult r;
+    auto map_fd = [&](int fd, uint64_t* handle_out, uint64_t* va_out) -> bool {
+        CUmemGenericAllocationHandle h = 0;
+        if ((r = d.MemImportFromShareableHandle(&h, reinterpret_cast<void*>(uintptr_t(fd)),
+                                                CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR)) !=
+            CUDA_SUCCESS)
+            return false;
+        *handle_out = h;
+        CUdeviceptr va = 0;
+        if ((r = d.MemAddressReserve(&va, bytes, 2u << 20, 0, 0)) != CUDA_SUCCESS ||
+            (r = d.MemMap(va, bytes, 0, h, 0)) != CUDA_SUCCESS ||
+            (r = d.MemSetAccess(va, bytes, &access, 1)) != CUDA_SUCCESS)
+            return false;
+        *va_out = uint64_t(va);
+        return true;
+    };
+    bool ok = map_fd(mc_fd, &im->mc_handle_, &im->mc_va_);
+    if (ok && mem_fd >= 0) ok = map_fd(mem_fd, &im->mem_handle_, &im->uc_va_);
+    if (prev >= 0) cudaSetDevice(prev);
+    if (!ok) return fail("importing the multicast group: " + cu_err(d, r));
+    return im;
+}
+
+NvlsImport::~NvlsImport() {
+    const Driver& d = driver();
+    if (!d.ok) return;
+    for (uint64_t va : {mc_va_, uc_va_}) {
+        if (!va) continue;
+        d.MemUnmap(CUdeviceptr(va), bytes_);
+        d.MemAddressFree(CUdeviceptr(va), bytes_);
+    }
+    if (mem_handle_) d.MemRelease(CUmemGenericAllocationHandle(mem_handle_));
+    if (mc_handle_) d.MemRelease(CUmemGenericAllocationHandle(mc_handle_));
 }
 
 NvlsGroup::~NvlsGroup() {

@@ -33,6 +33,12 @@ class NvlsGroup {
     // or a single-process test).  `bytes` is rounded up to the multicast granularity.
     static std::shared_ptr<NvlsGroup> create(const std::vector<int>& devices, size_t bytes,
                                              std::string* err);
+    // POSIX file descriptors of the multicast object / of replica i, to be passed to another
+    // process over a unix socket (fabric/fdpass.h).  The caller closes them.  -1 on failure.
+    int export_mc_fd() const;
+    int export_mem_fd(size_t i) const;
+    const std::vector<int>& devices() const { return devs_; }
+    int index_of_device(int device) const;
     uint64_t mc_ptr(size_t i) const { return i < devs_.size() ? mc_va_ : 0; }
     uint64_t uc_ptr(size_t i) const { return i < uc_va_.size() ? uc_va_[i] : 0; }
     size_t bytes() const { return bytes_; }
@@ -47,6 +53,24 @@ class NvlsGroup {
     std::vector<uint64_t> mem_handles_;
     std::vector<uint64_t> uc_va_;
     bool mc_mapped_ = false;
+};
+
+// A client process' view of a group owned by another process: the multicast object mapped
+// for writing and (optionally) the replica of the client's own GPU mapped for reading.
+class NvlsImport {
+   public:
+    ~NvlsImport();
+    static std::shared_ptr<NvlsImport> import(int mc_fd, int mem_fd, size_t bytes, int device,
+                                              std::string* err);
+    uint64_t mc_ptr() const { return mc_va_; }
+    uint64_t uc_ptr() const { return uc_va_; }
+    size_t bytes() const { return bytes_; }
+
+   private:
+    NvlsImport() = default;
+    size_t bytes_ = 0;
+    uint64_t mc_handle_ = 0, mem_handle_ = 0;
+    uint64_t mc_va_ = 0, uc_va_ = 0;
 };
 
 }  // namespace istore::fabric

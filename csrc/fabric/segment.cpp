@@ -184,6 +184,47 @@ std::unique_ptr<SegmentOwner> SegmentOwner::create_device(uint32_t id, int devic
     return s;
 }
 
+std::unique_ptr<SegmentOwner> SegmentOwner::create_replica(uint32_t id,
+                                                           const std::vector<int>& devices,
+                                                           size_t bytes, uint32_t granule, int port,
+                                                           std::string* err) {
+    std::unique_ptr<SegmentOwner> s(new SegmentOwner());
+    s->group_ = NvlsGroup::create(devices, bytes, err);
+    if (!s->group_) return nullptr;
+    char name[64];
+    std::snprintf(name, sizeof(name), "istore_b200_nvls_%d_%d_%u", int(getpid()), port, id);
+    s->fd_server_ = std::make_unique<FdServer>();
+    std::shared_ptr<NvlsGroup> group = s->group_;
+    auto provider = [group](int device, std::vector<int>* fds, uint64_t* payload) {
+        const int mc = group->export_mc_fd();
+        if (mc < 0) return false;
+        fds->push_back(mc);
+        const int idx = group->index_of_device(device);
+        if (idx >= 0) {
+            const int mem = group->export_mem_fd(size_t(idx));
+            if (mem >= 0) fds->push_back(mem);
+        }
+        *payload = group->bytes();
+        return true;
+    };
+    if (!s->fd_server_->start(name, provider, err)) return nullptr;
+    SegmentInfo& i = s->info_;
+    i.id = id;
+    i.kind = kSegReplica;
+    i.device = kReplicaDevice;
+    i.granule = granule;
+    i.bytes = s->group_->bytes() / granule * granule;
+    i.index_off = 0;
+    i.index_slots = 0;
+    i.map_bytes = s->group_->bytes();
+    std::memset(i.handle, 0, sizeof(i.handle));
+    std::memcpy(i.handle, name, std::strlen(name));
+    std::memcpy(i.owner, process_uuid(), 16);
+    i.owner_ptr = reinterpret_cast<uint64_t>(s->group_.get());
+    s->base_ = reinterpret_cast<void*>(s->group_->mc_ptr(0));
+    return s;
+}
+
 void SegmentOwner::clear_index() {
     if (info_.kind != kSegDeviceIpc || !info_.index_slots) return;
     DeviceGuard g(info_.device);
@@ -194,6 +235,11 @@ void SegmentOwner::clear_index() {
 }
 
 SegmentOwner::~SegmentOwner() {
+    if (info_.kind == kSegReplica) {
+        fd_server_.reset();
+        group_.reset();
+        return;
+    }
     if (!base_) return;
     if (info_.kind == kSegHostShm) {
         munmap(base_, info_.map_bytes);
@@ -295,6 +341,34 @@ std::shared_ptr<Mapping> map_segment(const SegmentInfo& info, int device, std::s
                     m->dev_ptr = static_cast<uint8_t*>(dp);
                 (void)cudaGetLastError();
             }
+        }
+    } else if (info.kind == kSegReplica) {
+        if (device < 0) {
+            if (err) *err = "the NVLS-replicated region needs a CUDA device on the client";
+            return nullptr;
+        }
+        if (same_process) {
+            auto* group = reinterpret_cast<NvlsGroup*>(info.owner_ptr);
+            const int idx = group->index_of_device(device);
+            m->mc_ptr = reinterpret_cast<uint8_t*>(group->mc_ptr(0));
+            m->dev_ptr = reinterpret_cast<uint8_t*>(group->uc_ptr(idx >= 0 ? size_t(idx) : 0));
+        } else {
+            char name[65];
+            std::memcpy(name, info.handle, 64);
+            name[64] = 0;
+            std::vector<int> fds;
+            uint64_t bytes = 0;
+            if (!fd_request(name, device, &fds, &bytes, err)) return nullptr;
+            if (fds.empty()) {
+                if (err) *err = "the server exported no multicast handle";
+                return nullptr;
+            }
+            m->nvls = NvlsImport::import(fds[0], fds.size() > 1 ? fds[1] : -1, size_t(bytes), device,
+                                         err);
+            for (int fd : fds) close(fd);
+            if (!m->nvls) return nullptr;
+            m->mc_ptr = reinterpret_cast<uint8_t*>(m->nvls->mc_ptr());
+            m->dev_ptr = reinterpret_cast<uint8_t*>(m->nvls->uc_ptr());  // null: no local replica
         }
     } else {
         if (device < 0) {

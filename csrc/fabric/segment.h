@@ -18,6 +18,8 @@
 #include <vector>
 
 #include "../wire/protocol.h"
+#include "fdpass.h"
+#include "nvls.h"
 
 namespace istore::fabric {
 
@@ -41,6 +43,11 @@ class SegmentOwner {
     static std::unique_ptr<SegmentOwner> create_device(uint32_t id, int device, size_t bytes,
                                                        uint32_t granule, size_t index_slots,
                                                        std::string* err);
+    // NVLS-replicated region over `devices` (needs multicast support); the VMM handles are
+    // handed to client processes through a unix socket named after `port`.
+    static std::unique_ptr<SegmentOwner> create_replica(uint32_t id, const std::vector<int>& devices,
+                                                        size_t bytes, uint32_t granule, int port,
+                                                        std::string* err);
     const SegmentInfo& info() const { return info_; }
     void* base() const { return base_; }
     // Zero the device index (purge).  No-op for host segments.
@@ -52,6 +59,8 @@ class SegmentOwner {
     void* base_ = nullptr;
     int shm_fd_ = -1;
     std::string shm_name_;
+    std::shared_ptr<NvlsGroup> group_;
+    std::unique_ptr<FdServer> fd_server_;
 };
 
 // ---------------------------------------------------------------- client side
@@ -61,8 +70,10 @@ struct Mapping {
     int device = -1;
     uint8_t* host_ptr = nullptr;  // CPU-addressable base (host segments only)
     uint8_t* dev_ptr = nullptr;   // GPU-addressable base for kernels / cudaMemcpy on `device`
+    uint8_t* mc_ptr = nullptr;    // replica segments: multicast address (writes go here)
     bool ipc_opened = false;
     bool host_registered = false;
+    std::shared_ptr<NvlsImport> nvls;  // replica segment of another process
     ~Mapping();
 };
 

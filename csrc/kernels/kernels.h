@@ -66,6 +66,7 @@ struct CopyLaunch {
     unsigned long long* trace = nullptr;  // optional per-CTA %globaltimer stamps (bench only)
     bool all_local = false;  // every destination and the index table are in this GPU's own HBM
     uint32_t debug = 0;      // bench only, see publish.cuh
+    bool multicast = false;  // every dst is an NVLS multicast address: store with multimem.st
 };
 cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream);
 

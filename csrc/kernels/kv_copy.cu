@@ -49,7 +49,7 @@ struct DescParam {
 
 // VEC = 16 / 32: vector width; VEC = 1: byte fallback for unaligned tensors.
 // Threads [0, 256) copy; warp 8 is the control warp (in-band commit, publish.cuh).
-template <int VEC, bool PARAM>
+template <int VEC, bool PARAM, bool MC = false>
 __global__ void __launch_bounds__(kLdStThreads + 32)
     kv_copy_ldst_kernel(const CopyDesc* __restrict__ descs,
                         const __grid_constant__ DescParam<PARAM ? kParamDescs : 1> pd, uint32_t n,
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kLdStThreads + 32)
         if constexpr (VEC == 1) {
             for (uint32_t b = threadIdx.x; b < len; b += kLdStThreads) dst[b] = src[b];
         } else {
-            copy_span<VEC>(dst, src, len);
+            copy_span<VEC, MC>(dst, src, len);
         }
     }
     if (pub.recs) ctrl_barrier_arrive(kLdStThreads + 32);
@@ -219,6 +219,10 @@ cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream) {
     // local address into align_or; pool blocks are granule aligned).
     const bool aligned16 = (a.bytes % 16) == 0 && (a.align_or & 15) == 0;
     const bool aligned32 = (a.bytes % 32) == 0 && (a.align_or & 31) == 0;
+    if (a.multicast) {
+        if (!aligned16) return cudaErrorInvalidValue;  // multimem.st moves 16-byte vectors
+        variant = kCopyLdSt;
+    }
     if (variant == kCopyAuto) variant = aligned32 ? kCopyLdSt256 : kCopyLdSt;
     if (!aligned16 && (variant == kCopyTma || variant == kCopyLdSt256)) variant = kCopyLdSt;
     if (variant == kCopyLdSt256 && !aligned32) variant = kCopyLdSt;
@@ -277,7 +281,11 @@ cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream) {
     const int per_sm = (variant == kCopyLdSt256) ? resident32 : resident16;
     int ctas = a.max_ctas > 0 ? a.max_ctas : per_sm * sms;
     ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
-    if (!aligned16)
+    if (a.multicast && param)
+        kv_copy_ldst_kernel<16, true, true><<<ctas, T, 0, stream>>>(a.descs, pd, a.n, a.bytes, chunk, cpb, pub);
+    else if (a.multicast)
+        kv_copy_ldst_kernel<16, false, true><<<ctas, T, 0, stream>>>(a.descs, none, a.n, a.bytes, chunk, cpb, pub);
+    else if (!aligned16)
         kv_copy_ldst_kernel<1, false><<<ctas, T, 0, stream>>>(a.descs, none, a.n, a.bytes, chunk, cpb, pub);
     else if (variant == kCopyLdSt256 && param)
         kv_copy_ldst_kernel<32, true><<<ctas, T, 0, stream>>>(a.descs, pd, a.n, a.bytes, chunk, cpb, pub);

@@ -220,7 +220,7 @@ void keys_from_py(const py::object& obj, std::vector<std::string_view>& out) {
 py::dict segment_dict(const SegmentInfo& s) {
     py::dict d;
     d["id"] = s.id;
-    d["kind"] = s.kind == kSegDeviceIpc ? "hbm" : "host";
+    d["kind"] = s.kind == kSegDeviceIpc ? "hbm" : (s.kind == kSegReplica ? "nvls-replica" : "host");
     d["device"] = s.device;
     d["granule"] = s.granule;
     d["bytes"] = s.bytes;
@@ -287,7 +287,9 @@ PYBIND11_MODULE(_infinistore, m) {
         .def_readwrite("pool_devices", &ServerConfig::pool_devices)
         .def_readwrite("extend_size", &ServerConfig::extend_size)
         .def_readwrite("prealloc_bytes", &ServerConfig::prealloc_bytes)
-        .def_readwrite("index_slots", &ServerConfig::index_slots);
+        .def_readwrite("index_slots", &ServerConfig::index_slots)
+        .def_readwrite("replica_bytes", &ServerConfig::replica_bytes)
+        .def_readwrite("replica_devices", &ServerConfig::replica_devices);
 
     // ------------------------------------------------------------ client
     py::class_<Connection, std::shared_ptr<Connection>>(m, "Connection")
@@ -310,18 +312,19 @@ PYBIND11_MODULE(_infinistore, m) {
              py::arg("device") = -1, py::call_guard<py::gil_scoped_release>())
         .def(
             "allocate_rdma",
-            [](Connection& c, const py::object& keys, int block_size) {
+            [](Connection& c, const py::object& keys, int block_size, int hint) {
                 std::vector<std::string_view> kv;
                 keys_from_py(keys, kv);
                 std::vector<RemoteBlock> out;
                 {
                     py::gil_scoped_release rel;
-                    if (c.allocate(kv, block_size, out) != 0) out.clear();
+                    if (c.allocate(kv, block_size, out, hint) != 0) out.clear();
                 }
                 return blocks_to_array(std::move(out));
             },
+            py::arg("keys"), py::arg("block_size"), py::arg("hint") = Connection::kHintDefault,
             "Reserve pool blocks for keys; returns a structured array (rkey, gen, remote_addr), "
-            "empty on failure")
+            "empty on failure.  hint = -2 allocates in the NVLS-replicated region")
         .def(
             "allocate_rdma_async",
             [](Connection& c, const std::vector<std::string>& keys, int block_size,

@@ -96,7 +96,11 @@ bool op_known(char op);
 bool op_has_body(char op);
 
 // Pool-map blob (reply to 'P'): u32 count, then `count` fixed-size records.
-enum SegKind : uint32_t { kSegHostShm = 0, kSegDeviceIpc = 1 };
+// kSegReplica: an NVLS-replicated region - one replica per GPU bound to a multicast object;
+// writes go to the multicast address, reads to the local replica.  `handle` names the unix
+// socket that hands out the VMM file descriptors (fabric/fdpass.h), `device` is -2.
+enum SegKind : uint32_t { kSegHostShm = 0, kSegDeviceIpc = 1, kSegReplica = 2 };
+constexpr int kReplicaDevice = -2;  // pool "device" / allocation hint of the replicated region
 #pragma pack(push, 1)
 struct SegmentInfo {
     uint32_t id;

@@ -138,6 +138,9 @@ class ServerConfig(_infinistore.ServerConfig):
         self.extend_size = kwargs.get("extend_size", 10)
         self.prealloc_bytes = kwargs.get("prealloc_bytes", 0)
         self.index_slots = kwargs.get("index_slots", 0)
+        # NVLS-replicated region (one replica per GPU behind one multicast object)
+        self.replica_bytes = kwargs.get("replica_bytes", 0) or (kwargs.get("replica_size", 0) << 30)
+        self.replica_devices = list(kwargs.get("replica_devices", []) or [])
 
     def __repr__(self):
         return (
@@ -621,13 +624,21 @@ class InfinityConnection:
             raise Exception("allocate memory failed")
         return blocks
 
-    def allocate_rdma(self, keys: List[str], page_size_in_bytes: int):
+    def allocate_rdma(self, keys: List[str], page_size_in_bytes: int, replicated: bool = False):
         """Reserve one pool block per key.  Returns a numpy structured array with fields
         ``rkey`` (u4 @0), ``gen`` (u4 @4) and ``remote_addr`` (u8 @8), itemsize 16; a
-        (0, 0) entry marks a key that already exists."""
+        (0, 0) entry marks a key that already exists.
+
+        ``replicated=True`` places the blocks in the server's NVLS-replicated region
+        (``ServerConfig(replica_size=...)``): ``rdma_write_cache`` then stores each vector
+        once to a multicast address and the NVSwitch delivers it to a replica on every GPU;
+        ``read_cache`` on any GPU reads its local replica at HBM speed."""
         if not self.rdma_connected:
             raise Exception("this function is only valid for connected rdma")
-        ret = self.conn.allocate_rdma(keys, page_size_in_bytes)
+        if replicated:
+            ret = self.conn.allocate_rdma(keys, page_size_in_bytes, -2)
+        else:
+            ret = self.conn.allocate_rdma(keys, page_size_in_bytes)
         if len(ret) == 0:
             raise Exception("allocate memory failed")
         return ret

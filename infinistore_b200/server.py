@@ -154,6 +154,8 @@ def parse_args(argv=None):
     p.add_argument("--pool-devices", default="", type=str,
                    help="comma separated CUDA ordinals that each host a pool segment")
     p.add_argument("--extend-size", default=10, type=int, help="GB per auto-increase step")
+    p.add_argument("--replica-size", default=0, type=int,
+                   help="GB per GPU of NVLS-replicated region for one-writer/many-reader blocks")
     return p.parse_args(argv)
 
 
@@ -183,6 +185,7 @@ def config_from_args(args) -> ServerConfig:
         pool_backend=args.pool_backend,
         pool_devices=devices,
         extend_size=args.extend_size,
+        replica_size=args.replica_size,
     )
 
 

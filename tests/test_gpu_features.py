@@ -166,3 +166,88 @@ def test_nvls_prefix_broadcast():
         torch.cuda.synchronize(d)
         for i in (0, 5, nblk - 1):
             assert torch.equal(rep[slots[i]:slots[i] + bs].cpu(), src[i * bs:(i + 1) * bs].cpu())
+
+
+def _nvls_server(replica_mb=64):
+    cfg = native.ServerConfig()
+    cfg.service_port = 0
+    cfg.host = "127.0.0.1"
+    cfg.pool_backend = "hbm"
+    cfg.pool_devices = [0]
+    cfg.prealloc_bytes = 256 << 20
+    cfg.minimal_allocate_size = 16
+    cfg.replica_bytes = replica_mb << 20
+    srv = native.Server(cfg)
+    srv.start()
+    return srv
+
+
+def _replica_child(port, q):
+    try:
+        torch.cuda.set_device(1)
+        conn = make_conn(port, device=1, device_lookup=True)
+        kinds = [s["kind"] for s in conn.segments()]
+        n, elems = 16, 32768
+        src = torch.randn(n * elems, device="cuda:1")
+        keys = [f"child-{i}" for i in range(n)]
+        blocks = conn.allocate_rdma(keys, elems * 4, replicated=True)
+        conn.register_mr(src)
+        conn.rdma_write_cache(src, [i * elems for i in range(n)], elems, blocks)  # multimem.st from GPU 1
+        conn.sync()
+        dst = torch.zeros_like(src)
+        conn.read_cache(dst, [(k, i * elems) for i, k in enumerate(keys)], elems)  # local replica on GPU 1
+        conn.sync()
+        q.put((kinds, bool(torch.equal(src, dst)), src.cpu()))
+    except Exception as e:  # pragma: no cover
+        q.put(repr(e))
+
+
+def test_nvls_replicated_blocks_through_the_store():
+    """Blocks allocated with replicated=True are written once through the multicast address
+    and readable from the local replica of every GPU - from this process and from another
+    process that obtains the VMM handles over the unix-socket side channel."""
+    import multiprocessing as mp
+
+    if torch.cuda.device_count() < 2 or not nvls_available():
+        pytest.skip("needs >= 2 GPUs with NVLS multicast")
+    srv = _nvls_server()
+    try:
+        assert [s["kind"] for s in srv.segments()] == ["hbm", "nvls-replica"]
+        port = srv.port()
+        w = make_conn(port, device=0, device_lookup=True)
+        n, elems = 48, 16384
+        src = torch.randn(n * elems, device="cuda:0")
+        keys = [rk() for _ in range(n)]
+        blocks = w.allocate_rdma(keys, elems * 4, replicated=True)
+        assert set(blocks["rkey"].tolist()) == {2}  # segment 1 = the replicated region
+        w.register_mr(src)
+        w.rdma_write_cache(src, [i * elems for i in range(n)], elems, blocks)
+        w.sync()
+        for dev, lookup in ((0, True), (1, True), (1, False)):
+            r = make_conn(port, device=dev, device_lookup=lookup)
+            dst = torch.zeros(n * elems, device=f"cuda:{dev}")
+            r.read_cache(dst, [(k, i * elems) for i, k in enumerate(keys)], elems)
+            r.sync()
+            assert torch.equal(src.cpu(), dst.cpu()), (dev, lookup)
+        # ordinary and replicated blocks must not share a batch
+        mixed = w.allocate_rdma(["plain-1"], elems * 4)
+        with pytest.raises(Exception):
+            w.rdma_write_cache(src, [0, elems], elems, np.concatenate([mixed, w.allocate_rdma(
+                ["rep-x"], elems * 4, replicated=True)]))
+        # a separate process: fd passing + cuMemImportFromShareableHandle
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        p = ctx.Process(target=_replica_child, args=(port, q))
+        p.start()
+        res = q.get(timeout=300)
+        p.join(60)
+        assert not isinstance(res, str), res
+        kinds, same, child_src = res
+        assert kinds == ["hbm", "nvls-replica"] and same
+        r0 = make_conn(port, device=0, device_lookup=True)
+        dst = torch.zeros(16 * 32768, device="cuda:0")
+        r0.read_cache(dst, [(f"child-{i}", i * 32768) for i in range(16)], 32768)
+        r0.sync()
+        assert torch.equal(dst.cpu(), child_src)  # GPU 0's replica received GPU 1's multicast
+    finally:
+        srv.stop()

@@ -34,6 +34,7 @@ HOST_SOURCES = [
     "core/kv_store.cpp",
     "fabric/segment.cpp",
     "fabric/nvls.cpp",
+    "fabric/fdpass.cpp",
     "ctrl/server.cpp",
     "ctrl/client.cpp",
 ]
