@@ -197,7 +197,7 @@ def _replica_child(port, q):
         dst = torch.zeros_like(src)
         conn.read_cache(dst, [(k, i * elems) for i, k in enumerate(keys)], elems)  # local replica on GPU 1
         conn.sync()
-        q.put((kinds, bool(torch.equal(src, dst)), src.cpu()))
+        q.put((kinds, bool(torch.equal(src, dst)), src.cpu().numpy().tobytes()))
     except Exception as e:  # pragma: no cover
         q.put(repr(e))
 
@@ -248,6 +248,7 @@ def test_nvls_replicated_blocks_through_the_store():
         dst = torch.zeros(16 * 32768, device="cuda:0")
         r0.read_cache(dst, [(f"child-{i}", i * 32768) for i in range(16)], 32768)
         r0.sync()
-        assert torch.equal(dst.cpu(), child_src)  # GPU 0's replica received GPU 1's multicast
+        want = torch.frombuffer(bytearray(child_src), dtype=torch.float32)
+        assert torch.equal(dst.cpu(), want)  # GPU 0's replica received GPU 1's multicast
     finally:
         srv.stop()
