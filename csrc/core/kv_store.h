@@ -78,6 +78,12 @@ class KVStore {
     size_t drop_uncommitted(uint64_t conn);
     size_t purge();
     size_t size() const { return map_.size(); }
+    // Visit every committed block (checkpointing).
+    template <typename F>
+    void for_each_committed(F&& fn) const {
+        for (auto& kv : map_)
+            if (kv.second && kv.second->committed) fn(kv.first, *kv.second);
+    }
     size_t inflight() const { return inflight_count_; }
 
    private:

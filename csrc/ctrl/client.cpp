@@ -16,6 +16,7 @@
 #include <cstring>
 
 #include "../core/log.h"
+#include "../core/trace.h"
 #include "../kernels/kernels.h"
 #include "../wire/messages.h"
 
@@ -500,6 +501,7 @@ int Connection::get_match_last_index(const std::vector<std::string_view>& keys) 
 }
 
 int Connection::sync_local() {
+    NvtxRange nvtx("istore.sync");
     if (drain_devices() != 0) return -1;
     if (flush_commits() != 0) return -1;
     int32_t code = 0;
@@ -749,6 +751,7 @@ uint8_t* Connection::seg_dev_ptr(DevCtx* ctx, uint32_t seg) {
 int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scale,
                             const RemoteBlock* blocks, size_t n, int block_size,
                             uint64_t base_ptr, int device, uint64_t stream_in, int fp8_elems) {
+    NvtxRange nvtx(write ? "istore.write_blocks" : "istore.read_blocks");
     std::lock_guard<std::mutex> lk(mu_);
     if (n == 0) return 0;
     int kd = device;
@@ -1038,6 +1041,7 @@ static size_t pack_keys(const std::string_view* keys, size_t n, uint8_t* bytes, 
 int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int block_size,
                                       uint64_t base_ptr, int device, uint64_t stream_in,
                                       int fp8_elems) {
+    NvtxRange nvtx("istore.read_via_device_index");
     std::lock_guard<std::mutex> lk(mu_);
     DevCtx* ctx = dev_ctx(device);
     if (!ctx) return -1;

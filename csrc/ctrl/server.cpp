@@ -13,7 +13,12 @@
 #include <chrono>
 #include <cstring>
 
+#include <cuda_runtime_api.h>
+
+#include <cstdio>
+
 #include "../core/log.h"
+#include "../kernels/kernels.h"
 #include "../wire/messages.h"
 
 namespace istore {
@@ -250,6 +255,191 @@ std::vector<SegmentInfo> Server::segments() {
     std::vector<SegmentInfo> v;
     for (auto& s : segs_) v.push_back(s->info());
     return v;
+}
+
+// ---------------------------------------------------------------- checkpoint / resume
+
+namespace {
+constexpr char kDumpMagic[8] = {'I', 'S', 'T', 'O', 'R', 'E', '0', '1'};
+
+struct DevGuard {
+    int prev = -1;
+    explicit DevGuard(int dev) {
+        if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev) cudaSetDevice(dev);
+    }
+    ~DevGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+}  // namespace
+
+long Server::dump(const std::string& path, std::string* err) {
+    std::lock_guard<std::mutex> lk(mu_);
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) {
+        if (err) *err = "cannot open " + path + ": " + std::strerror(errno);
+        return -1;
+    }
+    uint64_t count = 0;
+    std::fwrite(kDumpMagic, 1, 8, f);
+    std::fwrite(&count, 8, 1, f);  // patched at the end
+    std::vector<uint8_t> buf;
+    bool ok = true;
+    store_->for_each_committed([&](const std::string& key, const Block& b) {
+        if (!ok || b.seg >= segs_.size()) return;
+        const fabric::SegmentOwner& seg = *segs_[b.seg];
+        buf.resize(b.size);
+        const uint8_t* src = static_cast<const uint8_t*>(seg.rw_base()) + b.offset;
+        if (seg.info().kind == kSegHostShm) {
+            std::memcpy(buf.data(), src, b.size);
+        } else {
+            DevGuard g(seg.rw_device());
+            if (cudaMemcpy(buf.data(), src, b.size, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                (void)cudaGetLastError();
+                ok = false;
+                return;
+            }
+        }
+        const uint32_t klen = uint32_t(key.size()), size = b.size;
+        const uint8_t replicated = seg.info().kind == kSegReplica;
+        ok = std::fwrite(&klen, 4, 1, f) == 1 && std::fwrite(key.data(), 1, klen, f) == klen &&
+             std::fwrite(&size, 4, 1, f) == 1 && std::fwrite(&replicated, 1, 1, f) == 1 &&
+             std::fwrite(buf.data(), 1, size, f) == size;
+        ++count;
+    });
+    if (ok) {
+        std::fseek(f, 8, SEEK_SET);
+        ok = std::fwrite(&count, 8, 1, f) == 1;
+    }
+    std::fclose(f);
+    if (!ok) {
+        if (err) *err = "writing " + path + " failed";
+        return -1;
+    }
+    LOG_INFO("checkpoint: %llu blocks written to %s", (unsigned long long)count, path.c_str());
+    return long(count);
+}
+
+long Server::load(const std::string& path, std::string* err) {
+    std::lock_guard<std::mutex> lk(mu_);
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) {
+        if (err) *err = "cannot open " + path + ": " + std::strerror(errno);
+        return -1;
+    }
+    char magic[8];
+    uint64_t count = 0;
+    if (std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, kDumpMagic, 8) != 0 ||
+        std::fread(&count, 8, 1, f) != 1) {
+        std::fclose(f);
+        if (err) *err = path + " is not a store checkpoint";
+        return -1;
+    }
+    // pinned staging for the HBM path (the page mover reads it over PCIe)
+    void* staging = nullptr;
+    size_t staging_cap = 0;
+    uint32_t* scratch = nullptr;
+    long loaded = 0;
+    bool ok = true;
+    std::string key;
+    std::vector<uint8_t> host_buf;
+    for (uint64_t i = 0; i < count && ok; ++i) {
+        uint32_t klen = 0, size = 0;
+        uint8_t replicated = 0;
+        if (std::fread(&klen, 4, 1, f) != 1 || klen > (1u << 20)) {
+            ok = false;
+            break;
+        }
+        key.resize(klen);
+        if (std::fread(key.data(), 1, klen, f) != klen || std::fread(&size, 4, 1, f) != 1 ||
+            std::fread(&replicated, 1, 1, f) != 1 || size == 0 || size > (1u << 30)) {
+            ok = false;
+            break;
+        }
+        std::vector<RemoteBlock> blocks;
+        std::vector<std::string_view> keys{std::string_view(key)};
+        const int hint = replicated ? kReplicaDevice : -1;
+        int code = store_->reserve(keys, size, hint, 0, blocks);
+        while (code == kOutOfMemory && !replicated && maybe_extend())
+            code = store_->reserve(keys, size, hint, 0, blocks);
+        if (code != kFinish) {
+            if (err) *err = "pool exhausted while loading " + path;
+            ok = false;
+            break;
+        }
+        if (is_fake_block(blocks[0])) {  // key exists: keep the live copy, skip the bytes
+            std::fseek(f, long(size), SEEK_CUR);
+            continue;
+        }
+        const uint32_t segid = addr_seg(blocks[0].remote_addr);
+        const fabric::SegmentOwner& seg = *segs_[segid];
+        uint8_t* dst = static_cast<uint8_t*>(seg.rw_base()) + addr_off(blocks[0].remote_addr);
+        if (seg.info().kind == kSegHostShm) {
+            ok = std::fread(dst, 1, size, f) == size;
+        } else {
+            DevGuard g(seg.rw_device());
+            if (staging_cap < size_t(size) + 256) {
+                if (staging) cudaFreeHost(staging);
+                staging_cap = std::max<size_t>(size_t(size) + 256, 4u << 20);
+                if (cudaHostAlloc(&staging, staging_cap, cudaHostAllocMapped | cudaHostAllocPortable) !=
+                    cudaSuccess) {
+                    ok = false;
+                    break;
+                }
+            }
+            ok = std::fread(staging, 1, size, f) == size;
+            if (!ok) break;
+            if (seg.info().kind == kSegReplica) {
+                // every replica must receive the bytes: write through the multicast address
+                dst = static_cast<uint8_t*>(seg.base()) + addr_off(blocks[0].remote_addr);
+            }
+            // the descriptor lives in the pinned (device-mapped) staging buffer too
+            auto* descp = reinterpret_cast<kernels::CopyDesc*>(static_cast<uint8_t*>(staging) +
+                                                               ((size_t(size) + 63) & ~size_t(63)));
+            *descp = kernels::CopyDesc{reinterpret_cast<uint64_t>(staging), reinterpret_cast<uint64_t>(dst)};
+            const KeyHash kh = hash_key(reinterpret_cast<const uint8_t*>(key.data()), key.size());
+            kernels::IndexEntry rec{kh.h1, kh.h2, blocks[0].remote_addr, blocks[0].gen, size};
+            kernels::CopyLaunch L;
+            L.descs_host = descp;  // one block: the descriptor rides in the kernel parameters
+            L.descs = descp;
+            L.n = 1;
+            L.bytes = size;
+            L.align_or = size % 16 ? 1 : 0;
+            L.multicast = seg.info().kind == kSegReplica && size % 16 == 0;
+            const fabric::SegmentOwner& seg0 = *segs_[0];
+            void* rec_dev = nullptr;
+            if (seg0.info().index_slots && seg0.info().kind == kSegDeviceIpc) {
+                if (!scratch) {
+                    cudaMalloc(reinterpret_cast<void**>(&scratch), 64);
+                    cudaMemset(scratch, 0, 64);
+                }
+                cudaMalloc(&rec_dev, sizeof(rec));
+                cudaMemcpy(rec_dev, &rec, sizeof(rec), cudaMemcpyHostToDevice);
+                L.recs = static_cast<const kernels::IndexEntry*>(rec_dev);
+                L.table = reinterpret_cast<kernels::IndexEntry*>(static_cast<uint8_t*>(seg0.base()) +
+                                                                seg0.info().index_off);
+                L.table_mask = seg0.info().index_slots - 1;
+                L.done = scratch;
+            }
+            const cudaError_t e = kernels::launch_kv_copy(L, nullptr);
+            ok = e == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
+            if (rec_dev) cudaFree(rec_dev);
+            if (!ok) (void)cudaGetLastError();
+        }
+        if (!ok) break;
+        const uint64_t addr = blocks[0].remote_addr;
+        store_->commit(&addr, 1);
+        ++loaded;
+    }
+    if (staging) cudaFreeHost(staging);
+    if (scratch) cudaFree(scratch);
+    std::fclose(f);
+    if (!ok) {
+        if (err && err->empty()) *err = "reading " + path + " failed";
+        return -1;
+    }
+    LOG_INFO("checkpoint: %ld blocks loaded from %s", loaded, path.c_str());
+    return loaded;
 }
 
 // ---------------------------------------------------------------- reactor

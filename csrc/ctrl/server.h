@@ -59,6 +59,14 @@ class Server {
     ServerStats stats();
     std::vector<SegmentInfo> segments();
 
+    // Checkpoint / resume (the reference has none: a restart loses everything).
+    // dump: every committed block (key, size, bytes) to one file.  load: re-reserve, copy the
+    // bytes into the pool and commit; keys that already exist are skipped (first writer wins).
+    // For an HBM pool the bytes go through the kv_copy kernel, which also publishes the
+    // device index.  Both return the number of blocks, or -1 with `err` set.
+    long dump(const std::string& path, std::string* err);
+    long load(const std::string& path, std::string* err);
+
     // Fault injection for tests: close a connection instead of answering the n-th request
     // from now (0 = off).
     void inject_drop_after(uint64_t n) { drop_after_.store(n); }

@@ -50,6 +50,12 @@ class SegmentOwner {
                                                         std::string* err);
     const SegmentInfo& info() const { return info_; }
     void* base() const { return base_; }
+    // Base through which the owner can READ and WRITE block bytes itself (checkpointing): the
+    // replica of the first GPU for an NVLS segment (its base() is the write-only multicast VA).
+    void* rw_base() const {
+        return group_ ? reinterpret_cast<void*>(group_->uc_ptr(0)) : base_;
+    }
+    int rw_device() const { return group_ ? group_->devices()[0] : info_.device; }
     // Zero the device index (purge).  No-op for host segments.
     void clear_index();
 

@@ -25,6 +25,7 @@
 #include "core/kv_store.h"
 #include "core/log.h"
 #include "core/mempool.h"
+#include "core/trace.h"
 #include "ctrl/client.h"
 #include "ctrl/server.h"
 #include "fabric/nvls.h"
@@ -489,6 +490,32 @@ PYBIND11_MODULE(_infinistore, m) {
         .def("kvmap_len", &Server::kvmap_len, py::call_guard<py::gil_scoped_release>())
         .def("purge", &Server::purge, py::call_guard<py::gil_scoped_release>())
         .def("inject_drop_after", &Server::inject_drop_after)
+        .def(
+            "dump",
+            [](Server& s, const std::string& path) {
+                std::string err;
+                long n;
+                {
+                    py::gil_scoped_release rel;
+                    n = s.dump(path, &err);
+                }
+                if (n < 0) throw std::runtime_error("dump failed: " + err);
+                return n;
+            },
+            "Write every committed block to a checkpoint file; returns the block count")
+        .def(
+            "load",
+            [](Server& s, const std::string& path) {
+                std::string err;
+                long n;
+                {
+                    py::gil_scoped_release rel;
+                    n = s.load(path, &err);
+                }
+                if (n < 0) throw std::runtime_error("load failed: " + err);
+                return n;
+            },
+            "Load a checkpoint file into the pool (existing keys win); returns blocks loaded")
         .def("stats", [](Server& s) { return stats_dict(s.stats()); })
         .def("segments", [](Server& s) {
             py::list l;
@@ -533,6 +560,22 @@ PYBIND11_MODULE(_infinistore, m) {
         std::lock_guard<std::mutex> lk(g_server_mu);
         return g_server ? g_server->kvmap_len() : size_t(0);
     });
+    m.def("dump_kv_map", [](const std::string& path) {
+        std::lock_guard<std::mutex> lk(g_server_mu);
+        if (!g_server) throw std::runtime_error("no server in this process");
+        std::string err;
+        const long n = g_server->dump(path, &err);
+        if (n < 0) throw std::runtime_error("dump failed: " + err);
+        return n;
+    });
+    m.def("load_kv_map", [](const std::string& path) {
+        std::lock_guard<std::mutex> lk(g_server_mu);
+        if (!g_server) throw std::runtime_error("no server in this process");
+        std::string err;
+        const long n = g_server->load(path, &err);
+        if (n < 0) throw std::runtime_error("load failed: " + err);
+        return n;
+    });
     m.def("server_stats", [] {
         std::lock_guard<std::mutex> lk(g_server_mu);
         return g_server ? stats_dict(g_server->stats()) : py::dict();
@@ -542,6 +585,8 @@ PYBIND11_MODULE(_infinistore, m) {
         return g_server ? g_server->port() : 0;
     });
 
+    m.def("install_crash_handler", &install_crash_handler,
+          "Print a backtrace on SIGSEGV/SIGBUS/SIGFPE/SIGABRT, then take the default action");
     m.def("log_msg", &log_msg);
     m.def("set_log_level", [](const std::string& l) { set_log_level(l); });
     m.def("cuda_available", &fabric::cuda_available);

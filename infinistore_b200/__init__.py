@@ -19,6 +19,8 @@ from .lib import (
     server_stats,
     purge_kv_map,
     get_kvmap_len,
+    dump_kv_map,
+    load_kv_map,
 )
 
 __version__ = "0.1.0"
@@ -39,4 +41,6 @@ __all__ = [
     "LINK_IB",
     "purge_kv_map",
     "get_kvmap_len",
+    "dump_kv_map",
+    "load_kv_map",
 ]

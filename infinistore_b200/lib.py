@@ -218,6 +218,17 @@ def register_server(loop, config: ServerConfig):
         raise Exception("Failed to register server")
 
 
+def dump_kv_map(path: str) -> int:
+    """Checkpoint: write every committed block of the in-process server to `path`
+    (the reference is purely in-memory).  Returns the number of blocks."""
+    return _infinistore.dump_kv_map(path)
+
+
+def load_kv_map(path: str) -> int:
+    """Resume: load a checkpoint written by ``dump_kv_map`` (existing keys win)."""
+    return _infinistore.load_kv_map(path)
+
+
 def stop_server():
     _infinistore.stop_server()
 

@@ -4,8 +4,9 @@ Flags, defaults and endpoints follow the reference (infinistore/server.py:26-263
 ``--auto-increase --host --manage-port 18080 --service-port 22345 --log-level info
 --prealloc-size 16 --dev-name --ib-port --link-type --minimal-allocate-size 64
 --num-stream --warmup`` and ``POST /purge``, ``POST /selftest/{port}``, ``GET /kvmap_len``.
-New: ``--pool-backend``, ``--pool-devices``, ``--extend-size``, and ``GET /metrics``
-(Prometheus text) / ``GET /stats`` (JSON).  ``--host`` is honoured (the reference parses
+New: ``--pool-backend``, ``--pool-devices``, ``--extend-size``, ``--replica-size``,
+``--load-from``; ``GET /metrics`` (Prometheus text), ``GET /stats`` (JSON), ``POST /dump`` and
+``POST /load`` (checkpoint / resume).  ``--host`` is honoured (the reference parses
 and ignores it).  The data/control plane runs on a native reactor thread; uvicorn only
 serves the manage plane.
 """
@@ -56,6 +57,18 @@ def _make_app():
         port `number` of this host and check them (reference: server.py:41-91)."""
         Logger.info("selftest")
         return await run_selftest(number)
+
+    @app.post("/dump")
+    async def dump(path: str):
+        """Checkpoint every committed block to `path` on the server host."""
+        n = await asyncio.to_thread(_lib.dump_kv_map, path)
+        return {"status": "ok", "num": n, "path": path}
+
+    @app.post("/load")
+    async def load(path: str):
+        """Load a checkpoint (keys already in the store win)."""
+        n = await asyncio.to_thread(_lib.load_kv_map, path)
+        return {"status": "ok", "num": n, "path": path}
 
     @app.get("/kvmap_len")
     async def kvmap_len():
@@ -154,6 +167,8 @@ def parse_args(argv=None):
     p.add_argument("--pool-devices", default="", type=str,
                    help="comma separated CUDA ordinals that each host a pool segment")
     p.add_argument("--extend-size", default=10, type=int, help="GB per auto-increase step")
+    p.add_argument("--load-from", default="", type=str,
+                   help="checkpoint file (POST /dump) to load at start-up")
     p.add_argument("--replica-size", default=0, type=int,
                    help="GB per GPU of NVLS-replicated region for one-writer/many-reader blocks")
     return p.parse_args(argv)
@@ -194,6 +209,7 @@ def main(argv=None):
     config = config_from_args(args)
     config.verify()
     Logger.set_log_level(config.log_level)
+    _lib._infinistore.install_crash_handler()  # backtrace on a fatal signal (server process only)
     check_supported()
     Logger.info(config)
 
@@ -207,6 +223,8 @@ def main(argv=None):
         loop_kind = "asyncio"
     asyncio.set_event_loop(loop)
     register_server(loop, config)
+    if args.load_from:
+        Logger.info(f"loaded {_lib.load_kv_map(args.load_from)} blocks from {args.load_from}")
 
     if args.warmup:
         Logger.info("Starting warm up all cuda devices, it may take a while...")

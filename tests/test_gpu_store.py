@@ -244,3 +244,49 @@ def test_smoke_entry():
     import __graft_entry__
 
     __graft_entry__.smoke()
+
+
+def test_checkpoint_dump_and_load_hbm(tmp_path):
+    """Checkpoint of an HBM pool; the loader publishes the device index through kv_copy."""
+    from infinistore_b200 import _infinistore as m
+
+    def mk():
+        cfg = m.ServerConfig()
+        cfg.service_port = 0
+        cfg.host = "127.0.0.1"
+        cfg.pool_backend = "hbm"
+        cfg.pool_devices = [0]
+        cfg.prealloc_bytes = 256 << 20
+        cfg.minimal_allocate_size = 16
+        s = m.Server(cfg)
+        s.start()
+        return s
+
+    path = str(tmp_path / "hbm.ckpt")
+    srv = mk()
+    try:
+        conn = make_conn(srv.port(), device_lookup=True)
+        src = torch.randn(20 * 8192, device="cuda:0")
+        odd = torch.randn(1001, device="cuda:0")  # size that is not a multiple of 16 bytes
+        conn.register_mr(src)
+        keys = [f"hk-{i}" for i in range(20)]
+        conn.rdma_write_cache(src, [i * 8192 for i in range(20)], 8192, conn.allocate_rdma(keys, 32768))
+        conn.rdma_write_cache(odd, [0], 1001, conn.allocate_rdma(["odd"], 4004))
+        conn.sync()
+        assert srv.dump(path) == 21
+    finally:
+        srv.stop()
+    srv = mk()
+    try:
+        assert srv.load(path) == 21
+        for lookup in (True, False):  # device index and server map both know the keys
+            conn = make_conn(srv.port(), device_lookup=lookup)
+            dst = torch.zeros(20 * 8192, device="cuda:0")
+            conn.read_cache(dst, [(k, i * 8192) for i, k in enumerate(keys)], 8192)
+            back = torch.zeros(1001, device="cuda:0")
+            conn.read_cache(back, [("odd", 0)], 1001)
+            conn.sync()
+            assert torch.equal(dst, src) and torch.equal(back, odd)
+            assert conn.get_match_last_index(keys + ["none"]) == 19
+    finally:
+        srv.stop()

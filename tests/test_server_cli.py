@@ -61,9 +61,18 @@ def test_manage_plane_and_selftest(cli_server):
     assert stats["keys"] == 11 and stats["ops"]["ALLOCATE"] >= 2
     text = urllib.request.urlopen(base + "/metrics", timeout=10).read().decode()
     assert "infinistore_keys 11" in text and 'infinistore_op_total{op="COMMIT"}' in text
+    ckpt = "/tmp/istore_cli_test.ckpt"
+    assert _http("POST", base + f"/dump?path={ckpt}")["num"] == 11
     assert _http("POST", base + "/purge") == {"status": "ok", "num": 11}
     assert _http("GET", base + "/kvmap_len") == {"len": 0}
     assert not conn.check_exist("cli-0")
+    assert _http("POST", base + f"/load?path={ckpt}")["num"] == 11
+    assert conn.check_exist("cli-0")
+    dst = torch.zeros(1024)
+    conn.read_cache(dst, [("cli-5", 0)], 1024)
+    conn.sync()
+    assert torch.equal(dst, src[5 * 1024:6 * 1024])
+    _http("POST", base + "/purge")
 
 
 def test_cpu_benchmark_against_cli_server(cli_server):

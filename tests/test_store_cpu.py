@@ -466,3 +466,39 @@ def test_many_keys_single_request(host_server):
     conn.sync()
     assert torch.equal(src, dst)
     assert conn.get_match_last_index(keys) == n - 1
+
+
+def test_checkpoint_dump_and_load(tmp_path):
+    """Checkpoint / resume: dump a store, start a fresh one, load, read back."""
+    srv, port = _server(prealloc_bytes=64 * 16384)
+    path = str(tmp_path / "store.ckpt")
+    try:
+        conn = make_conn(port)
+        src = torch.randn(12 * 1024)
+        conn.register_mr(src)
+        keys = [f"ck-{i}" for i in range(12)]
+        conn.rdma_write_cache(src, [i * 1024 for i in range(12)], 1024, conn.allocate_rdma(keys, 4096))
+        conn.allocate_rdma(["reserved-only"], 4096)  # uncommitted: must not be dumped
+        conn.sync()
+        assert srv.dump(path) == 12
+    finally:
+        srv.stop()
+    srv2, port2 = _server(prealloc_bytes=64 * 16384)
+    try:
+        conn = make_conn(port2)
+        live = torch.full((1024,), 7.0)
+        conn.register_mr(live)
+        conn.rdma_write_cache(live, [0], 1024, conn.allocate_rdma(["ck-3"], 4096))  # newer copy wins
+        conn.sync()
+        assert srv2.load(path) == 11 and srv2.kvmap_len() == 12
+        dst = torch.zeros(12 * 1024)
+        conn.read_cache(dst, [(k, i * 1024) for i, k in enumerate(keys)], 1024)
+        conn.sync()
+        want = src.clone()
+        want[3 * 1024:4 * 1024] = 7.0
+        assert torch.equal(dst, want)
+        assert not conn.check_exist("reserved-only")
+        with pytest.raises(Exception):
+            srv2.load(str(tmp_path / "missing.ckpt"))
+    finally:
+        srv2.stop()

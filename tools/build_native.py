@@ -32,6 +32,7 @@ HOST_SOURCES = [
     "core/log.cpp",
     "core/mempool.cpp",
     "core/kv_store.cpp",
+    "core/trace.cpp",
     "fabric/segment.cpp",
     "fabric/nvls.cpp",
     "fabric/fdpass.cpp",
