@@ -7,6 +7,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 
 namespace istore {
 
