@@ -685,7 +685,7 @@ std::shared_ptr<fabric::Mapping> Connection::mapping(uint32_t seg, int device) {
     return host_maps_[seg];
 }
 
-int Connection::ensure_host_registered(uint64_t ptr, size_t bytes, int device) {
+int Connection::ensure_host_registered(uint64_t ptr, size_t bytes, int device, bool temporary) {
     auto it = host_regs_.upper_bound(ptr);
     if (it != host_regs_.begin()) {
         --it;
@@ -701,7 +701,35 @@ int Connection::ensure_host_registered(uint64_t ptr, size_t bytes, int device) {
         return -1;
     }
     (void)cudaGetLastError();
-    host_regs_[ptr] = HostReg{bytes, e == cudaSuccess};
+    host_regs_[ptr] = HostReg{bytes, e == cudaSuccess, temporary};
+    return 0;
+}
+
+// Implicit pins (a CPU tensor that was never register_mr'ed) live for one transfer only: the
+// caller may free the tensor after sync(), and a pin that outlives its memory would map stale
+// physical pages if the address is reused.
+void Connection::release_temporary_host_regs() {
+    for (auto it = host_regs_.begin(); it != host_regs_.end();) {
+        if (it->second.temporary) {
+            if (it->second.registered) cudaHostUnregister(reinterpret_cast<void*>(it->first));
+            (void)cudaGetLastError();
+            it = host_regs_.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
+
+int Connection::unregister_mr(uint64_t ptr) {
+    if (drain_devices() != 0) { /* report via the next sync; still unpin below */ }
+    std::lock_guard<std::mutex> lk(mu_);
+    mrs_.erase(ptr);
+    auto it = host_regs_.find(ptr);
+    if (it != host_regs_.end()) {
+        if (it->second.registered) cudaHostUnregister(reinterpret_cast<void*>(ptr));
+        (void)cudaGetLastError();
+        host_regs_.erase(it);
+    }
     return 0;
 }
 
@@ -712,7 +740,7 @@ int Connection::register_mr(uint64_t ptr, size_t size, int device) {
         // Pin + map host memory so that kernels can stream it over PCIe (the role
         // ibv_reg_mr plays for CPU tensors in the reference).
         const int kd = cfg_.device >= 0 ? cfg_.device : std::max(default_device_, 0);
-        if (ensure_host_registered(ptr, size, kd) != 0)
+        if (ensure_host_registered(ptr, size, kd, false) != 0)
             LOG_WARN("register_mr: could not pin host memory, falling back to staged copies");
     }
     if (device >= 0 && !dev_ctx(device)) return -1;
@@ -802,7 +830,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
         kd = cfg_.device >= 0 ? cfg_.device : std::max(default_device_, 0);
         auto mr = mrs_.find(base_ptr);
         const size_t span = mr != mrs_.end() ? mr->second : size_t(max_off) + size_t(block_size);
-        if (ensure_host_registered(base_ptr, span, kd) != 0) {
+        if (ensure_host_registered(base_ptr, span, kd, mr == mrs_.end()) != 0) {
             fail("cannot pin the host tensor for the GPU data path");
             return -1;
         }
@@ -1211,6 +1239,10 @@ int Connection::match_via_device_index(const std::vector<std::string_view>& keys
 int Connection::drain_devices() {
     std::lock_guard<std::mutex> lk(mu_);
     int rc = 0;
+    struct AtExit {
+        Connection* c;
+        ~AtExit() { c->release_temporary_host_regs(); }
+    } at_exit{this};
     for (auto& kv : devs_) {
         DevCtx& ctx = *kv.second;
         if (!ctx.dirty) continue;

@@ -94,6 +94,10 @@ class Connection {
     // --- data plane.  `device` is the CUDA ordinal owning base_ptr, -1 for host memory;
     //     `stream` is a cudaStream_t to order after (0 = the connection's own stream).
     int register_mr(uint64_t ptr, size_t size, int device);
+    // Forget a registered region; host memory is unpinned once no kernel can still read it.
+    // Must be called before registered HOST memory is freed: a stale pin would keep mapping
+    // the old physical pages at that virtual address.
+    int unregister_mr(uint64_t ptr);
     // hint: pool device to prefer, kReplicaDevice (-2) for the NVLS-replicated region,
     // kHintDefault for the connection's configured pool_hint
     static constexpr int kHintDefault = -1000;
@@ -160,7 +164,8 @@ class Connection {
     int read_via_device_index(const std::vector<KeyOffset>& blocks, int block_size,
                               uint64_t base_ptr, int device, uint64_t stream, int fp8_elems = 0);
     int match_via_device_index(const std::vector<std::string_view>& keys, bool exist_only);
-    int ensure_host_registered(uint64_t ptr, size_t bytes, int device);
+    int ensure_host_registered(uint64_t ptr, size_t bytes, int device, bool temporary);
+    void release_temporary_host_regs();
     int drain_devices();
     bool device_index_usable();
     void fail(const std::string& msg);
@@ -185,6 +190,7 @@ class Connection {
     struct HostReg {
         size_t bytes;
         bool registered;
+        bool temporary;  // pinned implicitly for one transfer: released at the next sync()
     };
     std::map<uint64_t, HostReg> host_regs_;  // register_mr'ed host ranges by base pointer
     std::map<uint64_t, size_t> mrs_;         // registered regions by base pointer (C10)

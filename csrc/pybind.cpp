@@ -311,6 +311,7 @@ PYBIND11_MODULE(_infinistore, m) {
         .def("sync_rdma", &Connection::sync_rdma, py::call_guard<py::gil_scoped_release>())
         .def("register_mr", &Connection::register_mr, py::arg("ptr"), py::arg("size"),
              py::arg("device") = -1, py::call_guard<py::gil_scoped_release>())
+        .def("unregister_mr", &Connection::unregister_mr, py::call_guard<py::gil_scoped_release>())
         .def(
             "allocate_rdma",
             [](Connection& c, const py::object& keys, int block_size, int hint) {

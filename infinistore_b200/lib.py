@@ -312,6 +312,15 @@ except AttributeError:  # pragma: no cover
     _raw_current_stream = None
 
 
+def _unregister_quietly(conn_ref, ptr):
+    conn = conn_ref()
+    if conn is not None:
+        try:
+            conn.unregister_mr(ptr)
+        except Exception:  # pragma: no cover - interpreter shutdown
+            pass
+
+
 class _TensorInfo:
     """Per-tensor facts the hot path needs, computed once (the KV cache tensor is registered
     once and then addressed by offsets, reference calling convention C10)."""
@@ -614,10 +623,16 @@ class InfinityConnection:
         self._verify(cache)
         if not self.rdma_connected:
             raise Exception("this function is only valid for connected rdma")
-        ret = self.conn.register_mr(cache.data_ptr(), cache.numel() * cache.element_size(),
-                                    _device_of(cache))
+        ptr = cache.data_ptr()
+        ret = self.conn.register_mr(ptr, cache.numel() * cache.element_size(), _device_of(cache))
         if ret < 0:
             raise Exception("register memory region failed")
+        if cache.device.type != "cuda":
+            # unpin before the tensor's memory is released: a stale pin would keep mapping the
+            # old physical pages if the allocator reuses the address
+            import weakref
+
+            weakref.finalize(cache, _unregister_quietly, weakref.ref(self.conn), ptr)
         return ret
 
     async def allocate_rdma_async(self, keys: List[str], page_size_in_bytes: int):
