@@ -34,8 +34,9 @@ namespace {
 using namespace dev;
 
 constexpr uint32_t kLdStChunk = 32u << 10;  // work item of the ld/st path
-constexpr int kTmaStages = 8;
-constexpr uint32_t kTmaChunk = 16u << 10;   // bytes per bulk copy / ring stage
+constexpr int kTmaMaxStages = 32;
+constexpr uint32_t kTmaChunk = 16u << 10;   // largest bulk copy / ring slot
+constexpr uint32_t kTmaRingBytes = 128u << 10;
 
 // ---------------------------------------------------------------- ld/st path (copy_span.cuh)
 // Descriptors of small batches travel in the kernel parameters (constant bank): reading
@@ -93,16 +94,26 @@ __global__ void __launch_bounds__(kLdStThreads + 32)
 }
 
 // ---------------------------------------------------------------- bulk-async (TMA) path
-// Two warps per CTA.  Warp 0: lane 0 runs the pipeline; all lanes prefetch descriptors (32 at
-// a time, one coalesced read even when they live in mapped host memory).  Warp 1 is the
-// control warp (in-band commit).
+// Two warps per CTA.  Warp 0: lane 0 drives an SMEM ring with 1-D bulk async copies; all lanes
+// prefetch descriptors (32 at a time, one coalesced read even when they live in mapped host
+// memory).  Warp 1 is the control warp (in-band commit).
+//
+// Ring: `stages` slots of `stage_bytes` (chosen per launch: 16 KB slots for big blocks, one
+// slot per block for small ones, up to 32 slots / 128 KB).  Global->shared copies complete on
+// the slot's mbarrier (complete_tx); shared->global copies are tracked as bulk groups, and a
+// slot is refilled once the store that used it has finished READING shared memory
+// (wait_group.read), with kPendingStores groups allowed to lag so that the issuing thread
+// never waits for the store it has just issued.
+constexpr int kPendingStores = 2;
+
 template <bool PARAM>
 __global__ void __launch_bounds__(64)
     kv_copy_tma_kernel(const CopyDesc* __restrict__ descs,
                        const __grid_constant__ DescParam<PARAM ? kParamDescs : 1> pd, uint32_t n,
-                       uint32_t bytes, uint32_t cpb, Publish pub) {
+                       uint32_t bytes, uint32_t stage_bytes, uint32_t stages, uint32_t cpb,
+                       Publish pub) {
     extern __shared__ __align__(128) uint8_t ring[];
-    __shared__ __align__(8) uint64_t full[kTmaStages];
+    __shared__ __align__(8) uint64_t full[kTmaMaxStages];
     const uint32_t total = n * cpb;
     const uint32_t grid = gridDim.x;
     const uint32_t nitems = blockIdx.x < total ? (total - blockIdx.x + grid - 1) / grid : 0;
@@ -113,7 +124,7 @@ __global__ void __launch_bounds__(64)
     const uint32_t lane = threadIdx.x;
 
     if (lane == 0) {
-        for (int s = 0; s < kTmaStages; ++s) mbar_init(&full[s], 1);
+        for (uint32_t s = 0; s < stages; ++s) mbar_init(&full[s], 1);
         mbar_fence_init();
     }
     __syncwarp();
@@ -139,19 +150,22 @@ __global__ void __launch_bounds__(64)
         r.dst = __shfl_sync(0xffffffffu, in_cur ? cur.dst : nxt.dst, l);
         return r;
     };
-    auto issue_load = [&](uint32_t k, const CopyDesc& d) {
-        const uint32_t s = k % kTmaStages;
-        const uint32_t off = ((blockIdx.x + k * grid) % cpb) * kTmaChunk;
-        const uint32_t len = min(kTmaChunk, bytes - off);
-        if (lane == 0 && d.src != 0) {
-            mbar_expect_tx(&full[s], len);
-            bulk_g2s(ring + size_t(s) * kTmaChunk, reinterpret_cast<const uint8_t*>(d.src) + off,
-                     len, &full[s]);
+    uint32_t loaded = 0;  // loads issued so far
+    auto pump = [&](uint32_t limit) {  // issue loads up to (excluding) item `limit`
+        while (loaded < nitems && loaded < limit) {
+            const CopyDesc d = desc_of(loaded);
+            const uint32_t s = loaded % stages;
+            const uint32_t off = ((blockIdx.x + loaded * grid) % cpb) * stage_bytes;
+            const uint32_t len = min(stage_bytes, bytes - off);
+            if (lane == 0 && d.src != 0) {
+                mbar_expect_tx(&full[s], len);
+                bulk_g2s(ring + size_t(s) * stage_bytes,
+                         reinterpret_cast<const uint8_t*>(d.src) + off, len, &full[s]);
+            }
+            ++loaded;
         }
     };
-
-    const uint32_t prologue = min(uint32_t(kTmaStages - 1), nitems);
-    for (uint32_t k = 0; k < prologue; ++k) issue_load(k, desc_of(k));
+    pump(stages);  // prologue: fill the ring (stages <= 32: inside the descriptor window)
 
     for (uint32_t k = 0; k < nitems; ++k) {
         if (k >= window + 32) {  // slide the descriptor window
@@ -160,27 +174,23 @@ __global__ void __launch_bounds__(64)
             nxt = fetch(window + 32);
         }
         const CopyDesc d = desc_of(k);
-        const uint32_t s = k % kTmaStages;
+        const uint32_t s = k % stages;
         const uint32_t item = blockIdx.x + k * grid;
-        const uint32_t off = (item % cpb) * kTmaChunk;
-        const uint32_t len = min(kTmaChunk, bytes - off);
+        const uint32_t off = (item % cpb) * stage_bytes;
+        const uint32_t len = min(stage_bytes, bytes - off);
         if (lane == 0) {
             if (d.src != 0) {
-                mbar_wait(&full[s], (k / kTmaStages) & 1);
-                bulk_s2g(reinterpret_cast<uint8_t*>(d.dst) + off, ring + size_t(s) * kTmaChunk, len);
+                mbar_wait(&full[s], (k / stages) & 1);
+                bulk_s2g(reinterpret_cast<uint8_t*>(d.dst) + off, ring + size_t(s) * stage_bytes, len);
             } else if (off == 0 && pub.status) {
                 atomicAdd(pub.status + kStatMiss, 1u);
             }
-            bulk_commit();  // one group per item keeps wait_group arithmetic simple
+            bulk_commit();  // one group per item keeps the wait_group arithmetic simple
+            // stores up to item k - kPendingStores have drained their slots
+            bulk_wait_read<kPendingStores>();
         }
-        const uint32_t kn = k + kTmaStages - 1;
-        if (kn < nitems) {
-            // stage kn % S was last read by the store of item k-1: wait until that store
-            // has drained its shared-memory source (all but the newest group)
-            if (lane == 0 && k >= 1) bulk_wait_read<1>();
-            // kn = k + S - 1 < window + 64 always holds (S - 1 < 32)
-            issue_load(kn, desc_of(kn));
-        }
+        // slot of store j is reused by load j + stages; loads < k + 32 stay in the window
+        if (k >= kPendingStores) pump(k - kPendingStores + 1 + stages);
     }
     if (lane == 0) {
         bulk_wait<0>();        // every bulk store of this CTA has completed its writes
@@ -234,29 +244,36 @@ cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream) {
     const DescParam<1> none{};
 
     if (variant == kCopyTma) {
-        const uint32_t cpb = (a.bytes + kTmaChunk - 1) / kTmaChunk;
+        // slot = 16 KB for big blocks, the block itself (rounded up to 16 B) for small ones
+        const uint32_t stage_bytes = std::min(kTmaChunk, (a.bytes + 15u) & ~15u);
+        const uint32_t stages = std::min<uint32_t>(kTmaMaxStages, kTmaRingBytes / stage_bytes);
+        const uint32_t cpb = (a.bytes + stage_bytes - 1) / stage_bytes;
         const uint64_t total = uint64_t(a.n) * cpb;
         int ctas = a.max_ctas > 0 ? a.max_ctas : 2 * sms;
         ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
-        const size_t smem = size_t(kTmaStages) * kTmaChunk;
+        const size_t smem = size_t(stages) * stage_bytes;
         int dev = 0;
         cudaGetDevice(&dev);
         {
             std::lock_guard<std::mutex> lk(g_attr_mu);
             if (dev >= 0 && dev < 64 && !g_tma_attr_set[dev]) {
-                cudaError_t e = cudaFuncSetAttribute(
-                    kv_copy_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+                cudaError_t e = cudaFuncSetAttribute(kv_copy_tma_kernel<false>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     int(kTmaRingBytes));
                 if (e == cudaSuccess)
                     e = cudaFuncSetAttribute(kv_copy_tma_kernel<true>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             int(kTmaRingBytes));
                 if (e != cudaSuccess) return e;
                 g_tma_attr_set[dev] = true;
             }
         }
         if (param)
-            kv_copy_tma_kernel<true><<<ctas, 64, smem, stream>>>(a.descs, pd, a.n, a.bytes, cpb, pub);
+            kv_copy_tma_kernel<true><<<ctas, 64, smem, stream>>>(a.descs, pd, a.n, a.bytes, stage_bytes,
+                                                                 stages, cpb, pub);
         else
-            kv_copy_tma_kernel<false><<<ctas, 64, smem, stream>>>(a.descs, none, a.n, a.bytes, cpb, pub);
+            kv_copy_tma_kernel<false><<<ctas, 64, smem, stream>>>(a.descs, none, a.n, a.bytes,
+                                                                  stage_bytes, stages, cpb, pub);
         return cudaGetLastError();
     }
 
