@@ -548,33 +548,59 @@ int Connection::flush_commits() {
     return 0;
 }
 
+// One control-plane message holds at most kMaxBody bytes: large key lists are sent in chunks.
+static std::vector<std::pair<size_t, size_t>> chunk_keys(const std::vector<std::string_view>& keys) {
+    constexpr size_t kBudget = 3u << 20;
+    std::vector<std::pair<size_t, size_t>> out;
+    size_t begin = 0, bytes = 0;
+    for (size_t i = 0; i < keys.size(); ++i) {
+        const size_t need = keys[i].size() + 16;
+        if (bytes + need > kBudget && i > begin) {
+            out.emplace_back(begin, i);
+            begin = i;
+            bytes = 0;
+        }
+        bytes += need;
+    }
+    if (begin < keys.size()) out.emplace_back(begin, keys.size());
+    return out;
+}
+
 int Connection::allocate(const std::vector<std::string_view>& keys, int block_size,
                          std::vector<RemoteBlock>& out, int hint) {
     out.clear();
     if (keys.empty() || block_size <= 0) return -1;
-    const std::vector<std::string_view>& kv = keys;
-    std::vector<uint8_t> buf(remote_meta_bound(kv, 0));
-    if (buf.size() > kMaxBody) {
-        fail("allocate: too many keys for one request");
-        return -1;
+    out.reserve(keys.size());
+    for (auto [b0, b1] : chunk_keys(keys)) {
+        const std::vector<std::string_view> kv(keys.begin() + b0, keys.begin() + b1);
+        std::vector<uint8_t> buf(remote_meta_bound(kv, 0));
+        fb::Builder b(buf.data(), buf.size());
+        encode_remote_meta(b, kv, block_size, 0, nullptr, 0, kOpAllocate,
+                           hint == kHintDefault ? cfg_.pool_hint : hint);
+        int32_t code = 0;
+        std::vector<uint8_t> p;
+        if (transact(kOpAllocate, b.data(), b.size(), &code, &p, kBlobPayload) != 0) return -1;
+        if (code != kFinish) {
+            // blocks reserved by earlier chunks stay reserved-uncommitted; the server releases
+            // them when this connection closes
+            fail("allocate: server returned " + std::to_string(code));
+            out.clear();
+            return -code;
+        }
+        std::vector<RemoteBlock> part;
+        try {
+            part = decode_allocate_response(p.data(), p.size());
+        } catch (const std::exception& e) {
+            fail(std::string("allocate: bad reply: ") + e.what());
+            out.clear();
+            return -1;
+        }
+        if (part.size() != kv.size()) {
+            out.clear();
+            return -1;
+        }
+        out.insert(out.end(), part.begin(), part.end());
     }
-    fb::Builder b(buf.data(), buf.size());
-    encode_remote_meta(b, kv, block_size, 0, nullptr, 0, kOpAllocate,
-                       hint == kHintDefault ? cfg_.pool_hint : hint);
-    int32_t code = 0;
-    std::vector<uint8_t> p;
-    if (transact(kOpAllocate, b.data(), b.size(), &code, &p, kBlobPayload) != 0) return -1;
-    if (code != kFinish) {
-        fail("allocate: server returned " + std::to_string(code));
-        return -code;
-    }
-    try {
-        out = decode_allocate_response(p.data(), p.size());
-    } catch (const std::exception& e) {
-        fail(std::string("allocate: bad reply: ") + e.what());
-        return -1;
-    }
-    if (out.size() != keys.size()) return -1;
     if (server_hbm_) {  // remember fingerprints: the write kernel publishes them in-band
         std::lock_guard<std::mutex> lk(mu_);
         for (size_t i = 0; i < keys.size(); ++i) {
@@ -599,12 +625,35 @@ int Connection::lookup_blocks(char op, const std::vector<KeyOffset>& blocks, int
         encode_local_meta(b, std::max(default_device_, 0), std::string_view(), block_size, lb);
         if (transact(op, b.data(), b.size(), &code, &p, kBlobPayload) != 0) return -1;
     } else {
-        std::vector<std::string_view> kv;
-        kv.reserve(blocks.size());
-        for (auto& kb : blocks) kv.push_back(kb.key);
-        std::vector<uint8_t> buf(remote_meta_bound(kv, 0));
+        std::vector<std::string_view> all;
+        all.reserve(blocks.size());
+        for (auto& kb : blocks) all.push_back(kb.key);
+        const auto chunks = chunk_keys(all);
+        if (chunks.size() > 1) {  // very large batch: one request per chunk
+            out.clear();
+            for (auto [b0, b1] : chunks) {
+                const std::vector<std::string_view> kv(all.begin() + b0, all.begin() + b1);
+                std::vector<uint8_t> buf(remote_meta_bound(kv, 0));
+                fb::Builder b(buf.data(), buf.size());
+                encode_remote_meta(b, kv, block_size, 0, nullptr, 0, op, cfg_.pool_hint);
+                if (transact(op, b.data(), b.size(), &code, &p, kBlobPayload) != 0) return -1;
+                if (code != kFinish && code != kTaskAccepted) {
+                    last_error_ = std::string(op_name(op)) + ": server returned " + std::to_string(code);
+                    return -code;
+                }
+                try {
+                    auto part = decode_allocate_response(p.data(), p.size());
+                    out.insert(out.end(), part.begin(), part.end());
+                } catch (const std::exception& e) {
+                    fail(std::string("bad reply: ") + e.what());
+                    return -1;
+                }
+            }
+            return out.size() == blocks.size() ? 0 : -1;
+        }
+        std::vector<uint8_t> buf(remote_meta_bound(all, 0));
         fb::Builder b(buf.data(), buf.size());
-        encode_remote_meta(b, kv, block_size, 0, nullptr, 0, op, cfg_.pool_hint);
+        encode_remote_meta(b, all, block_size, 0, nullptr, 0, op, cfg_.pool_hint);
         if (transact(op, b.data(), b.size(), &code, &p, kBlobPayload) != 0) return -1;
     }
     if (code != kFinish && code != kTaskAccepted) {

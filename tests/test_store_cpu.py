@@ -502,3 +502,25 @@ def test_checkpoint_dump_and_load(tmp_path):
             srv2.load(str(tmp_path / "missing.ckpt"))
     finally:
         srv2.stop()
+
+
+def test_huge_key_lists_are_chunked_transparently():
+    """150k keys x ~40 bytes exceed the 4 MiB message cap: allocate / lookup chunk them."""
+    srv, port = _server(prealloc_bytes=160000 * 16384)
+    try:
+        conn = make_conn(port)
+        n = 150000
+        keys = [f"{i:07d}-" + "k" * 32 for i in range(n)]
+        blocks = conn.allocate_rdma(keys, 64)
+        assert len(blocks) == n and len(set(blocks["remote_addr"].tolist())) == n
+        assert srv.stats()["ops"]["ALLOCATE"] >= 2
+        src = torch.arange(n * 16, dtype=torch.float32)
+        conn.register_mr(src)
+        conn.rdma_write_cache(src, np.arange(n) * 16, 16, blocks)
+        conn.sync()
+        dst = torch.zeros_like(src)
+        conn.read_cache(dst, list(zip(keys, (np.arange(n) * 16).tolist())), 16)
+        conn.sync()
+        assert torch.equal(src, dst)
+    finally:
+        srv.stop()
