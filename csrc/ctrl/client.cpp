@@ -502,12 +502,34 @@ int Connection::get_match_last_index(const std::vector<std::string_view>& keys) 
 
 int Connection::sync_local() {
     NvtxRange nvtx("istore.sync");
+    {
+        // Nothing to tell the server (no commits pending, no leases held by host-mediated
+        // lookups): completion of the kernels is all there is to wait for.
+        bool quiet;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            quiet = pending_commit_.empty() && !ctrl_dirty_;
+        }
+        bool async_idle;
+        {
+            std::lock_guard<std::mutex> lk(q_mu_);
+            async_idle = inflight_async_ == 0;
+        }
+        if (quiet && async_idle) {
+            const int drained = drain_devices();
+            return drained != 0 ? drained : 0;
+        }
+    }
     if (drain_devices() != 0) return -1;
     if (flush_commits() != 0) return -1;
     int32_t code = 0;
     std::vector<uint8_t> p;
     if (transact(kOpSync, nullptr, 0, &code, &p, sizeof(uint32_t)) != 0 || code != kFinish)
         return -1;
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        ctrl_dirty_ = false;
+    }
     uint32_t remain;
     std::memcpy(&remain, p.data(), sizeof(remain));
     return int(remain);
@@ -615,6 +637,10 @@ int Connection::allocate(const std::vector<std::string_view>& keys, int block_si
 
 int Connection::lookup_blocks(char op, const std::vector<KeyOffset>& blocks, int block_size,
                               std::vector<RemoteBlock>& out) {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        ctrl_dirty_ = true;  // the server pins looked-up blocks until our next SYNC
+    }
     int32_t code = 0;
     std::vector<uint8_t> p;
     if (op == kOpLocalRead || op == kOpLocalWrite) {
@@ -1165,7 +1191,14 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
         const uint64_t t_launch0 = now_ns();
         stats_.ns_build += t_launch0 - t_build0;
         cudaError_t e;
-        if (!fp8_elems && copy_variant_ != kernels::kCopyTma) {
+        // The fused kernel resolves a key in every CTA that moves a piece of its block, reading
+        // the key bytes from the pinned ring each time: right when a block is one work item
+        // (>= SM-count blocks of <= 1 MB), wasteful when a few large blocks are split over
+        // many CTAs (measured: 4 MB single-block read 83 us vs 42 us) - then resolve each key
+        // once with the lookup kernel and feed the descriptors to kv_copy.
+        const bool whole_blocks =
+            n >= size_t(kernels::sm_count()) && uint32_t(block_size) <= (1u << 20);
+        if (!fp8_elems && copy_variant_ != kernels::kCopyTma && whole_blocks) {
             // one kernel: hash + probe + move
             kernels::ReadFusedLaunch R;
             R.key_bytes = ctx->ring_d + at_bytes;

@@ -187,6 +187,7 @@ class Connection {
     std::vector<std::shared_ptr<fabric::Mapping>> host_maps_;  // CPU view of host segments
     PendingHashes pending_hash_;  // allocated addr -> key fingerprint
     std::vector<uint64_t> pending_commit_;
+    bool ctrl_dirty_ = false;  // the server holds state (leases) that the next SYNC releases
     struct HostReg {
         size_t bytes;
         bool registered;
