@@ -400,8 +400,12 @@ def main():
         roof = peaks.get("hbm_gbs", 6650.0) / 2
         roof_name = "measured HBM copy bandwidth / 2 (read+write per payload byte)"
     else:
-        roof = 770.0 * world
-        roof_name = "measured NVLink peer bandwidth, 770 GB/s per direction per GPU"
+        # ring placement: every GPU pushes and is pushed to (write phase), pulls and is pulled
+        # from (read phase) at the same time; measured with both directions busy
+        # (bench/bidir.py, profiles/r1_nvlink_bidirectional_roofline.json): 703 / 667 GB/s
+        roof = world * 2.0 / (1.0 / 703.0 + 1.0 / 667.0)
+        roof_name = ("measured NVLink bandwidth with both directions busy: 703 GB/s push, "
+                     "667 GB/s pull per GPU (unidirectional: 711 / 779; nominal 900)")
 
     conn.close()
     server.stop()
