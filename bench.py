@@ -63,17 +63,21 @@ def reference_arm(args):
     flatbuffers and boost, none of which exist here."""
     why = None
     ref = os.path.join(ROOT, "baseline", "_ref")
-    try:
-        sys.path.insert(0, ref)
-        import importlib
-
-        importlib.import_module("infinistore._infinistore")
-    except Exception as e:  # noqa: BLE001
-        why = (f"reference native module not buildable offline (needs libibverbs/libuv/"
-               f"flatbuffers/boost headers): {type(e).__name__}: {e}")
-    finally:
-        if ref in sys.path:
-            sys.path.remove(ref)
+    if not os.path.isdir(os.path.join(ref, "infinistore")):
+        why = ("baseline/_ref/infinistore is absent: the offline pip install of /root/reference "
+               "only yields its .py files and its native module cannot be built (no libibverbs, "
+               "libuv, flatbuffers, boost headers on this image)")
+    else:
+        # Import the reference in a clean interpreter (cwd and PYTHONPATH outside this repo),
+        # so that nothing of this repo - in particular its `infinistore` alias package - can
+        # stand in for the reference's own native module.
+        env = dict(os.environ, PYTHONPATH=ref)
+        r = subprocess.run([sys.executable, "-c", "import infinistore._infinistore"],
+                           cwd="/tmp", env=env, capture_output=True, text=True, timeout=300)
+        if r.returncode != 0:
+            last = (r.stderr.strip().splitlines() or ["import failed"])[-1]
+            why = ("reference native module not buildable offline (needs libibverbs/libuv/"
+                   "flatbuffers/boost headers): " + last)
     if why is None:
         why = "reference imported but needs an active mlx5 RDMA port, absent on this box"
     print(json.dumps({"impl": "reference", "unavailable": why[:300]}))
