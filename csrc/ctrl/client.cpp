@@ -95,15 +95,15 @@ inline uint64_t now_ns() {
 }  // namespace
 
 void PendingHashes::grow() {
-    std::vector<Slot> old;
+    std::vector<Entry> old;
     old.swap(slots_);
-    slots_.assign(old.empty() ? 1024 : old.size() * 2, Slot{});
+    slots_.assign(old.empty() ? 1024 : old.size() * 2, Entry{});
     count_ = 0;
     for (auto& sl : old)
-        if (sl.addr) put(sl.addr, sl.h);
+        if (sl.addr) map_put(sl.addr, sl.h);
 }
 
-void PendingHashes::put(uint64_t addr, const KeyHash& h) {
+void PendingHashes::map_put(uint64_t addr, const KeyHash& h) {
     if ((count_ + 1) * 2 > slots_.size()) grow();
     const size_t mask = slots_.size() - 1;
     size_t i = mix(addr) & mask;
@@ -113,8 +113,8 @@ void PendingHashes::put(uint64_t addr, const KeyHash& h) {
     slots_[i].h = h;
 }
 
-bool PendingHashes::take(uint64_t addr, KeyHash* out) {
-    if (slots_.empty()) return false;
+bool PendingHashes::map_take(uint64_t addr, KeyHash* out) {
+    if (slots_.empty() || count_ == 0) return false;
     const size_t mask = slots_.size() - 1;
     size_t i = mix(addr) & mask;
     while (slots_[i].addr != addr) {
@@ -136,6 +136,27 @@ bool PendingHashes::take(uint64_t addr, KeyHash* out) {
     slots_[i].addr = 0;
     --count_;
     return true;
+}
+
+void PendingHashes::spill() {
+    for (size_t i = head_; i < fifo_.size(); ++i) map_put(fifo_[i].addr, fifo_[i].h);
+    fifo_.clear();
+    head_ = 0;
+}
+
+bool PendingHashes::take(uint64_t addr, KeyHash* out) {
+    if (head_ < fifo_.size()) {
+        if (fifo_[head_].addr == addr) {  // in allocation order: the common case
+            *out = fifo_[head_].h;
+            if (++head_ == fifo_.size()) {
+                fifo_.clear();
+                head_ = 0;
+            }
+            return true;
+        }
+        spill();  // out of order: from here on look the blocks up by address
+    }
+    return map_take(addr, out);
 }
 
 // Per-device data-plane state.
@@ -402,12 +423,19 @@ void Connection::close() {
 // One request/response exchange.  fixed_payload: bytes following the code on success, or
 // kBlobPayload for "u32 length + blob".
 int Connection::transact(char op, const void* body, size_t len, int32_t* code,
-                         std::vector<uint8_t>* payload, size_t fixed_payload) {
+                         std::vector<uint8_t>* payload, size_t fixed_payload,
+                         const std::vector<uint8_t>* prefix) {
     std::lock_guard<std::mutex> lk(sock_mu_);
     if (fd_ < 0) return -1;
     Header h{kMagic, op, uint32_t(len)};
-    iovec iov[2] = {{&h, sizeof(h)}, {const_cast<void*>(body), len}};
-    if (!send_all(fd_, iov, len ? 2 : 1)) {
+    // `prefix`: already framed reply-less messages (COMMIT) that go out in the same segment
+    iovec iov[3];
+    int niov = 0;
+    if (prefix && !prefix->empty())
+        iov[niov++] = iovec{const_cast<uint8_t*>(prefix->data()), prefix->size()};
+    iov[niov++] = iovec{&h, sizeof(h)};
+    if (len) iov[niov++] = iovec{const_cast<void*>(body), len};
+    if (!send_all(fd_, iov, niov)) {
         fail(std::string("send ") + op_name(op) + ": " + std::strerror(errno));
         return -1;
     }
@@ -521,10 +549,29 @@ int Connection::sync_local() {
         }
     }
     if (drain_devices() != 0) return -1;
-    if (flush_commits() != 0) return -1;
+    // COMMIT (no reply) and SYNC travel in one send: one syscall, one server wake-up
+    std::vector<uint64_t> addrs;
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        addrs.swap(pending_commit_);
+    }
+    std::vector<uint8_t> framed;
+    constexpr size_t kInline = 128 * 1024;  // addresses; larger lists use the chunked path
+    if (!addrs.empty() && addrs.size() <= kInline) {
+        std::vector<uint8_t> buf(align_up(addrs.size() * 8 + 128, 8));
+        fb::Builder b(buf.data(), buf.size());
+        encode_remote_meta(b, {}, 0, 0, addrs.data(), addrs.size(), kOpCommit);
+        framed.resize(sizeof(Header) + b.size());
+        Header ch{kMagic, kOpCommit, uint32_t(b.size())};
+        std::memcpy(framed.data(), &ch, sizeof(ch));
+        std::memcpy(framed.data() + sizeof(ch), b.data(), b.size());
+    } else if (!addrs.empty() && send_commit(addrs.data(), addrs.size()) != 0) {
+        return -1;
+    }
     int32_t code = 0;
     std::vector<uint8_t> p;
-    if (transact(kOpSync, nullptr, 0, &code, &p, sizeof(uint32_t)) != 0 || code != kFinish)
+    if (transact(kOpSync, nullptr, 0, &code, &p, sizeof(uint32_t), &framed) != 0 ||
+        code != kFinish)
         return -1;
     {
         std::lock_guard<std::mutex> lk(mu_);
@@ -548,6 +595,22 @@ int Connection::sync_rdma() {
     return r < 0 ? r : 0;
 }
 
+int Connection::send_commit(const uint64_t* addrs, size_t count) {
+    // chunk so that one message stays far below the body cap
+    constexpr size_t kChunk = 256 * 1024;
+    for (size_t at = 0; at < count; at += kChunk) {
+        const size_t n = std::min(kChunk, count - at);
+        std::vector<uint8_t> buf(align_up(n * 8 + 128, 8));
+        fb::Builder b(buf.data(), buf.size());
+        encode_remote_meta(b, {}, 0, 0, addrs + at, n, kOpCommit);
+        if (send_only(kOpCommit, b.data(), b.size()) != 0) {
+            fail("commit: send failed");
+            return -1;
+        }
+    }
+    return 0;
+}
+
 int Connection::flush_commits() {
     std::vector<uint64_t> addrs;
     {
@@ -555,19 +618,7 @@ int Connection::flush_commits() {
         addrs.swap(pending_commit_);
     }
     if (addrs.empty()) return 0;
-    // chunk so that one message stays far below the body cap
-    constexpr size_t kChunk = 256 * 1024;
-    for (size_t at = 0; at < addrs.size(); at += kChunk) {
-        const size_t n = std::min(kChunk, addrs.size() - at);
-        std::vector<uint8_t> buf(align_up(n * 8 + 128, 8));
-        fb::Builder b(buf.data(), buf.size());
-        encode_remote_meta(b, {}, 0, 0, addrs.data() + at, n, kOpCommit);
-        if (send_only(kOpCommit, b.data(), b.size()) != 0) {
-            fail("commit: send failed");
-            return -1;
-        }
-    }
-    return 0;
+    return send_commit(addrs.data(), addrs.size());
 }
 
 // One control-plane message holds at most kMaxBody bytes: large key lists are sent in chunks.

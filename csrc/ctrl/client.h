@@ -38,23 +38,29 @@ struct KeyOffset {
     uint64_t offset;  // bytes from the tensor base
 };
 
-// addr -> key fingerprint of blocks that were allocated but not written yet.  Open
-// addressing with backward-shift deletion: entries live for microseconds (allocate ->
-// write), and the write path looks one up per block, so this must be a few ns per op.
+// addr -> key fingerprint of blocks that were allocated but not written yet.
+// Blocks are almost always written in the order they were allocated, so the entries sit in a
+// FIFO and `take` pops the head (a few ns per block on the write hot path); anything out of
+// order falls back to an open-addressing map with backward-shift deletion.
 class PendingHashes {
    public:
-    void put(uint64_t addr, const KeyHash& h);
+    void put(uint64_t addr, const KeyHash& h) { fifo_.push_back(Entry{addr, h}); }
     bool take(uint64_t addr, KeyHash* out);  // find + erase
-    size_t size() const { return count_; }
+    size_t size() const { return (fifo_.size() - head_) + count_; }
 
    private:
-    struct Slot {
+    struct Entry {
         uint64_t addr = 0;  // 0 = empty (block addresses are never 0)
         KeyHash h{};
     };
+    void spill();  // move the FIFO into the map
+    void map_put(uint64_t addr, const KeyHash& h);
+    bool map_take(uint64_t addr, KeyHash* out);
     void grow();
     static size_t mix(uint64_t a) { return size_t((a * 0x9e3779b97f4a7c15ull) >> 20); }
-    std::vector<Slot> slots_;
+    std::vector<Entry> fifo_;
+    size_t head_ = 0;
+    std::vector<Entry> slots_;
     size_t count_ = 0;
 };
 
@@ -147,12 +153,14 @@ class Connection {
 
     // control plane
     int transact(char op, const void* body, size_t len, int32_t* code,
-                 std::vector<uint8_t>* payload, size_t fixed_payload);
+                 std::vector<uint8_t>* payload, size_t fixed_payload,
+                 const std::vector<uint8_t>* prefix = nullptr);
     int send_only(char op, const void* body, size_t len);
     int refresh_pool_map();
     int lookup_blocks(char op, const std::vector<KeyOffset>& blocks, int block_size,
                       std::vector<RemoteBlock>& out);
     int flush_commits();
+    int send_commit(const uint64_t* addrs, size_t count);
 
     // data plane
     DevCtx* dev_ctx(int device);

@@ -15,6 +15,8 @@
 
 #include <cuda_runtime_api.h>
 
+#include <unistd.h>
+
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -789,6 +791,35 @@ PYBIND11_MODULE(_infinistore, m) {
         const std::string s = key;
         const KeyHash h = hash_key(reinterpret_cast<const uint8_t*>(s.data()), s.size());
         return py::make_tuple(h.h1, h.h2);
+    });
+    t.def("fd_pass_selftest", [] {
+        // SCM_RIGHTS round trip over the abstract unix socket used for VMM handles: the
+        // "server" hands out the read end of a pipe, the "client" reads through it.
+        int p[2];
+        if (pipe(p) != 0) return false;
+        (void)!write(p[1], "hello", 5);
+        fabric::FdServer srv;
+        std::string err;
+        const std::string name = "istore_b200_selftest_" + std::to_string(getpid());
+        const int rd = p[0];
+        bool ok = srv.start(name,
+                            [rd](int req, std::vector<int>* fds, uint64_t* payload) {
+                                fds->push_back(dup(rd));
+                                *payload = uint64_t(req) * 2;
+                                return true;
+                            },
+                            &err);
+        std::vector<int> fds;
+        uint64_t payload = 0;
+        ok = ok && fabric::fd_request(name, 21, &fds, &payload, &err) && fds.size() == 1 &&
+             payload == 42;
+        char buf[8] = {0};
+        ok = ok && read(fds[0], buf, 5) == 5 && std::memcmp(buf, "hello", 5) == 0;
+        for (int fd : fds) close(fd);
+        srv.stop();
+        close(p[0]);
+        close(p[1]);
+        return ok;
     });
     t.def("header_size", [] { return sizeof(Header); });
     t.def("conn_info_size", [] { return sizeof(ConnInfo); });

@@ -145,3 +145,8 @@ def test_hash_is_stable_and_nonzero():
     assert len(seen) == 20000
     for n in range(0, 40):  # every tail length of the 16-byte loop
         assert T.hash_key(b"a" * n) != T.hash_key(b"a" * n + b"\0")
+
+
+def test_fd_passing_side_channel():
+    """VMM / multicast handles travel as POSIX fds over an abstract unix socket (SCM_RIGHTS)."""
+    assert T.fd_pass_selftest()
