@@ -29,6 +29,9 @@ struct ServerConfig {
     size_t index_slots = 0;                // device-index entries per segment (0 = auto)
     size_t replica_bytes = 0;              // NVLS-replicated region per GPU (0 = none)
     std::vector<int> replica_devices;      // GPUs holding a replica (default: all visible)
+    bool evict = false;                    // full pool: evict least-recently-used blocks
+                                           // instead of answering 507 (reference: never)
+    double evict_ratio = 0.05;             // fraction of the pool freed per eviction round
 };
 
 struct ClientConfig {

@@ -66,7 +66,7 @@ IS_HD uint64_t hash_bytes(const uint8_t* p, size_t len, uint64_t seed) {
 }
 
 struct KeyHash {
-    uint64_t h1;  // table slot selector; never 0 (0 marks an empty slot)
+    uint64_t h1;  // bucket selector and fingerprint; never 0 (0 marks an empty index way)
     uint64_t h2;  // verifier
 };
 

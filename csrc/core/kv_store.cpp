@@ -14,6 +14,23 @@ Block*& KVStore::inflight_slot(uint32_t seg, uint64_t offset) {
     return v[offset / pool.granule()];
 }
 
+void KVStore::lru_push_front(Block* b) {
+    b->lru_prev = nullptr;
+    b->lru_next = lru_head_;
+    if (lru_head_) lru_head_->lru_prev = b;
+    lru_head_ = b;
+    if (!lru_tail_) lru_tail_ = b;
+    b->in_lru = true;
+}
+
+void KVStore::lru_unlink(Block* b) {
+    if (!b->in_lru) return;
+    (b->lru_prev ? b->lru_prev->lru_next : lru_head_) = b->lru_next;
+    (b->lru_next ? b->lru_next->lru_prev : lru_tail_) = b->lru_prev;
+    b->lru_prev = b->lru_next = nullptr;
+    b->in_lru = false;
+}
+
 int KVStore::reserve(const std::vector<std::string_view>& keys, size_t size, int device_hint,
                      uint64_t conn, std::vector<RemoteBlock>& out) {
     out.assign(keys.size(), RemoteBlock{0, 0, 0});
@@ -59,6 +76,7 @@ size_t KVStore::commit(const uint64_t* addrs, size_t n) {
         if (!b || b->offset != off) continue;  // unknown / already committed: ignored
         b->committed = true;
         b->owner = 0;
+        lru_push_front(b);
         slot = nullptr;
         --inflight_count_;
         ++done;
@@ -67,7 +85,7 @@ size_t KVStore::commit(const uint64_t* addrs, size_t n) {
 }
 
 int KVStore::lookup(const std::vector<std::string_view>& keys, size_t need,
-                    std::vector<RemoteBlock>& out, std::vector<BlockPtr>* lease) const {
+                    std::vector<RemoteBlock>& out, std::vector<BlockPtr>* lease) {
     out.clear();
     out.reserve(keys.size());
     for (auto k : keys) {
@@ -76,13 +94,17 @@ int KVStore::lookup(const std::vector<std::string_view>& keys, size_t need,
             out.clear();
             return kKeyNotFound;
         }
-        const Block& b = *it->second;
+        Block& b = *it->second;
         if (b.size < need) {  // never let a reader run past what was written
             out.clear();
             return kInvalidReq;
         }
         out.push_back(RemoteBlock{b.seg + 1, b.gen, b.addr()});
         if (lease) lease->push_back(it->second);
+        if (lru_head_ != &b) {
+            lru_unlink(&b);
+            lru_push_front(&b);
+        }
     }
     return kFinish;
 }
@@ -124,8 +146,33 @@ size_t KVStore::drop_uncommitted(uint64_t conn) {
     return n;
 }
 
+size_t KVStore::evict(size_t bytes, bool replica, std::vector<BlockPtr>& victims) {
+    size_t freed = 0;
+    Block* b = lru_tail_;
+    while (b && freed < bytes) {
+        Block* more_recent = b->lru_prev;
+        auto it = map_.find(*b->key);
+        const bool in_replica = mm_->pool(b->seg).device() == kReplicaDevice;
+        if (it != map_.end() && in_replica == replica &&
+            it->second.use_count() == 1) {  // nobody is reading it
+            const size_t g = mm_->pool(b->seg).granule();
+            freed += (size_t(b->size) + g - 1) / g * g;
+            lru_unlink(b);
+            b->evicted_hash =
+                hash_key(reinterpret_cast<const uint8_t*>(b->key->data()), b->key->size());
+            victims.push_back(std::move(it->second));
+            map_.erase(it);  // frees the node that owns *b->key; victims keeps the block alive
+            victims.back()->key = nullptr;
+            ++evicted_;
+        }
+        b = more_recent;
+    }
+    return freed;
+}
+
 size_t KVStore::purge() {
     const size_t n = map_.size();
+    lru_head_ = lru_tail_ = nullptr;
     for (auto& seg : inflight_) std::fill(seg.begin(), seg.end(), nullptr);
     inflight_count_ = 0;
     map_.clear();

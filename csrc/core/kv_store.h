@@ -9,7 +9,9 @@
 //     transfers are in flight;
 //   * get_match_last_index replays the reference's exact binary search (C7).
 // Additions: per-connection ownership of uncommitted blocks so that a writer that dies
-// before committing does not leave a permanently reserved key.
+// before committing does not leave a permanently reserved key, and an
+// LRU order over the committed blocks so that a full pool can evict instead of answering
+// 507 until an operator purges it (the reference has no eviction).
 #pragma once
 
 #include <cstdint>
@@ -34,6 +36,10 @@ struct Block {
     bool committed = false;
     uint64_t owner = 0;  // connection id that reserved it (0 once committed)
     const std::string* key = nullptr;  // the map node's key (node addresses are stable)
+    Block* lru_prev = nullptr;  // towards more recently used; linked only while committed
+    Block* lru_next = nullptr;  // towards less recently used
+    bool in_lru = false;
+    KeyHash evicted_hash{0, 0};  // fingerprint of the key, filled in when the block is evicted
     Block(MM* m, uint32_t s, uint64_t o, uint32_t sz, uint32_t g, uint64_t own)
         : mm(m), seg(s), offset(o), size(sz), gen(g), owner(own) {}
     ~Block() { mm->deallocate(seg, offset, size); }
@@ -69,14 +75,24 @@ class KVStore {
     // Locators of committed keys; kKeyNotFound if any key is missing or uncommitted.
     // `lease` receives references that keep the blocks alive until the caller drops them.
     // kInvalidReq if a stored block is smaller than `need` bytes.
+    // A hit makes the block the most recently used one.
     int lookup(const std::vector<std::string_view>& keys, size_t need,
-               std::vector<RemoteBlock>& out, std::vector<BlockPtr>* lease) const;
+               std::vector<RemoteBlock>& out, std::vector<BlockPtr>* lease);
     bool exists_committed(std::string_view key) const;
     bool present(std::string_view key) const { return map_.find(key) != map_.end(); }
     int match_last_index(const std::vector<std::string_view>& keys) const;
     // Drop every uncommitted block reserved by `conn` (connection closed).
     size_t drop_uncommitted(uint64_t conn);
     size_t purge();
+    // Remove least-recently-used committed blocks from the map until they cover at least
+    // `bytes` of pool space (rounded to granules) or none is left.  Blocks that a reader
+    // still leases are skipped.  The victims are handed to the caller, which must make them
+    // unreachable for device-side readers (index erase) BEFORE dropping the references -
+    // dropping the last reference returns the space to the pool.
+    // `replica`: take victims from the NVLS-replicated region (true) or from the ordinary
+    // pools (false) - space of one kind cannot serve requests for the other.
+    size_t evict(size_t bytes, bool replica, std::vector<BlockPtr>& victims);
+    uint64_t evicted() const { return evicted_; }
     size_t size() const { return map_.size(); }
     // Visit every committed block (checkpointing).
     template <typename F>
@@ -90,12 +106,17 @@ class KVStore {
     // In-flight (reserved, uncommitted) blocks are found by address in O(1): one slot per
     // allocation granule of every pool, holding the block that starts there.
     Block*& inflight_slot(uint32_t seg, uint64_t offset);
+    void lru_push_front(Block* b);
+    void lru_unlink(Block* b);
 
     MM* mm_;
     uint32_t next_gen_ = 1;
     std::unordered_map<std::string, BlockPtr, StrHash, StrEq> map_;
     std::vector<std::vector<Block*>> inflight_;  // [segment][granule]
     size_t inflight_count_ = 0;
+    Block* lru_head_ = nullptr;  // most recently used
+    Block* lru_tail_ = nullptr;  // eviction candidate
+    uint64_t evicted_ = 0;
 };
 
 }  // namespace istore

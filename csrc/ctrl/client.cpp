@@ -378,6 +378,7 @@ int Connection::init_connection(const ClientConfig& cfg) {
     }
     server_cuda_ = srv.lid & 1;
     server_hbm_ = srv.lid & 2;
+    server_evicts_ = srv.lid & 4;
     std::memcpy(server_uuid_, srv.gid, 16);
     if (!worker_.joinable()) {
         stop_ = false;
@@ -972,12 +973,12 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
     stats_.calls++;
 
     // the device index lives in segment 0
-    kernels::IndexEntry* table = nullptr;
+    kernels::IndexBucket* table = nullptr;
     uint64_t table_mask = 0;
     if (write && !segs_.empty() && segs_[0].index_slots) {
         if (uint8_t* p0 = seg_dev_ptr(ctx, 0)) {
-            table = reinterpret_cast<kernels::IndexEntry*>(p0 + segs_[0].index_off);
-            table_mask = segs_[0].index_slots - 1;
+            table = reinterpret_cast<kernels::IndexBucket*>(p0 + segs_[0].index_off);
+            table_mask = kernels::index_bucket_mask(segs_[0].index_slots);
         }
     }
 
@@ -1260,12 +1261,13 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             R.n = uint32_t(n);
             R.bytes = uint32_t(block_size);
             R.align_or = copy_variant_ == kernels::kCopyLdSt ? (align_or | 16) : align_or;
-            R.table = reinterpret_cast<const kernels::IndexEntry*>(m0->dev_ptr + segs_[0].index_off);
-            R.table_mask = segs_[0].index_slots - 1;
+            R.table = reinterpret_cast<const kernels::IndexBucket*>(m0->dev_ptr + segs_[0].index_off);
+            R.table_mask = kernels::index_bucket_mask(segs_[0].index_slots);
             R.nsegs = nsegs;
             for (uint32_t s = 0; s < nsegs; ++s) R.seg_base[s] = seg_base[s];
             R.status = ctx->status_d;
             R.max_ctas = grid_cap;
+            R.validate = server_evicts_;
             e = kernels::launch_kv_read_fused(R, stream);
             stats_.kernel_launches += 1;
         } else {
@@ -1274,8 +1276,8 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             Q.key_off = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_off);
             Q.key_len = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_len);
             Q.n = uint32_t(n);
-            Q.table = reinterpret_cast<const kernels::IndexEntry*>(m0->dev_ptr + segs_[0].index_off);
-            Q.table_mask = segs_[0].index_slots - 1;
+            Q.table = reinterpret_cast<const kernels::IndexBucket*>(m0->dev_ptr + segs_[0].index_off);
+            Q.table_mask = kernels::index_bucket_mask(segs_[0].index_slots);
             Q.nsegs = nsegs;
             for (uint32_t s = 0; s < nsegs; ++s) Q.seg_base[s] = seg_base[s];
             auto* out = reinterpret_cast<kernels::CopyDesc*>(
@@ -1285,6 +1287,9 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             Q.dst_base = base_ptr;
             Q.need_bytes = uint32_t(block_size);
             Q.status = ctx->status_d;
+            if (server_evicts_)
+                Q.found_at = reinterpret_cast<kernels::LookupLaunch::FoundAt*>(
+                    ctx->scratch + ctx->scratch_alloc(n * sizeof(kernels::LookupLaunch::FoundAt)));
             e = kernels::launch_index_lookup(Q, stream);
             if (e == cudaSuccess && fp8_elems) {
                 kernels::Fp8Launch F;
@@ -1306,6 +1311,16 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
                 e = kernels::launch_kv_copy(L, stream);
             }
             stats_.kernel_launches += 2;
+            if (e == cudaSuccess && Q.found_at) {
+                // the server evicts: the entries must still be the ones the lookup resolved
+                kernels::ValidateLaunch V;
+                V.found_at = Q.found_at;
+                V.n = uint32_t(n);
+                V.table = Q.table;
+                V.status = ctx->status_d;
+                e = kernels::launch_index_validate(V, stream);
+                stats_.kernel_launches += 1;
+            }
         }
         stats_.ns_launch += now_ns() - t_launch0;
         if (e != cudaSuccess) {
@@ -1345,8 +1360,8 @@ int Connection::match_via_device_index(const std::vector<std::string_view>& keys
     Q.key_off = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_off);
     Q.key_len = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_len);
     Q.n = uint32_t(n);
-    Q.table = reinterpret_cast<const kernels::IndexEntry*>(m0->dev_ptr + segs_[0].index_off);
-    Q.table_mask = segs_[0].index_slots - 1;
+    Q.table = reinterpret_cast<const kernels::IndexBucket*>(m0->dev_ptr + segs_[0].index_off);
+    Q.table_mask = kernels::index_bucket_mask(segs_[0].index_slots);
     const size_t words = (n + 31) / 32;
     Q.present = reinterpret_cast<uint32_t*>(ctx->scratch + ctx->scratch_alloc(words * 4));
     Q.ticket = reinterpret_cast<uint32_t*>(ctx->zeros + ctx->zeros_alloc(4));
@@ -1387,8 +1402,13 @@ int Connection::drain_devices() {
         }
         if (ctx.status_h[kernels::kStatMiss]) {
             fail("read: " + std::to_string(ctx.status_h[kernels::kStatMiss]) +
-                 " key(s) not found in the device index");
+                 " key(s) not found in the device index" +
+                 (ctx.status_h[kernels::kStatStale]
+                      ? " (" + std::to_string(ctx.status_h[kernels::kStatStale]) +
+                            " evicted while being read)"
+                      : std::string()));
             ctx.status_h[kernels::kStatMiss] = 0;
+            ctx.status_h[kernels::kStatStale] = 0;
             rc = -kKeyNotFound;
         }
         if (ctx.status_h[kernels::kStatPublishFail]) {

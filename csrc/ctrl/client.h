@@ -90,6 +90,7 @@ class Connection {
     void close();
     bool connected() const { return fd_ >= 0; }
     bool server_has_hbm() const { return server_hbm_; }
+    bool server_evicts() const { return server_evicts_; }
 
     // --- metadata
     int check_exist(const std::string& key);  // 0 = exists & committed, 1 = not, <0 error
@@ -206,6 +207,7 @@ class Connection {
     int copy_variant_ = 0;
     int max_ctas_ = 0;
     bool device_lookup_ = false;
+    bool server_evicts_ = false;  // device-path reads validate their index entries after the copy
     int streams_ = 4;
     int default_device_ = -1;
     ClientStats stats_;

@@ -46,6 +46,15 @@ bool set_nonblock(int fd) {
     const int fl = fcntl(fd, F_GETFL, 0);
     return fl >= 0 && fcntl(fd, F_SETFL, fl | O_NONBLOCK) == 0;
 }
+struct DevGuard {
+    int prev = -1;
+    explicit DevGuard(int dev) {
+        if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev) cudaSetDevice(dev);
+    }
+    ~DevGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
 size_t next_pow2(size_t v) {
     size_t p = 1;
     while (p < v) p <<= 1;
@@ -77,8 +86,9 @@ bool Server::add_segment(std::string* err) {
         device = cfg_.pool_devices.empty()
                      ? 0
                      : cfg_.pool_devices[next_pool_dev_++ % cfg_.pool_devices.size()];
-        // 2 slots per block keeps linear probing short; the table (segment 0 only) must also
-        // cover the blocks of segments added later by --auto-increase
+        // 2 entries per block: at half load a key's two 8-way buckets are practically never
+        // both full; the table (segment 0 only) must also cover the blocks of segments added
+        // later by --auto-increase
         const size_t growth = cfg_.auto_increase ? 8 : 1;
         size_t slots = cfg_.index_slots
                            ? next_pow2(cfg_.index_slots)
@@ -222,6 +232,14 @@ void Server::stop() {
     if (wake_fd_ >= 0) close(wake_fd_);
     listen_fd_ = epoll_fd_ = wake_fd_ = -1;
     store_->purge();
+    if (erase_buf_ || erase_stream_) {
+        DevGuard g(segs_.empty() ? -1 : segs_[0]->info().device);
+        if (erase_buf_) cudaFree(erase_buf_);
+        if (erase_stream_) cudaStreamDestroy(static_cast<cudaStream_t>(erase_stream_));
+        erase_buf_ = nullptr;
+        erase_stream_ = nullptr;
+        erase_cap_ = 0;
+    }
     segs_.clear();
 }
 
@@ -247,7 +265,69 @@ ServerStats Server::stats() {
     s.pool_bytes = mm_.total_bytes();
     s.used_bytes = mm_.used_bytes();
     s.segments = segs_.size();
+    s.evicted = store_->evicted();
     return s;
+}
+
+bool Server::erase_from_device_index(const std::vector<BlockPtr>& victims) {
+    if (segs_.empty()) return true;
+    const fabric::SegmentOwner& seg0 = *segs_[0];
+    if (seg0.info().kind != kSegDeviceIpc || !seg0.info().index_slots) return true;
+    DevGuard g(seg0.info().device);
+    std::vector<kernels::EraseRec> recs;
+    recs.reserve(victims.size());
+    for (auto& v : victims)
+        recs.push_back(kernels::EraseRec{v->evicted_hash.h1, v->evicted_hash.h2, v->addr()});
+    if (erase_cap_ < recs.size()) {
+        if (erase_buf_) cudaFree(erase_buf_);
+        erase_buf_ = nullptr;
+        erase_cap_ = std::max<size_t>(4096, next_pow2(recs.size()));
+        if (cudaMalloc(&erase_buf_, erase_cap_ * sizeof(kernels::EraseRec)) != cudaSuccess) {
+            erase_cap_ = 0;
+            (void)cudaGetLastError();
+            return false;
+        }
+    }
+    kernels::EraseLaunch E;
+    E.recs = static_cast<const kernels::EraseRec*>(erase_buf_);
+    E.n = uint32_t(recs.size());
+    E.table = reinterpret_cast<kernels::IndexBucket*>(static_cast<uint8_t*>(seg0.base()) +
+                                                     seg0.info().index_off);
+    E.table_mask = kernels::index_bucket_mask(seg0.info().index_slots);
+    // The space may be handed out again only once no reader can resolve the old entries.
+    // Own non-blocking stream: clients living in this process keep their kernels running.
+    if (!erase_stream_ &&
+        cudaStreamCreateWithFlags(reinterpret_cast<cudaStream_t*>(&erase_stream_),
+                                  cudaStreamNonBlocking) != cudaSuccess) {
+        erase_stream_ = nullptr;
+        (void)cudaGetLastError();
+        return false;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(erase_stream_);
+    const bool ok =
+        cudaMemcpyAsync(erase_buf_, recs.data(), recs.size() * sizeof(kernels::EraseRec),
+                        cudaMemcpyHostToDevice, st) == cudaSuccess &&
+        kernels::launch_index_erase(E, st) == cudaSuccess &&
+        cudaStreamSynchronize(st) == cudaSuccess;
+    if (!ok) LOG_ERROR("index erase failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return ok;
+}
+
+bool Server::evict_some(size_t want, bool replica) {
+    std::vector<BlockPtr> victims;
+    const size_t freed = store_->evict(want, replica, victims);
+    if (victims.empty()) return false;
+    if (!erase_from_device_index(victims)) {
+        // cannot prove the entries unreachable: keep the space reserved rather than risk a
+        // reader copying a reused block (the blocks leak until the next purge)
+        static std::vector<BlockPtr> quarantine;
+        quarantine.insert(quarantine.end(), victims.begin(), victims.end());
+        return false;
+    }
+    LOG_INFO("evicted %zu blocks (%zu KiB) from the %s", victims.size(), freed >> 10,
+             replica ? "replicated region" : "pool");
+    victims.clear();  // last references: the space returns to the pool
+    return true;
 }
 
 std::vector<SegmentInfo> Server::segments() {
@@ -262,15 +342,6 @@ std::vector<SegmentInfo> Server::segments() {
 namespace {
 constexpr char kDumpMagic[8] = {'I', 'S', 'T', 'O', 'R', 'E', '0', '1'};
 
-struct DevGuard {
-    int prev = -1;
-    explicit DevGuard(int dev) {
-        if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev) cudaSetDevice(dev);
-    }
-    ~DevGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
 }  // namespace
 
 long Server::dump(const std::string& path, std::string* err) {
@@ -416,9 +487,9 @@ long Server::load(const std::string& path, std::string* err) {
                 cudaMalloc(&rec_dev, sizeof(rec));
                 cudaMemcpy(rec_dev, &rec, sizeof(rec), cudaMemcpyHostToDevice);
                 L.recs = static_cast<const kernels::IndexEntry*>(rec_dev);
-                L.table = reinterpret_cast<kernels::IndexEntry*>(static_cast<uint8_t*>(seg0.base()) +
-                                                                seg0.info().index_off);
-                L.table_mask = seg0.info().index_slots - 1;
+                L.table = reinterpret_cast<kernels::IndexBucket*>(static_cast<uint8_t*>(seg0.base()) +
+                                                                 seg0.info().index_off);
+                L.table_mask = kernels::index_bucket_mask(seg0.info().index_slots);
                 L.done = scratch;
             }
             const cudaError_t e = kernels::launch_kv_copy(L, nullptr);
@@ -710,7 +781,8 @@ int Server::handle_exchange(Conn* c) {
     me.qpn = uint32_t(getpid());
     me.psn = uint32_t(segs_.size());
     std::memcpy(me.gid, fabric::process_uuid(), 16);
-    me.lid = uint16_t((fabric::cuda_available() ? 1 : 0) | (use_hbm_ ? 2 : 0));
+    me.lid = uint16_t((fabric::cuda_available() ? 1 : 0) | (use_hbm_ ? 2 : 0) |
+                      (cfg_.evict ? 4 : 0));
     me.mtu = kFabricVersion;
     reply(c, kFinish, &me, sizeof(me));
     return kFinish;
@@ -757,6 +829,16 @@ int Server::handle_allocate(Conn* c, bool local) {
     int code = store_->reserve(keys, size_t(block_size), hint, c->id, blocks);
     while (code == kOutOfMemory && maybe_extend())
         code = store_->reserve(keys, size_t(block_size), hint, c->id, blocks);
+    if (code == kOutOfMemory && cfg_.evict) {
+        // a full cache makes room for new blocks: least recently used first
+        const size_t granule = size_t(cfg_.minimal_allocate_size) << 10;
+        const size_t need = keys.size() * ((size_t(block_size) + granule - 1) / granule * granule);
+        const size_t want = std::max(need, size_t(double(mm_.total_bytes()) * cfg_.evict_ratio));
+        for (int round = 0; round < 16 && code == kOutOfMemory; ++round) {
+            if (!evict_some(want, hint == kReplicaDevice)) break;
+            code = store_->reserve(keys, size_t(block_size), hint, c->id, blocks);
+        }
+    }
     if (code != kFinish) {
         LOG_WARN("allocate of %zu x %d bytes failed: pool exhausted (%zu/%zu MiB used)",
                  keys.size(), block_size, mm_.used_bytes() >> 20, mm_.total_bytes() >> 20);

@@ -40,6 +40,7 @@ struct ServerStats {
     uint64_t pool_bytes = 0;
     uint64_t used_bytes = 0;
     uint64_t segments = 0;
+    uint64_t evicted = 0;           // blocks evicted since start
     uint64_t ops[128] = {0};        // per opcode
 };
 
@@ -83,6 +84,10 @@ class Server {
     void reply_blob(Conn* c, int32_t code, const void* blob, size_t len);
     bool add_segment(std::string* err);
     bool maybe_extend();
+    // Evict least-recently-used committed blocks covering `want` bytes: out of the map, out
+    // of the device index (erase kernel, synchronised), then back to the pool.
+    bool evict_some(size_t want, bool replica);
+    bool erase_from_device_index(const std::vector<BlockPtr>& victims);
 
     int handle_exchange(Conn* c);
     int handle_pool_map(Conn* c);
@@ -112,6 +117,9 @@ class Server {
     bool use_hbm_ = false;
     ServerStats stats_;
     std::vector<uint8_t> scratch_;  // reply serialisation buffer
+    void* erase_buf_ = nullptr;     // device staging of the erase kernel's records
+    size_t erase_cap_ = 0;          // records
+    void* erase_stream_ = nullptr;  // cudaStream_t
 };
 
 }  // namespace istore

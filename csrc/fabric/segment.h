@@ -5,7 +5,7 @@
 //   * kSegDeviceIpc : HBM on a pool GPU.  Clients on any GPU of the NVSwitch domain map it
 //     through a CUDA IPC handle and their kv_write / kv_read kernels address it directly
 //     with peer loads/stores over NVLink.  The tail of the mapping holds the device
-//     resident key index (open addressing, 32-byte entries, see kernels/index.cuh);
+//     resident key index (8-way buckets, 32 bytes per entry, see kernels/index.cuh);
 //   * kSegHostShm   : POSIX shared memory, the CPU-only plumbing backend and a host tier.
 //     Clients mmap it (and cudaHostRegister it when they own a GPU).
 // `rkey` of the reference becomes the segment id, `remote_addr` the byte offset.

@@ -9,11 +9,14 @@
 //                         (also non-monotone) input;
 //   * check_exist       : the same with one key.
 // One thread per key: the key bytes are hashed twice (core/hash.h, identical on host and
-// device) and the table — which lives in the pool GPU's HBM and is usually a PEER mapping
-// read over NVLink — is probed linearly.  An entry counts only once its tag has been
-// published with release.sys by the writer's kv_copy (acquire here).
+// device) and the key's two buckets of the table — which lives in the pool GPU's HBM and is
+// usually a PEER mapping read over NVLink — are searched (index.cuh).  An entry counts only
+// once its tag has been published with release semantics by the writer's kv_copy.
+// Also here: the eviction kernels (erase on the server side, post-copy validation on the
+// reader side).
 #include "../core/hash.h"
 #include "common.cuh"
+#include "index.cuh"
 #include "kernels.h"
 
 namespace istore::kernels {
@@ -23,49 +26,24 @@ namespace {
 using namespace dev;
 
 constexpr int kLookupThreads = 128;
-constexpr uint64_t kMaxProbe = 4096;
-
-struct Hit {
-    bool found;
-    uint64_t addr;
-    uint32_t size;
-};
-
-__device__ Hit probe(const IndexEntry* table, uint64_t mask, const KeyHash& kh) {
-    uint64_t slot = kh.h1 & mask;
-    const uint64_t limit = mask + 1 < kMaxProbe ? mask + 1 : kMaxProbe;
-    for (uint64_t p = 0; p < limit; ++p) {
-        const IndexEntry* e = table + slot;
-        // h1 and tag are fetched together (the acquire load does not depend on h1): a hit
-        // costs two fabric round trips, not three
-        const uint64_t h1 = ld_relaxed_sys_u64(&e->h1);
-        const uint32_t tag = ld_acquire_sys(&e->tag);
-        if (h1 == 0) break;  // empty slot terminates the probe sequence
-        if (h1 == kh.h1) {
-            if (tag == 0) break;  // reserved by a writer that has not committed yet
-            if (e->h2 == kh.h2) return Hit{true, e->addr, e->size};
-        }
-        slot = (slot + 1) & mask;
-    }
-    return Hit{false, 0, 0};
-}
-
 __global__ void __launch_bounds__(kLookupThreads)
     kv_index_lookup_kernel(const __grid_constant__ LookupLaunch a) {
     const uint32_t i = blockIdx.x * kLookupThreads + threadIdx.x;
     bool found = false;
     if (i < a.n) {
         const KeyHash kh = hash_key(a.key_bytes + a.key_off[i], a.key_len[i]);
-        const Hit h = probe(a.table, a.table_mask, kh);
-        found = h.found;
+        const idx::Found h = idx::find(a.table, a.table_mask, kh);
+        found = h.slot_plus1 != 0;
         if (a.out_descs) {
             uint64_t src = 0;
-            if (h.found && h.size >= a.need_bytes) {
+            if (found && h.size >= a.need_bytes) {
                 const uint32_t seg = uint32_t(h.addr >> 44) - 1;
                 if (seg < a.nsegs && a.seg_base[seg])
                     src = a.seg_base[seg] + (h.addr & ((1ull << 44) - 1));
             }
             a.out_descs[i] = CopyDesc{src, a.dst_base + a.dst_off[i]};
+            if (a.found_at)
+                a.found_at[i] = LookupLaunch::FoundAt{src ? h.slot_plus1 : 0u, h.tag};
         }
     }
     if (!a.present) return;
@@ -100,7 +78,43 @@ __global__ void __launch_bounds__(kLookupThreads)
     __threadfence_system();
 }
 
+// One thread per block that was read: the tag must be unchanged (see ValidateLaunch).
+__global__ void __launch_bounds__(kLookupThreads)
+    kv_index_validate_kernel(const __grid_constant__ ValidateLaunch a) {
+    const uint32_t i = blockIdx.x * kLookupThreads + threadIdx.x;
+    if (i >= a.n) return;
+    const LookupLaunch::FoundAt f = a.found_at[i];
+    if (!f.slot_plus1) return;  // a miss was counted by the lookup
+    if (!idx::still_valid(a.table, f.slot_plus1, f.tag)) {
+        atomicAdd(a.status + kStatMiss, 1u);
+        atomicAdd(a.status + kStatStale, 1u);
+    }
+}
+
+// One thread per evicted block (index.cuh: tag := 0, fence, h1 := 0).
+__global__ void __launch_bounds__(kLookupThreads)
+    kv_index_erase_kernel(const __grid_constant__ EraseLaunch a) {
+    const uint32_t i = blockIdx.x * kLookupThreads + threadIdx.x;
+    if (i >= a.n) return;
+    const EraseRec r = a.recs[i];
+    idx::erase(a.table, a.table_mask, r.h1, r.h2, r.addr);
+}
+
 }  // namespace
+
+cudaError_t launch_index_validate(const ValidateLaunch& a, cudaStream_t stream) {
+    if (a.n == 0) return cudaSuccess;
+    const unsigned grid = (a.n + kLookupThreads - 1) / kLookupThreads;
+    kv_index_validate_kernel<<<grid, kLookupThreads, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_index_erase(const EraseLaunch& a, cudaStream_t stream) {
+    if (a.n == 0) return cudaSuccess;
+    const unsigned grid = (a.n + kLookupThreads - 1) / kLookupThreads;
+    kv_index_erase_kernel<<<grid, kLookupThreads, 0, stream>>>(a);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_index_lookup(const LookupLaunch& a, cudaStream_t stream) {
     if (a.n == 0) return cudaSuccess;

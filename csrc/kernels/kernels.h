@@ -21,23 +21,46 @@ struct CopyDesc {
     uint64_t dst;
 };
 
-// Entry of the HBM-resident key index == record a writer publishes once the block's data
-// is visible system-wide.  Open addressing, linear probing, slot = h1 & mask.
-//   h1   : claimed with a 64-bit CAS (0 = empty slot)
-//   tag  : allocation generation, written last with release.sys; 0 = not yet committed
+// Record a writer publishes for one block once its data is visible system-wide.
 struct IndexEntry {
-    uint64_t h1;
+    uint64_t h1;    // 128-bit key fingerprint (core/hash.h)
     uint64_t h2;
     uint64_t addr;  // global block address: (segment+1) << 44 | offset
+    uint32_t tag;   // allocation generation (never 0)
+    uint32_t size;
+};
+static_assert(sizeof(IndexEntry) == 32, "index records are 32 bytes");
+
+// The HBM-resident key index: an array of 256-byte, 8-way buckets.  A key lives in one of
+// two buckets chosen by its fingerprint (index.cuh), in any way.  There are no probe chains,
+// so an evicted block's way simply becomes empty again - no tombstones, no degradation
+// under the steady churn of a full cache.
+//   h1[w] : claimed with a 64-bit CAS from 0 (empty).  All eight fingerprints of a bucket
+//           are one 64-byte read.
+//   tag   : written last with release semantics; 0 = claimed but not yet committed.
+//           Generations are unique per allocation, so "the tag I resolved is still there"
+//           proves that the block was not evicted (and the way reused) during a read.
+constexpr uint32_t kIndexWays = 8;
+struct IndexWay {
+    uint64_t h2;
+    uint64_t addr;
     uint32_t tag;
     uint32_t size;
 };
-static_assert(sizeof(IndexEntry) == 32, "index entries are 32 bytes");
+struct alignas(64) IndexBucket {
+    uint64_t h1[kIndexWays];
+    IndexWay way[kIndexWays];
+};
+static_assert(sizeof(IndexWay) == 24 && sizeof(IndexBucket) == 256, "index bucket layout");
+// An index of `slots` entries (a power of two, >= 8) has slots / 8 buckets; kernels take
+// the bucket mask.
+inline uint64_t index_bucket_mask(uint64_t slots) { return slots / kIndexWays - 1; }
 
 enum Status : int {
     kStatMiss = 0,         // blocks skipped by a read because the key was not in the index
     kStatPublishFail = 1,  // index insertions that found the table full
     kStatMatch = 2,        // result of the last match_last_index launch (int32)
+    kStatStale = 3,        // blocks whose index entry changed while they were read (evicted)
     kStatWords = 8,
 };
 
@@ -57,8 +80,8 @@ struct CopyLaunch {
     uint64_t align_or = 0;            // OR of every local address (pool blocks are granule aligned)
     // optional in-band commit (writes): publish recs[i] once block i has landed
     const IndexEntry* recs = nullptr;
-    IndexEntry* table = nullptr;
-    uint64_t table_mask = 0;
+    IndexBucket* table = nullptr;
+    uint64_t table_mask = 0;  // bucket mask
     uint32_t* done = nullptr;         // 3*n zeroed u32 of client-local device scratch
     uint32_t* status = nullptr;       // kStatWords u32, device-addressable
     int variant = kCopyAuto;
@@ -79,8 +102,8 @@ struct Fp8Launch {
     uint32_t elems = 0;   // bf16 elements per page
     uint32_t group = 128; // elements sharing one scale
     const IndexEntry* recs = nullptr;
-    IndexEntry* table = nullptr;
-    uint64_t table_mask = 0;
+    IndexBucket* table = nullptr;
+    uint64_t table_mask = 0;  // bucket mask
     uint32_t* done = nullptr;
     uint32_t* status = nullptr;
     int max_ctas = 0;
@@ -101,8 +124,8 @@ struct LookupLaunch {
     const uint32_t* key_off = nullptr;   // n byte offsets into key_bytes
     const uint32_t* key_len = nullptr;   // n lengths
     uint32_t n = 0;
-    const IndexEntry* table = nullptr;
-    uint64_t table_mask = 0;
+    const IndexBucket* table = nullptr;
+    uint64_t table_mask = 0;  // bucket mask
     // segment id -> mapped base pointer on the launching device
     static constexpr int kMaxSegs = 16;
     uint64_t seg_base[kMaxSegs] = {0};
@@ -117,8 +140,40 @@ struct LookupLaunch {
     uint32_t* status = nullptr;          // status[kStatMatch] receives the int32 result
     uint32_t* ticket = nullptr;          // zeroed u32 used to elect the last CTA
     bool want_match = false;
+    // optional: where every hit was found, for launch_index_validate after the copy
+    struct FoundAt {
+        uint32_t slot_plus1;  // 0 = miss
+        uint32_t tag;
+    };
+    FoundAt* found_at = nullptr;
 };
 cudaError_t launch_index_lookup(const LookupLaunch& a, cudaStream_t stream);
+
+// Optimistic-read validation (stores with eviction): after the copy, every entry must still
+// carry the tag the lookup saw; otherwise the block was evicted meanwhile and the bytes
+// just read may be another key's - counted in status[kStatMiss] and status[kStatStale].
+struct ValidateLaunch {
+    const LookupLaunch::FoundAt* found_at = nullptr;
+    uint32_t n = 0;
+    const IndexBucket* table = nullptr;
+    uint32_t* status = nullptr;
+};
+cudaError_t launch_index_validate(const ValidateLaunch& a, cudaStream_t stream);
+
+// Eviction: empty the ways of evicted blocks.  Runs on the pool GPU, from the server,
+// before the blocks' space is handed out again.
+struct EraseRec {
+    uint64_t h1;
+    uint64_t h2;
+    uint64_t addr;
+};
+struct EraseLaunch {
+    const EraseRec* recs = nullptr;  // device-addressable
+    uint32_t n = 0;
+    IndexBucket* table = nullptr;
+    uint64_t table_mask = 0;  // bucket mask
+};
+cudaError_t launch_index_erase(const EraseLaunch& a, cudaStream_t stream);
 
 // read_cache in one kernel: resolve the keys in the HBM index and move the pages.
 struct ReadFusedLaunch {
@@ -130,13 +185,14 @@ struct ReadFusedLaunch {
     uint32_t n = 0;
     uint32_t bytes = 0;                  // bytes per page; an index hit must hold at least this
     uint64_t align_or = 0;               // OR of every destination address
-    const IndexEntry* table = nullptr;
-    uint64_t table_mask = 0;
+    const IndexBucket* table = nullptr;
+    uint64_t table_mask = 0;  // bucket mask
     static constexpr int kMaxSegs = 16;
     uint64_t seg_base[kMaxSegs] = {0};
     uint32_t nsegs = 0;
     uint32_t* status = nullptr;          // status[kStatMiss] counts keys that were not found
     int max_ctas = 0;
+    bool validate = false;               // re-check every entry's tag after its copy (eviction)
 };
 cudaError_t launch_kv_read_fused(const ReadFusedLaunch& a, cudaStream_t stream);
 

@@ -7,19 +7,21 @@
 // RESOLVER warp that runs ahead of the copy warps: lane l hashes the key of the CTA's l-th
 // work item (core/hash.h), probes the index (ld.acquire.sys on peer memory) and hands the
 // pool address to the 256 copy threads through shared memory, double-buffered in rounds of
-// 32 items with named barriers.  The lookup latency (2-3 NVLink round trips) is paid once
+// 32 items with named barriers.  The lookup latency (2 NVLink round trips) is paid once
 // per CTA, overlapped with the copies of other CTAs and of kernels in other streams.
+// With a store that evicts (a.validate) the resolver re-checks every entry after its copy:
+// an optimistic read that reports a block evicted underneath it as a miss.
 #include <algorithm>
 
 #include "../core/hash.h"
 #include "copy_span.cuh"
+#include "index.cuh"
 #include "kernels.h"
 
 namespace istore::kernels {
 
 namespace {
 
-constexpr uint64_t kMaxProbe = 4096;
 constexpr int kRound = 32;
 // named barriers: full[p] (resolver -> copy warps), empty[p] (copy warps -> resolver)
 constexpr int kBarFull0 = 2, kBarEmpty0 = 4;
@@ -32,33 +34,25 @@ __device__ __forceinline__ void bar_arrive(int id) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kThreads) : "memory");
 }
 
-__device__ uint64_t resolve(const ReadFusedLaunch& a, uint32_t block) {
+struct Resolved {
+    uint64_t src;  // mapped pool address, 0 = miss
+    uint32_t slot_plus1;
+    uint32_t tag;
+};
+
+__device__ Resolved resolve(const ReadFusedLaunch& a, uint32_t block) {
     const KeyHash kh = hash_key(a.key_bytes + a.key_off[block], a.key_len[block]);
-    uint64_t slot = kh.h1 & a.table_mask;
-    const uint64_t limit = a.table_mask + 1 < kMaxProbe ? a.table_mask + 1 : kMaxProbe;
-    for (uint64_t p = 0; p < limit; ++p) {
-        const IndexEntry* e = a.table + slot;
-        // h1 and tag are fetched together (the acquire load does not depend on h1): a hit
-        // costs two fabric round trips, not three
-        const uint64_t h1 = ld_relaxed_sys_u64(&e->h1);
-        const uint32_t tag = ld_acquire_sys(&e->tag);
-        if (h1 == 0) return 0;
-        if (h1 == kh.h1) {
-            if (tag == 0) return 0;  // reserved, not committed
-            if (e->h2 == kh.h2) {
-                const uint64_t addr = e->addr;
-                const uint32_t seg = uint32_t(addr >> 44) - 1;
-                if (e->size < a.bytes || seg >= a.nsegs || !a.seg_base[seg]) return 0;
-                return a.seg_base[seg] + (addr & ((1ull << 44) - 1));
-            }
-        }
-        slot = (slot + 1) & a.table_mask;
-    }
-    return 0;
+    const idx::Found f = idx::find(a.table, a.table_mask, kh);
+    if (!f.slot_plus1) return Resolved{0, 0, 0};
+    const uint32_t seg = uint32_t(f.addr >> 44) - 1;
+    if (f.size < a.bytes || seg >= a.nsegs || !a.seg_base[seg]) return Resolved{0, 0, 0};
+    return Resolved{a.seg_base[seg] + (f.addr & ((1ull << 44) - 1)), f.slot_plus1, f.tag};
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kThreads)
+// 4 CTAs per SM (56 registers): the 16 fingerprints of idx::find cost the resolver warp a
+// few spilled words, not the copy warps their occupancy
+__global__ void __launch_bounds__(kThreads, 4)
     kv_read_fused_kernel(const __grid_constant__ ReadFusedLaunch a, uint32_t chunk, uint32_t cpb) {
     __shared__ uint64_t src_of[2][kRound];
     const uint32_t total = a.n * cpb;
@@ -67,17 +61,49 @@ __global__ void __launch_bounds__(kThreads)
 
     if (threadIdx.x >= kLdStThreads) {  // ---- resolver warp
         const uint32_t lane = threadIdx.x - kLdStThreads;
+        // what this lane resolved in the two rounds in flight, re-checked once the copy warps
+        // are done with the round (a.validate: the server may evict a block under a reader)
+        uint32_t slot0 = 0, tag0 = 0, slot1 = 0, tag1 = 0;  // scalars: no local memory
+        auto recheck = [&](uint32_t p) {
+            const uint32_t slot = p ? slot1 : slot0, tag = p ? tag1 : tag0;
+            if (slot && !idx::still_valid(a.table, slot, tag)) {
+                atomicAdd(a.status + kStatMiss, 1u);
+                atomicAdd(a.status + kStatStale, 1u);
+            }
+            if (p)
+                slot1 = 0;
+            else
+                slot0 = 0;
+        };
         for (uint32_t r = 0; r < rounds; ++r) {
             const uint32_t p = r & 1;
-            if (r >= 2) bar_sync(kBarEmpty0 + p);  // copy warps are done with this buffer
+            if (r >= 2) {
+                bar_sync(kBarEmpty0 + p);  // copy warps are done with this buffer
+                if (a.validate) recheck(p);
+            }
             const uint32_t k = r * kRound + lane;
             if (k < count) {
                 const uint32_t item = blockIdx.x + k * gridDim.x;
-                const uint64_t src = resolve(a, item / cpb);
-                src_of[p][lane] = src;
-                if (src == 0 && item % cpb == 0 && a.status) atomicAdd(a.status + kStatMiss, 1u);
+                const Resolved res = resolve(a, item / cpb);
+                src_of[p][lane] = res.src;
+                if (res.src == 0 && item % cpb == 0 && a.status) atomicAdd(a.status + kStatMiss, 1u);
+                // every chunk of a block is copied at a different time: each item re-checks
+                // the entry after its own copy
+                if (p) {
+                    slot1 = res.slot_plus1;
+                    tag1 = res.tag;
+                } else {
+                    slot0 = res.slot_plus1;
+                    tag0 = res.tag;
+                }
             }
             bar_arrive(kBarFull0 + p);
+        }
+        if (a.validate) {  // the last (up to) two rounds
+            for (uint32_t r = rounds >= 2 ? rounds - 2 : 0; r < rounds; ++r) {
+                bar_sync(kBarEmpty0 + (r & 1));
+                recheck(r & 1);
+            }
         }
         return;
     }
@@ -100,7 +126,7 @@ __global__ void __launch_bounds__(kThreads)
                 copy_span<VEC>(dst, src, len);
             }
         }
-        if (r + 2 < rounds) bar_arrive(kBarEmpty0 + p);
+        if (r + 2 < rounds || a.validate) bar_arrive(kBarEmpty0 + p);
     }
 }
 

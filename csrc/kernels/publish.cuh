@@ -8,7 +8,7 @@
 // Two phases, run by a dedicated CONTROL WARP of every CTA so that the copy warps never
 // wait on a fabric round trip (measured: doing the whole insertion after the data cost
 // +30 us per 32 MB launch over NVLink, profiles/r1_launch_overhead_v1.json):
-//   claim  (kernel start, overlaps the copy): CAS the slot's h1 from 0 (one NVLink round
+//   claim  (kernel start, overlaps the copy): CAS a way's h1 from 0 (one NVLink round
 //          trip), fill h2/addr/size with posted stores; tag stays 0 = invisible.
 //   commit (after the block's last chunk has landed): one posted st.release.sys of the tag.
 // Chunks of one block may be moved by several CTAs: completion is counted with
@@ -16,6 +16,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "index.cuh"
 #include "kernels.h"
 
 namespace istore::kernels {
@@ -24,8 +25,8 @@ using namespace dev;
 
 struct Publish {
     const IndexEntry* recs;  // one record per block (device-addressable, may be host memory)
-    IndexEntry* table;
-    uint64_t mask;
+    IndexBucket* table;
+    uint64_t mask;  // bucket mask
     uint32_t* scratch;  // 3*n zeroed u32 in client-local device memory: done | slot+1 | tag
     uint32_t* status;
     uint32_t n;
@@ -44,32 +45,13 @@ __device__ inline unsigned long long globaltimer_ns() {
     return t;
 }
 
-// Reserve a slot for `rec`.  Returns slot + 1, or 0 when nothing is to be committed (the
-// key is already published - first writer wins - or the table is full).
+// Reserve a way for `rec` (index.cuh).  Returns slot + 1, or 0 when nothing is to be
+// committed (the key is already published - first writer wins - or its buckets are full).
 __device__ inline uint32_t claim_entry(const Publish& pub, const IndexEntry& rec) {
-    uint64_t slot = rec.h1 & pub.mask;
-    for (uint64_t probe = 0; probe <= pub.mask; ++probe) {
-        IndexEntry* e = pub.table + slot;
-        // Atomics on one address are serialised at the L2 that owns it whatever the scope
-        // qualifier, so a local table may be claimed at gpu scope even if peers claim too.
-        const uint64_t cur = pub.sys ? cas_relaxed_sys_u64(&e->h1, 0, rec.h1)
-                                     : cas_relaxed_gpu_u64(&e->h1, 0, rec.h1);
-        if (cur == 0) {  // slot is ours; fields are posted stores, tag stays 0
-            e->h2 = rec.h2;
-            e->addr = rec.addr;
-            e->size = rec.size;
-            return uint32_t(slot) + 1;
-        }
-        if (cur == rec.h1) {
-            // same key already present, or a 64-bit collision with another key; either way
-            // the authoritative copy is the server's map
-            const uint32_t tag = ld_acquire_sys(&e->tag);
-            if (tag != 0 && e->h2 == rec.h2) return 0;
-        }
-        slot = (slot + 1) & pub.mask;
-    }
-    if (pub.status) atomicAdd(pub.status + kStatPublishFail, 1u);
-    return 0;
+    bool full = false;
+    const uint32_t s = idx::claim(pub.table, pub.mask, rec, pub.sys, &full);
+    if (full && pub.status) atomicAdd(pub.status + kStatPublishFail, 1u);
+    return s;
 }
 
 // The caller has just executed fence.acq_rel.sys; fence + relaxed store is a release
@@ -77,11 +59,7 @@ __device__ inline uint32_t claim_entry(const Publish& pub, const IndexEntry& rec
 // the epilogue, profiles/r1_ncu_kv_copy_*.txt).
 __device__ inline void commit_entry(const Publish& pub, uint32_t slot_plus1, uint32_t tag) {
     if (!slot_plus1 || (pub.debug & 4)) return;
-    uint32_t* p = &pub.table[slot_plus1 - 1].tag;
-    if (pub.sys)
-        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(tag) : "memory");
-    else
-        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(tag) : "memory");
+    idx::commit(pub.table, slot_plus1, tag, pub.sys);
 }
 
 constexpr int kCtrlBarrier = 1;  // named barrier shared by the copy warps and the control warp

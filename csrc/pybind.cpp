@@ -243,6 +243,7 @@ py::dict stats_dict(const ServerStats& s) {
     d["pool_bytes"] = s.pool_bytes;
     d["used_bytes"] = s.used_bytes;
     d["segments"] = s.segments;
+    d["evicted"] = s.evicted;
     py::dict ops;
     for (int i = 0; i < 128; ++i)
         if (s.ops[i]) ops[py::str(op_name(char(i)))] = s.ops[i];
@@ -292,6 +293,8 @@ PYBIND11_MODULE(_infinistore, m) {
         .def_readwrite("prealloc_bytes", &ServerConfig::prealloc_bytes)
         .def_readwrite("index_slots", &ServerConfig::index_slots)
         .def_readwrite("replica_bytes", &ServerConfig::replica_bytes)
+        .def_readwrite("evict", &ServerConfig::evict)
+        .def_readwrite("evict_ratio", &ServerConfig::evict_ratio)
         .def_readwrite("replica_devices", &ServerConfig::replica_devices);
 
     // ------------------------------------------------------------ client
@@ -450,6 +453,7 @@ PYBIND11_MODULE(_infinistore, m) {
         .def("set_streams", &Connection::set_streams)
         .def("device_lookup", &Connection::device_lookup)
         .def("server_has_hbm", &Connection::server_has_hbm)
+        .def("server_evicts", &Connection::server_evicts)
         .def("last_error", &Connection::last_error)
         .def("segments",
              [](Connection& c) {
@@ -643,6 +647,8 @@ PYBIND11_MODULE(_infinistore, m) {
     k.attr("STAT_MISS") = int(kernels::kStatMiss);
     k.attr("STAT_PUBLISH_FAIL") = int(kernels::kStatPublishFail);
     k.attr("STAT_MATCH") = int(kernels::kStatMatch);
+    k.attr("STAT_STALE") = int(kernels::kStatStale);
+    k.attr("INDEX_WAYS") = int(kernels::kIndexWays);
     k.attr("STAT_WORDS") = int(kernels::kStatWords);
     k.def(
         "kv_copy",
@@ -655,7 +661,7 @@ PYBIND11_MODULE(_infinistore, m) {
             L.bytes = bytes;
             L.align_or = align_or;
             L.recs = as_ptr<const kernels::IndexEntry>(recs);
-            L.table = as_ptr<kernels::IndexEntry>(table);
+            L.table = as_ptr<kernels::IndexBucket>(table);
             L.table_mask = table_mask;
             L.done = as_ptr<uint32_t>(done);
             L.status = as_ptr<uint32_t>(status);
@@ -677,13 +683,15 @@ PYBIND11_MODULE(_infinistore, m) {
         [](uint64_t key_bytes, uint64_t key_off, uint64_t key_len, uint32_t n, uint64_t table,
            uint64_t table_mask, const std::vector<uint64_t>& seg_base, uint64_t out_descs,
            uint64_t dst_off, uint64_t dst_base, uint32_t need_bytes, uint64_t present,
-           uint64_t status, uint64_t ticket, bool want_match, uint64_t stream) {
+           uint64_t status, uint64_t ticket, bool want_match, uint64_t stream,
+           uint64_t found_at) {
             kernels::LookupLaunch Q;
+            Q.found_at = as_ptr<kernels::LookupLaunch::FoundAt>(found_at);
             Q.key_bytes = as_ptr<const uint8_t>(key_bytes);
             Q.key_off = as_ptr<const uint32_t>(key_off);
             Q.key_len = as_ptr<const uint32_t>(key_len);
             Q.n = n;
-            Q.table = as_ptr<const kernels::IndexEntry>(table);
+            Q.table = as_ptr<const kernels::IndexBucket>(table);
             Q.table_mask = table_mask;
             Q.nsegs = uint32_t(std::min<size_t>(seg_base.size(), kernels::LookupLaunch::kMaxSegs));
             for (uint32_t i = 0; i < Q.nsegs; ++i) Q.seg_base[i] = seg_base[i];
@@ -702,7 +710,34 @@ PYBIND11_MODULE(_infinistore, m) {
         py::arg("table"), py::arg("table_mask"), py::arg("seg_base") = std::vector<uint64_t>(),
         py::arg("out_descs") = 0, py::arg("dst_off") = 0, py::arg("dst_base") = 0,
         py::arg("need_bytes") = 0, py::arg("present") = 0, py::arg("status") = 0,
-        py::arg("ticket") = 0, py::arg("want_match") = false, py::arg("stream") = 0);
+        py::arg("ticket") = 0, py::arg("want_match") = false, py::arg("stream") = 0,
+        py::arg("found_at") = 0);
+    k.def(
+        "index_validate",
+        [](uint64_t found_at, uint32_t n, uint64_t table, uint64_t status, uint64_t stream) {
+            kernels::ValidateLaunch V;
+            V.found_at = as_ptr<const kernels::LookupLaunch::FoundAt>(found_at);
+            V.n = n;
+            V.table = as_ptr<const kernels::IndexBucket>(table);
+            V.status = as_ptr<uint32_t>(status);
+            const cudaError_t e = kernels::launch_index_validate(V, as_ptr<CUstream_st>(stream));
+            if (e != cudaSuccess) throw std::runtime_error(cudaGetErrorString(e));
+        },
+        py::arg("found_at"), py::arg("n"), py::arg("table"), py::arg("status"),
+        py::arg("stream") = 0);
+    k.def(
+        "index_erase",
+        [](uint64_t recs, uint32_t n, uint64_t table, uint64_t table_mask, uint64_t stream) {
+            kernels::EraseLaunch E;
+            E.recs = as_ptr<const kernels::EraseRec>(recs);
+            E.n = n;
+            E.table = as_ptr<kernels::IndexBucket>(table);
+            E.table_mask = table_mask;
+            const cudaError_t e = kernels::launch_index_erase(E, as_ptr<CUstream_st>(stream));
+            if (e != cudaSuccess) throw std::runtime_error(cudaGetErrorString(e));
+        },
+        py::arg("recs"), py::arg("n"), py::arg("table"), py::arg("table_mask"),
+        py::arg("stream") = 0);
     auto fp8 = [](bool write) {
         return [write](uint64_t descs, uint32_t n, uint32_t elems, uint32_t group, int max_ctas,
                        uint64_t stream, uint64_t recs, uint64_t table, uint64_t table_mask,
@@ -713,7 +748,7 @@ PYBIND11_MODULE(_infinistore, m) {
             L.elems = elems;
             L.group = group;
             L.recs = as_ptr<const kernels::IndexEntry>(recs);
-            L.table = as_ptr<kernels::IndexEntry>(table);
+            L.table = as_ptr<kernels::IndexBucket>(table);
             L.table_mask = table_mask;
             L.done = as_ptr<uint32_t>(done);
             L.status = as_ptr<uint32_t>(status);

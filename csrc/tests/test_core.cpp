@@ -3,15 +3,19 @@
 // these are their working counterpart.  Build + run: python tools/build_native.py --tests
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <random>
+#include <atomic>
 #include <set>
+#include <thread>
 #include <string>
 #include <vector>
 
 #include "core/hash.h"
 #include "core/kv_store.h"
 #include "core/mempool.h"
+#include "kernels/index.cuh"
 #include "wire/messages.h"
 
 using namespace istore;
@@ -189,12 +193,251 @@ static void test_hash() {
     CHECK(a.h1 == b.h1 && a.h2 == b.h2);
 }
 
+static void test_kv_store_eviction() {
+    MM mm;
+    mm.add_pool(8 * 16384, 16384, -1);
+    KVStore st(&mm);
+    std::vector<RemoteBlock> out, found;
+    std::vector<std::string> names;
+    for (int i = 0; i < 8; ++i) names.push_back("k" + std::to_string(i));
+    std::vector<std::string_view> keys(names.begin(), names.end());
+    CHECK(st.reserve(keys, 16384, -1, 1, out) == kFinish);
+    std::vector<uint64_t> addrs;
+    for (auto& b : out) addrs.push_back(b.remote_addr);
+    // commit order = recency order: k0 is the oldest
+    for (uint64_t a : addrs) CHECK(st.commit(&a, 1) == 1);
+    CHECK(st.reserve({"new"}, 16384, -1, 1, out) == kOutOfMemory);
+    // a read makes k0 the most recently used; k1 is now the eviction candidate
+    CHECK(st.lookup({"k0"}, 1, found, nullptr) == kFinish);
+    // a leased block is skipped
+    std::vector<BlockPtr> lease;
+    CHECK(st.lookup({"k1"}, 1, found, &lease) == kFinish);
+    CHECK(st.lookup({"k0"}, 1, found, nullptr) == kFinish);
+    std::vector<BlockPtr> victims;
+    CHECK(st.evict(2 * 16384, false, victims) == 2 * 16384 && victims.size() == 2);
+    CHECK(!st.present("k2") && !st.present("k3") && st.present("k1") && st.present("k0"));
+    const KeyHash h2 = hash_key(reinterpret_cast<const uint8_t*>("k2"), 2);
+    CHECK(victims[0]->evicted_hash.h1 == h2.h1 && victims[0]->evicted_hash.h2 == h2.h2);
+    CHECK(victims[0]->addr() == addrs[2]);
+    CHECK(mm.used_bytes() == 8 * 16384);  // victims still hold the space
+    victims.clear();
+    CHECK(mm.used_bytes() == 6 * 16384 && st.evicted() == 2);
+    CHECK(st.reserve({"new", "new2"}, 16384, -1, 1, out) == kFinish);
+    // uncommitted blocks are never victims; replica filter selects nothing here
+    CHECK(st.evict(1, true, victims) == 0 && victims.empty());
+    lease.clear();
+    CHECK(st.evict(100 * 16384, false, victims) == 6 * 16384 && victims.size() == 6);
+    CHECK(st.size() == 2 && st.present("new") && st.inflight() == 2);
+    victims.clear();
+    CHECK(st.purge() == 2);
+    CHECK(mm.used_bytes() == 0);
+    // the LRU list survives purge + refill
+    CHECK(st.reserve({"z"}, 16384, -1, 1, out) == kFinish);
+    uint64_t za = out[0].remote_addr;
+    CHECK(st.commit(&za, 1) == 1);
+    CHECK(st.evict(1, false, victims) == 16384 && victims.size() == 1);
+}
+
+// The device index algorithm (kernels/index.cuh) compiled for the CPU.
+static void test_device_index_logic() {
+    using namespace istore::kernels;
+    const uint64_t slots = 1024, mask = index_bucket_mask(slots);
+    std::vector<IndexBucket> table(slots / kIndexWays);
+    std::memset(static_cast<void*>(table.data()), 0, table.size() * sizeof(IndexBucket));
+    auto rec_of = [](int i) {
+        const std::string k = "key/" + std::to_string(i);
+        const KeyHash h = hash_key(reinterpret_cast<const uint8_t*>(k.data()), k.size());
+        return IndexEntry{h.h1, h.h2, make_addr(0, uint64_t(i) * 4096), uint32_t(i + 1), 4096};
+    };
+    // half load: everything fits, claimed-but-uncommitted is invisible
+    std::vector<uint32_t> slot(512);
+    for (int i = 0; i < 512; ++i) {
+        bool full = false;
+        const IndexEntry r = rec_of(i);
+        slot[size_t(i)] = idx::claim(table.data(), mask, r, true, &full);
+        CHECK(slot[size_t(i)] != 0 && !full);
+        CHECK(idx::find(table.data(), mask, KeyHash{r.h1, r.h2}).slot_plus1 == 0);
+        idx::commit(table.data(), slot[size_t(i)], r.tag, true);
+    }
+    for (int i = 0; i < 600; ++i) {
+        const IndexEntry r = rec_of(i);
+        const idx::Found f = idx::find(table.data(), mask, KeyHash{r.h1, r.h2});
+        if (i < 512) {
+            CHECK(f.slot_plus1 == slot[size_t(i)] && f.tag == r.tag && f.addr == r.addr && f.size == 4096);
+            CHECK(idx::still_valid(table.data(), f.slot_plus1, f.tag));
+        } else {
+            CHECK(f.slot_plus1 == 0);
+        }
+    }
+    // first writer wins inside the index too
+    {
+        bool full = false;
+        IndexEntry r = rec_of(7);
+        r.addr += 64;
+        CHECK(idx::claim(table.data(), mask, r, true, &full) == 0 && !full);
+        CHECK(idx::find(table.data(), mask, KeyHash{r.h1, r.h2}).addr == rec_of(7).addr);
+    }
+    // eviction: the way becomes empty, readers that resolved it notice, the key can return
+    for (int i = 0; i < 512; i += 2) {
+        const IndexEntry r = rec_of(i);
+        CHECK(idx::erase(table.data(), mask, r.h1, r.h2, r.addr));
+        CHECK(!idx::erase(table.data(), mask, r.h1, r.h2, r.addr));
+        CHECK(!idx::still_valid(table.data(), slot[size_t(i)], r.tag));
+        CHECK(idx::find(table.data(), mask, KeyHash{r.h1, r.h2}).slot_plus1 == 0);
+    }
+    for (int i = 1; i < 512; i += 2) {
+        const IndexEntry r = rec_of(i);
+        CHECK(idx::find(table.data(), mask, KeyHash{r.h1, r.h2}).slot_plus1 == slot[size_t(i)]);
+    }
+    size_t used = 0;
+    for (auto& b : table)
+        for (uint64_t h : b.h1) used += h != 0;
+    CHECK(used == 256);  // no tombstones: erased ways are empty again
+    for (int i = 0; i < 512; i += 2) {
+        bool full = false;
+        IndexEntry r = rec_of(i);
+        r.tag += 100000;  // a new allocation generation
+        const uint32_t s = idx::claim(table.data(), mask, r, true, &full);
+        CHECK(s != 0);
+        idx::commit(table.data(), s, r.tag, true);
+        CHECK(idx::find(table.data(), mask, KeyHash{r.h1, r.h2}).tag == r.tag);
+    }
+    // overfull table: the failure is reported, everything claimed stays findable
+    std::vector<IndexBucket> tiny(2);
+    std::memset(static_cast<void*>(tiny.data()), 0, tiny.size() * sizeof(IndexBucket));
+    int ok = 0, failed = 0;
+    for (int i = 0; i < 40; ++i) {
+        bool full = false;
+        const IndexEntry r = rec_of(i);
+        const uint32_t s = idx::claim(tiny.data(), index_bucket_mask(16), r, true, &full);
+        if (s) {
+            idx::commit(tiny.data(), s, r.tag, true);
+            ++ok;
+        } else {
+            CHECK(full);
+            ++failed;
+        }
+    }
+    CHECK(ok == 16 && failed == 24);
+    // at the load the server sizes the table for (<= 0.5) nothing overflows
+    {
+        const uint64_t big = 65536;
+        std::vector<IndexBucket> t(big / kIndexWays);
+        std::memset(static_cast<void*>(t.data()), 0, t.size() * sizeof(IndexBucket));
+        int overflow = 0;
+        for (int i = 0; i < int(big / 2); ++i) {
+            bool full = false;
+            const IndexEntry r = rec_of(i);
+            const uint32_t s = idx::claim(t.data(), index_bucket_mask(big), r, true, &full);
+            if (!s) ++overflow;
+            else idx::commit(t.data(), s, r.tag, true);
+        }
+        CHECK(overflow == 0);
+        int missing = 0;
+        for (int i = 0; i < int(big / 2); ++i) {
+            const IndexEntry r = rec_of(i);
+            missing += idx::find(t.data(), index_bucket_mask(big), KeyHash{r.h1, r.h2}).addr != r.addr;
+        }
+        CHECK(missing == 0);
+    }
+    // one-bucket table (b == a)
+    std::vector<IndexBucket> one(1);
+    std::memset(static_cast<void*>(one.data()), 0, sizeof(IndexBucket));
+    for (int i = 0; i < 8; ++i) {
+        bool full = false;
+        const IndexEntry r = rec_of(i);
+        const uint32_t s = idx::claim(one.data(), 0, r, true, &full);
+        CHECK(s != 0);
+        idx::commit(one.data(), s, r.tag, true);
+        CHECK(idx::find(one.data(), 0, KeyHash{r.h1, r.h2}).addr == r.addr);
+    }
+}
+
+// Writers, an evictor and validating readers hammer one small table concurrently (threads
+// stand in for GPUs).  Invariant: a read that passes validation saw the address and
+// generation that belong to its key.
+static void test_device_index_concurrent() {
+    using namespace istore::kernels;
+    const uint64_t slots = 256, mask = index_bucket_mask(slots);
+    std::vector<IndexBucket> table(slots / kIndexWays);
+    std::memset(static_cast<void*>(table.data()), 0, table.size() * sizeof(IndexBucket));
+    constexpr int kKeys = 96;
+    struct KeyState {
+        KeyHash h;
+        std::atomic<uint32_t> live_gen{0};  // 0: not in the store (server's view)
+        std::atomic<uint32_t> slot{0};
+    };
+    std::vector<KeyState> ks(kKeys);
+    for (int i = 0; i < kKeys; ++i) {
+        const std::string k = "ck" + std::to_string(i);
+        ks[size_t(i)].h = hash_key(reinterpret_cast<const uint8_t*>(k.data()), k.size());
+    }
+    // address encodes (key, generation): a reader can check what it resolved
+    auto addr_of = [](int key, uint32_t gen) { return (uint64_t(key) << 32) | gen; };
+    std::atomic<bool> stop{false};
+    std::atomic<uint32_t> next_gen{1};
+    std::atomic<long> validated{0}, stale{0}, bad{0}, cycles{0};
+    // "server + writer + evictor" per key range: write -> commit -> (readers run) -> erase
+    auto churn = [&](int first, int last) {
+        std::mt19937 rng{unsigned(first)};
+        while (!stop.load()) {
+            const int i = first + int(rng() % unsigned(last - first));
+            KeyState& k = ks[size_t(i)];
+            if (k.live_gen.load() == 0) {
+                const uint32_t gen = next_gen.fetch_add(1);
+                bool full = false;
+                const IndexEntry r{k.h.h1, k.h.h2, addr_of(i, gen), gen, 64};
+                const uint32_t s = idx::claim(table.data(), mask, r, true, &full);
+                if (!s) continue;
+                idx::fence(true);
+                idx::commit(table.data(), s, gen, true);
+                k.slot.store(s);
+                k.live_gen.store(gen);
+            } else {
+                const uint32_t gen = k.live_gen.exchange(0);
+                if (!idx::erase(table.data(), mask, k.h.h1, k.h.h2, addr_of(i, gen))) ++bad;
+                ++cycles;
+            }
+        }
+    };
+    auto reader = [&](unsigned seed) {
+        std::mt19937 rng{seed};
+        while (!stop.load()) {
+            const int i = int(rng() % kKeys);
+            const idx::Found f = idx::find(table.data(), mask, ks[size_t(i)].h);
+            if (!f.slot_plus1) continue;
+            const uint64_t seen_addr = f.addr;
+            idx::fence(true);  // "the copy"
+            if (!idx::still_valid(table.data(), f.slot_plus1, f.tag)) {
+                ++stale;
+                continue;
+            }
+            ++validated;
+            if (seen_addr != addr_of(i, f.tag)) ++bad;
+        }
+    };
+    std::vector<std::thread> th;
+    th.emplace_back(churn, 0, kKeys / 2);
+    th.emplace_back(churn, kKeys / 2, kKeys);
+    for (unsigned r = 0; r < 3; ++r) th.emplace_back(reader, 100 + r);
+    std::this_thread::sleep_for(std::chrono::milliseconds(400));
+    stop.store(true);
+    for (auto& t : th) t.join();
+    CHECK(bad.load() == 0);
+    CHECK(validated.load() > 100 && cycles.load() > 100);
+    std::printf("index stress: %ld validated reads, %ld stale, %ld evictions\n", validated.load(),
+                stale.load(), cycles.load());
+}
+
 int main() {
     test_framing();
     test_flatbuffers();
     test_mempool();
     test_kv_store();
+    test_kv_store_eviction();
     test_hash();
+    test_device_index_logic();
+    test_device_index_concurrent();
     std::printf("%d checks, %d failed\n", g_checks, g_failed);
     return g_failed ? 1 : 0;
 }

@@ -63,7 +63,7 @@ struct ConnInfo {
     uint32_t qpn;      // pid of the sender
     uint32_t psn;      // client: CUDA device ordinal (0xffffffff = none); server: #segments
     uint8_t gid[16];   // process uuid (same-process detection: no IPC open on own memory)
-    uint16_t lid;      // fabric flags (bit0: CUDA available)
+    uint16_t lid;      // fabric flags (bit0: CUDA available, bit1: HBM pool, bit2: evicts)
     uint32_t mtu;      // fabric protocol version
 };
 #pragma pack(pop)

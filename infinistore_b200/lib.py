@@ -117,7 +117,10 @@ class ServerConfig(_infinistore.ServerConfig):
     num_stream (deprecated), auto_increase.  Fabric extensions: ``host`` (listen address,
     honoured here), ``pool_backend`` ("auto" | "hbm" | "host"), ``pool_devices`` (CUDA
     ordinals that each host one pool segment), ``extend_size`` (GB per auto-increase step),
-    ``prealloc_bytes`` (exact pool size, for tests), ``index_slots``.
+    ``prealloc_bytes`` (exact pool size, for tests), ``index_slots``, ``replica_size``,
+    ``evict`` (a full pool evicts least-recently-used blocks instead of answering 507 until
+    ``/purge`` - the reference never evicts) and ``evict_ratio`` (fraction of the pool freed
+    per eviction round, default 0.05).
     """
 
     def __init__(self, **kwargs):
@@ -141,6 +144,8 @@ class ServerConfig(_infinistore.ServerConfig):
         # NVLS-replicated region (one replica per GPU behind one multicast object)
         self.replica_bytes = kwargs.get("replica_bytes", 0) or (kwargs.get("replica_size", 0) << 30)
         self.replica_devices = list(kwargs.get("replica_devices", []) or [])
+        self.evict = bool(kwargs.get("evict", False))
+        self.evict_ratio = float(kwargs.get("evict_ratio", 0.05))
 
     def __repr__(self):
         return (
@@ -149,7 +154,8 @@ class ServerConfig(_infinistore.ServerConfig):
             f"link_type='{self.link_type}', prealloc_size={self.prealloc_size}, "
             f"minimal_allocate_size={self.minimal_allocate_size}, num_stream={self.num_stream}, "
             f"auto_increase={self.auto_increase}, host='{self.host}', "
-            f"pool_backend='{self.pool_backend}', pool_devices={list(self.pool_devices)}"
+            f"pool_backend='{self.pool_backend}', pool_devices={list(self.pool_devices)}, "
+            f"evict={self.evict}"
         )
 
     def verify(self):
@@ -169,6 +175,8 @@ class ServerConfig(_infinistore.ServerConfig):
             raise Exception("minimal allocate size should be greater than 16")
         if self.pool_backend not in ("auto", "hbm", "host"):
             raise Exception("pool backend should be auto, hbm or host")
+        if not 0.0 < self.evict_ratio <= 1.0:
+            raise Exception("evict ratio should be in (0, 1]")
 
 
 class Logger:

@@ -17,7 +17,13 @@ from .. import _infinistore
 K = _infinistore.kernels
 
 VARIANTS = {"auto": K.COPY_AUTO, "ldst": K.COPY_LDST, "tma": K.COPY_TMA, "ldst256": K.COPY_LDST256}
-INDEX_ENTRY_BYTES = 32
+INDEX_ENTRY_BYTES = 32   # per entry; the table is an array of 8-way, 256-byte buckets
+INDEX_WAYS = 8
+
+
+def index_bucket_mask(table: torch.Tensor) -> int:
+    slots = table.numel() * table.element_size() // INDEX_ENTRY_BYTES
+    return slots // INDEX_WAYS - 1
 
 
 def _stream(device) -> int:
@@ -61,12 +67,14 @@ class PublishArgs:
             rec[i, 3] = (int(gens[i]) & 0xFFFFFFFF) | (int(size) << 32)
         self.recs = torch.from_numpy(rec.view(np.int64)).to(dev)
         self.table = table
-        self.mask = table.numel() * table.element_size() // INDEX_ENTRY_BYTES - 1
+        self.mask = index_bucket_mask(table)
+        self.addrs = list(addrs)
+        self.keys = list(keys)
         self.done = torch.zeros(3 * len(keys), dtype=torch.int32, device=dev)  # done | slot | tag
 
 
 def new_index_table(slots: int, device) -> torch.Tensor:
-    assert slots & (slots - 1) == 0, "slots must be a power of two"
+    assert slots >= INDEX_WAYS and slots & (slots - 1) == 0, "slots: a power of two >= 8"
     return torch.zeros(slots * 4, dtype=torch.int64, device=device)
 
 
@@ -88,12 +96,14 @@ def pack_keys(keys: Sequence[bytes], device) -> Tuple[torch.Tensor, torch.Tensor
 
 def index_lookup(table: torch.Tensor, keys: Sequence[bytes], seg_base: Sequence[int] = (),
                  dst_base: int = 0, dst_off: Optional[Sequence[int]] = None, need_bytes: int = 0,
-                 want_match: bool = False):
-    """Probe `table` for `keys`.  Returns (descs | None, present bitmap, match index | None)."""
+                 want_match: bool = False, found_at: Optional[torch.Tensor] = None):
+    """Probe `table` for `keys`.  Returns (descs | None, present bitmap, match index | None).
+    `found_at` ((n, 2) int32, optional) receives (slot + 1, tag) of every hit for
+    :func:`index_validate`."""
     dev = table.device
     kb, ko, kl = pack_keys(keys, dev)
     n = len(keys)
-    mask = table.numel() * table.element_size() // INDEX_ENTRY_BYTES - 1
+    mask = index_bucket_mask(table)
     descs = torch.zeros((n, 2), dtype=torch.int64, device=dev) if dst_off is not None else None
     doff = (torch.tensor(list(dst_off), dtype=torch.int64, device=dev)
             if dst_off is not None else None)
@@ -105,12 +115,38 @@ def index_lookup(table: torch.Tensor, keys: Sequence[bytes], seg_base: Sequence[
                        list(seg_base), descs.data_ptr() if descs is not None else 0,
                        doff.data_ptr() if doff is not None else 0, dst_base, need_bytes,
                        present.data_ptr(), status.data_ptr(), ticket.data_ptr(), want_match,
-                       _stream(dev))
+                       _stream(dev), found_at.data_ptr() if found_at is not None else 0)
     match = None
     if want_match:
         torch.cuda.synchronize(dev)
         match = int(np.int32(status[K.STAT_MATCH].item()))
     return descs, present, match
+
+
+def index_erase(table: torch.Tensor, keys: Sequence[bytes], addrs: Sequence[int]) -> None:
+    """Empty the index ways of evicted blocks (what the server does before it reuses their
+    space)."""
+    dev = table.device
+    rec = np.zeros((len(keys), 3), dtype=np.uint64)
+    for i, k in enumerate(keys):
+        rec[i, 0], rec[i, 1] = _infinistore.testing.hash_key(k)
+        rec[i, 2] = addrs[i]
+    recs = torch.from_numpy(rec.view(np.int64)).to(dev)
+    with torch.cuda.device(dev):
+        K.index_erase(recs.data_ptr(), len(keys), table.data_ptr(), index_bucket_mask(table),
+                      _stream(dev))
+    torch.cuda.synchronize(dev)  # recs must outlive the kernel
+
+
+def index_validate(table: torch.Tensor, found_at: torch.Tensor) -> int:
+    """Number of entries that changed since the lookup that filled `found_at`."""
+    dev = table.device
+    status = torch.zeros(K.STAT_WORDS, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        K.index_validate(found_at.data_ptr(), found_at.shape[0], table.data_ptr(),
+                         status.data_ptr(), _stream(dev))
+    torch.cuda.synchronize(dev)
+    return int(status[K.STAT_STALE].item())
 
 
 def presence_bits(present: torch.Tensor, n: int) -> List[bool]:

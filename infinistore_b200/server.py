@@ -5,7 +5,7 @@ Flags, defaults and endpoints follow the reference (infinistore/server.py:26-263
 --prealloc-size 16 --dev-name --ib-port --link-type --minimal-allocate-size 64
 --num-stream --warmup`` and ``POST /purge``, ``POST /selftest/{port}``, ``GET /kvmap_len``.
 New: ``--pool-backend``, ``--pool-devices``, ``--extend-size``, ``--replica-size``,
-``--load-from``; ``GET /metrics`` (Prometheus text), ``GET /stats`` (JSON), ``POST /dump`` and
+``--load-from``, ``--evict``, ``--evict-ratio``; ``GET /metrics`` (Prometheus text), ``GET /stats`` (JSON), ``POST /dump`` and
 ``POST /load`` (checkpoint / resume).  ``--host`` is honoured (the reference parses
 and ignores it).  The data/control plane runs on a native reactor thread; uvicorn only
 serves the manage plane.
@@ -101,6 +101,7 @@ def prometheus_text(s: dict) -> str:
     gauge("connections", s.get("connections", 0), "open client connections")
     gauge("requests_total", s.get("requests", 0), "control-plane requests served")
     gauge("bad_requests_total", s.get("bad_requests", 0), "requests answered with an error")
+    gauge("evicted_blocks_total", s.get("evicted", 0), "blocks evicted to make room")
     for op, n in sorted(s.get("ops", {}).items()):
         lines.append(f'infinistore_op_total{{op="{op}"}} {n}')
     return "\n".join(lines) + "\n"
@@ -171,6 +172,11 @@ def parse_args(argv=None):
                    help="checkpoint file (POST /dump) to load at start-up")
     p.add_argument("--replica-size", default=0, type=int,
                    help="GB per GPU of NVLS-replicated region for one-writer/many-reader blocks")
+    p.add_argument("--evict", action="store_true",
+                   help="when the pool is full evict least-recently-used blocks instead of "
+                        "refusing writes (507) until /purge")
+    p.add_argument("--evict-ratio", default=0.05, type=float,
+                   help="fraction of the pool freed per eviction round")
     return p.parse_args(argv)
 
 
@@ -201,6 +207,8 @@ def config_from_args(args) -> ServerConfig:
         pool_devices=devices,
         extend_size=args.extend_size,
         replica_size=args.replica_size,
+        evict=args.evict,
+        evict_ratio=args.evict_ratio,
     )
 
 

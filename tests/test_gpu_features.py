@@ -78,6 +78,71 @@ def test_fused_read_many_rounds_and_misses(hbm_server):
     assert torch.equal(got, want)
 
 
+@pytest.mark.parametrize("device_lookup", [False, True])
+def test_hbm_pool_evicts_lru_blocks_and_device_index_follows(device_lookup):
+    """A full HBM pool with evict=True: old blocks leave the server map AND the device
+    index (erase kernel), device-side reads of evicted keys miss, everything else is intact,
+    and readers run with post-copy validation."""
+    cfg = native.ServerConfig()
+    cfg.service_port = 0
+    cfg.host = "127.0.0.1"
+    cfg.pool_backend = "hbm"
+    cfg.pool_devices = [0]
+    cfg.minimal_allocate_size = 16
+    cfg.prealloc_bytes = 512 * 16384
+    cfg.evict = True
+    cfg.evict_ratio = 0.25
+    srv = native.Server(cfg)
+    port = srv.start()
+    try:
+        conn = make_conn(port, device_lookup=device_lookup)
+        assert conn.conn.server_evicts()
+        n, elems = 512, 4096  # 16 KB blocks: exactly fills the pool
+        src = torch.randn(2 * n * elems, device="cuda:0")
+        dst = torch.zeros(n * elems, device="cuda:0")
+        conn.register_mr(src)
+        keys = [f"old-{i}" for i in range(n)]
+        conn.rdma_write_cache(src, [i * elems for i in range(n)], elems,
+                              conn.allocate_rdma(keys, elems * 4))
+        conn.sync()
+        assert srv.stats()["used_bytes"] == n * 16384
+        # 200 new blocks need room: two eviction rounds of 25 % (128 blocks) each
+        new = [f"new-{i}" for i in range(200)]
+        conn.rdma_write_cache(src, [(n + i) * elems for i in range(200)], elems,
+                              conn.allocate_rdma(new, elems * 4))
+        conn.sync()
+        st = srv.stats()
+        assert st["evicted"] == 256 and st["keys"] == n - 256 + 200
+        # the 256 oldest are gone, for the host map and for the device index alike
+        assert not conn.check_exist("old-0") and not conn.check_exist("old-255")
+        assert conn.check_exist("old-256") and conn.check_exist("new-199")
+        conn.read_cache(dst, [("old-3", 0)], elems)
+        with pytest.raises(Exception):
+            conn.sync()
+        # survivors and new blocks read back bit-exact (fused path: >= SM-count blocks)
+        q = [(f"old-{i}", (i - 256) * elems) for i in range(256, n)]
+        q += [(f"new-{i}", (256 + i) * elems) for i in range(200)]
+        conn.read_cache(dst, q, elems)
+        conn.sync()
+        want = torch.cat([src[256 * elems:n * elems], src[n * elems:(n + 200) * elems]])
+        assert torch.equal(dst[:(256 + 200) * elems], want)
+        # small batch (lookup + copy + validate path)
+        dst.zero_()
+        conn.read_cache(dst, [("new-7", 0), ("old-300", elems)], elems)
+        conn.sync()
+        assert torch.equal(dst[:elems], src[(n + 7) * elems:(n + 8) * elems])
+        assert torch.equal(dst[elems:2 * elems], src[300 * elems:301 * elems])
+        # an evicted key is simply written again
+        conn.rdma_write_cache(src, [0], elems, conn.allocate_rdma(["old-0"], elems * 4))
+        conn.sync()
+        dst.zero_()
+        conn.read_cache(dst, [("old-0", 0)], elems)
+        conn.sync()
+        assert torch.equal(dst[:elems], src[:elems])
+    finally:
+        srv.stop()
+
+
 def test_in_stream_mode_orders_with_the_callers_stream(hbm_server):
     """streams=0: kernels run in the caller's stream, so later work on that stream sees the
     data without sync() (the mode to use under CUDA-graph capture)."""

@@ -103,6 +103,56 @@ def test_publish_then_lookup_and_read(variant):
     assert (descs2.cpu().numpy().view(np.uint64)[:, 0] == 0).all()
 
 
+def test_index_erase_and_post_copy_validation():
+    """Eviction on the device index: erased ways are empty again (no tombstones), a reader
+    that resolved an entry before the eviction notices afterwards, and the key can return."""
+    ops = _ops()
+    n = 200
+    keys = [b"ev/%04d" % i for i in range(n)]
+    pool = torch.zeros(64, dtype=torch.uint8, device=DEV)
+    table = ops.new_index_table(512, DEV)
+    addrs = [(1 << 44) | (i * 4096) for i in range(n)]
+    status = torch.zeros(8, dtype=torch.int32, device=DEV)
+    wd = ops.make_descs([pool.data_ptr()] * n, [pool.data_ptr()] * n, DEV)
+    ops.kv_copy(wd, 64, publish=ops.PublishArgs(table, keys, addrs, list(range(1, n + 1)), 64),
+                status=status)
+    torch.cuda.synchronize()
+    assert int(status[1]) == 0
+    found_at = torch.zeros((n, 2), dtype=torch.int32, device=DEV)
+    _, present, _ = ops.index_lookup(table, keys, seg_base=[0x1000000], dst_base=0,
+                                     dst_off=[0] * n, need_bytes=1, found_at=found_at)
+    assert all(ops.presence_bits(present, n))
+    assert (found_at[:, 0] > 0).all()
+    assert found_at[:, 1].tolist() == list(range(1, n + 1))  # the tags (generations)
+    assert ops.index_validate(table, found_at) == 0
+    # evict every other block
+    gone = list(range(0, n, 2))
+    ops.index_erase(table, [keys[i] for i in gone], [addrs[i] for i in gone])
+    assert ops.index_validate(table, found_at) == len(gone)
+    _, present, _ = ops.index_lookup(table, keys)
+    bits = ops.presence_bits(present, n)
+    assert bits == [i % 2 == 1 for i in range(n)]
+    words = table.cpu().numpy().view(np.uint64).reshape(-1, 32)  # one 256-byte bucket per row
+    assert int((words[:, :8] != 0).sum()) == n - len(gone)  # fingerprints: no tombstones
+    # the evicted keys come back as new allocations (new generation, new address)
+    addrs2 = [(1 << 44) | ((n + i) * 4096) for i in gone]
+    wd2 = ops.make_descs([pool.data_ptr()] * len(gone), [pool.data_ptr()] * len(gone), DEV)
+    ops.kv_copy(wd2, 64, status=status,
+                publish=ops.PublishArgs(table, [keys[i] for i in gone], addrs2,
+                                        [1000 + i for i in gone], 64))
+    torch.cuda.synchronize()
+    found2 = torch.zeros((n, 2), dtype=torch.int32, device=DEV)
+    descs, present, _ = ops.index_lookup(table, keys, seg_base=[0x1000000], dst_base=0,
+                                         dst_off=[0] * n, need_bytes=1, found_at=found2)
+    assert all(ops.presence_bits(present, n))
+    d = descs.cpu().numpy().view(np.uint64)[:, 0]
+    assert d[0] == 0x1000000 + n * 4096 and d[1] == 0x1000000 + 4096
+    assert found2[0, 1].item() == 1000 and found2[1, 1].item() == 2
+    # the stale resolution of an evicted-and-rewritten key still fails validation
+    assert ops.index_validate(table, found_at) == len(gone)
+    assert ops.index_validate(table, found2) == 0
+
+
 def test_match_last_index_replays_reference_search_bit_exact():
     ops = _ops()
     rng = np.random.default_rng(7)

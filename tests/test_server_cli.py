@@ -96,3 +96,12 @@ def test_arg_defaults_match_reference():
     assert a.auto_increase is False and a.warmup is False and a.host == "0.0.0.0"
     cfg = server.config_from_args(server.parse_args(["--pool-devices", "0,2", "--auto-increase"]))
     assert list(cfg.pool_devices) == [0, 2] and cfg.auto_increase
+    assert cfg.evict is False and abs(cfg.evict_ratio - 0.05) < 1e-9
+    cfg = server.config_from_args(server.parse_args(["--evict", "--evict-ratio", "0.2"]))
+    assert cfg.evict is True and abs(cfg.evict_ratio - 0.2) < 1e-9
+    cfg.manage_port, cfg.service_port = 1, 2
+    cfg.verify()
+    cfg.evict_ratio = 0.0
+    import pytest
+    with pytest.raises(Exception):
+        cfg.verify()

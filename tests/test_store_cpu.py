@@ -290,6 +290,76 @@ def test_out_of_memory_is_reported_and_nothing_is_half_allocated():
         srv.stop()
 
 
+def test_full_pool_evicts_least_recently_used_when_enabled():
+    """The reference answers 507 forever once the pool is full; with --evict the
+    least recently used committed blocks make room."""
+    srv, port = _server(prealloc_bytes=8 * 16384, evict=True, evict_ratio=0.25)
+    try:
+        conn = make_conn(port)
+        src = torch.arange(12 * 4096, dtype=torch.float32)
+        dst = torch.zeros(4096)
+        conn.register_mr(src)
+        keys = [f"k{i}" for i in range(8)]
+        conn.rdma_write_cache(src, [i * 4096 for i in range(8)], 4096,
+                              conn.allocate_rdma(keys, 16384))
+        conn.sync()
+        assert srv.stats()["used_bytes"] == 8 * 16384
+        # touch k0: a read makes it the most recently used block
+        conn.read_cache(dst, [("k0", 0)], 4096)
+        conn.sync()
+        assert torch.equal(dst, src[:4096])
+        # the pool is full: two more blocks push out the two oldest ones (25 % per round)
+        more = conn.allocate_rdma(["k8", "k9"], 16384)
+        assert len(more) == 2 and (more["rkey"] != 0).all()
+        conn.rdma_write_cache(src, [8 * 4096, 9 * 4096], 4096, more)
+        conn.sync()
+        st = srv.stats()
+        assert st["evicted"] == 2 and st["keys"] == 8 and st["used_bytes"] == 8 * 16384
+        assert not conn.check_exist("k1") and not conn.check_exist("k2")
+        assert conn.check_exist("k0") and conn.check_exist("k3") and conn.check_exist("k9")
+        with pytest.raises(Exception):
+            conn.read_cache(dst, [("k1", 0)], 4096)
+        conn.read_cache(dst, [("k9", 0)], 4096)
+        conn.sync()
+        assert torch.equal(dst, src[9 * 4096:10 * 4096])
+        # an evicted key can be written again (it is a new block)
+        again = conn.allocate_rdma(["k1"], 16384)
+        assert again["rkey"][0] != 0
+        conn.rdma_write_cache(src, [11 * 4096], 4096, again)
+        conn.sync()
+        conn.read_cache(dst, [("k1", 0)], 4096)
+        conn.sync()
+        assert torch.equal(dst, src[11 * 4096:12 * 4096])
+    finally:
+        srv.stop()
+
+
+def test_eviction_skips_blocks_a_reader_holds_and_uncommitted_ones():
+    srv, port = _server(prealloc_bytes=4 * 16384, evict=True, evict_ratio=0.25)
+    try:
+        reader, writer = make_conn(port), make_conn(port)
+        src = torch.randn(8 * 4096)
+        writer.register_mr(src)
+        writer.rdma_write_cache(src, [0, 4096], 4096, writer.allocate_rdma(["a", "b"], 16384))
+        writer.sync()
+        dst = torch.zeros(4096)
+        reader.read_cache(dst, [("a", 0)], 4096)  # pinned until the reader's next sync
+        pending = writer.allocate_rdma(["c", "d"], 16384)  # reserved, never committed: pool full
+        assert len(pending) == 2
+        # only "b" can go: "a" is leased, "c"/"d" are in flight
+        one = writer.allocate_rdma(["e"], 16384)
+        assert one["rkey"][0] != 0 and srv.stats()["evicted"] == 1
+        assert not writer.check_exist("b")
+        with pytest.raises(Exception):
+            writer.allocate_rdma(["f"], 16384)  # nothing evictable left: 507
+        reader.sync()  # releases the lease on "a"
+        assert torch.equal(dst, src[:4096])
+        assert writer.allocate_rdma(["f"], 16384)["rkey"][0] != 0
+        assert srv.stats()["evicted"] == 2 and not writer.check_exist("a")
+    finally:
+        srv.stop()
+
+
 def test_auto_increase_adds_segments_and_clients_map_them():
     srv, port = _server(prealloc_bytes=8 * 16384, auto_increase=True)
     try:
