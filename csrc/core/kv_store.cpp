@@ -14,7 +14,7 @@ Block*& KVStore::inflight_slot(uint32_t seg, uint64_t offset) {
     return v[offset / pool.granule()];
 }
 
-void KVStore::lru_push_front(Block* b) {
+void KVStore::lru_push_front(LruBlock* b) {
     b->lru_prev = nullptr;
     b->lru_next = lru_head_;
     if (lru_head_) lru_head_->lru_prev = b;
@@ -23,7 +23,7 @@ void KVStore::lru_push_front(Block* b) {
     b->in_lru = true;
 }
 
-void KVStore::lru_unlink(Block* b) {
+void KVStore::lru_unlink(LruBlock* b) {
     if (!b->in_lru) return;
     (b->lru_prev ? b->lru_prev->lru_next : lru_head_) = b->lru_next;
     (b->lru_next ? b->lru_next->lru_prev : lru_tail_) = b->lru_prev;
@@ -54,8 +54,11 @@ int KVStore::reserve(const std::vector<std::string_view>& keys, size_t size, int
         const size_t i = fresh[j].first;
         uint32_t gen = next_gen_++;
         if (next_gen_ == 0) next_gen_ = 1;  // 0 means "not committed" in the device index
-        auto blk = std::make_shared<Block>(mm_, allocs[j].seg, allocs[j].offset, uint32_t(size),
-                                           gen, conn);
+        BlockPtr blk =
+            track_lru_ ? std::static_pointer_cast<Block>(std::make_shared<LruBlock>(
+                             mm_, allocs[j].seg, allocs[j].offset, uint32_t(size), gen, conn))
+                       : std::make_shared<Block>(mm_, allocs[j].seg, allocs[j].offset,
+                                                 uint32_t(size), gen, conn);
         blk->key = &fresh[j].second->first;
         inflight_slot(allocs[j].seg, allocs[j].offset) = blk.get();
         ++inflight_count_;
@@ -76,7 +79,7 @@ size_t KVStore::commit(const uint64_t* addrs, size_t n) {
         if (!b || b->offset != off) continue;  // unknown / already committed: ignored
         b->committed = true;
         b->owner = 0;
-        lru_push_front(b);
+        if (track_lru_) lru_push_front(static_cast<LruBlock*>(b));
         slot = nullptr;
         --inflight_count_;
         ++done;
@@ -101,9 +104,9 @@ int KVStore::lookup(const std::vector<std::string_view>& keys, size_t need,
         }
         out.push_back(RemoteBlock{b.seg + 1, b.gen, b.addr()});
         if (lease) lease->push_back(it->second);
-        if (lru_head_ != &b) {
-            lru_unlink(&b);
-            lru_push_front(&b);
+        if (track_lru_ && lru_head_ != &b) {
+            lru_unlink(static_cast<LruBlock*>(&b));
+            lru_push_front(static_cast<LruBlock*>(&b));
         }
     }
     return kFinish;
@@ -146,11 +149,11 @@ size_t KVStore::drop_uncommitted(uint64_t conn) {
     return n;
 }
 
-size_t KVStore::evict(size_t bytes, bool replica, std::vector<BlockPtr>& victims) {
+size_t KVStore::evict(size_t bytes, bool replica, std::vector<Victim>& victims) {
     size_t freed = 0;
-    Block* b = lru_tail_;
+    LruBlock* b = lru_tail_;
     while (b && freed < bytes) {
-        Block* more_recent = b->lru_prev;
+        LruBlock* more_recent = b->lru_prev;
         auto it = map_.find(*b->key);
         const bool in_replica = mm_->pool(b->seg).device() == kReplicaDevice;
         if (it != map_.end() && in_replica == replica &&
@@ -158,11 +161,11 @@ size_t KVStore::evict(size_t bytes, bool replica, std::vector<BlockPtr>& victims
             const size_t g = mm_->pool(b->seg).granule();
             freed += (size_t(b->size) + g - 1) / g * g;
             lru_unlink(b);
-            b->evicted_hash =
+            const KeyHash kh =
                 hash_key(reinterpret_cast<const uint8_t*>(b->key->data()), b->key->size());
-            victims.push_back(std::move(it->second));
+            victims.push_back(Victim{std::move(it->second), kh});
             map_.erase(it);  // frees the node that owns *b->key; victims keeps the block alive
-            victims.back()->key = nullptr;
+            b->key = nullptr;
             ++evicted_;
         }
         b = more_recent;

@@ -36,10 +36,6 @@ struct Block {
     bool committed = false;
     uint64_t owner = 0;  // connection id that reserved it (0 once committed)
     const std::string* key = nullptr;  // the map node's key (node addresses are stable)
-    Block* lru_prev = nullptr;  // towards more recently used; linked only while committed
-    Block* lru_next = nullptr;  // towards less recently used
-    bool in_lru = false;
-    KeyHash evicted_hash{0, 0};  // fingerprint of the key, filled in when the block is evicted
     Block(MM* m, uint32_t s, uint64_t o, uint32_t sz, uint32_t g, uint64_t own)
         : mm(m), seg(s), offset(o), size(sz), gen(g), owner(own) {}
     ~Block() { mm->deallocate(seg, offset, size); }
@@ -48,6 +44,17 @@ struct Block {
     uint64_t addr() const { return make_addr(seg, offset); }
 };
 using BlockPtr = std::shared_ptr<Block>;
+
+// A block of a store that evicts: the recency links live in a derived type so that the
+// default configuration (no eviction, the reference's behaviour) keeps the smaller block -
+// the commit path is bound by cache misses on these objects (measured: 16 more bytes per
+// block cost ~5 ns per committed block, 20 % of the 4 KB write rate).
+struct LruBlock : Block {
+    using Block::Block;
+    LruBlock* lru_prev = nullptr;  // towards more recently used; linked only while committed
+    LruBlock* lru_next = nullptr;  // towards less recently used
+    bool in_lru = false;
+};
 
 struct StrHash {
     using is_transparent = void;
@@ -63,7 +70,8 @@ struct StrEq {
 
 class KVStore {
    public:
-    explicit KVStore(MM* mm) : mm_(mm) {}
+    // track_recency: keep the LRU order that evict() needs (every block is an LruBlock)
+    explicit KVStore(MM* mm, bool track_recency = false) : mm_(mm), track_lru_(track_recency) {}
 
     // Reserve blocks for `keys`.  out[i] is the locator of key i, or the fake (0,0) block
     // when the key already exists (first writer wins).  Returns kFinish, or kOutOfMemory
@@ -91,7 +99,12 @@ class KVStore {
     // dropping the last reference returns the space to the pool.
     // `replica`: take victims from the NVLS-replicated region (true) or from the ordinary
     // pools (false) - space of one kind cannot serve requests for the other.
-    size_t evict(size_t bytes, bool replica, std::vector<BlockPtr>& victims);
+    struct Victim {
+        BlockPtr block;
+        KeyHash hash;  // fingerprint of the evicted key (its device-index entry)
+    };
+    size_t evict(size_t bytes, bool replica, std::vector<Victim>& victims);
+
     uint64_t evicted() const { return evicted_; }
     size_t size() const { return map_.size(); }
     // Visit every committed block (checkpointing).
@@ -106,17 +119,18 @@ class KVStore {
     // In-flight (reserved, uncommitted) blocks are found by address in O(1): one slot per
     // allocation granule of every pool, holding the block that starts there.
     Block*& inflight_slot(uint32_t seg, uint64_t offset);
-    void lru_push_front(Block* b);
-    void lru_unlink(Block* b);
+    void lru_push_front(LruBlock* b);
+    void lru_unlink(LruBlock* b);
 
     MM* mm_;
     uint32_t next_gen_ = 1;
     std::unordered_map<std::string, BlockPtr, StrHash, StrEq> map_;
     std::vector<std::vector<Block*>> inflight_;  // [segment][granule]
     size_t inflight_count_ = 0;
-    Block* lru_head_ = nullptr;  // most recently used
-    Block* lru_tail_ = nullptr;  // eviction candidate
+    LruBlock* lru_head_ = nullptr;  // most recently used
+    LruBlock* lru_tail_ = nullptr;  // eviction candidate
     uint64_t evicted_ = 0;
+    const bool track_lru_;
 };
 
 }  // namespace istore

@@ -63,7 +63,7 @@ size_t next_pow2(size_t v) {
 }  // namespace
 
 Server::Server(const ServerConfig& cfg) : cfg_(cfg) {
-    store_ = std::make_unique<KVStore>(&mm_);
+    store_ = std::make_unique<KVStore>(&mm_, cfg_.evict);
     scratch_.resize(64 << 10);
 }
 
@@ -269,7 +269,7 @@ ServerStats Server::stats() {
     return s;
 }
 
-bool Server::erase_from_device_index(const std::vector<BlockPtr>& victims) {
+bool Server::erase_from_device_index(const std::vector<KVStore::Victim>& victims) {
     if (segs_.empty()) return true;
     const fabric::SegmentOwner& seg0 = *segs_[0];
     if (seg0.info().kind != kSegDeviceIpc || !seg0.info().index_slots) return true;
@@ -277,7 +277,7 @@ bool Server::erase_from_device_index(const std::vector<BlockPtr>& victims) {
     std::vector<kernels::EraseRec> recs;
     recs.reserve(victims.size());
     for (auto& v : victims)
-        recs.push_back(kernels::EraseRec{v->evicted_hash.h1, v->evicted_hash.h2, v->addr()});
+        recs.push_back(kernels::EraseRec{v.hash.h1, v.hash.h2, v.block->addr()});
     if (erase_cap_ < recs.size()) {
         if (erase_buf_) cudaFree(erase_buf_);
         erase_buf_ = nullptr;
@@ -314,13 +314,13 @@ bool Server::erase_from_device_index(const std::vector<BlockPtr>& victims) {
 }
 
 bool Server::evict_some(size_t want, bool replica) {
-    std::vector<BlockPtr> victims;
+    std::vector<KVStore::Victim> victims;
     const size_t freed = store_->evict(want, replica, victims);
     if (victims.empty()) return false;
     if (!erase_from_device_index(victims)) {
         // cannot prove the entries unreachable: keep the space reserved rather than risk a
         // reader copying a reused block (the blocks leak until the next purge)
-        static std::vector<BlockPtr> quarantine;
+        static std::vector<KVStore::Victim> quarantine;
         quarantine.insert(quarantine.end(), victims.begin(), victims.end());
         return false;
     }

@@ -87,7 +87,7 @@ class Server {
     // Evict least-recently-used committed blocks covering `want` bytes: out of the map, out
     // of the device index (erase kernel, synchronised), then back to the pool.
     bool evict_some(size_t want, bool replica);
-    bool erase_from_device_index(const std::vector<BlockPtr>& victims);
+    bool erase_from_device_index(const std::vector<KVStore::Victim>& victims);
 
     int handle_exchange(Conn* c);
     int handle_pool_map(Conn* c);

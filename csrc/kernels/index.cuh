@@ -126,14 +126,24 @@ IS_HD const IndexWay* way_of(const IndexBucket* table, uint32_t slot) {
 // is already published (first writer wins) or both buckets are full (*full set).
 // Fast path: one CAS on the key's preferred way of bucket A - ONE fabric round trip for an
 // insertion into a lightly loaded table; the fields follow as posted stores, tag stays 0.
-// Slow path (that way is taken): read both buckets' fingerprints and take a free way of the
-// emptier bucket.  Two-choice placement keeps "both buckets full" out of reach at the load
-// the server sizes the table for (<= 0.5): none in 4e4 insertions at load 0.5, 3e-4 at 0.75.
+// Slow path (that way is taken): read the fingerprints of A, then of B, and take a free way
+// of the emptier bucket.  Two-choice placement keeps "both buckets full" out of reach at the
+// load the server sizes the table for (<= 0.5): none in 4e4 simulated insertions at load
+// 0.5, 3e-4 at 0.75.  The buckets are scanned one after the other (16 live registers, not
+// 32): this code is inlined into the copy kernels and must not cost them occupancy.
 IS_HD uint32_t take_way(IndexBucket* bk, uint64_t bi, uint32_t w, const IndexEntry& rec,
                         bool sys) {
-    st_u64(&bk->way[w].h2, rec.h2);  // posted; the tag stays 0
+    // posted stores, published by the writer's fence + tag store; the tag stays 0
+#if defined(__CUDA_ARCH__)
+    (void)sys;
+    bk->way[w].h2 = rec.h2;
+    bk->way[w].addr = rec.addr;
+    bk->way[w].size = rec.size;
+#else
+    st_u64(&bk->way[w].h2, rec.h2);
     st_u64(&bk->way[w].addr, rec.addr);
     st_u32(&bk->way[w].size, rec.size, sys);
+#endif
     return slot_id(bi, w) + 1;
 }
 IS_HD bool published_as(const IndexBucket* bk, uint32_t w, const IndexEntry& rec) {
@@ -141,61 +151,79 @@ IS_HD bool published_as(const IndexBucket* bk, uint32_t w, const IndexEntry& rec
     // collision with another key; the authoritative copy is the server's map either way
     return ld_acquire_u32(&bk->way[w].tag) != 0 && ld_u64(&bk->way[w].h2) == rec.h2;
 }
-#if defined(__CUDACC__)
-#define IS_HD_NOINLINE __host__ __device__ __noinline__
-#else
-#define IS_HD_NOINLINE inline
+// bit w set: way w of `bk` is free; bit 8 + w set: way w carries `h1` already.  Pure ALU on
+// one 64-byte read; kept small on purpose - this is inlined into the copy kernels, whose
+// control warp pays for every extra instruction-cache line on its critical path.
+IS_HD uint32_t scan_ways(const IndexBucket* bk, uint64_t h1) {
+    uint64_t h[kIndexWays];
+    ld_fingerprints(bk, h);
+    uint32_t m = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
 #endif
-// out of line: its 16 fingerprint registers must not inflate the copy kernels that inline
-// the one-CAS fast path
-IS_HD_NOINLINE uint32_t claim_slow(IndexBucket* table, uint64_t mask, const IndexEntry& rec,
-                                   bool sys, bool* full);
-
-IS_HD uint32_t claim(IndexBucket* table, uint64_t mask, const IndexEntry& rec, bool sys,
-                     bool* full) {
-    const uint64_t a = bucket_a(rec.h1, mask), b = bucket_b(rec.h1, rec.h2, mask);
-    const uint32_t w0 = first_way(rec.h2);
-    IndexBucket* ba = table + a;
-    IndexBucket* bb = table + b;
-    const uint64_t cur = cas_u64(&ba->h1[w0], 0, rec.h1, sys);
-    if (cur == 0) return take_way(ba, a, w0, rec, sys);
-    if (cur == rec.h1 && published_as(ba, w0, rec)) return 0;
-    return claim_slow(table, mask, rec, sys, full);
+    for (uint32_t w = 0; w < kIndexWays; ++w) {
+        m |= (h[w] == 0 ? 1u : 0u) << w;
+        m |= (h[w] == h1 ? 0x100u : 0u) << w;
+    }
+    return m;
 }
-
-IS_HD_NOINLINE uint32_t claim_slow(IndexBucket* table, uint64_t mask, const IndexEntry& rec,
-                                   bool sys, bool* full) {
+// does one of the ways flagged in `same` (bits 0..7) hold `rec`'s key, committed?
+IS_HD bool any_published(const IndexBucket* bk, uint32_t same, const IndexEntry& rec) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (uint32_t w = 0; same; ++w, same >>= 1)
+        if ((same & 1u) && published_as(bk, w, rec)) return true;
+    return false;
+}
+IS_HD uint32_t popcount8(uint32_t m) {
+    m = (m & 0x55u) + ((m >> 1) & 0x55u);
+    m = (m & 0x33u) + ((m >> 2) & 0x33u);
+    return (m & 0x0fu) + (m >> 4);
+}
+// The slow path of claim() below: both buckets are read, the emptier one is used.
+#define IDX_SLOW_PATH IS_HD
+IDX_SLOW_PATH uint32_t claim_slow(IndexBucket* table, uint64_t mask, const IndexEntry& rec,
+                                  bool sys, bool* full) {
     const uint64_t a = bucket_a(rec.h1, mask), b = bucket_b(rec.h1, rec.h2, mask);
     IndexBucket* ba = table + a;
     IndexBucket* bb = table + b;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (int attempt = 0; attempt < 4; ++attempt) {  // retried only when a CAS loses a race
-        uint64_t ha[kIndexWays], hb[kIndexWays];
-        ld_fingerprints(ba, ha);
-        ld_fingerprints(bb, hb);
-        uint32_t free_a = 0, free_b = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (uint32_t w = 0; w < kIndexWays; ++w) {
-            free_a += ha[w] == 0;
-            free_b += hb[w] == 0 && b != a;
-            if (ha[w] == rec.h1 && published_as(ba, w, rec)) return 0;
-            if (b != a && hb[w] == rec.h1 && published_as(bb, w, rec)) return 0;
-        }
-        if (free_a == 0 && free_b == 0) break;
-        const bool use_b = free_b > free_a;
+        const uint32_t ma = scan_ways(ba, rec.h1);
+        const uint32_t mb = b != a ? scan_ways(bb, rec.h1) : 0u;
+        if (((ma | mb) >> 8) &&
+            (any_published(ba, ma >> 8, rec) || any_published(bb, mb >> 8, rec)))
+            return 0;
+        const uint32_t free_a = ma & 0xffu, free_b = mb & 0xffu;
+        if ((free_a | free_b) == 0) break;
+        const bool use_b = popcount8(free_b) > popcount8(free_a);
         IndexBucket* bk = use_b ? bb : ba;
+        uint32_t m = use_b ? free_b : free_a;
 #if defined(__CUDA_ARCH__)
-#pragma unroll
+#pragma unroll 1
 #endif
-        for (uint32_t w = 0; w < kIndexWays; ++w) {
-            if ((use_b ? hb[w] : ha[w]) != 0) continue;
+        for (uint32_t w = 0; w < kIndexWays; ++w, m >>= 1) {
+            if (!(m & 1u)) continue;
             if (cas_u64(&bk->h1[w], 0, rec.h1, sys) == 0)
                 return take_way(bk, use_b ? b : a, w, rec, sys);
         }
     }
     *full = true;
     return 0;
+}
+
+IS_HD uint32_t claim(IndexBucket* table, uint64_t mask, const IndexEntry& rec, bool sys,
+                     bool* full) {
+    const uint64_t a = bucket_a(rec.h1, mask);
+    const uint32_t w0 = first_way(rec.h2);
+    IndexBucket* ba = table + a;
+    const uint64_t cur = cas_u64(&ba->h1[w0], 0, rec.h1, sys);
+    if (cur == 0) return take_way(ba, a, w0, rec, sys);
+    if (cur == rec.h1 && published_as(ba, w0, rec)) return 0;
+    return claim_slow(table, mask, rec, sys, full);
 }
 
 // The caller has fenced the block's data stores (and the claim's field stores): fence +
@@ -212,35 +240,45 @@ struct Found {
     uint32_t size;
 };
 
-// Round trip 1: the 16 fingerprints of both buckets and, speculatively, the tag of the
-// preferred way of bucket A (where the key sits unless that way was taken when it was
-// written).  Round trip 2: the fields.  A miss costs one round trip.
+// Search one bucket whose fingerprints are in `h`.  `tag0`: the already loaded tag of way
+// `w0` (pass w0 >= kIndexWays when none was loaded).
+IS_HD Found match_bucket(const IndexBucket* bk, uint64_t bi, const uint64_t (&h)[kIndexWays],
+                         const KeyHash& kh, uint32_t w0, uint32_t tag0) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t w = 0; w < kIndexWays; ++w) {
+        if (h[w] != kh.h1) continue;
+        const IndexWay* wy = &bk->way[w];
+        const uint32_t tag = w == w0 ? tag0 : ld_acquire_u32(&wy->tag);
+        if (tag == 0) continue;  // claimed, not committed
+        // all three fields in flight together: ONE round trip after the tag, not two
+        const uint64_t h2 = ld_u64(&wy->h2);
+        const uint64_t addr = ld_u64(&wy->addr);
+        const uint32_t size = ld_u32(&wy->size);
+        if (h2 != kh.h2) continue;
+        return Found{slot_id(bi, w) + 1, tag, addr, size};
+    }
+    return Found{0, 0, 0, 0};
+}
+
+// Round trip 1: the fingerprints of bucket A and, speculatively, the tag of the key's
+// preferred way (where it sits unless that way was taken when it was written).  Round trip 2:
+// the fields.  kBothAtOnce also fetches bucket B in round trip 1: a miss then costs one
+// round trip instead of two, for 16 more live registers - right for the lookup kernel
+// (get_match_last_index probes mostly absent keys), wrong inside a copy kernel.
+template <bool kBothAtOnce>
 IS_HD Found find(const IndexBucket* table, uint64_t mask, const KeyHash& kh) {
     const uint64_t a = bucket_a(kh.h1, mask), b = bucket_b(kh.h1, kh.h2, mask);
     const uint32_t w0 = first_way(kh.h2);
     uint64_t ha[kIndexWays], hb[kIndexWays];
     ld_fingerprints(table + a, ha);
-    ld_fingerprints(table + b, hb);
+    if constexpr (kBothAtOnce) ld_fingerprints(table + b, hb);
     const uint32_t tag0 = ld_acquire_u32(&table[a].way[w0].tag);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int which = 0; which < 2; ++which) {
-        const IndexBucket* bk = table + (which ? b : a);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (uint32_t w = 0; w < kIndexWays; ++w) {
-            if ((which ? hb[w] : ha[w]) != kh.h1) continue;
-            const IndexWay* wy = &bk->way[w];
-            const uint32_t tag = (which == 0 && w == w0) ? tag0 : ld_acquire_u32(&wy->tag);
-            if (tag == 0) continue;  // claimed, not committed
-            if (ld_u64(&wy->h2) != kh.h2) continue;
-            return Found{slot_id(which ? b : a, w) + 1, tag, ld_u64(&wy->addr), ld_u32(&wy->size)};
-        }
-        if (b == a) break;
-    }
-    return Found{0, 0, 0, 0};
+    const Found f = match_bucket(table + a, a, ha, kh, w0, tag0);
+    if (f.slot_plus1 || b == a) return f;
+    if constexpr (!kBothAtOnce) ld_fingerprints(table + b, hb);
+    return match_bucket(table + b, b, hb, kh, kIndexWays, 0);
 }
 
 // After the copy: is the entry the reader resolved still the one in the table?

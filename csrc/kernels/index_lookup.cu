@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(kLookupThreads)
     bool found = false;
     if (i < a.n) {
         const KeyHash kh = hash_key(a.key_bytes + a.key_off[i], a.key_len[i]);
-        const idx::Found h = idx::find(a.table, a.table_mask, kh);
+        const idx::Found h = idx::find<true>(a.table, a.table_mask, kh);
         found = h.slot_plus1 != 0;
         if (a.out_descs) {
             uint64_t src = 0;

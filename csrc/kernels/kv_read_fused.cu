@@ -42,7 +42,7 @@ struct Resolved {
 
 __device__ Resolved resolve(const ReadFusedLaunch& a, uint32_t block) {
     const KeyHash kh = hash_key(a.key_bytes + a.key_off[block], a.key_len[block]);
-    const idx::Found f = idx::find(a.table, a.table_mask, kh);
+    const idx::Found f = idx::find<false>(a.table, a.table_mask, kh);
     if (!f.slot_plus1) return Resolved{0, 0, 0};
     const uint32_t seg = uint32_t(f.addr >> 44) - 1;
     if (f.size < a.bytes || seg >= a.nsegs || !a.seg_base[seg]) return Resolved{0, 0, 0};
@@ -50,9 +50,7 @@ __device__ Resolved resolve(const ReadFusedLaunch& a, uint32_t block) {
 }
 
 template <int VEC>
-// 4 CTAs per SM (56 registers): the 16 fingerprints of idx::find cost the resolver warp a
-// few spilled words, not the copy warps their occupancy
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads)
     kv_read_fused_kernel(const __grid_constant__ ReadFusedLaunch a, uint32_t chunk, uint32_t cpb) {
     __shared__ uint64_t src_of[2][kRound];
     const uint32_t total = a.n * cpb;

@@ -196,7 +196,7 @@ static void test_hash() {
 static void test_kv_store_eviction() {
     MM mm;
     mm.add_pool(8 * 16384, 16384, -1);
-    KVStore st(&mm);
+    KVStore st(&mm, true);
     std::vector<RemoteBlock> out, found;
     std::vector<std::string> names;
     for (int i = 0; i < 8; ++i) names.push_back("k" + std::to_string(i));
@@ -213,12 +213,12 @@ static void test_kv_store_eviction() {
     std::vector<BlockPtr> lease;
     CHECK(st.lookup({"k1"}, 1, found, &lease) == kFinish);
     CHECK(st.lookup({"k0"}, 1, found, nullptr) == kFinish);
-    std::vector<BlockPtr> victims;
+    std::vector<KVStore::Victim> victims;
     CHECK(st.evict(2 * 16384, false, victims) == 2 * 16384 && victims.size() == 2);
     CHECK(!st.present("k2") && !st.present("k3") && st.present("k1") && st.present("k0"));
     const KeyHash h2 = hash_key(reinterpret_cast<const uint8_t*>("k2"), 2);
-    CHECK(victims[0]->evicted_hash.h1 == h2.h1 && victims[0]->evicted_hash.h2 == h2.h2);
-    CHECK(victims[0]->addr() == addrs[2]);
+    CHECK(victims[0].hash.h1 == h2.h1 && victims[0].hash.h2 == h2.h2);
+    CHECK(victims[0].block->addr() == addrs[2]);
     CHECK(mm.used_bytes() == 8 * 16384);  // victims still hold the space
     victims.clear();
     CHECK(mm.used_bytes() == 6 * 16384 && st.evicted() == 2);
@@ -256,15 +256,17 @@ static void test_device_index_logic() {
         const IndexEntry r = rec_of(i);
         slot[size_t(i)] = idx::claim(table.data(), mask, r, true, &full);
         CHECK(slot[size_t(i)] != 0 && !full);
-        CHECK(idx::find(table.data(), mask, KeyHash{r.h1, r.h2}).slot_plus1 == 0);
+        CHECK(idx::find<true>(table.data(), mask, KeyHash{r.h1, r.h2}).slot_plus1 == 0);
         idx::commit(table.data(), slot[size_t(i)], r.tag, true);
     }
     for (int i = 0; i < 600; ++i) {
         const IndexEntry r = rec_of(i);
-        const idx::Found f = idx::find(table.data(), mask, KeyHash{r.h1, r.h2});
+        const idx::Found f = idx::find<true>(table.data(), mask, KeyHash{r.h1, r.h2});
         if (i < 512) {
             CHECK(f.slot_plus1 == slot[size_t(i)] && f.tag == r.tag && f.addr == r.addr && f.size == 4096);
             CHECK(idx::still_valid(table.data(), f.slot_plus1, f.tag));
+            const idx::Found g = idx::find<false>(table.data(), mask, KeyHash{r.h1, r.h2});
+            CHECK(g.slot_plus1 == f.slot_plus1 && g.tag == f.tag && g.addr == f.addr);
         } else {
             CHECK(f.slot_plus1 == 0);
         }
@@ -275,7 +277,7 @@ static void test_device_index_logic() {
         IndexEntry r = rec_of(7);
         r.addr += 64;
         CHECK(idx::claim(table.data(), mask, r, true, &full) == 0 && !full);
-        CHECK(idx::find(table.data(), mask, KeyHash{r.h1, r.h2}).addr == rec_of(7).addr);
+        CHECK(idx::find<true>(table.data(), mask, KeyHash{r.h1, r.h2}).addr == rec_of(7).addr);
     }
     // eviction: the way becomes empty, readers that resolved it notice, the key can return
     for (int i = 0; i < 512; i += 2) {
@@ -283,11 +285,11 @@ static void test_device_index_logic() {
         CHECK(idx::erase(table.data(), mask, r.h1, r.h2, r.addr));
         CHECK(!idx::erase(table.data(), mask, r.h1, r.h2, r.addr));
         CHECK(!idx::still_valid(table.data(), slot[size_t(i)], r.tag));
-        CHECK(idx::find(table.data(), mask, KeyHash{r.h1, r.h2}).slot_plus1 == 0);
+        CHECK(idx::find<true>(table.data(), mask, KeyHash{r.h1, r.h2}).slot_plus1 == 0);
     }
     for (int i = 1; i < 512; i += 2) {
         const IndexEntry r = rec_of(i);
-        CHECK(idx::find(table.data(), mask, KeyHash{r.h1, r.h2}).slot_plus1 == slot[size_t(i)]);
+        CHECK(idx::find<true>(table.data(), mask, KeyHash{r.h1, r.h2}).slot_plus1 == slot[size_t(i)]);
     }
     size_t used = 0;
     for (auto& b : table)
@@ -300,7 +302,7 @@ static void test_device_index_logic() {
         const uint32_t s = idx::claim(table.data(), mask, r, true, &full);
         CHECK(s != 0);
         idx::commit(table.data(), s, r.tag, true);
-        CHECK(idx::find(table.data(), mask, KeyHash{r.h1, r.h2}).tag == r.tag);
+        CHECK(idx::find<true>(table.data(), mask, KeyHash{r.h1, r.h2}).tag == r.tag);
     }
     // overfull table: the failure is reported, everything claimed stays findable
     std::vector<IndexBucket> tiny(2);
@@ -336,7 +338,7 @@ static void test_device_index_logic() {
         int missing = 0;
         for (int i = 0; i < int(big / 2); ++i) {
             const IndexEntry r = rec_of(i);
-            missing += idx::find(t.data(), index_bucket_mask(big), KeyHash{r.h1, r.h2}).addr != r.addr;
+            missing += idx::find<true>(t.data(), index_bucket_mask(big), KeyHash{r.h1, r.h2}).addr != r.addr;
         }
         CHECK(missing == 0);
     }
@@ -349,7 +351,7 @@ static void test_device_index_logic() {
         const uint32_t s = idx::claim(one.data(), 0, r, true, &full);
         CHECK(s != 0);
         idx::commit(one.data(), s, r.tag, true);
-        CHECK(idx::find(one.data(), 0, KeyHash{r.h1, r.h2}).addr == r.addr);
+        CHECK(idx::find<true>(one.data(), 0, KeyHash{r.h1, r.h2}).addr == r.addr);
     }
 }
 
@@ -404,7 +406,8 @@ static void test_device_index_concurrent() {
         std::mt19937 rng{seed};
         while (!stop.load()) {
             const int i = int(rng() % kKeys);
-            const idx::Found f = idx::find(table.data(), mask, ks[size_t(i)].h);
+            const idx::Found f = (seed & 1) ? idx::find<true>(table.data(), mask, ks[size_t(i)].h)
+                                            : idx::find<false>(table.data(), mask, ks[size_t(i)].h);
             if (!f.slot_plus1) continue;
             const uint64_t seen_addr = f.addr;
             idx::fence(true);  // "the copy"

@@ -106,26 +106,26 @@ def test_hbm_pool_evicts_lru_blocks_and_device_index_follows(device_lookup):
                               conn.allocate_rdma(keys, elems * 4))
         conn.sync()
         assert srv.stats()["used_bytes"] == n * 16384
-        # 200 new blocks need room: two eviction rounds of 25 % (128 blocks) each
+        # 200 new blocks need room: one eviction round frees max(need, 25 % of the pool)
         new = [f"new-{i}" for i in range(200)]
         conn.rdma_write_cache(src, [(n + i) * elems for i in range(200)], elems,
                               conn.allocate_rdma(new, elems * 4))
         conn.sync()
         st = srv.stats()
-        assert st["evicted"] == 256 and st["keys"] == n - 256 + 200
-        # the 256 oldest are gone, for the host map and for the device index alike
-        assert not conn.check_exist("old-0") and not conn.check_exist("old-255")
-        assert conn.check_exist("old-256") and conn.check_exist("new-199")
-        conn.read_cache(dst, [("old-3", 0)], elems)
-        with pytest.raises(Exception):
+        assert st["evicted"] == 200 and st["keys"] == n
+        # the 200 oldest are gone, for the host map and for the device index alike
+        assert not conn.check_exist("old-0") and not conn.check_exist("old-199")
+        assert conn.check_exist("old-200") and conn.check_exist("new-199")
+        with pytest.raises(Exception):  # host lookup: 404 at once; device lookup: at sync()
+            conn.read_cache(dst, [("old-3", 0)], elems)
             conn.sync()
         # survivors and new blocks read back bit-exact (fused path: >= SM-count blocks)
-        q = [(f"old-{i}", (i - 256) * elems) for i in range(256, n)]
-        q += [(f"new-{i}", (256 + i) * elems) for i in range(200)]
+        q = [(f"old-{i}", (i - 200) * elems) for i in range(200, n)]
+        q += [(f"new-{i}", (n - 200 + i) * elems) for i in range(200)]
         conn.read_cache(dst, q, elems)
         conn.sync()
-        want = torch.cat([src[256 * elems:n * elems], src[n * elems:(n + 200) * elems]])
-        assert torch.equal(dst[:(256 + 200) * elems], want)
+        want = torch.cat([src[200 * elems:n * elems], src[n * elems:(n + 200) * elems]])
+        assert torch.equal(dst, want)
         # small batch (lookup + copy + validate path)
         dst.zero_()
         conn.read_cache(dst, [("new-7", 0), ("old-300", elems)], elems)
