@@ -20,7 +20,8 @@ def ring_peer(rank: int, world: int, hop: int = 1) -> int:
 
 def start_shard_server(device: int, port: int, pool_bytes: int, granule_kb: int = 64,
                        host: str = "127.0.0.1", auto_increase: bool = False,
-                       log_level: str = "warning"):
+                       log_level: str = "warning", evict: bool = False,
+                       evict_ratio: float = 0.05):
     """Start a store server thread in this process with an HBM pool on `device`.
     Returns the native Server object (keep a reference; ``.stop()`` to shut down)."""
     cfg = _infinistore.ServerConfig()
@@ -31,6 +32,8 @@ def start_shard_server(device: int, port: int, pool_bytes: int, granule_kb: int 
     cfg.prealloc_bytes = pool_bytes
     cfg.minimal_allocate_size = granule_kb
     cfg.auto_increase = auto_increase
+    cfg.evict = evict
+    cfg.evict_ratio = evict_ratio
     cfg.log_level = log_level
     srv = _infinistore.Server(cfg)
     srv.start()
