@@ -240,15 +240,34 @@ struct Found {
     uint32_t size;
 };
 
-// Search one bucket whose fingerprints are in `h`.  `tag0`: the already loaded tag of way
-// `w0` (pass w0 >= kIndexWays when none was loaded).
-IS_HD Found match_bucket(const IndexBucket* bk, uint64_t bi, const uint64_t (&h)[kIndexWays],
-                         const KeyHash& kh, uint32_t w0, uint32_t tag0) {
+// bit w set: way w carries the fingerprint h1
+IS_HD uint32_t match_mask(const uint64_t (&h)[kIndexWays], uint64_t h1) {
+    uint32_t m = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (uint32_t w = 0; w < kIndexWays; ++w) {
-        if (h[w] != kh.h1) continue;
+    for (uint32_t w = 0; w < kIndexWays; ++w) m |= (h[w] == h1 ? 1u : 0u) << w;
+    return m;
+}
+IS_HD uint32_t lowest_bit(uint32_t m) {
+#if defined(__CUDA_ARCH__)
+    return uint32_t(__ffs(int(m))) - 1u;
+#else
+    return uint32_t(__builtin_ctz(m));
+#endif
+}
+
+// Check the ways of one bucket whose fingerprint matched (`m`).  `tag0`: the already loaded
+// tag of way `w0` (pass w0 >= kIndexWays when none was loaded).  A rolled loop on purpose:
+// almost always one iteration, and the unrolled form cost every reader kilobytes of
+// instruction fetch on a cold kernel.
+IS_HD Found match_bucket(const IndexBucket* bk, uint64_t bi, uint32_t m, const KeyHash& kh,
+                         uint32_t w0, uint32_t tag0) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (; m; m &= m - 1) {
+        const uint32_t w = lowest_bit(m);
         const IndexWay* wy = &bk->way[w];
         const uint32_t tag = w == w0 ? tag0 : ld_acquire_u32(&wy->tag);
         if (tag == 0) continue;  // claimed, not committed
@@ -265,20 +284,35 @@ IS_HD Found match_bucket(const IndexBucket* bk, uint64_t bi, const uint64_t (&h)
 // Round trip 1: the fingerprints of bucket A and, speculatively, the tag of the key's
 // preferred way (where it sits unless that way was taken when it was written).  Round trip 2:
 // the fields.  kBothAtOnce also fetches bucket B in round trip 1: a miss then costs one
-// round trip instead of two, for 16 more live registers - right for the lookup kernel
-// (get_match_last_index probes mostly absent keys), wrong inside a copy kernel.
+// round trip instead of two - right for get_match_last_index, which probes mostly absent
+// keys; the read path, whose keys are almost always in bucket A, skips those four loads.
 template <bool kBothAtOnce>
 IS_HD Found find(const IndexBucket* table, uint64_t mask, const KeyHash& kh) {
     const uint64_t a = bucket_a(kh.h1, mask), b = bucket_b(kh.h1, kh.h2, mask);
     const uint32_t w0 = first_way(kh.h2);
-    uint64_t ha[kIndexWays], hb[kIndexWays];
-    ld_fingerprints(table + a, ha);
-    if constexpr (kBothAtOnce) ld_fingerprints(table + b, hb);
-    const uint32_t tag0 = ld_acquire_u32(&table[a].way[w0].tag);
-    const Found f = match_bucket(table + a, a, ha, kh, w0, tag0);
+    uint32_t ma, mb = 0;
+    uint32_t tag0;
+    {
+        uint64_t ha[kIndexWays];
+        ld_fingerprints(table + a, ha);
+        if constexpr (kBothAtOnce) {
+            uint64_t hb[kIndexWays];
+            ld_fingerprints(table + b, hb);
+            tag0 = ld_acquire_u32(&table[a].way[w0].tag);
+            mb = match_mask(hb, kh.h1);
+        } else {
+            tag0 = ld_acquire_u32(&table[a].way[w0].tag);
+        }
+        ma = match_mask(ha, kh.h1);
+    }
+    const Found f = match_bucket(table + a, a, ma, kh, w0, tag0);
     if (f.slot_plus1 || b == a) return f;
-    if constexpr (!kBothAtOnce) ld_fingerprints(table + b, hb);
-    return match_bucket(table + b, b, hb, kh, kIndexWays, 0);
+    if constexpr (!kBothAtOnce) {
+        uint64_t hb[kIndexWays];
+        ld_fingerprints(table + b, hb);
+        mb = match_mask(hb, kh.h1);
+    }
+    return match_bucket(table + b, b, mb, kh, kIndexWays, 0);
 }
 
 // After the copy: is the entry the reader resolved still the one in the table?

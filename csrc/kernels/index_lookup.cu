@@ -25,14 +25,18 @@ namespace {
 
 using namespace dev;
 
-constexpr int kLookupThreads = 128;
+// one warp per CTA: a batch of lookups spreads over many SMs instead of queueing hundreds of
+// fabric loads behind one SM's load unit
+constexpr int kLookupThreads = 32;
 __global__ void __launch_bounds__(kLookupThreads)
     kv_index_lookup_kernel(const __grid_constant__ LookupLaunch a) {
     const uint32_t i = blockIdx.x * kLookupThreads + threadIdx.x;
     bool found = false;
     if (i < a.n) {
         const KeyHash kh = hash_key(a.key_bytes + a.key_off[i], a.key_len[i]);
-        const idx::Found h = idx::find<true>(a.table, a.table_mask, kh);
+        // reads resolve present keys (bucket A first), match / exist probes mostly absent ones
+        const idx::Found h = a.present ? idx::find<true>(a.table, a.table_mask, kh)
+                                       : idx::find<false>(a.table, a.table_mask, kh);
         found = h.slot_plus1 != 0;
         if (a.out_descs) {
             uint64_t src = 0;
