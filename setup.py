@@ -3,7 +3,7 @@
 import os
 import sys
 
-from setuptools import find_packages, setup
+from setuptools import Distribution, find_packages, setup
 from setuptools.command.build_py import build_py
 from setuptools.command.develop import develop
 
@@ -29,7 +29,15 @@ class Develop(develop):
         super().run()
 
 
+class BinaryDistribution(Distribution):
+    """The package ships a prebuilt CPython extension: tag the wheel for this platform/ABI."""
+
+    def has_ext_modules(self):
+        return True
+
+
 setup(
+    distclass=BinaryDistribution,
     name="infinistore-b200",
     version="0.1.0",
     description="Blackwell-native KV-cache block store with infiniStore's API",
