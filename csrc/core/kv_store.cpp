@@ -1,19 +1,95 @@
 #include "kv_store.h"
 
 #include <algorithm>
+#include <new>
 
 #include "log.h"
 
 namespace istore {
 
-Block*& KVStore::inflight_slot(uint32_t seg, uint64_t offset) {
-    if (inflight_.size() <= seg) inflight_.resize(seg + 1);
-    std::vector<Block*>& v = inflight_[seg];
-    const MemoryPool& pool = mm_->pool(seg);
-    if (v.size() != pool.total_blocks()) v.assign(pool.total_blocks(), nullptr);
-    return v[offset / pool.granule()];
+namespace {
+constexpr size_t kInitialSlots = 1024;
 }
 
+KVStore::KVStore(MM* mm, bool track_recency) : mm_(mm), track_lru_(track_recency) {
+    table_.resize(kInitialSlots);
+}
+
+KVStore::~KVStore() { purge(); }
+
+// ---------------------------------------------------------------- flat table
+Block* KVStore::find(std::string_view key, uint64_t h) const {
+    const size_t mask = table_.size() - 1;
+    for (size_t i = size_t(h) & mask;; i = (i + 1) & mask) {
+        const Slot& s = table_[i];
+        if (!s.block) return nullptr;
+        if (s.hash == h && s.block->key() == key) return s.block;
+    }
+}
+
+void KVStore::grow() {
+    std::vector<Slot> old(table_.size() * 2);
+    old.swap(table_);
+    const size_t mask = table_.size() - 1;
+    for (const Slot& s : old) {
+        if (!s.block) continue;
+        size_t i = size_t(s.hash) & mask;
+        while (table_[i].block) i = (i + 1) & mask;
+        table_[i] = s;
+    }
+}
+
+void KVStore::insert(Block* b) {
+    if ((count_ + 1) * 10 > table_.size() * 6) grow();  // load <= 0.6
+    const size_t mask = table_.size() - 1;
+    size_t i = size_t(b->hash) & mask;
+    while (table_[i].block) i = (i + 1) & mask;
+    table_[i] = Slot{b->hash, b};
+    ++count_;
+}
+
+BlockPtr KVStore::remove(Block* b) {
+    const size_t mask = table_.size() - 1;
+    size_t i = size_t(b->hash) & mask;
+    while (table_[i].block != b) {
+        if (!table_[i].block) return BlockPtr();  // not in the table
+        i = (i + 1) & mask;
+    }
+    // backward-shift deletion keeps every probe sequence intact without tombstones
+    size_t hole = i;
+    for (size_t j = (hole + 1) & mask; table_[j].block; j = (j + 1) & mask) {
+        const size_t home = size_t(table_[j].hash) & mask;
+        // may entry j move into the hole?  only if its home is not cyclically in (hole, j]
+        const bool stays = hole <= j ? (home > hole && home <= j) : (home > hole || home <= j);
+        if (stays) continue;
+        table_[hole] = table_[j];
+        hole = j;
+    }
+    table_[hole] = Slot{};
+    --count_;
+    return BlockPtr(b);  // adopts the count the table held
+}
+
+Block* KVStore::new_block(std::string_view key, uint64_t h, const Allocation& a, size_t size,
+                          uint32_t gen, uint64_t conn) const {
+    const size_t header = track_lru_ ? sizeof(LruBlock) : sizeof(Block);
+    void* mem = std::malloc(header + key.size());
+    if (!mem) throw std::bad_alloc();
+    Block* b = track_lru_ ? static_cast<Block*>(new (mem) LruBlock()) : new (mem) Block();
+    b->seg = a.seg;
+    b->mm = mm_;
+    b->offset = a.offset;
+    b->size = uint32_t(size);
+    b->gen = gen;
+    b->owner = conn;
+    b->hash = h;
+    b->key_len = uint32_t(key.size());
+    b->key_off = uint16_t(header);
+    std::memcpy(reinterpret_cast<char*>(mem) + header, key.data(), key.size());
+    return b;
+}
+
+// ---------------------------------------------------------------- recency list
 void KVStore::lru_push_front(LruBlock* b) {
     b->lru_prev = nullptr;
     b->lru_next = lru_head_;
@@ -31,39 +107,59 @@ void KVStore::lru_unlink(LruBlock* b) {
     b->in_lru = false;
 }
 
+Block*& KVStore::inflight_slot(uint32_t seg, uint64_t offset) {
+    if (inflight_.size() <= seg) inflight_.resize(seg + 1);
+    std::vector<Block*>& v = inflight_[seg];
+    const MemoryPool& pool = mm_->pool(seg);
+    if (v.size() != pool.total_blocks()) v.assign(pool.total_blocks(), nullptr);
+    return v[offset / pool.granule()];
+}
+
+// ---------------------------------------------------------------- store operations
 int KVStore::reserve(const std::vector<std::string_view>& keys, size_t size, int device_hint,
                      uint64_t conn, std::vector<RemoteBlock>& out) {
     out.assign(keys.size(), RemoteBlock{0, 0, 0});
     // Decide about duplicates first, then allocate exactly what is needed: nothing leaks for
-    // deduplicated keys.  A placeholder entry per fresh key also catches duplicates inside
-    // the batch (the second occurrence finds the placeholder).
-    using Iter = decltype(map_)::iterator;
-    std::vector<std::pair<size_t, Iter>> fresh;
+    // deduplicated keys.  Duplicates inside the batch are caught by comparing against the
+    // fresh keys of the batch that share the hash (rare: checked linearly among equals only).
+    struct Fresh {
+        size_t idx;
+        uint64_t hash;
+    };
+    std::vector<Fresh> fresh;
     fresh.reserve(keys.size());
+    // small open-addressing set of the batch's own hashes -> position in `fresh`
+    size_t cap = 16;
+    while (cap < keys.size() * 2) cap <<= 1;
+    std::vector<uint32_t> seen(cap, UINT32_MAX);
     for (size_t i = 0; i < keys.size(); ++i) {
-        if (map_.find(keys[i]) != map_.end()) continue;
-        fresh.emplace_back(i, map_.emplace(std::string(keys[i]), nullptr).first);
+        const uint64_t h = hash_of(keys[i]);
+        if (find(keys[i], h)) continue;
+        bool dup = false;
+        size_t s = size_t(h) & (cap - 1);
+        for (; seen[s] != UINT32_MAX; s = (s + 1) & (cap - 1)) {
+            const Fresh& f = fresh[seen[s]];
+            if (f.hash == h && keys[f.idx] == keys[i]) {
+                dup = true;
+                break;
+            }
+        }
+        if (dup) continue;
+        seen[s] = uint32_t(fresh.size());
+        fresh.push_back(Fresh{i, h});
     }
     std::vector<Allocation> allocs;
     allocs.reserve(fresh.size());
-    if (!mm_->allocate(size, fresh.size(), device_hint, allocs)) {
-        for (auto& f : fresh) map_.erase(f.second);
-        return kOutOfMemory;
-    }
+    if (!mm_->allocate(size, fresh.size(), device_hint, allocs)) return kOutOfMemory;
     for (size_t j = 0; j < fresh.size(); ++j) {
-        const size_t i = fresh[j].first;
+        const size_t i = fresh[j].idx;
         uint32_t gen = next_gen_++;
         if (next_gen_ == 0) next_gen_ = 1;  // 0 means "not committed" in the device index
-        BlockPtr blk =
-            track_lru_ ? std::static_pointer_cast<Block>(std::make_shared<LruBlock>(
-                             mm_, allocs[j].seg, allocs[j].offset, uint32_t(size), gen, conn))
-                       : std::make_shared<Block>(mm_, allocs[j].seg, allocs[j].offset,
-                                                 uint32_t(size), gen, conn);
-        blk->key = &fresh[j].second->first;
-        inflight_slot(allocs[j].seg, allocs[j].offset) = blk.get();
+        Block* blk = new_block(keys[i], fresh[j].hash, allocs[j], size, gen, conn);
+        inflight_slot(allocs[j].seg, allocs[j].offset) = blk;
         ++inflight_count_;
         out[i] = RemoteBlock{allocs[j].seg + 1, gen, blk->addr()};
-        fresh[j].second->second = std::move(blk);
+        insert(blk);  // the table owns the creator's count
     }
     return kFinish;
 }
@@ -91,30 +187,35 @@ int KVStore::lookup(const std::vector<std::string_view>& keys, size_t need,
                     std::vector<RemoteBlock>& out, std::vector<BlockPtr>* lease) {
     out.clear();
     out.reserve(keys.size());
+    const size_t lease_mark = lease ? lease->size() : 0;
     for (auto k : keys) {
-        auto it = map_.find(k);
-        if (it == map_.end() || !it->second->committed) {
+        Block* b = find(k);
+        int code = kFinish;
+        if (!b || !b->committed)
+            code = kKeyNotFound;
+        else if (b->size < need)  // never let a reader run past what was written
+            code = kInvalidReq;
+        if (code != kFinish) {
             out.clear();
-            return kKeyNotFound;
+            if (lease) lease->resize(lease_mark);
+            return code;
         }
-        Block& b = *it->second;
-        if (b.size < need) {  // never let a reader run past what was written
-            out.clear();
-            return kInvalidReq;
+        out.push_back(RemoteBlock{b->seg + 1, b->gen, b->addr()});
+        if (lease) {
+            ++b->refs;
+            lease->push_back(BlockPtr(b));
         }
-        out.push_back(RemoteBlock{b.seg + 1, b.gen, b.addr()});
-        if (lease) lease->push_back(it->second);
-        if (track_lru_ && lru_head_ != &b) {
-            lru_unlink(static_cast<LruBlock*>(&b));
-            lru_push_front(static_cast<LruBlock*>(&b));
+        if (track_lru_ && lru_head_ != b) {
+            lru_unlink(static_cast<LruBlock*>(b));
+            lru_push_front(static_cast<LruBlock*>(b));
         }
     }
     return kFinish;
 }
 
 bool KVStore::exists_committed(std::string_view key) const {
-    auto it = map_.find(key);
-    return it != map_.end() && it->second->committed;
+    const Block* b = find(key);
+    return b && b->committed;
 }
 
 // Exact replay of the reference's search (src/infinistore.cpp:1092-1108): presence is
@@ -142,8 +243,7 @@ size_t KVStore::drop_uncommitted(uint64_t conn) {
             slot = nullptr;
             --inflight_count_;
             ++n;
-            const std::string key = *b->key;  // copy: erasing frees the node that owns it
-            map_.erase(key);
+            remove(b);  // the returned reference dies here: space back to the pool
         }
     }
     return n;
@@ -154,18 +254,14 @@ size_t KVStore::evict(size_t bytes, bool replica, std::vector<Victim>& victims) 
     LruBlock* b = lru_tail_;
     while (b && freed < bytes) {
         LruBlock* more_recent = b->lru_prev;
-        auto it = map_.find(*b->key);
         const bool in_replica = mm_->pool(b->seg).device() == kReplicaDevice;
-        if (it != map_.end() && in_replica == replica &&
-            it->second.use_count() == 1) {  // nobody is reading it
+        if (in_replica == replica && b->refs == 1) {  // only the table holds it: nobody reads
             const size_t g = mm_->pool(b->seg).granule();
             freed += (size_t(b->size) + g - 1) / g * g;
             lru_unlink(b);
-            const KeyHash kh =
-                hash_key(reinterpret_cast<const uint8_t*>(b->key->data()), b->key->size());
-            victims.push_back(Victim{std::move(it->second), kh});
-            map_.erase(it);  // frees the node that owns *b->key; victims keeps the block alive
-            b->key = nullptr;
+            const std::string_view key = b->key();
+            const KeyHash kh = hash_key(reinterpret_cast<const uint8_t*>(key.data()), key.size());
+            victims.push_back(Victim{remove(b), kh});
             ++evicted_;
         }
         b = more_recent;
@@ -174,11 +270,17 @@ size_t KVStore::evict(size_t bytes, bool replica, std::vector<Victim>& victims) 
 }
 
 size_t KVStore::purge() {
-    const size_t n = map_.size();
-    lru_head_ = lru_tail_ = nullptr;
+    const size_t n = count_;
     for (auto& seg : inflight_) std::fill(seg.begin(), seg.end(), nullptr);
     inflight_count_ = 0;
-    map_.clear();
+    lru_head_ = lru_tail_ = nullptr;
+    for (Slot& s : table_) {
+        if (!s.block) continue;
+        s.block->in_lru = false;  // a leased block outlives the list it was linked in
+        BlockPtr drop(s.block);   // the table's count
+        s = Slot{};
+    }
+    count_ = 0;
     return n;
 }
 

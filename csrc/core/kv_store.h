@@ -12,13 +12,21 @@
 // before committing does not leave a permanently reserved key, and an
 // LRU order over the committed blocks so that a full pool can evict instead of answering
 // 507 until an operator purges it (the reference has no eviction).
+//
+// Layout.  The reference keeps `unordered_map<string, intrusive_ptr<PTR>>`: a node, a key
+// string and a PTR allocation per block.  Here a block is ONE allocation (header + key
+// bytes, intrusive count as in the reference's PTR) and the map is a flat open-addressing
+// table of {64-bit key hash, block pointer}: allocate costs ~100 ns per key instead of ~250,
+// and the commit path touches one cache line per block.
+// Threading: a KVStore and every BlockPtr to its blocks are used under the server mutex only.
 #pragma once
 
 #include <cstdint>
-#include <memory>
+#include <cstdlib>
+#include <cstring>
 #include <string>
 #include <string_view>
-#include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "hash.h"
@@ -28,50 +36,72 @@
 namespace istore {
 
 struct Block {
-    MM* mm;
+    uint32_t refs = 1;  // intrusive count (server mutex); the creator holds the first one
     uint32_t seg;
+    MM* mm;
     uint64_t offset;
     uint32_t size;
     uint32_t gen;
+    uint64_t owner;  // connection id that reserved it (0 once committed)
+    uint64_t hash;   // table hash of the key
+    uint32_t key_len;
+    uint16_t key_off;  // key bytes start this far behind `this` (header size of the block kind)
     bool committed = false;
-    uint64_t owner = 0;  // connection id that reserved it (0 once committed)
-    const std::string* key = nullptr;  // the map node's key (node addresses are stable)
-    Block(MM* m, uint32_t s, uint64_t o, uint32_t sz, uint32_t g, uint64_t own)
-        : mm(m), seg(s), offset(o), size(sz), gen(g), owner(own) {}
-    ~Block() { mm->deallocate(seg, offset, size); }
-    Block(const Block&) = delete;
-    Block& operator=(const Block&) = delete;
+    bool in_lru = false;
+
+    std::string_view key() const {
+        return std::string_view(reinterpret_cast<const char*>(this) + key_off, key_len);
+    }
     uint64_t addr() const { return make_addr(seg, offset); }
 };
-using BlockPtr = std::shared_ptr<Block>;
 
 // A block of a store that evicts: the recency links live in a derived type so that the
-// default configuration (no eviction, the reference's behaviour) keeps the smaller block -
+// default configuration (no eviction, the reference's behaviour) keeps the smaller header -
 // the commit path is bound by cache misses on these objects (measured: 16 more bytes per
 // block cost ~5 ns per committed block, 20 % of the 4 KB write rate).
 struct LruBlock : Block {
-    using Block::Block;
     LruBlock* lru_prev = nullptr;  // towards more recently used; linked only while committed
     LruBlock* lru_next = nullptr;  // towards less recently used
-    bool in_lru = false;
 };
 
-struct StrHash {
-    using is_transparent = void;
-    size_t operator()(std::string_view s) const {
-        return size_t(hash_bytes(reinterpret_cast<const uint8_t*>(s.data()), s.size(), kHashSeed1));
+// Counted reference to a block; dropping the last one returns the pool space.
+class BlockPtr {
+   public:
+    BlockPtr() = default;
+    explicit BlockPtr(Block* adopt) : b_(adopt) {}  // takes over one existing count
+    BlockPtr(const BlockPtr& o) : b_(o.b_) {
+        if (b_) ++b_->refs;
     }
-    size_t operator()(const std::string& s) const { return (*this)(std::string_view(s)); }
-};
-struct StrEq {
-    using is_transparent = void;
-    bool operator()(std::string_view a, std::string_view b) const { return a == b; }
+    BlockPtr(BlockPtr&& o) noexcept : b_(o.b_) { o.b_ = nullptr; }
+    BlockPtr& operator=(BlockPtr o) noexcept {
+        std::swap(b_, o.b_);
+        return *this;
+    }
+    ~BlockPtr() { reset(); }
+    void reset() {
+        if (b_ && --b_->refs == 0) {
+            b_->mm->deallocate(b_->seg, b_->offset, b_->size);
+            std::free(b_);
+        }
+        b_ = nullptr;
+    }
+    Block* get() const { return b_; }
+    Block* operator->() const { return b_; }
+    Block& operator*() const { return *b_; }
+    explicit operator bool() const { return b_ != nullptr; }
+    uint32_t use_count() const { return b_ ? b_->refs : 0; }
+
+   private:
+    Block* b_ = nullptr;
 };
 
 class KVStore {
    public:
     // track_recency: keep the LRU order that evict() needs (every block is an LruBlock)
-    explicit KVStore(MM* mm, bool track_recency = false) : mm_(mm), track_lru_(track_recency) {}
+    explicit KVStore(MM* mm, bool track_recency = false);
+    ~KVStore();
+    KVStore(const KVStore&) = delete;
+    KVStore& operator=(const KVStore&) = delete;
 
     // Reserve blocks for `keys`.  out[i] is the locator of key i, or the fake (0,0) block
     // when the key already exists (first writer wins).  Returns kFinish, or kOutOfMemory
@@ -87,7 +117,7 @@ class KVStore {
     int lookup(const std::vector<std::string_view>& keys, size_t need,
                std::vector<RemoteBlock>& out, std::vector<BlockPtr>* lease);
     bool exists_committed(std::string_view key) const;
-    bool present(std::string_view key) const { return map_.find(key) != map_.end(); }
+    bool present(std::string_view key) const { return find(key) != nullptr; }
     int match_last_index(const std::vector<std::string_view>& keys) const;
     // Drop every uncommitted block reserved by `conn` (connection closed).
     size_t drop_uncommitted(uint64_t conn);
@@ -104,18 +134,33 @@ class KVStore {
         KeyHash hash;  // fingerprint of the evicted key (its device-index entry)
     };
     size_t evict(size_t bytes, bool replica, std::vector<Victim>& victims);
-
     uint64_t evicted() const { return evicted_; }
-    size_t size() const { return map_.size(); }
+    size_t size() const { return count_; }
     // Visit every committed block (checkpointing).
     template <typename F>
     void for_each_committed(F&& fn) const {
-        for (auto& kv : map_)
-            if (kv.second && kv.second->committed) fn(kv.first, *kv.second);
+        for (const Slot& s : table_)
+            if (s.block && s.block->committed) fn(std::string(s.block->key()), *s.block);
     }
     size_t inflight() const { return inflight_count_; }
 
    private:
+    // Open addressing, linear probing, backward-shift deletion.  The slot holds one count.
+    struct Slot {
+        uint64_t hash = 0;
+        Block* block = nullptr;  // nullptr = empty
+    };
+    static uint64_t hash_of(std::string_view key) {
+        return hash_bytes(reinterpret_cast<const uint8_t*>(key.data()), key.size(), kHashSeed1);
+    }
+    Block* find(std::string_view key) const { return find(key, hash_of(key)); }
+    Block* find(std::string_view key, uint64_t h) const;
+    void insert(Block* b);          // b->hash set; the table takes over one count
+    BlockPtr remove(Block* b);      // out of the table; the table's count moves to the result
+    void grow();
+    Block* new_block(std::string_view key, uint64_t h, const Allocation& a, size_t size,
+                     uint32_t gen, uint64_t conn) const;
+
     // In-flight (reserved, uncommitted) blocks are found by address in O(1): one slot per
     // allocation granule of every pool, holding the block that starts there.
     Block*& inflight_slot(uint32_t seg, uint64_t offset);
@@ -123,14 +168,15 @@ class KVStore {
     void lru_unlink(LruBlock* b);
 
     MM* mm_;
+    const bool track_lru_;
     uint32_t next_gen_ = 1;
-    std::unordered_map<std::string, BlockPtr, StrHash, StrEq> map_;
+    std::vector<Slot> table_;
+    size_t count_ = 0;
     std::vector<std::vector<Block*>> inflight_;  // [segment][granule]
     size_t inflight_count_ = 0;
     LruBlock* lru_head_ = nullptr;  // most recently used
     LruBlock* lru_tail_ = nullptr;  // eviction candidate
     uint64_t evicted_ = 0;
-    const bool track_lru_;
 };
 
 }  // namespace istore
