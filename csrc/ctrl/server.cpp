@@ -231,6 +231,7 @@ void Server::stop() {
     if (epoll_fd_ >= 0) close(epoll_fd_);
     if (wake_fd_ >= 0) close(wake_fd_);
     listen_fd_ = epoll_fd_ = wake_fd_ = -1;
+    quarantine_.clear();
     store_->purge();
     if (erase_buf_ || erase_stream_) {
         DevGuard g(segs_.empty() ? -1 : segs_[0]->info().device);
@@ -253,6 +254,7 @@ size_t Server::purge() {
     for (auto& kv : conns_) kv.second->leases.clear();
     const size_t n = store_->purge();
     for (auto& s : segs_) s->clear_index();
+    quarantine_.clear();  // the index is empty now: nothing can resolve these blocks any more
     return n;
 }
 
@@ -320,8 +322,7 @@ bool Server::evict_some(size_t want, bool replica) {
     if (!erase_from_device_index(victims)) {
         // cannot prove the entries unreachable: keep the space reserved rather than risk a
         // reader copying a reused block (the blocks leak until the next purge)
-        static std::vector<KVStore::Victim> quarantine;
-        quarantine.insert(quarantine.end(), victims.begin(), victims.end());
+        quarantine_.insert(quarantine_.end(), victims.begin(), victims.end());
         return false;
     }
     LOG_INFO("evicted %zu blocks (%zu KiB) from the %s", victims.size(), freed >> 10,

@@ -120,6 +120,8 @@ class Server {
     void* erase_buf_ = nullptr;     // device staging of the erase kernel's records
     size_t erase_cap_ = 0;          // records
     void* erase_stream_ = nullptr;  // cudaStream_t
+    // evicted blocks whose index entries could not be erased: their space stays reserved
+    std::vector<KVStore::Victim> quarantine_;
 };
 
 }  // namespace istore
