@@ -28,8 +28,8 @@ def _send_and_drain(port, payload: bytes):
         s.close()
 
 
-@settings(max_examples=120, deadline=None,
-          suppress_health_check=[HealthCheck.function_scoped_fixture])
+@settings(max_examples=60, deadline=None, derandomize=True,
+          suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(op=st.sampled_from(list(OPS) + [0, 0x7f, 0xff]),
        body=st.binary(min_size=0, max_size=512),
        claimed=st.one_of(st.none(), st.integers(min_value=0, max_value=(1 << 32) - 1)),
@@ -48,8 +48,8 @@ def test_random_requests_never_take_the_server_down(host_server, op, body, claim
         conn.close()
 
 
-@settings(max_examples=60, deadline=None,
-          suppress_health_check=[HealthCheck.function_scoped_fixture])
+@settings(max_examples=30, deadline=None, derandomize=True,
+          suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(chunks=st.lists(st.binary(min_size=1, max_size=64), min_size=1, max_size=12))
 def test_arbitrary_byte_streams(host_server, chunks):
     srv, port = host_server
@@ -70,7 +70,7 @@ def test_arbitrary_byte_streams(host_server, chunks):
     assert srv.stats()["used_bytes"] == before
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(ops=st.lists(st.tuples(st.booleans(), st.integers(min_value=1, max_value=5 * 4096)),
                     min_size=1, max_size=60))
 def test_mempool_model(ops):
