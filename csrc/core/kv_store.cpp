@@ -183,6 +183,15 @@ size_t KVStore::commit(const uint64_t* addrs, size_t n) {
     return done;
 }
 
+void KVStore::warm(const uint64_t* addrs, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t seg = addr_seg(addrs[i]);
+        const uint64_t off = addr_off(addrs[i]);
+        if (seg >= mm_->num_pools() || off >= mm_->pool(seg).bytes()) continue;
+        if (const Block* b = inflight_slot(seg, off)) __builtin_prefetch(b, 1);
+    }
+}
+
 int KVStore::lookup(const std::vector<std::string_view>& keys, size_t need,
                     std::vector<RemoteBlock>& out, std::vector<BlockPtr>* lease) {
     out.clear();

@@ -110,6 +110,9 @@ class KVStore {
                 uint64_t conn, std::vector<RemoteBlock>& out);
     // Flip the blocks at `addrs` to committed.  Unknown addresses are ignored.
     size_t commit(const uint64_t* addrs, size_t n);
+    // Pull the headers of the in-flight blocks at `addrs` towards the cache (a commit for them
+    // is about to arrive).  No state changes.
+    void warm(const uint64_t* addrs, size_t n);
     // Locators of committed keys; kKeyNotFound if any key is missing or uncommitted.
     // `lease` receives references that keep the blocks alive until the caller drops them.
     // kInvalidReq if a stored block is smaller than `need` bytes.

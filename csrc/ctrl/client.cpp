@@ -459,6 +459,15 @@ int Connection::transact(char op, const void* body, size_t len, int32_t* code,
     return 0;
 }
 
+int Connection::send_raw(const void* framed, size_t len) {
+    std::lock_guard<std::mutex> lk(sock_mu_);
+    if (fd_ < 0) return -1;
+    iovec iov[1] = {{const_cast<void*>(framed), len}};
+    if (!send_all(fd_, iov, 1)) return -1;
+    stats_.ctrl_requests++;
+    return 0;
+}
+
 int Connection::send_only(char op, const void* body, size_t len) {
     std::lock_guard<std::mutex> lk(sock_mu_);
     if (fd_ < 0) return -1;
@@ -531,6 +540,8 @@ int Connection::get_match_last_index(const std::vector<std::string_view>& keys) 
 
 int Connection::sync_local() {
     NvtxRange nvtx("istore.sync");
+    // one sync at a time: a staged commit list and the SYNC that applies it belong together
+    std::lock_guard<std::mutex> sync_lk(sync_mu_);
     {
         // Nothing to tell the server (no commits pending, no leases held by host-mediated
         // lookups): completion of the kernels is all there is to wait for.
@@ -549,26 +560,47 @@ int Connection::sync_local() {
             return drained != 0 ? drained : 0;
         }
     }
-    if (drain_devices() != 0) return -1;
-    // COMMIT (no reply) and SYNC travel in one send: one syscall, one server wake-up
+    // The commit list is taken BEFORE waiting for the GPU, so it names only blocks whose
+    // kernels the drain below covers, and it is shipped right away as a STAGED commit: the
+    // server decodes it and pulls the block headers into its cache while this thread waits
+    // for the kernels; the SYNC that follows the drain applies it.  (Measured at N=1: the
+    // commit of 8192 blocks was ~0.1 ms of a 0.5 ms write phase when it followed the drain.)
     std::vector<uint64_t> addrs;
     {
         std::lock_guard<std::mutex> lk(mu_);
         addrs.swap(pending_commit_);
     }
-    std::vector<uint8_t> framed;
     constexpr size_t kInline = 128 * 1024;  // addresses; larger lists use the chunked path
-    if (!addrs.empty() && addrs.size() <= kInline) {
-        std::vector<uint8_t> buf(align_up(addrs.size() * 8 + 128, 8));
+    auto frame_of = [&](char op, int32_t block_size, const uint64_t* a, size_t n) {
+        std::vector<uint8_t> buf(align_up(n * 8 + 128, 8));
         fb::Builder b(buf.data(), buf.size());
-        encode_remote_meta(b, {}, 0, 0, addrs.data(), addrs.size(), kOpCommit);
-        framed.resize(sizeof(Header) + b.size());
-        Header ch{kMagic, kOpCommit, uint32_t(b.size())};
+        encode_remote_meta(b, {}, block_size, 0, a, n, op);
+        std::vector<uint8_t> framed(sizeof(Header) + b.size());
+        Header ch{kMagic, op, uint32_t(b.size())};
         std::memcpy(framed.data(), &ch, sizeof(ch));
         std::memcpy(framed.data() + sizeof(ch), b.data(), b.size());
-    } else if (!addrs.empty() && send_commit(addrs.data(), addrs.size()) != 0) {
+        return framed;
+    };
+    bool staged = false;
+    if (!addrs.empty() && addrs.size() <= kInline) {
+        const std::vector<uint8_t> f = frame_of(kOpStageCommit, 0, addrs.data(), addrs.size());
+        if (send_raw(f.data(), f.size()) != 0) {
+            fail("commit: send failed");
+            return -1;
+        }
+        staged = true;
+    }
+    if (drain_devices() != 0) {
+        // the data of these blocks may not have landed: they must never become visible (they
+        // stay reserved until this connection closes)
+        if (staged) {
+            const std::vector<uint8_t> f = frame_of(kOpStageCommit, -1, nullptr, 0);
+            (void)send_raw(f.data(), f.size());
+        }
         return -1;
     }
+    std::vector<uint8_t> framed;  // reply-less messages that travel with the SYNC
+    if (!staged && !addrs.empty() && send_commit(addrs.data(), addrs.size()) != 0) return -1;
     int32_t code = 0;
     std::vector<uint8_t> p;
     if (transact(kOpSync, nullptr, 0, &code, &p, sizeof(uint32_t), &framed) != 0 ||

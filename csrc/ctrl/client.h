@@ -156,6 +156,7 @@ class Connection {
     int transact(char op, const void* body, size_t len, int32_t* code,
                  std::vector<uint8_t>* payload, size_t fixed_payload,
                  const std::vector<uint8_t>* prefix = nullptr);
+    int send_raw(const void* framed, size_t len);  // already framed, reply-less message(s)
     int send_only(char op, const void* body, size_t len);
     int refresh_pool_map();
     int lookup_blocks(char op, const std::vector<KeyOffset>& blocks, int block_size,
@@ -186,6 +187,7 @@ class Connection {
     ClientConfig cfg_;
     int fd_ = -1;
     std::mutex sock_mu_;  // one request/response transaction at a time
+    std::mutex sync_mu_;  // one sync() at a time (staged commit + SYNC form a pair)
     bool server_cuda_ = false;
     bool server_hbm_ = false;
     uint8_t server_uuid_[16] = {0};

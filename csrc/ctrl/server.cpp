@@ -38,6 +38,7 @@ struct Server::Conn {
     bool closing = false;  // flush pending output, then close
     ConnInfo peer{};
     std::vector<BlockPtr> leases;  // blocks pinned for this client's in-flight reads
+    std::vector<uint64_t> staged;  // commit list received with 'U', applied at the next 'S'
     std::string addr;
 };
 
@@ -740,9 +741,14 @@ bool Server::dispatch(Conn* c) {
             case kOpReadLookup: code = handle_lookup(c, false); break;
             case kOpLocalRead: code = handle_lookup(c, true); break;
             case kOpCommit: code = handle_commit(c); break;
+            case kOpStageCommit: code = handle_stage_commit(c); break;
             case kOpCheckExist: code = handle_check_exist(c); break;
             case kOpMatchLastIdx: code = handle_match(c); break;
             case kOpSync: {
+                if (!c->staged.empty()) {  // the client's kernels have completed: now visible
+                    store_->commit(c->staged.data(), c->staged.size());
+                    c->staged.clear();
+                }
                 c->leases.clear();  // the client's reads have completed
                 const uint32_t remain = 0;  // no server-side transfers exist in this design
                 reply(c, kFinish, &remain, sizeof(remain));
@@ -755,11 +761,11 @@ bool Server::dispatch(Conn* c) {
         LOG_WARN("malformed %s request from %s: %s", op_name(c->hdr.op), c->addr.c_str(),
                  e.what());
         code = kInvalidReq;
-        if (c->hdr.op != kOpCommit) reply(c, kInvalidReq);
+        if (c->hdr.op != kOpCommit && c->hdr.op != kOpStageCommit) reply(c, kInvalidReq);
     } catch (const std::exception& e) {
         LOG_ERROR("%s request failed: %s", op_name(c->hdr.op), e.what());
         code = kInternalError;
-        if (c->hdr.op != kOpCommit) reply(c, kInternalError);
+        if (c->hdr.op != kOpCommit && c->hdr.op != kOpStageCommit) reply(c, kInternalError);
     }
     if (code >= 400) stats_.bad_requests++;
     const auto us = std::chrono::duration_cast<std::chrono::microseconds>(
@@ -884,6 +890,22 @@ int Server::handle_lookup(Conn* c, bool local) {
     encode_allocate_response(b, blocks.data(), blocks.size());
     reply_blob(c, local ? kTaskAccepted : kFinish, b.data(), b.size());
     return kFinish;
+}
+
+int Server::handle_stage_commit(Conn* c) {
+    RemoteMetaRequest req = decode_remote_meta(c->body.data(), c->body.size());
+    if (req.block_size < 0) {  // the writer's kernels failed: nothing of it becomes visible
+        c->staged.clear();
+        return kFinish;
+    }
+    if (c->staged.size() + req.remote_addrs.size() > (size_t(1) << 24)) {
+        LOG_WARN("conn %llu stages too many commits: dropped", (unsigned long long)c->id);
+        c->staged.clear();
+        return kInvalidReq;
+    }
+    store_->warm(req.remote_addrs.data(), req.remote_addrs.size());
+    c->staged.insert(c->staged.end(), req.remote_addrs.begin(), req.remote_addrs.end());
+    return kFinish;  // no reply: applied by the next SYNC of this connection
 }
 
 int Server::handle_commit(Conn* c) {

@@ -94,6 +94,7 @@ class Server {
     int handle_allocate(Conn* c, bool local);
     int handle_lookup(Conn* c, bool local);
     int handle_commit(Conn* c);
+    int handle_stage_commit(Conn* c);
     int handle_check_exist(Conn* c);
     int handle_match(Conn* c);
 

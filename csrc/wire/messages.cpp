@@ -14,6 +14,7 @@ const char* op_name(char op) {
         case kOpCheckExist: return "CHECK_EXIST";
         case kOpMatchLastIdx: return "MATCH_LAST_INDEX";
         case kOpPoolMap: return "POOL_MAP";
+        case kOpStageCommit: return "STAGE_COMMIT";
         default: return "UNKNOWN";
     }
 }

@@ -11,6 +11,9 @@
 //     carries inside RDMA SEND messages, ride the same TCP connection here;
 //   * 'P' (pool map) is new: it hands the client the list of pool segments (HBM IPC
 //     handles or shm names) it must map before launching kv_write / kv_read kernels;
+//   * 'U' (staged commit) is new: the writer ships its commit list BEFORE it waits for its
+//     kernels; the server decodes it and warms the blocks meanwhile and applies it at the
+//     next 'S' - the commit leaves the critical path of sync() without becoming visible early;
 //   * variable-size reply payloads are prefixed with a u32 byte length.
 #pragma once
 
@@ -34,6 +37,8 @@ enum Op : char {
     kOpCheckExist = 'C',    // raw key bytes     -> code + i32 (0 = exists & committed)
     kOpMatchLastIdx = 'M',  // GetMatchLastIndexRequest -> code + i32
     kOpPoolMap = 'P',       // u32 first_segment -> code + len + PoolMap blob
+    kOpStageCommit = 'U',   // RemoteMetaRequest -> (no reply) addresses to commit at the next 'S';
+                            // block_size -1 discards what was staged
 };
 
 enum Code : int32_t {
@@ -70,7 +75,7 @@ struct ConnInfo {
 static_assert(sizeof(Header) == 9, "header must be 9 bytes");
 static_assert(sizeof(ConnInfo) == 30, "conn info must be 30 bytes");
 
-constexpr uint32_t kFabricVersion = 1;
+constexpr uint32_t kFabricVersion = 2;  // 2: staged commits ('U')
 
 // 16-byte block locator returned by allocate / lookup.  numpy ABI: rkey:u4 @0,
 // remote_addr:u8 @8, itemsize 16 (reference: src/pybind.cpp:47).  The 4 padding bytes of

@@ -510,6 +510,63 @@ def test_request_split_across_tcp_segments(host_server):
     assert struct.unpack("<iiiI", data) == (200, -1, 200, 0)
 
 
+def _raw_request(s, op, body=b""):
+    s.sendall(struct.pack("<IcI", 0xDEADBEEF, op, len(body)) + body)
+
+
+def _recv_exact(s, n):
+    data = b""
+    while len(data) < n:
+        chunk = s.recv(n - len(data))
+        assert chunk, "connection closed"
+        data += chunk
+    return data
+
+
+def test_staged_commit_becomes_visible_only_at_sync(host_server):
+    """'U' ships the commit list ahead of the writer's drain; nothing is visible until the
+    writer's next 'S'; block_size -1 discards; a dead writer's staged list dies with it."""
+    from infinistore_b200 import _infinistore as m
+
+    srv, port = host_server
+    enc = m.testing.encode_remote_meta
+    s = _raw(port)
+    s.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+    _raw_request(s, b"D", enc(["st-a", "st-b", "st-c"], 4096, 0, [], "D"))
+    code, n = struct.unpack("<iI", _recv_exact(s, 8))
+    assert code == 200
+    blocks = m.testing.decode_allocate_response(_recv_exact(s, n))
+    addrs = [int(a) for a in blocks["remote_addr"]]
+    observer = make_conn(port)
+    # staged: still invisible
+    _raw_request(s, b"U", enc([], 0, 0, addrs[:2], "U"))
+    _raw_request(s, b"C", b"st-a")  # a round trip on the same connection orders us after 'U'
+    assert struct.unpack("<ii", _recv_exact(s, 8)) == (200, 1)
+    assert not observer.check_exist("st-a") and srv.stats()["inflight"] == 3
+    # discard, then stage only the first block, then SYNC applies exactly that
+    _raw_request(s, b"U", enc([], -1, 0, [], "U"))
+    _raw_request(s, b"U", enc([], 0, 0, addrs[:1], "U"))
+    _raw_request(s, b"S")
+    assert struct.unpack("<iI", _recv_exact(s, 8)) == (200, 0)
+    assert observer.check_exist("st-a") and not observer.check_exist("st-b")
+    assert srv.stats()["inflight"] == 2
+    # a writer that dies with a staged list commits nothing
+    _raw_request(s, b"U", enc([], 0, 0, addrs[1:], "U"))
+    _raw_request(s, b"C", b"st-b")
+    assert struct.unpack("<ii", _recv_exact(s, 8)) == (200, 1)
+    s.close()
+    deadline = time.time() + 5
+    while srv.stats()["inflight"] and time.time() < deadline:
+        time.sleep(0.01)
+    assert srv.stats()["inflight"] == 0 and srv.kvmap_len() == 1
+    assert not observer.check_exist("st-b") and not observer.check_exist("st-c")
+    # malformed 'U' gets no reply and does not desynchronise the stream
+    s2 = _raw(port)
+    _raw_request(s2, b"U", b"\xff" * 24)
+    _raw_request(s2, b"C", b"st-a")
+    assert struct.unpack("<ii", _recv_exact(s2, 8)) == (200, 0)
+
+
 def test_fault_injection_dropped_request_surfaces_as_error(host_server):
     srv, port = host_server
     conn = make_conn(port, timeout_ms=2000)
