@@ -360,6 +360,67 @@ def test_eviction_skips_blocks_a_reader_holds_and_uncommitted_ones():
         srv.stop()
 
 
+def test_concurrent_clients_on_an_evicting_store_never_read_foreign_bytes():
+    """Four writer/reader threads hammer a pool that holds a fraction of what they write.
+    A read may miss (the block was evicted) but a read that succeeds returns the writer's
+    bytes: leases keep blocks alive while they are read, staged commits of one connection
+    never commit another connection's blocks."""
+    import threading
+
+    srv, port = _server(prealloc_bytes=96 * 16384, evict=True, evict_ratio=0.1)
+    errors, stats = [], {"hits": 0, "misses": 0}
+    lock = threading.Lock()
+
+    def worker(tid):
+        try:
+            conn = make_conn(port)
+            rng = np.random.default_rng(tid)
+            src = torch.zeros(8 * 4096)
+            dst = torch.zeros(4096)
+            conn.register_mr(src)
+            mine = []
+            for it in range(60):
+                keys = [f"t{tid}-i{it}-b{b}" for b in range(8)]
+                for b in range(8):
+                    src[b * 4096:(b + 1) * 4096] = float(tid * 100000 + it * 8 + b)
+                try:
+                    blocks = conn.allocate_rdma(keys, 16384)
+                except Exception:
+                    continue  # everything evictable is leased or in flight right now
+                conn.rdma_write_cache(src, [b * 4096 for b in range(8)], 4096, blocks)
+                conn.sync()
+                mine.extend((k, float(tid * 100000 + it * 8 + b)) for b, k in enumerate(keys))
+                for _ in range(4):
+                    k, want = mine[int(rng.integers(0, len(mine)))]
+                    try:
+                        conn.read_cache(dst, [(k, 0)], 4096)
+                        conn.sync()
+                    except Exception:
+                        with lock:
+                            stats["misses"] += 1
+                        continue
+                    with lock:
+                        stats["hits"] += 1
+                    if not bool((dst == want).all()):
+                        errors.append((k, want, float(dst[0])))
+            conn.close()
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    try:
+        threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(120)
+        assert not errors, errors[:3]
+        st = srv.stats()
+        assert st["evicted"] > 0 and stats["hits"] > 0 and stats["misses"] > 0
+        assert st["used_bytes"] <= 96 * 16384 and st["inflight"] == 0
+    finally:
+        srv.stop()
+
+
 def test_auto_increase_adds_segments_and_clients_map_them():
     srv, port = _server(prealloc_bytes=8 * 16384, auto_increase=True)
     try:
