@@ -7,6 +7,7 @@
 #include <cstring>
 #include <random>
 #include <atomic>
+#include <map>
 #include <set>
 #include <thread>
 #include <string>
@@ -238,6 +239,77 @@ static void test_kv_store_eviction() {
     CHECK(st.evict(1, false, victims) == 16384 && victims.size() == 1);
 }
 
+// The flat key table (open addressing + backward-shift deletion) against a std::set model:
+// random batches of reserve / commit / drop-by-connection / evict, membership checked for
+// every key ever used after each step.
+static void test_kv_store_table_model() {
+    MM mm;
+    mm.add_pool(size_t(1) << 30, 4096, -1);  // 262144 granules
+    KVStore st(&mm, true);
+    std::mt19937 rng{12345};
+    std::set<std::string> live;
+    std::vector<std::string> universe;
+    std::map<uint64_t, std::vector<std::pair<std::string, uint64_t>>> uncommitted;  // conn -> (key, addr)
+    uint64_t next_conn = 1;
+    int next_key = 0;
+    for (int step = 0; step < 400; ++step) {
+        const int op = int(rng() % 10);
+        if (op < 5) {  // reserve a batch (with some duplicates of existing keys)
+            const int n = 1 + int(rng() % 300);
+            std::vector<std::string> names;
+            for (int i = 0; i < n; ++i) {
+                if (!universe.empty() && rng() % 8 == 0)
+                    names.push_back(universe[rng() % universe.size()]);
+                else
+                    names.push_back("model-key-" + std::to_string(next_key++) + std::string(rng() % 40, 'x'));
+            }
+            std::vector<std::string_view> keys(names.begin(), names.end());
+            std::vector<RemoteBlock> out;
+            const uint64_t conn = next_conn++;
+            CHECK(st.reserve(keys, 4096, -1, conn, out) == kFinish);
+            std::set<std::string> in_batch;
+            for (int i = 0; i < n; ++i) {
+                const bool existed = live.count(names[size_t(i)]) || in_batch.count(names[size_t(i)]);
+                CHECK(is_fake_block(out[size_t(i)]) == existed);
+                if (!existed) {
+                    in_batch.insert(names[size_t(i)]);
+                    uncommitted[conn].emplace_back(names[size_t(i)], out[size_t(i)].remote_addr);
+                    universe.push_back(names[size_t(i)]);
+                }
+            }
+            live.insert(in_batch.begin(), in_batch.end());
+        } else if (op < 7 && !uncommitted.empty()) {  // commit one connection's blocks
+            auto it = uncommitted.begin();
+            std::advance(it, long(rng() % uncommitted.size()));
+            std::vector<uint64_t> addrs;
+            for (auto& kv : it->second) addrs.push_back(kv.second);
+            CHECK(st.commit(addrs.data(), addrs.size()) == addrs.size());
+            uncommitted.erase(it);
+        } else if (op < 9 && !uncommitted.empty()) {  // a writer dies
+            auto it = uncommitted.begin();
+            std::advance(it, long(rng() % uncommitted.size()));
+            CHECK(st.drop_uncommitted(it->first) == it->second.size());
+            for (auto& kv : it->second) live.erase(kv.first);
+            uncommitted.erase(it);
+        } else {  // evict some committed blocks
+            std::vector<KVStore::Victim> victims;
+            st.evict(size_t(1 + rng() % 200) * 4096, false, victims);
+            for (auto& v : victims) {
+                const std::string k(v.block->key());
+                CHECK(live.erase(k) == 1);
+            }
+        }
+        CHECK(st.size() == live.size());
+        if (step % 20 == 0 || step == 399)
+            for (auto& k : universe) CHECK(st.present(k) == (live.count(k) == 1));
+    }
+    size_t inflight = 0;
+    for (auto& kv : uncommitted) inflight += kv.second.size();
+    CHECK(st.inflight() == inflight);
+    const size_t n_live = live.size();
+    CHECK(st.purge() == n_live && st.size() == 0 && mm.used_bytes() == 0);
+}
+
 // The device index algorithm (kernels/index.cuh) compiled for the CPU.
 static void test_device_index_logic() {
     using namespace istore::kernels;
@@ -438,6 +510,7 @@ int main() {
     test_mempool();
     test_kv_store();
     test_kv_store_eviction();
+    test_kv_store_table_model();
     test_hash();
     test_device_index_logic();
     test_device_index_concurrent();
