@@ -227,6 +227,20 @@ bool KVStore::exists_committed(std::string_view key) const {
     return b && b->committed;
 }
 
+size_t KVStore::touch(const std::vector<std::string_view>& keys) {
+    if (!track_lru_) return 0;
+    size_t n = 0;
+    for (auto k : keys) {
+        Block* b = find(k);
+        if (!b || !b->committed) continue;
+        ++n;
+        if (lru_head_ == b) continue;
+        lru_unlink(static_cast<LruBlock*>(b));
+        lru_push_front(static_cast<LruBlock*>(b));
+    }
+    return n;
+}
+
 // Exact replay of the reference's search (src/infinistore.cpp:1092-1108): presence is
 // assumed prefix-monotone; on other inputs the answer is whatever this probe sequence
 // yields, and callers depend on that.

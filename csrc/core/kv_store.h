@@ -120,6 +120,9 @@ class KVStore {
     int lookup(const std::vector<std::string_view>& keys, size_t need,
                std::vector<RemoteBlock>& out, std::vector<BlockPtr>* lease);
     bool exists_committed(std::string_view key) const;
+    // Recency hint: the committed blocks among `keys` become the most recently used ones (in
+    // list order).  Returns how many were refreshed; a store that does not evict returns 0.
+    size_t touch(const std::vector<std::string_view>& keys);
     bool present(std::string_view key) const { return find(key) != nullptr; }
     int match_last_index(const std::vector<std::string_view>& keys) const;
     // Drop every uncommitted block reserved by `conn` (connection closed).

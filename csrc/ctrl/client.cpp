@@ -719,6 +719,26 @@ int Connection::allocate(const std::vector<std::string_view>& keys, int block_si
     return 0;
 }
 
+int Connection::touch(const std::vector<std::string_view>& keys) {
+    if (keys.empty()) return 0;
+    int total = 0;
+    for (auto [b0, b1] : chunk_keys(keys)) {
+        const std::vector<std::string_view> kv(keys.begin() + b0, keys.begin() + b1);
+        std::vector<uint8_t> buf(remote_meta_bound(kv, 0));
+        fb::Builder b(buf.data(), buf.size());
+        encode_match_request(b, kv);
+        int32_t code = 0;
+        std::vector<uint8_t> p;
+        if (transact(kOpTouch, b.data(), b.size(), &code, &p, sizeof(int32_t)) != 0 ||
+            code != kFinish)
+            return -1;
+        int32_t v;
+        std::memcpy(&v, p.data(), sizeof(v));
+        total += v;
+    }
+    return total;
+}
+
 int Connection::lookup_blocks(char op, const std::vector<KeyOffset>& blocks, int block_size,
                               std::vector<RemoteBlock>& out) {
     {

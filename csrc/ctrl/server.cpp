@@ -744,6 +744,7 @@ bool Server::dispatch(Conn* c) {
             case kOpStageCommit: code = handle_stage_commit(c); break;
             case kOpCheckExist: code = handle_check_exist(c); break;
             case kOpMatchLastIdx: code = handle_match(c); break;
+            case kOpTouch: code = handle_touch(c); break;
             case kOpSync: {
                 if (!c->staged.empty()) {  // the client's kernels have completed: now visible
                     store_->commit(c->staged.data(), c->staged.size());
@@ -918,6 +919,13 @@ int Server::handle_check_exist(Conn* c) {
     const std::string_view key(reinterpret_cast<const char*>(c->body.data()), c->body.size());
     const int32_t v = store_->exists_committed(key) ? 0 : 1;
     reply(c, kFinish, &v, sizeof(v));
+    return kFinish;
+}
+
+int Server::handle_touch(Conn* c) {
+    std::vector<std::string_view> keys = decode_match_request(c->body.data(), c->body.size());
+    const int32_t n = int32_t(store_->touch(keys));
+    reply(c, kFinish, &n, sizeof(n));
     return kFinish;
 }
 

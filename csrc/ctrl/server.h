@@ -97,6 +97,7 @@ class Server {
     int handle_stage_commit(Conn* c);
     int handle_check_exist(Conn* c);
     int handle_match(Conn* c);
+    int handle_touch(Conn* c);
 
     ServerConfig cfg_;
     int port_ = 0;

@@ -312,6 +312,13 @@ PYBIND11_MODULE(_infinistore, m) {
                  py::gil_scoped_release rel;
                  return c.get_match_last_index(kv);
              })
+        .def("touch",
+             [](Connection& c, const py::object& keys) {
+                 std::vector<std::string_view> kv;
+                 keys_from_py(keys, kv);
+                 py::gil_scoped_release rel;
+                 return c.touch(kv);
+             })
         .def("sync_local", &Connection::sync_local, py::call_guard<py::gil_scoped_release>())
         .def("sync_rdma", &Connection::sync_rdma, py::call_guard<py::gil_scoped_release>())
         .def("register_mr", &Connection::register_mr, py::arg("ptr"), py::arg("size"),

@@ -15,6 +15,7 @@ const char* op_name(char op) {
         case kOpMatchLastIdx: return "MATCH_LAST_INDEX";
         case kOpPoolMap: return "POOL_MAP";
         case kOpStageCommit: return "STAGE_COMMIT";
+        case kOpTouch: return "TOUCH";
         default: return "UNKNOWN";
     }
 }

@@ -37,6 +37,8 @@ enum Op : char {
     kOpCheckExist = 'C',    // raw key bytes     -> code + i32 (0 = exists & committed)
     kOpMatchLastIdx = 'M',  // GetMatchLastIndexRequest -> code + i32
     kOpPoolMap = 'P',       // u32 first_segment -> code + len + PoolMap blob
+    kOpTouch = 'H',         // GetMatchLastIndexRequest (keys) -> code + i32 blocks refreshed:
+                            // recency hint for stores that evict
     kOpStageCommit = 'U',   // RemoteMetaRequest -> (no reply) addresses to commit at the next 'S';
                             // block_size -1 discards what was staged
 };

@@ -677,6 +677,17 @@ class InfinityConnection:
             raise Exception("allocate memory failed")
         return ret
 
+    def touch(self, keys: List[str]) -> int:
+        """Recency hint for a server started with ``--evict``: the blocks of ``keys`` were just
+        used.  Server-mediated reads refresh recency by themselves; reads that resolve keys on
+        the GPU (``device_lookup=True``) never reach the server, so a cache manager calls
+        this after a prefix hit to keep hot prefixes from being evicted.  Returns the number
+        of blocks refreshed (0 when the server does not evict)."""
+        ret = self.conn.touch(keys)
+        if ret < 0:
+            raise Exception("touch failed")
+        return ret
+
     # ------------------------------------------------------------------ introspection
     def stats(self):
         return self.conn.stats()

@@ -11,7 +11,7 @@ from hypothesis import strategies as st
 from conftest import make_conn
 
 MAGIC = 0xDEADBEEF
-OPS = b"RWSEDATCMPU"
+OPS = b"RWSEDATCMPUH"
 
 
 def _send_and_drain(port, payload: bytes):

@@ -334,6 +334,36 @@ def test_full_pool_evicts_least_recently_used_when_enabled():
         srv.stop()
 
 
+def test_touch_refreshes_recency_for_readers_the_server_does_not_see():
+    srv, port = _server(prealloc_bytes=8 * 16384, evict=True, evict_ratio=0.25)
+    try:
+        conn = make_conn(port)
+        src = torch.randn(10 * 4096)
+        conn.register_mr(src)
+        keys = [f"k{i}" for i in range(8)]
+        conn.rdma_write_cache(src, [i * 4096 for i in range(8)], 4096,
+                              conn.allocate_rdma(keys, 16384))
+        conn.sync()
+        # the oldest two would be evicted next; a cache manager says they were just used
+        assert conn.touch(["k0", "k1", "not-there"]) == 2
+        conn.rdma_write_cache(src, [8 * 4096, 9 * 4096], 4096,
+                              conn.allocate_rdma(["k8", "k9"], 16384))
+        conn.sync()
+        assert conn.check_exist("k0") and conn.check_exist("k1")
+        assert not conn.check_exist("k2") and not conn.check_exist("k3")
+    finally:
+        srv.stop()
+    # a store that does not evict keeps no recency order: the hint is a no-op
+    srv, port = _server(prealloc_bytes=8 * 16384)
+    try:
+        conn = make_conn(port)
+        conn.rdma_write_cache(src, [0], 4096, conn.allocate_rdma(["x"], 16384))
+        conn.sync()
+        assert conn.touch(["x"]) == 0
+    finally:
+        srv.stop()
+
+
 def test_eviction_skips_blocks_a_reader_holds_and_uncommitted_ones():
     srv, port = _server(prealloc_bytes=4 * 16384, evict=True, evict_ratio=0.25)
     try:
