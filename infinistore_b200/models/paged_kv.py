@@ -90,3 +90,14 @@ class PagedKVCache:
             return conn.get_match_last_index(keys) + 1
         except Exception:
             return 0
+
+    def touch_prefix(self, conn, page_hashes: Sequence[str]) -> int:
+        """Tell an evicting store (``--evict``) that these pages were just used: every layer's
+        K and V block of every page becomes most-recently-used.  Needed by clients that read
+        through the device index, whose reads the server never sees.  Returns the number of
+        blocks refreshed."""
+        keys: List[str] = []
+        for layer in range(self.layout.layers):
+            for kv in (0, 1):
+                keys.extend(self.keys(layer, kv, page_hashes))
+        return conn.touch(keys) if keys else 0

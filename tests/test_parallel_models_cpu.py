@@ -123,6 +123,34 @@ def test_start_shard_server_helper():
         srv.stop()
 
 
+def test_paged_kv_touch_prefix_keeps_a_hot_prefix_from_eviction():
+    layout = KVLayout("tiny", layers=2, kv_heads=1, head_dim=16, page_tokens=8,
+                      dtype=torch.float32)
+    # room for exactly two prefixes of 2 pages (2 layers x K,V x 2 pages = 8 blocks each)
+    srv = start_shard_server(0, 0, 16 * 16384, granule_kb=16, evict=True, evict_ratio=0.5)
+    try:
+        conn = make_conn(srv.port())
+        cache = PagedKVCache(layout, num_pages=4, device="cpu")
+        cache.data.normal_()
+        hot = chain_hashes(list(range(16)), 8, salt="hot")
+        cold = chain_hashes(list(range(16)), 8, salt="cold")
+        new = chain_hashes(list(range(16)), 8, salt="new")
+        for hashes in (hot, cold):
+            for layer in range(layout.layers):
+                cache.write_layer(conn, layer, [0, 1], hashes)
+        conn.sync()
+        assert srv.stats()["used_bytes"] == 16 * 16384
+        assert cache.touch_prefix(conn, hot) == 8  # the older prefix is the hot one
+        for layer in range(layout.layers):
+            cache.write_layer(conn, layer, [2, 3], new)
+        conn.sync()
+        assert cache.cached_prefix_pages(conn, hot) == 2
+        assert cache.cached_prefix_pages(conn, cold) == 0
+        assert cache.cached_prefix_pages(conn, new) == 2
+    finally:
+        srv.stop()
+
+
 def test_examples_run_on_cpu(host_server, monkeypatch, capsys):
     import sys
     from infinistore_b200.example import client, client_async
