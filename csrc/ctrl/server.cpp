@@ -854,6 +854,7 @@ int Server::handle_allocate(Conn* c, bool local) {
         return code;
     }
     if (cfg_.auto_increase && mm_.need_extend()) maybe_extend();
+    for (const RemoteBlock& rb : blocks) stats_.dedup_skips += is_fake_block(rb);
     const size_t need = blocks.size() * sizeof(RemoteBlock) + 64;
     if (scratch_.size() < need) scratch_.resize((need + 7) & ~size_t(7));
     fb::Builder b(scratch_.data(), scratch_.size() & ~size_t(7));
@@ -882,9 +883,11 @@ int Server::handle_lookup(Conn* c, bool local) {
     std::vector<RemoteBlock> blocks;
     const int code = store_->lookup(keys, size_t(block_size), blocks, &c->leases);
     if (code != kFinish) {
+        if (code == kKeyNotFound) stats_.lookup_misses++;
         reply(c, code);  // explicit error reply (the reference's RDMA path stays silent)
         return code;
     }
+    stats_.lookup_hits += keys.size();
     const size_t need = blocks.size() * sizeof(RemoteBlock) + 64;
     if (scratch_.size() < need) scratch_.resize((need + 7) & ~size_t(7));
     fb::Builder b(scratch_.data(), scratch_.size() & ~size_t(7));

@@ -41,6 +41,9 @@ struct ServerStats {
     uint64_t used_bytes = 0;
     uint64_t segments = 0;
     uint64_t evicted = 0;           // blocks evicted since start
+    uint64_t lookup_hits = 0;       // keys resolved by server-mediated reads
+    uint64_t lookup_misses = 0;     // server-mediated read requests answered 404
+    uint64_t dedup_skips = 0;       // allocate requests for keys that already existed
     uint64_t ops[128] = {0};        // per opcode
 };
 

@@ -244,6 +244,9 @@ py::dict stats_dict(const ServerStats& s) {
     d["used_bytes"] = s.used_bytes;
     d["segments"] = s.segments;
     d["evicted"] = s.evicted;
+    d["lookup_hits"] = s.lookup_hits;
+    d["lookup_misses"] = s.lookup_misses;
+    d["dedup_skips"] = s.dedup_skips;
     py::dict ops;
     for (int i = 0; i < 128; ++i)
         if (s.ops[i]) ops[py::str(op_name(char(i)))] = s.ops[i];

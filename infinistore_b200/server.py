@@ -102,6 +102,11 @@ def prometheus_text(s: dict) -> str:
     gauge("requests_total", s.get("requests", 0), "control-plane requests served")
     gauge("bad_requests_total", s.get("bad_requests", 0), "requests answered with an error")
     gauge("evicted_blocks_total", s.get("evicted", 0), "blocks evicted to make room")
+    gauge("lookup_hits_total", s.get("lookup_hits", 0), "keys resolved by server-mediated reads")
+    gauge("lookup_misses_total", s.get("lookup_misses", 0),
+          "server-mediated read requests answered 404")
+    gauge("dedup_skips_total", s.get("dedup_skips", 0),
+          "allocations skipped because the key already existed (first writer wins)")
     for op, n in sorted(s.get("ops", {}).items()):
         lines.append(f'infinistore_op_total{{op="{op}"}} {n}')
     return "\n".join(lines) + "\n"

@@ -63,6 +63,8 @@ def test_manage_plane_and_selftest(cli_server):
     assert "infinistore_keys 11" in text and 'infinistore_op_total{op="COMMIT"}' in text
     assert 'infinistore_op_total{op="STAGE_COMMIT"}' in text  # the sync API stages its commits
     assert "infinistore_evicted_blocks_total 0" in text
+    assert "infinistore_lookup_hits_total 3" in text  # the selftest read three blocks back
+    assert "infinistore_dedup_skips_total 0" in text
     ckpt = "/tmp/istore_cli_test.ckpt"
     assert _http("POST", base + f"/dump?path={ckpt}")["num"] == 11
     assert _http("POST", base + "/purge") == {"status": "ok", "num": 11}

@@ -178,6 +178,25 @@ def test_deduplicate_first_writer_wins(host_server):
     assert torch.equal(src, dst) and not torch.equal(src2, dst)
 
 
+def test_server_counts_hits_misses_and_dedup(host_server):
+    srv, port = host_server
+    conn = make_conn(port)
+    src = torch.randn(2 * 1024)
+    dst = torch.zeros(1024)
+    conn.register_mr(src)
+    conn.rdma_write_cache(src, [0, 1024], 1024, conn.allocate_rdma(["h-a", "h-b"], 4096))
+    conn.sync()
+    again = conn.allocate_rdma(["h-a", "h-c"], 4096)  # one duplicate, one fresh
+    assert again["rkey"][0] == 0 and again["rkey"][1] != 0
+    conn.read_cache(dst, [("h-a", 0)], 1024)
+    conn.read_cache(dst, [("h-b", 0)], 1024)
+    with pytest.raises(Exception):
+        conn.read_cache(dst, [("h-missing", 0)], 1024)
+    conn.sync()
+    st = srv.stats()
+    assert (st["lookup_hits"], st["lookup_misses"], st["dedup_skips"]) == (2, 1, 1)
+
+
 def test_partial_dedup_batch_completes(host_server):
     """Reference defect D2: a batch whose LAST block is a duplicate must still complete."""
     _, port = host_server
