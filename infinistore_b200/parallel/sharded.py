@@ -99,6 +99,14 @@ class ShardedConnection:
     def check_exist(self, key: str) -> bool:
         return self.conns[shard_of(key, self.nshards)].check_exist(key)
 
+    def touch(self, keys: Sequence[str]) -> int:
+        """Recency hint (see ``InfinityConnection.touch``), routed to the owning shards."""
+        n = 0
+        for s, pos in enumerate(self._split(keys)):
+            if len(pos):
+                n += self.conns[s].touch([keys[i] for i in pos])
+        return n
+
     def get_match_last_index(self, keys: List[str]) -> int:
         """The reference's binary search (src/infinistore.cpp:1092-1108) with each probe
         answered by the shard owning that key."""

@@ -59,6 +59,7 @@ def test_sharded_connection_routes_and_round_trips(three_shards):
     assert conn.get_match_last_index(keys[:10] + ["x", "y"]) == 9
     with pytest.raises(Exception):
         conn.get_match_last_index(["x", "y"])
+    assert conn.touch(keys[:7]) == 0  # routed to every shard; these shards do not evict
     conn.close()
 
 
