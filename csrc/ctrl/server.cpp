@@ -772,6 +772,7 @@ bool Server::dispatch(Conn* c) {
     const auto us = std::chrono::duration_cast<std::chrono::microseconds>(
                         std::chrono::steady_clock::now() - t0)
                         .count();
+    stats_.timing[uint8_t(c->hdr.op) & 127].add(uint64_t(us < 0 ? 0 : us));
     LOG_DEBUG("%s from conn %llu -> %d in %lld us", op_name(c->hdr.op),
               (unsigned long long)c->id, code, (long long)us);
     // A malformed request leaves the stream position well defined (the body was consumed),

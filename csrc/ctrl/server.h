@@ -30,6 +30,35 @@
 
 namespace istore {
 
+// Service-time histogram of one opcode: bucket b counts requests that took < 2^b microseconds
+// (bucket 0: < 1 us ... bucket 23: everything longer than ~4 s).
+struct OpTiming {
+    static constexpr int kBuckets = 24;
+    uint64_t count = 0;
+    uint64_t sum_us = 0;
+    uint64_t max_us = 0;
+    uint64_t bucket[kBuckets] = {0};
+    void add(uint64_t us) {
+        ++count;
+        sum_us += us;
+        if (us > max_us) max_us = us;
+        int b = 0;
+        while (b < kBuckets - 1 && (uint64_t(1) << b) <= us) ++b;
+        ++bucket[b];
+    }
+    // upper bound (us) of the bucket that holds quantile q in (0, 1]
+    uint64_t quantile_us(double q) const {
+        if (!count) return 0;
+        const uint64_t want = uint64_t(q * double(count) + 0.999999);
+        uint64_t seen = 0;
+        for (int b = 0; b < kBuckets; ++b) {
+            seen += bucket[b];
+            if (seen >= want) return b == kBuckets - 1 ? max_us : (uint64_t(1) << b);
+        }
+        return max_us;
+    }
+};
+
 struct ServerStats {
     uint64_t connections = 0;       // currently open
     uint64_t accepted = 0;          // total accepted
@@ -45,6 +74,7 @@ struct ServerStats {
     uint64_t lookup_misses = 0;     // server-mediated read requests answered 404
     uint64_t dedup_skips = 0;       // allocate requests for keys that already existed
     uint64_t ops[128] = {0};        // per opcode
+    OpTiming timing[128];           // per opcode service time (reactor thread, decode -> reply queued)
 };
 
 class Server {

@@ -251,6 +251,19 @@ py::dict stats_dict(const ServerStats& s) {
     for (int i = 0; i < 128; ++i)
         if (s.ops[i]) ops[py::str(op_name(char(i)))] = s.ops[i];
     d["ops"] = ops;
+    py::dict lat;  // service time of the control-plane ops, microseconds (log2 buckets)
+    for (int i = 0; i < 128; ++i) {
+        const OpTiming& t = s.timing[i];
+        if (!t.count) continue;
+        py::dict e;
+        e["count"] = t.count;
+        e["mean_us"] = double(t.sum_us) / double(t.count);
+        e["p50_us"] = t.quantile_us(0.5);
+        e["p99_us"] = t.quantile_us(0.99);
+        e["max_us"] = t.max_us;
+        lat[py::str(op_name(char(i)))] = e;
+    }
+    d["op_latency_us"] = lat;
     return d;
 }
 

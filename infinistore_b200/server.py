@@ -109,6 +109,13 @@ def prometheus_text(s: dict) -> str:
           "allocations skipped because the key already existed (first writer wins)")
     for op, n in sorted(s.get("ops", {}).items()):
         lines.append(f'infinistore_op_total{{op="{op}"}} {n}')
+    lines.append("# HELP infinistore_op_service_us control-plane service time per op (log2 buckets)")
+    lines.append("# TYPE infinistore_op_service_us summary")
+    for op, t in sorted(s.get("op_latency_us", {}).items()):
+        for q, key in (("0.5", "p50_us"), ("0.99", "p99_us"), ("1", "max_us")):
+            lines.append(f'infinistore_op_service_us{{op="{op}",quantile="{q}"}} {t[key]}')
+        lines.append(f'infinistore_op_service_us_sum{{op="{op}"}} {t["mean_us"] * t["count"]:.0f}')
+        lines.append(f'infinistore_op_service_us_count{{op="{op}"}} {t["count"]}')
     return "\n".join(lines) + "\n"
 
 

@@ -65,6 +65,9 @@ def test_manage_plane_and_selftest(cli_server):
     assert "infinistore_evicted_blocks_total 0" in text
     assert "infinistore_lookup_hits_total 3" in text  # the selftest read three blocks back
     assert "infinistore_dedup_skips_total 0" in text
+    assert 'infinistore_op_service_us{op="ALLOCATE",quantile="0.99"}' in text
+    lat = stats["op_latency_us"]["ALLOCATE"]
+    assert lat["count"] >= 2 and 0 < lat["p50_us"] <= lat["p99_us"] and lat["max_us"] >= lat["mean_us"]
     ckpt = "/tmp/istore_cli_test.ckpt"
     assert _http("POST", base + f"/dump?path={ckpt}")["num"] == 11
     assert _http("POST", base + "/purge") == {"status": "ok", "num": 11}
