@@ -436,25 +436,35 @@ int Connection::transact(char op, const void* body, size_t len, int32_t* code,
         iov[niov++] = iovec{const_cast<uint8_t*>(prefix->data()), prefix->size()};
     iov[niov++] = iovec{&h, sizeof(h)};
     if (len) iov[niov++] = iovec{const_cast<void*>(body), len};
-    if (!send_all(fd_, iov, niov)) {
-        fail(std::string("send ") + op_name(op) + ": " + std::strerror(errno));
+    // A transaction that breaks half way (send error, reply timeout, short reply) leaves the
+    // byte stream in an unknown position: a late reply would be taken for the answer to the
+    // NEXT request.  The connection is closed instead; later calls fail fast.
+    auto broken = [&](const std::string& why) {
+        fail(why);
+        ::shutdown(fd_, SHUT_RDWR);
+        ::close(fd_);
+        fd_ = -1;
         return -1;
-    }
+    };
+    if (!send_all(fd_, iov, niov))
+        return broken(std::string("send ") + op_name(op) + ": " + std::strerror(errno));
     stats_.ctrl_requests++;
-    if (!recv_all(fd_, code, sizeof(*code))) {
-        fail(std::string("no reply to ") + op_name(op) + " (timeout or connection closed)");
-        return -1;
-    }
+    if (!recv_all(fd_, code, sizeof(*code)))
+        return broken(std::string("no reply to ") + op_name(op) +
+                      " (timeout or connection closed): connection dropped");
     if (payload) payload->clear();
     if (*code != kFinish && *code != kTaskAccepted) return 0;  // error replies carry no payload
     if (fixed_payload == kBlobPayload) {
         uint32_t n = 0;
-        if (!recv_all(fd_, &n, sizeof(n)) || n > kMaxBody + 4096) return -1;
+        if (!recv_all(fd_, &n, sizeof(n)) || n > kMaxBody + 4096)
+            return broken(std::string("short reply to ") + op_name(op));
         payload->resize(n);
-        if (n && !recv_all(fd_, payload->data(), n)) return -1;
+        if (n && !recv_all(fd_, payload->data(), n))
+            return broken(std::string("short reply to ") + op_name(op));
     } else if (fixed_payload) {
         payload->resize(fixed_payload);
-        if (!recv_all(fd_, payload->data(), fixed_payload)) return -1;
+        if (!recv_all(fd_, payload->data(), fixed_payload))
+            return broken(std::string("short reply to ") + op_name(op));
     }
     return 0;
 }

@@ -16,6 +16,7 @@
 #include <cuda_runtime_api.h>
 
 #include <cstdio>
+#include <thread>
 
 #include "../core/log.h"
 #include "../kernels/kernels.h"
@@ -720,6 +721,8 @@ void Server::on_readable(Conn* c) {
                 close_conn(c);
                 return;
             }
+            if (delay_count_.load() && delay_count_.fetch_sub(1) >= 1)  // fault injection
+                std::this_thread::sleep_for(std::chrono::milliseconds(delay_ms_.load()));
             if (!dispatch(c)) {
                 c->closing = true;
                 break;

@@ -104,6 +104,12 @@ class Server {
     // Fault injection for tests: close a connection instead of answering the n-th request
     // from now (0 = off).
     void inject_drop_after(uint64_t n) { drop_after_.store(n); }
+    // Fault injection for tests: stall the reactor for `ms` before serving each of the next
+    // `count` requests (a slow / overloaded server).
+    void inject_delay(uint32_t ms, uint64_t count) {
+        delay_ms_.store(ms);
+        delay_count_.store(count);
+    }
 
    private:
     struct Conn;
@@ -141,6 +147,8 @@ class Server {
     std::atomic<bool> running_{false};
     std::atomic<bool> stop_{false};
     std::atomic<uint64_t> drop_after_{0};
+    std::atomic<uint32_t> delay_ms_{0};
+    std::atomic<uint64_t> delay_count_{0};
 
     std::mutex mu_;  // guards everything below (reactor thread vs. manage-plane callers)
     MM mm_;

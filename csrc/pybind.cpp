@@ -519,6 +519,10 @@ PYBIND11_MODULE(_infinistore, m) {
         .def("running", &Server::running)
         .def("kvmap_len", &Server::kvmap_len, py::call_guard<py::gil_scoped_release>())
         .def("purge", &Server::purge, py::call_guard<py::gil_scoped_release>())
+        .def("inject_delay", &Server::inject_delay, py::arg("ms"), py::arg("count") = 1,
+             "fault injection: stall the reactor `ms` before each of the next `count` requests")
+        .def("inject_delay", &Server::inject_delay, py::arg("ms"), py::arg("count") = 1,
+             "fault injection: stall the reactor `ms` before each of the next `count` requests")
         .def("inject_drop_after", &Server::inject_drop_after)
         .def(
             "dump",

@@ -687,6 +687,30 @@ def test_fault_injection_dropped_request_surfaces_as_error(host_server):
     assert not conn2.check_exist("k")
 
 
+def test_reply_timeout_drops_the_connection_instead_of_desynchronising_it(host_server):
+    """A reply that arrives after the client's deadline must never be taken for the answer to
+    the next request: the client closes the connection on a timeout and fails fast after."""
+    srv, port = host_server
+    writer = make_conn(port)
+    src = torch.randn(1024)
+    writer.register_mr(src)
+    writer.rdma_write_cache(src, [0], 1024, writer.allocate_rdma(["slow-key"], 4096))
+    writer.sync()
+    conn = make_conn(port, timeout_ms=200)
+    assert conn.check_exist("slow-key") is True
+    srv.inject_delay(700, 1)  # the next request is answered long after the 200 ms deadline
+    t0 = time.time()
+    with pytest.raises(Exception):
+        conn.check_exist("slow-key")
+    assert time.time() - t0 < 0.65  # the client gave up at its own deadline
+    time.sleep(0.8)  # the late reply (exists = 0) is on the wire now
+    # without the fix this call would read that stale reply and report "missing-key exists"
+    with pytest.raises(Exception):
+        conn.check_exist("missing-key")
+    conn2 = make_conn(port, timeout_ms=2000)
+    assert conn2.check_exist("slow-key") and not conn2.check_exist("missing-key")
+
+
 def test_many_keys_single_request(host_server):
     _, port = host_server
     conn = make_conn(port)
