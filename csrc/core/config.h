@@ -32,6 +32,8 @@ struct ServerConfig {
     bool evict = false;                    // full pool: evict least-recently-used blocks
                                            // instead of answering 507 (reference: never)
     double evict_ratio = 0.05;             // fraction of the pool freed per eviction round
+    size_t max_pending_reply_bytes = 64u << 20;  // a client that pipelines requests without
+                                           // reading its replies is disconnected beyond this
 };
 
 struct ClientConfig {

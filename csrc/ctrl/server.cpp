@@ -727,6 +727,15 @@ void Server::on_readable(Conn* c) {
                 c->closing = true;
                 break;
             }
+            if (c->out.size() - c->out_off > cfg_.max_pending_reply_bytes) {
+                // the peer keeps sending requests but does not read the answers: do not
+                // buffer without bound on its behalf
+                LOG_WARN("conn %llu (%s): %zu MiB of unread replies: disconnected",
+                         (unsigned long long)c->id, c->addr.c_str(),
+                         (c->out.size() - c->out_off) >> 20);
+                close_conn(c);
+                return;
+            }
         }
     }
     if (conns_.count(fd)) on_writable(c);  // flush replies (may close when `closing`)

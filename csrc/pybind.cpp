@@ -311,6 +311,7 @@ PYBIND11_MODULE(_infinistore, m) {
         .def_readwrite("replica_bytes", &ServerConfig::replica_bytes)
         .def_readwrite("evict", &ServerConfig::evict)
         .def_readwrite("evict_ratio", &ServerConfig::evict_ratio)
+        .def_readwrite("max_pending_reply_bytes", &ServerConfig::max_pending_reply_bytes)
         .def_readwrite("replica_devices", &ServerConfig::replica_devices);
 
     // ------------------------------------------------------------ client

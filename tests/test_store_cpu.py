@@ -711,6 +711,28 @@ def test_reply_timeout_drops_the_connection_instead_of_desynchronising_it(host_s
     assert conn2.check_exist("slow-key") and not conn2.check_exist("missing-key")
 
 
+def test_client_that_never_reads_replies_is_disconnected():
+    srv, port = _server(prealloc_bytes=64 << 20, max_pending_reply_bytes=256 << 10)
+    try:
+        s = _raw(port)
+        s.setsockopt(socket.SOL_SOCKET, socket.SO_RCVBUF, 4096)
+        msg = struct.pack("<IcII", 0xDEADBEEF, b"P", 4, 0)  # pool map: a ~170-byte reply each
+        sent = 0
+        s.settimeout(5)
+        try:
+            for _ in range(20000):  # unread replies pile up: the server gives up on us
+                s.sendall(msg * 64)
+                sent += 64
+        except (BrokenPipeError, ConnectionResetError, socket.timeout):
+            pass
+        assert sent < 20000 * 64  # we were cut off
+        assert srv.running()
+        conn = make_conn(port)
+        assert conn.check_exist("anything") is False
+    finally:
+        srv.stop()
+
+
 def test_many_keys_single_request(host_server):
     _, port = host_server
     conn = make_conn(port)
