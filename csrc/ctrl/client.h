@@ -94,11 +94,11 @@ class Connection {
 
     // --- metadata
     int check_exist(const std::string& key);  // 0 = exists & committed, 1 = not, <0 error
-    int get_match_last_index(const std::vector<std::string_view>& keys);
+    int get_match_last_index(const std::vector<std::string_view>& keys);  // index, -1 none, <-1 error
     // Recency hint for a store that evicts: the blocks of `keys` were just used (e.g. read
     // through the device index, which the server does not see).  Returns the number of
     // blocks refreshed, < 0 on error.
-    int touch(const std::vector<std::string_view>& keys);  // index, -1 none, <-1 error
+    int touch(const std::vector<std::string_view>& keys);
     int sync_local();  // remaining server-side tasks (always 0 here) or <0
     int sync_rdma();   // drain kernels + async ops, commit, control-plane barrier
 

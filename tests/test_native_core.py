@@ -27,3 +27,17 @@ def test_native_core_under_asan_ubsan():
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout + r.stderr[-4000:]
     assert "0 failed" in r.stdout
+
+
+def test_server_and_client_loopback_under_asan_ubsan():
+    """Server + client over loop-back TCP in one sanitized native binary: store round trips,
+    eviction, dead writers, garbage on the wire, checkpoint / resume."""
+    from tools import build_native
+
+    exe = build_native.build_loopback_test(sanitize=True)
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0:protect_shadow_gap=0",
+               UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-6000:]
+    assert "0 failed" in r.stdout
+    assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr

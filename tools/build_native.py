@@ -146,6 +146,25 @@ def build_cpp_tests(force: bool = False, sanitize: bool = False) -> Path:
     return out
 
 
+def build_loopback_test(force: bool = False, sanitize: bool = True) -> Path:
+    """Server + client over loop-back TCP in one native binary (csrc/tests/test_loopback.cpp):
+    every host source is compiled with AddressSanitizer + UBSan and linked against the
+    kernel objects of the regular build (device code is not instrumented; without a GPU the
+    CUDA calls fail gracefully and the host-memory pool is used)."""
+    build()  # makes sure the kernel objects exist
+    out = BUILD / ("test_loopback_san" if sanitize else "test_loopback")
+    srcs = [CSRC / "tests" / "test_loopback.cpp", *(CSRC / s for s in HOST_SOURCES)]
+    kernel_objs = [BUILD / (rel.replace("/", "_") + ".o") for rel in CUDA_SOURCES]
+    if force or not out.exists() or any(_newer(s, out, _headers()) for s in srcs):
+        flags = ["-std=c++20", "-O1", "-g", "-Wall", "-pthread"]
+        if sanitize:
+            flags += ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"]
+        _run(["g++", *flags, f"-I{CSRC}", f"-I{CUDA_HOME / 'include'}", *map(str, srcs),
+              *map(str, kernel_objs), f"-L{CUDA_HOME / 'lib64'}", "-lcudart_static", "-lrt",
+              "-ldl", "-o", str(out)])
+    return out
+
+
 def sass_listing(dst_dir: Path) -> list[Path]:
     """cuobjdump -sass of every kernel object (committed under docs/sass/)."""
     dst_dir.mkdir(parents=True, exist_ok=True)
