@@ -6,6 +6,8 @@
 #include <unistd.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <random>
@@ -75,6 +77,63 @@ static void store_round_trips(int port, Server& srv) {
     CHECK(c->get_match_last_index(probe) == 1);
     CHECK(c->touch(keys) >= 0);
     CHECK(srv.stats().keys == uint64_t(n));
+    c->close();
+}
+
+// The async API: callbacks run on the connection's completion thread.
+static void async_api(int port) {
+    auto c = connect_to(port);
+    CHECK(c != nullptr);
+    if (!c) return;
+    const int n = 16, bs = 4096;
+    std::vector<uint8_t> src(size_t(n) * bs, 0x77), dst(size_t(n) * bs, 0);
+    CHECK(c->register_mr(reinterpret_cast<uint64_t>(src.data()), src.size(), -1) > 0);
+    CHECK(c->register_mr(reinterpret_cast<uint64_t>(dst.data()), dst.size(), -1) > 0);
+    std::vector<std::string> names;
+    for (int i = 0; i < n; ++i) names.push_back("async/" + std::to_string(i));
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<RemoteBlock> blocks;
+    int stage = 0, status = -99;
+    c->allocate_async(names, bs, [&](std::vector<RemoteBlock> v) {
+        std::lock_guard<std::mutex> lk(mu);
+        blocks = std::move(v);
+        stage = 1;
+        cv.notify_all();
+    });
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        CHECK(cv.wait_for(lk, std::chrono::seconds(10), [&] { return stage == 1; }));
+    }
+    CHECK(blocks.size() == size_t(n));
+    std::vector<uint64_t> offs(static_cast<size_t>(n), 0);
+    for (int i = 0; i < n; ++i) offs[size_t(i)] = uint64_t(i) * bs;
+    c->w_rdma_async(offs, bs, blocks.data(), blocks.size(), reinterpret_cast<uint64_t>(src.data()),
+                    -1, 0, [&](int st) {
+                        std::lock_guard<std::mutex> lk(mu);
+                        status = st;
+                        stage = 2;
+                        cv.notify_all();
+                    });
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        CHECK(cv.wait_for(lk, std::chrono::seconds(10), [&] { return stage == 2; }));
+    }
+    CHECK(status == 0);
+    CHECK(c->sync_rdma() >= 0);
+    std::vector<KeyOffset> rb;
+    for (int i = 0; i < n; ++i) rb.push_back(KeyOffset{names[size_t(i)], uint64_t(i) * bs});
+    c->r_rdma_async(rb, bs, reinterpret_cast<uint64_t>(dst.data()), -1, 0, [&](int st) {
+        std::lock_guard<std::mutex> lk(mu);
+        status = st;
+        stage = 3;
+        cv.notify_all();
+    });
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        CHECK(cv.wait_for(lk, std::chrono::seconds(10), [&] { return stage == 3; }));
+    }
+    CHECK(status == 0 && src == dst);
     c->close();
 }
 
@@ -166,6 +225,8 @@ int main() {
     }
     const int port = srv.port();
     store_round_trips(port, srv);
+    srv.purge();
+    async_api(port);
     srv.purge();
     eviction_and_dead_writers(port, srv);
     garbage_on_the_wire(port, srv);
