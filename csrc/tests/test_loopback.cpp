@@ -5,6 +5,7 @@
 #include <sys/socket.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
@@ -137,6 +138,52 @@ static void async_api(int port) {
     c->close();
 }
 
+// Several threads share ONE connection (the layer-wise upload pattern: a compute thread and
+// an upload thread, example/demo_prefill.py): every call is thread-safe.
+static void shared_connection_threads(int port) {
+    auto c = connect_to(port);
+    CHECK(c != nullptr);
+    if (!c) return;
+    const int bs = 4096, per = 8, rounds = 12, nthreads = 4;
+    std::vector<std::vector<uint8_t>> bufs(nthreads, std::vector<uint8_t>(size_t(per) * bs));
+    std::vector<std::vector<uint8_t>> outs(nthreads, std::vector<uint8_t>(size_t(per) * bs));
+    for (int t = 0; t < nthreads; ++t) {
+        CHECK(c->register_mr(reinterpret_cast<uint64_t>(bufs[size_t(t)].data()), bufs[size_t(t)].size(), -1) > 0);
+        CHECK(c->register_mr(reinterpret_cast<uint64_t>(outs[size_t(t)].data()), outs[size_t(t)].size(), -1) > 0);
+    }
+    std::atomic<int> bad{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) {
+        th.emplace_back([&, t] {
+            std::vector<uint8_t>& src = bufs[size_t(t)];
+            std::vector<uint8_t>& dst = outs[size_t(t)];
+            std::vector<uint64_t> offs(static_cast<size_t>(per), 0);
+            for (int i = 0; i < per; ++i) offs[size_t(i)] = uint64_t(i) * bs;
+            for (int r = 0; r < rounds; ++r) {
+                std::memset(src.data(), t * 16 + r, src.size());
+                std::vector<std::string> names;
+                for (int i = 0; i < per; ++i)
+                    names.push_back("shared/" + std::to_string(t) + "/" + std::to_string(r) + "/" + std::to_string(i));
+                std::vector<std::string_view> keys(names.begin(), names.end());
+                std::vector<RemoteBlock> blocks;
+                if (c->allocate(keys, bs, blocks) != 0) { ++bad; continue; }
+                if (c->w_rdma(offs.data(), offs.size(), 1, bs, blocks.data(), blocks.size(),
+                              reinterpret_cast<uint64_t>(src.data()), -1, 0) != 0) ++bad;
+                if (c->sync_rdma() < 0) ++bad;
+                std::vector<KeyOffset> rb;
+                for (int i = 0; i < per; ++i) rb.push_back(KeyOffset{names[size_t(i)], uint64_t(i) * bs});
+                if (c->r_rdma(rb, bs, reinterpret_cast<uint64_t>(dst.data()), -1, 0) != 0) ++bad;
+                if (c->sync_rdma() < 0) ++bad;
+                if (src != dst) ++bad;
+                if (c->check_exist(names[0]) != 0) ++bad;
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    CHECK(bad.load() == 0);
+    c->close();
+}
+
 static void eviction_and_dead_writers(int port, Server& srv) {
     auto w = connect_to(port);
     CHECK(w != nullptr);
@@ -227,6 +274,8 @@ int main() {
     store_round_trips(port, srv);
     srv.purge();
     async_api(port);
+    srv.purge();
+    shared_connection_threads(port);
     srv.purge();
     eviction_and_dead_writers(port, srv);
     garbage_on_the_wire(port, srv);
