@@ -6,6 +6,7 @@ Ports the behaviour the reference's integration tests assert
 SURVEY §2.5 and the reference defects that must NOT be reproduced (D1-D5, D10-D12).
 """
 import asyncio
+import os
 import multiprocessing as mp
 import random
 import socket
@@ -807,3 +808,16 @@ def test_huge_key_lists_are_chunked_transparently():
         assert torch.equal(src, dst)
     finally:
         srv.stop()
+
+
+@pytest.mark.parametrize("seed", [1, 21])
+def test_randomised_soak_against_a_model(seed):
+    """tools/soak_cpu.py for a bounded number of operations (seed 21 forces auto-increase)."""
+    import subprocess
+    import sys as _sys
+    from conftest import ROOT
+
+    env = dict(os.environ, **({"SOAK_AUTO": "1"} if seed == 21 else {}))
+    r = subprocess.run([_sys.executable, os.path.join(ROOT, "tools", "soak_cpu.py"), str(seed),
+                        "120", "2000"], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and " OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
