@@ -70,11 +70,9 @@ BlockPtr KVStore::remove(Block* b) {
     return BlockPtr(b);  // adopts the count the table held
 }
 
-Block* KVStore::new_block(std::string_view key, uint64_t h, const Allocation& a, size_t size,
-                          uint32_t gen, uint64_t conn) const {
+Block* KVStore::init_block(void* mem, std::string_view key, uint64_t h, const Allocation& a,
+                           size_t size, uint32_t gen, uint64_t conn) const {
     const size_t header = track_lru_ ? sizeof(LruBlock) : sizeof(Block);
-    void* mem = std::malloc(header + key.size());
-    if (!mem) throw std::bad_alloc();
     Block* b = track_lru_ ? static_cast<Block*>(new (mem) LruBlock()) : new (mem) Block();
     b->seg = a.seg;
     b->mm = mm_;
@@ -148,18 +146,48 @@ int KVStore::reserve(const std::vector<std::string_view>& keys, size_t size, int
         seen[s] = uint32_t(fresh.size());
         fresh.push_back(Fresh{i, h});
     }
+    // Everything that can fail for lack of HOST memory happens before any state changes: the
+    // table is grown, the block headers are allocated, the in-flight slot arrays are sized.
+    // After that the batch cannot fail half way (all or nothing).
+    try {
+        while ((count_ + fresh.size()) * 10 > table_.size() * 6) grow();
+    } catch (const std::bad_alloc&) {
+        return kOutOfMemory;
+    }
+    const size_t header = track_lru_ ? sizeof(LruBlock) : sizeof(Block);
+    std::vector<void*> mem(fresh.size(), nullptr);
+    auto free_mem = [&] {
+        for (void* m : mem) std::free(m);
+    };
+    for (size_t j = 0; j < fresh.size(); ++j) {
+        mem[j] = std::malloc(header + keys[fresh[j].idx].size());
+        if (!mem[j]) {
+            free_mem();
+            return kOutOfMemory;
+        }
+    }
     std::vector<Allocation> allocs;
     allocs.reserve(fresh.size());
-    if (!mm_->allocate(size, fresh.size(), device_hint, allocs)) return kOutOfMemory;
+    if (!mm_->allocate(size, fresh.size(), device_hint, allocs)) {
+        free_mem();
+        return kOutOfMemory;
+    }
+    try {
+        for (const Allocation& a : allocs) (void)inflight_slot(a.seg, a.offset);
+    } catch (const std::bad_alloc&) {
+        for (const Allocation& a : allocs) mm_->deallocate(a.seg, a.offset, size);
+        free_mem();
+        return kOutOfMemory;
+    }
     for (size_t j = 0; j < fresh.size(); ++j) {
         const size_t i = fresh[j].idx;
         uint32_t gen = next_gen_++;
         if (next_gen_ == 0) next_gen_ = 1;  // 0 means "not committed" in the device index
-        Block* blk = new_block(keys[i], fresh[j].hash, allocs[j], size, gen, conn);
+        Block* blk = init_block(mem[j], keys[i], fresh[j].hash, allocs[j], size, gen, conn);
         inflight_slot(allocs[j].seg, allocs[j].offset) = blk;
         ++inflight_count_;
         out[i] = RemoteBlock{allocs[j].seg + 1, gen, blk->addr()};
-        insert(blk);  // the table owns the creator's count
+        insert(blk);  // the table owns the creator's count; capacity was ensured above
     }
     return kFinish;
 }

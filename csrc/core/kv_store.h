@@ -164,8 +164,9 @@ class KVStore {
     void insert(Block* b);          // b->hash set; the table takes over one count
     BlockPtr remove(Block* b);      // out of the table; the table's count moves to the result
     void grow();
-    Block* new_block(std::string_view key, uint64_t h, const Allocation& a, size_t size,
-                     uint32_t gen, uint64_t conn) const;
+    // placement-construct a block (header + key bytes) in `mem`
+    Block* init_block(void* mem, std::string_view key, uint64_t h, const Allocation& a,
+                      size_t size, uint32_t gen, uint64_t conn) const;
 
     // In-flight (reserved, uncommitted) blocks are found by address in O(1): one slot per
     // allocation granule of every pool, holding the block that starts there.
