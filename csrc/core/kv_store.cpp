@@ -284,7 +284,7 @@ int KVStore::match_last_index(const std::vector<std::string_view>& keys) const {
     return left - 1;
 }
 
-size_t KVStore::drop_uncommitted(uint64_t conn) {
+size_t KVStore::drop_uncommitted(uint64_t conn, std::vector<Victim>* victims) {
     if (inflight_count_ == 0) return 0;
     size_t n = 0;
     for (auto& seg : inflight_) {
@@ -294,10 +294,42 @@ size_t KVStore::drop_uncommitted(uint64_t conn) {
             slot = nullptr;
             --inflight_count_;
             ++n;
-            remove(b);  // the returned reference dies here: space back to the pool
+            if (victims) {
+                // the writer's kernel may have claimed (or even published) a way of the device
+                // index for this block: the caller erases it before the space is reused
+                const std::string_view key = b->key();
+                const KeyHash kh = hash_key(reinterpret_cast<const uint8_t*>(key.data()), key.size());
+                victims->push_back(Victim{remove(b), kh});
+            } else {
+                remove(b);  // the returned reference dies here: space back to the pool
+            }
         }
     }
     return n;
+}
+
+size_t KVStore::drop_inflight(const uint64_t* addrs, size_t n, uint64_t conn,
+                              std::vector<Victim>* victims) {
+    size_t done = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t seg = addr_seg(addrs[i]);
+        const uint64_t off = addr_off(addrs[i]);
+        if (seg >= mm_->num_pools() || off >= mm_->pool(seg).bytes()) continue;
+        Block*& slot = inflight_slot(seg, off);
+        Block* b = slot;
+        if (!b || b->offset != off || b->owner != conn) continue;
+        slot = nullptr;
+        --inflight_count_;
+        ++done;
+        if (victims) {
+            const std::string_view key = b->key();
+            const KeyHash kh = hash_key(reinterpret_cast<const uint8_t*>(key.data()), key.size());
+            victims->push_back(Victim{remove(b), kh});
+        } else {
+            remove(b);
+        }
+    }
+    return done;
 }
 
 size_t KVStore::evict(size_t bytes, bool replica, std::vector<Victim>& victims) {

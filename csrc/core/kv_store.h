@@ -125,8 +125,18 @@ class KVStore {
     size_t touch(const std::vector<std::string_view>& keys);
     bool present(std::string_view key) const { return find(key) != nullptr; }
     int match_last_index(const std::vector<std::string_view>& keys) const;
-    // Drop every uncommitted block reserved by `conn` (connection closed).
-    size_t drop_uncommitted(uint64_t conn);
+    struct Victim;
+    // Drop every uncommitted block reserved by `conn` (connection closed).  With `victims`
+    // the blocks are handed to the caller instead of being released: a writer kernel may
+    // already have claimed or published their device-index ways, which must be erased
+    // BEFORE the space can be reused (same contract as evict()).
+    size_t drop_uncommitted(uint64_t conn, std::vector<Victim>* victims = nullptr);
+    // The same for the in-flight blocks at `addrs` that `conn` reserved (a writer reports
+    // that its kernels failed: nothing of that batch may ever become visible).
+    size_t drop_inflight(const uint64_t* addrs, size_t n, uint64_t conn,
+                         std::vector<Victim>* victims = nullptr);
+    // Empties the map.  Blocks that a reader still leases stay alive (and their space stays
+    // reserved) until the lease is dropped - purge is safe while transfers are in flight.
     size_t purge();
     // Remove least-recently-used committed blocks from the map until they cover at least
     // `bytes` of pool space (rounded to granules) or none is left.  Blocks that a reader

@@ -305,6 +305,7 @@ struct Connection::Task {
     cudaEvent_t event = nullptr;
     int status = 0;
     bool commit = false;
+    std::vector<uint64_t> commits;  // addresses written by exactly this task's launches
     std::function<void(int)> done_cb;
 };
 
@@ -600,15 +601,22 @@ int Connection::sync_local() {
         }
         staged = true;
     }
-    if (drain_devices() != 0) {
-        // the data of these blocks may not have landed: they must never become visible (they
-        // stay reserved until this connection closes)
+    bool device_error = false;
+    const int drained = drain_devices(&device_error);
+    if (device_error) {
+        // The data of these blocks may not have landed, while the in-band commit may already
+        // have published some of them in the device index: the server releases them now,
+        // index entries included (reservations it cannot match die with the connection).
         if (staged) {
             const std::vector<uint8_t> f = frame_of(kOpStageCommit, -1, nullptr, 0);
             (void)send_raw(f.data(), f.size());
+        } else {
+            (void)discard_blocks(addrs.data(), addrs.size());
         }
         return -1;
     }
+    // A read that missed (drained < 0 without a device error) does not undo the writes of
+    // the same window: their kernels completed, so their commits are applied all the same.
     std::vector<uint8_t> framed;  // reply-less messages that travel with the SYNC
     if (!staged && !addrs.empty() && send_commit(addrs.data(), addrs.size()) != 0) return -1;
     int32_t code = 0;
@@ -620,6 +628,7 @@ int Connection::sync_local() {
         std::lock_guard<std::mutex> lk(mu_);
         ctrl_dirty_ = false;
     }
+    if (drained != 0) return drained;
     uint32_t remain;
     std::memcpy(&remain, p.data(), sizeof(remain));
     return int(remain);
@@ -650,6 +659,18 @@ int Connection::send_commit(const uint64_t* addrs, size_t count) {
             fail("commit: send failed");
             return -1;
         }
+    }
+    return 0;
+}
+
+int Connection::discard_blocks(const uint64_t* addrs, size_t count) {
+    constexpr size_t kChunk = 256 * 1024;
+    for (size_t at = 0; at < count; at += kChunk) {
+        const size_t n = std::min(kChunk, count - at);
+        std::vector<uint8_t> buf(align_up(n * 8 + 128, 8));
+        fb::Builder b(buf.data(), buf.size());
+        encode_remote_meta(b, {}, -1, 0, addrs + at, n, kOpStageCommit);
+        if (send_only(kOpStageCommit, b.data(), b.size()) != 0) return -1;
     }
     return 0;
 }
@@ -967,10 +988,18 @@ uint8_t* Connection::seg_dev_ptr(DevCtx* ctx, uint32_t seg) {
 // byte offset of block i from base_ptr.
 int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scale,
                             const RemoteBlock* blocks, size_t n, int block_size,
-                            uint64_t base_ptr, int device, uint64_t stream_in, int fp8_elems) {
+                            uint64_t base_ptr, int device, uint64_t stream_in, int fp8_elems,
+                            MoveResult* res) {
     NvtxRange nvtx(write ? "istore.write_blocks" : "istore.read_blocks");
     std::lock_guard<std::mutex> lk(mu_);
     if (n == 0) return 0;
+    // Where the addresses to COMMIT go: the connection-wide list shipped by the next sync(),
+    // or the caller's own list (async writes commit exactly their own blocks when THEIR
+    // kernels have finished, reference: src/libinfinistore.cpp:362-395).  An address is
+    // appended only after the launch that writes the block has succeeded; every error return
+    // below leaves the sink exactly as the last successful launch left it.
+    std::vector<uint64_t>& sink = (res && res->commits) ? *res->commits : pending_commit_;
+    std::vector<uint64_t> batch_commits;
     int kd = device;
     if (device < 0 && fp8_elems) {
         fail("the fp8 KV path needs a CUDA tensor");
@@ -1006,7 +1035,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
                     std::memcpy(pool, local, size_t(block_size));
                 else
                     std::memcpy(local, pool, size_t(block_size));
-                if (write) pending_commit_.push_back(blocks[i].remote_addr);
+                if (write) sink.push_back(blocks[i].remote_addr);
                 stats_.host_copies++;
             }
             (write ? stats_.bytes_written : stats_.bytes_read) += live * uint64_t(block_size);
@@ -1033,6 +1062,10 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
     cudaStream_t stream = ctx->pick(reinterpret_cast<cudaStream_t>(stream_in), write, streams_);
     stats_.ns_streams += now_ns() - t_pick0;
     stats_.calls++;
+    if (res) {
+        res->stream = stream;
+        res->device = kd;
+    }
 
     // the device index lives in segment 0
     kernels::IndexBucket* table = nullptr;
@@ -1057,6 +1090,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             recs = reinterpret_cast<kernels::IndexEntry*>(ctx->ring_h + at_rec);
         }
         uint32_t m = 0;
+        batch_commits.clear();
         uint32_t n_mc = 0;  // blocks of this batch that live in the NVLS-replicated region
         bool can_publish = table != nullptr;
         bool all_remote = true;
@@ -1097,7 +1131,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
                     else
                         can_publish = false;  // not allocated through this connection
                 }
-                pending_commit_.push_back(rb.remote_addr);
+                batch_commits.push_back(rb.remote_addr);
             }
             ++m;
         }
@@ -1152,6 +1186,8 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             return -1;
         }
         ctx->mark(stream);
+        if (res) res->launched = true;
+        sink.insert(sink.end(), batch_commits.begin(), batch_commits.end());
         stats_.kernel_launches++;
         (write ? stats_.bytes_written : stats_.bytes_read) += uint64_t(m) * uint64_t(block_size);
     }
@@ -1160,13 +1196,13 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
 
 int Connection::w_rdma(const uint64_t* offsets, size_t noffsets, uint64_t scale, int block_size,
                        const RemoteBlock* blocks, size_t nblocks, uint64_t base_ptr, int device,
-                       uint64_t stream) {
+                       uint64_t stream, MoveResult* res) {
     if (noffsets != nblocks) {
         fail("w_rdma: offsets and remote blocks differ in length");
         return -1;
     }
     return move_blocks(true, offsets, scale, blocks, nblocks, block_size, base_ptr, device,
-                       stream);
+                       stream, 0, res);
 }
 
 int Connection::w_rdma_fp8(const uint64_t* offsets, size_t noffsets, uint64_t scale, int elems,
@@ -1201,17 +1237,17 @@ int Connection::r_rdma_fp8(const std::vector<KeyOffset>& blocks, int elems, uint
 }
 
 int Connection::r_rdma(const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr,
-                       int device, uint64_t stream) {
+                       int device, uint64_t stream, MoveResult* res) {
     if (blocks.empty()) return 0;
     if (device_lookup_ && server_hbm_ && device >= 0 && device_index_usable())
-        return read_via_device_index(blocks, block_size, base_ptr, device, stream);
+        return read_via_device_index(blocks, block_size, base_ptr, device, stream, 0, res);
     std::vector<RemoteBlock> rb;
     const int r = lookup_blocks(kOpReadLookup, blocks, block_size, rb);
     if (r != 0) return r;
     std::vector<uint64_t> offs(blocks.size());
     for (size_t i = 0; i < blocks.size(); ++i) offs[i] = blocks[i].offset;
     return move_blocks(false, offs.data(), 1, rb.data(), rb.size(), block_size, base_ptr, device,
-                       stream);
+                       stream, 0, res);
 }
 
 int Connection::rw_local(char op, const std::vector<KeyOffset>& blocks, int block_size,
@@ -1257,7 +1293,7 @@ static size_t pack_keys(const std::string_view* keys, size_t n, uint8_t* bytes, 
 
 int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int block_size,
                                       uint64_t base_ptr, int device, uint64_t stream_in,
-                                      int fp8_elems) {
+                                      int fp8_elems, MoveResult* res) {
     NvtxRange nvtx("istore.read_via_device_index");
     std::lock_guard<std::mutex> lk(mu_);
     DevCtx* ctx = dev_ctx(device);
@@ -1272,6 +1308,10 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
     cudaStream_t stream = ctx->pick(reinterpret_cast<cudaStream_t>(stream_in), false, streams_);
     stats_.ns_streams += now_ns() - t_pick0;
     stats_.calls++;
+    if (res) {
+        res->stream = stream;
+        res->device = device;
+    }
     for (size_t base = 0; base < blocks.size(); base += kMaxBatch) {
         const uint64_t t_build0 = now_ns();
         const size_t n = std::min(kMaxBatch, blocks.size() - base);
@@ -1390,6 +1430,7 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             return -1;
         }
         ctx->mark(stream);
+        if (res) res->launched = true;
         stats_.bytes_read += uint64_t(n) * uint64_t(block_size);
     }
     return 0;
@@ -1446,9 +1487,10 @@ int Connection::match_via_device_index(const std::vector<std::string_view>& keys
     return result;
 }
 
-int Connection::drain_devices() {
+int Connection::drain_devices(bool* device_error) {
     std::lock_guard<std::mutex> lk(mu_);
     int rc = 0;
+    if (device_error) *device_error = false;
     struct AtExit {
         Connection* c;
         ~AtExit() { c->release_temporary_host_regs(); }
@@ -1461,6 +1503,7 @@ int Connection::drain_devices() {
         if (e != cudaSuccess) {
             fail(std::string("device error during transfer: ") + cudaGetErrorString(e));
             rc = -1;
+            if (device_error) *device_error = true;
         }
         if (ctx.status_h[kernels::kStatMiss]) {
             fail("read: " + std::to_string(ctx.status_h[kernels::kStatMiss]) +
@@ -1515,7 +1558,14 @@ void Connection::worker() {
                 if (cudaEventSynchronize(t.event) != cudaSuccess) status = -1;
                 cudaEventDestroy(t.event);
             }
-            if (status == 0 && t.commit && flush_commits() != 0) status = -1;
+            if (t.commit && !t.commits.empty()) {
+                if (status == 0) {
+                    if (send_commit(t.commits.data(), t.commits.size()) != 0) status = -1;
+                } else {
+                    // this write's kernels failed: its blocks must never become visible
+                    discard_blocks(t.commits.data(), t.commits.size());
+                }
+            }
             if (t.done_cb) t.done_cb(status);
         }
         {
@@ -1540,22 +1590,29 @@ int Connection::allocate_async(const std::vector<std::string>& keys, int block_s
 int Connection::w_rdma_async(const std::vector<uint64_t>& offsets, int block_size,
                              const RemoteBlock* blocks, size_t nblocks, uint64_t base_ptr,
                              int device, uint64_t stream, std::function<void(int)> cb) {
-    const int r = w_rdma(offsets.data(), offsets.size(), 1, block_size, blocks, nblocks, base_ptr,
-                         device, stream);
+    // The task owns the addresses of exactly the blocks this call wrote; its completion
+    // commits those and no others (later writes of the connection may still be in flight on
+    // other streams).  The event is recorded on the stream this call launched on.
     Task t;
     t.kind = Task::kWaitEvent;
-    t.status = r;
     t.commit = true;
+    MoveResult res;
+    res.commits = &t.commits;
+    const int r = w_rdma(offsets.data(), offsets.size(), 1, block_size, blocks, nblocks, base_ptr,
+                         device, stream, &res);
+    t.status = r;
     t.done_cb = std::move(cb);
-    const int kd = device >= 0 ? device : (cfg_.device >= 0 ? cfg_.device : default_device_);
-    if (r == 0 && kd >= 0 && fabric::cuda_available()) {
-        std::lock_guard<std::mutex> lk(mu_);
-        auto it = devs_.find(kd);
-        if (it != devs_.end() && it->second->dirty) {
-            DeviceGuard g(kd);
-            cudaEventCreateWithFlags(&t.event, cudaEventDisableTiming);
-            cudaEventRecord(t.event, it->second->last);
-            t.device = kd;
+    if (res.launched && res.device >= 0) {
+        DeviceGuard g(res.device);
+        if (cudaEventCreateWithFlags(&t.event, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventRecord(t.event, static_cast<cudaStream_t>(res.stream)) == cudaSuccess) {
+            t.device = res.device;
+        } else {
+            // no event: fall back to waiting for the whole stream before the commit
+            if (t.event) cudaEventDestroy(t.event);
+            t.event = nullptr;
+            (void)cudaGetLastError();
+            if (cudaStreamSynchronize(static_cast<cudaStream_t>(res.stream)) != cudaSuccess) t.status = -1;
         }
     }
     post(std::move(t));
@@ -1565,20 +1622,22 @@ int Connection::w_rdma_async(const std::vector<uint64_t>& offsets, int block_siz
 int Connection::r_rdma_async(const std::vector<KeyOffset>& blocks, int block_size,
                              uint64_t base_ptr, int device, uint64_t stream,
                              std::function<void(int)> cb) {
-    const int r = r_rdma(blocks, block_size, base_ptr, device, stream);
+    MoveResult res;
+    const int r = r_rdma(blocks, block_size, base_ptr, device, stream, &res);
     Task t;
     t.kind = Task::kWaitEvent;
     t.status = r;
     t.done_cb = std::move(cb);
-    const int kd = device >= 0 ? device : (cfg_.device >= 0 ? cfg_.device : default_device_);
-    if (r == 0 && kd >= 0 && fabric::cuda_available()) {
-        std::lock_guard<std::mutex> lk(mu_);
-        auto it = devs_.find(kd);
-        if (it != devs_.end() && it->second->dirty) {
-            DeviceGuard g(kd);
-            cudaEventCreateWithFlags(&t.event, cudaEventDisableTiming);
-            cudaEventRecord(t.event, it->second->last);
-            t.device = kd;
+    if (r == 0 && res.launched && res.device >= 0) {
+        DeviceGuard g(res.device);
+        if (cudaEventCreateWithFlags(&t.event, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventRecord(t.event, static_cast<cudaStream_t>(res.stream)) == cudaSuccess) {
+            t.device = res.device;
+        } else {
+            if (t.event) cudaEventDestroy(t.event);
+            t.event = nullptr;
+            (void)cudaGetLastError();
+            if (cudaStreamSynchronize(static_cast<cudaStream_t>(res.stream)) != cudaSuccess) t.status = -1;
         }
     }
     post(std::move(t));

@@ -115,11 +115,20 @@ class Connection {
     int allocate(const std::vector<std::string_view>& keys, int block_size,
                  std::vector<RemoteBlock>& out, int hint = kHintDefault);
     // offsets[i] * scale = byte offset of block i (scale lets callers pass element offsets)
+    // What one data-plane call did: the stream (and device) its kernels were launched on,
+    // and - for writes, when `commits` is set - the addresses of exactly the blocks it wrote
+    // (otherwise they join the connection-wide list that the next sync() commits).
+    struct MoveResult {
+        std::vector<uint64_t>* commits = nullptr;
+        void* stream = nullptr;  // cudaStream_t
+        int device = -1;
+        bool launched = false;
+    };
     int w_rdma(const uint64_t* offsets, size_t noffsets, uint64_t scale, int block_size,
                const RemoteBlock* blocks, size_t nblocks, uint64_t base_ptr, int device,
-               uint64_t stream);
+               uint64_t stream, MoveResult* res = nullptr);
     int r_rdma(const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr, int device,
-               uint64_t stream);
+               uint64_t stream, MoveResult* res = nullptr);
     int rw_local(char op, const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr,
                  int device, uint64_t stream);
     // fp8 KV path: pages are bf16 in the caller's tensor (`elems` elements each) and
@@ -173,14 +182,18 @@ class Connection {
     std::shared_ptr<fabric::Mapping> mapping(uint32_t seg, int device);
     int move_blocks(bool write, const uint64_t* local_off, uint64_t scale,
                     const RemoteBlock* blocks, size_t n, int block_size, uint64_t base_ptr,
-                    int device, uint64_t stream, int fp8_elems = 0);
+                    int device, uint64_t stream, int fp8_elems = 0, MoveResult* res = nullptr);
+    // tell the server that the blocks at `addrs` were not (completely) written: it releases
+    // them, device-index entries included
+    int discard_blocks(const uint64_t* addrs, size_t count);
     uint8_t* seg_dev_ptr(DevCtx* ctx, uint32_t seg);
     int read_via_device_index(const std::vector<KeyOffset>& blocks, int block_size,
-                              uint64_t base_ptr, int device, uint64_t stream, int fp8_elems = 0);
+                              uint64_t base_ptr, int device, uint64_t stream, int fp8_elems = 0,
+                              MoveResult* res = nullptr);
     int match_via_device_index(const std::vector<std::string_view>& keys, bool exist_only);
     int ensure_host_registered(uint64_t ptr, size_t bytes, int device, bool temporary);
     void release_temporary_host_regs();
-    int drain_devices();
+    int drain_devices(bool* device_error = nullptr);
     bool device_index_usable();
     void fail(const std::string& msg);
 

@@ -253,7 +253,10 @@ size_t Server::kvmap_len() {
 
 size_t Server::purge() {
     std::lock_guard<std::mutex> lk(mu_);
-    for (auto& kv : conns_) kv.second->leases.clear();
+    // Leases of host-mediated readers are NOT dropped here: a leased block leaves the map but
+    // keeps its pool space until the reader's SYNC lets go of it, so a copy that is still
+    // running never sees the space handed to a new writer (reference: intrusive_ptr keeps
+    // in-flight blocks alive across purge, src/infinistore.cpp:1110-1116).
     const size_t n = store_->purge();
     for (auto& s : segs_) s->clear_index();
     quarantine_.clear();  // the index is empty now: nothing can resolve these blocks any more
@@ -457,12 +460,13 @@ long Server::load(const std::string& path, std::string* err) {
                 staging_cap = std::max<size_t>(size_t(size) + 256, 4u << 20);
                 if (cudaHostAlloc(&staging, staging_cap, cudaHostAllocMapped | cudaHostAllocPortable) !=
                     cudaSuccess) {
+                    staging = nullptr;
+                    staging_cap = 0;
                     ok = false;
-                    break;
                 }
             }
-            ok = std::fread(staging, 1, size, f) == size;
-            if (!ok) break;
+            ok = ok && std::fread(staging, 1, size, f) == size;
+            if (ok) {
             if (seg.info().kind == kSegReplica) {
                 // every replica must receive the bytes: write through the multicast address
                 dst = static_cast<uint8_t*>(seg.base()) + addr_off(blocks[0].remote_addr);
@@ -498,10 +502,17 @@ long Server::load(const std::string& path, std::string* err) {
             const cudaError_t e = kernels::launch_kv_copy(L, nullptr);
             ok = e == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
             if (rec_dev) cudaFree(rec_dev);
+            }  // if (ok)
             if (!ok) (void)cudaGetLastError();
         }
-        if (!ok) break;
         const uint64_t addr = blocks[0].remote_addr;
+        if (!ok) {
+            // the block was reserved for connection 0 and never committed: give it back
+            std::vector<KVStore::Victim> victims;
+            store_->drop_inflight(&addr, 1, 0, &victims);
+            release_dropped(victims);
+            break;
+        }
         store_->commit(&addr, 1);
         ++loaded;
     }
@@ -586,8 +597,22 @@ void Server::on_accept() {
     }
 }
 
+// Blocks a writer reserved but never committed.  Its kernel may already have claimed - or,
+// with the in-band commit, even published - their ways of the device index, so the entries
+// are erased before the space returns to the pool; if that cannot be proven the blocks are
+// quarantined (space stays reserved until the next purge) rather than risk a device-path
+// reader resolving the key to reused memory.
+void Server::release_dropped(std::vector<KVStore::Victim>& victims) {
+    if (victims.empty()) return;
+    if (!erase_from_device_index(victims))
+        quarantine_.insert(quarantine_.end(), victims.begin(), victims.end());
+    victims.clear();
+}
+
 void Server::close_conn(Conn* c) {
-    const size_t dropped = store_->drop_uncommitted(c->id);
+    std::vector<KVStore::Victim> victims;
+    const size_t dropped = store_->drop_uncommitted(c->id, &victims);
+    release_dropped(victims);
     if (dropped)
         LOG_WARN("connection %llu closed with %zu uncommitted blocks: released",
                  (unsigned long long)c->id, dropped);
@@ -912,6 +937,12 @@ int Server::handle_lookup(Conn* c, bool local) {
 int Server::handle_stage_commit(Conn* c) {
     RemoteMetaRequest req = decode_remote_meta(c->body.data(), c->body.size());
     if (req.block_size < 0) {  // the writer's kernels failed: nothing of it becomes visible
+        // the staged blocks (plus any the client names) are released right away, device-index
+        // entries included: the in-band commit may already have published some of them
+        std::vector<KVStore::Victim> victims;
+        store_->drop_inflight(c->staged.data(), c->staged.size(), c->id, &victims);
+        store_->drop_inflight(req.remote_addrs.data(), req.remote_addrs.size(), c->id, &victims);
+        release_dropped(victims);
         c->staged.clear();
         return kFinish;
     }

@@ -127,6 +127,9 @@ class Server {
     // of the device index (erase kernel, synchronised), then back to the pool.
     bool evict_some(size_t want, bool replica);
     bool erase_from_device_index(const std::vector<KVStore::Victim>& victims);
+    // Uncommitted blocks taken out of the map: erase their device-index ways, then free them
+    // (or quarantine them when the erase cannot be confirmed).
+    void release_dropped(std::vector<KVStore::Victim>& victims);
 
     int handle_exchange(Conn* c);
     int handle_pool_map(Conn* c);

@@ -6,7 +6,8 @@ Flags, defaults and endpoints follow the reference (infinistore/server.py:26-263
 --num-stream --warmup`` and ``POST /purge``, ``POST /selftest/{port}``, ``GET /kvmap_len``.
 New: ``--pool-backend``, ``--pool-devices``, ``--extend-size``, ``--replica-size``,
 ``--load-from``, ``--evict``, ``--evict-ratio``; ``GET /metrics`` (Prometheus text), ``GET /stats`` (JSON), ``POST /dump`` and
-``POST /load`` (checkpoint / resume).  ``--host`` is honoured (the reference parses
+``POST /load`` (checkpoint / resume; bare names inside ``--checkpoint-dir`` only, token or
+loopback callers only).  ``--host`` is honoured (the reference parses
 and ignores it).  The data/control plane runs on a native reactor thread; uvicorn only
 serves the manage plane.
 """
@@ -35,14 +36,93 @@ from .lib import (
     server_stats,
 )
 
+try:  # resolvable from module scope: the endpoint annotations below are strings (PEP 563)
+    from fastapi import Request
+except ImportError:  # pragma: no cover - the manage plane needs fastapi, the library does not
+    Request = None
+
 logging.disable(logging.INFO)  # the store has its own logger
 
 
-def _make_app():
-    from fastapi import FastAPI
+class CheckpointPolicy:
+    """Where the manage plane may read and write checkpoints, and who may ask.
+
+    ``/dump`` and ``/load`` take a bare file NAME that is resolved inside ``directory``
+    (``--checkpoint-dir``); without a directory both endpoints answer 403.  Names with a path
+    separator, a leading dot or ``..`` are refused, so a request can never reach a file outside
+    the directory.  Callers must present ``token`` (``--manage-token``, header
+    ``X-Infinistore-Token``) when one is configured; without a token only loopback peers
+    are served, because the manage port listens on ``--host`` (0.0.0.0 by default, as in the
+    reference).  Dumps are written to a temporary file and renamed into place."""
+
+    def __init__(self, directory: str = "", token: str = ""):
+        self.directory = os.path.realpath(directory) if directory else ""
+        self.token = token or ""
+
+    def authorize(self, client_host: str | None, presented: str | None) -> str | None:
+        """None when the caller may use a mutating endpoint, else the reason."""
+        if self.token:
+            import hmac
+
+            if presented is None or not hmac.compare_digest(presented, self.token):
+                return "missing or wrong X-Infinistore-Token"
+            return None
+        if client_host in ("127.0.0.1", "::1", "localhost", "testclient"):
+            return None
+        return "checkpoint endpoints without --manage-token are served to loopback peers only"
+
+    def resolve(self, name: str) -> str:
+        if not self.directory:
+            raise PermissionError("checkpoints are disabled: start the server with --checkpoint-dir")
+        if (not name or name != os.path.basename(name) or name.startswith(".")
+                or "/" in name or "\\" in name or "\x00" in name or ".." in name):
+            raise ValueError("checkpoint name must be a bare file name")
+        path = os.path.realpath(os.path.join(self.directory, name))
+        if os.path.dirname(path) != self.directory:
+            raise ValueError("checkpoint name escapes the checkpoint directory")
+        return path
+
+    def dump(self, name: str) -> int:
+        path = self.resolve(name)
+        os.makedirs(self.directory, exist_ok=True)
+        tmp = f"{path}.tmp.{os.getpid()}"
+        try:
+            n = _lib.dump_kv_map(tmp)
+            os.replace(tmp, path)
+        finally:
+            if os.path.exists(tmp):
+                os.unlink(tmp)
+        return n
+
+    def load(self, name: str) -> int:
+        path = self.resolve(name)
+        if not os.path.isfile(path):
+            raise FileNotFoundError(name)
+        return _lib.load_kv_map(path)
+
+
+def _make_app(policy: CheckpointPolicy | None = None):
+    from fastapi import FastAPI, HTTPException
     from fastapi.responses import PlainTextResponse
 
     app = FastAPI()
+    policy = policy or CheckpointPolicy()
+
+    def _guard(request: Request):
+        why = policy.authorize(request.client.host if request.client else None,
+                               request.headers.get("x-infinistore-token"))
+        if why:
+            raise HTTPException(status_code=403, detail=why)
+
+    async def _checkpoint(fn, name: str):
+        try:
+            return await asyncio.to_thread(fn, name)
+        except PermissionError as e:
+            raise HTTPException(status_code=403, detail=str(e))
+        except FileNotFoundError:
+            raise HTTPException(status_code=404, detail="no such checkpoint")
+        except ValueError as e:
+            raise HTTPException(status_code=400, detail=str(e))
 
     @app.post("/purge")
     async def purge():
@@ -59,16 +139,18 @@ def _make_app():
         return await run_selftest(number)
 
     @app.post("/dump")
-    async def dump(path: str):
-        """Checkpoint every committed block to `path` on the server host."""
-        n = await asyncio.to_thread(_lib.dump_kv_map, path)
-        return {"status": "ok", "num": n, "path": path}
+    async def dump(name: str, request: Request):
+        """Checkpoint every committed block to the file `name` inside --checkpoint-dir."""
+        _guard(request)
+        n = await _checkpoint(policy.dump, name)
+        return {"status": "ok", "num": n, "name": name}
 
     @app.post("/load")
-    async def load(path: str):
-        """Load a checkpoint (keys already in the store win)."""
-        n = await asyncio.to_thread(_lib.load_kv_map, path)
-        return {"status": "ok", "num": n, "path": path}
+    async def load(name: str, request: Request):
+        """Load the checkpoint `name` from --checkpoint-dir (keys already in the store win)."""
+        _guard(request)
+        n = await _checkpoint(policy.load, name)
+        return {"status": "ok", "num": n, "name": name}
 
     @app.get("/kvmap_len")
     async def kvmap_len():
@@ -182,6 +264,12 @@ def parse_args(argv=None):
     p.add_argument("--extend-size", default=10, type=int, help="GB per auto-increase step")
     p.add_argument("--load-from", default="", type=str,
                    help="checkpoint file (POST /dump) to load at start-up")
+    p.add_argument("--checkpoint-dir", default="", type=str,
+                   help="directory POST /dump and POST /load may use (bare file names only); "
+                        "empty = both endpoints disabled")
+    p.add_argument("--manage-token", default=os.environ.get("INFINISTORE_MANAGE_TOKEN", ""),
+                   type=str, help="shared secret for /dump and /load (header X-Infinistore-Token); "
+                                  "without it only loopback callers are served")
     p.add_argument("--replica-size", default=0, type=int,
                    help="GB per GPU of NVLS-replicated region for one-writer/many-reader blocks")
     p.add_argument("--evict", action="store_true",
@@ -256,7 +344,8 @@ def main(argv=None):
 
     import uvicorn
 
-    http_config = uvicorn.Config(_make_app(), host=args.host, port=config.manage_port,
+    policy = CheckpointPolicy(args.checkpoint_dir, args.manage_token)
+    http_config = uvicorn.Config(_make_app(policy), host=args.host, port=config.manage_port,
                                  loop=loop_kind, log_level="warning")
     server = uvicorn.Server(http_config)
     Logger.warn("server started")

@@ -5,6 +5,8 @@ import signal
 import subprocess
 import sys
 import time
+import urllib.error
+import urllib.parse
 import urllib.request
 
 import pytest
@@ -13,15 +15,19 @@ import torch
 from conftest import ROOT, free_port, make_conn
 
 
+CKPT_DIR = f"/tmp/istore_cli_ckpt_{os.getpid()}"
+
+
 @pytest.fixture(scope="module")
 def cli_server():
     sport, mport = free_port(), free_port()
+    os.makedirs(CKPT_DIR, exist_ok=True)
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
     proc = subprocess.Popen(
         [sys.executable, "-m", "infinistore.server", "--service-port", str(sport),
          "--manage-port", str(mport), "--host", "127.0.0.1", "--pool-backend", "host",
          "--prealloc-size", "1", "--minimal-allocate-size", "16", "--log-level", "warning",
-         "--dev-name", "mlx5_2", "--link-type", "Ethernet"],
+         "--dev-name", "mlx5_2", "--link-type", "Ethernet", "--checkpoint-dir", CKPT_DIR],
         env=env, cwd=ROOT)
     deadline = time.time() + 60
     while time.time() < deadline:
@@ -68,12 +74,22 @@ def test_manage_plane_and_selftest(cli_server):
     assert 'infinistore_op_service_us{op="ALLOCATE",quantile="0.99"}' in text
     lat = stats["op_latency_us"]["ALLOCATE"]
     assert lat["count"] >= 2 and 0 < lat["p50_us"] <= lat["p99_us"] and lat["max_us"] >= lat["mean_us"]
-    ckpt = "/tmp/istore_cli_test.ckpt"
-    assert _http("POST", base + f"/dump?path={ckpt}")["num"] == 11
+    ckpt = "cli_test.ckpt"
+    # checkpoints are bare names inside --checkpoint-dir: a path can never leave it
+    for bad in ("/etc/passwd", "../x.ckpt", "..", ".hidden", "a/b"):
+        with pytest.raises(urllib.error.HTTPError) as ei:
+            _http("POST", base + "/dump?name=" + urllib.parse.quote(bad, safe=""))
+        assert ei.value.code == 400
+    with pytest.raises(urllib.error.HTTPError) as ei:
+        _http("POST", base + "/load?name=absent.ckpt")
+    assert ei.value.code == 404
+    assert _http("POST", base + f"/dump?name={ckpt}")["num"] == 11
+    assert os.path.isfile(os.path.join(CKPT_DIR, ckpt))
+    assert not [f for f in os.listdir(CKPT_DIR) if ".tmp." in f]  # written then renamed
     assert _http("POST", base + "/purge") == {"status": "ok", "num": 11}
     assert _http("GET", base + "/kvmap_len") == {"len": 0}
     assert not conn.check_exist("cli-0")
-    assert _http("POST", base + f"/load?path={ckpt}")["num"] == 11
+    assert _http("POST", base + f"/load?name={ckpt}")["num"] == 11
     assert conn.check_exist("cli-0")
     dst = torch.zeros(1024)
     conn.read_cache(dst, [("cli-5", 0)], 1024)
@@ -112,3 +128,21 @@ def test_arg_defaults_match_reference():
     import pytest
     with pytest.raises(Exception):
         cfg.verify()
+
+
+def test_checkpoint_policy_token_and_disabled():
+    from infinistore_b200.server import CheckpointPolicy
+
+    off = CheckpointPolicy("", "")
+    with pytest.raises(PermissionError):
+        off.resolve("x.ckpt")  # no --checkpoint-dir: endpoints disabled
+    assert off.authorize("127.0.0.1", None) is None
+    assert off.authorize("10.1.2.3", None) is not None  # remote callers need a token
+    tok = CheckpointPolicy("/tmp/istore_policy_dir", "s3cret")
+    assert tok.authorize("10.1.2.3", "s3cret") is None
+    assert tok.authorize("127.0.0.1", None) is not None
+    assert tok.authorize("127.0.0.1", "wrong") is not None
+    assert tok.resolve("a.ckpt") == os.path.realpath("/tmp/istore_policy_dir/a.ckpt")
+    for bad in ("../a", "/abs", "a/b", ".a", "", "a..b"):
+        with pytest.raises(ValueError):
+            tok.resolve(bad)

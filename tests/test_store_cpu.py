@@ -535,9 +535,78 @@ def test_purge_while_reader_holds_lease(host_server):
     dst = torch.zeros(4096)
     conn.read_cache(dst, [("p", 0)], 4096)  # lookup pins the block until the next sync
     assert srv.purge() == 1
+    # the leased block left the map but keeps its pool space until the reader's sync(): a new
+    # writer can never be handed memory that an in-flight copy is still reading
+    assert srv.stats()["used_bytes"] == 16384
     conn.sync()
     assert srv.stats()["used_bytes"] == 0
     assert not conn.check_exist("p")
+
+
+def test_purge_does_not_hand_leased_space_to_a_new_writer():
+    """A pool of exactly two blocks, both leased by a reader: after purge() an allocation
+    must fail (507) until the reader's sync() releases them (purge dropped leases)."""
+    from infinistore_b200 import _infinistore as m
+
+    cfg = m.ServerConfig()
+    cfg.service_port = 0
+    cfg.host = "127.0.0.1"
+    cfg.pool_backend = "host"
+    cfg.prealloc_bytes = 2 * 16384
+    cfg.minimal_allocate_size = 16
+    srv = m.Server(cfg)
+    port = srv.start()
+    try:
+        writer, reader, other = make_conn(port), make_conn(port), make_conn(port)
+        src = torch.randn(2 * 4096)
+        writer.register_mr(src)
+        writer.rdma_write_cache(src, [0, 4096], 4096, writer.allocate_rdma(["a", "b"], 16384))
+        writer.sync()
+        dst = torch.zeros(2 * 4096)
+        reader.read_cache(dst, [("a", 0), ("b", 4096)], 4096)  # leases until reader.sync()
+        assert srv.purge() == 2
+        with pytest.raises(Exception):
+            other.allocate_rdma(["c"], 16384)  # the space is still the reader's
+        reader.sync()
+        assert torch.equal(src, dst)
+        assert len(other.allocate_rdma(["c"], 16384)) == 1
+    finally:
+        srv.stop()
+
+
+def test_async_write_commits_only_its_own_blocks(host_server):
+    """An async write's completion commits exactly the blocks it wrote - not blocks of other
+    writes of the connection that are still waiting for their sync()."""
+    _, port = host_server
+    conn = make_conn(port)
+    probe = make_conn(port)
+    src = torch.randn(2 * 1024)
+    conn.register_mr(src)
+    blocks = conn.allocate_rdma(["sync-side", "async-side"], 4096)
+    conn.rdma_write_cache(src, [0], 1024, blocks[:1])  # pending until conn.sync()
+
+    async def run():
+        await conn.rdma_write_cache_async(src, [1024], 1024, blocks[1:])
+
+    asyncio.run(asyncio.wait_for(run(), 10))
+    assert probe.check_exist("async-side")
+    assert not probe.check_exist("sync-side")  # its commit still waits for sync()
+    conn.sync()
+    assert probe.check_exist("sync-side")
+
+
+def test_read_miss_does_not_discard_commits_of_the_same_window(host_server):
+    _, port = host_server
+    conn = make_conn(port)
+    src = torch.randn(1024)
+    conn.register_mr(src)
+    conn.rdma_write_cache(src, [0], 1024, conn.allocate_rdma(["w-ok"], 4096))
+    dst = torch.zeros(1024)
+    with pytest.raises(Exception):
+        conn.read_cache(dst, [("absent-key", 0)], 1024)
+        conn.sync()
+    conn.sync()
+    assert conn.check_exist("w-ok")
 
 
 # ------------------------------------------------------------------ protocol hardening
@@ -654,27 +723,36 @@ def test_staged_commit_becomes_visible_only_at_sync(host_server):
     _raw_request(s, b"C", b"st-a")  # a round trip on the same connection orders us after 'U'
     assert struct.unpack("<ii", _recv_exact(s, 8)) == (200, 1)
     assert not observer.check_exist("st-a") and srv.stats()["inflight"] == 3
-    # discard, then stage only the first block, then SYNC applies exactly that
+    # discard (the writer's kernels failed): the staged blocks are released right away - their
+    # data may be incomplete, so they must never become visible - and the keys are free again
     _raw_request(s, b"U", enc([], -1, 0, [], "U"))
-    _raw_request(s, b"U", enc([], 0, 0, addrs[:1], "U"))
+    _raw_request(s, b"C", b"st-a")
+    assert struct.unpack("<ii", _recv_exact(s, 8)) == (200, 1)
+    assert srv.stats()["inflight"] == 1
+    # stage the remaining block, then SYNC applies exactly that
+    _raw_request(s, b"U", enc([], 0, 0, addrs[2:], "U"))
     _raw_request(s, b"S")
     assert struct.unpack("<iI", _recv_exact(s, 8)) == (200, 0)
-    assert observer.check_exist("st-a") and not observer.check_exist("st-b")
-    assert srv.stats()["inflight"] == 2
+    assert observer.check_exist("st-c") and not observer.check_exist("st-b")
+    assert srv.stats()["inflight"] == 0
     # a writer that dies with a staged list commits nothing
-    _raw_request(s, b"U", enc([], 0, 0, addrs[1:], "U"))
-    _raw_request(s, b"C", b"st-b")
+    _raw_request(s, b"D", enc(["st-d"], 4096, 0, [], "D"))
+    code, n = struct.unpack("<iI", _recv_exact(s, 8))
+    assert code == 200
+    late = [int(a) for a in m.testing.decode_allocate_response(_recv_exact(s, n))["remote_addr"]]
+    _raw_request(s, b"U", enc([], 0, 0, late, "U"))
+    _raw_request(s, b"C", b"st-d")
     assert struct.unpack("<ii", _recv_exact(s, 8)) == (200, 1)
     s.close()
     deadline = time.time() + 5
     while srv.stats()["inflight"] and time.time() < deadline:
         time.sleep(0.01)
     assert srv.stats()["inflight"] == 0 and srv.kvmap_len() == 1
-    assert not observer.check_exist("st-b") and not observer.check_exist("st-c")
+    assert not observer.check_exist("st-b") and not observer.check_exist("st-d")
     # malformed 'U' gets no reply and does not desynchronise the stream
     s2 = _raw(port)
     _raw_request(s2, b"U", b"\xff" * 24)
-    _raw_request(s2, b"C", b"st-a")
+    _raw_request(s2, b"C", b"st-c")
     assert struct.unpack("<ii", _recv_exact(s2, 8)) == (200, 0)
 
 
