@@ -1,14 +1,21 @@
 #!/usr/bin/env python
-"""The multi-GPU configurations of BASELINE.json beyond the flagship (bench.py = config 2).
+"""The configurations of BASELINE.json beyond the flagship (bench.py = config 2), single-block
+latency percentiles and the emulated baselines - as functions bench.py calls inside its own
+run (so they land in the driver-visible JSON line under `extra` / `baselines`) and as a CLI:
+
+    torchrun --nproc-per-node N bench/configs.py {fanin,fp8,bcast,latency,baselines}
 
   fanin   (config 3)  N-1 client GPUs -> 1 pool GPU, Llama-3-8B KV pages (256 KiB per K or V
-                      page per layer), layer-wise writes then reads.     torchrun, N ranks
-  bcast   (config 4)  1 writer -> all GPUs through NVLS multicast, 1 MB blocks, plus
-                      get_match_last_index on the device.                 single process
+                      page per layer), layer-wise writes then reads.
+  bcast   (config 4)  1 writer -> every GPU through the store's NVLS-replicated region
+                      (multimem.st, 1 MB blocks), readers on every rank read their local
+                      replica; plus get_match_last_index on the device vs the server op.
   fp8     (config 5)  fp8 KV path: write fused with the bf16->e4m3 cast, read fused with the
-                      dequantising gather, 64 KB (fp8) blocks, ring over N GPUs.  torchrun
+                      dequantising gather, 64 KB (fp8) blocks, ring over N GPUs.
 
-Every number is wall time around (issue + sync) taken as the max over ranks; one JSON line.
+Timing: CUDA events recorded on the rank's current stream around (issue + sync()); the
+stream is otherwise idle, so the pair brackets the transfer on the device clock; every number
+is the max over ranks.
 """
 from __future__ import annotations
 
@@ -18,200 +25,251 @@ import os
 import sys
 import time
 import uuid
+from dataclasses import dataclass
+from typing import Any, Callable
 
 import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 import infinistore_b200 as ist  # noqa: E402
 from infinistore_b200 import _infinistore as native  # noqa: E402
 from infinistore_b200.models import get_layout  # noqa: E402
-from infinistore_b200.parallel import PrefixBroadcaster, nvls_available, start_shard_server  # noqa: E402
+from infinistore_b200.parallel import nvls_available, start_shard_server  # noqa: E402
 
 
-def dist_setup():
-    import torch.distributed as dist
-
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
-    return dist, rank, world, local, dev
-
-
-def allmax(dist, dev, x):
-    t = torch.tensor([x], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+@dataclass
+class Ctx:
+    dist: Any
+    rank: int
+    world: int
+    local: int
+    dev: torch.device
+    base_port: int
+    barrier: Callable[[], None]
+    allmax: Callable[[float], float]
+    allsum: Callable[[float], float]
+    allmin: Callable[[float], float]
 
 
-def base_port():
-    return 25000 + int(os.environ.get("MASTER_PORT", "0")) % 2000
+class DevTimer:
+    """Accumulates device time (ms) between start() and stop() with CUDA events."""
+
+    def __init__(self):
+        self.ms = 0.0
+
+    def start(self):
+        self.e0 = torch.cuda.Event(enable_timing=True)
+        self.e1 = torch.cuda.Event(enable_timing=True)
+        self.e0.record()
+
+    def stop(self):
+        self.e1.record()
+        self.e1.synchronize()
+        self.ms += self.e0.elapsed_time(self.e1)
+
+
+def _client(ctx: Ctx, port: int, **kw):
+    conn = ist.InfinityConnection(ist.ClientConfig(
+        host_addr="127.0.0.1", service_port=port, connection_type=ist.TYPE_RDMA,
+        device=ctx.local, device_lookup=True, log_level="warning", **kw))
+    conn.connect()
+    return conn
+
+
+# --------------------------------------------------------------------------- latency
+def latency(ctx: Ctx, conn, sizes_kb=(4, 128, 1024), samples=200):
+    """One block written (or read) + sync(): p50 / p99 in microseconds, per block size, over
+    the ring peer (NVLink for N >= 2, local HBM at N = 1).  Host clock around the call pair -
+    this IS a host-visible latency - max over ranks of each percentile."""
+    out = {}
+    for kb in sizes_kb:
+        elems = kb * 1024 // 2
+        src = torch.randn(elems, device=ctx.dev).to(torch.bfloat16)
+        dst = torch.zeros_like(src)
+        conn.register_mr(src)
+        conn.register_mr(dst)
+        keys = [f"lat-{kb}-{ctx.rank}-{uuid.uuid4().hex[:8]}-{i}" for i in range(samples + 20)]
+        remote = conn.allocate_rdma(keys, kb * 1024)
+        tw, tr = [], []
+        for i, k in enumerate(keys):
+            t0 = time.perf_counter()
+            conn.rdma_write_cache(src, [0], elems, remote[i:i + 1])
+            conn.sync()
+            t1 = time.perf_counter()
+            conn.read_cache(dst, [(k, 0)], elems)
+            conn.sync()
+            t2 = time.perf_counter()
+            if i >= 20:
+                tw.append((t1 - t0) * 1e6)
+                tr.append((t2 - t1) * 1e6)
+        tw.sort()
+        tr.sort()
+        assert torch.equal(src, dst)
+        q = lambda v, p: v[min(len(v) - 1, int(p * len(v)))]  # noqa: E731
+        out[f"{kb}KB"] = {"write_sync_p50": round(ctx.allmax(q(tw, 0.5)), 1),
+                          "write_sync_p99": round(ctx.allmax(q(tw, 0.99)), 1),
+                          "read_sync_p50": round(ctx.allmax(q(tr, 0.5)), 1),
+                          "read_sync_p99": round(ctx.allmax(q(tr, 0.99)), 1)}
+    out["path"] = "NVLink (ring peer)" if ctx.world > 1 else "local HBM"
+    return out
+
+
+# --------------------------------------------------------------------------- baselines
+def baselines(ctx: Ctx, block_bytes: int, size_bytes: int = 1 << 30, layers: int = 32):
+    """EMULATIONS, built from library calls only (none of this repo's kernels): the
+    reference cannot be built offline, so its data-movement patterns are re-created.
+      reference_localgpu_pattern : reference LOCAL_GPU path (src/infinistore.cpp:570-804):
+          per block one cudaMemcpyAsync GPU -> pinned host pool (write) and back (read), a
+          fresh stream + event per request.  All ranks run it at once.
+      nccl_sendrecv_ring : "only calls NCCL": each request's pages as one contiguous tensor
+          to the ring peer and back (N >= 2)."""
+    out = {}
+    nblocks = size_bytes // block_bytes
+    per = nblocks // layers
+    src = torch.empty(size_bytes, dtype=torch.uint8, device=ctx.dev).random_(0, 255)
+    dst = torch.zeros_like(src)
+    pool = torch.empty(size_bytes, dtype=torch.uint8).pin_memory()
+    sp = [src.data_ptr() + i * block_bytes for i in range(nblocks)]
+    pp = [pool.data_ptr() + i * block_bytes for i in range(nblocks)]
+    dp = [dst.data_ptr() + i * block_bytes for i in range(nblocks)]
+    tm = DevTimer()
+    for it in range(2):
+        torch.cuda.synchronize()
+        ctx.barrier()
+        if it:
+            tm.start()
+        for l in range(layers):
+            native.baseline.memcpy_blocks(pp[l * per:(l + 1) * per], sp[l * per:(l + 1) * per],
+                                          block_bytes, True, ctx.local)
+        for l in range(layers):
+            native.baseline.memcpy_blocks(dp[l * per:(l + 1) * per], pp[l * per:(l + 1) * per],
+                                          block_bytes, True, ctx.local)
+        torch.cuda.synchronize()
+        if it:
+            tm.stop()
+    ok = bool(torch.equal(src, dst))
+    ms = ctx.allmax(tm.ms)
+    out["reference_localgpu_pattern"] = {
+        "kind": "EMULATION of the reference's LOCAL_GPU path with per-block cudaMemcpyAsync to a "
+                "pinned host pool, fresh stream+event per request (src/infinistore.cpp:570-804)",
+        "aggregate_GBps": round(ctx.world * 2 * size_bytes / ms / 1e6, 2),
+        "per_gpu_GBps": round(2 * size_bytes / ms / 1e6, 2), "block_kb": block_bytes >> 10,
+        "verified": ok}
+    del pool
+    if ctx.world > 1:
+        dist = ctx.dist
+        nxt, prv = (ctx.rank + 1) % ctx.world, (ctx.rank - 1) % ctx.world
+        rbuf = torch.empty_like(src)
+        seg = size_bytes // layers
+        tm = DevTimer()
+        for it in range(2):
+            torch.cuda.synchronize()
+            ctx.barrier()
+            if it:
+                tm.start()
+            for phase in range(2):  # "write" to the next rank's pool, "read" it back
+                for l in range(layers):
+                    s = slice(l * seg, (l + 1) * seg)
+                    a, b = (src, rbuf) if phase == 0 else (rbuf, dst)
+                    to, frm = (nxt, prv) if phase == 0 else (prv, nxt)
+                    ops = [dist.P2POp(dist.isend, a[s], to), dist.P2POp(dist.irecv, b[s], frm)]
+                    for r in dist.batch_isend_irecv(ops):
+                        r.wait()
+            torch.cuda.synchronize()
+            if it:
+                tm.stop()
+        ms = ctx.allmax(tm.ms)
+        out["nccl_sendrecv_ring"] = {
+            "kind": "library baseline: NCCL send/recv of each request's pages as one tensor to "
+                    "the ring peer and back",
+            "aggregate_GBps": round(ctx.world * 2 * size_bytes / ms / 1e6, 1),
+            "per_gpu_GBps": round(2 * size_bytes / ms / 1e6, 1)}
+    return out
 
 
 # --------------------------------------------------------------------------- config 3
-def fanin(a):
-    dist, rank, world, local, dev = dist_setup()
+def fanin(ctx: Ctx, pages: int = 64, iters: int = 2):
     layout = get_layout("llama-3-8b")           # 256 KiB pages
-    pages, layers, elems = a.pages, layout.layers, layout.page_elems
+    layers, elems = layout.layers, layout.page_elems
     nblk = pages * 2 * layers                    # K and V pages of every layer
     per_client = nblk * layout.page_bytes
-    port = base_port()
+    port = ctx.base_port + 50
     server = None
-    if rank == 0:
-        server = start_shard_server(local, port, (world - 1) * per_client * (a.iters + 2) + (256 << 20),
+    if ctx.rank == 0:
+        server = start_shard_server(ctx.local, port,
+                                    (ctx.world - 1) * per_client * (iters + 2) + (256 << 20),
                                     granule_kb=64)
-    dist.barrier()
-    tw = tr = 0.0
+    ctx.barrier()
+    tw, tr = DevTimer(), DevTimer()
     ok = True
-    if rank > 0:
-        conn = ist.InfinityConnection(ist.ClientConfig(
-            host_addr="127.0.0.1", service_port=port, connection_type=ist.TYPE_RDMA,
-            device=local, device_lookup=True))
-        conn.connect()
-        src = torch.randn(nblk * elems, device=dev).to(torch.bfloat16)
+    conn = None
+    if ctx.rank > 0:
+        conn = _client(ctx, port)
+        src = torch.randn(nblk * elems, device=ctx.dev).to(torch.bfloat16)
         dst = torch.zeros_like(src)
         conn.register_mr(src)
         conn.register_mr(dst)
         per_layer = pages * 2
         offs = np.arange(nblk, dtype=np.int64) * elems
-    for it in range(a.iters + 1):
-        if rank > 0:
-            keys = [f"r{rank}/{it}/{i}/{uuid.uuid4().hex[:8]}" for i in range(nblk)]
+    for it in range(iters + 1):
+        if ctx.rank > 0:
+            tag = uuid.uuid4().hex[:12]
+            keys = [f"r{ctx.rank}/{tag}/{i}" for i in range(nblk)]
             remote = conn.allocate_rdma(keys, layout.page_bytes)
             blocks = list(zip(keys, offs.tolist()))
         torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
-        if rank > 0:
+        ctx.barrier()
+        if it:
+            tw.start()
+        if ctx.rank > 0:
             for l in range(layers):
                 s = slice(l * per_layer, (l + 1) * per_layer)
                 conn.rdma_write_cache(src, offs[s], elems, remote[s])
             conn.sync()
-        t1 = time.perf_counter()
-        dist.barrier()
-        t2 = time.perf_counter()
-        if rank > 0:
+        if it:
+            tw.stop()
+        ctx.barrier()
+        if it:
+            tr.start()
+        if ctx.rank > 0:
             for l in range(layers):
                 s = slice(l * per_layer, (l + 1) * per_layer)
                 conn.read_cache(dst, blocks[s], elems)
             conn.sync()
-        t3 = time.perf_counter()
-        dist.barrier()
         if it:
-            tw += t1 - t0
-            tr += t3 - t2
-    if rank > 0:
+            tr.stop()
+        ctx.barrier()
+    if ctx.rank > 0:
         ok = bool(torch.equal(src, dst))
         conn.close()
-    tw, tr = allmax(dist, dev, tw), allmax(dist, dev, tr)
-    okall = allmax(dist, dev, 0.0 if ok else 1.0) == 0.0
-    total = (world - 1) * per_client * a.iters
-    if rank == 0:
-        print(json.dumps({"config": "fanin (BASELINE config 3)", "clients": world - 1, "model": "llama-3-8b",
-                          "page_kib": layout.page_bytes >> 10, "bytes_per_client_per_iter": per_client,
-                          "write_GBps_aggregate": round(total / tw / 1e9, 1),
-                          "read_GBps_aggregate": round(total / tr / 1e9, 1),
-                          "roofline_GBps": {"pool_ingress_write": 711, "pool_egress_read": 779},
-                          "verified": okall}))
+    w, r = ctx.allmax(tw.ms), ctx.allmax(tr.ms)
+    okall = ctx.allsum(0.0 if ok else 1.0) == 0.0
+    ctx.barrier()
+    if server is not None:
         server.stop()
-    dist.destroy_process_group()
-
-
-# --------------------------------------------------------------------------- config 4
-def bcast(a):
-    ndev = torch.cuda.device_count()
-    out = {"config": "bcast (BASELINE config 4)", "gpus": ndev}
-    if ndev < 2 or not nvls_available():
-        out["unavailable"] = "needs >= 2 GPUs with NVLS multicast"
-        print(json.dumps(out))
-        return
-    bs, nblk = 1 << 20, a.blocks
-    bc = PrefixBroadcaster(list(range(ndev)), nblk * bs)
-    src = torch.randint(0, 255, (nblk * bs,), dtype=torch.uint8, device="cuda:0")
-    offs = [i * bs for i in range(nblk)]
-    for ctas in (0, 148, 296):
-        for _ in range(2):
-            bc.broadcast(src, offs, offs, bs, max_ctas=ctas)
-        torch.cuda.synchronize(0)
-        ts = []
-        for _ in range(5):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with torch.cuda.device(0):
-                e0.record()
-                bc.broadcast(src, offs, offs, bs, max_ctas=ctas)
-                e1.record()
-            e1.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ms = sorted(ts)[len(ts) // 2]
-        out[f"ctas={ctas or 'auto'}"] = {
-            "ms": round(ms, 3), "writer_egress_GBps": round(nblk * bs / ms / 1e6, 1),
-            "delivered_GBps": round((ndev - 1) * nblk * bs / ms / 1e6, 1)}
-    for d in range(ndev):
-        torch.cuda.synchronize(d)
-    out["verified"] = all(bool(torch.equal(bc.replica(d)[:nblk * bs].cpu(), src.cpu()))
-                          for d in range(ndev))
-    # unicast comparison: the same blocks pushed to each peer one after the other
-    from infinistore_b200 import ops
-
-    peers = []
-    for d in range(1, ndev):
-        native.enable_peer_access(0, d)
-        peers.append(torch.empty(nblk * bs, dtype=torch.uint8, device=f"cuda:{d}"))
-    descs = [ops.make_descs([src.data_ptr() + o for o in offs], [p.data_ptr() + o for o in offs], "cuda:0")
-             for p in peers]
-    with torch.cuda.device(0):
-        for _ in range(2):
-            for d in descs:
-                ops.kv_copy(d, bs)
-        torch.cuda.synchronize(0)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for d in descs:
-            ops.kv_copy(d, bs)
-        e1.record()
-        e1.synchronize()
-    ms = e0.elapsed_time(e1)
-    out["unicast_to_each_peer"] = {"ms": round(ms, 3),
-                                   "delivered_GBps": round((ndev - 1) * nblk * bs / ms / 1e6, 1)}
-    # get_match_last_index on the device: keys published in a local index table
-    table = ops.new_index_table(1 << 18, "cuda:0")
-    nkeys = a.keys
-    keys = [b"prefix-%08d" % i for i in range(nkeys)]
-    pool = torch.zeros(64, dtype=torch.uint8, device="cuda:0")
-    pub = ops.PublishArgs(table, keys[: nkeys // 2], [(1 << 44)] * (nkeys // 2),
-                          list(range(1, nkeys // 2 + 1)), 64)
-    d = ops.make_descs([pool.data_ptr()] * (nkeys // 2), [pool.data_ptr()] * (nkeys // 2), "cuda:0")
-    ops.kv_copy(d, 64, publish=pub)
-    torch.cuda.synchronize(0)
-    t0 = time.perf_counter()
-    reps = 20
-    for _ in range(reps):
-        _, _, match = ops.index_lookup(table, keys, want_match=True)
-    dt = (time.perf_counter() - t0) / reps
-    out["match_last_index"] = {"keys": nkeys, "result": match, "expected": nkeys // 2 - 1,
-                               "ms_per_call_incl_pack_and_sync": round(dt * 1e3, 3)}
-    print(json.dumps(out))
-    os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open("gpurun_out/config4_bcast.json", "w"), indent=1)
+    total = (ctx.world - 1) * per_client * iters
+    return {"what": f"{ctx.world - 1} client GPUs -> 1 pool GPU, Llama-3-8B KV pages",
+            "page_kib": layout.page_bytes >> 10, "bytes_per_client_per_iter": per_client,
+            "write_GBps_aggregate": round(total / w / 1e6, 1),
+            "read_GBps_aggregate": round(total / r / 1e6, 1),
+            "roofline": "pool GPU ingress / egress: 900 GB/s nominal, ~770 copy engine",
+            "fraction_of_900": [round(total / w / 1e6 / 900, 3), round(total / r / 1e6 / 900, 3)],
+            "verified": okall, "timing": "CUDA events around issue+sync, max over ranks"}
 
 
 # --------------------------------------------------------------------------- config 5
-def fp8(a):
-    dist, rank, world, local, dev = dist_setup()
+def fp8_ring(ctx: Ctx, size_mb: int = 2048, iters: int = 2):
     elems = 65536                                  # 128 KB bf16 page -> 64 KB e4m3 (+ scales)
-    nblk = (a.size_mb << 20) // (elems * 2)
-    port = base_port()
-    server = start_shard_server(local, port + rank, (a.iters + 2) * nblk * 80 * 1024 + (256 << 20),
-                                granule_kb=16)
-    dist.barrier()
-    conn = ist.InfinityConnection(ist.ClientConfig(
-        host_addr="127.0.0.1", service_port=port + (rank + 1) % world,
-        connection_type=ist.TYPE_RDMA, device=local, device_lookup=True))
-    conn.connect()
-    src = (torch.randn(nblk * elems, device=dev) * 2).to(torch.bfloat16)
+    nblk = (size_mb << 20) // (elems * 2)
+    port = ctx.base_port + 60
+    server = start_shard_server(ctx.local, port + ctx.rank,
+                                (iters + 2) * nblk * 80 * 1024 + (256 << 20), granule_kb=16)
+    ctx.barrier()
+    conn = _client(ctx, port + (ctx.rank + 1) % ctx.world)
+    src = (torch.randn(nblk * elems, device=ctx.dev) * 2).to(torch.bfloat16)
     dst = torch.zeros_like(src)
     conn.register_mr(src)
     conn.register_mr(dst)
@@ -219,56 +277,210 @@ def fp8(a):
     per = nblk // layers
     offs = np.arange(nblk, dtype=np.int64) * elems
     nbytes = conn.fp8_page_bytes(elems)
-    tw = tr = 0.0
-    for it in range(a.iters + 1):
-        keys = [uuid.uuid4().hex for _ in range(nblk)]
+    tw, tr = DevTimer(), DevTimer()
+    for it in range(iters + 1):
+        tag = uuid.uuid4().hex[:12]
+        keys = [f"{tag}-{i}" for i in range(nblk)]
         remote = conn.allocate_rdma(keys, nbytes)
         blocks = list(zip(keys, offs.tolist()))
         torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
+        ctx.barrier()
+        if it:
+            tw.start()
         for l in range(layers):
             s = slice(l * per, (l + 1) * per)
             conn.rdma_write_cache_fp8(src, offs[s], elems, remote[s])
         conn.sync()
-        t1 = time.perf_counter()
+        if it:
+            tw.stop()
+            tr.start()
         for l in range(layers):
             s = slice(l * per, (l + 1) * per)
             conn.read_cache_fp8(dst, blocks[s], elems)
         conn.sync()
-        t2 = time.perf_counter()
-        dist.barrier()
         if it:
-            tw += t1 - t0
-            tr += t2 - t1
+            tr.stop()
+        ctx.barrier()
     err = (dst.float() - src.float()).abs().max().item() / src.float().abs().max().item()
-    tw, tr = allmax(dist, dev, tw), allmax(dist, dev, tr)
-    err = allmax(dist, dev, err)
+    w, r, err = ctx.allmax(tw.ms), ctx.allmax(tr.ms), ctx.allmax(err)
     conn.close()
-    dist.barrier()
+    ctx.barrier()
     server.stop()
-    if rank == 0:
-        fp8_bytes = world * nblk * nbytes * a.iters
-        bf16_bytes = world * nblk * elems * 2 * a.iters
-        print(json.dumps({"config": "fp8 ring (BASELINE config 5)", "gpus": world, "fp8_block_kb": nbytes / 1024,
-                          "write_GBps_fp8_bytes": round(fp8_bytes / tw / 1e9, 1),
-                          "read_GBps_fp8_bytes": round(fp8_bytes / tr / 1e9, 1),
-                          "write_GBps_bf16_equiv": round(bf16_bytes / tw / 1e9, 1),
-                          "read_GBps_bf16_equiv": round(bf16_bytes / tr / 1e9, 1),
-                          "max_rel_err_vs_bf16": round(err, 4)}))
-    dist.destroy_process_group()
+    fp8_bytes = ctx.world * nblk * nbytes * iters
+    bf16_bytes = ctx.world * nblk * elems * 2 * iters
+    return {"what": "fp8 KV path, ring over N GPUs: cast fused into the write, dequantising "
+                    "gather fused into the read", "fp8_block_kb": nbytes / 1024,
+            "write_GBps_fp8_bytes": round(fp8_bytes / w / 1e6, 1),
+            "read_GBps_fp8_bytes": round(fp8_bytes / r / 1e6, 1),
+            "write_GBps_bf16_equiv": round(bf16_bytes / w / 1e6, 1),
+            "read_GBps_bf16_equiv": round(bf16_bytes / r / 1e6, 1),
+            "fraction_of_900_on_fp8_bytes": [round(fp8_bytes / w / 1e6 / ctx.world / 900, 3),
+                                             round(fp8_bytes / r / 1e6 / ctx.world / 900, 3)],
+            "max_rel_err_vs_bf16": round(err, 4),
+            "timing": "CUDA events around issue+sync, max over ranks"}
+
+
+# --------------------------------------------------------------------------- config 4
+def nvls_bcast(ctx: Ctx, blocks_n: int = 512, iters: int = 3, match_keys: int = 4096):
+    """1 writer -> N replicas through the STORE API: rank 0 hosts a server with an
+    NVLS-replicated region on every GPU; rank 0's client allocates replicated blocks and
+    writes them once (multimem.st through the multicast mapping, in-band commit); every
+    rank's client - separate processes, handles over the fd side channel - then reads its
+    LOCAL replica.  Also: get_match_last_index on the device index vs the server 'M' op."""
+    bs = 1 << 20
+    out = {"what": "prefix broadcast 1 writer -> all GPUs, NVLS multicast, 1 MB blocks, store API"}
+    if not nvls_available(ctx.local):
+        out["unavailable"] = "NVLS multicast not supported on this box"
+        return out
+    port = ctx.base_port + 70
+    server = None
+    if ctx.rank == 0:
+        cfg = native.ServerConfig()
+        cfg.service_port = port
+        cfg.host = "127.0.0.1"
+        cfg.pool_backend = "hbm"
+        cfg.pool_devices = [ctx.local]
+        cfg.prealloc_bytes = 512 << 20
+        cfg.minimal_allocate_size = 64
+        cfg.replica_bytes = (iters + 2) * blocks_n * bs + (64 << 20)
+        cfg.replica_devices = list(range(ctx.world))
+        cfg.log_level = "warning"
+        server = native.Server(cfg)
+        server.start()
+    ctx.barrier()
+    conn = _client(ctx, port)
+    elems = bs // 2
+    src = torch.randn(blocks_n * elems, device=ctx.dev).to(torch.bfloat16) if ctx.rank == 0 else None
+    dst = torch.zeros(blocks_n * elems, device=ctx.dev, dtype=torch.bfloat16)
+    conn.register_mr(dst)
+    offs = np.arange(blocks_n, dtype=np.int64) * elems
+    tw, tr = DevTimer(), DevTimer()
+    ok = True
+    for it in range(iters + 1):
+        tag = [uuid.uuid4().hex[:12]]
+        if ctx.dist is not None:
+            ctx.dist.broadcast_object_list(tag, src=0)
+        keys = [f"{tag[0]}-{i}" for i in range(blocks_n)]
+        blocks = list(zip(keys, offs.tolist()))
+        torch.cuda.synchronize()
+        ctx.barrier()
+        if ctx.rank == 0:
+            remote = conn.allocate_rdma(keys, bs, replicated=True)
+            if it:
+                tw.start()
+            conn.rdma_write_cache(src, offs, elems, remote)
+            conn.sync()
+            if it:
+                tw.stop()
+        ctx.barrier()
+        if it:
+            tr.start()
+        conn.read_cache(dst, blocks, elems)
+        conn.sync()
+        if it:
+            tr.stop()
+        ctx.barrier()
+    # verify: every rank's dst equals rank 0's pages
+    chk = dst.float().sum().item()
+    ref = [src.float().sum().item() if ctx.rank == 0 else 0.0]
+    if ctx.dist is not None:
+        ctx.dist.broadcast_object_list(ref, src=0)
+    ok = abs(chk - ref[0]) <= 1e-3 * max(1.0, abs(ref[0]))
+    w = ctx.allmax(tw.ms)          # only rank 0 wrote
+    r = ctx.allmax(tr.ms)
+    total = blocks_n * bs * iters
+    out.update({
+        "writer_egress_GBps": round(total / w / 1e6, 1),
+        "delivered_GBps": round((ctx.world - 1) * total / w / 1e6, 1),
+        "fraction_of_900_egress": round(total / w / 1e6 / 900, 3),
+        "readers_local_replica_GBps_aggregate": round(ctx.world * total / r / 1e6, 1),
+        "verified": ctx.allsum(0.0 if ok else 1.0) == 0.0})
+    # get_match_last_index: device kernel vs server op, same keys (half present)
+    if ctx.rank == 0:
+        present = [f"{tag[0]}-{i}" for i in range(min(blocks_n, match_keys // 2))]
+        probe = present + [f"absent-{i}" for i in range(match_keys - len(present))]
+        host_conn = ist.InfinityConnection(ist.ClientConfig(
+            host_addr="127.0.0.1", service_port=port, connection_type=ist.TYPE_RDMA,
+            device=ctx.local, device_lookup=False, log_level="warning"))
+        host_conn.connect()
+        res = {}
+        for name, c in (("device_kernel", conn), ("server_op", host_conn)):
+            ts = []
+            for _ in range(30):
+                t0 = time.perf_counter()
+                m = c.get_match_last_index(probe)
+                ts.append((time.perf_counter() - t0) * 1e6)
+            ts.sort()
+            res[name] = {"result": m, "p50_us": round(ts[len(ts) // 2], 1), "p99_us": round(ts[-1], 1)}
+        res["keys"] = len(probe)
+        res["expected"] = len(present) - 1
+        out["get_match_last_index"] = res
+        host_conn.close()
+    conn.close()
+    ctx.barrier()
+    if server is not None:
+        server.stop()
+    return out
+
+
+# --------------------------------------------------------------------------- CLI
+def _standalone_ctx():
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    def red(x, op):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    return Ctx(dist, rank, world, local, dev,
+               25000 + int(os.environ.get("MASTER_PORT", "0")) % 2000, barrier,
+               lambda x: red(x, dist.ReduceOp.MAX), lambda x: red(x, dist.ReduceOp.SUM),
+               lambda x: red(x, dist.ReduceOp.MIN))
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("config", choices=["fanin", "bcast", "fp8"])
-    ap.add_argument("--iters", type=int, default=3)
-    ap.add_argument("--pages", type=int, default=8, help="fanin: 128-token pages per client")
-    ap.add_argument("--blocks", type=int, default=256, help="bcast: 1 MB blocks")
-    ap.add_argument("--keys", type=int, default=4096, help="bcast: keys for match_last_index")
-    ap.add_argument("--size-mb", type=int, default=1024, help="fp8: bf16 MB per GPU per iteration")
+    ap.add_argument("config", choices=["fanin", "bcast", "fp8", "latency", "baselines"])
     a = ap.parse_args()
-    {"fanin": fanin, "bcast": bcast, "fp8": fp8}[a.config](a)
+    ctx = _standalone_ctx()
+    if a.config == "fanin":
+        res = fanin(ctx)
+    elif a.config == "fp8":
+        res = fp8_ring(ctx)
+    elif a.config == "bcast":
+        res = nvls_bcast(ctx)
+    elif a.config == "baselines":
+        res = baselines(ctx, 128 << 10)
+    else:
+        srv = start_shard_server(ctx.local, ctx.base_port + ctx.rank, 1 << 30, granule_kb=16)
+        ctx.barrier()
+        conn = _client(ctx, ctx.base_port + (ctx.rank + 1) % ctx.world)
+        res = latency(ctx, conn)
+        conn.close()
+        ctx.barrier()
+        srv.stop()
+    if ctx.rank == 0:
+        print(json.dumps({a.config: res}))
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open(f"gpurun_out/config_{a.config}_n{ctx.world}.json", "w") as f:
+            json.dump(res, f, indent=1)
+    if ctx.dist is not None:
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

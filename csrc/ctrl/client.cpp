@@ -1352,7 +1352,7 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
         // once with the lookup kernel and feed the descriptors to kv_copy.
         const bool whole_blocks =
             n >= size_t(kernels::sm_count()) && uint32_t(block_size) <= (1u << 20);
-        if (!fp8_elems && copy_variant_ != kernels::kCopyTma && whole_blocks) {
+        if (!fp8_elems && whole_blocks) {
             // one kernel: hash + probe + move
             kernels::ReadFusedLaunch R;
             R.key_bytes = ctx->ring_d + at_bytes;
@@ -1370,6 +1370,7 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             R.status = ctx->status_d;
             R.max_ctas = grid_cap;
             R.validate = server_evicts_;
+            R.variant = copy_variant_;
             e = kernels::launch_kv_read_fused(R, stream);
             stats_.kernel_launches += 1;
         } else {
@@ -1433,6 +1434,131 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
         if (res) res->launched = true;
         stats_.bytes_read += uint64_t(n) * uint64_t(block_size);
     }
+    return 0;
+}
+
+// The same pages into several destination tensors (TP ranks / beams sharing a prefix): every
+// pool block crosses NVLink once and is fanned out inside a thread-block cluster
+// (kernels/kv_pipe.cu: cp.async.bulk ... .multicast::cluster).  bases[r] is the base pointer
+// of destination r; every destination uses the same page offsets.
+int Connection::r_rdma_multi(const std::vector<KeyOffset>& blocks, int block_size,
+                             const std::vector<uint64_t>& bases, int device, uint64_t stream_in) {
+    if (blocks.empty() || bases.empty()) return 0;
+    if (device < 0 || !server_hbm_) {
+        fail("read_cache_multi needs CUDA destinations and an HBM pool");
+        return -1;
+    }
+    if (bases.size() == 1) return r_rdma(blocks, block_size, bases[0], device, stream_in);
+    const bool via_index = device_lookup_ && device_index_usable();
+    std::vector<RemoteBlock> rb;
+    if (!via_index) {
+        const int r = lookup_blocks(kOpReadLookup, blocks, block_size, rb);
+        if (r != 0) return r;
+    }
+    NvtxRange nvtx("istore.read_multi");
+    std::lock_guard<std::mutex> lk(mu_);
+    DevCtx* ctx = dev_ctx(device);
+    if (!ctx) return -1;
+    DeviceGuard g(device);
+    cudaStream_t stream = ctx->pick(reinterpret_cast<cudaStream_t>(stream_in), false, streams_);
+    stats_.calls++;
+    uint64_t align_or = 0;
+    for (uint64_t b : bases) align_or |= b;
+    for (size_t base = 0; base < blocks.size(); base += kMaxBatch) {
+        const size_t n = std::min(kMaxBatch, blocks.size() - base);
+        const kernels::CopyDesc* descs_d = nullptr;
+        for (size_t i = 0; i < n; ++i) align_or |= blocks[base + i].offset;
+        cudaError_t e = cudaSuccess;
+        if (via_index) {
+            auto m0 = mapping(0, device);
+            if (!m0 || !m0->dev_ptr) return -1;
+            size_t key_bytes = 0;
+            std::vector<std::string_view> kp(n);
+            for (size_t i = 0; i < n; ++i) {
+                kp[i] = blocks[base + i].key;
+                key_bytes += align_up(std::max<size_t>(kp[i].size(), 1), 8);
+            }
+            const size_t at_bytes = ctx->ring_alloc(key_bytes);
+            const size_t at_off = ctx->ring_alloc(n * 4);
+            const size_t at_len = ctx->ring_alloc(n * 4);
+            const size_t at_dst = ctx->ring_alloc(n * 8);
+            pack_keys(kp.data(), n, ctx->ring_h + at_bytes,
+                      reinterpret_cast<uint32_t*>(ctx->ring_h + at_off),
+                      reinterpret_cast<uint32_t*>(ctx->ring_h + at_len));
+            auto* dst = reinterpret_cast<uint64_t*>(ctx->ring_h + at_dst);
+            for (size_t i = 0; i < n; ++i) dst[i] = blocks[base + i].offset;
+            kernels::LookupLaunch Q;
+            Q.key_bytes = ctx->ring_d + at_bytes;
+            Q.key_off = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_off);
+            Q.key_len = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_len);
+            Q.n = uint32_t(n);
+            Q.table = reinterpret_cast<const kernels::IndexBucket*>(m0->dev_ptr + segs_[0].index_off);
+            Q.table_mask = kernels::index_bucket_mask(segs_[0].index_slots);
+            Q.nsegs = uint32_t(std::min<size_t>(segs_.size(), kernels::LookupLaunch::kMaxSegs));
+            for (uint32_t sgi = 0; sgi < Q.nsegs; ++sgi)
+                Q.seg_base[sgi] = reinterpret_cast<uint64_t>(seg_dev_ptr(ctx, sgi));
+            auto* out = reinterpret_cast<kernels::CopyDesc*>(
+                ctx->scratch + ctx->scratch_alloc(n * sizeof(kernels::CopyDesc)));
+            Q.out_descs = out;
+            Q.dst_off = reinterpret_cast<const uint64_t*>(ctx->ring_d + at_dst);
+            Q.dst_base = bases[0];
+            Q.need_bytes = uint32_t(block_size);
+            Q.status = ctx->status_d;
+            e = kernels::launch_index_lookup(Q, stream);
+            stats_.kernel_launches++;
+            descs_d = out;
+        } else {
+            const size_t at_desc = ctx->ring_alloc(n * sizeof(kernels::CopyDesc));
+            auto* descs = reinterpret_cast<kernels::CopyDesc*>(ctx->ring_h + at_desc);
+            for (size_t i = 0; i < n; ++i) {
+                const RemoteBlock& b = rb[base + i];
+                uint8_t* segbase = seg_dev_ptr(ctx, addr_seg(b.remote_addr));
+                if (!segbase) return -1;
+                descs[i].src = reinterpret_cast<uint64_t>(segbase) + addr_off(b.remote_addr);
+                descs[i].dst = bases[0] + blocks[base + i].offset;
+            }
+            descs_d = reinterpret_cast<const kernels::CopyDesc*>(ctx->ring_d + at_desc);
+        }
+        // clusters of 4, then 2, then a plain copy for an odd destination
+        size_t r = 0;
+        while (e == cudaSuccess && r < bases.size()) {
+            const size_t left = bases.size() - r;
+            if (left >= 2) {
+                kernels::McastLaunch M;
+                M.descs = descs_d;
+                M.n = uint32_t(n);
+                M.bytes = uint32_t(block_size);
+                M.align_or = align_or;
+                M.ndst = left >= 4 ? 4 : 2;
+                for (int j = 0; j < M.ndst; ++j) M.delta[j] = int64_t(bases[r + j]) - int64_t(bases[0]);
+                M.status = r == 0 ? ctx->status_d : nullptr;
+                e = kernels::launch_kv_pipe_mcast(M, stream);
+                r += size_t(M.ndst);
+            } else {
+                // single leftover destination: shift the descriptors with delta through the
+                // cluster kernel's smallest form is not possible; use a 2-cluster onto the
+                // previous destination as well (idempotent rewrite of identical bytes)
+                kernels::McastLaunch M;
+                M.descs = descs_d;
+                M.n = uint32_t(n);
+                M.bytes = uint32_t(block_size);
+                M.align_or = align_or;
+                M.ndst = 2;
+                M.delta[0] = int64_t(bases[r - 1]) - int64_t(bases[0]);
+                M.delta[1] = int64_t(bases[r]) - int64_t(bases[0]);
+                e = kernels::launch_kv_pipe_mcast(M, stream);
+                r += 1;
+            }
+            stats_.kernel_launches++;
+        }
+        if (e != cudaSuccess) {
+            fail(std::string("multi-destination read failed to launch: ") + cudaGetErrorString(e));
+            return -1;
+        }
+        ctx->mark(stream);
+        stats_.bytes_read += uint64_t(n) * uint64_t(block_size) * bases.size();
+    }
+    if (!via_index) ctrl_dirty_ = true;
     return 0;
 }
 

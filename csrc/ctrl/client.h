@@ -131,6 +131,10 @@ class Connection {
                uint64_t stream, MoveResult* res = nullptr);
     int rw_local(char op, const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr,
                  int device, uint64_t stream);
+    // read the same pages into several destination tensors of one device: each pool block
+    // crosses the fabric once and is fanned out by a thread-block cluster (TMA multicast)
+    int r_rdma_multi(const std::vector<KeyOffset>& blocks, int block_size,
+                     const std::vector<uint64_t>& bases, int device, uint64_t stream);
     // fp8 KV path: pages are bf16 in the caller's tensor (`elems` elements each) and
     // e4m3 + per-128 fp32 scales in the pool (kernels::fp8_block_bytes(elems) bytes, which is
     // the size to allocate).  The cast is fused into the page mover.

@@ -67,7 +67,7 @@ enum Status : int {
 enum CopyVariant : int {
     kCopyAuto = 0,
     kCopyLdSt = 1,  // 128-bit ld/st, all threads: LDG.128 / STG.128 on (peer) global memory
-    kCopyTma = 2,   // 1-D bulk async copies through an SMEM ring: UBLKCP.S.G / UBLKCP.G.S
+    kCopyTma = 2,   // warp-specialised TMA pipeline (kv_pipe.cu): UBLKCP.S.G / UBLKCP.G.S + mbarriers
     kCopyLdSt256 = 3,  // 256-bit ld/st (LDG.E.ENL2.256 / STG.E.ENL2.256)
 };
 
@@ -90,8 +90,22 @@ struct CopyLaunch {
     bool all_local = false;  // every destination and the index table are in this GPU's own HBM
     uint32_t debug = 0;      // bench only, see publish.cuh
     bool multicast = false;  // every dst is an NVLS multicast address: store with multimem.st
+    // TMA pipeline geometry (0 = default: 16 KB slots, 128 KB ring per CTA)
+    uint32_t stage_bytes = 0;
+    uint32_t ring_bytes = 0;
 };
+// Picks the data path (CopyVariant) and launches it.  kCopyAuto: the TMA pipeline for every
+// 16-byte aligned transfer of blocks >= kPipeMinBytes, 256-bit ld/st below that.
 cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream);
+constexpr uint32_t kPipeMinBytes = 8u << 10;
+// The TMA pipeline itself (kv_pipe.cu); needs 16-byte aligned addresses and sizes.
+cudaError_t launch_kv_pipe_copy(const CopyLaunch& a, cudaStream_t stream);
+struct PipeGeometry {
+    uint32_t stage_bytes = 0;
+    uint32_t stages = 0;
+    size_t smem = 0;
+};
+PipeGeometry pipe_geometry(uint32_t bytes, uint32_t stage_pref, uint32_t ring_pref);
 
 // fp8 (e4m3) fused variants: the write converts bf16 pages to e4m3 with one fp32 scale
 // per `group` elements (the head_dim row) and stores payload + scales into the pool block;
@@ -193,8 +207,33 @@ struct ReadFusedLaunch {
     uint32_t* status = nullptr;          // status[kStatMiss] counts keys that were not found
     int max_ctas = 0;
     bool validate = false;               // re-check every entry's tag after its copy (eviction)
+    int variant = kCopyAuto;             // kCopyTma: resolver warp feeding the TMA pipeline
+    uint32_t stage_bytes = 0;            // TMA pipeline geometry, 0 = default
+    uint32_t ring_bytes = 0;
 };
+// kCopyAuto / kCopyTma run the TMA pipeline (kv_pipe.cu) when the transfer is 16-byte
+// aligned and needs no post-copy validation; the ld/st kernel otherwise.
 cudaError_t launch_kv_read_fused(const ReadFusedLaunch& a, cudaStream_t stream);
+bool pipe_read_supported(const ReadFusedLaunch& a);
+cudaError_t launch_kv_pipe_read(const ReadFusedLaunch& a, cudaStream_t stream);
+
+// One pool block -> 2 or 4 destinations with a thread-block cluster: the leader CTA fetches
+// the tile once (cp.async.bulk ... .multicast::cluster lands it in every CTA's shared
+// memory), each CTA stores it to its own destination.  Destination r of block i is
+// descs[i].dst + delta[r] (the same page offset in every destination tensor).
+struct McastLaunch {
+    const CopyDesc* descs = nullptr;  // device memory (e.g. written by launch_index_lookup)
+    uint32_t n = 0;
+    uint32_t bytes = 0;
+    uint64_t align_or = 0;  // OR of every destination base and offset
+    int ndst = 2;           // 2 or 4 = cluster size
+    int64_t delta[4] = {0, 0, 0, 0};
+    uint32_t* status = nullptr;
+    int max_clusters = 0;
+    uint32_t stage_bytes = 0;
+    uint32_t ring_bytes = 0;
+};
+cudaError_t launch_kv_pipe_mcast(const McastLaunch& a, cudaStream_t stream);
 
 // One writer -> all readers replication through an NVLS multicast mapping (multimem.st).
 struct BcastLaunch {

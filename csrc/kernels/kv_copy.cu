@@ -12,12 +12,12 @@
 //     255-271): the kernel publishes each block in the HBM-resident index itself, with
 //     release semantics at system scope, once the block's bytes have landed.
 //
-// Two data paths, selected per launch (measured, not guessed — see profiles/):
-//   kCopyLdSt : every thread streams 128-bit (or 256-bit) vectors, 4 in flight per thread;
-//   kCopyTma  : one elected thread per CTA drives an SMEM ring with 1-D bulk async copies
-//               (cp.async.bulk, mbarrier completion in, bulk-group completion out).  A few
-//               CTAs of one warp each keep megabytes in flight, leaving the SMs to the
-//               model's own kernels when the transfer overlaps prefill.
+// Data paths, selected per launch (measured, not guessed — see profiles/):
+//   kCopyTma  : the default - the warp-specialised TMA pipeline of kv_pipe.cu (loader /
+//               storer / control warps around an mbarrier-guarded SMEM ring);
+//   kCopyLdSt / kCopyLdSt256 : this file - every thread streams 128-bit (or 256-bit)
+//               vectors, 4 in flight per thread; used for small or unaligned blocks and for
+//               NVLS multicast stores (multimem.st has no bulk form).
 #include <algorithm>
 #include <cstring>
 #include <mutex>
@@ -34,9 +34,6 @@ namespace {
 using namespace dev;
 
 constexpr uint32_t kLdStChunk = 32u << 10;  // work item of the ld/st path
-constexpr int kTmaMaxStages = 32;
-constexpr uint32_t kTmaChunk = 16u << 10;   // largest bulk copy / ring slot
-constexpr uint32_t kTmaRingBytes = 128u << 10;
 
 // ---------------------------------------------------------------- ld/st path (copy_span.cuh)
 // Descriptors of small batches travel in the kernel parameters (constant bank): reading
@@ -93,116 +90,6 @@ __global__ void __launch_bounds__(kLdStThreads + 32)
     if (pub.recs) ctrl_barrier_arrive(kLdStThreads + 32);
 }
 
-// ---------------------------------------------------------------- bulk-async (TMA) path
-// Two warps per CTA.  Warp 0: lane 0 drives an SMEM ring with 1-D bulk async copies; all lanes
-// prefetch descriptors (32 at a time, one coalesced read even when they live in mapped host
-// memory).  Warp 1 is the control warp (in-band commit).
-//
-// Ring: `stages` slots of `stage_bytes` (chosen per launch: 16 KB slots for big blocks, one
-// slot per block for small ones, up to 32 slots / 128 KB).  Global->shared copies complete on
-// the slot's mbarrier (complete_tx); shared->global copies are tracked as bulk groups, and a
-// slot is refilled once the store that used it has finished READING shared memory
-// (wait_group.read), with kPendingStores groups allowed to lag so that the issuing thread
-// never waits for the store it has just issued.
-constexpr int kPendingStores = 2;
-
-template <bool PARAM>
-__global__ void __launch_bounds__(64)
-    kv_copy_tma_kernel(const CopyDesc* __restrict__ descs,
-                       const __grid_constant__ DescParam<PARAM ? kParamDescs : 1> pd, uint32_t n,
-                       uint32_t bytes, uint32_t stage_bytes, uint32_t stages, uint32_t cpb,
-                       Publish pub) {
-    extern __shared__ __align__(128) uint8_t ring[];
-    __shared__ __align__(8) uint64_t full[kTmaMaxStages];
-    const uint32_t total = n * cpb;
-    const uint32_t grid = gridDim.x;
-    const uint32_t nitems = blockIdx.x < total ? (total - blockIdx.x + grid - 1) / grid : 0;
-    if (threadIdx.x >= 32) {
-        if (pub.recs) control_warp(pub, threadIdx.x - 32, blockIdx.x, nitems, grid, cpb, 64);
-        return;
-    }
-    const uint32_t lane = threadIdx.x;
-
-    if (lane == 0) {
-        for (uint32_t s = 0; s < stages; ++s) mbar_init(&full[s], 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
-
-    // item k of this CTA -> global item blockIdx.x + k * grid
-    auto fetch = [&](uint32_t k0) -> CopyDesc {  // lane l gets the descriptor of item k0 + l
-        const uint32_t k = k0 + lane;
-        if (k >= nitems) return CopyDesc{0, 0};
-        const uint32_t block = (blockIdx.x + k * grid) / cpb;
-        if constexpr (PARAM)
-            return pd.d[block];
-        else
-            return descs[block];
-    };
-    // The descriptors of items [w, w+32) live in `cur`, of [w+32, w+64) in `nxt`.
-    CopyDesc cur = fetch(0), nxt = fetch(32);
-    uint32_t window = 0;
-    auto desc_of = [&](uint32_t k) -> CopyDesc {  // warp-uniform k in [window, window + 64)
-        const bool in_cur = k < window + 32;
-        const uint32_t l = (k - window) & 31;
-        CopyDesc r;
-        r.src = __shfl_sync(0xffffffffu, in_cur ? cur.src : nxt.src, l);
-        r.dst = __shfl_sync(0xffffffffu, in_cur ? cur.dst : nxt.dst, l);
-        return r;
-    };
-    uint32_t loaded = 0;  // loads issued so far
-    auto pump = [&](uint32_t limit) {  // issue loads up to (excluding) item `limit`
-        while (loaded < nitems && loaded < limit) {
-            const CopyDesc d = desc_of(loaded);
-            const uint32_t s = loaded % stages;
-            const uint32_t off = ((blockIdx.x + loaded * grid) % cpb) * stage_bytes;
-            const uint32_t len = min(stage_bytes, bytes - off);
-            if (lane == 0 && d.src != 0) {
-                mbar_expect_tx(&full[s], len);
-                bulk_g2s(ring + size_t(s) * stage_bytes,
-                         reinterpret_cast<const uint8_t*>(d.src) + off, len, &full[s]);
-            }
-            ++loaded;
-        }
-    };
-    pump(stages);  // prologue: fill the ring (stages <= 32: inside the descriptor window)
-
-    for (uint32_t k = 0; k < nitems; ++k) {
-        if (k >= window + 32) {  // slide the descriptor window
-            window += 32;
-            cur = nxt;
-            nxt = fetch(window + 32);
-        }
-        const CopyDesc d = desc_of(k);
-        const uint32_t s = k % stages;
-        const uint32_t item = blockIdx.x + k * grid;
-        const uint32_t off = (item % cpb) * stage_bytes;
-        const uint32_t len = min(stage_bytes, bytes - off);
-        if (lane == 0) {
-            if (d.src != 0) {
-                mbar_wait(&full[s], (k / stages) & 1);
-                bulk_s2g(reinterpret_cast<uint8_t*>(d.dst) + off, ring + size_t(s) * stage_bytes, len);
-            } else if (off == 0 && pub.status) {
-                atomicAdd(pub.status + kStatMiss, 1u);
-            }
-            bulk_commit();  // one group per item keeps the wait_group arithmetic simple
-            // stores up to item k - kPendingStores have drained their slots
-            bulk_wait_read<kPendingStores>();
-        }
-        // slot of store j is reused by load j + stages; loads < k + 32 stay in the window
-        if (k >= kPendingStores) pump(k - kPendingStores + 1 + stages);
-    }
-    if (lane == 0) {
-        bulk_wait<0>();        // every bulk store of this CTA has completed its writes
-        fence_proxy_async();   // order async-proxy writes before the generic-proxy commit
-    }
-    __syncwarp();
-    if (pub.recs) ctrl_barrier_arrive(64);
-}
-
-std::mutex g_attr_mu;
-bool g_tma_attr_set[64] = {false};
-
 }  // namespace
 
 int sm_count() {
@@ -233,7 +120,12 @@ cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream) {
         if (!aligned16) return cudaErrorInvalidValue;  // multimem.st moves 16-byte vectors
         variant = kCopyLdSt;
     }
-    if (variant == kCopyAuto) variant = aligned32 ? kCopyLdSt256 : kCopyLdSt;
+    // auto: the TMA pipeline wherever it applies (profiles/r2_sweep_*: it matches or beats the
+    // ld/st kernels from 8 KB blocks up, on local HBM and over NVLink, with 3 warps per CTA);
+    // small blocks are bound by per-block issue cost, where 256 threads win
+    if (variant == kCopyAuto)
+        variant = (aligned16 && a.bytes >= kPipeMinBytes) ? kCopyTma
+                                                          : (aligned32 ? kCopyLdSt256 : kCopyLdSt);
     if (!aligned16 && (variant == kCopyTma || variant == kCopyLdSt256)) variant = kCopyLdSt;
     if (variant == kCopyLdSt256 && !aligned32) variant = kCopyLdSt;
 
@@ -243,39 +135,7 @@ cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream) {
     if (param) std::memcpy(pd.d, a.descs_host, size_t(a.n) * sizeof(CopyDesc));
     const DescParam<1> none{};
 
-    if (variant == kCopyTma) {
-        // slot = 16 KB for big blocks, the block itself (rounded up to 16 B) for small ones
-        const uint32_t stage_bytes = std::min(kTmaChunk, (a.bytes + 15u) & ~15u);
-        const uint32_t stages = std::min<uint32_t>(kTmaMaxStages, kTmaRingBytes / stage_bytes);
-        const uint32_t cpb = (a.bytes + stage_bytes - 1) / stage_bytes;
-        const uint64_t total = uint64_t(a.n) * cpb;
-        int ctas = a.max_ctas > 0 ? a.max_ctas : 2 * sms;
-        ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
-        const size_t smem = size_t(stages) * stage_bytes;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        {
-            std::lock_guard<std::mutex> lk(g_attr_mu);
-            if (dev >= 0 && dev < 64 && !g_tma_attr_set[dev]) {
-                cudaError_t e = cudaFuncSetAttribute(kv_copy_tma_kernel<false>,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     int(kTmaRingBytes));
-                if (e == cudaSuccess)
-                    e = cudaFuncSetAttribute(kv_copy_tma_kernel<true>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             int(kTmaRingBytes));
-                if (e != cudaSuccess) return e;
-                g_tma_attr_set[dev] = true;
-            }
-        }
-        if (param)
-            kv_copy_tma_kernel<true><<<ctas, 64, smem, stream>>>(a.descs, pd, a.n, a.bytes, stage_bytes,
-                                                                 stages, cpb, pub);
-        else
-            kv_copy_tma_kernel<false><<<ctas, 64, smem, stream>>>(a.descs, none, a.n, a.bytes,
-                                                                  stage_bytes, stages, cpb, pub);
-        return cudaGetLastError();
-    }
+    if (variant == kCopyTma) return launch_kv_pipe_copy(a, stream);
 
     // Work item = one 32 KB chunk, or - when there are at least as many blocks as SMs - one
     // whole block: then a block is moved by a single CTA, its commit needs no cross-CTA

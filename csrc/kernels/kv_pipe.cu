@@ -1,0 +1,572 @@
+// kv_pipe: the Blackwell-native page movers — warp-specialised TMA pipelines.
+//
+// This is the default data path of write_cache / read_cache: every byte moves
+//     global (local HBM or a peer GPU over NVLink 5) --cp.async.bulk--> SMEM ring
+//     SMEM ring --cp.async.bulk--> global (peer pool or local KV cache)
+// with no register staging and two or three warps per CTA, so a transfer that overlaps
+// prefill leaves the SM's issue slots and register file to the model's kernels.  It
+// replaces, per batch, the reference's N cudaMemcpyAsync calls (src/infinistore.cpp:623-624,
+// 747-748), its RDMA_WRITE work-request chains (src/libinfinistore.cpp:905-970,
+// src/infinistore.cpp:456-530) and the COMMIT / lookup messages around them.
+//
+// Roles (one warp each, lane 0 issues, all lanes prefetch descriptors):
+//   loader   : waits for a free ring slot (empty[s]), arms full[s] with the byte count
+//              (mbarrier expect_tx) and issues the global->shared bulk copy   UBLKCP.S.G
+//   storer   : waits for full[s] (SYNCS...TRYWAIT), issues the shared->global bulk copy
+//              (UBLKCP.G.S) as its own bulk group, and releases slots whose stores have
+//              finished READING shared memory (wait_group.read) kStoreLag groups behind, so
+//              neither thread ever waits for the copy it has just issued
+//   control  : (writes) the in-band commit of publish.cuh: claim early, one system fence once
+//              the storer reports every bulk store complete, tag stores
+//   resolver : (fused reads) hashes the keys of the CTA's items, probes the HBM index over
+//              NVLink and feeds {pool address, destination} to loader and storer through a
+//              double-buffered SMEM queue guarded by mbarriers - read_cache in ONE launch
+//              with no server round trip, now on the bulk-async path as well.
+//
+// kv_pipe_mcast: thread-block CLUSTER variant (2 or 4 CTAs).  One pool block is fetched over
+// NVLink ONCE by the cluster's leader with cp.async.bulk ... .multicast::cluster, which lands
+// the tile in the shared memory of every CTA of the cluster; each CTA then stores it to its
+// own destination (the same KV page wanted by several TP ranks / beams).  Slots are handed
+// back to the leader with remote mbarrier arrivals (DSMEM), the cluster barrier closes the
+// kernel.  NVLink bytes: 1x instead of Kx.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+#include "../core/hash.h"
+#include "common.cuh"
+#include "index.cuh"
+#include "kernels.h"
+#include "publish.cuh"
+
+namespace istore::kernels {
+
+namespace {
+
+using namespace dev;
+
+constexpr int kPipeMaxStages = 32;
+constexpr int kStoreLag = 2;  // bulk-store groups that may still be reading SMEM
+constexpr int kPipeThreads = 96;
+constexpr int kPipeParamDescs = 256;
+
+template <int N>
+struct PipeDescParam {
+    CopyDesc d[N];
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {  // SYNCS.ARRIVE
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Static schedule shared by every role of a CTA: item k of this CTA is global item
+// first + k * stride = chunk (item % cpb) of block (item / cpb); a chunk is moved in pieces
+// of at most stage_bytes through consecutive ring slots.
+struct Shape {
+    uint32_t n, bytes, chunk, cpb, stage_bytes, stages;
+};
+
+// 64 descriptors in registers per warp (two coalesced fetches of 32), handed out by shuffle:
+// descriptors may live in pinned host memory, one PCIe read per 32 items instead of one each.
+template <bool PARAM>
+struct DescWindow {
+    const CopyDesc* descs;
+    const PipeDescParam<PARAM ? kPipeParamDescs : 1>* pd;
+    uint32_t first, stride, cpb, nitems, lane;
+    CopyDesc cur, nxt;
+    uint32_t window = 0;
+    __device__ __forceinline__ CopyDesc fetch(uint32_t k0) const {
+        const uint32_t k = k0 + lane;
+        if (k >= nitems) return CopyDesc{0, 0};
+        const uint32_t block = (first + k * stride) / cpb;
+        if constexpr (PARAM)
+            return pd->d[block];
+        else
+            return descs[block];
+    }
+    __device__ __forceinline__ void init() {
+        cur = fetch(0);
+        nxt = fetch(32);
+    }
+    __device__ __forceinline__ CopyDesc at(uint32_t k) {  // k non-decreasing, warp-uniform
+        if (k >= window + 32) {
+            window += 32;
+            cur = nxt;
+            nxt = fetch(window + 32);
+        }
+        const uint32_t l = (k - window) & 31;
+        CopyDesc r;
+        r.src = __shfl_sync(0xffffffffu, cur.src, l);
+        r.dst = __shfl_sync(0xffffffffu, cur.dst, l);
+        return r;
+    }
+};
+
+// ---------------------------------------------------------------- loader / storer bodies
+// `desc_at(k)` returns the descriptor of the CTA's k-th item (warp-collective call).
+template <typename DescAt>
+__device__ __forceinline__ void loader_body(const Shape& sh, uint32_t first, uint32_t stride,
+                                            uint32_t nitems, uint32_t lane, uint8_t* ring,
+                                            uint64_t* full, uint64_t* empty, DescAt&& desc_at) {
+    uint32_t s = 0, use = 0;  // ring slot and how many times it has been used
+    for (uint32_t k = 0; k < nitems; ++k) {
+        const CopyDesc d = desc_at(k);
+        const uint32_t item = first + k * stride;
+        const uint32_t off0 = (item % sh.cpb) * sh.chunk;
+        const uint32_t len = min(sh.chunk, sh.bytes - off0);
+        for (uint32_t o = 0; o < len; o += sh.stage_bytes) {
+            if (lane == 0) {
+                if (use) mbar_wait(&empty[s], (use - 1) & 1);
+                const uint32_t plen = min(sh.stage_bytes, len - o);
+                if (d.src) {
+                    mbar_expect_tx(&full[s], plen);
+                    bulk_g2s(ring + size_t(s) * sh.stage_bytes,
+                             reinterpret_cast<const uint8_t*>(d.src) + off0 + o, plen, &full[s]);
+                } else {
+                    mbar_arrive(&full[s]);  // a miss: nothing to move, keep the ring in step
+                }
+            }
+            if (++s == sh.stages) {
+                s = 0;
+                ++use;
+            }
+        }
+    }
+}
+
+template <typename DescAt>
+__device__ __forceinline__ void storer_body(const Shape& sh, uint32_t first, uint32_t stride,
+                                            uint32_t nitems, uint32_t lane, uint8_t* ring,
+                                            uint64_t* full, uint64_t* empty, uint32_t* status,
+                                            DescAt&& desc_at) {
+    uint32_t s = 0, ph = 0;  // slot being stored and its full-phase parity
+    uint32_t sf = 0;         // slot to release next
+    uint32_t q = 0;          // pieces issued
+    for (uint32_t k = 0; k < nitems; ++k) {
+        const CopyDesc d = desc_at(k);
+        const uint32_t item = first + k * stride;
+        const uint32_t off0 = (item % sh.cpb) * sh.chunk;
+        const uint32_t len = min(sh.chunk, sh.bytes - off0);
+        if (lane == 0 && d.src == 0 && off0 == 0 && status) atomicAdd(status + kStatMiss, 1u);
+        for (uint32_t o = 0; o < len; o += sh.stage_bytes, ++q) {
+            if (lane == 0) {
+                mbar_wait(&full[s], ph);
+                if (d.src)
+                    bulk_s2g(reinterpret_cast<uint8_t*>(d.dst) + off0 + o,
+                             ring + size_t(s) * sh.stage_bytes, min(sh.stage_bytes, len - o));
+                bulk_commit();  // one group per piece (an empty one for a miss)
+                bulk_wait_read<kStoreLag>();  // pieces <= q - kStoreLag have left the ring
+                if (q >= uint32_t(kStoreLag)) {
+                    mbar_arrive(&empty[sf]);
+                    if (++sf == sh.stages) sf = 0;
+                }
+            }
+            if (++s == sh.stages) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+    }
+    if (lane == 0) {
+        bulk_wait<0>();       // every bulk store of this CTA has completed its writes
+        fence_proxy_async();  // async-proxy writes before the generic-proxy commit / exit
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------- kv_pipe_copy
+template <bool PARAM>
+__global__ void __launch_bounds__(kPipeThreads)
+    kv_pipe_copy_kernel(const CopyDesc* __restrict__ descs,
+                        const __grid_constant__ PipeDescParam<PARAM ? kPipeParamDescs : 1> pd,
+                        const Shape sh, Publish pub) {
+    extern __shared__ __align__(128) uint8_t ring[];
+    __shared__ __align__(8) uint64_t full[kPipeMaxStages];
+    __shared__ __align__(8) uint64_t empty[kPipeMaxStages];
+    const uint32_t total = sh.n * sh.cpb;
+    const uint32_t grid = gridDim.x;
+    const uint32_t nitems = blockIdx.x < total ? (total - blockIdx.x + grid - 1) / grid : 0;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < sh.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == 2) {  // control warp: in-band commit
+        if (pub.recs) control_warp(pub, lane, blockIdx.x, nitems, grid, sh.cpb, 64);
+        return;
+    }
+    DescWindow<PARAM> win{descs, &pd, blockIdx.x, grid, sh.cpb, nitems, lane};
+    win.init();
+    auto desc_at = [&](uint32_t k) { return win.at(k); };
+    if (warp == 0) {
+        loader_body(sh, blockIdx.x, grid, nitems, lane, ring, full, empty, desc_at);
+    } else {
+        storer_body(sh, blockIdx.x, grid, nitems, lane, ring, full, empty, pub.status, desc_at);
+        if (pub.recs) ctrl_barrier_arrive(64);
+    }
+}
+
+// ---------------------------------------------------------------- kv_pipe_read (fused)
+struct PipeReadArgs {
+    const uint8_t* key_bytes;
+    const uint32_t* key_off;
+    const uint32_t* key_len;
+    const uint64_t* dst_off;
+    uint64_t dst_base;
+    const IndexBucket* table;
+    uint64_t table_mask;
+    uint64_t seg_base[ReadFusedLaunch::kMaxSegs];
+    uint32_t nsegs;
+    uint32_t* status;
+};
+
+constexpr int kQ = 32;  // descriptors per queue half
+
+__global__ void __launch_bounds__(kPipeThreads)
+    kv_pipe_read_kernel(const __grid_constant__ PipeReadArgs a, const Shape sh) {
+    extern __shared__ __align__(128) uint8_t ring[];
+    __shared__ __align__(8) uint64_t full[kPipeMaxStages];
+    __shared__ __align__(8) uint64_t empty[kPipeMaxStages];
+    __shared__ __align__(8) uint64_t qfull[2];
+    __shared__ __align__(8) uint64_t qempty[2];
+    __shared__ CopyDesc queue[2][kQ];
+    const uint32_t total = sh.n;  // fused reads move whole blocks: cpb == 1
+    const uint32_t grid = gridDim.x;
+    const uint32_t nitems = blockIdx.x < total ? (total - blockIdx.x + grid - 1) / grid : 0;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < sh.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(&qfull[0], 1);
+        mbar_init(&qfull[1], 1);
+        mbar_init(&qempty[0], 1);
+        mbar_init(&qempty[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const uint32_t nbatches = (nitems + kQ - 1) / kQ;
+    if (warp == 2) {  // ---- resolver: runs ahead of the copy by up to two batches
+        for (uint32_t b = 0; b < nbatches; ++b) {
+            const uint32_t p = b & 1;
+            if (b >= 2) mbar_wait(&qempty[p], ((b >> 1) - 1) & 1);
+            const uint32_t k = b * kQ + lane;
+            if (k < nitems) {
+                const uint32_t block = blockIdx.x + k * grid;
+                const KeyHash kh = hash_key(a.key_bytes + a.key_off[block], a.key_len[block]);
+                const idx::Found f = idx::find<false>(a.table, a.table_mask, kh);
+                uint64_t src = 0;
+                if (f.slot_plus1) {
+                    const uint32_t seg = uint32_t(f.addr >> 44) - 1;
+                    if (f.size >= sh.bytes && seg < a.nsegs && a.seg_base[seg])
+                        src = a.seg_base[seg] + (f.addr & ((1ull << 44) - 1));
+                }
+                queue[p][lane] = CopyDesc{src, a.dst_base + a.dst_off[block]};
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&qfull[p]);  // release: the queue half is visible
+        }
+        return;
+    }
+    // loader and storer read their descriptors from the queue; the storer, the last reader
+    // of a half, hands it back to the resolver
+    const bool is_storer = warp == 1;
+    auto desc_at = [&](uint32_t k) -> CopyDesc {
+        const uint32_t b = k / kQ, p = b & 1;
+        if (k % kQ == 0) mbar_wait(&qfull[p], (b >> 1) & 1);
+        const CopyDesc d = queue[p][k % kQ];
+        if (is_storer && (k % kQ == kQ - 1 || k + 1 == nitems)) {
+            __syncwarp();  // every lane has read its copy of the entry
+            if (lane == 0) mbar_arrive(&qempty[p]);
+        }
+        return d;
+    };
+    if (warp == 0)
+        loader_body(sh, blockIdx.x, grid, nitems, lane, ring, full, empty, desc_at);
+    else
+        storer_body(sh, blockIdx.x, grid, nitems, lane, ring, full, empty, a.status, desc_at);
+}
+
+// ---------------------------------------------------------------- kv_pipe_mcast (clusters)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // UCGABAR_ARV / UCGABAR_WAIT
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    long long start = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spins == 64) start = clock64();
+        if (spins > 64 && (spins & 1023) == 0 && clock64() - start > 8000000000ll) __trap();
+    }
+}
+// global -> the shared memory of every CTA in `mask`, completing on the barrier at the same
+// offset in each of them                                        UBLKCP.S.G ... MULTICAST
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gsrc,
+                                                   uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+
+struct McastArgs {
+    const CopyDesc* descs;  // src = pool block, dst = its place in destination 0
+    uint32_t n, bytes, stage_bytes, stages;
+    int64_t delta[4];  // destination r = dst + delta[r]   (delta[0] = 0)
+    uint32_t* status;
+};
+
+template <int K>
+__global__ void __launch_bounds__(64)
+    kv_pipe_mcast_kernel(const __grid_constant__ McastArgs a) {
+    extern __shared__ __align__(128) uint8_t ring[];
+    __shared__ __align__(8) uint64_t full[kPipeMaxStages];   // per CTA: the tile has landed here
+    __shared__ __align__(8) uint64_t empty[kPipeMaxStages];  // leader only: K CTAs released it
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t cluster = blockIdx.x / K, nclusters = gridDim.x / K;
+    const uint32_t nitems = cluster < a.n ? (a.n - cluster + nclusters - 1) / nclusters : 0;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < a.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], K);
+        }
+        mbar_fence_init();
+    }
+    cluster_sync_all();  // every CTA's barriers exist before the leader multicasts into them
+    DescWindow<false> win{a.descs, nullptr, cluster, nclusters, 1, nitems, lane};
+    win.init();
+    if (warp == 0) {
+        if (rank == 0) {  // ---- leader's loader: one fetch over NVLink feeds K CTAs
+            uint32_t s = 0, use = 0;
+            for (uint32_t k = 0; k < nitems; ++k) {
+                const CopyDesc d = win.at(k);
+                for (uint32_t o = 0; o < a.bytes; o += a.stage_bytes) {
+                    if (lane == 0) {
+                        if (use) mbar_wait_cluster(&empty[s], (use - 1) & 1);
+                        if (d.src)
+                            bulk_g2s_multicast(ring + size_t(s) * a.stage_bytes,
+                                               reinterpret_cast<const uint8_t*>(d.src) + o,
+                                               min(a.stage_bytes, a.bytes - o), &full[s],
+                                               uint16_t((1u << K) - 1));
+                    }
+                    if (++s == a.stages) {
+                        s = 0;
+                        ++use;
+                    }
+                }
+            }
+        }
+    } else {  // ---- every CTA: store the tile to its own destination
+        uint32_t s = 0, ph = 0, sf = 0, q = 0;
+        for (uint32_t k = 0; k < nitems; ++k) {
+            const CopyDesc d = win.at(k);
+            if (lane == 0 && rank == 0 && d.src == 0 && a.status) atomicAdd(a.status + kStatMiss, 1u);
+            for (uint32_t o = 0; o < a.bytes; o += a.stage_bytes, ++q) {
+                if (lane == 0) {
+                    const uint32_t plen = min(a.stage_bytes, a.bytes - o);
+                    if (d.src) {
+                        // arm this CTA's barrier for the bytes the leader multicasts (they may
+                        // already have landed: the phase completes once both have happened)
+                        mbar_expect_tx(&full[s], plen);
+                        mbar_wait(&full[s], ph);
+                        bulk_s2g(reinterpret_cast<uint8_t*>(int64_t(d.dst) + a.delta[rank]) + o,
+                                 ring + size_t(s) * a.stage_bytes, plen);
+                    } else {
+                        mbar_arrive(&full[s]);  // a miss: complete the phase, keep parities in step
+                    }
+                    bulk_commit();
+                    bulk_wait_read<kStoreLag>();
+                    if (q >= uint32_t(kStoreLag)) {
+                        mbar_arrive_remote(&empty[sf], 0);  // DSMEM: hand the slot back to the leader
+                        if (++sf == a.stages) sf = 0;
+                    }
+                }
+                if (++s == a.stages) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+        if (lane == 0) {
+            bulk_wait<0>();
+            fence_proxy_async();
+        }
+    }
+    __syncwarp();
+    cluster_sync_all();  // nobody leaves while a sibling may still arrive on its barriers
+}
+
+std::mutex g_pipe_attr_mu;
+bool g_pipe_attr_set[64] = {false};
+
+cudaError_t ensure_pipe_attrs() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_pipe_attr_mu);
+    if (dev < 0 || dev >= 64 || g_pipe_attr_set[dev]) return cudaSuccess;
+    const int kMax = 200 << 10;
+    cudaError_t e = cudaFuncSetAttribute(kv_pipe_copy_kernel<false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kv_pipe_copy_kernel<true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kv_pipe_read_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kMax);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kv_pipe_mcast_kernel<2>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kv_pipe_mcast_kernel<4>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+    if (e != cudaSuccess) return e;
+    g_pipe_attr_set[dev] = true;
+    return cudaSuccess;
+}
+
+}  // namespace
+
+// Ring geometry: slots of up to `stage` bytes (16-byte multiple), as many as fit `ring` bytes.
+PipeGeometry pipe_geometry(uint32_t bytes, uint32_t stage_pref, uint32_t ring_pref) {
+    PipeGeometry g;
+    const uint32_t stage_cap = stage_pref ? stage_pref : (16u << 10);
+    const uint32_t ring = ring_pref ? ring_pref : (128u << 10);
+    g.stage_bytes = std::min(stage_cap, (bytes + 15u) & ~15u);
+    g.stages = std::max<uint32_t>(kStoreLag + 1,
+                                  std::min<uint32_t>(kPipeMaxStages, ring / g.stage_bytes));
+    g.smem = size_t(g.stages) * g.stage_bytes;
+    return g;
+}
+
+cudaError_t launch_kv_pipe_copy(const CopyLaunch& a, cudaStream_t stream) {
+    if (a.n == 0 || a.bytes == 0) return cudaSuccess;
+    if ((a.bytes % 16) != 0 || (a.align_or & 15) != 0 || a.multicast) return cudaErrorInvalidValue;
+    cudaError_t e = ensure_pipe_attrs();
+    if (e != cudaSuccess) return e;
+    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n, a.trace, !a.all_local, a.debug};
+    if (!a.table || !a.done) pub.recs = nullptr;
+    const int sms = sm_count();
+    const PipeGeometry g = pipe_geometry(a.bytes, a.stage_bytes, a.ring_bytes);
+    // Work item: a whole block when there are at least as many blocks as CTAs (the commit of a
+    // block then needs no cross-CTA counter), otherwise chunks of a few ring slots.
+    // the ring takes most of an SM's shared memory: one CTA per SM is resident (two when the
+    // ring was configured at half size), more would only queue behind them
+    const int resident = (g.smem > (110u << 10) ? 1 : 2) * sms;
+    int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, resident) : sms;
+    uint32_t chunk = a.bytes;
+    if (a.n < uint32_t(ctas) || a.bytes > (1u << 20)) {
+        const uint32_t per = g.stage_bytes * 4;
+        if (a.bytes > per) chunk = per;
+    }
+    const uint32_t cpb = (a.bytes + chunk - 1) / chunk;
+    const uint64_t total = uint64_t(a.n) * cpb;
+    ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
+    const Shape sh{a.n, a.bytes, chunk, cpb, g.stage_bytes, g.stages};
+    const bool param = a.descs_host != nullptr && a.n <= uint32_t(kPipeParamDescs);
+    if (param) {
+        PipeDescParam<kPipeParamDescs> pd;
+        std::memcpy(pd.d, a.descs_host, size_t(a.n) * sizeof(CopyDesc));
+        kv_pipe_copy_kernel<true><<<ctas, kPipeThreads, g.smem, stream>>>(a.descs, pd, sh, pub);
+    } else {
+        const PipeDescParam<1> none{};
+        kv_pipe_copy_kernel<false><<<ctas, kPipeThreads, g.smem, stream>>>(a.descs, none, sh, pub);
+    }
+    return cudaGetLastError();
+}
+
+bool pipe_read_supported(const ReadFusedLaunch& a) {
+    return !a.validate && (a.bytes % 16) == 0 && (a.align_or & 15) == 0;
+}
+
+cudaError_t launch_kv_pipe_read(const ReadFusedLaunch& a, cudaStream_t stream) {
+    if (a.n == 0 || a.bytes == 0) return cudaSuccess;
+    if (!pipe_read_supported(a)) return cudaErrorInvalidValue;
+    cudaError_t e = ensure_pipe_attrs();
+    if (e != cudaSuccess) return e;
+    const PipeGeometry g = pipe_geometry(a.bytes, a.stage_bytes, a.ring_bytes);
+    const int resident = (g.smem > (110u << 10) ? 1 : 2) * sm_count();
+    int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, resident) : sm_count();
+    ctas = int(std::min<uint32_t>(uint32_t(ctas), a.n));
+    PipeReadArgs r{};
+    r.key_bytes = a.key_bytes;
+    r.key_off = a.key_off;
+    r.key_len = a.key_len;
+    r.dst_off = a.dst_off;
+    r.dst_base = a.dst_base;
+    r.table = a.table;
+    r.table_mask = a.table_mask;
+    r.nsegs = a.nsegs;
+    for (uint32_t s = 0; s < a.nsegs && s < uint32_t(ReadFusedLaunch::kMaxSegs); ++s)
+        r.seg_base[s] = a.seg_base[s];
+    r.status = a.status;
+    const Shape sh{a.n, a.bytes, a.bytes, 1, g.stage_bytes, g.stages};
+    kv_pipe_read_kernel<<<ctas, kPipeThreads, g.smem, stream>>>(r, sh);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kv_pipe_mcast(const McastLaunch& a, cudaStream_t stream) {
+    if (a.n == 0 || a.bytes == 0) return cudaSuccess;
+    if ((a.ndst != 2 && a.ndst != 4) || (a.bytes % 16) != 0 || (a.align_or & 15) != 0)
+        return cudaErrorInvalidValue;
+    cudaError_t e = ensure_pipe_attrs();
+    if (e != cudaSuccess) return e;
+    // two CTAs of a cluster may share an SM: keep the ring at half the usual size
+    const PipeGeometry g = pipe_geometry(a.bytes, a.stage_bytes, a.ring_bytes ? a.ring_bytes : (64u << 10));
+    McastArgs m{};
+    m.descs = a.descs;
+    m.n = a.n;
+    m.bytes = a.bytes;
+    m.stage_bytes = g.stage_bytes;
+    m.stages = g.stages;
+    for (int r = 0; r < 4; ++r) m.delta[r] = r < a.ndst ? a.delta[r] : 0;
+    m.status = a.status;
+    int clusters = a.max_clusters > 0 ? a.max_clusters : sm_count() / a.ndst;
+    clusters = int(std::min<uint32_t>(uint32_t(clusters), a.n));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(clusters * a.ndst));
+    cfg.blockDim = dim3(64);
+    cfg.dynamicSmemBytes = g.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = unsigned(a.ndst);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (a.ndst == 2) return cudaLaunchKernelEx(&cfg, kv_pipe_mcast_kernel<2>, m);
+    return cudaLaunchKernelEx(&cfg, kv_pipe_mcast_kernel<4>, m);
+}
+
+}  // namespace istore::kernels

@@ -132,6 +132,11 @@ __global__ void __launch_bounds__(kThreads)
 
 cudaError_t launch_kv_read_fused(const ReadFusedLaunch& a, cudaStream_t stream) {
     if (a.n == 0 || a.bytes == 0) return cudaSuccess;
+    // default: resolver warp + TMA pipeline (kv_pipe.cu); this file's ld/st kernel serves
+    // small or unaligned pages and stores that evict (post-copy validation)
+    if ((a.variant == kCopyTma || (a.variant == kCopyAuto && a.bytes >= kPipeMinBytes)) &&
+        pipe_read_supported(a))
+        return launch_kv_pipe_read(a, stream);
     uint32_t chunk = std::min(a.bytes, 32u << 10);
     if (a.n >= uint32_t(sm_count()) && a.bytes <= (1u << 20)) chunk = a.bytes;  // see kv_copy.cu
     const uint32_t cpb = (a.bytes + chunk - 1) / chunk;

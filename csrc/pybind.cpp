@@ -418,6 +418,17 @@ PYBIND11_MODULE(_infinistore, m) {
             py::arg("blocks"), py::arg("block_size"), py::arg("base_ptr"),
             py::arg("device") = -1, py::arg("stream") = 0, py::arg("scale") = 1)
         .def(
+            "r_rdma_multi",
+            [](Connection& c, const py::object& blocks, int block_size,
+               const std::vector<uint64_t>& bases, int device, uint64_t stream, uint64_t scale) {
+                std::vector<KeyOffset> kb;
+                blocks_list_from_py(blocks, scale, kb);
+                py::gil_scoped_release rel;
+                return c.r_rdma_multi(kb, block_size, bases, device, stream);
+            },
+            py::arg("blocks"), py::arg("block_size"), py::arg("bases"), py::arg("device") = -1,
+            py::arg("stream") = 0, py::arg("scale") = 1)
+        .def(
             "r_rdma_async",
             [](Connection& c, const py::object& blocks, int block_size, uint64_t base_ptr,
                py::function cb, int device, uint64_t stream, uint64_t scale) {
@@ -682,8 +693,11 @@ PYBIND11_MODULE(_infinistore, m) {
         "kv_copy",
         [](uint64_t descs, uint32_t n, uint32_t bytes, int variant, int max_ctas, uint64_t stream,
            uint64_t recs, uint64_t table, uint64_t table_mask, uint64_t done, uint64_t status,
-           uint64_t align_or, uint64_t trace, bool all_local, uint32_t debug) {
+           uint64_t align_or, uint64_t trace, bool all_local, uint32_t debug,
+           uint32_t stage_bytes, uint32_t ring_bytes) {
             kernels::CopyLaunch L;
+            L.stage_bytes = stage_bytes;
+            L.ring_bytes = ring_bytes;
             L.descs = as_ptr<const kernels::CopyDesc>(descs);
             L.n = n;
             L.bytes = bytes;
@@ -705,7 +719,30 @@ PYBIND11_MODULE(_infinistore, m) {
         py::arg("max_ctas") = 0, py::arg("stream") = 0, py::arg("recs") = 0,
         py::arg("table") = 0, py::arg("table_mask") = 0, py::arg("done") = 0,
         py::arg("status") = 0, py::arg("align_or") = 0, py::arg("trace") = 0,
-        py::arg("all_local") = false, py::arg("debug") = 0);
+        py::arg("all_local") = false, py::arg("debug") = 0, py::arg("stage_bytes") = 0,
+        py::arg("ring_bytes") = 0);
+    k.def(
+        "kv_pipe_mcast",
+        [](uint64_t descs, uint32_t n, uint32_t bytes, const std::vector<int64_t>& delta,
+           int max_clusters, uint64_t stream, uint64_t status, uint32_t stage_bytes,
+           uint32_t ring_bytes) {
+            kernels::McastLaunch M;
+            M.descs = as_ptr<const kernels::CopyDesc>(descs);
+            M.n = n;
+            M.bytes = bytes;
+            M.ndst = int(delta.size());
+            for (size_t i = 0; i < delta.size() && i < 4; ++i) M.delta[i] = delta[i];
+            M.status = as_ptr<uint32_t>(status);
+            M.max_clusters = max_clusters;
+            M.stage_bytes = stage_bytes;
+            M.ring_bytes = ring_bytes;
+            const cudaError_t e = kernels::launch_kv_pipe_mcast(M, as_ptr<CUstream_st>(stream));
+            if (e != cudaSuccess) throw std::runtime_error(cudaGetErrorString(e));
+        },
+        py::arg("descs"), py::arg("n"), py::arg("bytes"), py::arg("delta"),
+        py::arg("max_clusters") = 0, py::arg("stream") = 0, py::arg("status") = 0,
+        py::arg("stage_bytes") = 0, py::arg("ring_bytes") = 0,
+        "one pool block -> 2 or 4 destinations through a thread-block cluster (TMA multicast)");
     k.def(
         "index_lookup",
         [](uint64_t key_bytes, uint64_t key_off, uint64_t key_len, uint32_t n, uint64_t table,

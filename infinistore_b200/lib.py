@@ -519,6 +519,29 @@ class InfinityConnection:
         if ret < 0:
             raise Exception(f"Failed to read to infinistore, ret = {ret}")
 
+    def read_cache_multi(self, caches: List[torch.Tensor], blocks: List[Tuple[str, int]],
+                         page_size: int, stream="current"):
+        """Read the same pages into several CUDA tensors of ONE device (the KV cache replicas
+        of beams / tensor-parallel consumers that share a prefix): every page is fetched from
+        the pool once - one trip over NVLink - and fanned out to all destinations by a
+        thread-block cluster (TMA multicast into the shared memory of 2 or 4 CTAs, one
+        destination per CTA).  Each destination receives page ``key`` at the same element
+        ``offset``.  No reference counterpart: the reference would run N independent reads
+        (src/infinistore.cpp:424-533)."""
+        if not self.rdma_connected:
+            raise Exception("this function is only valid for connected rdma")
+        if not caches:
+            return
+        infos = [self._info(c) for c in caches]
+        first = infos[0]
+        for c, i in zip(caches, infos):
+            if i.dev < 0 or i.dev != first.dev or i.es != first.es:
+                raise Exception("read_cache_multi: CUDA tensors of one device and dtype")
+        ret = self.conn.r_rdma_multi(blocks, page_size * first.es, [i.ptr for i in infos],
+                                     first.dev, self._stream(first, caches[0], stream), first.es)
+        if ret < 0:
+            raise Exception(f"Failed to read to infinistore, ret = {ret}")
+
     async def read_cache_async(self, cache: torch.Tensor, blocks: List[Tuple[str, int]],
                                page_size: int, stream="current"):
         if not self.rdma_connected:

@@ -41,8 +41,11 @@ def make_descs(src_ptrs: Sequence[int], dst_ptrs: Sequence[int], device) -> torc
 
 def kv_copy(descs: torch.Tensor, nbytes: int, variant: str = "auto", max_ctas: int = 0,
             publish: Optional["PublishArgs"] = None, status: Optional[torch.Tensor] = None,
-            align_or: int = 0) -> None:
-    """Move descs.shape[0] blocks of `nbytes` bytes.  See csrc/kernels/kv_copy.cu."""
+            align_or: int = 0, stage_bytes: int = 0, ring_bytes: int = 0,
+            all_local: bool = False) -> None:
+    """Move descs.shape[0] blocks of `nbytes` bytes.  ``variant``: "auto" / "tma" = the
+    warp-specialised TMA pipeline (csrc/kernels/kv_pipe.cu; ``stage_bytes`` / ``ring_bytes``
+    set its ring geometry), "ldst" / "ldst256" = csrc/kernels/kv_copy.cu."""
     assert descs.is_cuda and descs.dtype == torch.int64 and descs.is_contiguous()
     n = descs.shape[0]
     with torch.cuda.device(descs.device):
@@ -51,7 +54,23 @@ def kv_copy(descs: torch.Tensor, nbytes: int, variant: str = "auto", max_ctas: i
                   publish.table.data_ptr() if publish else 0,
                   publish.mask if publish else 0,
                   publish.done.data_ptr() if publish else 0,
-                  status.data_ptr() if status is not None else 0, align_or)
+                  status.data_ptr() if status is not None else 0, align_or, 0, all_local, 0,
+                  stage_bytes, ring_bytes)
+
+
+def kv_copy_multicast(descs: torch.Tensor, nbytes: int, dst_deltas: Sequence[int],
+                      max_clusters: int = 0, status: Optional[torch.Tensor] = None,
+                      stage_bytes: int = 0, ring_bytes: int = 0) -> None:
+    """Every block descs[i].src -> descs[i].dst + dst_deltas[r] for r in range(2 or 4), with a
+    thread-block cluster: the source is fetched ONCE (``cp.async.bulk ...
+    .multicast::cluster`` into every CTA's shared memory) and each CTA of the cluster stores
+    it to its own destination (csrc/kernels/kv_pipe.cu: kv_pipe_mcast)."""
+    assert descs.is_cuda and descs.dtype == torch.int64 and descs.is_contiguous()
+    assert len(dst_deltas) in (2, 4), "clusters of 2 or 4 CTAs"
+    with torch.cuda.device(descs.device):
+        K.kv_pipe_mcast(descs.data_ptr(), descs.shape[0], nbytes, [int(d) for d in dst_deltas],
+                        max_clusters, _stream(descs.device),
+                        status.data_ptr() if status is not None else 0, stage_bytes, ring_bytes)
 
 
 class PublishArgs:

@@ -48,6 +48,59 @@ def test_kv_copy_small_grid_and_many_blocks(variant):
     assert torch.equal(dst, src.flip(0))
 
 
+@pytest.mark.parametrize("stage_kb,ring_kb", [(4, 12), (8, 64), (16, 128), (32, 192)])
+@pytest.mark.parametrize("nbytes,n", [(131072, 300), (8192 + 48, 77), (3 << 20, 5)])
+def test_tma_pipeline_ring_geometries(stage_kb, ring_kb, nbytes, n):
+    """The TMA pipeline with different ring geometries: 3-slot minimum ring, pieces that do not
+    divide the block, blocks split over several CTAs (few large blocks)."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(nbytes + stage_kb)
+    src = torch.randint(0, 255, (n, nbytes), dtype=torch.uint8, device=DEV, generator=g)
+    dst = torch.zeros_like(src)
+    order = torch.randperm(n, generator=torch.Generator().manual_seed(3)).tolist()
+    descs = ops.make_descs([src[i].data_ptr() for i in range(n)],
+                           [dst[order[i]].data_ptr() for i in range(n)], DEV)
+    ops.kv_copy(descs, nbytes, variant="tma", stage_bytes=stage_kb << 10, ring_bytes=ring_kb << 10)
+    torch.cuda.synchronize()
+    ref = torch.empty_like(src)
+    ref[order] = src
+    assert torch.equal(dst, ref)
+
+
+@pytest.mark.parametrize("ndst", [2, 4])
+@pytest.mark.parametrize("nbytes,n", [(131072, 200), (16384, 1000), (40960 + 16, 33)])
+def test_cluster_multicast_copy_fans_one_source_out(ndst, nbytes, n):
+    """kv_pipe_mcast: one fetch of every source block, ndst destinations (torch reference:
+    index_select + broadcast)."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(nbytes * ndst)
+    stride = (nbytes + 255) // 256 * 256
+    src = torch.randint(0, 255, (n, stride), dtype=torch.uint8, device=DEV, generator=g)
+    dsts = torch.zeros((ndst, n, stride), dtype=torch.uint8, device=DEV)
+    order = torch.randperm(n, generator=torch.Generator().manual_seed(5)).tolist()
+    descs = ops.make_descs([src[i].data_ptr() for i in range(n)],
+                           [dsts[0, order[i]].data_ptr() for i in range(n)], DEV)
+    deltas = [dsts[r].data_ptr() - dsts[0].data_ptr() for r in range(ndst)]
+    status = torch.zeros(8, dtype=torch.int32, device=DEV)
+    ops.kv_copy_multicast(descs, nbytes, deltas, status=status)
+    torch.cuda.synchronize()
+    ref = torch.zeros((n, stride), dtype=torch.uint8, device=DEV)
+    ref[order, :nbytes] = src[:, :nbytes]
+    for r in range(ndst):
+        assert torch.equal(dsts[r], ref), f"destination {r}"
+    assert int(status[0]) == 0
+    # a descriptor without a source (a key the lookup did not find) is skipped and counted
+    d2 = descs.clone()
+    d2[3, 0] = 0
+    dsts.zero_()
+    ops.kv_copy_multicast(d2, nbytes, deltas, status=status, max_clusters=3)
+    torch.cuda.synchronize()
+    ref[order[3]] = 0
+    for r in range(ndst):
+        assert torch.equal(dsts[r], ref), f"destination {r} (with a miss)"
+    assert int(status[0]) == 1
+
+
 def test_kv_copy_unaligned_falls_back_to_bytes():
     ops = _ops()
     n, nbytes = 9, 1000  # not a multiple of 16, odd addresses

@@ -290,3 +290,73 @@ def test_checkpoint_dump_and_load_hbm(tmp_path):
             assert conn.get_match_last_index(keys + ["none"]) == 19
     finally:
         srv.stop()
+
+
+@pytest.mark.parametrize("device_lookup", [True, False])
+@pytest.mark.parametrize("ndst", [2, 3, 4])
+def test_read_cache_multi_fans_pages_out_through_a_cluster(hbm_server, device_lookup, ndst):
+    """One fetch per page, `ndst` destination tensors (thread-block cluster + TMA multicast);
+    torch reference: every destination equals a plain read_cache."""
+    _, port = hbm_server
+    conn = make_conn(port, device_lookup=device_lookup)
+    nblocks, elems = 300, 16384  # 64 KB fp32 pages
+    src = torch.randn(nblocks * elems, device="cuda:0")
+    conn.register_mr(src)
+    keys = [rand_key(14) for _ in range(nblocks)]
+    conn.rdma_write_cache(src, [i * elems for i in range(nblocks)], elems,
+                          conn.allocate_rdma(keys, elems * 4))
+    conn.sync()
+    order = list(range(nblocks))
+    random.Random(7).shuffle(order)
+    blocks = [(keys[k], i * elems) for i, k in enumerate(order)]
+    ref = torch.zeros_like(src)
+    conn.read_cache(ref, blocks, elems)
+    conn.sync()
+    assert torch.equal(ref.view(nblocks, elems), src.view(nblocks, elems)[order])
+    dsts = [torch.zeros_like(src) for _ in range(ndst)]
+    before = conn.stats()["kernel_launches"]
+    conn.read_cache_multi(dsts, blocks, elems)
+    conn.sync()
+    assert conn.stats()["kernel_launches"] > before
+    for d in dsts:
+        assert torch.equal(d, ref)
+    if device_lookup:  # a missing key is reported by sync(), the found pages still arrive
+        with pytest.raises(Exception):
+            conn.read_cache_multi(dsts[:2], [("no-such-key", 0)], elems)
+            conn.sync()
+
+
+def test_dead_writer_leaves_no_device_index_entry(hbm_server):
+    """A writer whose kernel published its block in-band but which died before sync(): the
+    server erases the index entry when it releases the reservation, device-path readers miss
+    (they must not resolve the key to freed memory) and the key can be written again."""
+    srv, port = hbm_server
+    writer = make_conn(port, device_lookup=True)
+    src = torch.randn(8192, device="cuda:0")
+    writer.register_mr(src)
+    writer.rdma_write_cache(src, [0], 8192, writer.allocate_rdma(["orphaned"], 8192 * 4))
+    torch.cuda.synchronize()  # the kernel ran: tag published in the HBM index
+    reader = make_conn(port, device_lookup=True)
+    assert reader.check_exist("orphaned")  # device index: visible although never committed
+    writer.conn.close()  # dies without sync(): no COMMIT ever reaches the server
+    import time
+
+    deadline = time.time() + 10
+    while srv.stats()["inflight"] and time.time() < deadline:
+        time.sleep(0.01)
+    assert srv.stats()["inflight"] == 0 and srv.stats()["used_bytes"] == 0
+    assert not reader.check_exist("orphaned")
+    dst = torch.zeros(8192, device="cuda:0")
+    with pytest.raises(Exception):
+        reader.read_cache(dst, [("orphaned", 0)], 8192)
+        reader.sync()
+    # first-writer-wins must not block the rewrite: the way was erased, not left claimed
+    w2 = make_conn(port, device_lookup=True)
+    src2 = torch.randn(8192, device="cuda:0")
+    w2.register_mr(src2)
+    w2.rdma_write_cache(src2, [0], 8192, w2.allocate_rdma(["orphaned"], 8192 * 4))
+    w2.sync()
+    reader2 = make_conn(port, device_lookup=True)
+    reader2.read_cache(dst, [("orphaned", 0)], 8192)
+    reader2.sync()
+    assert torch.equal(dst, src2)

@@ -41,6 +41,7 @@ HOST_SOURCES = [
 ]
 CUDA_SOURCES = [
     "kernels/kv_copy.cu",
+    "kernels/kv_pipe.cu",
     "kernels/index_lookup.cu",
     "kernels/kv_read_fused.cu",
     "kernels/kv_fp8.cu",
