@@ -179,28 +179,28 @@ class ServerConfig(_infinistore.ServerConfig):
             raise Exception("evict ratio should be in (0, 1]")
 
 
+class _LevelMethod:
+    """Descriptor producing ``Logger.<level>(msg)`` for one level of the native logger."""
+
+    def __init__(self, level: str):
+        self._level = level
+
+    def __get__(self, obj, owner=None):
+        level = self._level
+        return lambda msg: _infinistore.log_msg(level, str(msg))
+
+
 class Logger:
-    """Thin wrappers over the native logger (reference: infinistore/lib.py:131-150)."""
+    """Python face of the native logger (same surface as the reference's ``Logger``,
+    infinistore/lib.py:131-150: ``info / debug / error / warn / set_log_level``).  Messages
+    go through the C++ sink so that Python and native lines share one format and level."""
 
-    @staticmethod
-    def info(msg):
-        _infinistore.log_msg("info", str(msg))
-
-    @staticmethod
-    def debug(msg):
-        _infinistore.log_msg("debug", str(msg))
-
-    @staticmethod
-    def error(msg):
-        _infinistore.log_msg("error", str(msg))
-
-    @staticmethod
-    def warn(msg):
-        _infinistore.log_msg("warning", str(msg))
-
-    @staticmethod
-    def set_log_level(level):
-        _infinistore.set_log_level(level)
+    info = _LevelMethod("info")
+    debug = _LevelMethod("debug")
+    error = _LevelMethod("error")
+    warn = _LevelMethod("warning")
+    warning = warn
+    set_log_level = staticmethod(_infinistore.set_log_level)
 
 
 def get_kvmap_len():
@@ -369,12 +369,29 @@ class InfinityConnection:
 
     def __init__(self, config: ClientConfig):
         config.verify()
-        self.conn = _infinistore.Connection()
-        self.local_connected = False
-        self.rdma_connected = False
-        self.config = config
-        self._tinfo = {}
         Logger.set_log_level(config.log_level)
+        self.config = config
+        self.conn = _infinistore.Connection()
+        # which flavour is up: "" (none), "local" (TYPE_LOCAL_GPU) or "rdma" (TYPE_RDMA)
+        self._mode = ""
+        self._tinfo = {}
+
+    # The reference exposes two booleans (lib.py:288-289); they are views of one state here.
+    @property
+    def local_connected(self) -> bool:
+        return self._mode == "local"
+
+    @local_connected.setter
+    def local_connected(self, up: bool):
+        self._mode = "local" if up else ("" if self._mode == "local" else self._mode)
+
+    @property
+    def rdma_connected(self) -> bool:
+        return self._mode == "rdma"
+
+    @rdma_connected.setter
+    def rdma_connected(self, up: bool):
+        self._mode = "rdma" if up else ("" if self._mode == "rdma" else self._mode)
 
     def _info(self, cache: torch.Tensor) -> "_TensorInfo":
         """Validated facts about `cache` (contiguous, device rule), cached per tensor object."""
@@ -404,46 +421,35 @@ class InfinityConnection:
         self.conn.set_streams(int(self.config.streams))
         self.conn.set_device_lookup(bool(self.config.device_lookup) and self.conn.server_has_hbm())
 
+    def _bring_up(self):
+        """TCP connect + exchange, pool map, per-connection options.  Blocking."""
+        for step, what in ((self.conn.init_connection, "initialize remote connection"),
+                           (self.conn.setup_rdma, "setup RDMA connection")):
+            if step(self.config) < 0:
+                raise Exception(f"Failed to {what}")
+        self._apply_options()
+
     async def connect_async(self):
-        """Connect without blocking the event loop (RDMA type only, as in the reference)."""
+        """Connect from a coroutine: the blocking bring-up runs on the default executor.
+        As in the reference (lib.py:291-312) only the RDMA flavour has an async connect."""
         if self.config.connection_type == TYPE_LOCAL_GPU:
             raise Exception("Local GPU connection is not supported in async mode")
-        loop = asyncio.get_running_loop()
-
-        def blocking_connect():
-            if self.conn.init_connection(self.config) < 0:
-                raise Exception("Failed to initialize remote connection")
-            if self.conn.setup_rdma(self.config) < 0:
-                raise Exception("Failed to setup RDMA connection")
-            self._apply_options()
-            self.rdma_connected = True
-
-        await loop.run_in_executor(None, blocking_connect)
+        await asyncio.get_running_loop().run_in_executor(None, self._bring_up)
+        self._mode = "rdma"
 
     def connect(self):
-        if self.local_connected:
-            raise Exception("Already connected to local instance")
-        if self.rdma_connected:
-            raise Exception("Already connected to remote instance")
-        if self.config.connection_type == TYPE_LOCAL_GPU and self.config.host_addr not in (
-            "127.0.0.1",
-            "localhost",
-        ):
+        if self._mode:
+            raise Exception("Already connected to %s instance"
+                            % ("local" if self._mode == "local" else "remote"))
+        local = self.config.connection_type == TYPE_LOCAL_GPU
+        if local and self.config.host_addr not in ("127.0.0.1", "localhost"):
             raise Exception("Local GPU connection must be to localhost")
-        if self.conn.init_connection(self.config) < 0:
-            raise Exception("Failed to initialize remote connection")
-        if self.conn.setup_rdma(self.config) < 0:
-            raise Exception("Failed to setup RDMA connection")
-        self._apply_options()
-        if self.config.connection_type == TYPE_LOCAL_GPU:
-            self.local_connected = True
-        else:
-            self.rdma_connected = True
+        self._bring_up()
+        self._mode = "local" if local else "rdma"
 
     def close(self):
         self.conn.close()
-        self.local_connected = False
-        self.rdma_connected = False
+        self._mode = ""
 
     # ------------------------------------------------------------------ writes
     def local_gpu_write_cache(self, cache: torch.Tensor, blocks: List[Tuple[str, int]],
@@ -625,16 +631,22 @@ class InfinityConnection:
         return
 
     def _verify(self, cache: torch.Tensor):
-        if (not self.rdma_connected) and cache.device.type != "cuda":
-            raise Exception("Tensor must be on CUDA device for local GPU connection")
-        if cache.is_contiguous() is False:
-            raise Exception("Tensor must be contiguous")
+        """Layout rules of every data-plane call: dense memory; and a LOCAL_GPU connection
+        moves CUDA tensors only (a host tensor needs the RDMA flavour's pinned path)."""
+        problems = []
+        if self._mode != "rdma" and cache.device.type != "cuda":
+            problems.append("Tensor must be on CUDA device for local GPU connection")
+        if not cache.is_contiguous():
+            problems.append("Tensor must be contiguous")
+        if problems:
+            raise Exception(problems[0])
 
-    def check_exist(self, key: str):
-        ret = self.conn.check_exist(key)
-        if ret < 0:
+    def check_exist(self, key: str) -> bool:
+        """True when `key` is stored and committed."""
+        status = self.conn.check_exist(key)
+        if status < 0:
             raise Exception("Failed to check if this key exists")
-        return True if ret == 0 else False
+        return status == 0
 
     def get_match_last_index(self, keys: List[str]):
         """Index of the last key of the longest matching prefix, computed with the
@@ -667,17 +679,17 @@ class InfinityConnection:
         return ret
 
     async def allocate_rdma_async(self, keys: List[str], page_size_in_bytes: int):
-        if not self.rdma_connected:
+        """Awaitable ``allocate_rdma``: the request runs on the connection's completion thread
+        and the result is handed back to the calling event loop."""
+        if self._mode != "rdma":
             raise Exception("this function is only valid for connected rdma")
         loop = asyncio.get_running_loop()
-        future = loop.create_future()
-
-        def _callback(remote_addrs):
-            loop.call_soon_threadsafe(future.set_result, remote_addrs)
-
-        self.conn.allocate_rdma_async(keys, page_size_in_bytes, _callback)
-        blocks = await future
-        if len(blocks) == 0:
+        done: asyncio.Future = loop.create_future()
+        self.conn.allocate_rdma_async(
+            keys, page_size_in_bytes,
+            lambda blocks: loop.call_soon_threadsafe(done.set_result, blocks))
+        blocks = await done
+        if not len(blocks):
             raise Exception("allocate memory failed")
         return blocks
 

@@ -11,6 +11,24 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+def get_version() -> str:
+    """`<latest tag>.<commits since>` as the reference does (setup.py:7-28); without a tag
+    (this repository has none yet) 0.2.0.dev<commit count>, and 0.2.0 outside a checkout."""
+    import subprocess
+
+    def git(*a):
+        return subprocess.check_output(["git", *a], cwd=ROOT, stderr=subprocess.DEVNULL).decode().strip()
+
+    try:
+        try:
+            tag = git("describe", "--tags", "--abbrev=0")
+            return f"{tag.lstrip('v')}.{git('rev-list', f'{tag}..HEAD', '--count')}"
+        except subprocess.CalledProcessError:
+            return f"0.2.0.dev{git('rev-list', 'HEAD', '--count')}"
+    except Exception:  # noqa: BLE001 - sdist / no git
+        return "0.2.0"
+
+
 def _build_native():
     from tools import build_native
 
@@ -39,7 +57,7 @@ class BinaryDistribution(Distribution):
 setup(
     distclass=BinaryDistribution,
     name="infinistore-b200",
-    version="0.1.0",
+    version=get_version(),
     description="Blackwell-native KV-cache block store with infiniStore's API",
     packages=find_packages(include=["infinistore_b200", "infinistore_b200.*", "infinistore"]),
     package_data={"infinistore_b200": ["_infinistore*.so"]},
