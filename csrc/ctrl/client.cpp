@@ -1437,6 +1437,65 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
     return 0;
 }
 
+// Device-addressable copy descriptors {mapped pool address (0 = miss), dst_base + offset} for
+// blocks[base, base + n): resolved on the GPU by the lookup kernel (rb == nullptr, the
+// descriptors land in device scratch) or taken from a server lookup (rb, pinned ring).
+const kernels::CopyDesc* Connection::resolve_descs(DevCtx* ctx, const std::vector<KeyOffset>& blocks,
+                                                   size_t base, size_t n, int block_size,
+                                                   uint64_t dst_base,
+                                                   const std::vector<RemoteBlock>* rb,
+                                                   void* stream_v) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (rb) {
+        const size_t at_desc = ctx->ring_alloc(n * sizeof(kernels::CopyDesc));
+        auto* descs = reinterpret_cast<kernels::CopyDesc*>(ctx->ring_h + at_desc);
+        for (size_t i = 0; i < n; ++i) {
+            const RemoteBlock& b = (*rb)[base + i];
+            uint8_t* segbase = seg_dev_ptr(ctx, addr_seg(b.remote_addr));
+            if (!segbase) return nullptr;
+            descs[i].src = reinterpret_cast<uint64_t>(segbase) + addr_off(b.remote_addr);
+            descs[i].dst = dst_base + blocks[base + i].offset;
+        }
+        return reinterpret_cast<const kernels::CopyDesc*>(ctx->ring_d + at_desc);
+    }
+    auto m0 = mapping(0, ctx->device);
+    if (!m0 || !m0->dev_ptr) return nullptr;
+    size_t key_bytes = 0;
+    std::vector<std::string_view> kp(n);
+    for (size_t i = 0; i < n; ++i) {
+        kp[i] = blocks[base + i].key;
+        key_bytes += align_up(std::max<size_t>(kp[i].size(), 1), 8);
+    }
+    const size_t at_bytes = ctx->ring_alloc(key_bytes);
+    const size_t at_off = ctx->ring_alloc(n * 4);
+    const size_t at_len = ctx->ring_alloc(n * 4);
+    const size_t at_dst = ctx->ring_alloc(n * 8);
+    pack_keys(kp.data(), n, ctx->ring_h + at_bytes, reinterpret_cast<uint32_t*>(ctx->ring_h + at_off),
+              reinterpret_cast<uint32_t*>(ctx->ring_h + at_len));
+    auto* dst = reinterpret_cast<uint64_t*>(ctx->ring_h + at_dst);
+    for (size_t i = 0; i < n; ++i) dst[i] = blocks[base + i].offset;
+    kernels::LookupLaunch Q;
+    Q.key_bytes = ctx->ring_d + at_bytes;
+    Q.key_off = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_off);
+    Q.key_len = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_len);
+    Q.n = uint32_t(n);
+    Q.table = reinterpret_cast<const kernels::IndexBucket*>(m0->dev_ptr + segs_[0].index_off);
+    Q.table_mask = kernels::index_bucket_mask(segs_[0].index_slots);
+    Q.nsegs = uint32_t(std::min<size_t>(segs_.size(), kernels::LookupLaunch::kMaxSegs));
+    for (uint32_t sgi = 0; sgi < Q.nsegs; ++sgi)
+        Q.seg_base[sgi] = reinterpret_cast<uint64_t>(seg_dev_ptr(ctx, sgi));
+    auto* out = reinterpret_cast<kernels::CopyDesc*>(
+        ctx->scratch + ctx->scratch_alloc(n * sizeof(kernels::CopyDesc)));
+    Q.out_descs = out;
+    Q.dst_off = reinterpret_cast<const uint64_t*>(ctx->ring_d + at_dst);
+    Q.dst_base = dst_base;
+    Q.need_bytes = uint32_t(block_size);
+    Q.status = ctx->status_d;
+    if (kernels::launch_index_lookup(Q, stream) != cudaSuccess) return nullptr;
+    stats_.kernel_launches++;
+    return out;
+}
+
 // The same pages into several destination tensors (TP ranks / beams sharing a prefix): every
 // pool block crosses NVLink once and is fanned out inside a thread-block cluster
 // (kernels/kv_pipe.cu: cp.async.bulk ... .multicast::cluster).  bases[r] is the base pointer
@@ -1466,89 +1525,31 @@ int Connection::r_rdma_multi(const std::vector<KeyOffset>& blocks, int block_siz
     for (uint64_t b : bases) align_or |= b;
     for (size_t base = 0; base < blocks.size(); base += kMaxBatch) {
         const size_t n = std::min(kMaxBatch, blocks.size() - base);
-        const kernels::CopyDesc* descs_d = nullptr;
         for (size_t i = 0; i < n; ++i) align_or |= blocks[base + i].offset;
-        cudaError_t e = cudaSuccess;
-        if (via_index) {
-            auto m0 = mapping(0, device);
-            if (!m0 || !m0->dev_ptr) return -1;
-            size_t key_bytes = 0;
-            std::vector<std::string_view> kp(n);
-            for (size_t i = 0; i < n; ++i) {
-                kp[i] = blocks[base + i].key;
-                key_bytes += align_up(std::max<size_t>(kp[i].size(), 1), 8);
-            }
-            const size_t at_bytes = ctx->ring_alloc(key_bytes);
-            const size_t at_off = ctx->ring_alloc(n * 4);
-            const size_t at_len = ctx->ring_alloc(n * 4);
-            const size_t at_dst = ctx->ring_alloc(n * 8);
-            pack_keys(kp.data(), n, ctx->ring_h + at_bytes,
-                      reinterpret_cast<uint32_t*>(ctx->ring_h + at_off),
-                      reinterpret_cast<uint32_t*>(ctx->ring_h + at_len));
-            auto* dst = reinterpret_cast<uint64_t*>(ctx->ring_h + at_dst);
-            for (size_t i = 0; i < n; ++i) dst[i] = blocks[base + i].offset;
-            kernels::LookupLaunch Q;
-            Q.key_bytes = ctx->ring_d + at_bytes;
-            Q.key_off = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_off);
-            Q.key_len = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_len);
-            Q.n = uint32_t(n);
-            Q.table = reinterpret_cast<const kernels::IndexBucket*>(m0->dev_ptr + segs_[0].index_off);
-            Q.table_mask = kernels::index_bucket_mask(segs_[0].index_slots);
-            Q.nsegs = uint32_t(std::min<size_t>(segs_.size(), kernels::LookupLaunch::kMaxSegs));
-            for (uint32_t sgi = 0; sgi < Q.nsegs; ++sgi)
-                Q.seg_base[sgi] = reinterpret_cast<uint64_t>(seg_dev_ptr(ctx, sgi));
-            auto* out = reinterpret_cast<kernels::CopyDesc*>(
-                ctx->scratch + ctx->scratch_alloc(n * sizeof(kernels::CopyDesc)));
-            Q.out_descs = out;
-            Q.dst_off = reinterpret_cast<const uint64_t*>(ctx->ring_d + at_dst);
-            Q.dst_base = bases[0];
-            Q.need_bytes = uint32_t(block_size);
-            Q.status = ctx->status_d;
-            e = kernels::launch_index_lookup(Q, stream);
-            stats_.kernel_launches++;
-            descs_d = out;
-        } else {
-            const size_t at_desc = ctx->ring_alloc(n * sizeof(kernels::CopyDesc));
-            auto* descs = reinterpret_cast<kernels::CopyDesc*>(ctx->ring_h + at_desc);
-            for (size_t i = 0; i < n; ++i) {
-                const RemoteBlock& b = rb[base + i];
-                uint8_t* segbase = seg_dev_ptr(ctx, addr_seg(b.remote_addr));
-                if (!segbase) return -1;
-                descs[i].src = reinterpret_cast<uint64_t>(segbase) + addr_off(b.remote_addr);
-                descs[i].dst = bases[0] + blocks[base + i].offset;
-            }
-            descs_d = reinterpret_cast<const kernels::CopyDesc*>(ctx->ring_d + at_desc);
+        const kernels::CopyDesc* descs_d =
+            resolve_descs(ctx, blocks, base, n, block_size, bases[0], via_index ? nullptr : &rb, stream);
+        if (!descs_d) {
+            fail("multi-destination read: cannot resolve the blocks");
+            return -1;
         }
-        // clusters of 4, then 2, then a plain copy for an odd destination
+        // clusters of 4, then 2; an odd last destination shares a 2-cluster with its
+        // predecessor (which is rewritten with the same bytes)
+        cudaError_t e = cudaSuccess;
         size_t r = 0;
         while (e == cudaSuccess && r < bases.size()) {
             const size_t left = bases.size() - r;
-            if (left >= 2) {
-                kernels::McastLaunch M;
-                M.descs = descs_d;
-                M.n = uint32_t(n);
-                M.bytes = uint32_t(block_size);
-                M.align_or = align_or;
-                M.ndst = left >= 4 ? 4 : 2;
-                for (int j = 0; j < M.ndst; ++j) M.delta[j] = int64_t(bases[r + j]) - int64_t(bases[0]);
-                M.status = r == 0 ? ctx->status_d : nullptr;
-                e = kernels::launch_kv_pipe_mcast(M, stream);
-                r += size_t(M.ndst);
-            } else {
-                // single leftover destination: shift the descriptors with delta through the
-                // cluster kernel's smallest form is not possible; use a 2-cluster onto the
-                // previous destination as well (idempotent rewrite of identical bytes)
-                kernels::McastLaunch M;
-                M.descs = descs_d;
-                M.n = uint32_t(n);
-                M.bytes = uint32_t(block_size);
-                M.align_or = align_or;
-                M.ndst = 2;
-                M.delta[0] = int64_t(bases[r - 1]) - int64_t(bases[0]);
-                M.delta[1] = int64_t(bases[r]) - int64_t(bases[0]);
-                e = kernels::launch_kv_pipe_mcast(M, stream);
-                r += 1;
-            }
+            kernels::McastLaunch M;
+            M.descs = descs_d;
+            M.n = uint32_t(n);
+            M.bytes = uint32_t(block_size);
+            M.align_or = align_or;
+            M.status = r == 0 ? ctx->status_d : nullptr;  // count a miss once
+            const size_t first = left >= 2 ? r : r - 1;
+            M.ndst = left >= 4 ? 4 : 2;
+            for (int j = 0; j < M.ndst; ++j)
+                M.delta[j] = int64_t(bases[first + size_t(j)]) - int64_t(bases[0]);
+            e = kernels::launch_kv_pipe_mcast(M, stream);
+            r = first + size_t(M.ndst);
             stats_.kernel_launches++;
         }
         if (e != cudaSuccess) {
@@ -1558,7 +1559,69 @@ int Connection::r_rdma_multi(const std::vector<KeyOffset>& blocks, int block_siz
         ctx->mark(stream);
         stats_.bytes_read += uint64_t(n) * uint64_t(block_size) * bases.size();
     }
-    if (!via_index) ctrl_dirty_ = true;
+    return 0;
+}
+
+// read_cache fused with the layout swizzle of the attention consumer: pages are stored
+// token-major ([tok][head][dim], as the prefill wrote them) and land head-major in a paged KV
+// cache [page][head][tok][dim]; blocks[i].offset is the destination PAGE INDEX.  The
+// transposition is done by the TMA unit (4-D tensor-map store, kernels/kv_pipe.cu).
+int Connection::r_rdma_hnd(const std::vector<KeyOffset>& blocks, int tokens, int heads, int dim,
+                           int elem_size, uint64_t base_ptr, uint64_t num_pages, int device,
+                           uint64_t stream_in) {
+    if (blocks.empty()) return 0;
+    if (device < 0 || !server_hbm_) {
+        fail("read_cache_hnd needs a CUDA destination and an HBM pool");
+        return -1;
+    }
+    const int block_size = tokens * heads * dim * elem_size;
+    for (const KeyOffset& b : blocks)
+        if (b.offset >= num_pages) {
+            fail("read_cache_hnd: page index beyond the destination tensor");
+            return -1;
+        }
+    const bool via_index = device_lookup_ && device_index_usable();
+    std::vector<RemoteBlock> rb;
+    if (!via_index) {
+        const int r = lookup_blocks(kOpReadLookup, blocks, block_size, rb);
+        if (r != 0) return r;
+    }
+    NvtxRange nvtx("istore.read_hnd");
+    std::lock_guard<std::mutex> lk(mu_);
+    DevCtx* ctx = dev_ctx(device);
+    if (!ctx) return -1;
+    DeviceGuard g(device);
+    cudaStream_t stream = ctx->pick(reinterpret_cast<cudaStream_t>(stream_in), false, streams_);
+    stats_.calls++;
+    for (size_t base = 0; base < blocks.size(); base += kMaxBatch) {
+        const size_t n = std::min(kMaxBatch, blocks.size() - base);
+        // dst_base 0: the descriptor's dst field carries the page index
+        const kernels::CopyDesc* descs_d =
+            resolve_descs(ctx, blocks, base, n, block_size, 0, via_index ? nullptr : &rb, stream);
+        if (!descs_d) {
+            fail("read_cache_hnd: cannot resolve the blocks");
+            return -1;
+        }
+        kernels::HndLaunch H;
+        H.descs = descs_d;
+        H.n = uint32_t(n);
+        H.tokens = uint32_t(tokens);
+        H.heads = uint32_t(heads);
+        H.dim = uint32_t(dim);
+        H.elem_size = uint32_t(elem_size);
+        H.dst_base = base_ptr;
+        H.num_pages = uint32_t(num_pages);
+        H.status = ctx->status_d;
+        H.max_ctas = max_ctas_;
+        const cudaError_t e = kernels::launch_kv_pipe_hnd(H, stream);
+        if (e != cudaSuccess) {
+            fail(std::string("layout-swizzling read failed to launch: ") + cudaGetErrorString(e));
+            return -1;
+        }
+        stats_.kernel_launches++;
+        ctx->mark(stream);
+        stats_.bytes_read += uint64_t(n) * uint64_t(block_size);
+    }
     return 0;
 }
 
@@ -1596,6 +1659,7 @@ int Connection::match_via_device_index(const std::vector<std::string_view>& keys
     Q.ticket = reinterpret_cast<uint32_t*>(ctx->zeros + ctx->zeros_alloc(4));
     Q.status = ctx->status_d;
     Q.want_match = true;
+    Q.accept_claimed = !exist_only;  // C3: reserved-but-uncommitted keys count for match only
     // The launch is ordered after this connection's writes on the same stream, so keys
     // written just before (even without sync) are visible, as in the reference.
     cudaStream_t stream = ctx->pick(nullptr, false, std::max(streams_, 1));
@@ -1608,9 +1672,7 @@ int Connection::match_via_device_index(const std::vector<std::string_view>& keys
     // external streams may hold this connection's writes: wait for them too
     ctx->mark(stream);
     ctx->wait_all();
-    const int32_t result = int32_t(ctx->status_h[kernels::kStatMatch]);
-    (void)exist_only;
-    return result;
+    return int32_t(ctx->status_h[kernels::kStatMatch]);
 }
 
 int Connection::drain_devices(bool* device_error) {

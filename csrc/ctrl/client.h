@@ -32,6 +32,11 @@
 
 namespace istore {
 
+namespace kernels {
+struct CopyDesc;
+}
+using kernels_CopyDesc = kernels::CopyDesc;
+
 // Non-owning: the key bytes must stay valid for the duration of the call.
 struct KeyOffset {
     std::string_view key;
@@ -135,6 +140,12 @@ class Connection {
     // crosses the fabric once and is fanned out by a thread-block cluster (TMA multicast)
     int r_rdma_multi(const std::vector<KeyOffset>& blocks, int block_size,
                      const std::vector<uint64_t>& bases, int device, uint64_t stream);
+    // read fused with the attention consumer's layout: token-major pool pages
+    // ([tokens][heads][dim]) land head-major in base_ptr = [num_pages][heads][tokens][dim];
+    // blocks[i].offset is the destination page index (TMA tensor-map store)
+    int r_rdma_hnd(const std::vector<KeyOffset>& blocks, int tokens, int heads, int dim,
+                   int elem_size, uint64_t base_ptr, uint64_t num_pages, int device,
+                   uint64_t stream);
     // fp8 KV path: pages are bf16 in the caller's tensor (`elems` elements each) and
     // e4m3 + per-128 fp32 scales in the pool (kernels::fp8_block_bytes(elems) bytes, which is
     // the size to allocate).  The cast is fused into the page mover.
@@ -191,6 +202,9 @@ class Connection {
     // them, device-index entries included
     int discard_blocks(const uint64_t* addrs, size_t count);
     uint8_t* seg_dev_ptr(DevCtx* ctx, uint32_t seg);
+    const kernels_CopyDesc* resolve_descs(DevCtx* ctx, const std::vector<KeyOffset>& blocks,
+                                          size_t base, size_t n, int block_size, uint64_t dst_base,
+                                          const std::vector<RemoteBlock>* rb, void* stream);
     int read_via_device_index(const std::vector<KeyOffset>& blocks, int block_size,
                               uint64_t base_ptr, int device, uint64_t stream, int fp8_elems = 0,
                               MoveResult* res = nullptr);

@@ -261,6 +261,11 @@ IS_HD uint32_t lowest_bit(uint32_t m) {
 // tag of way `w0` (pass w0 >= kIndexWays when none was loaded).  A rolled loop on purpose:
 // almost always one iteration, and the unrolled form cost every reader kilobytes of
 // instruction fetch on a cold kernel.
+// kAcceptClaimed: a way that a writer has claimed but not yet committed (tag == 0) counts
+// as a hit (returned with tag 0).  That is the reference's rule for get_match_last_index -
+// a key is "present" from the moment it is reserved, committed or not
+// (src/infinistore.cpp:1097) - and ONLY for it: reads and check_exist need the commit.
+template <bool kAcceptClaimed = false>
 IS_HD Found match_bucket(const IndexBucket* bk, uint64_t bi, uint32_t m, const KeyHash& kh,
                          uint32_t w0, uint32_t tag0) {
 #if defined(__CUDA_ARCH__)
@@ -270,7 +275,7 @@ IS_HD Found match_bucket(const IndexBucket* bk, uint64_t bi, uint32_t m, const K
         const uint32_t w = lowest_bit(m);
         const IndexWay* wy = &bk->way[w];
         const uint32_t tag = w == w0 ? tag0 : ld_acquire_u32(&wy->tag);
-        if (tag == 0) continue;  // claimed, not committed
+        if (!kAcceptClaimed && tag == 0) continue;  // claimed, not committed
         // all three fields in flight together: ONE round trip after the tag, not two
         const uint64_t h2 = ld_u64(&wy->h2);
         const uint64_t addr = ld_u64(&wy->addr);
@@ -286,7 +291,7 @@ IS_HD Found match_bucket(const IndexBucket* bk, uint64_t bi, uint32_t m, const K
 // the fields.  kBothAtOnce also fetches bucket B in round trip 1: a miss then costs one
 // round trip instead of two - right for get_match_last_index, which probes mostly absent
 // keys; the read path, whose keys are almost always in bucket A, skips those four loads.
-template <bool kBothAtOnce>
+template <bool kBothAtOnce, bool kAcceptClaimed = false>
 IS_HD Found find(const IndexBucket* table, uint64_t mask, const KeyHash& kh) {
     const uint64_t a = bucket_a(kh.h1, mask), b = bucket_b(kh.h1, kh.h2, mask);
     const uint32_t w0 = first_way(kh.h2);
@@ -305,14 +310,14 @@ IS_HD Found find(const IndexBucket* table, uint64_t mask, const KeyHash& kh) {
         }
         ma = match_mask(ha, kh.h1);
     }
-    const Found f = match_bucket(table + a, a, ma, kh, w0, tag0);
+    const Found f = match_bucket<kAcceptClaimed>(table + a, a, ma, kh, w0, tag0);
     if (f.slot_plus1 || b == a) return f;
     if constexpr (!kBothAtOnce) {
         uint64_t hb[kIndexWays];
         ld_fingerprints(table + b, hb);
         mb = match_mask(hb, kh.h1);
     }
-    return match_bucket(table + b, b, mb, kh, kIndexWays, 0);
+    return match_bucket<kAcceptClaimed>(table + b, b, mb, kh, kIndexWays, 0);
 }
 
 // After the copy: is the entry the reader resolved still the one in the table?

@@ -8,10 +8,12 @@
 //                         the reference's binary search over that bitmap, bit-exact on any
 //                         (also non-monotone) input;
 //   * check_exist       : the same with one key.
-// One thread per key: the key bytes are hashed twice (core/hash.h, identical on host and
-// device) and the key's two buckets of the table — which lives in the pool GPU's HBM and is
-// usually a PEER mapping read over NVLink — are searched (index.cuh).  An entry counts only
-// once its tag has been published with release semantics by the writer's kv_copy.
+// One thread per key, keys staged per warp through shared memory: the key bytes are hashed
+// twice (core/hash.h, identical on host and device) and the key's two buckets of the table -
+// which lives in the pool GPU's HBM and is usually a PEER mapping read over NVLink - are
+// searched (index.cuh).  For reads and check_exist an entry counts only once its tag has been
+// published with release semantics by the writer's kernel; get_match_last_index also counts
+// ways that a writer has claimed but not committed yet (reference visibility rule C3).
 // Also here: the eviction kernels (erase on the server side, post-copy validation on the
 // reader side).
 #include "../core/hash.h"
@@ -25,22 +27,50 @@ namespace {
 
 using namespace dev;
 
-// one warp per CTA: a batch of lookups spreads over many SMs instead of queueing hundreds of
-// fabric loads behind one SM's load unit
+// One warp per CTA: a batch of lookups spreads over many SMs instead of queueing hundreds of
+// fabric loads behind one SM's load unit.
+//
+// Key bytes usually sit in the client's pinned ring (PCIe): a thread that walked its own key
+// with serial 8-byte loads paid one PCIe round trip per 8 bytes (1.4 ms for 4096 keys in
+// round 1).  The warp's 32 keys are packed back to back, so the warp first stages their whole
+// byte range into shared memory with coalesced 8-byte loads - a handful of PCIe reads in
+// flight at once - and every thread then hashes its key from shared memory.
 constexpr int kLookupThreads = 32;
+constexpr uint32_t kStageBytes = 8192;  // shared staging per warp; longer ranges hash from global
+
+template <bool kAcceptClaimed>
+__device__ __forceinline__ idx::Found probe(const LookupLaunch& a, const KeyHash& kh) {
+    // reads resolve present keys (bucket A first), match / exist probes mostly absent ones
+    return a.present ? idx::find<true, kAcceptClaimed>(a.table, a.table_mask, kh)
+                     : idx::find<false, kAcceptClaimed>(a.table, a.table_mask, kh);
+}
+
 __global__ void __launch_bounds__(kLookupThreads)
     kv_index_lookup_kernel(const __grid_constant__ LookupLaunch a) {
-    const uint32_t i = blockIdx.x * kLookupThreads + threadIdx.x;
+    __shared__ __align__(8) uint8_t stage[kStageBytes];
+    const uint32_t first = blockIdx.x * kLookupThreads;
+    const uint32_t i = first + threadIdx.x;
+    const uint32_t last = min(first + kLookupThreads, a.n) - 1;
+    // byte range of this warp's keys (each key starts 8-byte aligned, zero padded)
+    const uint32_t lo = a.key_off[first];
+    const uint32_t hi = a.key_off[last] + ((max(a.key_len[last], 1u) + 7u) & ~7u);
+    const bool staged = hi > lo && hi - lo <= kStageBytes;
+    if (staged) {
+        const uint64_t* g = reinterpret_cast<const uint64_t*>(a.key_bytes + lo);
+        uint64_t* sm = reinterpret_cast<uint64_t*>(stage);
+        for (uint32_t w = threadIdx.x; w < (hi - lo) / 8; w += kLookupThreads) sm[w] = g[w];
+        __syncwarp();
+    }
     bool found = false;
     if (i < a.n) {
-        const KeyHash kh = hash_key(a.key_bytes + a.key_off[i], a.key_len[i]);
-        // reads resolve present keys (bucket A first), match / exist probes mostly absent ones
-        const idx::Found h = a.present ? idx::find<true>(a.table, a.table_mask, kh)
-                                       : idx::find<false>(a.table, a.table_mask, kh);
+        const uint32_t off = a.key_off[i];
+        const uint8_t* kp = staged ? stage + (off - lo) : a.key_bytes + off;
+        const KeyHash kh = hash_key(kp, a.key_len[i]);
+        const idx::Found h = a.accept_claimed ? probe<true>(a, kh) : probe<false>(a, kh);
         found = h.slot_plus1 != 0;
         if (a.out_descs) {
             uint64_t src = 0;
-            if (found && h.size >= a.need_bytes) {
+            if (found && h.tag != 0 && h.size >= a.need_bytes) {
                 const uint32_t seg = uint32_t(h.addr >> 44) - 1;
                 if (seg < a.nsegs && a.seg_base[seg])
                     src = a.seg_base[seg] + (h.addr & ((1ull << 44) - 1));

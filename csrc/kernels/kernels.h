@@ -154,6 +154,10 @@ struct LookupLaunch {
     uint32_t* status = nullptr;          // status[kStatMatch] receives the int32 result
     uint32_t* ticket = nullptr;          // zeroed u32 used to elect the last CTA
     bool want_match = false;
+    // get_match_last_index: a way claimed by a writer that has not committed yet counts as
+    // present (the reference counts reserved keys, src/infinistore.cpp:1097); never set for
+    // reads or check_exist
+    bool accept_claimed = false;
     // optional: where every hit was found, for launch_index_validate after the copy
     struct FoundAt {
         uint32_t slot_plus1;  // 0 = miss
@@ -234,6 +238,22 @@ struct McastLaunch {
     uint32_t ring_bytes = 0;
 };
 cudaError_t launch_kv_pipe_mcast(const McastLaunch& a, cudaStream_t stream);
+
+// read fused with the layout swizzle for the attention consumer: pool pages are token-major
+// [tok][head][dim]; the destination is a head-major paged KV cache [page][head][tok][dim].
+// The tile is loaded with a 1-D bulk copy and stored with a 4-D tensor-map TMA
+// (cp.async.bulk.tensor, SASS UTMASTG) that performs the transposition in hardware.
+struct HndLaunch {
+    const CopyDesc* descs = nullptr;  // src = mapped pool page (0 = miss), dst = page INDEX
+    uint32_t n = 0;
+    uint32_t tokens = 0, heads = 0, dim = 0, elem_size = 2;
+    uint64_t dst_base = 0;   // [num_pages][heads][tokens][dim]
+    uint32_t num_pages = 0;
+    uint32_t* status = nullptr;
+    int max_ctas = 0;
+    uint32_t stage_bytes = 0, ring_bytes = 0;
+};
+cudaError_t launch_kv_pipe_hnd(const HndLaunch& a, cudaStream_t stream);
 
 // One writer -> all readers replication through an NVLS multicast mapping (multimem.st).
 struct BcastLaunch {

@@ -29,6 +29,8 @@
 // own destination (the same KV page wanted by several TP ranks / beams).  Slots are handed
 // back to the leader with remote mbarrier arrivals (DSMEM), the cluster barrier closes the
 // kernel.  NVLink bytes: 1x instead of Kx.
+#include <cuda.h>  // CUtensorMap + enums only: the encoder is fetched through cudart at run time
+
 #include <algorithm>
 #include <cstring>
 #include <mutex>
@@ -427,6 +429,90 @@ __global__ void __launch_bounds__(64)
     cluster_sync_all();  // nobody leaves while a sibling may still arrive on its barriers
 }
 
+// ---------------------------------------------------------------- kv_pipe_hnd (layout swizzle)
+// read_cache fused with the layout change the attention consumer wants: pool pages are
+// token-major, [tok][head][dim]; the destination KV cache is head-major, [page][head][tok][dim]
+// (contiguous per head: what a paged-attention kernel streams).  The tile is loaded with one
+// 1-D bulk copy (the pool page is contiguous) and STORED with a 4-D tensor-map TMA whose
+// dimensions are declared in the order (dim, head, tok, page): the box (D, H, Tt, 1) then
+// enumerates shared memory as [tok][head][dim] - exactly the source order - while the tensor
+// map's strides scatter every (tok, head) row to its head-major place.  The transposition is
+// done by the TMA unit: no thread touches the data, no separate pack/unpack kernel.
+//   SASS: UBLKCP.S.G (load) + UTMASTG.4D (store).
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src,
+                                             int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::
+            "l"(reinterpret_cast<uint64_t>(map)),
+        "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(smem_src))
+        : "memory");
+}
+
+struct HndArgs {
+    const CopyDesc* descs;  // src = pool page (mapped), dst = destination page index
+    uint32_t n;
+    uint32_t page_bytes;   // T * H * D * elem_size
+    uint32_t tile_bytes;   // Tt * H * D * elem_size (one ring slot)
+    uint32_t tile_tokens;  // Tt
+    uint32_t stages;
+    uint32_t* status;
+};
+
+__global__ void __launch_bounds__(64)
+    kv_pipe_hnd_kernel(const __grid_constant__ CUtensorMap tmap, const HndArgs a) {
+    extern __shared__ __align__(128) uint8_t ring[];
+    __shared__ __align__(8) uint64_t full[kPipeMaxStages];
+    __shared__ __align__(8) uint64_t empty[kPipeMaxStages];
+    const uint32_t grid = gridDim.x;
+    const uint32_t nitems = blockIdx.x < a.n ? (a.n - blockIdx.x + grid - 1) / grid : 0;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < a.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_fence_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+    }
+    __syncthreads();
+    const Shape sh{a.n, a.page_bytes, a.page_bytes, 1, a.tile_bytes, a.stages};
+    DescWindow<false> win{a.descs, nullptr, blockIdx.x, grid, 1, nitems, lane};
+    win.init();
+    if (warp == 0) {
+        loader_body(sh, blockIdx.x, grid, nitems, lane, ring, full, empty,
+                    [&](uint32_t k) { return win.at(k); });
+        return;
+    }
+    uint32_t s = 0, ph = 0, sf = 0, q = 0;
+    for (uint32_t k = 0; k < nitems; ++k) {
+        const CopyDesc d = win.at(k);
+        if (lane == 0 && d.src == 0 && a.status) atomicAdd(a.status + kStatMiss, 1u);
+        uint32_t t0 = 0;
+        for (uint32_t o = 0; o < a.page_bytes; o += a.tile_bytes, t0 += a.tile_tokens, ++q) {
+            if (lane == 0) {
+                mbar_wait(&full[s], ph);
+                if (d.src)  // box (D, H, Tt, 1) at (0, 0, t0, page): tokens beyond T are clipped
+                    tma_store_4d(&tmap, ring + size_t(s) * a.tile_bytes, 0, 0, int32_t(t0),
+                                 int32_t(d.dst));
+                bulk_commit();
+                bulk_wait_read<kStoreLag>();
+                if (q >= uint32_t(kStoreLag)) {
+                    mbar_arrive(&empty[sf]);
+                    if (++sf == a.stages) sf = 0;
+                }
+            }
+            if (++s == a.stages) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+    }
+    if (lane == 0) {
+        bulk_wait<0>();
+        fence_proxy_async();
+    }
+}
+
 std::mutex g_pipe_attr_mu;
 bool g_pipe_attr_set[64] = {false};
 
@@ -450,9 +536,32 @@ cudaError_t ensure_pipe_attrs() {
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(kv_pipe_mcast_kernel<4>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kv_pipe_hnd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kMax);
     if (e != cudaSuccess) return e;
     g_pipe_attr_set[dev] = true;
     return cudaSuccess;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup: the module links
+// cudart statically and must import on hosts without libcuda (CPU-only CI).
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q{};
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) !=
+                cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
 }
 
 }  // namespace
@@ -532,6 +641,57 @@ cudaError_t launch_kv_pipe_read(const ReadFusedLaunch& a, cudaStream_t stream) {
     r.status = a.status;
     const Shape sh{a.n, a.bytes, a.bytes, 1, g.stage_bytes, g.stages};
     kv_pipe_read_kernel<<<ctas, kPipeThreads, g.smem, stream>>>(r, sh);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kv_pipe_hnd(const HndLaunch& a, cudaStream_t stream) {
+    if (a.n == 0) return cudaSuccess;
+    const uint64_t row = uint64_t(a.dim) * a.elem_size;          // one (tok, head) row
+    const uint64_t tok_bytes = row * a.heads;                      // one token of a pool page
+    const uint64_t page_bytes = tok_bytes * a.tokens;
+    if (!a.tokens || !a.heads || !a.dim || a.dim > 256 || a.heads > 256 || row % 16 ||
+        (a.elem_size != 1 && a.elem_size != 2 && a.elem_size != 4) || page_bytes > (1ull << 30) ||
+        (a.dst_base & 15) || !a.num_pages)
+        return cudaErrorInvalidValue;
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (!encode) return cudaErrorNotSupported;
+    cudaError_t e = ensure_pipe_attrs();
+    if (e != cudaSuccess) return e;
+    // ring slot = as many whole tokens as fit 16 KB (at least one), box dims are <= 256
+    const uint32_t stage_cap = a.stage_bytes ? a.stage_bytes : (16u << 10);
+    uint32_t tt = uint32_t(std::max<uint64_t>(1, stage_cap / tok_bytes));
+    tt = std::min<uint32_t>({tt, a.tokens, 256u});
+    const uint32_t tile_bytes = uint32_t(tt * tok_bytes);
+    if (tile_bytes > (96u << 10)) return cudaErrorInvalidValue;  // one token must fit a slot
+    const uint32_t ring = a.ring_bytes ? a.ring_bytes : (128u << 10);
+    const uint32_t stages = std::max<uint32_t>(kStoreLag + 1,
+                                               std::min<uint32_t>(kPipeMaxStages, ring / tile_bytes));
+    CUtensorMap tmap;
+    const CUtensorMapDataType dt = a.elem_size == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
+                                   : a.elem_size == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32
+                                                      : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    // destination [page][head][tok][dim], declared as (dim, head, tok, page)
+    const cuuint64_t gdim[4] = {a.dim, a.heads, a.tokens, a.num_pages};
+    const cuuint64_t gstr[3] = {uint64_t(a.tokens) * row, row, page_bytes};
+    const cuuint32_t box[4] = {a.dim, a.heads, tt, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (encode(&tmap, dt, 4, reinterpret_cast<void*>(a.dst_base), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+    HndArgs h{};
+    h.descs = a.descs;
+    h.n = a.n;
+    h.page_bytes = uint32_t(page_bytes);
+    h.tile_bytes = tile_bytes;
+    h.tile_tokens = tt;
+    h.stages = stages;
+    h.status = a.status;
+    const size_t smem = size_t(stages) * tile_bytes;
+    const int resident = (smem > (110u << 10) ? 1 : 2) * sm_count();
+    int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, resident) : sm_count();
+    ctas = int(std::min<uint32_t>(uint32_t(ctas), a.n));
+    kv_pipe_hnd_kernel<<<ctas, 64, smem, stream>>>(tmap, h);
     return cudaGetLastError();
 }
 

@@ -429,6 +429,19 @@ PYBIND11_MODULE(_infinistore, m) {
             py::arg("blocks"), py::arg("block_size"), py::arg("bases"), py::arg("device") = -1,
             py::arg("stream") = 0, py::arg("scale") = 1)
         .def(
+            "r_rdma_hnd",
+            [](Connection& c, const py::object& blocks, int tokens, int heads, int dim,
+               int elem_size, uint64_t base_ptr, uint64_t num_pages, int device, uint64_t stream) {
+                std::vector<KeyOffset> kb;
+                blocks_list_from_py(blocks, 1, kb);  // (key, page index)
+                py::gil_scoped_release rel;
+                return c.r_rdma_hnd(kb, tokens, heads, dim, elem_size, base_ptr, num_pages, device,
+                                    stream);
+            },
+            py::arg("blocks"), py::arg("tokens"), py::arg("heads"), py::arg("dim"),
+            py::arg("elem_size"), py::arg("base_ptr"), py::arg("num_pages"),
+            py::arg("device") = -1, py::arg("stream") = 0)
+        .def(
             "r_rdma_async",
             [](Connection& c, const py::object& blocks, int block_size, uint64_t base_ptr,
                py::function cb, int device, uint64_t stream, uint64_t scale) {
@@ -744,13 +757,40 @@ PYBIND11_MODULE(_infinistore, m) {
         py::arg("stage_bytes") = 0, py::arg("ring_bytes") = 0,
         "one pool block -> 2 or 4 destinations through a thread-block cluster (TMA multicast)");
     k.def(
+        "kv_pipe_hnd",
+        [](uint64_t descs, uint32_t n, uint32_t tokens, uint32_t heads, uint32_t dim,
+           uint32_t elem_size, uint64_t dst_base, uint32_t num_pages, int max_ctas, uint64_t stream,
+           uint64_t status, uint32_t stage_bytes, uint32_t ring_bytes) {
+            kernels::HndLaunch H;
+            H.descs = as_ptr<const kernels::CopyDesc>(descs);
+            H.n = n;
+            H.tokens = tokens;
+            H.heads = heads;
+            H.dim = dim;
+            H.elem_size = elem_size;
+            H.dst_base = dst_base;
+            H.num_pages = num_pages;
+            H.max_ctas = max_ctas;
+            H.status = as_ptr<uint32_t>(status);
+            H.stage_bytes = stage_bytes;
+            H.ring_bytes = ring_bytes;
+            const cudaError_t e = kernels::launch_kv_pipe_hnd(H, as_ptr<CUstream_st>(stream));
+            if (e != cudaSuccess) throw std::runtime_error(cudaGetErrorString(e));
+        },
+        py::arg("descs"), py::arg("n"), py::arg("tokens"), py::arg("heads"), py::arg("dim"),
+        py::arg("elem_size"), py::arg("dst_base"), py::arg("num_pages"), py::arg("max_ctas") = 0,
+        py::arg("stream") = 0, py::arg("status") = 0, py::arg("stage_bytes") = 0,
+        py::arg("ring_bytes") = 0,
+        "token-major pages -> head-major paged KV cache; transposition by a 4-D TMA tensor store");
+    k.def(
         "index_lookup",
         [](uint64_t key_bytes, uint64_t key_off, uint64_t key_len, uint32_t n, uint64_t table,
            uint64_t table_mask, const std::vector<uint64_t>& seg_base, uint64_t out_descs,
            uint64_t dst_off, uint64_t dst_base, uint32_t need_bytes, uint64_t present,
            uint64_t status, uint64_t ticket, bool want_match, uint64_t stream,
-           uint64_t found_at) {
+           uint64_t found_at, bool accept_claimed) {
             kernels::LookupLaunch Q;
+            Q.accept_claimed = accept_claimed;
             Q.found_at = as_ptr<kernels::LookupLaunch::FoundAt>(found_at);
             Q.key_bytes = as_ptr<const uint8_t>(key_bytes);
             Q.key_off = as_ptr<const uint32_t>(key_off);
@@ -776,7 +816,7 @@ PYBIND11_MODULE(_infinistore, m) {
         py::arg("out_descs") = 0, py::arg("dst_off") = 0, py::arg("dst_base") = 0,
         py::arg("need_bytes") = 0, py::arg("present") = 0, py::arg("status") = 0,
         py::arg("ticket") = 0, py::arg("want_match") = false, py::arg("stream") = 0,
-        py::arg("found_at") = 0);
+        py::arg("found_at") = 0, py::arg("accept_claimed") = false);
     k.def(
         "index_validate",
         [](uint64_t found_at, uint32_t n, uint64_t table, uint64_t status, uint64_t stream) {

@@ -548,6 +548,26 @@ class InfinityConnection:
         if ret < 0:
             raise Exception(f"Failed to read to infinistore, ret = {ret}")
 
+    def read_cache_hnd(self, cache: torch.Tensor, blocks: List[Tuple[str, int]], stream="current"):
+        """Read pages into a HEAD-MAJOR paged KV cache, fused with the layout change.
+
+        ``cache`` is a contiguous CUDA tensor ``[num_pages, heads, tokens, dim]`` (what a
+        paged-attention kernel streams per head); the pages were written token-major,
+        ``[tokens, heads, dim]`` per page (how prefill produces them).  ``blocks`` is a list of
+        ``(key, page_index)``.  The transposition happens inside the read kernel - a 4-D
+        tensor-map TMA store - so no separate permute/pack kernel runs and the page crosses
+        HBM once.  The reference moves opaque bytes only (infinistore/lib.py:377-379)."""
+        if not self.rdma_connected:
+            raise Exception("this function is only valid for connected rdma")
+        info = self._info(cache)
+        if info.dev < 0 or cache.dim() != 4:
+            raise Exception("read_cache_hnd takes a CUDA tensor [num_pages, heads, tokens, dim]")
+        pages, heads, tokens, dim = cache.shape
+        ret = self.conn.r_rdma_hnd(blocks, tokens, heads, dim, info.es, info.ptr, pages, info.dev,
+                                   self._stream(info, cache, stream))
+        if ret < 0:
+            raise Exception(f"Failed to read to infinistore, ret = {ret}: {self.conn.last_error()}")
+
     async def read_cache_async(self, cache: torch.Tensor, blocks: List[Tuple[str, int]],
                                page_size: int, stream="current"):
         if not self.rdma_connected:

@@ -42,7 +42,7 @@ def make_descs(src_ptrs: Sequence[int], dst_ptrs: Sequence[int], device) -> torc
 def kv_copy(descs: torch.Tensor, nbytes: int, variant: str = "auto", max_ctas: int = 0,
             publish: Optional["PublishArgs"] = None, status: Optional[torch.Tensor] = None,
             align_or: int = 0, stage_bytes: int = 0, ring_bytes: int = 0,
-            all_local: bool = False) -> None:
+            all_local: bool = False, debug: int = 0) -> None:
     """Move descs.shape[0] blocks of `nbytes` bytes.  ``variant``: "auto" / "tma" = the
     warp-specialised TMA pipeline (csrc/kernels/kv_pipe.cu; ``stage_bytes`` / ``ring_bytes``
     set its ring geometry), "ldst" / "ldst256" = csrc/kernels/kv_copy.cu."""
@@ -54,7 +54,7 @@ def kv_copy(descs: torch.Tensor, nbytes: int, variant: str = "auto", max_ctas: i
                   publish.table.data_ptr() if publish else 0,
                   publish.mask if publish else 0,
                   publish.done.data_ptr() if publish else 0,
-                  status.data_ptr() if status is not None else 0, align_or, 0, all_local, 0,
+                  status.data_ptr() if status is not None else 0, align_or, 0, all_local, debug,
                   stage_bytes, ring_bytes)
 
 
@@ -71,6 +71,21 @@ def kv_copy_multicast(descs: torch.Tensor, nbytes: int, dst_deltas: Sequence[int
         K.kv_pipe_mcast(descs.data_ptr(), descs.shape[0], nbytes, [int(d) for d in dst_deltas],
                         max_clusters, _stream(descs.device),
                         status.data_ptr() if status is not None else 0, stage_bytes, ring_bytes)
+
+
+def kv_read_swizzle_hnd(descs: torch.Tensor, dst: torch.Tensor, tokens: int, heads: int,
+                        dim: int, max_ctas: int = 0, status: Optional[torch.Tensor] = None,
+                        stage_bytes: int = 0, ring_bytes: int = 0) -> None:
+    """Pages stored token-major ([tokens][heads][dim], descs[i].src) -> the head-major paged KV
+    cache ``dst`` of shape [num_pages][heads][tokens][dim]; descs[i].dst is the PAGE INDEX.
+    One 1-D bulk load per tile, one 4-D tensor-map TMA store (``cp.async.bulk.tensor``, SASS
+    ``UTMASTG``) that does the transposition (csrc/kernels/kv_pipe.cu: kv_pipe_hnd)."""
+    assert dst.is_cuda and dst.is_contiguous() and dst.dim() == 4
+    assert tuple(dst.shape[1:]) == (heads, tokens, dim)
+    with torch.cuda.device(descs.device):
+        K.kv_pipe_hnd(descs.data_ptr(), descs.shape[0], tokens, heads, dim, dst.element_size(),
+                      dst.data_ptr(), dst.shape[0], max_ctas, _stream(descs.device),
+                      status.data_ptr() if status is not None else 0, stage_bytes, ring_bytes)
 
 
 class PublishArgs:
@@ -115,8 +130,11 @@ def pack_keys(keys: Sequence[bytes], device) -> Tuple[torch.Tensor, torch.Tensor
 
 def index_lookup(table: torch.Tensor, keys: Sequence[bytes], seg_base: Sequence[int] = (),
                  dst_base: int = 0, dst_off: Optional[Sequence[int]] = None, need_bytes: int = 0,
-                 want_match: bool = False, found_at: Optional[torch.Tensor] = None):
+                 want_match: bool = False, found_at: Optional[torch.Tensor] = None,
+                 accept_claimed: bool = False):
     """Probe `table` for `keys`.  Returns (descs | None, present bitmap, match index | None).
+    `accept_claimed`: ways claimed by a writer that has not committed yet count as present
+    (the reference's rule for get_match_last_index; never for reads).
     `found_at` ((n, 2) int32, optional) receives (slot + 1, tag) of every hit for
     :func:`index_validate`."""
     dev = table.device
@@ -134,7 +152,8 @@ def index_lookup(table: torch.Tensor, keys: Sequence[bytes], seg_base: Sequence[
                        list(seg_base), descs.data_ptr() if descs is not None else 0,
                        doff.data_ptr() if doff is not None else 0, dst_base, need_bytes,
                        present.data_ptr(), status.data_ptr(), ticket.data_ptr(), want_match,
-                       _stream(dev), found_at.data_ptr() if found_at is not None else 0)
+                       _stream(dev), found_at.data_ptr() if found_at is not None else 0,
+                       accept_claimed)
     match = None
     if want_match:
         torch.cuda.synchronize(dev)

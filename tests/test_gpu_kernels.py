@@ -318,3 +318,84 @@ def test_fp8_write_matches_fp32_reference(elems):
 
 def test_fp8_roundtrip_helper():
     _ops().fp8_roundtrip_check(torch.device(DEV))
+
+
+def test_match_counts_claimed_but_uncommitted_keys_and_reads_do_not():
+    """Reference rule C3 (src/infinistore.cpp:1080,1097): a key counts for
+    get_match_last_index from the moment it is reserved; check_exist and reads need the
+    commit.  debug=4 stops the write kernel right before the tag store (claimed, tag == 0)."""
+    ops = _ops()
+    n, nbytes = 64, 4096
+    keys = [b"c3/%03d" % i for i in range(n)]
+    pool = torch.zeros((n, nbytes), dtype=torch.uint8, device=DEV)
+    src = torch.randint(0, 255, (n, nbytes), dtype=torch.uint8, device=DEV)
+    table = ops.new_index_table(512, DEV)
+    addrs = [(1 << 44) | (i * nbytes) for i in range(n)]
+    half = n // 2
+    wd = ops.make_descs([src[i].data_ptr() for i in range(n)],
+                        [pool[i].data_ptr() for i in range(n)], DEV)
+    # first half committed, second half claimed only
+    ops.kv_copy(wd[:half].contiguous(), nbytes, variant="ldst",
+                publish=ops.PublishArgs(table, keys[:half], addrs[:half], list(range(1, half + 1)), nbytes))
+    ops.kv_copy(wd[half:].contiguous(), nbytes, variant="ldst", debug=4,
+                publish=ops.PublishArgs(table, keys[half:], addrs[half:],
+                                        list(range(half + 1, n + 1)), nbytes))
+    torch.cuda.synchronize()
+    query = keys + [b"c3/absent"]
+    _, present, match = ops.index_lookup(table, query, want_match=True)
+    assert ops.presence_bits(present, len(query)) == [True] * half + [False] * (half + 1)
+    assert match == half - 1
+    _, present, match = ops.index_lookup(table, query, want_match=True, accept_claimed=True)
+    assert ops.presence_bits(present, len(query)) == [True] * n + [False]
+    assert match == n - 1
+    # a read never resolves a claimed-only way, whatever the flag
+    descs, _, _ = ops.index_lookup(table, query, seg_base=[pool.data_ptr()], dst_base=0,
+                                   dst_off=[0] * len(query), need_bytes=nbytes, accept_claimed=True)
+    d = descs.cpu().numpy().view(np.uint64)
+    assert (d[:half, 0] != 0).all() and (d[half:, 0] == 0).all()
+
+
+def test_lookup_stages_long_and_odd_keys():
+    """Keys of 1..700 bytes: the warp stages its keys through shared memory when they fit
+    (8 KB) and hashes from global memory otherwise; both must agree with the host hash."""
+    ops = _ops()
+    lens = [1, 7, 8, 9, 36, 63, 64, 65, 255, 256, 257, 700] * 6
+    keys = [(b"k%03d-" % i) + bytes([65 + (i * 7 + j) % 26 for j in range(max(0, L - 5))])
+            for i, L in enumerate(lens)]
+    keys = [k[:L] if len(k) > L else k for k, L in zip(keys, lens)]
+    n = len(keys)
+    pool = torch.zeros(64, dtype=torch.uint8, device=DEV)
+    table = ops.new_index_table(1024, DEV)
+    pub_keys = keys[::2]
+    wd = ops.make_descs([pool.data_ptr()] * len(pub_keys), [pool.data_ptr()] * len(pub_keys), DEV)
+    ops.kv_copy(wd, 64, publish=ops.PublishArgs(table, pub_keys, [(1 << 44)] * len(pub_keys),
+                                                list(range(1, len(pub_keys) + 1)), 64))
+    torch.cuda.synchronize()
+    _, present, _ = ops.index_lookup(table, keys)
+    want = [k in set(pub_keys) for k in keys]
+    assert ops.presence_bits(present, n) == want
+
+
+@pytest.mark.parametrize("tokens,heads,dim,dtype", [(128, 8, 128, torch.bfloat16),
+                                                     (64, 4, 64, torch.float16),
+                                                     (100, 8, 128, torch.bfloat16),
+                                                     (16, 2, 256, torch.float32)])
+def test_read_fused_with_layout_swizzle_matches_torch_permute(tokens, heads, dim, dtype):
+    """kv_pipe_hnd: token-major pages -> head-major paged KV cache with a TMA tensor store;
+    reference: page.view(T, H, D).permute(1, 0, 2)."""
+    ops = _ops()
+    npages, nsel = 40, 25
+    g = torch.Generator(device=DEV).manual_seed(tokens * heads)
+    pool = torch.randn((npages, tokens, heads, dim), device=DEV, generator=g).to(dtype)
+    dst = torch.zeros((npages, heads, tokens, dim), device=DEV, dtype=dtype)
+    sel = torch.randperm(npages, generator=torch.Generator().manual_seed(9))[:nsel].tolist()
+    where = torch.randperm(npages, generator=torch.Generator().manual_seed(10))[:nsel].tolist()
+    descs = ops.make_descs([pool[s].data_ptr() for s in sel], where, DEV)
+    status = torch.zeros(8, dtype=torch.int32, device=DEV)
+    ops.kv_read_swizzle_hnd(descs, dst, tokens, heads, dim, status=status)
+    torch.cuda.synchronize()
+    ref = torch.zeros_like(dst)
+    for s, w in zip(sel, where):
+        ref[w] = pool[s].permute(1, 0, 2)
+    assert torch.equal(dst, ref)
+    assert int(status[0]) == 0

@@ -360,3 +360,29 @@ def test_dead_writer_leaves_no_device_index_entry(hbm_server):
     reader2.read_cache(dst, [("orphaned", 0)], 8192)
     reader2.sync()
     assert torch.equal(dst, src2)
+
+
+@pytest.mark.parametrize("device_lookup", [True, False])
+def test_read_cache_hnd_swizzles_pages_for_the_attention_consumer(hbm_server, device_lookup):
+    """Pages written token-major come back head-major ([page][head][tok][dim]) in one read
+    kernel (TMA tensor store); torch reference: permute."""
+    _, port = hbm_server
+    conn = make_conn(port, device_lookup=device_lookup)
+    npages, tokens, heads, dim = 48, 128, 8, 128
+    src = torch.randn((npages, tokens, heads, dim), device="cuda:0").to(torch.bfloat16)
+    conn.register_mr(src)
+    page = tokens * heads * dim
+    keys = [rand_key(16) for _ in range(npages)]
+    conn.rdma_write_cache(src, [i * page for i in range(npages)], page,
+                          conn.allocate_rdma(keys, page * 2))
+    conn.sync()
+    dst = torch.zeros((npages, heads, tokens, dim), device="cuda:0", dtype=torch.bfloat16)
+    where = list(range(npages))
+    random.Random(3).shuffle(where)
+    conn.read_cache_hnd(dst, [(keys[i], where[i]) for i in range(npages)])
+    conn.sync()
+    ref = torch.empty_like(dst)
+    ref[where] = src.permute(0, 2, 1, 3)
+    assert torch.equal(dst, ref)
+    with pytest.raises(Exception):
+        conn.read_cache_hnd(dst, [(keys[0], npages)])  # page index out of range
