@@ -517,9 +517,11 @@ def main():
                      base_port=base_port + 100, barrier=barrier, allmax=allmax, allsum=allsum,
                      allmin=allmin)
         extra = {}
+        barrier()
         server.purge()
+        barrier()
         try:
-            extra["latency_us"] = xc.latency(ctx, conn)
+            extra["latency_us"] = xc.latency(ctx, base_port + peer)
         except Exception as e:  # noqa: BLE001
             extra["latency_us"] = {"error": repr(e)[:300]}
         try:

@@ -80,40 +80,49 @@ def _client(ctx: Ctx, port: int, **kw):
 
 
 # --------------------------------------------------------------------------- latency
-def latency(ctx: Ctx, conn, sizes_kb=(4, 128, 1024), samples=200):
-    """One block written (or read) + sync(): p50 / p99 in microseconds, per block size, over
-    the ring peer (NVLink for N >= 2, local HBM at N = 1).  Host clock around the call pair -
-    this IS a host-visible latency - max over ranks of each percentile."""
-    out = {}
-    for kb in sizes_kb:
-        elems = kb * 1024 // 2
-        src = torch.randn(elems, device=ctx.dev).to(torch.bfloat16)
-        dst = torch.zeros_like(src)
-        conn.register_mr(src)
-        conn.register_mr(dst)
-        keys = [f"lat-{kb}-{ctx.rank}-{uuid.uuid4().hex[:8]}-{i}" for i in range(samples + 20)]
-        remote = conn.allocate_rdma(keys, kb * 1024)
-        tw, tr = [], []
-        for i, k in enumerate(keys):
-            t0 = time.perf_counter()
-            conn.rdma_write_cache(src, [0], elems, remote[i:i + 1])
-            conn.sync()
-            t1 = time.perf_counter()
-            conn.read_cache(dst, [(k, 0)], elems)
-            conn.sync()
-            t2 = time.perf_counter()
-            if i >= 20:
-                tw.append((t1 - t0) * 1e6)
-                tr.append((t2 - t1) * 1e6)
-        tw.sort()
-        tr.sort()
-        assert torch.equal(src, dst)
-        q = lambda v, p: v[min(len(v) - 1, int(p * len(v)))]  # noqa: E731
-        out[f"{kb}KB"] = {"write_sync_p50": round(ctx.allmax(q(tw, 0.5)), 1),
-                          "write_sync_p99": round(ctx.allmax(q(tw, 0.99)), 1),
-                          "read_sync_p50": round(ctx.allmax(q(tr, 0.5)), 1),
-                          "read_sync_p99": round(ctx.allmax(q(tr, 0.99)), 1)}
-    out["path"] = "NVLink (ring peer)" if ctx.world > 1 else "local HBM"
+def latency(ctx: Ctx, port: int, sizes_kb=(4, 128, 1024), samples=200):
+    """One block written (or read) + sync(): p50 / p99 in microseconds per block size, against
+    the store on `port` (the ring peer: NVLink for N >= 2, local HBM at N = 1).  Host clock
+    around the call pair - this IS a host-visible latency - max over ranks of each
+    percentile.  Two sync() flavours: "strict" (default: control-plane round trip, every
+    client sees the write when sync() returns) and "posted" (ClientConfig(posted_commit=True):
+    one-way commit like the reference's COMMIT SEND; device-path readers see the write at
+    once through the in-band commit)."""
+    out = {"path": "NVLink (ring peer)" if ctx.world > 1 else "local HBM"}
+    q = lambda v, p: v[min(len(v) - 1, int(p * len(v)))]  # noqa: E731
+    for mode in ("strict", "posted"):
+        conn = _client(ctx, port, posted_commit=(mode == "posted"))
+        res = {}
+        for kb in sizes_kb:
+            elems = kb * 1024 // 2
+            src = torch.randn(elems, device=ctx.dev).to(torch.bfloat16)
+            dst = torch.zeros_like(src)
+            conn.register_mr(src)
+            conn.register_mr(dst)
+            keys = [f"lat-{mode}-{kb}-{ctx.rank}-{uuid.uuid4().hex[:8]}-{i}"
+                    for i in range(samples + 20)]
+            remote = conn.allocate_rdma(keys, kb * 1024)
+            tw, tr = [], []
+            for i, k in enumerate(keys):
+                t0 = time.perf_counter()
+                conn.rdma_write_cache(src, [0], elems, remote[i:i + 1])
+                conn.sync()
+                t1 = time.perf_counter()
+                conn.read_cache(dst, [(k, 0)], elems)
+                conn.sync()
+                t2 = time.perf_counter()
+                if i >= 20:
+                    tw.append((t1 - t0) * 1e6)
+                    tr.append((t2 - t1) * 1e6)
+            tw.sort()
+            tr.sort()
+            assert torch.equal(src, dst)
+            res[f"{kb}KB"] = {"write_sync_p50": round(ctx.allmax(q(tw, 0.5)), 1),
+                              "write_sync_p99": round(ctx.allmax(q(tw, 0.99)), 1),
+                              "read_sync_p50": round(ctx.allmax(q(tr, 0.5)), 1),
+                              "read_sync_p99": round(ctx.allmax(q(tr, 0.99)), 1)}
+        out[mode] = res
+        conn.close()
     return out
 
 
@@ -469,9 +478,7 @@ def main():
     else:
         srv = start_shard_server(ctx.local, ctx.base_port + ctx.rank, 1 << 30, granule_kb=16)
         ctx.barrier()
-        conn = _client(ctx, ctx.base_port + (ctx.rank + 1) % ctx.world)
-        res = latency(ctx, conn)
-        conn.close()
+        res = latency(ctx, ctx.base_port + (ctx.rank + 1) % ctx.world)
         ctx.barrier()
         srv.stop()
     if ctx.rank == 0:

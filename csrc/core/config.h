@@ -48,6 +48,14 @@ struct ClientConfig {
     int device = -1;          // CUDA ordinal the client launches kernels on (-1: decide per tensor)
     int timeout_ms = 10000;   // per-request deadline on the control plane
     int pool_hint = -1;       // preferred pool segment device for allocations (-1 = any)
+    // sync() and the server's host-side map.  false (default): sync() ends with a SYNC round
+    // trip, so when it returns every client - also one that asks the SERVER - sees the writes.
+    // true: the commit list is POSTED (one-way, like the reference's COMMIT SEND,
+    // src/libinfinistore.cpp:362-395) and sync() returns once the kernels have finished; the
+    // writes are already visible to every device-path reader (in-band commit in the HBM
+    // index), server-mediated lookups of other connections follow within the TCP delivery
+    // time.  Saves the control-plane round trip: the single-block write latency.
+    bool posted_commit = false;
 };
 
 }  // namespace istore

@@ -247,9 +247,24 @@ struct Connection::DevCtx {
         if (zeros) cudaFree(zeros);
     }
 
+    // Completion of everything launched so far.  A blocking cudaStreamSynchronize sleeps on an
+    // interrupt (+5..10 us for a transfer that itself takes 10 us); short transfers are
+    // therefore polled with cudaStreamQuery for a bounded time first.
     void wait_all() {
         DeviceGuard g(device);
-        for (cudaStream_t s : busy) cudaStreamSynchronize(s);
+        for (cudaStream_t s : busy) {
+            bool done = false;
+            const uint64_t t0 = now_ns();
+            for (int spin = 0; spin < 4096; ++spin) {
+                const cudaError_t q = cudaStreamQuery(s);
+                if (q != cudaErrorNotReady) {  // finished, or failed: let synchronize report it
+                    done = q == cudaSuccess;
+                    break;
+                }
+                if ((spin & 15) == 15 && now_ns() - t0 > 60000) break;  // 60 us: not a short one
+            }
+            if (!done) cudaStreamSynchronize(s);
+        }
         busy.clear();
         dirty = false;
     }
@@ -569,6 +584,31 @@ int Connection::sync_local() {
         if (quiet && async_idle) {
             const int drained = drain_devices();
             return drained != 0 ? drained : 0;
+        }
+    }
+    if (cfg_.posted_commit) {
+        bool leases;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            leases = ctrl_dirty_;
+        }
+        if (!leases) {
+            // Posted commit: wait for the kernels, then send the commit list one-way.  The
+            // blocks are already visible to device-path readers (in-band commit); the server's
+            // map follows when the message arrives - no round trip on the caller's path.
+            std::vector<uint64_t> mine;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                mine.swap(pending_commit_);
+            }
+            bool device_error = false;
+            const int drained = drain_devices(&device_error);
+            if (device_error) {
+                (void)discard_blocks(mine.data(), mine.size());
+                return -1;
+            }
+            if (!mine.empty() && send_commit(mine.data(), mine.size()) != 0) return -1;
+            return drained;
         }
     }
     // The commit list is taken BEFORE waiting for the GPU, so it names only blocks whose

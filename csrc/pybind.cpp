@@ -289,7 +289,8 @@ PYBIND11_MODULE(_infinistore, m) {
         .def_readwrite("link_type", &ClientConfig::link_type)
         .def_readwrite("device", &ClientConfig::device)
         .def_readwrite("timeout_ms", &ClientConfig::timeout_ms)
-        .def_readwrite("pool_hint", &ClientConfig::pool_hint);
+        .def_readwrite("pool_hint", &ClientConfig::pool_hint)
+        .def_readwrite("posted_commit", &ClientConfig::posted_commit);
 
     py::class_<ServerConfig>(m, "ServerConfig")
         .def(py::init<>())

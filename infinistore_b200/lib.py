@@ -51,7 +51,10 @@ class ClientConfig(_infinistore.ClientConfig):
     for the caller's stream, so their fixed head/tail latencies overlap; completion is
     established by ``sync()`` as in the reference.  0: launch in the caller's stream
     itself, e.g. for CUDA-graph capture or when later work on that stream must see the
-    result without a ``sync()``).
+    result without a ``sync()``).  ``posted_commit`` (default False): ``sync()`` posts the
+    commit list one-way instead of waiting for a control-plane round trip - the writes are
+    visible to every device-path reader when it returns (in-band commit), server-mediated
+    lookups of OTHER connections follow within the TCP delivery time, as in the reference.
     """
 
     def __init__(self, **kwargs):
@@ -73,6 +76,7 @@ class ClientConfig(_infinistore.ClientConfig):
         self.copy_variant = kwargs.get("copy_variant", "auto")
         self.max_ctas = kwargs.get("max_ctas", 0)
         self.streams = kwargs.get("streams", 4)
+        self.posted_commit = bool(kwargs.get("posted_commit", False))
 
     def __repr__(self):
         return (

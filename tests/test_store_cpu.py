@@ -899,3 +899,28 @@ def test_randomised_soak_against_a_model(seed):
     r = subprocess.run([_sys.executable, os.path.join(ROOT, "tools", "soak_cpu.py"), str(seed),
                         "120", "2000"], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and " OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_posted_commit_skips_the_round_trip_and_still_commits(host_server):
+    """posted_commit=True: sync() sends the commit list one-way (reference semantics); the
+    same connection sees its writes at once (TCP order), other connections shortly after."""
+    srv, port = host_server
+    conn = make_conn(port, posted_commit=True)
+    src = torch.randn(4 * 1024)
+    conn.register_mr(src)
+    keys = [f"posted-{i}" for i in range(4)]
+    before = conn.stats()["ctrl_requests"]
+    conn.rdma_write_cache(src, [i * 1024 for i in range(4)], 1024, conn.allocate_rdma(keys, 4096))
+    conn.sync()
+    assert conn.stats()["ctrl_requests"] - before == 2  # ALLOCATE + one-way COMMIT, no SYNC
+    assert conn.check_exist(keys[0])  # ordered behind the commit on the same connection
+    other = make_conn(port)
+    deadline = time.time() + 5
+    while not other.check_exist(keys[3]) and time.time() < deadline:
+        time.sleep(0.001)
+    assert other.check_exist(keys[3])
+    dst = torch.zeros(4 * 1024)
+    conn.read_cache(dst, [(k, i * 1024) for i, k in enumerate(keys)], 1024)  # takes leases
+    conn.sync()  # leases held: this sync does the round trip that releases them
+    assert torch.equal(src, dst)
+    assert srv.stats()["inflight"] == 0
