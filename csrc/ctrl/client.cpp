@@ -395,6 +395,7 @@ int Connection::init_connection(const ClientConfig& cfg) {
     server_cuda_ = srv.lid & 1;
     server_hbm_ = srv.lid & 2;
     server_evicts_ = srv.lid & 4;
+    index_incomplete_.store((srv.lid & 8) != 0, std::memory_order_relaxed);
     std::memcpy(server_uuid_, srv.gid, 16);
     if (!worker_.joinable()) {
         stop_ = false;
@@ -526,6 +527,10 @@ int Connection::refresh_pool_map() {
 // is served through the control plane (authoritative anyway).
 bool Connection::device_index_usable() {
     if (segs_.empty() || !segs_[0].index_slots) return false;
+    // Some writer could not publish a block in the HBM index (both of the key's buckets were
+    // full): that key is reachable through the server only, so every read of this connection
+    // resolves through the server from now on instead of reporting a false miss.
+    if (index_incomplete_.load(std::memory_order_relaxed)) return false;
     return segs_.size() <= size_t(kernels::LookupLaunch::kMaxSegs);
 }
 
@@ -583,6 +588,18 @@ int Connection::sync_local() {
         }
         if (quiet && async_idle) {
             const int drained = drain_devices();
+            if (drained == -kKeyNotFound && !index_incomplete_.load()) {
+                // a device-side miss: ask the server whether the HBM index is complete - if a
+                // writer overflowed it, the key may exist and later reads go through the server
+                int32_t code = 0;
+                std::vector<uint8_t> p;
+                if (transact(kOpSync, nullptr, 0, &code, &p, sizeof(uint32_t)) == 0 &&
+                    code == kFinish && p.size() == sizeof(uint32_t)) {
+                    uint32_t remain;
+                    std::memcpy(&remain, p.data(), sizeof(remain));
+                    if (remain & kSyncIndexIncomplete) index_incomplete_.store(true);
+                }
+            }
             return drained != 0 ? drained : 0;
         }
     }
@@ -625,7 +642,7 @@ int Connection::sync_local() {
     auto frame_of = [&](char op, int32_t block_size, const uint64_t* a, size_t n) {
         std::vector<uint8_t> buf(align_up(n * 8 + 128, 8));
         fb::Builder b(buf.data(), buf.size());
-        encode_remote_meta(b, {}, block_size, 0, a, n, op);
+        encode_remote_meta(b, {}, block_size, block_size >= 0 ? take_publish_failures() : 0, a, n, op);
         std::vector<uint8_t> framed(sizeof(Header) + b.size());
         Header ch{kMagic, op, uint32_t(b.size())};
         std::memcpy(framed.data(), &ch, sizeof(ch));
@@ -671,7 +688,8 @@ int Connection::sync_local() {
     if (drained != 0) return drained;
     uint32_t remain;
     std::memcpy(&remain, p.data(), sizeof(remain));
-    return int(remain);
+    if (remain & kSyncIndexIncomplete) index_incomplete_.store(true, std::memory_order_relaxed);
+    return int(remain & ~kSyncIndexIncomplete);
 }
 
 int Connection::sync_rdma() {
@@ -694,7 +712,8 @@ int Connection::send_commit(const uint64_t* addrs, size_t count) {
         const size_t n = std::min(kChunk, count - at);
         std::vector<uint8_t> buf(align_up(n * 8 + 128, 8));
         fb::Builder b(buf.data(), buf.size());
-        encode_remote_meta(b, {}, 0, 0, addrs + at, n, kOpCommit);
+        // rkey (unused by COMMIT in the reference) reports index insertions that failed
+        encode_remote_meta(b, {}, 0, take_publish_failures(), addrs + at, n, kOpCommit);
         if (send_only(kOpCommit, b.data(), b.size()) != 0) {
             fail("commit: send failed");
             return -1;
@@ -713,6 +732,13 @@ int Connection::discard_blocks(const uint64_t* addrs, size_t count) {
         if (send_only(kOpStageCommit, b.data(), b.size()) != 0) return -1;
     }
     return 0;
+}
+
+uint32_t Connection::take_publish_failures() {
+    std::lock_guard<std::mutex> lk(mu_);
+    const uint32_t n = publish_failures_;
+    publish_failures_ = 0;
+    return n;
 }
 
 int Connection::flush_commits() {
@@ -1409,7 +1435,9 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             for (uint32_t s = 0; s < nsegs; ++s) R.seg_base[s] = seg_base[s];
             R.status = ctx->status_d;
             R.max_ctas = grid_cap;
-            R.validate = server_evicts_;
+            // always: a purge (or an eviction) may free a block while a device-path read is
+            // copying it; the post-copy tag check turns that into a reported miss
+            R.validate = true;
             R.variant = copy_variant_;
             e = kernels::launch_kv_read_fused(R, stream);
             stats_.kernel_launches += 1;
@@ -1430,8 +1458,8 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             Q.dst_base = base_ptr;
             Q.need_bytes = uint32_t(block_size);
             Q.status = ctx->status_d;
-            if (server_evicts_)
-                Q.found_at = reinterpret_cast<kernels::LookupLaunch::FoundAt*>(
+            // optimistic read: the entries are re-checked after the copy (purge / eviction)
+            Q.found_at = reinterpret_cast<kernels::LookupLaunch::FoundAt*>(
                     ctx->scratch + ctx->scratch_alloc(n * sizeof(kernels::LookupLaunch::FoundAt)));
             e = kernels::launch_index_lookup(Q, stream);
             if (e == cudaSuccess && fp8_elems) {
@@ -1745,8 +1773,11 @@ int Connection::drain_devices(bool* device_error) {
             rc = -kKeyNotFound;
         }
         if (ctx.status_h[kernels::kStatPublishFail]) {
-            LOG_WARN("device index is full: %u block(s) are only reachable through the server",
+            LOG_WARN("device index is full: %u block(s) are only reachable through the server; "
+                     "reads fall back to server lookups",
                      ctx.status_h[kernels::kStatPublishFail]);
+            publish_failures_ += ctx.status_h[kernels::kStatPublishFail];
+            index_incomplete_.store(true, std::memory_order_relaxed);
             ctx.status_h[kernels::kStatPublishFail] = 0;
         }
     }

@@ -96,6 +96,7 @@ class Connection {
     bool connected() const { return fd_ >= 0; }
     bool server_has_hbm() const { return server_hbm_; }
     bool server_evicts() const { return server_evicts_; }
+    bool index_incomplete() const { return index_incomplete_.load(); }
 
     // --- metadata
     int check_exist(const std::string& key);  // 0 = exists & committed, 1 = not, <0 error
@@ -190,6 +191,7 @@ class Connection {
     int lookup_blocks(char op, const std::vector<KeyOffset>& blocks, int block_size,
                       std::vector<RemoteBlock>& out);
     int flush_commits();
+    uint32_t take_publish_failures();
     int send_commit(const uint64_t* addrs, size_t count);
 
     // data plane
@@ -244,7 +246,11 @@ class Connection {
     int copy_variant_ = 0;
     int max_ctas_ = 0;
     bool device_lookup_ = false;
-    bool server_evicts_ = false;  // device-path reads validate their index entries after the copy
+    bool server_evicts_ = false;
+    // set when any writer failed to publish a block in the HBM index (learnt from own kernels,
+    // the server's exchange flags or a SYNC reply): reads then resolve through the server
+    std::atomic<bool> index_incomplete_{false};
+    uint32_t publish_failures_ = 0;  // own failures not yet reported to the server
     int streams_ = 4;
     int default_device_ = -1;
     ClientStats stats_;

@@ -259,6 +259,7 @@ size_t Server::purge() {
     // in-flight blocks alive across purge, src/infinistore.cpp:1110-1116).
     const size_t n = store_->purge();
     for (auto& s : segs_) s->clear_index();
+    index_incomplete_ = false;  // host map and device index are empty and in step again
     quarantine_.clear();  // the index is empty now: nothing can resolve these blocks any more
     return n;
 }
@@ -609,6 +610,17 @@ void Server::release_dropped(std::vector<KVStore::Victim>& victims) {
     victims.clear();
 }
 
+// A writer reports that `n` of its blocks found both index buckets full: those keys live in
+// the host map only.  Sticky until the next purge; readers learn it from the exchange flags
+// and from every SYNC reply, and resolve through the server from then on.
+void Server::note_publish_failures(uint32_t n) {
+    if (!index_incomplete_)
+        LOG_WARN("device index overflow: %u block(s) not indexed on the GPU; device-side lookups "
+                 "are disabled for clients until the next purge", n);
+    index_incomplete_ = true;
+    stats_.index_overflows += n;
+}
+
 void Server::close_conn(Conn* c) {
     std::vector<KVStore::Victim> victims;
     const size_t dropped = store_->drop_uncommitted(c->id, &victims);
@@ -788,7 +800,8 @@ bool Server::dispatch(Conn* c) {
                     c->staged.clear();
                 }
                 c->leases.clear();  // the client's reads have completed
-                const uint32_t remain = 0;  // no server-side transfers exist in this design
+                // no server-side transfers exist in this design: the count is always 0
+                const uint32_t remain = index_incomplete_ ? kSyncIndexIncomplete : 0u;
                 reply(c, kFinish, &remain, sizeof(remain));
                 code = kFinish;
                 break;
@@ -828,7 +841,7 @@ int Server::handle_exchange(Conn* c) {
     me.psn = uint32_t(segs_.size());
     std::memcpy(me.gid, fabric::process_uuid(), 16);
     me.lid = uint16_t((fabric::cuda_available() ? 1 : 0) | (use_hbm_ ? 2 : 0) |
-                      (cfg_.evict ? 4 : 0));
+                      (cfg_.evict ? 4 : 0) | (index_incomplete_ ? 8 : 0));
     me.mtu = kFabricVersion;
     reply(c, kFinish, &me, sizeof(me));
     return kFinish;
@@ -951,6 +964,7 @@ int Server::handle_stage_commit(Conn* c) {
         c->staged.clear();
         return kInvalidReq;
     }
+    if (req.rkey) note_publish_failures(req.rkey);
     store_->warm(req.remote_addrs.data(), req.remote_addrs.size());
     c->staged.insert(c->staged.end(), req.remote_addrs.begin(), req.remote_addrs.end());
     return kFinish;  // no reply: applied by the next SYNC of this connection
@@ -958,6 +972,7 @@ int Server::handle_stage_commit(Conn* c) {
 
 int Server::handle_commit(Conn* c) {
     RemoteMetaRequest req = decode_remote_meta(c->body.data(), c->body.size());
+    if (req.rkey) note_publish_failures(req.rkey);
     store_->commit(req.remote_addrs.data(), req.remote_addrs.size());
     return kFinish;  // no reply: ordered before the client's next SYNC on this connection
 }

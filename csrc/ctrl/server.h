@@ -73,6 +73,7 @@ struct ServerStats {
     uint64_t lookup_hits = 0;       // keys resolved by server-mediated reads
     uint64_t lookup_misses = 0;     // server-mediated read requests answered 404
     uint64_t dedup_skips = 0;       // allocate requests for keys that already existed
+    uint64_t index_overflows = 0;   // blocks writers could not insert into the HBM index
     uint64_t ops[128] = {0};        // per opcode
     OpTiming timing[128];           // per opcode service time (reactor thread, decode -> reply queued)
 };
@@ -130,6 +131,7 @@ class Server {
     // Uncommitted blocks taken out of the map: erase their device-index ways, then free them
     // (or quarantine them when the erase cannot be confirmed).
     void release_dropped(std::vector<KVStore::Victim>& victims);
+    void note_publish_failures(uint32_t n);
 
     int handle_exchange(Conn* c);
     int handle_pool_map(Conn* c);
@@ -161,6 +163,7 @@ class Server {
     uint64_t next_conn_id_ = 1;
     size_t next_pool_dev_ = 0;
     bool use_hbm_ = false;
+    bool index_incomplete_ = false;  // some block is in the host map but not in the HBM index
     ServerStats stats_;
     std::vector<uint8_t> scratch_;  // reply serialisation buffer
     void* erase_buf_ = nullptr;     // device staging of the erase kernel's records

@@ -254,9 +254,28 @@ __global__ void __launch_bounds__(kPipeThreads)
     __syncthreads();
     const uint32_t nbatches = (nitems + kQ - 1) / kQ;
     if (warp == 2) {  // ---- resolver: runs ahead of the copy by up to two batches
+        // Optimistic read: what this lane resolved in the two batches in flight is re-checked
+        // once the storer has released the batch - by then every byte of its blocks has been
+        // read from the pool.  A block that was purged or evicted meanwhile (its space may
+        // already belong to another key) shows a changed tag and is reported as a miss.
+        uint32_t vslot0 = 0, vtag0 = 0, vslot1 = 0, vtag1 = 0;  // scalars: no local memory
+        auto recheck = [&](uint32_t p) {
+            const uint32_t slot = p ? vslot1 : vslot0, tag = p ? vtag1 : vtag0;
+            if (slot && !idx::still_valid(a.table, slot, tag) && a.status) {
+                atomicAdd(a.status + kStatMiss, 1u);
+                atomicAdd(a.status + kStatStale, 1u);
+            }
+            if (p)
+                vslot1 = 0;
+            else
+                vslot0 = 0;
+        };
         for (uint32_t b = 0; b < nbatches; ++b) {
             const uint32_t p = b & 1;
-            if (b >= 2) mbar_wait(&qempty[p], ((b >> 1) - 1) & 1);
+            if (b >= 2) {
+                mbar_wait(&qempty[p], ((b >> 1) - 1) & 1);
+                recheck(p);
+            }
             const uint32_t k = b * kQ + lane;
             if (k < nitems) {
                 const uint32_t block = blockIdx.x + k * grid;
@@ -269,29 +288,44 @@ __global__ void __launch_bounds__(kPipeThreads)
                         src = a.seg_base[seg] + (f.addr & ((1ull << 44) - 1));
                 }
                 queue[p][lane] = CopyDesc{src, a.dst_base + a.dst_off[block]};
+                if (p) {
+                    vslot1 = src ? f.slot_plus1 : 0;
+                    vtag1 = f.tag;
+                } else {
+                    vslot0 = src ? f.slot_plus1 : 0;
+                    vtag0 = f.tag;
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&qfull[p]);  // release: the queue half is visible
         }
+        for (uint32_t b = nbatches >= 2 ? nbatches - 2 : 0; b < nbatches; ++b) {  // the tail
+            mbar_wait(&qempty[b & 1], (b >> 1) & 1);
+            recheck(b & 1);
+        }
         return;
     }
-    // loader and storer read their descriptors from the queue; the storer, the last reader
-    // of a half, hands it back to the resolver
+    // Loader and storer read their descriptors from the queue.  The storer hands a half back
+    // when it moves on to the next batch (or finishes): every load of the half's blocks has
+    // completed by then, which is what the resolver's re-check relies on.
     const bool is_storer = warp == 1;
     auto desc_at = [&](uint32_t k) -> CopyDesc {
         const uint32_t b = k / kQ, p = b & 1;
-        if (k % kQ == 0) mbar_wait(&qfull[p], (b >> 1) & 1);
-        const CopyDesc d = queue[p][k % kQ];
-        if (is_storer && (k % kQ == kQ - 1 || k + 1 == nitems)) {
-            __syncwarp();  // every lane has read its copy of the entry
-            if (lane == 0) mbar_arrive(&qempty[p]);
+        if (k % kQ == 0) {
+            if (is_storer && k) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&qempty[p ^ 1]);
+            }
+            mbar_wait(&qfull[p], (b >> 1) & 1);
         }
-        return d;
+        return queue[p][k % kQ];
     };
-    if (warp == 0)
+    if (warp == 0) {
         loader_body(sh, blockIdx.x, grid, nitems, lane, ring, full, empty, desc_at);
-    else
+    } else {
         storer_body(sh, blockIdx.x, grid, nitems, lane, ring, full, empty, a.status, desc_at);
+        if (lane == 0 && nitems) mbar_arrive(&qempty[((nitems - 1) / kQ) & 1]);
+    }
 }
 
 // ---------------------------------------------------------------- kv_pipe_mcast (clusters)
@@ -615,7 +649,7 @@ cudaError_t launch_kv_pipe_copy(const CopyLaunch& a, cudaStream_t stream) {
 }
 
 bool pipe_read_supported(const ReadFusedLaunch& a) {
-    return !a.validate && (a.bytes % 16) == 0 && (a.align_or & 15) == 0;
+    return (a.bytes % 16) == 0 && (a.align_or & 15) == 0;
 }
 
 cudaError_t launch_kv_pipe_read(const ReadFusedLaunch& a, cudaStream_t stream) {

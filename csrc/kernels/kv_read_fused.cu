@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kThreads)
 cudaError_t launch_kv_read_fused(const ReadFusedLaunch& a, cudaStream_t stream) {
     if (a.n == 0 || a.bytes == 0) return cudaSuccess;
     // default: resolver warp + TMA pipeline (kv_pipe.cu); this file's ld/st kernel serves
-    // small or unaligned pages and stores that evict (post-copy validation)
+    // small or unaligned pages.  Both re-check every entry after its copy.
     if ((a.variant == kCopyTma || (a.variant == kCopyAuto && a.bytes >= kPipeMinBytes)) &&
         pipe_read_supported(a))
         return launch_kv_pipe_read(a, stream);

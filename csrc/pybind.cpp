@@ -247,6 +247,7 @@ py::dict stats_dict(const ServerStats& s) {
     d["lookup_hits"] = s.lookup_hits;
     d["lookup_misses"] = s.lookup_misses;
     d["dedup_skips"] = s.dedup_skips;
+    d["index_overflows"] = s.index_overflows;
     py::dict ops;
     for (int i = 0; i < 128; ++i)
         if (s.ops[i]) ops[py::str(op_name(char(i)))] = s.ops[i];
@@ -503,6 +504,7 @@ PYBIND11_MODULE(_infinistore, m) {
         .def("device_lookup", &Connection::device_lookup)
         .def("server_has_hbm", &Connection::server_has_hbm)
         .def("server_evicts", &Connection::server_evicts)
+        .def("index_incomplete", &Connection::index_incomplete)
         .def("last_error", &Connection::last_error)
         .def("segments",
              [](Connection& c) {

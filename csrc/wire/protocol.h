@@ -78,6 +78,9 @@ static_assert(sizeof(Header) == 9, "header must be 9 bytes");
 static_assert(sizeof(ConnInfo) == 30, "conn info must be 30 bytes");
 
 constexpr uint32_t kFabricVersion = 2;  // 2: staged commits ('U')
+// Bit 31 of the u32 that follows a SYNC reply's code (and bit 3 of ConnInfo::lid): some block
+// could not be inserted into the HBM index, device-side lookups may miss keys that exist.
+constexpr uint32_t kSyncIndexIncomplete = 1u << 31;
 
 // 16-byte block locator returned by allocate / lookup.  numpy ABI: rkey:u4 @0,
 // remote_addr:u8 @8, itemsize 16 (reference: src/pybind.cpp:47).  The 4 padding bytes of

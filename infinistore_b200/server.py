@@ -187,6 +187,8 @@ def prometheus_text(s: dict) -> str:
     gauge("lookup_hits_total", s.get("lookup_hits", 0), "keys resolved by server-mediated reads")
     gauge("lookup_misses_total", s.get("lookup_misses", 0),
           "server-mediated read requests answered 404")
+    gauge("index_overflows_total", s.get("index_overflows", 0),
+          "blocks that could not be inserted into the HBM index (served through the server)")
     gauge("dedup_skips_total", s.get("dedup_skips", 0),
           "allocations skipped because the key already existed (first writer wins)")
     for op, n in sorted(s.get("ops", {}).items()):

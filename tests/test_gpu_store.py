@@ -386,3 +386,54 @@ def test_read_cache_hnd_swizzles_pages_for_the_attention_consumer(hbm_server, de
     assert torch.equal(dst, ref)
     with pytest.raises(Exception):
         conn.read_cache_hnd(dst, [(keys[0], npages)])  # page index out of range
+
+
+def test_index_overflow_falls_back_to_server_lookups():
+    """An HBM index with a single 8-way bucket and 24 keys: 16 insertions fail.  The writer
+    reports it, the server flags the index as incomplete, and device-lookup clients - the
+    writer at once, others from their connect / next sync - resolve through the server
+    instead of reporting keys that exist as missing."""
+    from infinistore_b200 import _infinistore as m
+
+    cfg = m.ServerConfig()
+    cfg.service_port = 0
+    cfg.host = "127.0.0.1"
+    cfg.pool_backend = "hbm"
+    cfg.pool_devices = [0]
+    cfg.prealloc_bytes = 64 << 20
+    cfg.minimal_allocate_size = 16
+    cfg.index_slots = 8
+    srv = m.Server(cfg)
+    port = srv.start()
+    try:
+        early = make_conn(port, device_lookup=True)  # connected before the overflow
+        w = make_conn(port, device_lookup=True)
+        n, elems = 24, 4096
+        src = torch.randn(n * elems, device="cuda:0")
+        w.register_mr(src)
+        keys = [f"ovf-{i}" for i in range(n)]
+        w.rdma_write_cache(src, [i * elems for i in range(n)], elems, w.allocate_rdma(keys, elems * 4))
+        w.sync()
+        assert w.conn.index_incomplete()
+        assert srv.stats()["index_overflows"] == n - 8
+        blocks = [(k, i * elems) for i, k in enumerate(keys)]
+        for conn in (w, make_conn(port, device_lookup=True)):
+            dst = torch.zeros_like(src)
+            conn.read_cache(dst, blocks, elems)
+            conn.sync()
+            assert torch.equal(dst, src)
+        # a client that connected earlier learns it from its next sync: at most one false miss
+        dst = torch.zeros_like(src)
+        try:
+            early.read_cache(dst, blocks, elems)
+            early.sync()
+        except Exception:
+            assert early.conn.index_incomplete()
+            early.read_cache(dst, blocks, elems)
+            early.sync()
+        assert torch.equal(dst, src)
+        assert w.get_match_last_index(keys) == n - 1
+        srv.purge()  # host map and index empty again: the flag is cleared
+        assert not make_conn(port, device_lookup=True).conn.index_incomplete()
+    finally:
+        srv.stop()
