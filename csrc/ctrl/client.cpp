@@ -1242,6 +1242,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             F.status = L.status;
             F.max_ctas = L.max_ctas;
             F.all_local = all_local;
+            F.aligned16 = (align_or & 15) == 0;
             e = write ? kernels::launch_kv_write_fp8(F, stream) : kernels::launch_kv_read_fp8(F, stream);
         } else {
             e = kernels::launch_kv_copy(L, stream);
@@ -1469,6 +1470,7 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
                 F.elems = uint32_t(fp8_elems);
                 F.status = ctx->status_d;
                 F.max_ctas = grid_cap;
+                F.aligned16 = (align_or & 15) == 0;
                 e = kernels::launch_kv_read_fp8(F, stream);
             } else if (e == cudaSuccess) {
                 kernels::CopyLaunch L;

@@ -122,7 +122,12 @@ struct Fp8Launch {
     uint32_t* status = nullptr;
     int max_ctas = 0;
     bool all_local = false;
+    bool aligned16 = true;  // every page address is 16-byte aligned (bulk copies need it)
+    int variant = 0;        // 0 = auto (TMA pipeline when supported), 1 = ld/st kernels
 };
+// The TMA-pipelined flavour (kv_fp8_pipe.cu): needs elems % 512 == 0 and aligned pages.
+bool fp8_pipe_supported(const Fp8Launch& a);
+cudaError_t launch_kv_fp8_pipe(const Fp8Launch& a, bool write, cudaStream_t stream);
 // bytes a quantised page occupies in the pool: elems (e4m3) + 4 * elems/group (scales)
 inline uint32_t fp8_block_bytes(uint32_t elems, uint32_t group) {
     return elems + 4u * (elems / group);

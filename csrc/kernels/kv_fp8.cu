@@ -1,4 +1,6 @@
-// fp8 KV path: the quantisation is fused into the page mover.
+// fp8 KV path: the quantisation is fused into the page mover.  This file holds the ld/st
+// flavour (any page size that is a multiple of 128 elements); pages of a multiple of 512
+// elements - every real KV layout - take the TMA-pipelined flavour in kv_fp8_pipe.cu.
 //
 //   kv_write_fp8 : bf16 page in the client's paged KV cache -> e4m3 payload + one fp32 scale
 //                  per 128-element row (head_dim) written straight into the (peer) pool
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(kThreads)
 cudaError_t launch_kv_write_fp8(const Fp8Launch& a, cudaStream_t stream) {
     if (a.n == 0 || a.elems == 0) return cudaSuccess;
     if (a.group != kRow || a.elems % kRow != 0) return cudaErrorInvalidValue;
+    if (a.variant == 0 && fp8_pipe_supported(a)) return launch_kv_fp8_pipe(a, true, stream);
     Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n, nullptr, !a.all_local};
     if (!a.table || !a.done) pub.recs = nullptr;
     // whole pages per CTA when there are enough of them (single-CTA commit, see kv_copy.cu)
@@ -208,6 +211,7 @@ cudaError_t launch_kv_write_fp8(const Fp8Launch& a, cudaStream_t stream) {
 cudaError_t launch_kv_read_fp8(const Fp8Launch& a, cudaStream_t stream) {
     if (a.n == 0 || a.elems == 0) return cudaSuccess;
     if (a.group != kRow || a.elems % kRow != 0) return cudaErrorInvalidValue;
+    if (a.variant == 0 && fp8_pipe_supported(a)) return launch_kv_fp8_pipe(a, false, stream);
     uint32_t chunk = kChunkElems;
     if (a.n >= uint32_t(sm_count()) && a.elems <= (1u << 19)) chunk = a.elems;
     const uint32_t cpb = (a.elems + chunk - 1) / chunk;

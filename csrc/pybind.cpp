@@ -849,8 +849,9 @@ PYBIND11_MODULE(_infinistore, m) {
     auto fp8 = [](bool write) {
         return [write](uint64_t descs, uint32_t n, uint32_t elems, uint32_t group, int max_ctas,
                        uint64_t stream, uint64_t recs, uint64_t table, uint64_t table_mask,
-                       uint64_t done, uint64_t status) {
+                       uint64_t done, uint64_t status, int variant) {
             kernels::Fp8Launch L;
+            L.variant = variant;
             L.descs = as_ptr<const kernels::CopyDesc>(descs);
             L.n = n;
             L.elems = elems;
@@ -870,11 +871,11 @@ PYBIND11_MODULE(_infinistore, m) {
     k.def("kv_write_fp8", fp8(true), py::arg("descs"), py::arg("n"), py::arg("elems"),
           py::arg("group") = 128, py::arg("max_ctas") = 0, py::arg("stream") = 0,
           py::arg("recs") = 0, py::arg("table") = 0, py::arg("table_mask") = 0,
-          py::arg("done") = 0, py::arg("status") = 0);
+          py::arg("done") = 0, py::arg("status") = 0, py::arg("variant") = 0);
     k.def("kv_read_fp8", fp8(false), py::arg("descs"), py::arg("n"), py::arg("elems"),
           py::arg("group") = 128, py::arg("max_ctas") = 0, py::arg("stream") = 0,
           py::arg("recs") = 0, py::arg("table") = 0, py::arg("table_mask") = 0,
-          py::arg("done") = 0, py::arg("status") = 0);
+          py::arg("done") = 0, py::arg("status") = 0, py::arg("variant") = 0);
     k.def("fp8_block_bytes", &kernels::fp8_block_bytes);
     k.def(
         "kv_bcast_nvls",

@@ -209,25 +209,29 @@ def fp8_block_bytes(elems: int, group: int = 128) -> int:
     return K.fp8_block_bytes(elems, group)
 
 
+FP8_VARIANTS = {"auto": 0, "ldst": 1}
+
+
 def kv_write_fp8(descs: torch.Tensor, elems: int, max_ctas: int = 0,
-                 publish: Optional[PublishArgs] = None) -> None:
-    """bf16 pages (desc.src) -> e4m3 payload + per-128 scales (desc.dst)."""
+                 publish: Optional[PublishArgs] = None, variant: str = "auto") -> None:
+    """bf16 pages (desc.src) -> e4m3 payload + per-128 scales (desc.dst).  "auto": the
+    TMA-pipelined kernel (kv_fp8_pipe.cu) when elems % 512 == 0, else / "ldst": kv_fp8.cu."""
     with torch.cuda.device(descs.device):
         K.kv_write_fp8(descs.data_ptr(), descs.shape[0], elems, 128, max_ctas,
                        _stream(descs.device),
                        publish.recs.data_ptr() if publish else 0,
                        publish.table.data_ptr() if publish else 0,
                        publish.mask if publish else 0,
-                       publish.done.data_ptr() if publish else 0, 0)
+                       publish.done.data_ptr() if publish else 0, 0, FP8_VARIANTS[variant])
 
 
 def kv_read_fp8(descs: torch.Tensor, elems: int, max_ctas: int = 0,
-                status: Optional[torch.Tensor] = None) -> None:
+                status: Optional[torch.Tensor] = None, variant: str = "auto") -> None:
     """e4m3 payload + scales (desc.src) -> bf16 pages (desc.dst)."""
     with torch.cuda.device(descs.device):
         K.kv_read_fp8(descs.data_ptr(), descs.shape[0], elems, 128, max_ctas,
                       _stream(descs.device), 0, 0, 0, 0,
-                      status.data_ptr() if status is not None else 0)
+                      status.data_ptr() if status is not None else 0, FP8_VARIANTS[variant])
 
 
 def fp8_reference(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:

@@ -278,10 +278,14 @@ def test_first_writer_wins_in_the_device_index():
     assert int(descs.cpu().numpy().view(np.uint64)[0, 0]) == 0x1000000 + 4096
 
 
-@pytest.mark.parametrize("elems", [128, 8192, 16384, 65536, 8192 + 128 * 5])
-def test_fp8_write_matches_fp32_reference(elems):
+@pytest.mark.parametrize("variant", ["auto", "ldst"])
+@pytest.mark.parametrize("elems,pages", [(128, 11), (512, 11), (8192, 11), (16384, 400),
+                                         (65536, 11), (8192 + 512 * 3, 11), (8192 + 128 * 5, 11),
+                                         (1 << 20, 3)])
+def test_fp8_write_matches_fp32_reference(elems, pages, variant):
+    """Both flavours: "auto" = the TMA-pipelined kernel (elems % 512 == 0, else it falls back),
+    "ldst" = the per-thread kernel.  400 pages: whole pages per CTA; 3 x 1M: chunked pages."""
     ops = _ops()
-    pages = 11
     g = torch.Generator(device=DEV).manual_seed(elems)
     x = (torch.randn(pages, elems, device=DEV, generator=g) * 4).to(torch.bfloat16)
     x[0, :128] = 0  # an all-zero row must not divide by zero
@@ -292,7 +296,7 @@ def test_fp8_write_matches_fp32_reference(elems):
     pool = torch.zeros(pages, stride, dtype=torch.uint8, device=DEV)
     wd = ops.make_descs([x[i].data_ptr() for i in range(pages)],
                         [pool[i].data_ptr() for i in range(pages)], DEV)
-    ops.kv_write_fp8(wd, elems)
+    ops.kv_write_fp8(wd, elems, variant=variant)
     torch.cuda.synchronize()
     ref_deq, ref_scale, ref_q = ops.fp8_reference(x)
     payload = pool[:, :elems].contiguous().view(torch.float8_e4m3fn)
@@ -307,7 +311,7 @@ def test_fp8_write_matches_fp32_reference(elems):
     out = torch.zeros_like(x)
     rd = ops.make_descs([pool[i].data_ptr() for i in range(pages)],
                         [out[i].data_ptr() for i in range(pages)], DEV)
-    ops.kv_read_fp8(rd, elems)
+    ops.kv_read_fp8(rd, elems, variant=variant)
     torch.cuda.synchronize()
     assert torch.equal(out, got.reshape(pages, elems).to(torch.bfloat16))
     # quantisation error bound: half an e4m3 ulp relative to the row maximum (2^-4)
