@@ -1602,24 +1602,47 @@ int Connection::r_rdma_multi(const std::vector<KeyOffset>& blocks, int block_siz
             fail("multi-destination read: cannot resolve the blocks");
             return -1;
         }
-        // clusters of 4, then 2; an odd last destination shares a 2-cluster with its
-        // predecessor (which is rewritten with the same bytes)
+        // Local pool: thread-block clusters (multicast bulk load into 2 or 4 CTAs, one
+        // destination each; an odd last destination shares a 2-cluster with its predecessor,
+        // which is rewritten with the same bytes).  Pool behind NVLink: one load, K stores
+        // per CTA (the fan-out flavour of the TMA pipeline) - the fabric still carries every
+        // page once.
+        bool src_local = true;
+        for (size_t sgi = 0; sgi < ctx->seg_remote.size(); ++sgi)
+            if (ctx->seg_ptr[sgi] && ctx->seg_remote[sgi]) src_local = false;
         cudaError_t e = cudaSuccess;
         size_t r = 0;
         while (e == cudaSuccess && r < bases.size()) {
             const size_t left = bases.size() - r;
-            kernels::McastLaunch M;
-            M.descs = descs_d;
-            M.n = uint32_t(n);
-            M.bytes = uint32_t(block_size);
-            M.align_or = align_or;
-            M.status = r == 0 ? ctx->status_d : nullptr;  // count a miss once
-            const size_t first = left >= 2 ? r : r - 1;
-            M.ndst = left >= 4 ? 4 : 2;
-            for (int j = 0; j < M.ndst; ++j)
-                M.delta[j] = int64_t(bases[first + size_t(j)]) - int64_t(bases[0]);
-            e = kernels::launch_kv_pipe_mcast(M, stream);
-            r = first + size_t(M.ndst);
+            if (src_local) {
+                kernels::McastLaunch M;
+                M.descs = descs_d;
+                M.n = uint32_t(n);
+                M.bytes = uint32_t(block_size);
+                M.align_or = align_or;
+                M.src_local = true;
+                M.status = r == 0 ? ctx->status_d : nullptr;  // count a miss once
+                const size_t first = left >= 2 ? r : r - 1;
+                M.ndst = left >= 4 ? 4 : 2;
+                for (int j = 0; j < M.ndst; ++j)
+                    M.delta[j] = int64_t(bases[first + size_t(j)]) - int64_t(bases[0]);
+                e = kernels::launch_kv_pipe_mcast(M, stream);
+                r = first + size_t(M.ndst);
+            } else {
+                kernels::CopyLaunch L;
+                L.descs = descs_d;
+                L.n = uint32_t(n);
+                L.bytes = uint32_t(block_size);
+                L.align_or = align_or;
+                L.status = r == 0 ? ctx->status_d : nullptr;
+                L.variant = kernels::kCopyTma;
+                L.max_ctas = max_ctas_;
+                L.fan_n = int(std::min<size_t>(left, 4));
+                for (int j = 0; j < L.fan_n; ++j)
+                    L.fan_delta[j] = int64_t(bases[r + size_t(j)]) - int64_t(bases[0]);
+                e = kernels::launch_kv_pipe_copy(L, stream);
+                r += size_t(L.fan_n);
+            }
             stats_.kernel_launches++;
         }
         if (e != cudaSuccess) {

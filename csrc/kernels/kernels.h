@@ -93,6 +93,10 @@ struct CopyLaunch {
     // TMA pipeline geometry (0 = default: 16 KB slots, 128 KB ring per CTA)
     uint32_t stage_bytes = 0;
     uint32_t ring_bytes = 0;
+    // TMA pipeline only, reads only: store every block to fan_n destinations,
+    // desc.dst + fan_delta[r] (one load over the fabric, fan_n local stores)
+    int fan_n = 1;
+    int64_t fan_delta[4] = {0, 0, 0, 0};
 };
 // Picks the data path (CopyVariant) and launches it.  kCopyAuto: the TMA pipeline for every
 // 16-byte aligned transfer of blocks >= kPipeMinBytes, 256-bit ld/st below that.
@@ -237,6 +241,7 @@ struct McastLaunch {
     uint64_t align_or = 0;  // OR of every destination base and offset
     int ndst = 2;           // 2 or 4 = cluster size
     int64_t delta[4] = {0, 0, 0, 0};
+    bool src_local = false;  // every source is in the launching GPU's own HBM (required)
     uint32_t* status = nullptr;
     int max_clusters = 0;
     uint32_t stage_bytes = 0;

@@ -136,11 +136,18 @@ __device__ __forceinline__ void loader_body(const Shape& sh, uint32_t first, uin
     }
 }
 
+// Fan-out: every piece is stored to `n` destinations, dst + delta[r] (one load, n stores from
+// the same ring slot - the multi-destination read when the source sits behind NVLink).
+struct FanOut {
+    uint32_t n = 1;
+    int64_t delta[4] = {0, 0, 0, 0};
+};
+
 template <typename DescAt>
 __device__ __forceinline__ void storer_body(const Shape& sh, uint32_t first, uint32_t stride,
                                             uint32_t nitems, uint32_t lane, uint8_t* ring,
                                             uint64_t* full, uint64_t* empty, uint32_t* status,
-                                            DescAt&& desc_at) {
+                                            DescAt&& desc_at, const FanOut fan = FanOut{}) {
     uint32_t s = 0, ph = 0;  // slot being stored and its full-phase parity
     uint32_t sf = 0;         // slot to release next
     uint32_t q = 0;          // pieces issued
@@ -153,9 +160,12 @@ __device__ __forceinline__ void storer_body(const Shape& sh, uint32_t first, uin
         for (uint32_t o = 0; o < len; o += sh.stage_bytes, ++q) {
             if (lane == 0) {
                 mbar_wait(&full[s], ph);
-                if (d.src)
-                    bulk_s2g(reinterpret_cast<uint8_t*>(d.dst) + off0 + o,
-                             ring + size_t(s) * sh.stage_bytes, min(sh.stage_bytes, len - o));
+                if (d.src) {
+                    const uint32_t plen = min(sh.stage_bytes, len - o);
+                    for (uint32_t r = 0; r < fan.n; ++r)  // delta[0] == 0 without fan-out
+                        bulk_s2g(reinterpret_cast<uint8_t*>(int64_t(d.dst) + fan.delta[r]) + off0 + o,
+                                 ring + size_t(s) * sh.stage_bytes, plen);
+                }
                 bulk_commit();  // one group per piece (an empty one for a miss)
                 bulk_wait_read<kStoreLag>();  // pieces <= q - kStoreLag have left the ring
                 if (q >= uint32_t(kStoreLag)) {
@@ -181,7 +191,7 @@ template <bool PARAM>
 __global__ void __launch_bounds__(kPipeThreads)
     kv_pipe_copy_kernel(const CopyDesc* __restrict__ descs,
                         const __grid_constant__ PipeDescParam<PARAM ? kPipeParamDescs : 1> pd,
-                        const Shape sh, Publish pub) {
+                        const Shape sh, Publish pub, const FanOut fan) {
     extern __shared__ __align__(128) uint8_t ring[];
     __shared__ __align__(8) uint64_t full[kPipeMaxStages];
     __shared__ __align__(8) uint64_t empty[kPipeMaxStages];
@@ -207,7 +217,7 @@ __global__ void __launch_bounds__(kPipeThreads)
     if (warp == 0) {
         loader_body(sh, blockIdx.x, grid, nitems, lane, ring, full, empty, desc_at);
     } else {
-        storer_body(sh, blockIdx.x, grid, nitems, lane, ring, full, empty, pub.status, desc_at);
+        storer_body(sh, blockIdx.x, grid, nitems, lane, ring, full, empty, pub.status, desc_at, fan);
         if (pub.recs) ctrl_barrier_arrive(64);
     }
 }
@@ -636,14 +646,20 @@ cudaError_t launch_kv_pipe_copy(const CopyLaunch& a, cudaStream_t stream) {
     const uint64_t total = uint64_t(a.n) * cpb;
     ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
     const Shape sh{a.n, a.bytes, chunk, cpb, g.stage_bytes, g.stages};
+    FanOut fan;
+    if (a.fan_n > 1) {
+        if (a.fan_n > 4 || pub.recs) return cudaErrorInvalidValue;  // reads only
+        fan.n = uint32_t(a.fan_n);
+        for (int r = 0; r < a.fan_n; ++r) fan.delta[r] = a.fan_delta[r];
+    }
     const bool param = a.descs_host != nullptr && a.n <= uint32_t(kPipeParamDescs);
     if (param) {
         PipeDescParam<kPipeParamDescs> pd;
         std::memcpy(pd.d, a.descs_host, size_t(a.n) * sizeof(CopyDesc));
-        kv_pipe_copy_kernel<true><<<ctas, kPipeThreads, g.smem, stream>>>(a.descs, pd, sh, pub);
+        kv_pipe_copy_kernel<true><<<ctas, kPipeThreads, g.smem, stream>>>(a.descs, pd, sh, pub, fan);
     } else {
         const PipeDescParam<1> none{};
-        kv_pipe_copy_kernel<false><<<ctas, kPipeThreads, g.smem, stream>>>(a.descs, none, sh, pub);
+        kv_pipe_copy_kernel<false><<<ctas, kPipeThreads, g.smem, stream>>>(a.descs, none, sh, pub, fan);
     }
     return cudaGetLastError();
 }
@@ -733,6 +749,11 @@ cudaError_t launch_kv_pipe_mcast(const McastLaunch& a, cudaStream_t stream) {
     if (a.n == 0 || a.bytes == 0) return cudaSuccess;
     if ((a.ndst != 2 && a.ndst != 4) || (a.bytes % 16) != 0 || (a.align_or & 15) != 0)
         return cudaErrorInvalidValue;
+    // The multicast bulk load is used on LOCAL sources only: with a peer-mapped source
+    // (NVLink aperture) the launch wedged a B200 in round 2 (gpurun strike) - the fabric path
+    // of multicast TMA reads is not something this store relies on.  Peer sources take the
+    // fan-out flavour of kv_pipe_copy instead (one load, K stores per CTA).
+    if (!a.src_local) return cudaErrorNotSupported;
     cudaError_t e = ensure_pipe_attrs();
     if (e != cudaSuccess) return e;
     // two CTAs of a cluster may share an SM: keep the ring at half the usual size

@@ -710,10 +710,15 @@ PYBIND11_MODULE(_infinistore, m) {
         [](uint64_t descs, uint32_t n, uint32_t bytes, int variant, int max_ctas, uint64_t stream,
            uint64_t recs, uint64_t table, uint64_t table_mask, uint64_t done, uint64_t status,
            uint64_t align_or, uint64_t trace, bool all_local, uint32_t debug,
-           uint32_t stage_bytes, uint32_t ring_bytes) {
+           uint32_t stage_bytes, uint32_t ring_bytes, const std::vector<int64_t>& fan_delta) {
             kernels::CopyLaunch L;
             L.stage_bytes = stage_bytes;
             L.ring_bytes = ring_bytes;
+            if (!fan_delta.empty()) {
+                if (fan_delta.size() > 4) throw std::runtime_error("at most 4 destinations");
+                L.fan_n = int(fan_delta.size());
+                for (size_t i = 0; i < fan_delta.size(); ++i) L.fan_delta[i] = fan_delta[i];
+            }
             L.descs = as_ptr<const kernels::CopyDesc>(descs);
             L.n = n;
             L.bytes = bytes;
@@ -736,7 +741,7 @@ PYBIND11_MODULE(_infinistore, m) {
         py::arg("table") = 0, py::arg("table_mask") = 0, py::arg("done") = 0,
         py::arg("status") = 0, py::arg("align_or") = 0, py::arg("trace") = 0,
         py::arg("all_local") = false, py::arg("debug") = 0, py::arg("stage_bytes") = 0,
-        py::arg("ring_bytes") = 0);
+        py::arg("ring_bytes") = 0, py::arg("fan_delta") = std::vector<int64_t>());
     k.def(
         "kv_pipe_mcast",
         [](uint64_t descs, uint32_t n, uint32_t bytes, const std::vector<int64_t>& delta,
@@ -749,6 +754,7 @@ PYBIND11_MODULE(_infinistore, m) {
             M.ndst = int(delta.size());
             for (size_t i = 0; i < delta.size() && i < 4; ++i) M.delta[i] = delta[i];
             M.status = as_ptr<uint32_t>(status);
+            M.src_local = true;  // raw launcher: the caller vouches for local sources
             M.max_clusters = max_clusters;
             M.stage_bytes = stage_bytes;
             M.ring_bytes = ring_bytes;

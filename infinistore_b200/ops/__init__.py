@@ -42,10 +42,13 @@ def make_descs(src_ptrs: Sequence[int], dst_ptrs: Sequence[int], device) -> torc
 def kv_copy(descs: torch.Tensor, nbytes: int, variant: str = "auto", max_ctas: int = 0,
             publish: Optional["PublishArgs"] = None, status: Optional[torch.Tensor] = None,
             align_or: int = 0, stage_bytes: int = 0, ring_bytes: int = 0,
-            all_local: bool = False, debug: int = 0) -> None:
+            all_local: bool = False, debug: int = 0,
+            fan_deltas: Optional[Sequence[int]] = None) -> None:
     """Move descs.shape[0] blocks of `nbytes` bytes.  ``variant``: "auto" / "tma" = the
     warp-specialised TMA pipeline (csrc/kernels/kv_pipe.cu; ``stage_bytes`` / ``ring_bytes``
-    set its ring geometry), "ldst" / "ldst256" = csrc/kernels/kv_copy.cu."""
+    set its ring geometry), "ldst" / "ldst256" = csrc/kernels/kv_copy.cu.  ``fan_deltas``
+    (TMA pipeline, no publish): every block is stored to ``dst + delta`` for each delta - one
+    load, several stores (the multi-destination read for sources behind NVLink)."""
     assert descs.is_cuda and descs.dtype == torch.int64 and descs.is_contiguous()
     n = descs.shape[0]
     with torch.cuda.device(descs.device):
@@ -55,7 +58,7 @@ def kv_copy(descs: torch.Tensor, nbytes: int, variant: str = "auto", max_ctas: i
                   publish.mask if publish else 0,
                   publish.done.data_ptr() if publish else 0,
                   status.data_ptr() if status is not None else 0, align_or, 0, all_local, debug,
-                  stage_bytes, ring_bytes)
+                  stage_bytes, ring_bytes, [int(d) for d in fan_deltas] if fan_deltas else [])
 
 
 def kv_copy_multicast(descs: torch.Tensor, nbytes: int, dst_deltas: Sequence[int],
@@ -64,7 +67,9 @@ def kv_copy_multicast(descs: torch.Tensor, nbytes: int, dst_deltas: Sequence[int
     """Every block descs[i].src -> descs[i].dst + dst_deltas[r] for r in range(2 or 4), with a
     thread-block cluster: the source is fetched ONCE (``cp.async.bulk ...
     .multicast::cluster`` into every CTA's shared memory) and each CTA of the cluster stores
-    it to its own destination (csrc/kernels/kv_pipe.cu: kv_pipe_mcast)."""
+    it to its own destination (csrc/kernels/kv_pipe.cu: kv_pipe_mcast).  LOCAL sources only:
+    a multicast bulk load from a peer-mapped (NVLink) address wedged a B200 in round 2; for
+    peer sources use ``kv_copy(..., variant="tma", fan_deltas=...)``."""
     assert descs.is_cuda and descs.dtype == torch.int64 and descs.is_contiguous()
     assert len(dst_deltas) in (2, 4), "clusters of 2 or 4 CTAs"
     with torch.cuda.device(descs.device):

@@ -101,6 +101,32 @@ def test_cluster_multicast_copy_fans_one_source_out(ndst, nbytes, n):
     assert int(status[0]) == 1
 
 
+@pytest.mark.parametrize("ndst", [2, 3, 4])
+def test_tma_pipeline_fan_out_stores(ndst):
+    """One load, ndst stores per ring slot (the multi-destination read for a pool behind
+    NVLink); with a second GPU the source lives there."""
+    ops = _ops()
+    n, nbytes = 150, 65536 + 32
+    src_dev = "cuda:1" if torch.cuda.device_count() >= 2 else DEV
+    stride = (nbytes + 255) // 256 * 256
+    src = torch.randint(0, 255, (n, stride), dtype=torch.uint8, device=src_dev)
+    dsts = torch.zeros((ndst + 1, n, stride), dtype=torch.uint8, device=DEV)
+    if src_dev != DEV:
+        from infinistore_b200 import _infinistore as native
+        assert native.enable_peer_access(0, 1)
+    descs = ops.make_descs([src[i].data_ptr() for i in range(n)],
+                           [dsts[0, n - 1 - i].data_ptr() for i in range(n)], DEV)
+    # destinations 1..ndst (not 0): the first delta is non-zero, as in a second fan-out group
+    deltas = [dsts[r + 1].data_ptr() - dsts[0].data_ptr() for r in range(ndst)]
+    ops.kv_copy(descs, nbytes, variant="tma", fan_deltas=deltas)
+    torch.cuda.synchronize()
+    ref = torch.zeros((n, stride), dtype=torch.uint8, device=DEV)
+    ref[:, :nbytes] = src.to(DEV).flip(0)[:, :nbytes]
+    assert int(dsts[0].sum()) == 0
+    for r in range(ndst):
+        assert torch.equal(dsts[r + 1], ref), f"destination {r}"
+
+
 def test_kv_copy_unaligned_falls_back_to_bytes():
     ops = _ops()
     n, nbytes = 9, 1000  # not a multiple of 16, odd addresses
