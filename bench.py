@@ -58,6 +58,8 @@ def parse_args():
     p.add_argument("--variant", default="auto", choices=["auto", "ldst", "tma", "ldst256"])
     p.add_argument("--max-ctas", type=int, default=0)
     p.add_argument("--streams", type=int, default=4, help="internal launch streams per connection")
+    p.add_argument("--stage-kb", type=int, default=0, help="TMA pipeline slot size (0 = default)")
+    p.add_argument("--ring-kb", type=int, default=0, help="TMA pipeline ring per CTA (0 = default)")
     p.add_argument("--host-lookup", action="store_true",
                    help="resolve read keys through the server instead of the HBM index")
     p.add_argument("--base-port", type=int, default=0)
@@ -291,7 +293,8 @@ def main():
                             connection_type=ist.TYPE_RDMA, log_level="warning",
                             device=local_rank, device_lookup=not args.host_lookup,
                             copy_variant=args.variant, max_ctas=args.max_ctas,
-                            streams=args.streams)
+                            streams=args.streams, pipe_stage_kb=args.stage_kb,
+                            pipe_ring_kb=args.ring_kb)
     conn = ist.InfinityConnection(ccfg)
     conn.connect()
 
@@ -562,6 +565,7 @@ def main():
                        "l2": f"working set {2 * size_bytes >> 20} MiB per GPU per round >> 126 MB L2 "
                              "(no flush needed)",
                        "variant": args.variant, "streams": args.streams,
+                       "pipe_stage_kb": args.stage_kb or "default", "pipe_ring_kb": args.ring_kb or "default",
                        "lookup": "host" if args.host_lookup else "device-index",
                        "phase_sync": True, "timed_region_s": round(ms_max / 1e3, 3)},
             "roofline": roof,

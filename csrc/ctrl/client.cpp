@@ -676,6 +676,17 @@ int Connection::sync_local() {
     // the same window: their kernels completed, so their commits are applied all the same.
     std::vector<uint8_t> framed;  // reply-less messages that travel with the SYNC
     if (!staged && !addrs.empty() && send_commit(addrs.data(), addrs.size()) != 0) return -1;
+    if (const uint32_t pf = take_publish_failures()) {
+        // index insertions that failed are known only now (after the drain): an empty COMMIT
+        // carries the count, ahead of the SYNC in the same segment
+        std::vector<uint8_t> buf(256);
+        fb::Builder b(buf.data(), buf.size());
+        encode_remote_meta(b, {}, 0, pf, nullptr, 0, kOpCommit);
+        framed.resize(sizeof(Header) + b.size());
+        Header ch{kMagic, kOpCommit, uint32_t(b.size())};
+        std::memcpy(framed.data(), &ch, sizeof(ch));
+        std::memcpy(framed.data() + sizeof(ch), b.data(), b.size());
+    }
     int32_t code = 0;
     std::vector<uint8_t> p;
     if (transact(kOpSync, nullptr, 0, &code, &p, sizeof(uint32_t), &framed) != 0 ||
@@ -1215,6 +1226,8 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
         L.align_or = align_or;
         L.status = ctx->status_d;
         L.variant = copy_variant_;
+        L.stage_bytes = pipe_stage_;
+        L.ring_bytes = pipe_ring_;
         L.max_ctas = max_ctas_ ? max_ctas_ : (all_remote ? 2 * kernels::sm_count() : 0);
         L.all_local = all_local && !L.multicast;
         if (L.multicast && fp8_elems) {
@@ -1417,8 +1430,11 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
         // (>= SM-count blocks of <= 1 MB), wasteful when a few large blocks are split over
         // many CTAs (measured: 4 MB single-block read 83 us vs 42 us) - then resolve each key
         // once with the lookup kernel and feed the descriptors to kv_copy.
+        // ... and for a handful of blocks (<= 4 MB in all) the single launch wins on latency:
+        // lookup + copy + re-check would be three kernels for microseconds of data.
         const bool whole_blocks =
-            n >= size_t(kernels::sm_count()) && uint32_t(block_size) <= (1u << 20);
+            uint32_t(block_size) <= (1u << 20) &&
+            (n >= size_t(kernels::sm_count()) || n * size_t(block_size) <= (4u << 20));
         if (!fp8_elems && whole_blocks) {
             // one kernel: hash + probe + move
             kernels::ReadFusedLaunch R;
@@ -1440,6 +1456,8 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             // copying it; the post-copy tag check turns that into a reported miss
             R.validate = true;
             R.variant = copy_variant_;
+            R.stage_bytes = pipe_stage_;
+            R.ring_bytes = pipe_ring_;
             e = kernels::launch_kv_read_fused(R, stream);
             stats_.kernel_launches += 1;
         } else {
@@ -1480,6 +1498,8 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
                 L.align_or = align_or;
                 L.status = ctx->status_d;
                 L.variant = copy_variant_;
+                L.stage_bytes = pipe_stage_;
+                L.ring_bytes = pipe_ring_;
                 L.max_ctas = grid_cap;
                 e = kernels::launch_kv_copy(L, stream);
             }

@@ -168,6 +168,11 @@ class Connection {
     // --- tuning / introspection
     void set_copy_variant(int v) { copy_variant_ = v; }
     void set_max_ctas(int n) { max_ctas_ = n; }
+    // TMA pipeline ring geometry: slot bytes and ring bytes per CTA (0 = kernel default)
+    void set_pipe_geometry(uint32_t stage_bytes, uint32_t ring_bytes) {
+        pipe_stage_ = stage_bytes;
+        pipe_ring_ = ring_bytes;
+    }
     void set_device_lookup(bool on) { device_lookup_ = on; }
     // 0: launch in the caller's stream; n >= 1: round-robin over n internal streams that
     // wait for the caller's stream (kernels of successive calls overlap)
@@ -245,6 +250,7 @@ class Connection {
     std::map<uint64_t, size_t> mrs_;         // registered regions by base pointer (C10)
     int copy_variant_ = 0;
     int max_ctas_ = 0;
+    uint32_t pipe_stage_ = 0, pipe_ring_ = 0;
     bool device_lookup_ = false;
     bool server_evicts_ = false;
     // set when any writer failed to publish a block in the HBM index (learnt from own kernels,

@@ -99,9 +99,11 @@ struct CopyLaunch {
     int64_t fan_delta[4] = {0, 0, 0, 0};
 };
 // Picks the data path (CopyVariant) and launches it.  kCopyAuto: the TMA pipeline for every
-// 16-byte aligned transfer of blocks >= kPipeMinBytes, 256-bit ld/st below that.
+// 16-byte aligned transfer of blocks >= kPipeMinBytes, 256-bit ld/st below that (one issuing
+// thread per CTA cannot keep up with the per-block work of small blocks: 534 vs 2307 GB/s at
+// 4 KB, 2090 vs 3035 at 16 KB, equal from 64 KB on - profiles/r2_lab_1gpu.json).
 cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream);
-constexpr uint32_t kPipeMinBytes = 8u << 10;
+constexpr uint32_t kPipeMinBytes = 64u << 10;
 // The TMA pipeline itself (kv_pipe.cu); needs 16-byte aligned addresses and sizes.
 cudaError_t launch_kv_pipe_copy(const CopyLaunch& a, cudaStream_t stream);
 struct PipeGeometry {

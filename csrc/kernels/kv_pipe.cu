@@ -613,7 +613,9 @@ EncodeTiledFn encode_tiled_fn() {
 // Ring geometry: slots of up to `stage` bytes (16-byte multiple), as many as fit `ring` bytes.
 PipeGeometry pipe_geometry(uint32_t bytes, uint32_t stage_pref, uint32_t ring_pref) {
     PipeGeometry g;
-    const uint32_t stage_cap = stage_pref ? stage_pref : (16u << 10);
+    // 32 KB slots, 4 of them: the best of the round-2 sweep on local HBM (3225 GB/s at 128 KB
+    // blocks = the copy engine's rate; 16 KB slots: 2982) - profiles/r2_lab_*.json
+    const uint32_t stage_cap = stage_pref ? stage_pref : (32u << 10);
     const uint32_t ring = ring_pref ? ring_pref : (128u << 10);
     g.stage_bytes = std::min(stage_cap, (bytes + 15u) & ~15u);
     g.stages = std::max<uint32_t>(kStoreLag + 1,

@@ -499,6 +499,8 @@ PYBIND11_MODULE(_infinistore, m) {
             py::arg("device") = -1, py::arg("stream") = 0, py::arg("scale") = 1)
         .def("set_copy_variant", &Connection::set_copy_variant)
         .def("set_max_ctas", &Connection::set_max_ctas)
+        .def("set_pipe_geometry", &Connection::set_pipe_geometry, py::arg("stage_bytes"),
+             py::arg("ring_bytes"))
         .def("set_device_lookup", &Connection::set_device_lookup)
         .def("set_streams", &Connection::set_streams)
         .def("device_lookup", &Connection::device_lookup)

@@ -55,6 +55,7 @@ class ClientConfig(_infinistore.ClientConfig):
     commit list one-way instead of waiting for a control-plane round trip - the writes are
     visible to every device-path reader when it returns (in-band commit), server-mediated
     lookups of OTHER connections follow within the TCP delivery time, as in the reference.
+    ``pipe_stage_kb`` / ``pipe_ring_kb``: ring geometry of the TMA pipeline (0 = default).
     """
 
     def __init__(self, **kwargs):
@@ -77,6 +78,8 @@ class ClientConfig(_infinistore.ClientConfig):
         self.max_ctas = kwargs.get("max_ctas", 0)
         self.streams = kwargs.get("streams", 4)
         self.posted_commit = bool(kwargs.get("posted_commit", False))
+        self.pipe_stage_kb = int(kwargs.get("pipe_stage_kb", 0))
+        self.pipe_ring_kb = int(kwargs.get("pipe_ring_kb", 0))
 
     def __repr__(self):
         return (
@@ -423,6 +426,8 @@ class InfinityConnection:
         self.conn.set_copy_variant(_COPY_VARIANTS[self.config.copy_variant])
         self.conn.set_max_ctas(int(self.config.max_ctas))
         self.conn.set_streams(int(self.config.streams))
+        self.conn.set_pipe_geometry(int(getattr(self.config, "pipe_stage_kb", 0)) << 10,
+                                    int(getattr(self.config, "pipe_ring_kb", 0)) << 10)
         self.conn.set_device_lookup(bool(self.config.device_lookup) and self.conn.server_has_hbm())
 
     def _bring_up(self):
