@@ -613,10 +613,15 @@ EncodeTiledFn encode_tiled_fn() {
 // Ring geometry: slots of up to `stage` bytes (16-byte multiple), as many as fit `ring` bytes.
 PipeGeometry pipe_geometry(uint32_t bytes, uint32_t stage_pref, uint32_t ring_pref) {
     PipeGeometry g;
-    // 32 KB slots, 4 of them: the best of the round-2 sweep on local HBM (3225 GB/s at 128 KB
-    // blocks = the copy engine's rate; 16 KB slots: 2982) - profiles/r2_lab_*.json
-    const uint32_t stage_cap = stage_pref ? stage_pref : (32u << 10);
-    const uint32_t ring = ring_pref ? ring_pref : (128u << 10);
+    // 16 KB slots, 4 of them (64 KB per CTA), ONE CTA per SM per launch: a single launch then
+    // runs a little below the best single-kernel geometry (32 KB x 4 at 128 KB per CTA: 3225
+    // vs 2561 GB/s on local HBM, equal over NVLink), but three such kernels fit an SM side by
+    // side, and that is what the API needs - the calls of a phase go round-robin over the
+    // connection's streams, and the next kernel must be able to start (descriptor fetch, index
+    // claims) while the previous one drains (store acknowledgements, system fence, commit):
+    // ~20 us of every 180 us call over NVLink otherwise (profiles/r2_bench_n2_ring*.json).
+    const uint32_t stage_cap = stage_pref ? stage_pref : (16u << 10);
+    const uint32_t ring = ring_pref ? ring_pref : (64u << 10);
     g.stage_bytes = std::min(stage_cap, (bytes + 15u) & ~15u);
     g.stages = std::max<uint32_t>(kStoreLag + 1,
                                   std::min<uint32_t>(kPipeMaxStages, ring / g.stage_bytes));
@@ -637,8 +642,9 @@ cudaError_t launch_kv_pipe_copy(const CopyLaunch& a, cudaStream_t stream) {
     // block then needs no cross-CTA counter), otherwise chunks of a few ring slots.
     // the ring takes most of an SM's shared memory: one CTA per SM is resident (two when the
     // ring was configured at half size), more would only queue behind them
-    const int resident = (g.smem > (110u << 10) ? 1 : 2) * sms;
-    int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, resident) : sms;
+    // one CTA per SM: the rest of the SM's shared memory is for the kernels of the connection's
+    // other streams (see pipe_geometry)
+    int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, sms) : sms;
     uint32_t chunk = a.bytes;
     if (a.n < uint32_t(ctas) || a.bytes > (1u << 20)) {
         const uint32_t per = g.stage_bytes * 4;
@@ -676,8 +682,7 @@ cudaError_t launch_kv_pipe_read(const ReadFusedLaunch& a, cudaStream_t stream) {
     cudaError_t e = ensure_pipe_attrs();
     if (e != cudaSuccess) return e;
     const PipeGeometry g = pipe_geometry(a.bytes, a.stage_bytes, a.ring_bytes);
-    const int resident = (g.smem > (110u << 10) ? 1 : 2) * sm_count();
-    int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, resident) : sm_count();
+    int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, sm_count()) : sm_count();
     ctas = int(std::min<uint32_t>(uint32_t(ctas), a.n));
     PipeReadArgs r{};
     r.key_bytes = a.key_bytes;
@@ -715,7 +720,7 @@ cudaError_t launch_kv_pipe_hnd(const HndLaunch& a, cudaStream_t stream) {
     tt = std::min<uint32_t>({tt, a.tokens, 256u});
     const uint32_t tile_bytes = uint32_t(tt * tok_bytes);
     if (tile_bytes > (96u << 10)) return cudaErrorInvalidValue;  // one token must fit a slot
-    const uint32_t ring = a.ring_bytes ? a.ring_bytes : (128u << 10);
+    const uint32_t ring = a.ring_bytes ? a.ring_bytes : (64u << 10);
     const uint32_t stages = std::max<uint32_t>(kStoreLag + 1,
                                                std::min<uint32_t>(kPipeMaxStages, ring / tile_bytes));
     CUtensorMap tmap;
@@ -740,8 +745,7 @@ cudaError_t launch_kv_pipe_hnd(const HndLaunch& a, cudaStream_t stream) {
     h.stages = stages;
     h.status = a.status;
     const size_t smem = size_t(stages) * tile_bytes;
-    const int resident = (smem > (110u << 10) ? 1 : 2) * sm_count();
-    int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, resident) : sm_count();
+    int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, sm_count()) : sm_count();
     ctas = int(std::min<uint32_t>(uint32_t(ctas), a.n));
     kv_pipe_hnd_kernel<<<ctas, 64, smem, stream>>>(tmap, h);
     return cudaGetLastError();
