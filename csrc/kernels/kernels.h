@@ -273,8 +273,26 @@ struct BcastLaunch {
     uint32_t n = 0;
     uint32_t bytes = 0;
     int max_ctas = 0;
+    // optional in-band readiness: u32 per block INSIDE the multicast mapping; the writer adds
+    // 1 per finished chunk to every replica's copy (multimem.red.release.sys)
+    uint32_t* flags_mc = nullptr;
 };
 cudaError_t launch_kv_bcast_nvls(const BcastLaunch& a, cudaStream_t stream);
+// chunks the broadcast kernel splits a block of `bytes` into = what a block's flag reaches
+uint32_t bcast_chunks_per_block(uint32_t bytes);
+
+// Reader of an NVLS broadcast: waits for each block's flag in the LOCAL replica
+// (ld.acquire.sys, no host sync) and then copies the block out of the local replica.
+struct ReadyLaunch {
+    const CopyDesc* descs = nullptr;      // src = local replica address, dst = destination
+    uint32_t n = 0;
+    uint32_t bytes = 0;
+    const uint32_t* flags_local = nullptr;  // this GPU's replica of the flag array
+    uint32_t ready_value = 0;               // flag value that means "block complete"
+    uint32_t* status = nullptr;             // kStatMiss counts blocks that never became ready
+    int max_ctas = 0;
+};
+cudaError_t launch_kv_read_when_ready(const ReadyLaunch& a, cudaStream_t stream);
 
 // Number of SMs of the current device (cached per device).
 int sm_count();

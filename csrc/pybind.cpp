@@ -887,17 +887,38 @@ PYBIND11_MODULE(_infinistore, m) {
     k.def("fp8_block_bytes", &kernels::fp8_block_bytes);
     k.def(
         "kv_bcast_nvls",
-        [](uint64_t descs, uint32_t n, uint32_t bytes, int max_ctas, uint64_t stream) {
+        [](uint64_t descs, uint32_t n, uint32_t bytes, int max_ctas, uint64_t stream,
+           uint64_t flags_mc) {
             kernels::BcastLaunch L;
             L.descs = as_ptr<const kernels::CopyDesc>(descs);
             L.n = n;
             L.bytes = bytes;
             L.max_ctas = max_ctas;
+            L.flags_mc = as_ptr<uint32_t>(flags_mc);
             const cudaError_t e = kernels::launch_kv_bcast_nvls(L, as_ptr<CUstream_st>(stream));
             if (e != cudaSuccess) throw std::runtime_error(cudaGetErrorString(e));
         },
         py::arg("descs"), py::arg("n"), py::arg("bytes"), py::arg("max_ctas") = 0,
-        py::arg("stream") = 0);
+        py::arg("stream") = 0, py::arg("flags_mc") = 0);
+    k.def("bcast_chunks_per_block", &kernels::bcast_chunks_per_block);
+    k.def(
+        "kv_read_when_ready",
+        [](uint64_t descs, uint32_t n, uint32_t bytes, uint64_t flags_local, uint32_t ready_value,
+           int max_ctas, uint64_t stream, uint64_t status) {
+            kernels::ReadyLaunch L;
+            L.descs = as_ptr<const kernels::CopyDesc>(descs);
+            L.n = n;
+            L.bytes = bytes;
+            L.flags_local = as_ptr<const uint32_t>(flags_local);
+            L.ready_value = ready_value;
+            L.max_ctas = max_ctas;
+            L.status = as_ptr<uint32_t>(status);
+            const cudaError_t e = kernels::launch_kv_read_when_ready(L, as_ptr<CUstream_st>(stream));
+            if (e != cudaSuccess) throw std::runtime_error(cudaGetErrorString(e));
+        },
+        py::arg("descs"), py::arg("n"), py::arg("bytes"), py::arg("flags_local"),
+        py::arg("ready_value"), py::arg("max_ctas") = 0, py::arg("stream") = 0,
+        py::arg("status") = 0);
 
     // ------------------------------------------------------------ comparison baselines
     // The reference's data-movement pattern, reproduced for bench/ only (never on the

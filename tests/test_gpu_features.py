@@ -233,6 +233,37 @@ def test_nvls_prefix_broadcast():
             assert torch.equal(rep[slots[i]:slots[i] + bs].cpu(), src[i * bs:(i + 1) * bs].cpu())
 
 
+def test_nvls_broadcast_with_in_band_ready_flags():
+    """The reader kernel is launched BEFORE the writer's broadcast: it waits for each block's
+    flag in its local replica (multimem.red.release by the writer, ld.acquire by the reader)
+    and copies the block out - no host synchronisation between the two."""
+    if torch.cuda.device_count() < 2 or not nvls_available():
+        pytest.skip("needs >= 2 GPUs with NVLS multicast")
+    ndev = torch.cuda.device_count()
+    nblk, bs = 96, 256 << 10
+    bc = PrefixBroadcaster(list(range(ndev)), nblk * bs, flag_slots=nblk)
+    src = torch.randint(0, 255, (nblk * bs,), dtype=torch.uint8, device="cuda:0")
+    offs = [i * bs for i in range(nblk)]
+    ids = list(range(nblk))
+    for rnd in range(2):  # flags count up: a slot can be broadcast again
+        src.random_(0, 255)
+        torch.cuda.synchronize(0)
+        want = bc.expected_flags(ids, bs)
+        outs, stats = [], []
+        for r in range(1, ndev):  # readers first: they spin on their local flags
+            dst = torch.zeros(nblk * bs, dtype=torch.uint8, device=f"cuda:{r}")
+            st = torch.zeros(8, dtype=torch.int32, device=f"cuda:{r}")
+            bc.read_when_ready(r, dst, offs, offs, bs, ids, expect=want, status=st)
+            outs.append(dst)
+            stats.append(st)
+        bc.broadcast(src, offs, offs, bs, flag_ids=ids)
+        for r in range(1, ndev):
+            torch.cuda.synchronize(r)
+            assert int(stats[r - 1][0]) == 0, "a block never became ready"
+            assert torch.equal(outs[r - 1].cpu(), src.cpu()), (rnd, r)
+        torch.cuda.synchronize(0)
+
+
 def _nvls_server(replica_mb=64):
     cfg = native.ServerConfig()
     cfg.service_port = 0

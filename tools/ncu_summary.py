@@ -19,6 +19,11 @@ METRICS = [
     "sm__throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
     "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
+    # NVLink: user payload vs protocol overhead, per direction (32-byte granularity)
+    "nvltx__bytes.sum", "nvltx__bytes_data_user.sum", "nvltx__bytes_data_protocol.sum",
+    "nvlrx__bytes.sum", "nvlrx__bytes_data_user.sum", "nvlrx__bytes_data_protocol.sum",
+    "nvltx__bytes_packet_request_data_user.sum", "nvltx__bytes_packet_response_data_user.sum",
+    "nvlrx__bytes_packet_request_data_user.sum", "nvlrx__bytes_packet_response_data_user.sum",
 ]
 
 
@@ -35,10 +40,33 @@ def main():
         for r in rows[2:]:
             name = r[hdr.index("Kernel Name")]
             lines.append(f"kernel: {name[:140]}")
+            vals = {}
             for m in METRICS:
                 if m in hdr:
                     i = hdr.index(m)
                     lines.append(f"  {m:62s} {r[i]:>14s} {units[i]}")
+                    vals[m] = (r[i], units[i])
+
+            def num(m):
+                if m not in vals:
+                    return None
+                try:
+                    v = float(vals[m][0].replace(",", ""))
+                except ValueError:
+                    return None
+                u = vals[m][1].lower()
+                scale = {"kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "byte": 1.0,
+                         "ns": 1e-9, "us": 1e-6, "usecond": 1e-6, "msecond": 1e-3,
+                         "nsecond": 1e-9, "ms": 1e-3, "second": 1.0}.get(u, 1.0)
+                return v * scale
+
+            t = num("gpu__time_duration.sum")
+            for d in ("tx", "rx"):
+                tot, usr = num(f"nvl{d}__bytes.sum"), num(f"nvl{d}__bytes_data_user.sum")
+                if t and tot and usr and tot > 0:
+                    lines.append(f"  -> NVLink {d}: {tot / t / 1e9:8.1f} GB/s on the wire, "
+                                 f"{usr / t / 1e9:8.1f} GB/s user payload, "
+                                 f"payload share {100 * usr / tot:5.1f} %")
             lines.append("")
     src = list(csv.reader(io.StringIO(run([rep, "--page", "source", "--csv"]))))
     body, seen = [], 0
