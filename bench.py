@@ -66,35 +66,164 @@ def parse_args():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-extra", action="store_true", help="skip configs 3-5, latency, baselines")
     p.add_argument("--pool-gb", type=int, default=0, help="HBM pool per GPU (0 = auto: what fits)")
+    p.add_argument("--ref-size-mb", type=int, default=1024,
+                   help="reference arm: MB written+read per step (one round)")
     p.add_argument("--quick", action="store_true",
                    help="small shapes for a functional check (256 MB x 2 rounds, no extras)")
     return p.parse_args()
 
 
 def reference_arm(args):
-    """The reference cannot be built on this image: `pip install` of /root/reference succeeds
-    only for its Python files; the native module needs infiniband/verbs.h, libuv,
-    flatbuffers and boost, none of which exist here."""
-    why = None
+    """The UNMODIFIED reference, built by baseline/build_reference.sh into baseline/_ref (its
+    own sources and Makefile; the missing system libraries are stood in for as that script
+    documents) and driven through its own stock entry points, in clean interpreters that
+    cannot see this repo: `python -m infinistore.server` and `python -m infinistore.benchmark`
+    (infinistore/benchmark.py: fresh UUID keys per iteration, `--steps` batches per phase,
+    one sync() per phase, host clock - the methodology this file mirrors).
+
+    Only the reference's LOCAL_GPU data path can run here: its RDMA path needs an RDMA NIC,
+    and the box has none (the verbs stand-in creates no queue pairs).  One server + one
+    benchmark client per rank, client tensors on the rank's GPU, pool in pinned host memory
+    (where the reference always keeps it).  A reference step is ONE round of `--ref-size-mb`
+    written and read back (the b200 arm moves 16 x 4 GiB per step; at PCIe speed that would
+    take minutes per step) - rates, not step times, are comparable."""
+    import re
+    import signal
+    import socket
+    import urllib.request
+
     ref = os.path.join(ROOT, "baseline", "_ref")
-    if not os.path.isdir(os.path.join(ref, "infinistore")):
-        why = ("baseline/_ref/infinistore is absent: the offline pip install of /root/reference "
-               "only yields its .py files and its native module cannot be built (no libibverbs, "
-               "libuv, flatbuffers, boost headers on this image)")
+    so = [f for f in (os.listdir(os.path.join(ref, "infinistore"))
+                      if os.path.isdir(os.path.join(ref, "infinistore")) else [])
+          if f.startswith("_infinistore") and f.endswith(".so")]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def unavailable(why):
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": why[:300]}))
+
+    if not so:
+        return unavailable("baseline/_ref has no native module: run baseline/build_reference.sh "
+                           "(needs uvloop's libuv, flashinfer's spdlog headers, nvcc toolchain)")
+    env = dict(os.environ, PYTHONPATH=ref,
+               PATH=os.path.join(ROOT, "baseline", "refshim", "bin") + os.pathsep + os.environ.get("PATH", ""))
+    env.pop("PYTHONHOME", None)
+    probe = subprocess.run([sys.executable, "-c", "import infinistore._infinistore, torch; "
+                            "assert torch.cuda.is_available()"],
+                           cwd="/tmp", env=env, capture_output=True, text=True, timeout=600)
+    if probe.returncode != 0:
+        last = (probe.stderr.strip().splitlines() or ["import failed"])[-1]
+        return unavailable("reference module does not import / no GPU: " + last)
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("gloo")  # host-side rendezvous only: no GPU work in this process
+
+    def allmax(x):
+        if dist is None:
+            return x
+        import torch
+
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    size_mb, block_kb = args.ref_size_mb, args.block_kb
+    rounds = max(args.steps, args.warmup, 1)
+    base = args.base_port or (27000 + (int(os.environ.get("MASTER_PORT", "0")) % 2000))
+    sport, mport = base + 2 * rank, base + 2 * rank + 1
+    pool_gb = (rounds * size_mb + 1023) // 1024 + 2
+    log = open(f"/tmp/ref_server_{rank}.log", "w")
+    server = subprocess.Popen(
+        [sys.executable, "-m", "infinistore.server", "--service-port", str(sport),
+         "--manage-port", str(mport), "--prealloc-size", str(pool_gb),
+         "--minimal-allocate-size", str(min(block_kb, 64)), "--log-level", "warning"],
+        cwd="/tmp", env=env, stdout=log, stderr=subprocess.STDOUT, start_new_session=True)
+    result = None
+    try:
+        deadline = time.time() + 300  # pinning tens of GB of host memory takes a while
+        up = False
+        while time.time() < deadline and server.poll() is None:
+            try:
+                urllib.request.urlopen(f"http://127.0.0.1:{mport}/kvmap_len", timeout=2).read()
+                socket.create_connection(("127.0.0.1", sport), timeout=2).close()
+                up = True
+                break
+            except Exception:  # noqa: BLE001
+                time.sleep(0.5)
+        if not up:
+            log.flush()
+            tail = open(log.name).read()[-300:].replace("\n", " | ")
+            raise RuntimeError("reference server did not come up: " + tail)
+
+        def bench(iterations):
+            r = subprocess.run(
+                [sys.executable, "-m", "infinistore.benchmark", "--service-port", str(sport),
+                 "--size", str(size_mb), "--block-size", str(block_kb), "--iteration", str(iterations),
+                 "--src-gpu", str(local_rank), "--dst-gpu", str(local_rank), "--steps", str(args.layers)],
+                cwd="/tmp", env=env, capture_output=True, text=True, timeout=1800)
+            m = re.search(r"write cache: ([0-9.]+) MB/s, read cache: ([0-9.]+) MB/s", r.stdout)
+            if r.returncode != 0 or not m:
+                raise RuntimeError("reference benchmark failed: " +
+                                   (r.stderr.strip().splitlines() or r.stdout.strip().splitlines() or ["?"])[-1])
+            return float(m.group(1)), float(m.group(2))
+
+        if args.warmup:
+            bench(args.warmup)
+            urllib.request.urlopen(urllib.request.Request(f"http://127.0.0.1:{mport}/purge", method="POST"),
+                                   timeout=60).read()
+        if dist is not None:
+            dist.barrier()
+        w_mibs, r_mibs = bench(args.steps)
+        mib = float(size_mb * args.steps)
+        secs = mib / w_mibs + mib / r_mibs  # the benchmark's own write_sum + read_sum
+        result = (secs, w_mibs, r_mibs)
+    except Exception as e:  # noqa: BLE001
+        result = e
+    finally:
+        try:
+            os.killpg(server.pid, signal.SIGINT)
+            server.wait(20)
+        except Exception:  # noqa: BLE001
+            try:
+                os.killpg(server.pid, signal.SIGKILL)
+            except Exception:  # noqa: BLE001
+                pass
+    failed = allmax(1.0 if isinstance(result, Exception) else 0.0)
+    if failed:
+        why = repr(result) if isinstance(result, Exception) else "another rank failed"
+        unavailable("reference run failed: " + why)
     else:
-        # Import the reference in a clean interpreter (cwd and PYTHONPATH outside this repo),
-        # so that nothing of this repo - in particular its `infinistore` alias package - can
-        # stand in for the reference's own native module.
-        env = dict(os.environ, PYTHONPATH=ref)
-        r = subprocess.run([sys.executable, "-c", "import infinistore._infinistore"],
-                           cwd="/tmp", env=env, capture_output=True, text=True, timeout=300)
-        if r.returncode != 0:
-            last = (r.stderr.strip().splitlines() or ["import failed"])[-1]
-            why = ("reference native module not buildable offline (needs libibverbs/libuv/"
-                   "flatbuffers/boost headers): " + last)
-    if why is None:
-        why = "reference imported but needs an active mlx5 RDMA port, absent on this box"
-    print(json.dumps({"impl": "reference", "unavailable": why[:300]}))
+        secs = allmax(result[0])
+        bytes_per_step = 2 * (size_mb << 20)
+        value = world * bytes_per_step * args.steps / secs / 1e9
+        if rank == 0:
+            print(json.dumps({
+                "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(secs / args.steps * 1e3, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "fp32 pages (dtype-blind bytes)",
+                "data": "synthetic random KV pages, fresh UUID keys per iteration",
+                "impl": "reference",
+                "config": {"model": "paged-KV blocks", "block_kb": block_kb,
+                           "bytes_per_gpu_per_step": bytes_per_step, "layers_per_phase": args.layers,
+                           "data_path": "LOCAL_GPU (TCP + CUDA IPC + per-block cudaMemcpyAsync to the "
+                                        "pinned host pool): the only reference path that can run "
+                                        "without an RDMA NIC",
+                           "driver": "python -m infinistore.server + python -m infinistore.benchmark "
+                                     "(stock), one pair per GPU",
+                           "clock": "the reference benchmark's own host clock around issue+sync",
+                           "build": "unmodified sources, reference Makefile, stand-ins for missing "
+                                    "system libraries: baseline/build_reference.sh"},
+                "breakdown": {"write_MiBps_rank0": result[1], "read_MiBps_rank0": result[2]},
+                "e2e": None, "gpu_launches": 0,
+            }))
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def bind_to_gpu_numa_node(index: int):
