@@ -139,7 +139,8 @@ def reference_arm(args):
     pool_gb = (rounds * size_mb + 1023) // 1024 + 2
     log = open(f"/tmp/ref_server_{rank}.log", "w")
     server = subprocess.Popen(
-        [sys.executable, "-m", "infinistore.server", "--service-port", str(sport),
+        [sys.executable, os.path.join(ROOT, "baseline", "ref_server_launch.py"),
+         "--service-port", str(sport),
          "--manage-port", str(mport), "--prealloc-size", str(pool_gb),
          "--minimal-allocate-size", str(min(block_kb, 64)), "--log-level", "warning"],
         cwd="/tmp", env=env, stdout=log, stderr=subprocess.STDOUT, start_new_session=True)
@@ -214,8 +215,9 @@ def reference_arm(args):
                            "data_path": "LOCAL_GPU (TCP + CUDA IPC + per-block cudaMemcpyAsync to the "
                                         "pinned host pool): the only reference path that can run "
                                         "without an RDMA NIC",
-                           "driver": "python -m infinistore.server + python -m infinistore.benchmark "
-                                     "(stock), one pair per GPU",
+                           "driver": "infinistore.server.main (stock; baseline/ref_server_launch.py "
+                                     "tolerates the container's refusal of oom_score_adj) + "
+                                     "python -m infinistore.benchmark (stock), one pair per GPU",
                            "clock": "the reference benchmark's own host clock around issue+sync",
                            "build": "unmodified sources, reference Makefile, stand-ins for missing "
                                     "system libraries: baseline/build_reference.sh"},

@@ -210,9 +210,32 @@ def lab_mcast(out, two):
     out["mcast"] = rows
 
 
+def lab_fp8(out, two):
+    """fp8 KV path kernels: GB/s of fp8 payload bytes (the bytes that cross the fabric)."""
+    rows = []
+    elems, pages = 65536, 2048  # 128 KB bf16 pages -> 64 KB e4m3 + 2 KB scales
+    bb = ops.fp8_block_bytes(elems)
+    stride = (bb + 255) // 256 * 256
+    x = (torch.randn(pages, elems, device="cuda:0") * 3).to(torch.bfloat16)
+    out_t = torch.zeros_like(x)
+    for name, pool_dev in (("local", "cuda:0"),) + ((("nvlink", "cuda:1"),) if two else ()):
+        pool = torch.zeros(pages, stride, dtype=torch.uint8, device=pool_dev)
+        wd = ops.make_descs([x[i].data_ptr() for i in range(pages)],
+                            [pool[i].data_ptr() for i in range(pages)], "cuda:0")
+        rd = ops.make_descs([pool[i].data_ptr() for i in range(pages)],
+                            [out_t[i].data_ptr() for i in range(pages)], "cuda:0")
+        row = {"path": name}
+        for v in ("auto", "pipe4", "ldst"):
+            row["write_" + v] = gbps(ev_time(lambda: ops.kv_write_fp8(wd, elems, variant=v), 0), pages * bb)
+            row["read_" + v] = gbps(ev_time(lambda: ops.kv_read_fp8(rd, elems, variant=v), 0), pages * bb)
+        rows.append(row)
+        print("fp8", row, flush=True)
+    out["fp8"] = rows
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="ce,geom,sizes,bidir,mcast")
+    ap.add_argument("--only", default="ce,geom,sizes,bidir,mcast,fp8")
     ap.add_argument("--out", default="gpurun_out/r2_lab.json")
     a = ap.parse_args()
     two = torch.cuda.device_count() >= 2

@@ -1430,11 +1430,12 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
         // (>= SM-count blocks of <= 1 MB), wasteful when a few large blocks are split over
         // many CTAs (measured: 4 MB single-block read 83 us vs 42 us) - then resolve each key
         // once with the lookup kernel and feed the descriptors to kv_copy.
-        // ... and for a handful of blocks (<= 4 MB in all) the single launch wins on latency:
-        // lookup + copy + re-check would be three kernels for microseconds of data.
+        // ... and for a handful of SMALL blocks (<= 64 KB each, <= 4 MB in all) the single
+        // launch wins on latency; a lone large block must be spread over many CTAs instead
+        // (measured over NVLink: one 1 MB block through one CTA's 64 KB ring takes 98 us).
         const bool whole_blocks =
-            uint32_t(block_size) <= (1u << 20) &&
-            (n >= size_t(kernels::sm_count()) || n * size_t(block_size) <= (4u << 20));
+            (uint32_t(block_size) <= (1u << 20) && n >= size_t(kernels::sm_count())) ||
+            (uint32_t(block_size) <= (64u << 10) && n * size_t(block_size) <= (4u << 20));
         if (!fp8_elems && whole_blocks) {
             // one kernel: hash + probe + move
             kernels::ReadFusedLaunch R;

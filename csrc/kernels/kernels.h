@@ -129,7 +129,8 @@ struct Fp8Launch {
     int max_ctas = 0;
     bool all_local = false;
     bool aligned16 = true;  // every page address is 16-byte aligned (bulk copies need it)
-    int variant = 0;        // 0 = auto (TMA pipeline when supported), 1 = ld/st kernels
+    int variant = 0;        // 0 = auto (TMA pipeline, 8 compute warps), 1 = ld/st kernels,
+                            // 2 = TMA pipeline with 4 compute warps (A/B)
 };
 // The TMA-pipelined flavour (kv_fp8_pipe.cu): needs elems % 512 == 0 and aligned pages.
 bool fp8_pipe_supported(const Fp8Launch& a);

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kThreads)
 cudaError_t launch_kv_write_fp8(const Fp8Launch& a, cudaStream_t stream) {
     if (a.n == 0 || a.elems == 0) return cudaSuccess;
     if (a.group != kRow || a.elems % kRow != 0) return cudaErrorInvalidValue;
-    if (a.variant == 0 && fp8_pipe_supported(a)) return launch_kv_fp8_pipe(a, true, stream);
+    if (a.variant != 1 && fp8_pipe_supported(a)) return launch_kv_fp8_pipe(a, true, stream);
     Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n, nullptr, !a.all_local};
     if (!a.table || !a.done) pub.recs = nullptr;
     // whole pages per CTA when there are enough of them (single-CTA commit, see kv_copy.cu)
@@ -211,7 +211,7 @@ cudaError_t launch_kv_write_fp8(const Fp8Launch& a, cudaStream_t stream) {
 cudaError_t launch_kv_read_fp8(const Fp8Launch& a, cudaStream_t stream) {
     if (a.n == 0 || a.elems == 0) return cudaSuccess;
     if (a.group != kRow || a.elems % kRow != 0) return cudaErrorInvalidValue;
-    if (a.variant == 0 && fp8_pipe_supported(a)) return launch_kv_fp8_pipe(a, false, stream);
+    if (a.variant != 1 && fp8_pipe_supported(a)) return launch_kv_fp8_pipe(a, false, stream);
     uint32_t chunk = kChunkElems;
     if (a.n >= uint32_t(sm_count()) && a.elems <= (1u << 19)) chunk = a.elems;
     const uint32_t cpb = (a.elems + chunk - 1) / chunk;

@@ -37,9 +37,7 @@ constexpr uint32_t kTileElems = kRow * kTileRows;
 constexpr uint32_t kTileBf16 = kTileElems * 2;  // 16 KB
 constexpr uint32_t kTileQ = kTileElems;         // 8 KB
 constexpr uint32_t kTileScale = kTileRows * 4;  // 256 B
-constexpr int kComputeWarps = 4;
 constexpr int kInStages = 4, kOutStages = 3, kLag = 2;
-constexpr int kThreads = (3 + kComputeWarps) * 32;  // loader, storer, control, compute...
 constexpr float kE4m3Max = 448.f;
 
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
@@ -74,8 +72,9 @@ struct Fp8Shape {
     uint32_t n, elems, chunk_elems, cpb;
 };
 
-template <bool WRITE>
-__global__ void __launch_bounds__(kThreads)
+// NCW compute warps (4 or 8) besides the loader, storer and control warps.
+template <bool WRITE, int NCW>
+__global__ void __launch_bounds__((3 + NCW) * 32)
     kv_fp8_pipe_kernel(const CopyDesc* __restrict__ descs, const Fp8Shape sh, Publish pub,
                        uint32_t* status) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -91,10 +90,10 @@ __global__ void __launch_bounds__(kThreads)
     if (threadIdx.x == 0) {
         for (int s = 0; s < kInStages; ++s) {
             mbar_init(&bars.full_in[s], 1);
-            mbar_init(&bars.empty_in[s], kComputeWarps);
+            mbar_init(&bars.empty_in[s], NCW);
         }
         for (int t = 0; t < kOutStages; ++t) {
-            mbar_init(&bars.full_out[t], kComputeWarps);
+            mbar_init(&bars.full_out[t], NCW);
             mbar_init(&bars.empty_out[t], 1);
         }
         mbar_fence_init();
@@ -180,7 +179,7 @@ __global__ void __launch_bounds__(kThreads)
         const uint8_t* in = in_ring + s * kInTile;
         uint8_t* out = out_ring + t * kOutTile;
         if (d.src) {
-            for (uint32_t r = cw * 2 + half; r < rows; r += kComputeWarps * 2) {
+            for (uint32_t r = cw * 2 + half; r < rows; r += NCW * 2) {
                 if constexpr (WRITE) {
                     const uint4 v = *reinterpret_cast<const uint4*>(in + (size_t(r) * kRow + hl * 8) * 2);
                     float2 f[4] = {bf16x2_to_f2(v.x), bf16x2_to_f2(v.y), bf16x2_to_f2(v.z),
@@ -243,11 +242,15 @@ cudaError_t ensure_attrs() {
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(g_mu);
     if (dev < 0 || dev >= 64 || g_attr[dev]) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(kv_fp8_pipe_kernel<true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemWrite));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(kv_fp8_pipe_kernel<false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemRead));
+    cudaError_t e = cudaSuccess;
+    auto set = [&](auto* fn, size_t bytes) {
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    };
+    set(kv_fp8_pipe_kernel<true, 4>, kSmemWrite);
+    set(kv_fp8_pipe_kernel<true, 8>, kSmemWrite);
+    set(kv_fp8_pipe_kernel<false, 4>, kSmemRead);
+    set(kv_fp8_pipe_kernel<false, 8>, kSmemRead);
     if (e != cudaSuccess) return e;
     g_attr[dev] = true;
     return cudaSuccess;
@@ -279,10 +282,15 @@ cudaError_t launch_kv_fp8_pipe(const Fp8Launch& a, bool write, cudaStream_t stre
     int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, 2 * sms) : 2 * sms;  // ~90 KB smem: 2 per SM
     const Fp8Shape sh = shape_of(a, ctas);
     ctas = int(std::min<uint64_t>(uint64_t(ctas), uint64_t(sh.n) * sh.cpb));
-    if (write)
-        kv_fp8_pipe_kernel<true><<<ctas, kThreads, kSmemWrite, stream>>>(a.descs, sh, pub, a.status);
+    const bool wide = a.variant != 2;  // 8 compute warps unless variant 2 asks for 4 (A/B)
+    if (write && wide)
+        kv_fp8_pipe_kernel<true, 8><<<ctas, (3 + 8) * 32, kSmemWrite, stream>>>(a.descs, sh, pub, a.status);
+    else if (write)
+        kv_fp8_pipe_kernel<true, 4><<<ctas, (3 + 4) * 32, kSmemWrite, stream>>>(a.descs, sh, pub, a.status);
+    else if (wide)
+        kv_fp8_pipe_kernel<false, 8><<<ctas, (3 + 8) * 32, kSmemRead, stream>>>(a.descs, sh, pub, a.status);
     else
-        kv_fp8_pipe_kernel<false><<<ctas, kThreads, kSmemRead, stream>>>(a.descs, sh, pub, a.status);
+        kv_fp8_pipe_kernel<false, 4><<<ctas, (3 + 4) * 32, kSmemRead, stream>>>(a.descs, sh, pub, a.status);
     return cudaGetLastError();
 }
 

@@ -214,7 +214,7 @@ def fp8_block_bytes(elems: int, group: int = 128) -> int:
     return K.fp8_block_bytes(elems, group)
 
 
-FP8_VARIANTS = {"auto": 0, "ldst": 1}
+FP8_VARIANTS = {"auto": 0, "ldst": 1, "pipe4": 2}
 
 
 def kv_write_fp8(descs: torch.Tensor, elems: int, max_ctas: int = 0,
