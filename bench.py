@@ -104,6 +104,7 @@ def reference_arm(args):
         if rank == 0:
             print(json.dumps({"impl": "reference", "unavailable": why[:300]}))
 
+    bind_to_gpu_numa_node(local_rank)  # same placement help as the b200 arm; children inherit it
     if not so:
         return unavailable("baseline/_ref has no native module: run baseline/build_reference.sh "
                            "(needs uvloop's libuv, flashinfer's spdlog headers, nvcc toolchain)")
@@ -182,7 +183,21 @@ def reference_arm(args):
         w_mibs, r_mibs = bench(args.steps)
         mib = float(size_mb * args.steps)
         secs = mib / w_mibs + mib / r_mibs  # the benchmark's own write_sum + read_sum
-        result = (secs, w_mibs, r_mibs)
+        e2e = None
+        if not args.no_e2e:
+            urllib.request.urlopen(urllib.request.Request(f"http://127.0.0.1:{mport}/purge", method="POST"),
+                                   timeout=60).read()
+            if dist is not None:
+                dist.barrier()
+            r = subprocess.run(
+                [sys.executable, os.path.join(ROOT, "baseline", "ref_e2e.py"), "--service-port", str(sport),
+                 "--size-mb", str(size_mb), "--block-kb", str(block_kb), "--layers", str(args.layers),
+                 "--steps", "2", "--gpu", str(local_rank)],
+                cwd="/tmp", env=env, capture_output=True, text=True, timeout=1200)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode == 0 and lines:
+                e2e = json.loads(lines[-1])
+        result = (secs, w_mibs, r_mibs, e2e)
     except Exception as e:  # noqa: BLE001
         result = e
     finally:
@@ -202,6 +217,17 @@ def reference_arm(args):
         secs = allmax(result[0])
         bytes_per_step = 2 * (size_mb << 20)
         value = world * bytes_per_step * args.steps / secs / 1e9
+        e2e_json = None
+        have_e2e = allmax(0.0 if result[3] else 1.0) == 0.0
+        if have_e2e:
+            e_secs = allmax(result[3]["e2e_secs"])
+            e2e_json = {"value": round(world * bytes_per_step * result[3]["steps"] / e_secs / 1e9, 3),
+                        "unit": "GB/s", "h2d_bytes_per_step": result[3]["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": result[3]["d2h_bytes_per_step"],
+                        "steps": result[3]["steps"], "verified": result[3]["verified"],
+                        "how": "baseline/ref_e2e.py: the reference's public API, pinned host pages "
+                               "H2D per layer + synchronize before each write (its servers copy "
+                               "on their own streams), D2H of the result"}
         if rank == 0:
             print(json.dumps({
                 "metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world,
@@ -222,7 +248,7 @@ def reference_arm(args):
                            "build": "unmodified sources, reference Makefile, stand-ins for missing "
                                     "system libraries: baseline/build_reference.sh"},
                 "breakdown": {"write_MiBps_rank0": result[1], "read_MiBps_rank0": result[2]},
-                "e2e": None, "gpu_launches": 0,
+                "e2e": e2e_json, "gpu_launches": 0,
             }))
     if dist is not None:
         dist.destroy_process_group()

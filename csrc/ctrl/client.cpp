@@ -1256,6 +1256,9 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             F.max_ctas = L.max_ctas;
             F.all_local = all_local;
             F.aligned16 = (align_or & 15) == 0;
+            // TMA-pipelined flavour over NVLink (write 622 vs 537, read 705 vs 507 GB/s of fp8
+            // bytes), per-thread flavour on local HBM (1705 vs 1223): profiles/r2_lab_fp8_2gpu.json
+            F.variant = all_local ? 1 : 0;
             e = write ? kernels::launch_kv_write_fp8(F, stream) : kernels::launch_kv_read_fp8(F, stream);
         } else {
             e = kernels::launch_kv_copy(L, stream);
@@ -1434,9 +1437,13 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
         // launch wins on latency; a lone large block must be spread over many CTAs instead
         // (measured over NVLink: one 1 MB block through one CTA's 64 KB ring takes 98 us).
         const bool whole_blocks =
-            (uint32_t(block_size) <= (1u << 20) && n >= size_t(kernels::sm_count())) ||
-            (uint32_t(block_size) <= (64u << 10) && n * size_t(block_size) <= (4u << 20));
-        if (!fp8_elems && whole_blocks) {
+            uint32_t(block_size) <= (1u << 20) && n >= size_t(kernels::sm_count());
+        // A handful of blocks (<= 4 MB in all): latency matters, not bandwidth.  One launch of
+        // the ld/st flavour, which splits a block into 32 KB chunks over CTAs (each resolves its
+        // block's key itself - a few redundant probes) and re-checks the entries in the same
+        // kernel: lookup + copy + validate would be three launches (+7..15 us per read).
+        const bool small_batch = !whole_blocks && n * size_t(block_size) <= (4u << 20);
+        if (!fp8_elems && (whole_blocks || small_batch)) {
             // one kernel: hash + probe + move
             kernels::ReadFusedLaunch R;
             R.key_bytes = ctx->ring_d + at_bytes;
@@ -1456,7 +1463,7 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             // always: a purge (or an eviction) may free a block while a device-path read is
             // copying it; the post-copy tag check turns that into a reported miss
             R.validate = true;
-            R.variant = copy_variant_;
+            R.variant = small_batch ? int(kernels::kCopyLdSt256) : copy_variant_;
             R.stage_bytes = pipe_stage_;
             R.ring_bytes = pipe_ring_;
             e = kernels::launch_kv_read_fused(R, stream);
@@ -1490,6 +1497,7 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
                 F.status = ctx->status_d;
                 F.max_ctas = grid_cap;
                 F.aligned16 = (align_or & 15) == 0;
+                F.variant = all_remote ? 0 : 1;
                 e = kernels::launch_kv_read_fp8(F, stream);
             } else if (e == cudaSuccess) {
                 kernels::CopyLaunch L;
