@@ -1061,6 +1061,27 @@ uint8_t* Connection::seg_dev_ptr(DevCtx* ctx, uint32_t seg) {
     return mp->dev_ptr;
 }
 
+// The index shards beyond shard 0 as seen from `ctx`'s device: the k-th HBM segment (in id
+// order) that carries a table is shard k.  *all_local is cleared when a shard's table lives
+// on another GPU.
+kernels::IndexShards Connection::index_shards(DevCtx* ctx, bool* all_local) {
+    kernels::IndexShards sh;
+    uint32_t n = 0;
+    for (uint32_t id = 0; id < segs_.size() && n < kernels::kMaxIndexShards; ++id) {
+        if (segs_[id].kind != kSegDeviceIpc || !segs_[id].index_slots) continue;
+        if (n > 0) {
+            uint8_t* base = seg_dev_ptr(ctx, id);
+            if (!base) break;  // cannot map it: stay with the shards found so far
+            sh.table[n - 1] = reinterpret_cast<kernels::IndexBucket*>(base + segs_[id].index_off);
+            sh.mask[n - 1] = kernels::index_bucket_mask(segs_[id].index_slots);
+            if (all_local && ctx->seg_remote[id]) *all_local = false;
+        }
+        ++n;
+    }
+    sh.n = n;
+    return sh;
+}
+
 // Move n blocks between the caller's tensor and the pool.  local_off[i] * scale is the
 // byte offset of block i from base_ptr.
 int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scale,
@@ -1238,6 +1259,10 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             L.recs = reinterpret_cast<const kernels::IndexEntry*>(ctx->ring_d + at_rec);
             L.table = table;
             L.table_mask = table_mask;
+            bool shards_local = true;
+            L.shards = index_shards(ctx, &shards_local);
+            L.all_local = L.all_local && shards_local;
+            all_local = all_local && shards_local;
             L.done = reinterpret_cast<uint32_t*>(ctx->zeros + ctx->zeros_alloc(size_t(m) * 12));
         }
         const uint64_t t_launch0 = now_ns();
@@ -1251,6 +1276,7 @@ int Connection::move_blocks(bool write, const uint64_t* local_off, uint64_t scal
             F.recs = L.recs;
             F.table = L.table;
             F.table_mask = L.table_mask;
+            F.shards = L.shards;
             F.done = L.done;
             F.status = L.status;
             F.max_ctas = L.max_ctas;
@@ -1456,6 +1482,7 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             R.align_or = copy_variant_ == kernels::kCopyLdSt ? (align_or | 16) : align_or;
             R.table = reinterpret_cast<const kernels::IndexBucket*>(m0->dev_ptr + segs_[0].index_off);
             R.table_mask = kernels::index_bucket_mask(segs_[0].index_slots);
+            R.shards = index_shards(ctx, nullptr);
             R.nsegs = nsegs;
             for (uint32_t s = 0; s < nsegs; ++s) R.seg_base[s] = seg_base[s];
             R.status = ctx->status_d;
@@ -1476,6 +1503,8 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             Q.n = uint32_t(n);
             Q.table = reinterpret_cast<const kernels::IndexBucket*>(m0->dev_ptr + segs_[0].index_off);
             Q.table_mask = kernels::index_bucket_mask(segs_[0].index_slots);
+    Q.shards = index_shards(ctx, nullptr);
+            Q.shards = index_shards(ctx, nullptr);
             Q.nsegs = nsegs;
             for (uint32_t s = 0; s < nsegs; ++s) Q.seg_base[s] = seg_base[s];
             auto* out = reinterpret_cast<kernels::CopyDesc*>(
@@ -1519,6 +1548,7 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
                 V.found_at = Q.found_at;
                 V.n = uint32_t(n);
                 V.table = Q.table;
+                V.shards = Q.shards;
                 V.status = ctx->status_d;
                 e = kernels::launch_index_validate(V, stream);
                 stats_.kernel_launches += 1;
@@ -1580,6 +1610,7 @@ const kernels::CopyDesc* Connection::resolve_descs(DevCtx* ctx, const std::vecto
     Q.n = uint32_t(n);
     Q.table = reinterpret_cast<const kernels::IndexBucket*>(m0->dev_ptr + segs_[0].index_off);
     Q.table_mask = kernels::index_bucket_mask(segs_[0].index_slots);
+    Q.shards = index_shards(ctx, nullptr);
     Q.nsegs = uint32_t(std::min<size_t>(segs_.size(), kernels::LookupLaunch::kMaxSegs));
     for (uint32_t sgi = 0; sgi < Q.nsegs; ++sgi)
         Q.seg_base[sgi] = reinterpret_cast<uint64_t>(seg_dev_ptr(ctx, sgi));
@@ -1776,6 +1807,7 @@ int Connection::match_via_device_index(const std::vector<std::string_view>& keys
     Q.n = uint32_t(n);
     Q.table = reinterpret_cast<const kernels::IndexBucket*>(m0->dev_ptr + segs_[0].index_off);
     Q.table_mask = kernels::index_bucket_mask(segs_[0].index_slots);
+    Q.shards = index_shards(ctx, nullptr);
     const size_t words = (n + 31) / 32;
     Q.present = reinterpret_cast<uint32_t*>(ctx->scratch + ctx->scratch_alloc(words * 4));
     Q.ticket = reinterpret_cast<uint32_t*>(ctx->zeros + ctx->zeros_alloc(4));

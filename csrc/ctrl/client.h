@@ -34,8 +34,10 @@ namespace istore {
 
 namespace kernels {
 struct CopyDesc;
+struct IndexShards;
 }
 using kernels_CopyDesc = kernels::CopyDesc;
+using kernels_IndexShards = kernels::IndexShards;
 
 // Non-owning: the key bytes must stay valid for the duration of the call.
 struct KeyOffset {
@@ -209,6 +211,7 @@ class Connection {
     // them, device-index entries included
     int discard_blocks(const uint64_t* addrs, size_t count);
     uint8_t* seg_dev_ptr(DevCtx* ctx, uint32_t seg);
+    kernels_IndexShards index_shards(DevCtx* ctx, bool* all_local);
     const kernels_CopyDesc* resolve_descs(DevCtx* ctx, const std::vector<KeyOffset>& blocks,
                                           size_t base, size_t n, int block_size, uint64_t dst_base,
                                           const std::vector<RemoteBlock>* rb, void* stream);

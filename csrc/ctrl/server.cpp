@@ -89,13 +89,17 @@ bool Server::add_segment(std::string* err) {
                      ? 0
                      : cfg_.pool_devices[next_pool_dev_++ % cfg_.pool_devices.size()];
         // 2 entries per block: at half load a key's two 8-way buckets are practically never
-        // both full; the table (segment 0 only) must also cover the blocks of segments added
-        // later by --auto-increase
+        // both full.  Every INITIAL segment (one per --pool-devices entry) carries a table:
+        // the index is sharded by key fingerprint over them, so the probes and claims of all
+        // clients spread over the pool GPUs instead of landing on segment 0's.  Together the
+        // shards must also cover the blocks of segments added later by --auto-increase,
+        // which carry no table (the shard count is fixed at start).
         const size_t growth = cfg_.auto_increase ? 8 : 1;
         size_t slots = cfg_.index_slots
                            ? next_pow2(cfg_.index_slots)
                            : next_pow2(std::max<size_t>(1024, 2 * growth * (bytes / granule)));
-        if (id != 0) slots = 0;
+        if (!first_round || index_shards_.size() >= kernels::kMaxIndexShards) slots = 0;
+        if (slots) index_shards_.push_back(id);
         seg = fabric::SegmentOwner::create_device(id, device, bytes, granule, slots, err);
     } else {
         seg = fabric::SegmentOwner::create_host(id, bytes, granule, port_, err);
@@ -235,14 +239,14 @@ void Server::stop() {
     listen_fd_ = epoll_fd_ = wake_fd_ = -1;
     quarantine_.clear();
     store_->purge();
-    if (erase_buf_ || erase_stream_) {
-        DevGuard g(segs_.empty() ? -1 : segs_[0]->info().device);
-        if (erase_buf_) cudaFree(erase_buf_);
-        if (erase_stream_) cudaStreamDestroy(static_cast<cudaStream_t>(erase_stream_));
-        erase_buf_ = nullptr;
-        erase_stream_ = nullptr;
-        erase_cap_ = 0;
+    for (EraseCtx& ec : erase_) {
+        if (!ec.buf && !ec.stream) continue;
+        DevGuard g(ec.device);
+        if (ec.buf) cudaFree(ec.buf);
+        if (ec.stream) cudaStreamDestroy(static_cast<cudaStream_t>(ec.stream));
     }
+    erase_.clear();
+    index_shards_.clear();
     segs_.clear();
 }
 
@@ -278,47 +282,79 @@ ServerStats Server::stats() {
 }
 
 bool Server::erase_from_device_index(const std::vector<KVStore::Victim>& victims) {
-    if (segs_.empty()) return true;
-    const fabric::SegmentOwner& seg0 = *segs_[0];
-    if (seg0.info().kind != kSegDeviceIpc || !seg0.info().index_slots) return true;
-    DevGuard g(seg0.info().device);
-    std::vector<kernels::EraseRec> recs;
-    recs.reserve(victims.size());
+    if (segs_.empty() || index_shards_.empty()) return true;
+    // group the victims by the shard their fingerprint selects; each shard's table is erased
+    // by a kernel on the GPU that holds it
+    const uint32_t nshards = uint32_t(index_shards_.size());
+    std::vector<std::vector<kernels::EraseRec>> per(nshards);
     for (auto& v : victims)
-        recs.push_back(kernels::EraseRec{v.hash.h1, v.hash.h2, v.block->addr()});
-    if (erase_cap_ < recs.size()) {
-        if (erase_buf_) cudaFree(erase_buf_);
-        erase_buf_ = nullptr;
-        erase_cap_ = std::max<size_t>(4096, next_pow2(recs.size()));
-        if (cudaMalloc(&erase_buf_, erase_cap_ * sizeof(kernels::EraseRec)) != cudaSuccess) {
-            erase_cap_ = 0;
+        per[kernels::index_shard_of(v.hash.h2, nshards)].push_back(
+            kernels::EraseRec{v.hash.h1, v.hash.h2, v.block->addr()});
+    if (erase_.size() < nshards) erase_.resize(nshards);
+    bool ok = true;
+    for (uint32_t sh = 0; sh < nshards && ok; ++sh) {
+        std::vector<kernels::EraseRec>& recs = per[sh];
+        if (recs.empty()) continue;
+        const fabric::SegmentOwner& seg = *segs_[index_shards_[sh]];
+        if (seg.info().kind != kSegDeviceIpc || !seg.info().index_slots) continue;
+        DevGuard g(seg.info().device);
+        EraseCtx& ec = erase_[sh];
+        ec.device = seg.info().device;
+        if (ec.cap < recs.size()) {
+            if (ec.buf) cudaFree(ec.buf);
+            ec.buf = nullptr;
+            ec.cap = std::max<size_t>(4096, next_pow2(recs.size()));
+            if (cudaMalloc(&ec.buf, ec.cap * sizeof(kernels::EraseRec)) != cudaSuccess) {
+                ec.cap = 0;
+                (void)cudaGetLastError();
+                return false;
+            }
+        }
+        kernels::EraseLaunch E;
+        E.recs = static_cast<const kernels::EraseRec*>(ec.buf);
+        E.n = uint32_t(recs.size());
+        E.table = reinterpret_cast<kernels::IndexBucket*>(static_cast<uint8_t*>(seg.base()) +
+                                                         seg.info().index_off);
+        E.table_mask = kernels::index_bucket_mask(seg.info().index_slots);
+        // The space may be handed out again only once no reader can resolve the old entries.
+        // Own non-blocking stream: clients living in this process keep their kernels running.
+        if (!ec.stream && cudaStreamCreateWithFlags(reinterpret_cast<cudaStream_t*>(&ec.stream),
+                                                    cudaStreamNonBlocking) != cudaSuccess) {
+            ec.stream = nullptr;
             (void)cudaGetLastError();
             return false;
         }
+        cudaStream_t st = static_cast<cudaStream_t>(ec.stream);
+        ok = cudaMemcpyAsync(ec.buf, recs.data(), recs.size() * sizeof(kernels::EraseRec),
+                             cudaMemcpyHostToDevice, st) == cudaSuccess &&
+             kernels::launch_index_erase(E, st) == cudaSuccess &&
+             cudaStreamSynchronize(st) == cudaSuccess;
+        if (!ok) LOG_ERROR("index erase failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    kernels::EraseLaunch E;
-    E.recs = static_cast<const kernels::EraseRec*>(erase_buf_);
-    E.n = uint32_t(recs.size());
-    E.table = reinterpret_cast<kernels::IndexBucket*>(static_cast<uint8_t*>(seg0.base()) +
-                                                     seg0.info().index_off);
-    E.table_mask = kernels::index_bucket_mask(seg0.info().index_slots);
-    // The space may be handed out again only once no reader can resolve the old entries.
-    // Own non-blocking stream: clients living in this process keep their kernels running.
-    if (!erase_stream_ &&
-        cudaStreamCreateWithFlags(reinterpret_cast<cudaStream_t*>(&erase_stream_),
-                                  cudaStreamNonBlocking) != cudaSuccess) {
-        erase_stream_ = nullptr;
-        (void)cudaGetLastError();
-        return false;
-    }
-    cudaStream_t st = static_cast<cudaStream_t>(erase_stream_);
-    const bool ok =
-        cudaMemcpyAsync(erase_buf_, recs.data(), recs.size() * sizeof(kernels::EraseRec),
-                        cudaMemcpyHostToDevice, st) == cudaSuccess &&
-        kernels::launch_index_erase(E, st) == cudaSuccess &&
-        cudaStreamSynchronize(st) == cudaSuccess;
-    if (!ok) LOG_ERROR("index erase failed: %s", cudaGetErrorString(cudaGetLastError()));
     return ok;
+}
+
+// Shard 0's table plus the others, as the server's own process addresses them (load()).
+void Server::fill_index_view(kernels::IndexBucket** table, uint64_t* mask,
+                             kernels::IndexShards* shards) const {
+    *table = nullptr;
+    *mask = 0;
+    uint32_t n = 0;
+    for (uint32_t id : index_shards_) {
+        const fabric::SegmentOwner& seg = *segs_[id];
+        auto* t = reinterpret_cast<kernels::IndexBucket*>(static_cast<uint8_t*>(seg.base()) +
+                                                         seg.info().index_off);
+        const uint64_t m = kernels::index_bucket_mask(seg.info().index_slots);
+        if (n == 0) {
+            *table = t;
+            *mask = m;
+        } else {
+            shards->table[n - 1] = t;
+            shards->mask[n - 1] = m;
+        }
+        ++n;
+    }
+    shards->n = n;
 }
 
 bool Server::evict_some(size_t want, bool replica) {
@@ -485,9 +521,8 @@ long Server::load(const std::string& path, std::string* err) {
             L.bytes = size;
             L.align_or = size % 16 ? 1 : 0;
             L.multicast = seg.info().kind == kSegReplica && size % 16 == 0;
-            const fabric::SegmentOwner& seg0 = *segs_[0];
             void* rec_dev = nullptr;
-            if (seg0.info().index_slots && seg0.info().kind == kSegDeviceIpc) {
+            if (!index_shards_.empty()) {
                 if (!scratch) {
                     cudaMalloc(reinterpret_cast<void**>(&scratch), 64);
                     cudaMemset(scratch, 0, 64);
@@ -495,9 +530,7 @@ long Server::load(const std::string& path, std::string* err) {
                 cudaMalloc(&rec_dev, sizeof(rec));
                 cudaMemcpy(rec_dev, &rec, sizeof(rec), cudaMemcpyHostToDevice);
                 L.recs = static_cast<const kernels::IndexEntry*>(rec_dev);
-                L.table = reinterpret_cast<kernels::IndexBucket*>(static_cast<uint8_t*>(seg0.base()) +
-                                                                 seg0.info().index_off);
-                L.table_mask = kernels::index_bucket_mask(seg0.info().index_slots);
+                fill_index_view(&L.table, &L.table_mask, &L.shards);
                 L.done = scratch;
             }
             const cudaError_t e = kernels::launch_kv_copy(L, nullptr);

@@ -30,6 +30,11 @@
 
 namespace istore {
 
+namespace kernels {
+struct IndexBucket;
+struct IndexShards;
+}  // namespace kernels
+
 // Service-time histogram of one opcode: bucket b counts requests that took < 2^b microseconds
 // (bucket 0: < 1 us ... bucket 23: everything longer than ~4 s).
 struct OpTiming {
@@ -132,6 +137,8 @@ class Server {
     // (or quarantine them when the erase cannot be confirmed).
     void release_dropped(std::vector<KVStore::Victim>& victims);
     void note_publish_failures(uint32_t n);
+    void fill_index_view(kernels::IndexBucket** table, uint64_t* mask,
+                         kernels::IndexShards* shards) const;
 
     int handle_exchange(Conn* c);
     int handle_pool_map(Conn* c);
@@ -166,9 +173,15 @@ class Server {
     bool index_incomplete_ = false;  // some block is in the host map but not in the HBM index
     ServerStats stats_;
     std::vector<uint8_t> scratch_;  // reply serialisation buffer
-    void* erase_buf_ = nullptr;     // device staging of the erase kernel's records
-    size_t erase_cap_ = 0;          // records
-    void* erase_stream_ = nullptr;  // cudaStream_t
+    // segment ids that carry an index shard, in shard order (shard k = index_shards_[k])
+    std::vector<uint32_t> index_shards_;
+    struct EraseCtx {  // per shard: device staging + stream of the erase kernel
+        int device = -1;
+        void* buf = nullptr;
+        size_t cap = 0;        // records
+        void* stream = nullptr;  // cudaStream_t
+    };
+    std::vector<EraseCtx> erase_;
     // evicted blocks whose index entries could not be erased: their space stays reserved
     std::vector<KVStore::Victim> quarantine_;
 };

@@ -105,6 +105,28 @@ IS_HD void fence(bool sys) {
 #endif
 }
 
+// ---------------------------------------------------------------- shards
+struct TableRef {
+    IndexBucket* table;
+    uint64_t mask;
+    uint32_t shard;
+};
+// The table a key lives in (kernels.h: IndexShards).
+IS_HD TableRef select_shard(const IndexBucket* t0, uint64_t m0, const IndexShards& sh, uint64_t h2) {
+    const uint32_t s = index_shard_of(h2, sh.n);
+    if (s == 0) return TableRef{const_cast<IndexBucket*>(t0), m0, 0};
+    return TableRef{sh.table[s - 1], sh.mask[s - 1], s};
+}
+// slot ids that leave a kernel (or a kernel phase) carry their shard in the top 3 bits
+IS_HD uint32_t pack_slot(uint32_t shard, uint32_t slot_plus1) {
+    return slot_plus1 ? (shard << kSlotShardShift) | slot_plus1 : 0u;
+}
+IS_HD uint32_t slot_local(uint32_t packed) { return packed & ((1u << kSlotShardShift) - 1); }
+IS_HD IndexBucket* table_of_slot(const IndexBucket* t0, const IndexShards& sh, uint32_t packed) {
+    const uint32_t s = packed >> kSlotShardShift;
+    return s == 0 ? const_cast<IndexBucket*>(t0) : sh.table[s - 1];
+}
+
 // ---------------------------------------------------------------- placement
 IS_HD uint64_t bucket_a(uint64_t h1, uint64_t mask) { return h1 & mask; }
 IS_HD uint64_t bucket_b(uint64_t h1, uint64_t h2, uint64_t mask) {

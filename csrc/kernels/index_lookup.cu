@@ -40,9 +40,12 @@ constexpr uint32_t kStageBytes = 8192;  // shared staging per warp; longer range
 
 template <bool kAcceptClaimed>
 __device__ __forceinline__ idx::Found probe(const LookupLaunch& a, const KeyHash& kh) {
+    const idx::TableRef t = idx::select_shard(a.table, a.table_mask, a.shards, kh.h2);
     // reads resolve present keys (bucket A first), match / exist probes mostly absent ones
-    return a.present ? idx::find<true, kAcceptClaimed>(a.table, a.table_mask, kh)
-                     : idx::find<false, kAcceptClaimed>(a.table, a.table_mask, kh);
+    idx::Found f = a.present ? idx::find<true, kAcceptClaimed>(t.table, t.mask, kh)
+                             : idx::find<false, kAcceptClaimed>(t.table, t.mask, kh);
+    f.slot_plus1 = idx::pack_slot(t.shard, f.slot_plus1);
+    return f;
 }
 
 __global__ void __launch_bounds__(kLookupThreads)
@@ -119,7 +122,8 @@ __global__ void __launch_bounds__(kLookupThreads)
     if (i >= a.n) return;
     const LookupLaunch::FoundAt f = a.found_at[i];
     if (!f.slot_plus1) return;  // a miss was counted by the lookup
-    if (!idx::still_valid(a.table, f.slot_plus1, f.tag)) {
+    if (!idx::still_valid(idx::table_of_slot(a.table, a.shards, f.slot_plus1),
+                          idx::slot_local(f.slot_plus1), f.tag)) {
         atomicAdd(a.status + kStatMiss, 1u);
         atomicAdd(a.status + kStatStale, 1u);
     }

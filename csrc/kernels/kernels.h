@@ -56,6 +56,28 @@ static_assert(sizeof(IndexWay) == 24 && sizeof(IndexBucket) == 256, "index bucke
 // the bucket mask.
 inline uint64_t index_bucket_mask(uint64_t slots) { return slots / kIndexWays - 1; }
 
+// Sharded index.  A server with several pool GPUs (--pool-devices 0,1,...) keeps one table
+// per initial HBM segment; a key lives in the table its fingerprint selects - independent of
+// where its block lives - so probes and claims spread over the pool GPUs instead of all
+// landing on segment 0's.  Launch structs carry shard 0 as `table` / `table_mask` and the
+// others here (n <= 1: unsharded).  Slot ids handed around by the kernels carry the shard in
+// their top 3 bits.
+constexpr uint32_t kMaxIndexShards = 8;
+constexpr uint32_t kSlotShardShift = 29;
+struct IndexShards {
+    uint32_t n = 0;  // total number of shards including shard 0
+    IndexBucket* table[kMaxIndexShards - 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint64_t mask[kMaxIndexShards - 1] = {0, 0, 0, 0, 0, 0, 0};
+};
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint32_t index_shard_of(uint64_t h2, uint32_t nshards) {
+    // bits 20..52 of the verifier half: not used by the way preference (top 3 bits) and only
+    // mixed into the bucket choice
+    return nshards <= 1 ? 0u : uint32_t((h2 >> 20) % nshards);
+}
+
 enum Status : int {
     kStatMiss = 0,         // blocks skipped by a read because the key was not in the index
     kStatPublishFail = 1,  // index insertions that found the table full
@@ -88,6 +110,7 @@ struct CopyLaunch {
     int max_ctas = 0;                 // 0 = pick from the problem size
     unsigned long long* trace = nullptr;  // optional per-CTA %globaltimer stamps (bench only)
     bool all_local = false;  // every destination and the index table are in this GPU's own HBM
+    IndexShards shards;      // further index shards (shard 0 = table / table_mask)
     uint32_t debug = 0;      // bench only, see publish.cuh
     bool multicast = false;  // every dst is an NVLS multicast address: store with multimem.st
     // TMA pipeline geometry (0 = default: 16 KB slots, 128 KB ring per CTA)
@@ -128,6 +151,7 @@ struct Fp8Launch {
     uint32_t* status = nullptr;
     int max_ctas = 0;
     bool all_local = false;
+    IndexShards shards;     // further index shards (shard 0 = table / table_mask)
     bool aligned16 = true;  // every page address is 16-byte aligned (bulk copies need it)
     int variant = 0;        // 0 = auto (TMA pipeline, 8 compute warps), 1 = ld/st kernels,
                             // 2 = TMA pipeline with 4 compute warps (A/B)
@@ -152,6 +176,7 @@ struct LookupLaunch {
     uint32_t n = 0;
     const IndexBucket* table = nullptr;
     uint64_t table_mask = 0;  // bucket mask
+    IndexShards shards;       // further index shards
     // segment id -> mapped base pointer on the launching device
     static constexpr int kMaxSegs = 16;
     uint64_t seg_base[kMaxSegs] = {0};
@@ -186,6 +211,7 @@ struct ValidateLaunch {
     const LookupLaunch::FoundAt* found_at = nullptr;
     uint32_t n = 0;
     const IndexBucket* table = nullptr;
+    IndexShards shards;  // further index shards (found_at slots carry the shard)
     uint32_t* status = nullptr;
 };
 cudaError_t launch_index_validate(const ValidateLaunch& a, cudaStream_t stream);
@@ -217,6 +243,7 @@ struct ReadFusedLaunch {
     uint64_t align_or = 0;               // OR of every destination address
     const IndexBucket* table = nullptr;
     uint64_t table_mask = 0;  // bucket mask
+    IndexShards shards;       // further index shards
     static constexpr int kMaxSegs = 16;
     uint64_t seg_base[kMaxSegs] = {0};
     uint32_t nsegs = 0;

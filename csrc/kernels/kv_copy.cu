@@ -107,7 +107,8 @@ int sm_count() {
 
 cudaError_t launch_kv_copy(const CopyLaunch& a, cudaStream_t stream) {
     if (a.n == 0 || a.bytes == 0) return cudaSuccess;
-    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n, a.trace, !a.all_local, a.debug};
+    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n, a.trace, !a.all_local, a.debug,
+                a.shards};
     if (!a.table || !a.done) pub.recs = nullptr;
     const int sms = sm_count();
 

@@ -195,7 +195,8 @@ cudaError_t launch_kv_write_fp8(const Fp8Launch& a, cudaStream_t stream) {
     if (a.n == 0 || a.elems == 0) return cudaSuccess;
     if (a.group != kRow || a.elems % kRow != 0) return cudaErrorInvalidValue;
     if (a.variant != 1 && fp8_pipe_supported(a)) return launch_kv_fp8_pipe(a, true, stream);
-    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n, nullptr, !a.all_local};
+    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n, nullptr, !a.all_local, 0,
+                a.shards};
     if (!a.table || !a.done) pub.recs = nullptr;
     // whole pages per CTA when there are enough of them (single-CTA commit, see kv_copy.cu)
     uint32_t chunk = kChunkElems;

@@ -276,7 +276,8 @@ cudaError_t launch_kv_fp8_pipe(const Fp8Launch& a, bool write, cudaStream_t stre
     if (!fp8_pipe_supported(a)) return cudaErrorInvalidValue;
     cudaError_t e = ensure_attrs();
     if (e != cudaSuccess) return e;
-    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n, nullptr, !a.all_local};
+    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n, nullptr, !a.all_local, 0,
+                a.shards};
     if (!write || !a.table || !a.done) pub.recs = nullptr;
     const int sms = sm_count();
     int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, 2 * sms) : 2 * sms;  // ~90 KB smem: 2 per SM

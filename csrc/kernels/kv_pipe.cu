@@ -231,6 +231,7 @@ struct PipeReadArgs {
     uint64_t dst_base;
     const IndexBucket* table;
     uint64_t table_mask;
+    IndexShards shards;
     uint64_t seg_base[ReadFusedLaunch::kMaxSegs];
     uint32_t nsegs;
     uint32_t* status;
@@ -271,7 +272,8 @@ __global__ void __launch_bounds__(kPipeThreads)
         uint32_t vslot0 = 0, vtag0 = 0, vslot1 = 0, vtag1 = 0;  // scalars: no local memory
         auto recheck = [&](uint32_t p) {
             const uint32_t slot = p ? vslot1 : vslot0, tag = p ? vtag1 : vtag0;
-            if (slot && !idx::still_valid(a.table, slot, tag) && a.status) {
+            if (slot && a.status &&
+                !idx::still_valid(idx::table_of_slot(a.table, a.shards, slot), idx::slot_local(slot), tag)) {
                 atomicAdd(a.status + kStatMiss, 1u);
                 atomicAdd(a.status + kStatStale, 1u);
             }
@@ -290,7 +292,9 @@ __global__ void __launch_bounds__(kPipeThreads)
             if (k < nitems) {
                 const uint32_t block = blockIdx.x + k * grid;
                 const KeyHash kh = hash_key(a.key_bytes + a.key_off[block], a.key_len[block]);
-                const idx::Found f = idx::find<false>(a.table, a.table_mask, kh);
+                const idx::TableRef t = idx::select_shard(a.table, a.table_mask, a.shards, kh.h2);
+                idx::Found f = idx::find<false>(t.table, t.mask, kh);
+                f.slot_plus1 = idx::pack_slot(t.shard, f.slot_plus1);
                 uint64_t src = 0;
                 if (f.slot_plus1) {
                     const uint32_t seg = uint32_t(f.addr >> 44) - 1;
@@ -634,7 +638,8 @@ cudaError_t launch_kv_pipe_copy(const CopyLaunch& a, cudaStream_t stream) {
     if ((a.bytes % 16) != 0 || (a.align_or & 15) != 0 || a.multicast) return cudaErrorInvalidValue;
     cudaError_t e = ensure_pipe_attrs();
     if (e != cudaSuccess) return e;
-    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n, a.trace, !a.all_local, a.debug};
+    Publish pub{a.recs, a.table, a.table_mask, a.done, a.status, a.n, a.trace, !a.all_local, a.debug,
+                a.shards};
     if (!a.table || !a.done) pub.recs = nullptr;
     const int sms = sm_count();
     const PipeGeometry g = pipe_geometry(a.bytes, a.stage_bytes, a.ring_bytes);
@@ -692,6 +697,7 @@ cudaError_t launch_kv_pipe_read(const ReadFusedLaunch& a, cudaStream_t stream) {
     r.dst_base = a.dst_base;
     r.table = a.table;
     r.table_mask = a.table_mask;
+    r.shards = a.shards;
     r.nsegs = a.nsegs;
     for (uint32_t s = 0; s < a.nsegs && s < uint32_t(ReadFusedLaunch::kMaxSegs); ++s)
         r.seg_base[s] = a.seg_base[s];

@@ -42,7 +42,9 @@ struct Resolved {
 
 __device__ Resolved resolve(const ReadFusedLaunch& a, uint32_t block) {
     const KeyHash kh = hash_key(a.key_bytes + a.key_off[block], a.key_len[block]);
-    const idx::Found f = idx::find<false>(a.table, a.table_mask, kh);
+    const idx::TableRef t = idx::select_shard(a.table, a.table_mask, a.shards, kh.h2);
+    idx::Found f = idx::find<false>(t.table, t.mask, kh);
+    f.slot_plus1 = idx::pack_slot(t.shard, f.slot_plus1);
     if (!f.slot_plus1) return Resolved{0, 0, 0};
     const uint32_t seg = uint32_t(f.addr >> 44) - 1;
     if (f.size < a.bytes || seg >= a.nsegs || !a.seg_base[seg]) return Resolved{0, 0, 0};
@@ -64,7 +66,8 @@ __global__ void __launch_bounds__(kThreads)
         uint32_t slot0 = 0, tag0 = 0, slot1 = 0, tag1 = 0;  // scalars: no local memory
         auto recheck = [&](uint32_t p) {
             const uint32_t slot = p ? slot1 : slot0, tag = p ? tag1 : tag0;
-            if (slot && !idx::still_valid(a.table, slot, tag)) {
+            if (slot && !idx::still_valid(idx::table_of_slot(a.table, a.shards, slot),
+                                          idx::slot_local(slot), tag)) {
                 atomicAdd(a.status + kStatMiss, 1u);
                 atomicAdd(a.status + kStatStale, 1u);
             }

@@ -37,6 +37,7 @@ struct Publish {
     // for local memory, also for peers reading it over NVLink, so gpu scope suffices.
     bool sys = true;
     uint32_t debug = 0;  // bench only: 1 = skip claim, 2 = skip fence, 4 = skip commit store
+    IndexShards shards;  // further index shards (shard 0 = table / mask)
 };
 
 __device__ inline unsigned long long globaltimer_ns() {
@@ -49,9 +50,10 @@ __device__ inline unsigned long long globaltimer_ns() {
 // committed (the key is already published - first writer wins - or its buckets are full).
 __device__ inline uint32_t claim_entry(const Publish& pub, const IndexEntry& rec) {
     bool full = false;
-    const uint32_t s = idx::claim(pub.table, pub.mask, rec, pub.sys, &full);
+    const idx::TableRef t = idx::select_shard(pub.table, pub.mask, pub.shards, rec.h2);
+    const uint32_t s = idx::claim(t.table, t.mask, rec, pub.sys, &full);
     if (full && pub.status) atomicAdd(pub.status + kStatPublishFail, 1u);
-    return s;
+    return idx::pack_slot(t.shard, s);
 }
 
 // The caller has just executed fence.acq_rel.sys; fence + relaxed store is a release
@@ -59,7 +61,8 @@ __device__ inline uint32_t claim_entry(const Publish& pub, const IndexEntry& rec
 // the epilogue, profiles/r1_ncu_kv_copy_*.txt).
 __device__ inline void commit_entry(const Publish& pub, uint32_t slot_plus1, uint32_t tag) {
     if (!slot_plus1 || (pub.debug & 4)) return;
-    idx::commit(pub.table, slot_plus1, tag, pub.sys);
+    idx::commit(idx::table_of_slot(pub.table, pub.shards, slot_plus1), idx::slot_local(slot_plus1),
+                tag, pub.sys);
 }
 
 constexpr int kCtrlBarrier = 1;  // named barrier shared by the copy warps and the control warp

@@ -960,6 +960,11 @@ PYBIND11_MODULE(_infinistore, m) {
 
     // ------------------------------------------------------------ unit-test access to the core
     py::module_ t = m.def_submodule("testing", "wire codec, allocator and hash for unit tests");
+    t.def("index_shard_of", [](py::bytes key, uint32_t nshards) {
+        const std::string k = key;
+        const KeyHash h = hash_key(reinterpret_cast<const uint8_t*>(k.data()), k.size());
+        return kernels::index_shard_of(h.h2, nshards);
+    });
     t.def("hash_key", [](py::bytes key) {
         const std::string s = key;
         const KeyHash h = hash_key(reinterpret_cast<const uint8_t*>(s.data()), s.size());

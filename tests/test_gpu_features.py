@@ -348,3 +348,63 @@ def test_nvls_replicated_blocks_through_the_store():
         assert torch.equal(dst.cpu(), want)  # GPU 0's replica received GPU 1's multicast
     finally:
         srv.stop()
+
+
+def test_index_is_sharded_over_the_pool_gpus():
+    """--pool-devices 0,1: every initial segment carries an index table and keys are spread
+    over them by fingerprint, so probes / claims do not all land on GPU 0.  Device-path writes,
+    reads, match and eviction must work across both shards, from clients on either GPU."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cfg = native.ServerConfig()
+    cfg.service_port = 0
+    cfg.host = "127.0.0.1"
+    cfg.pool_backend = "hbm"
+    cfg.pool_devices = [0, 1]
+    cfg.prealloc_bytes = 64 << 20
+    cfg.minimal_allocate_size = 16
+    cfg.evict = True
+    srv = native.Server(cfg)
+    port = srv.start()
+    try:
+        segs = srv.segments()
+        assert [s["index_slots"] > 0 for s in segs] == [True, True]
+        n, elems = 1500, 4096  # 16 KB fp32 pages
+        keys = [f"shard-{i}" for i in range(n)]
+        blocks = [(k, i * elems) for i, k in enumerate(keys)]
+        w = make_conn(port, device=0, device_lookup=True)
+        src = torch.randn(n * elems, device="cuda:0")
+        w.register_mr(src)
+        w.rdma_write_cache(src, [i * elems for i in range(n)], elems, w.allocate_rdma(keys, elems * 4))
+        w.sync()
+        assert not w.conn.index_incomplete()
+        # both tables hold entries: count non-empty fingerprints through a raw view of the shards
+        from infinistore_b200 import _infinistore as m
+        shard_of = [m.testing.index_shard_of(k.encode(), 2) for k in keys]
+        assert 0.35 < sum(shard_of) / n < 0.65  # fingerprints split the keys about evenly
+        for dev in (0, 1):
+            r = make_conn(port, device=dev, device_lookup=True)
+            dst = torch.zeros(n * elems, device=f"cuda:{dev}")
+            r.read_cache(dst, blocks, elems)
+            r.sync()
+            assert torch.equal(dst.cpu(), src.cpu()), dev
+            assert r.get_match_last_index(keys + ["absent"]) == n - 1
+            assert r.check_exist(keys[7]) and not r.check_exist("absent")
+        # fill the pool: LRU eviction must erase entries from whichever shard holds them
+        more = [f"shard-more-{i}" for i in range(8000)]
+        for a in range(0, len(more), 1000):
+            part = more[a:a + 1000]
+            w.rdma_write_cache(src, [i * elems for i in range(len(part))], elems,
+                               w.allocate_rdma(part, elems * 4))
+            w.sync()
+        assert srv.stats()["evicted"] > 0
+        r = make_conn(port, device=1, device_lookup=True)
+        gone = [k for k in keys if not r.check_exist(k)]
+        assert gone, "the oldest keys were evicted"
+        assert {shard_of[keys.index(k)] for k in gone} == {0, 1}  # erased from both shards
+        dst = torch.zeros(elems, device="cuda:1")
+        with pytest.raises(Exception):
+            r.read_cache(dst, [(gone[0], 0)], elems)
+            r.sync()
+    finally:
+        srv.stop()
