@@ -1469,9 +1469,11 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
         // block's key itself - a few redundant probes) and re-checks the entries in the same
         // kernel: lookup + copy + validate would be three launches (+7..15 us per read).
         const bool small_batch = !whole_blocks && n * size_t(block_size) <= (4u << 20);
-        if (!fp8_elems && (whole_blocks || small_batch)) {
+        kernels::ReadFusedLaunch R;
+        R.align_or = align_or;
+        const bool fp8_fused = fp8_elems && kernels::fp8_read_fused_supported(R, uint32_t(fp8_elems));
+        if (fp8_fused || (!fp8_elems && (whole_blocks || small_batch))) {
             // one kernel: hash + probe + move
-            kernels::ReadFusedLaunch R;
             R.key_bytes = ctx->ring_d + at_bytes;
             R.key_off = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_off);
             R.key_len = reinterpret_cast<const uint32_t*>(ctx->ring_d + at_len);
@@ -1493,7 +1495,10 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             R.variant = small_batch ? int(kernels::kCopyLdSt256) : copy_variant_;
             R.stage_bytes = pipe_stage_;
             R.ring_bytes = pipe_ring_;
-            e = kernels::launch_kv_read_fused(R, stream);
+            // fp8 pages: the resolver rides in the dequantising TMA pipeline (one launch
+            // instead of lookup + read + validate: 32 calls of 512 pages were launch-bound)
+            e = fp8_fused ? kernels::launch_kv_fp8_read_fused(R, uint32_t(fp8_elems), stream)
+                          : kernels::launch_kv_read_fused(R, stream);
             stats_.kernel_launches += 1;
         } else {
             kernels::LookupLaunch Q;
@@ -1503,7 +1508,6 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             Q.n = uint32_t(n);
             Q.table = reinterpret_cast<const kernels::IndexBucket*>(m0->dev_ptr + segs_[0].index_off);
             Q.table_mask = kernels::index_bucket_mask(segs_[0].index_slots);
-    Q.shards = index_shards(ctx, nullptr);
             Q.shards = index_shards(ctx, nullptr);
             Q.nsegs = nsegs;
             for (uint32_t s = 0; s < nsegs; ++s) Q.seg_base[s] = seg_base[s];

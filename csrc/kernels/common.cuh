@@ -107,6 +107,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {  // S
 __device__ __forceinline__ void mbar_fence_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {  // SYNCS.ARRIVE
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {  // SYNCS.ARRIVE.TRANS64
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
                  "r"(bytes)

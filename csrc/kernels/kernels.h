@@ -255,10 +255,16 @@ struct ReadFusedLaunch {
     uint32_t ring_bytes = 0;
 };
 // kCopyAuto / kCopyTma run the TMA pipeline (kv_pipe.cu) when the transfer is 16-byte
-// aligned and needs no post-copy validation; the ld/st kernel otherwise.
+// aligned and the blocks are >= kPipeMinBytes; the ld/st kernel otherwise.  Both re-check
+// every entry after its copy.
 cudaError_t launch_kv_read_fused(const ReadFusedLaunch& a, cudaStream_t stream);
 bool pipe_read_supported(const ReadFusedLaunch& a);
 cudaError_t launch_kv_pipe_read(const ReadFusedLaunch& a, cudaStream_t stream);
+// The same for fp8 pages ([elems x e4m3][elems/128 x fp32 scale] in the pool, bf16 at the
+// destination): resolver + dequantising TMA pipeline in one launch (kv_fp8_pipe.cu).
+// `bytes` / `variant` / ring geometry of the launch are ignored.
+bool fp8_read_fused_supported(const ReadFusedLaunch& a, uint32_t elems);
+cudaError_t launch_kv_fp8_read_fused(const ReadFusedLaunch& a, uint32_t elems, cudaStream_t stream);
 
 // One pool block -> 2 or 4 destinations with a thread-block cluster: the leader CTA fetches
 // the tile once (cp.async.bulk ... .multicast::cluster lands it in every CTA's shared

@@ -6,6 +6,11 @@
 //           then the in-band commit                                   [control warp]
 //   read  : payload + scales --cp.async.bulk--> SMEM, dequantise to bf16 in SMEM,
 //           --cp.async.bulk--> destination page.
+//   fused read : the (otherwise idle) third warp is the RESOLVER of resolve.cuh - it hashes the
+//           keys, probes the HBM index and feeds {pool block, destination} to loader and storer
+//           through the shared-memory queue, then re-checks the entries after the copy:
+//           read_cache_fp8 through the device index is ONE launch instead of lookup +
+//           read + validate.
 // Compared with kv_fp8.cu (every thread loads 16 bytes, stores 8, one scalar store per row
 // for the scale): the fabric sees whole 8 KB / 256 B bulk requests instead of 8-byte stores,
 // the scales of a tile travel as one vector, and the global loads no longer sit in the
@@ -20,10 +25,12 @@
 
 #include <algorithm>
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.h"
 #include "publish.cuh"
+#include "resolve.cuh"
 
 namespace istore::kernels {
 
@@ -40,9 +47,6 @@ constexpr uint32_t kTileScale = kTileRows * 4;  // 256 B
 constexpr int kInStages = 4, kOutStages = 3, kLag = 2;
 constexpr float kE4m3Max = 448.f;
 
-__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ uint16_t cvt_e4m3x2(float hi, float lo) {
     uint16_t r;
     asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
@@ -72,13 +76,16 @@ struct Fp8Shape {
     uint32_t n, elems, chunk_elems, cpb;
 };
 
-// NCW compute warps (4 or 8) besides the loader, storer and control warps.
-template <bool WRITE, int NCW>
+// NCW compute warps (4 or 8) besides the loader, storer and control / resolver warps.
+// FUSED (reads only): descriptors come from the resolver warp's queue instead of `descs`.
+template <bool WRITE, int NCW, bool FUSED>
 __global__ void __launch_bounds__((3 + NCW) * 32)
     kv_fp8_pipe_kernel(const CopyDesc* __restrict__ descs, const Fp8Shape sh, Publish pub,
-                       uint32_t* status) {
+                       uint32_t* status, const __grid_constant__ ResolveArgs ra) {
+    static_assert(!(WRITE && FUSED), "only reads resolve keys");
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ Smem bars;
+    __shared__ __align__(16) ResolveQueue rq;
     constexpr uint32_t kInTile = WRITE ? kTileBf16 : (kTileQ + kTileScale);
     constexpr uint32_t kOutTile = WRITE ? (kTileQ + kTileScale) : kTileBf16;
     uint8_t* in_ring = smem;
@@ -96,19 +103,32 @@ __global__ void __launch_bounds__((3 + NCW) * 32)
             mbar_init(&bars.full_out[t], NCW);
             mbar_init(&bars.empty_out[t], 1);
         }
+        if (FUSED) resolve_queue_init(rq);
         mbar_fence_init();
     }
     __syncthreads();
-    if (warp == 2) {  // control warp: in-band commit (writes only)
+    if (warp == 2) {  // control warp: in-band commit (writes) / resolver (fused reads)
         if (WRITE && pub.recs) control_warp(pub, lane, blockIdx.x, nitems, grid, sh.cpb, 64);
+        if (FUSED)
+            resolver_warp(ra, rq, sh.elems + sh.elems / kRow * 4, blockIdx.x, grid,
+                          sh.cpb, nitems, lane);
         return;
     }
-    // every role walks the same sequence of tiles
-    auto for_each_tile = [&](auto&& fn) {
+    // Every role walks the same sequence of tiles.  `role`: 0 loader, 1 storer (hands queue
+    // halves back to the resolver), 2 compute (never looks at a descriptor when FUSED: a
+    // missing block's tile is converted from whatever the slot holds and not stored).
+    auto for_each_tile = [&](auto role, auto&& fn) {
+        [[maybe_unused]] constexpr int kRole = decltype(role)::value;
         uint32_t q = 0;  // running tile number of this CTA
         for (uint32_t k = 0; k < nitems; ++k) {
             const uint32_t item = blockIdx.x + k * grid;
-            const CopyDesc d = descs[item / sh.cpb];
+            CopyDesc d;
+            if constexpr (!FUSED)
+                d = descs[item / sh.cpb];
+            else if constexpr (kRole == 2)
+                d = CopyDesc{1, 0};
+            else  // one lane per role makes this call: not warp wide
+                d = resolved_desc<kRole == 1, false>(rq, k, 0);
             const uint32_t e0 = (item % sh.cpb) * sh.chunk_elems;
             const uint32_t e1 = min(sh.elems, e0 + sh.chunk_elems);
             for (uint32_t e = e0; e < e1; e += kTileElems, ++q)
@@ -117,12 +137,13 @@ __global__ void __launch_bounds__((3 + NCW) * 32)
     };
     if (warp == 0) {  // ---- loader
         if (lane != 0) return;
-        for_each_tile([&](uint32_t q, const CopyDesc& d, uint32_t e, uint32_t rows, bool) {
+        for_each_tile(std::integral_constant<int, 0>{},
+                      [&](uint32_t q, const CopyDesc& d, uint32_t e, uint32_t rows, bool) {
             const uint32_t s = q % kInStages, use = q / kInStages;
             if (use) mbar_wait(&bars.empty_in[s], (use - 1) & 1);
             uint8_t* tile = in_ring + s * kInTile;
             if (!d.src) {
-                mbar_arrive_cta(&bars.full_in[s]);
+                mbar_arrive(&bars.full_in[s]);
                 return;
             }
             const uint8_t* src = reinterpret_cast<const uint8_t*>(d.src);
@@ -141,7 +162,8 @@ __global__ void __launch_bounds__((3 + NCW) * 32)
     if (warp == 1) {  // ---- storer
         if (lane == 0) {
             uint32_t released = 0;
-            for_each_tile([&](uint32_t q, const CopyDesc& d, uint32_t e, uint32_t rows, bool first) {
+            for_each_tile(std::integral_constant<int, 1>{},
+                          [&](uint32_t q, const CopyDesc& d, uint32_t e, uint32_t rows, bool first) {
                 const uint32_t t = q % kOutStages;
                 if (!d.src && first && status) atomicAdd(status + kStatMiss, 1u);
                 mbar_wait(&bars.full_out[t], (q / kOutStages) & 1);
@@ -158,12 +180,13 @@ __global__ void __launch_bounds__((3 + NCW) * 32)
                 bulk_commit();
                 bulk_wait_read<kLag>();
                 if (q >= uint32_t(kLag)) {
-                    mbar_arrive_cta(&bars.empty_out[released % kOutStages]);
+                    mbar_arrive(&bars.empty_out[released % kOutStages]);
                     ++released;
                 }
             });
             bulk_wait<0>();
             fence_proxy_async();
+            if (FUSED) resolved_done(rq, nitems, 0);
         }
         __syncwarp();
         if (WRITE && pub.recs) ctrl_barrier_arrive(64);
@@ -172,7 +195,8 @@ __global__ void __launch_bounds__((3 + NCW) * 32)
     // ---- compute warps: half-warp per row, two rows per step
     const uint32_t cw = warp - 3;
     const uint32_t half = lane >> 4, hl = lane & 15;
-    for_each_tile([&](uint32_t q, const CopyDesc& d, uint32_t, uint32_t rows, bool) {
+    for_each_tile(std::integral_constant<int, 2>{},
+                  [&](uint32_t q, const CopyDesc& d, uint32_t, uint32_t rows, bool) {
         const uint32_t s = q % kInStages, t = q % kOutStages;
         mbar_wait(&bars.full_in[s], (q / kInStages) & 1);
         if (q >= uint32_t(kOutStages)) mbar_wait(&bars.empty_out[t], (q / kOutStages - 1) & 1);
@@ -225,8 +249,8 @@ __global__ void __launch_bounds__((3 + NCW) * 32)
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-            mbar_arrive_cta(&bars.empty_in[s]);
-            mbar_arrive_cta(&bars.full_out[t]);
+            mbar_arrive(&bars.empty_in[s]);
+            mbar_arrive(&bars.full_out[t]);
         }
     });
 }
@@ -247,10 +271,11 @@ cudaError_t ensure_attrs() {
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
     };
-    set(kv_fp8_pipe_kernel<true, 4>, kSmemWrite);
-    set(kv_fp8_pipe_kernel<true, 8>, kSmemWrite);
-    set(kv_fp8_pipe_kernel<false, 4>, kSmemRead);
-    set(kv_fp8_pipe_kernel<false, 8>, kSmemRead);
+    set(kv_fp8_pipe_kernel<true, 4, false>, kSmemWrite);
+    set(kv_fp8_pipe_kernel<true, 8, false>, kSmemWrite);
+    set(kv_fp8_pipe_kernel<false, 4, false>, kSmemRead);
+    set(kv_fp8_pipe_kernel<false, 8, false>, kSmemRead);
+    set(kv_fp8_pipe_kernel<false, 8, true>, kSmemRead);
     if (e != cudaSuccess) return e;
     g_attr[dev] = true;
     return cudaSuccess;
@@ -284,14 +309,53 @@ cudaError_t launch_kv_fp8_pipe(const Fp8Launch& a, bool write, cudaStream_t stre
     const Fp8Shape sh = shape_of(a, ctas);
     ctas = int(std::min<uint64_t>(uint64_t(ctas), uint64_t(sh.n) * sh.cpb));
     const bool wide = a.variant != 2;  // 8 compute warps unless variant 2 asks for 4 (A/B)
+    const ResolveArgs none{};
     if (write && wide)
-        kv_fp8_pipe_kernel<true, 8><<<ctas, (3 + 8) * 32, kSmemWrite, stream>>>(a.descs, sh, pub, a.status);
+        kv_fp8_pipe_kernel<true, 8, false><<<ctas, (3 + 8) * 32, kSmemWrite, stream>>>(a.descs, sh, pub, a.status, none);
     else if (write)
-        kv_fp8_pipe_kernel<true, 4><<<ctas, (3 + 4) * 32, kSmemWrite, stream>>>(a.descs, sh, pub, a.status);
+        kv_fp8_pipe_kernel<true, 4, false><<<ctas, (3 + 4) * 32, kSmemWrite, stream>>>(a.descs, sh, pub, a.status, none);
     else if (wide)
-        kv_fp8_pipe_kernel<false, 8><<<ctas, (3 + 8) * 32, kSmemRead, stream>>>(a.descs, sh, pub, a.status);
+        kv_fp8_pipe_kernel<false, 8, false><<<ctas, (3 + 8) * 32, kSmemRead, stream>>>(a.descs, sh, pub, a.status, none);
     else
-        kv_fp8_pipe_kernel<false, 4><<<ctas, (3 + 4) * 32, kSmemRead, stream>>>(a.descs, sh, pub, a.status);
+        kv_fp8_pipe_kernel<false, 4, false><<<ctas, (3 + 4) * 32, kSmemRead, stream>>>(a.descs, sh, pub, a.status, none);
+    return cudaGetLastError();
+}
+
+// read_cache_fp8 through the device index in one launch: keys -> (resolver warp) -> pool
+// blocks -> dequantised pages.  Same contract as launch_kv_read_fused (misses and entries that
+// changed under the copy are counted in status[kStatMiss] / [kStatStale]).
+bool fp8_read_fused_supported(const ReadFusedLaunch& a, uint32_t elems) {
+    return elems > 0 && elems % 512 == 0 && (a.align_or & 15) == 0;
+}
+
+cudaError_t launch_kv_fp8_read_fused(const ReadFusedLaunch& a, uint32_t elems, cudaStream_t stream) {
+    if (a.n == 0) return cudaSuccess;
+    if (!fp8_read_fused_supported(a, elems)) return cudaErrorInvalidValue;
+    cudaError_t e = ensure_attrs();
+    if (e != cudaSuccess) return e;
+    ResolveArgs r{};
+    r.key_bytes = a.key_bytes;
+    r.key_off = a.key_off;
+    r.key_len = a.key_len;
+    r.dst_off = a.dst_off;
+    r.dst_base = a.dst_base;
+    r.table = a.table;
+    r.table_mask = a.table_mask;
+    r.shards = a.shards;
+    r.nsegs = a.nsegs;
+    for (uint32_t s = 0; s < a.nsegs && s < uint32_t(ReadFusedLaunch::kMaxSegs); ++s)
+        r.seg_base[s] = a.seg_base[s];
+    r.status = a.status;
+    Fp8Launch shape_in;
+    shape_in.n = a.n;
+    shape_in.elems = elems;
+    const int sms = sm_count();
+    int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, 2 * sms) : 2 * sms;
+    const Fp8Shape sh = shape_of(shape_in, ctas);
+    ctas = int(std::min<uint64_t>(uint64_t(ctas), uint64_t(sh.n) * sh.cpb));
+    Publish pub{};
+    pub.recs = nullptr;
+    kv_fp8_pipe_kernel<false, 8, true><<<ctas, (3 + 8) * 32, kSmemRead, stream>>>(nullptr, sh, pub, a.status, r);
     return cudaGetLastError();
 }
 

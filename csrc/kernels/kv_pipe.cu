@@ -40,6 +40,7 @@
 #include "index.cuh"
 #include "kernels.h"
 #include "publish.cuh"
+#include "resolve.cuh"
 
 namespace istore::kernels {
 
@@ -56,10 +57,6 @@ template <int N>
 struct PipeDescParam {
     CopyDesc d[N];
 };
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {  // SYNCS.ARRIVE
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // Static schedule shared by every role of a CTA: item k of this CTA is global item
 // first + k * stride = chunk (item % cpb) of block (item / cpb); a chunk is moved in pieces
@@ -223,30 +220,13 @@ __global__ void __launch_bounds__(kPipeThreads)
 }
 
 // ---------------------------------------------------------------- kv_pipe_read (fused)
-struct PipeReadArgs {
-    const uint8_t* key_bytes;
-    const uint32_t* key_off;
-    const uint32_t* key_len;
-    const uint64_t* dst_off;
-    uint64_t dst_base;
-    const IndexBucket* table;
-    uint64_t table_mask;
-    IndexShards shards;
-    uint64_t seg_base[ReadFusedLaunch::kMaxSegs];
-    uint32_t nsegs;
-    uint32_t* status;
-};
-
-constexpr int kQ = 32;  // descriptors per queue half
-
+// resolver warp + queue: resolve.cuh
 __global__ void __launch_bounds__(kPipeThreads)
-    kv_pipe_read_kernel(const __grid_constant__ PipeReadArgs a, const Shape sh) {
+    kv_pipe_read_kernel(const __grid_constant__ ResolveArgs a, const Shape sh) {
     extern __shared__ __align__(128) uint8_t ring[];
     __shared__ __align__(8) uint64_t full[kPipeMaxStages];
     __shared__ __align__(8) uint64_t empty[kPipeMaxStages];
-    __shared__ __align__(8) uint64_t qfull[2];
-    __shared__ __align__(8) uint64_t qempty[2];
-    __shared__ CopyDesc queue[2][kQ];
+    __shared__ __align__(16) ResolveQueue rq;
     const uint32_t total = sh.n;  // fused reads move whole blocks: cpb == 1
     const uint32_t grid = gridDim.x;
     const uint32_t nitems = blockIdx.x < total ? (total - blockIdx.x + grid - 1) / grid : 0;
@@ -256,89 +236,24 @@ __global__ void __launch_bounds__(kPipeThreads)
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(&qfull[0], 1);
-        mbar_init(&qfull[1], 1);
-        mbar_init(&qempty[0], 1);
-        mbar_init(&qempty[1], 1);
+        resolve_queue_init(rq);
         mbar_fence_init();
     }
     __syncthreads();
-    const uint32_t nbatches = (nitems + kQ - 1) / kQ;
     if (warp == 2) {  // ---- resolver: runs ahead of the copy by up to two batches
-        // Optimistic read: what this lane resolved in the two batches in flight is re-checked
-        // once the storer has released the batch - by then every byte of its blocks has been
-        // read from the pool.  A block that was purged or evicted meanwhile (its space may
-        // already belong to another key) shows a changed tag and is reported as a miss.
-        uint32_t vslot0 = 0, vtag0 = 0, vslot1 = 0, vtag1 = 0;  // scalars: no local memory
-        auto recheck = [&](uint32_t p) {
-            const uint32_t slot = p ? vslot1 : vslot0, tag = p ? vtag1 : vtag0;
-            if (slot && a.status &&
-                !idx::still_valid(idx::table_of_slot(a.table, a.shards, slot), idx::slot_local(slot), tag)) {
-                atomicAdd(a.status + kStatMiss, 1u);
-                atomicAdd(a.status + kStatStale, 1u);
-            }
-            if (p)
-                vslot1 = 0;
-            else
-                vslot0 = 0;
-        };
-        for (uint32_t b = 0; b < nbatches; ++b) {
-            const uint32_t p = b & 1;
-            if (b >= 2) {
-                mbar_wait(&qempty[p], ((b >> 1) - 1) & 1);
-                recheck(p);
-            }
-            const uint32_t k = b * kQ + lane;
-            if (k < nitems) {
-                const uint32_t block = blockIdx.x + k * grid;
-                const KeyHash kh = hash_key(a.key_bytes + a.key_off[block], a.key_len[block]);
-                const idx::TableRef t = idx::select_shard(a.table, a.table_mask, a.shards, kh.h2);
-                idx::Found f = idx::find<false>(t.table, t.mask, kh);
-                f.slot_plus1 = idx::pack_slot(t.shard, f.slot_plus1);
-                uint64_t src = 0;
-                if (f.slot_plus1) {
-                    const uint32_t seg = uint32_t(f.addr >> 44) - 1;
-                    if (f.size >= sh.bytes && seg < a.nsegs && a.seg_base[seg])
-                        src = a.seg_base[seg] + (f.addr & ((1ull << 44) - 1));
-                }
-                queue[p][lane] = CopyDesc{src, a.dst_base + a.dst_off[block]};
-                if (p) {
-                    vslot1 = src ? f.slot_plus1 : 0;
-                    vtag1 = f.tag;
-                } else {
-                    vslot0 = src ? f.slot_plus1 : 0;
-                    vtag0 = f.tag;
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&qfull[p]);  // release: the queue half is visible
-        }
-        for (uint32_t b = nbatches >= 2 ? nbatches - 2 : 0; b < nbatches; ++b) {  // the tail
-            mbar_wait(&qempty[b & 1], (b >> 1) & 1);
-            recheck(b & 1);
-        }
+        resolver_warp(a, rq, sh.bytes, blockIdx.x, grid, 1, nitems, lane);
         return;
     }
     // Loader and storer read their descriptors from the queue.  The storer hands a half back
     // when it moves on to the next batch (or finishes): every load of the half's blocks has
     // completed by then, which is what the resolver's re-check relies on.
-    const bool is_storer = warp == 1;
-    auto desc_at = [&](uint32_t k) -> CopyDesc {
-        const uint32_t b = k / kQ, p = b & 1;
-        if (k % kQ == 0) {
-            if (is_storer && k) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&qempty[p ^ 1]);
-            }
-            mbar_wait(&qfull[p], (b >> 1) & 1);
-        }
-        return queue[p][k % kQ];
-    };
     if (warp == 0) {
-        loader_body(sh, blockIdx.x, grid, nitems, lane, ring, full, empty, desc_at);
+        loader_body(sh, blockIdx.x, grid, nitems, lane, ring, full, empty,
+                    [&](uint32_t k) { return resolved_desc<false, true>(rq, k, lane); });
     } else {
-        storer_body(sh, blockIdx.x, grid, nitems, lane, ring, full, empty, a.status, desc_at);
-        if (lane == 0 && nitems) mbar_arrive(&qempty[((nitems - 1) / kQ) & 1]);
+        storer_body(sh, blockIdx.x, grid, nitems, lane, ring, full, empty, a.status,
+                    [&](uint32_t k) { return resolved_desc<true, true>(rq, k, lane); });
+        resolved_done(rq, nitems, lane);
     }
 }
 
@@ -689,7 +604,7 @@ cudaError_t launch_kv_pipe_read(const ReadFusedLaunch& a, cudaStream_t stream) {
     const PipeGeometry g = pipe_geometry(a.bytes, a.stage_bytes, a.ring_bytes);
     int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, sm_count()) : sm_count();
     ctas = int(std::min<uint32_t>(uint32_t(ctas), a.n));
-    PipeReadArgs r{};
+    ResolveArgs r{};
     r.key_bytes = a.key_bytes;
     r.key_off = a.key_off;
     r.key_len = a.key_len;

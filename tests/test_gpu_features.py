@@ -49,6 +49,46 @@ def test_fp8_kv_path_through_the_store(hbm_server, device_lookup):
         conn.sync()
 
 
+@pytest.mark.parametrize("n,elems,max_ctas", [
+    (300, 2048, 3),      # 100 items per CTA: four resolver rounds, queue halves recycled
+    (5, 1 << 20, 0),     # few big pages: chunked over the grid, every CTA resolves its block
+    (148 * 3, 8192, 0),  # whole pages per CTA
+])
+def test_fp8_fused_read_resolves_dequantises_and_reports_misses(hbm_server, n, elems, max_ctas):
+    """read_cache_fp8 through the device index is ONE launch (resolver warp inside the
+    dequantising TMA pipeline); reference: ops.fp8_reference (fp32 math in PyTorch)."""
+    _, port = hbm_server
+    conn = make_conn(port, device_lookup=True, max_ctas=max_ctas)
+    x = (torch.randn(n, elems, device="cuda:0") * 3).to(torch.bfloat16)
+    out = torch.zeros_like(x)
+    conn.register_mr(x)
+    conn.register_mr(out)
+    keys = [f"f8-{i}-{rk(5)}" for i in range(n)]
+    blocks = conn.allocate_rdma(keys, conn.fp8_page_bytes(elems))
+    conn.rdma_write_cache_fp8(x, [i * elems for i in range(n)], elems, blocks)
+    conn.sync()
+    before = conn.stats()["kernel_launches"]
+    conn.read_cache_fp8(out, [(k, i * elems) for i, k in enumerate(keys)], elems)
+    conn.sync()
+    assert conn.stats()["kernel_launches"] - before == 1
+    ref, _, _ = ops.fp8_reference(x)
+    tol = float(x.float().abs().max()) * 2 ** -7
+    assert (out.float() - ref.to(torch.bfloat16).float()).abs().max().item() <= tol
+    # misses in the middle: reported, the pages that exist still arrive, nothing else is touched
+    out.zero_()
+    holes = {1, n // 2, n - 1}
+    asked = [(("no-such-" + rk()) if i in holes else k, i * elems) for i, k in enumerate(keys)]
+    with pytest.raises(Exception):
+        conn.read_cache_fp8(out, asked, elems)
+        conn.sync()
+    torch.cuda.synchronize()
+    for i in range(n):
+        if i in holes:
+            assert not out[i].any()
+        else:
+            assert (out[i].float() - ref[i].to(torch.bfloat16).float()).abs().max().item() <= tol
+
+
 def test_fused_read_many_rounds_and_misses(hbm_server):
     """Few CTAs, many items per CTA (several resolver rounds), misses in the middle."""
     _, port = hbm_server

@@ -8,6 +8,7 @@
 #   bench   bench.py at N GPUs             ref    bench.py --impl reference at N GPUs
 #   quick   bench.py without extras / e2e  lab    bench/r2_lab.py sweeps (1 or 2 GPUs)
 #   lat     bench/configs.py latency       ncu    bench/ncu_driver.py under ncu --set full (1 process)
+#   fp8     bench/configs.py fp8 (ring)    fanin  bench/configs.py fanin
 #
 # A step that runs into its limit may have wedged the GPU (it has happened: a multicast bulk
 # load from peer memory); going on would burn the whole gpurun limit, so the script aborts.
@@ -40,6 +41,8 @@ for s in $STEPS; do
     quick)  step quick 300 $LAUNCH bench.py --gpus $N --steps 4 --warmup 3 --no-extra --no-e2e ;;
     ref)    step ref 600 $LAUNCH bench.py --impl reference --gpus $N --steps 3 --warmup 1 ;;
     lat)    step lat 200 $LAUNCH bench/configs.py latency ;;
+    fp8)    step fp8 300 $LAUNCH bench/configs.py fp8 ;;
+    fanin)  step fanin 300 $LAUNCH bench/configs.py fanin ;;
     lab)    step lab 600 $LAUNCH bench/r2_lab.py ;;
     ncu)    step ncu 900 ncu --set full --section Nvlink --clock-control none --import-source on \
                 -o $OUT/all_kernels -f python bench/ncu_driver.py ;;
