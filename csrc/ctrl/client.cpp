@@ -1454,21 +1454,18 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
         const uint64_t t_launch0 = now_ns();
         stats_.ns_build += t_launch0 - t_build0;
         cudaError_t e;
-        // The fused kernel resolves a key in every CTA that moves a piece of its block, reading
-        // the key bytes from the pinned ring each time: right when a block is one work item
-        // (>= SM-count blocks of <= 1 MB), wasteful when a few large blocks are split over
-        // many CTAs (measured: 4 MB single-block read 83 us vs 42 us) - then resolve each key
-        // once with the lookup kernel and feed the descriptors to kv_copy.
-        // ... and for a handful of SMALL blocks (<= 64 KB each, <= 4 MB in all) the single
-        // launch wins on latency; a lone large block must be spread over many CTAs instead
-        // (measured over NVLink: one 1 MB block through one CTA's 64 KB ring takes 98 us).
-        const bool whole_blocks =
-            uint32_t(block_size) <= (1u << 20) && n >= size_t(kernels::sm_count());
+        // The fused kernels resolve a key in every CTA that moves a piece of its block, reading
+        // the key bytes from the pinned ring each time: right for a batch of blocks (items are
+        // whole blocks, or chunks when that balances the grid better - kernels/balance.h),
+        // wasteful when a few LARGE blocks are split over many CTAs (measured: 4 MB
+        // single-block read 83 us vs 42 us) - then resolve each key once with the lookup kernel
+        // and feed the descriptors to kv_copy.
         // A handful of blocks (<= 4 MB in all): latency matters, not bandwidth.  One launch of
         // the ld/st flavour, which splits a block into 32 KB chunks over CTAs (each resolves its
         // block's key itself - a few redundant probes) and re-checks the entries in the same
         // kernel: lookup + copy + validate would be three launches (+7..15 us per read).
-        const bool small_batch = !whole_blocks && n * size_t(block_size) <= (4u << 20);
+        const bool small_batch = n * size_t(block_size) <= (4u << 20);
+        const bool whole_blocks = !small_batch && uint32_t(block_size) <= (1u << 20) && n >= 32;
         kernels::ReadFusedLaunch R;
         R.align_or = align_or;
         const bool fp8_fused = fp8_elems && kernels::fp8_read_fused_supported(R, uint32_t(fp8_elems));

@@ -27,6 +27,7 @@
 #include <mutex>
 #include <type_traits>
 
+#include "balance.h"
 #include "common.cuh"
 #include "kernels.h"
 #include "publish.cuh"
@@ -282,12 +283,12 @@ cudaError_t ensure_attrs() {
 }
 
 Fp8Shape shape_of(const Fp8Launch& a, int ctas) {
-    // whole pages per CTA when there are enough of them (single-CTA commit), else chunks of
-    // four tiles spread over the grid
-    uint32_t chunk = a.elems;
-    if (a.n < uint32_t(ctas) || a.elems > (1u << 19)) chunk = std::min(a.elems, 4 * kTileElems);
-    const uint32_t cpb = (a.elems + chunk - 1) / chunk;
-    return Fp8Shape{a.n, a.elems, chunk, cpb};
+    // whole pages per CTA when that keeps the grid evenly busy (single-CTA commit), else
+    // chunks of at least two tiles (balance.h); never more than 512 K elements per item
+    const uint32_t tiles = (a.elems + kTileElems - 1) / kTileElems;
+    const ChunkPlan plan = plan_chunks(a.n, tiles, 2, 64, uint32_t(ctas));
+    const uint32_t chunk = std::min(a.elems, plan.chunk * kTileElems);
+    return Fp8Shape{a.n, a.elems, chunk, (a.elems + chunk - 1) / chunk};
 }
 
 }  // namespace

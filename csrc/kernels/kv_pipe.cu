@@ -38,6 +38,7 @@
 #include "../core/hash.h"
 #include "common.cuh"
 #include "index.cuh"
+#include "balance.h"
 #include "kernels.h"
 #include "publish.cuh"
 #include "resolve.cuh"
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(kPipeThreads)
     __shared__ __align__(8) uint64_t full[kPipeMaxStages];
     __shared__ __align__(8) uint64_t empty[kPipeMaxStages];
     __shared__ __align__(16) ResolveQueue rq;
-    const uint32_t total = sh.n;  // fused reads move whole blocks: cpb == 1
+    const uint32_t total = sh.n * sh.cpb;
     const uint32_t grid = gridDim.x;
     const uint32_t nitems = blockIdx.x < total ? (total - blockIdx.x + grid - 1) / grid : 0;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(kPipeThreads)
     }
     __syncthreads();
     if (warp == 2) {  // ---- resolver: runs ahead of the copy by up to two batches
-        resolver_warp(a, rq, sh.bytes, blockIdx.x, grid, 1, nitems, lane);
+        resolver_warp(a, rq, sh.bytes, blockIdx.x, grid, sh.cpb, nitems, lane);
         return;
     }
     // Loader and storer read their descriptors from the queue.  The storer hands a half back
@@ -558,18 +559,14 @@ cudaError_t launch_kv_pipe_copy(const CopyLaunch& a, cudaStream_t stream) {
     if (!a.table || !a.done) pub.recs = nullptr;
     const int sms = sm_count();
     const PipeGeometry g = pipe_geometry(a.bytes, a.stage_bytes, a.ring_bytes);
-    // Work item: a whole block when there are at least as many blocks as CTAs (the commit of a
-    // block then needs no cross-CTA counter), otherwise chunks of a few ring slots.
-    // the ring takes most of an SM's shared memory: one CTA per SM is resident (two when the
-    // ring was configured at half size), more would only queue behind them
-    // one CTA per SM: the rest of the SM's shared memory is for the kernels of the connection's
-    // other streams (see pipe_geometry)
+    // One CTA per SM: the rest of the SM's shared memory is for the kernels of the connection's
+    // other streams (see pipe_geometry).  Work item: a whole block when that keeps the grid
+    // evenly busy (the commit of a block then needs no cross-CTA counter), otherwise chunks of
+    // at least four ring slots and at most 1 MB (balance.h).
     int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, sms) : sms;
-    uint32_t chunk = a.bytes;
-    if (a.n < uint32_t(ctas) || a.bytes > (1u << 20)) {
-        const uint32_t per = g.stage_bytes * 4;
-        if (a.bytes > per) chunk = per;
-    }
+    const ChunkPlan plan = plan_chunks(a.n, (a.bytes + g.stage_bytes - 1) / g.stage_bytes, 4,
+                                       std::max(4u, (1u << 20) / g.stage_bytes), uint32_t(ctas));
+    const uint32_t chunk = std::min(a.bytes, plan.chunk * g.stage_bytes);
     const uint32_t cpb = (a.bytes + chunk - 1) / chunk;
     const uint64_t total = uint64_t(a.n) * cpb;
     ctas = int(std::min<uint64_t>(uint64_t(ctas), total));
@@ -603,7 +600,12 @@ cudaError_t launch_kv_pipe_read(const ReadFusedLaunch& a, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     const PipeGeometry g = pipe_geometry(a.bytes, a.stage_bytes, a.ring_bytes);
     int ctas = a.max_ctas > 0 ? std::min(a.max_ctas, sm_count()) : sm_count();
-    ctas = int(std::min<uint32_t>(uint32_t(ctas), a.n));
+    // a block that is split over several CTAs is resolved by each of them (balance.h)
+    const ChunkPlan plan = plan_chunks(a.n, (a.bytes + g.stage_bytes - 1) / g.stage_bytes, 4,
+                                       std::max(4u, (1u << 20) / g.stage_bytes), uint32_t(ctas));
+    const uint32_t chunk = std::min(a.bytes, plan.chunk * g.stage_bytes);
+    const uint32_t cpb = (a.bytes + chunk - 1) / chunk;
+    ctas = int(std::min<uint64_t>(uint64_t(ctas), uint64_t(a.n) * cpb));
     ResolveArgs r{};
     r.key_bytes = a.key_bytes;
     r.key_off = a.key_off;
@@ -617,7 +619,7 @@ cudaError_t launch_kv_pipe_read(const ReadFusedLaunch& a, cudaStream_t stream) {
     for (uint32_t s = 0; s < a.nsegs && s < uint32_t(ReadFusedLaunch::kMaxSegs); ++s)
         r.seg_base[s] = a.seg_base[s];
     r.status = a.status;
-    const Shape sh{a.n, a.bytes, a.bytes, 1, g.stage_bytes, g.stages};
+    const Shape sh{a.n, a.bytes, chunk, cpb, g.stage_bytes, g.stages};
     kv_pipe_read_kernel<<<ctas, kPipeThreads, g.smem, stream>>>(r, sh);
     return cudaGetLastError();
 }

@@ -32,6 +32,7 @@
 #include "ctrl/server.h"
 #include "fabric/nvls.h"
 #include "fabric/segment.h"
+#include "kernels/balance.h"
 #include "kernels/kernels.h"
 #include "wire/messages.h"
 
@@ -960,6 +961,12 @@ PYBIND11_MODULE(_infinistore, m) {
 
     // ------------------------------------------------------------ unit-test access to the core
     py::module_ t = m.def_submodule("testing", "wire codec, allocator and hash for unit tests");
+    t.def("plan_chunks",
+          [](uint32_t n, uint32_t units, uint32_t min_units, uint32_t max_units, uint32_t ctas) {
+              const kernels::ChunkPlan p = kernels::plan_chunks(n, units, min_units, max_units, ctas);
+              return py::make_tuple(p.chunk, p.cpb);
+          },
+          "work-item split of a batch for a persistent grid (kernels/balance.h)");
     t.def("index_shard_of", [](py::bytes key, uint32_t nshards) {
         const std::string k = key;
         const KeyHash h = hash_key(reinterpret_cast<const uint8_t*>(k.data()), k.size());

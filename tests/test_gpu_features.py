@@ -53,6 +53,7 @@ def test_fp8_kv_path_through_the_store(hbm_server, device_lookup):
     (300, 2048, 3),      # 100 items per CTA: four resolver rounds, queue halves recycled
     (5, 1 << 20, 0),     # few big pages: chunked over the grid, every CTA resolves its block
     (148 * 3, 8192, 0),  # whole pages per CTA
+    (200, 65536, 0),     # 200 pages of 8 tiles on 296 CTAs: quarter pages balance the grid
 ])
 def test_fp8_fused_read_resolves_dequantises_and_reports_misses(hbm_server, n, elems, max_ctas):
     """read_cache_fp8 through the device index is ONE launch (resolver warp inside the
@@ -87,6 +88,39 @@ def test_fp8_fused_read_resolves_dequantises_and_reports_misses(hbm_server, n, e
             assert not out[i].any()
         else:
             assert (out[i].float() - ref[i].to(torch.bfloat16).float()).abs().max().item() <= tol
+
+
+def test_unbalanced_batches_are_moved_in_chunks(hbm_server):
+    """200 pages of 128 KB on 148 CTAs: whole pages would leave 96 CTAs idle for the second
+    round, so writes and fused reads move half pages (kernels/balance.h).  The chunks of a
+    page are committed through the cross-CTA counter; the read resolves a page in every CTA
+    that moves a piece of it."""
+    _, port = hbm_server
+    conn = make_conn(port, device_lookup=True)
+    n, elems = 200, 65536
+    src = torch.randn(n * elems, device="cuda:0").to(torch.bfloat16)
+    dst = torch.zeros_like(src)
+    conn.register_mr(src)
+    conn.register_mr(dst)
+    keys = [f"ub-{i}-{rk(6)}" for i in range(n)]
+    blocks = conn.allocate_rdma(keys, elems * 2)
+    conn.rdma_write_cache(src, [i * elems for i in range(n)], elems, blocks)
+    conn.sync()
+    before = conn.stats()["kernel_launches"]
+    conn.read_cache(dst, [(k, i * elems) for i, k in enumerate(keys)], elems)
+    conn.sync()
+    assert conn.stats()["kernel_launches"] - before == 1   # hits in the device index: published
+    assert torch.equal(src, dst)
+    dst.zero_()
+    holes = {0, 77, n - 1}
+    asked = [(("absent-" + rk()) if i in holes else k, i * elems) for i, k in enumerate(keys)]
+    with pytest.raises(Exception):
+        conn.read_cache(dst, asked, elems)
+        conn.sync()
+    torch.cuda.synchronize()
+    got, want = dst.view(n, elems), src.view(n, elems)
+    for i in range(n):
+        assert (not got[i].any()) if i in holes else torch.equal(got[i], want[i])
 
 
 def test_fused_read_many_rounds_and_misses(hbm_server):

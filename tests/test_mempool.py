@@ -90,3 +90,34 @@ def test_mm_multi_pool_hint_and_extend_trigger():
     assert mm.need_extend()  # last pool is more than half full
     assert mm.deallocate(1, 0, g) and not mm.deallocate(1, 0, g)
     assert not mm.deallocate(5, 0, g)
+
+
+def test_chunk_plan_balances_a_persistent_grid():
+    """kernels/balance.h: items per block so that the busiest CTA of a strided persistent grid
+    moves (nearly) the least; whole blocks whenever that is within 4 % of the best."""
+    from infinistore_b200 import _infinistore as m
+
+    plan = m.testing.plan_chunks
+
+    def makespan(n, units, chunk, ctas):
+        cpb = -(-units // chunk)
+        return -(-n * cpb // ctas) * chunk
+
+    # the flagship batch (1024 pages of 8 ring slots on 148 CTAs) stays whole
+    assert plan(1024, 8, 4, 64, 148) == (8, 1)
+    # one layer of the fp8 ring bench: 512 pages of 8 tiles on 296 CTAs -> quarters (14 vs 16)
+    assert plan(512, 8, 2, 64, 296) == (2, 4)
+    # a lone 1 MB block: the smallest chunks allowed
+    assert plan(1, 64, 4, 64, 148) == (4, 16)
+    # never below min, never above max, short blocks are one item
+    assert plan(7, 3, 4, 64, 148) == (3, 1)
+    assert plan(100000, 4096, 4, 64, 148)[0] <= 64
+    import random
+    rnd = random.Random(7)
+    for _ in range(300):
+        n, units, ctas = rnd.randint(1, 5000), rnd.randint(1, 300), rnd.choice([1, 3, 148, 296])
+        lo = rnd.randint(1, 8)
+        chunk, cpb = plan(n, units, lo, 64, ctas)
+        assert cpb == -(-units // chunk) and min(lo, units) <= chunk <= max(min(units, 64), min(lo, units))
+        best = min(makespan(n, units, c, ctas) for c in range(min(lo, units), max(min(units, 64), min(lo, units)) + 1))
+        assert makespan(n, units, chunk, ctas) * 100 <= best * 104
