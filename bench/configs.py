@@ -274,19 +274,18 @@ def fanin(ctx: Ctx, pages: int = 64, iters: int = 2):
 
 
 # --------------------------------------------------------------------------- config 5
-def fp8_ring(ctx: Ctx, size_mb: int = 2048, iters: int = 2):
+def fp8_ring(ctx: Ctx, size_mb: int = 2048, iters: int = 2, layers: int = 32, **client_kw):
     elems = 65536                                  # 128 KB bf16 page -> 64 KB e4m3 (+ scales)
     nblk = (size_mb << 20) // (elems * 2)
     port = ctx.base_port + 60
     server = start_shard_server(ctx.local, port + ctx.rank,
                                 (iters + 2) * nblk * 80 * 1024 + (256 << 20), granule_kb=16)
     ctx.barrier()
-    conn = _client(ctx, port + (ctx.rank + 1) % ctx.world)
+    conn = _client(ctx, port + (ctx.rank + 1) % ctx.world, **client_kw)
     src = (torch.randn(nblk * elems, device=ctx.dev) * 2).to(torch.bfloat16)
     dst = torch.zeros_like(src)
     conn.register_mr(src)
     conn.register_mr(dst)
-    layers = 32
     per = nblk // layers
     offs = np.arange(nblk, dtype=np.int64) * elems
     nbytes = conn.fp8_page_bytes(elems)
@@ -323,6 +322,7 @@ def fp8_ring(ctx: Ctx, size_mb: int = 2048, iters: int = 2):
     bf16_bytes = ctx.world * nblk * elems * 2 * iters
     return {"what": "fp8 KV path, ring over N GPUs: cast fused into the write, dequantising "
                     "gather fused into the read", "fp8_block_kb": nbytes / 1024,
+            "pages_per_call": per, "calls_per_phase": layers,
             "write_GBps_fp8_bytes": round(fp8_bytes / w / 1e6, 1),
             "read_GBps_fp8_bytes": round(fp8_bytes / r / 1e6, 1),
             "write_GBps_bf16_equiv": round(bf16_bytes / w / 1e6, 1),
@@ -469,12 +469,14 @@ def _standalone_ctx():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("config", choices=["fanin", "bcast", "fp8", "latency", "baselines"])
+    ap.add_argument("--max-ctas", type=int, default=0, help="fp8: grid cap of the client's kernels")
+    ap.add_argument("--layers", type=int, default=32, help="fp8: calls per phase (pages per call = 16384 / layers)")
     a = ap.parse_args()
     ctx = _standalone_ctx()
     if a.config == "fanin":
         res = fanin(ctx)
     elif a.config == "fp8":
-        res = fp8_ring(ctx)
+        res = fp8_ring(ctx, layers=a.layers, **({"max_ctas": a.max_ctas} if a.max_ctas else {}))
     elif a.config == "bcast":
         res = nvls_bcast(ctx)
     elif a.config == "baselines":

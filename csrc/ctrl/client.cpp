@@ -569,6 +569,21 @@ int Connection::get_match_last_index(const std::vector<std::string_view>& keys) 
     return v;
 }
 
+// A device-side miss on a path that makes no SYNC round trip: ask the server whether the HBM
+// index is complete - if a writer overflowed it, the key may exist all the same, and from now
+// on this connection resolves its reads through the server.
+void Connection::refresh_index_state() {
+    if (index_incomplete_.load(std::memory_order_relaxed)) return;
+    int32_t code = 0;
+    std::vector<uint8_t> p;
+    if (transact(kOpSync, nullptr, 0, &code, &p, sizeof(uint32_t)) == 0 && code == kFinish &&
+        p.size() == sizeof(uint32_t)) {
+        uint32_t remain;
+        std::memcpy(&remain, p.data(), sizeof(remain));
+        if (remain & kSyncIndexIncomplete) index_incomplete_.store(true, std::memory_order_relaxed);
+    }
+}
+
 int Connection::sync_local() {
     NvtxRange nvtx("istore.sync");
     // one sync at a time: a staged commit list and the SYNC that applies it belong together
@@ -588,18 +603,7 @@ int Connection::sync_local() {
         }
         if (quiet && async_idle) {
             const int drained = drain_devices();
-            if (drained == -kKeyNotFound && !index_incomplete_.load()) {
-                // a device-side miss: ask the server whether the HBM index is complete - if a
-                // writer overflowed it, the key may exist and later reads go through the server
-                int32_t code = 0;
-                std::vector<uint8_t> p;
-                if (transact(kOpSync, nullptr, 0, &code, &p, sizeof(uint32_t)) == 0 &&
-                    code == kFinish && p.size() == sizeof(uint32_t)) {
-                    uint32_t remain;
-                    std::memcpy(&remain, p.data(), sizeof(remain));
-                    if (remain & kSyncIndexIncomplete) index_incomplete_.store(true);
-                }
-            }
+            if (drained == -kKeyNotFound) refresh_index_state();
             return drained != 0 ? drained : 0;
         }
     }
@@ -625,6 +629,7 @@ int Connection::sync_local() {
                 return -1;
             }
             if (!mine.empty() && send_commit(mine.data(), mine.size()) != 0) return -1;
+            if (drained == -kKeyNotFound) refresh_index_state();
             return drained;
         }
     }
@@ -1448,7 +1453,12 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
             seg_base[s] = reinterpret_cast<uint64_t>(seg_dev_ptr(ctx, s));
             all_remote = all_remote && ctx->seg_remote[s];
         }
-        const int grid_cap = max_ctas_ ? max_ctas_ : (all_remote ? 2 * kernels::sm_count() : 0);
+        // fp8 pages pulled over NVLink: one CTA per SM.  With both link directions busy, 296
+        // CTAs of 8 compute warps pull 954 GB/s (2 GPUs, fp8 bytes), 148 pull 1085
+        // (bench/configs.py fp8 --max-ctas 148, round 2); writes prefer two per SM.
+        const int grid_cap = max_ctas_ ? max_ctas_
+                             : all_remote ? (fp8_elems ? 1 : 2) * kernels::sm_count()
+                                          : 0;
         uint64_t align_or = base_ptr;
         for (size_t i = 0; i < n; ++i) align_or |= blocks[base + i].offset;
         const uint64_t t_launch0 = now_ns();

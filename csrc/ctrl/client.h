@@ -199,6 +199,7 @@ class Connection {
                       std::vector<RemoteBlock>& out);
     int flush_commits();
     uint32_t take_publish_failures();
+    void refresh_index_state();
     int send_commit(const uint64_t* addrs, size_t count);
 
     // data plane

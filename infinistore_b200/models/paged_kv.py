@@ -9,6 +9,13 @@ import torch
 from .kv_layout import KVLayout, page_key
 
 
+def layer_keys(layout: KVLayout, tp_rank: int, layer: int, kv: int,
+               page_hashes: Sequence[str]) -> List[str]:
+    """Store keys of one layer's K (kv = 0) or V (kv = 1) pages."""
+    kind = "K" if kv == 0 else "V"
+    return [page_key(layout.name, layer, kind, tp_rank, h) for h in page_hashes]
+
+
 class PagedKVCache:
     """``cache[layer, kv, page]`` is one contiguous page of ``layout.page_elems`` elements.
 
@@ -38,8 +45,7 @@ class PagedKVCache:
         return self.data[layer, kv, page]
 
     def keys(self, layer: int, kv: int, page_hashes: Sequence[str]) -> List[str]:
-        kind = "K" if kv == 0 else "V"
-        return [page_key(self.layout.name, layer, kind, self.tp_rank, h) for h in page_hashes]
+        return layer_keys(self.layout, self.tp_rank, layer, kv, page_hashes)
 
     def _ensure_registered(self, conn):
         if id(conn) not in self._registered:
@@ -80,7 +86,8 @@ class PagedKVCache:
             n += len(keys)
         return n
 
-    def cached_prefix_pages(self, conn, page_hashes: Sequence[str], layer: int = 0) -> int:
+    def cached_prefix_pages(self, conn, page_hashes: Sequence[str],
+                            layer: Optional[int] = None) -> int:
         """How many leading pages of this prefix the store already holds (last layer's V
         pages are written last, so probing them answers for the whole stack)."""
         if not page_hashes:
@@ -101,3 +108,62 @@ class PagedKVCache:
             for kv in (0, 1):
                 keys.extend(self.keys(layer, kv, page_hashes))
         return conn.touch(keys) if keys else 0
+
+
+def read_layer_multi(conn, caches: Sequence[PagedKVCache], layer: int, pages: Sequence[int],
+                     page_hashes: Sequence[str], stream="current") -> int:
+    """The same prefix pages into several caches of ONE GPU (beams, or tensor-parallel
+    consumers that replicate KV heads): every page crosses the fabric once and is stored to
+    all destinations by the read kernel (``InfinityConnection.read_cache_multi``: fan-out
+    stores for a pool behind NVLink, a thread-block cluster with TMA multicast for a local
+    pool).  The caches share layout, page numbering and TP rank.  Returns the number of
+    blocks read per cache."""
+    first = caches[0]
+    for c in caches:
+        if c.layout != first.layout or c.num_pages != first.num_pages or c.tp_rank != first.tp_rank:
+            raise ValueError("read_layer_multi: caches of one layout, size and TP rank")
+    n = 0
+    for kv in (0, 1):
+        keys = first.keys(layer, kv, page_hashes)
+        blocks = [(k, first.page_offset(layer, kv, p)) for k, p in zip(keys, pages)]
+        conn.read_cache_multi([c.data for c in caches], blocks, first.layout.page_elems,
+                              stream=stream)
+        n += len(keys)
+    return n
+
+
+class HeadMajorKVCache:
+    """Decode-side cache in the layout a paged-attention kernel streams:
+    ``data[layer, kv]`` is ``[num_pages, heads, page_tokens, head_dim]`` - one head's tokens
+    of a page are contiguous.  Prefill writes pages token-major (``[tokens, heads, dim]``,
+    :class:`PagedKVCache`); ``read_layer`` fetches them with
+    ``InfinityConnection.read_cache_hnd``, whose store is a 4-D tensor-map TMA: the
+    transposition happens inside the read, the page crosses HBM once and no permute kernel
+    runs on the decode GPU.  The reference hands opaque bytes to the consumer
+    (infinistore/lib.py:377-379), which then repacks them itself."""
+
+    def __init__(self, layout: KVLayout, num_pages: int, device, tp_rank: int = 0):
+        self.layout = layout
+        self.num_pages = num_pages
+        self.tp_rank = tp_rank
+        self.data = torch.zeros(layout.layers, 2, num_pages, layout.heads_per_rank,
+                                layout.page_tokens, layout.head_dim, dtype=layout.dtype,
+                                device=device)
+
+    def keys(self, layer: int, kv: int, page_hashes: Sequence[str]) -> List[str]:
+        return layer_keys(self.layout, self.tp_rank, layer, kv, page_hashes)
+
+    def page_token_major(self, layer: int, kv: int, page: int) -> torch.Tensor:
+        """A page as prefill laid it out, ``[tokens, heads, dim]`` (a permuted view)."""
+        return self.data[layer, kv, page].permute(1, 0, 2)
+
+    def read_layer(self, conn, layer: int, pages: Sequence[int], page_hashes: Sequence[str],
+                   stream="current") -> int:
+        """Fetch K and V pages of one layer into head-major pages ``pages``."""
+        n = 0
+        for kv in (0, 1):
+            keys = self.keys(layer, kv, page_hashes)
+            conn.read_cache_hnd(self.data[layer, kv], list(zip(keys, [int(p) for p in pages])),
+                                stream=stream)
+            n += len(keys)
+        return n

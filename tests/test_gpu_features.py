@@ -10,7 +10,8 @@ import torch
 import infinistore_b200 as ist
 from infinistore_b200 import _infinistore as native
 from infinistore_b200 import ops
-from infinistore_b200.models import PagedKVCache, KVLayout, chain_hashes
+from infinistore_b200.models import (HeadMajorKVCache, KVLayout, PagedKVCache, chain_hashes,
+                                     read_layer_multi)
 from infinistore_b200.parallel import (PrefixBroadcaster, ShardedConnection, nvls_available,
                                        start_shard_server)
 from conftest import make_conn
@@ -288,6 +289,63 @@ def test_paged_kv_cache_on_gpu(hbm_server, fp8):
             assert (x - y).abs().max().item() <= x.abs().max().item() * 2 ** -4
         else:
             assert torch.equal(x, y)
+
+
+def test_decode_side_caches_head_major_and_multi_destination(hbm_server):
+    """Prefill uploads token-major pages; the decode side (a) fills a HEAD-major cache with the
+    layout-swizzling read - reference: torch.permute of the prefill pages - and (b) fills
+    two caches of one GPU with one fetch per page."""
+    _, port = hbm_server
+    layout = KVLayout("tiny-hnd", layers=3, kv_heads=4, head_dim=64, page_tokens=32)
+    a = PagedKVCache(layout, num_pages=8, device="cuda:0")
+    a.data.normal_()
+    ca = make_conn(port, device_lookup=True)
+    cb = make_conn(port, device_lookup=True)
+    hashes = chain_hashes(list(range(32 * 4)), 32, salt="hnd")
+    pages, dst_pages = [6, 1, 4, 3], [0, 5, 2, 7]
+    for layer in range(layout.layers):
+        a.write_layer(ca, layer, pages, hashes)
+    ca.sync()
+    hm = HeadMajorKVCache(layout, num_pages=8, device="cuda:0")
+    assert hm.data.shape == (3, 2, 8, 4, 32, 64)
+    for layer in range(layout.layers):
+        assert hm.read_layer(cb, layer, dst_pages, hashes) == 2 * len(pages)
+    cb.sync()
+    for layer in range(layout.layers):
+        for kv in (0, 1):
+            for s, d in zip(pages, dst_pages):
+                want = a.page(layer, kv, s).view(32, 4, 64)          # [tok][head][dim]
+                assert torch.equal(hm.page_token_major(layer, kv, d), want)
+                assert torch.equal(hm.data[layer, kv, d], want.permute(1, 0, 2))
+    untouched = [p for p in range(8) if p not in dst_pages]
+    assert not hm.data[:, :, untouched].any()
+    # (b) two beams / replicas on this GPU
+    b1 = PagedKVCache(layout, num_pages=8, device="cuda:0")
+    b2 = PagedKVCache(layout, num_pages=8, device="cuda:0")
+    for c in (b1, b2):
+        cb.register_mr(c.data)
+    for layer in range(layout.layers):
+        assert read_layer_multi(cb, [b1, b2], layer, dst_pages, hashes) == 2 * len(pages)
+    cb.sync()
+    for s, d in zip(pages, dst_pages):
+        assert torch.equal(b1.data[:, :, d], a.data[:, :, s])
+        assert torch.equal(b2.data[:, :, d], a.data[:, :, s])
+
+
+def test_prefill_and_decode_examples_run(hbm_server, monkeypatch, capsys):
+    import sys
+    from infinistore_b200.example import demo_decode, demo_prefill
+
+    _, port = hbm_server
+    monkeypatch.setattr(sys, "argv", ["demo_prefill", "--service-port", str(port),
+                                      "--model", "qwen2.5-7b", "--pages", "2"])
+    demo_prefill.main()
+    monkeypatch.setattr(sys, "argv", ["demo_decode", "--service-port", str(port),
+                                      "--model", "qwen2.5-7b", "--pages", "4"])
+    demo_decode.main()
+    out = capsys.readouterr().out
+    assert "with layer-wise upload" in out
+    assert "4 of 4 prompt pages are cached" in out and "layout check: ok" in out
 
 
 def test_nvls_prefix_broadcast():

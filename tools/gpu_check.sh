@@ -42,6 +42,8 @@ for s in $STEPS; do
     ref)    step ref 600 $LAUNCH bench.py --impl reference --gpus $N --steps 3 --warmup 1 ;;
     lat)    step lat 200 $LAUNCH bench/configs.py latency ;;
     fp8)    step fp8 300 $LAUNCH bench/configs.py fp8 ;;
+    fp8x)   step fp8_ctas148 300 $LAUNCH bench/configs.py fp8 --max-ctas 148; launch
+            step fp8_4calls 300 $LAUNCH bench/configs.py fp8 --layers 4 ;;
     fanin)  step fanin 300 $LAUNCH bench/configs.py fanin ;;
     lab)    step lab 600 $LAUNCH bench/r2_lab.py ;;
     ncu)    step ncu 900 ncu --set full --section Nvlink --clock-control none --import-source on \
