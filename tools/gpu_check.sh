@@ -9,6 +9,7 @@
 #   quick   bench.py without extras / e2e  lab    bench/r2_lab.py sweeps (1 or 2 GPUs)
 #   lat     bench/configs.py latency       ncu    bench/ncu_driver.py under ncu --set full (1 process)
 #   fp8     bench/configs.py fp8 (ring)    fanin  bench/configs.py fanin
+#   fp8ab   fp8 ring with grid caps 296 / 148, twice, interleaved
 #
 # A step that runs into its limit may have wedged the GPU (it has happened: a multicast bulk
 # load from peer memory); going on would burn the whole gpurun limit, so the script aborts.
@@ -42,8 +43,9 @@ for s in $STEPS; do
     ref)    step ref 600 $LAUNCH bench.py --impl reference --gpus $N --steps 3 --warmup 1 ;;
     lat)    step lat 200 $LAUNCH bench/configs.py latency ;;
     fp8)    step fp8 300 $LAUNCH bench/configs.py fp8 ;;
-    fp8x)   step fp8_ctas148 300 $LAUNCH bench/configs.py fp8 --max-ctas 148; launch
-            step fp8_4calls 300 $LAUNCH bench/configs.py fp8 --layers 4 ;;
+    fp8ab)  for i in 1 2; do for c in 296 148; do   # interleaved A/B of the client's grid cap
+                launch; step fp8_ctas${c}_$i 300 $LAUNCH bench/configs.py fp8 --max-ctas $c
+            done; done ;;
     fanin)  step fanin 300 $LAUNCH bench/configs.py fanin ;;
     lab)    step lab 600 $LAUNCH bench/r2_lab.py ;;
     ncu)    step ncu 900 ncu --set full --section Nvlink --clock-control none --import-source on \
