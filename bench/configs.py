@@ -87,13 +87,18 @@ def latency(ctx: Ctx, port: int, sizes_kb=(4, 128, 1024), samples=200):
     percentile.  Two sync() flavours: "strict" (default: control-plane round trip, every
     client sees the write when sync() returns) and "posted" (ClientConfig(posted_commit=True):
     one-way commit like the reference's COMMIT SEND; device-path readers see the write at
-    once through the in-band commit); "posted_in_stream" adds streams=0."""
+    once through the in-band commit); "posted_in_stream" adds streams=0; "doorbell" /
+    "posted_doorbell" hand single blocks to the persistent worker."""
     out = {"path": "NVLink (ring peer)" if ctx.world > 1 else "local HBM"}
     q = lambda v, p: v[min(len(v) - 1, int(p * len(v)))]  # noqa: E731
     modes = {"strict": {}, "posted": {"posted_commit": True},
              # launches in the caller's stream: no event record / wait between the caller's
              # stream and an internal one
-             "posted_in_stream": {"posted_commit": True, "streams": 0}}
+             "posted_in_stream": {"posted_commit": True, "streams": 0},
+             # latency mode: a persistent worker CTA polls a request ring in pinned host memory
+             # (kernels/kv_doorbell.cu; blocks <= 256 KB, larger ones take the ordinary path)
+             "doorbell": {"doorbell": True},
+             "posted_doorbell": {"posted_commit": True, "doorbell": True}}
     for mode, kw in modes.items():
         conn = _client(ctx, port, **kw)
         res = {}

@@ -56,6 +56,12 @@ struct ClientConfig {
     // index), server-mediated lookups of other connections follow within the TCP delivery
     // time.  Saves the control-plane round trip: the single-block write latency.
     bool posted_commit = false;
+    // Latency mode: single blocks of <= 256 KB are served by a persistent worker CTA that
+    // polls a request ring in pinned host memory (kernels/kv_doorbell.cu) - no launch, no
+    // event, no stream poll per operation.  The worker leaves after doorbell_idle_us without
+    // a request (a device-wide synchronise waits at most that long for it).
+    bool doorbell = false;
+    int doorbell_idle_us = 200;
 };
 
 }  // namespace istore

@@ -82,6 +82,8 @@ struct ClientStats {
     uint64_t ns_streams = 0;  // stream selection + cross-stream event dependencies
     uint64_t ns_launch = 0;   // cudaLaunchKernel and friends
     uint64_t calls = 0;
+    uint64_t doorbell_ops = 0;      // single-block operations served by the persistent worker
+    uint64_t doorbell_launches = 0;  // (re)launches of the worker
 };
 
 class Connection {
@@ -200,6 +202,14 @@ class Connection {
     int flush_commits();
     uint32_t take_publish_failures();
     void refresh_index_state();
+    // doorbell worker (latency mode); all under mu_
+    bool doorbell_ready(DevCtx* ctx, uint64_t user_stream, size_t bytes);
+    int doorbell_post(DevCtx* ctx, uint32_t op, const uint64_t (&q)[6]);
+    int doorbell_start(DevCtx* ctx);
+    int doorbell_wait(DevCtx* ctx);
+    int doorbell_quiesce(DevCtx* ctx);
+    void doorbell_collect(DevCtx* ctx);
+    void doorbell_stop(DevCtx* ctx);
     int send_commit(const uint64_t* addrs, size_t count);
 
     // data plane

@@ -328,6 +328,52 @@ struct ReadyLaunch {
 };
 cudaError_t launch_kv_read_when_ready(const ReadyLaunch& a, cudaStream_t stream);
 
+// ---------------------------------------------------------------- doorbell worker (kv_doorbell.cu)
+// One persistent CTA that serves single-block writes / reads posted into a ring in pinned
+// host memory: no launch, no event, no stream poll on the caller's path.
+#if defined(__CUDACC__)
+#define ISTORE_KHD __host__ __device__
+#else
+#define ISTORE_KHD
+#endif
+constexpr int kDoorbellMaxSlots = 64;
+constexpr uint32_t kDoorbellMaxBytes = 256u << 10;  // larger blocks want more than one CTA
+constexpr uint64_t kDoorbellMagic = 0x646f6f7262656c6cull;
+enum : uint32_t { kDoorbellWrite = 1, kDoorbellRead = 2, kDoorbellStop = 3 };
+enum : uint32_t { kDoorbellOk = 0, kDoorbellMiss = 1, kDoorbellStale = 2, kDoorbellIndexFull = 3 };
+enum : uint32_t { kDoorbellRunning = 1, kDoorbellExited = 2 };
+// q0 = seq << 2 | op                 q1 = local address (write: source, read: destination)
+// q2 = mapped pool address (write)   q3, q4 = key fingerprint (write: h1 = 0 -> not indexed)
+// q5 = global block address (write)  q6 = generation | bytes << 32
+// q7 = q0 ^ ... ^ q6 ^ kDoorbellMagic: a line the host is still writing never matches
+struct alignas(64) DoorbellReq {
+    uint64_t q[8];
+};
+struct DoorbellCtl {
+    alignas(64) uint64_t done_seq;  // worker -> host: every request <= done_seq has completed
+    alignas(64) uint64_t state;     // worker -> host: doorbell_state(epoch, next request, code)
+    alignas(64) uint32_t status[kDoorbellMaxSlots];  // per ring slot, valid once done
+};
+ISTORE_KHD inline uint64_t doorbell_state(uint32_t epoch, uint64_t next, uint32_t code) {
+    return (uint64_t(epoch & 0xfffffu) << 44) | ((next & ((1ull << 42) - 1)) << 2) | code;
+}
+struct DoorbellLaunch {
+    const DoorbellReq* ring = nullptr;  // device address of the pinned ring
+    DoorbellCtl* ctl = nullptr;         // device address of the pinned control block
+    uint32_t slots = 0;
+    uint32_t epoch = 0;      // launch number (the host tells launches apart in `state`)
+    uint64_t first_seq = 1;  // first request this launch serves
+    uint64_t idle_ns = 200000;
+    IndexBucket* table = nullptr;  // shard 0 of the device index (nullptr: nothing is indexed)
+    uint64_t table_mask = 0;
+    IndexShards shards;
+    static constexpr int kMaxSegs = 16;
+    uint64_t seg_base[kMaxSegs] = {0};
+    uint32_t nsegs = 0;
+    bool sys = true;
+};
+cudaError_t launch_kv_doorbell(const DoorbellLaunch& a, cudaStream_t stream);
+
 // Number of SMs of the current device (cached per device).
 int sm_count();
 

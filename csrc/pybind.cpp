@@ -292,7 +292,9 @@ PYBIND11_MODULE(_infinistore, m) {
         .def_readwrite("device", &ClientConfig::device)
         .def_readwrite("timeout_ms", &ClientConfig::timeout_ms)
         .def_readwrite("pool_hint", &ClientConfig::pool_hint)
-        .def_readwrite("posted_commit", &ClientConfig::posted_commit);
+        .def_readwrite("posted_commit", &ClientConfig::posted_commit)
+        .def_readwrite("doorbell", &ClientConfig::doorbell)
+        .def_readwrite("doorbell_idle_us", &ClientConfig::doorbell_idle_us);
 
     py::class_<ServerConfig>(m, "ServerConfig")
         .def(py::init<>())
@@ -519,6 +521,8 @@ PYBIND11_MODULE(_infinistore, m) {
             const ClientStats s = c.stats();
             py::dict d;
             d["kernel_launches"] = s.kernel_launches;
+            d["doorbell_ops"] = s.doorbell_ops;
+            d["doorbell_launches"] = s.doorbell_launches;
             d["bytes_written"] = s.bytes_written;
             d["bytes_read"] = s.bytes_read;
             d["ctrl_requests"] = s.ctrl_requests;

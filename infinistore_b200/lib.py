@@ -56,6 +56,12 @@ class ClientConfig(_infinistore.ClientConfig):
     visible to every device-path reader when it returns (in-band commit), server-mediated
     lookups of OTHER connections follow within the TCP delivery time, as in the reference.
     ``pipe_stage_kb`` / ``pipe_ring_kb``: ring geometry of the TMA pipeline (0 = default).
+    ``doorbell`` (default False): latency mode - writes and device-index reads of ONE block of
+    at most 256 KB are handed to a persistent worker CTA through a request ring in pinned host
+    memory instead of launching a kernel (no launch, no event, completion seen by polling host
+    memory in ``sync()``); the worker leaves after ``doorbell_idle_us`` (default 200) without
+    a request, so a device-wide ``torch.cuda.synchronize()`` waits at most that long for it.
+    Needs ``streams >= 1`` (completion by ``sync()``); other operations take the ordinary path.
     """
 
     def __init__(self, **kwargs):
@@ -80,6 +86,8 @@ class ClientConfig(_infinistore.ClientConfig):
         self.posted_commit = bool(kwargs.get("posted_commit", False))
         self.pipe_stage_kb = int(kwargs.get("pipe_stage_kb", 0))
         self.pipe_ring_kb = int(kwargs.get("pipe_ring_kb", 0))
+        self.doorbell = bool(kwargs.get("doorbell", False))
+        self.doorbell_idle_us = int(kwargs.get("doorbell_idle_us", 200))
 
     def __repr__(self):
         return (

@@ -437,3 +437,126 @@ def test_index_overflow_falls_back_to_server_lookups():
         assert not make_conn(port, device_lookup=True).conn.index_incomplete()
     finally:
         srv.stop()
+
+
+# ---------------------------------------------------------------- doorbell worker (latency mode)
+@pytest.mark.parametrize("posted", [False, True])
+def test_doorbell_worker_serves_single_blocks(hbm_server, posted):
+    """ClientConfig(doorbell=True): one-block writes and device-index reads go through the
+    persistent worker CTA - no kernel launch per operation - with the same semantics: in-band
+    commit, first writer wins, misses reported by sync(), other connections see the blocks."""
+    import time
+
+    srv, port = hbm_server
+    conn = make_conn(port, device_lookup=True, doorbell=True, posted_commit=posted)
+    plain = make_conn(port, device_lookup=True)
+    via_server = make_conn(port)
+    sizes = [4096, 100, 131072, 262144, 48 * 1024 + 16]          # bytes; one is unaligned
+    buf = torch.empty(262144, dtype=torch.uint8, device="cuda:0")
+    out = torch.zeros_like(buf)
+    peek = torch.zeros_like(buf)
+    conn.register_mr(buf)
+    conn.register_mr(out)
+    plain.register_mr(peek)
+    via_server.register_mr(peek)
+    launches0 = conn.stats()["kernel_launches"]
+    want = {}
+    for round_ in range(3):
+        for nbytes in sizes:
+            key = f"db-{posted}-{round_}-{nbytes}-{rand_key(5)}"
+            # the SAME source buffer is rewritten before every request: the worker must not
+            # serve it out of a stale L1 line
+            buf.random_(0, 255)
+            torch.cuda.synchronize()
+            want[key] = buf[:nbytes].clone()
+            blocks = conn.allocate_rdma([key], nbytes)
+            conn.rdma_write_cache(buf, [0], nbytes, blocks)
+            conn.sync()
+            out.zero_()
+            torch.cuda.synchronize()
+            conn.read_cache(out, [(key, 0)], nbytes)
+            conn.sync()
+            assert torch.equal(out[:nbytes], want[key]) and not out[nbytes:].any()
+        if round_ == 1:
+            time.sleep(0.02)          # > doorbell_idle_us: the worker has left, the next op relaunches it
+            torch.cuda.synchronize()  # ... so a device-wide synchronise returns
+    st = conn.stats()
+    assert st["doorbell_ops"] == 2 * 3 * len(sizes)
+    assert st["doorbell_launches"] >= 2
+    assert st["kernel_launches"] - launches0 == st["doorbell_launches"]   # nothing else was launched
+    # what the worker published is what every other reader finds (device index and server map)
+    deadline = time.time() + 5
+    for key, data in want.items():
+        n = data.numel()
+        peek.zero_()
+        plain.read_cache(peek, [(key, 0)], n)
+        plain.sync()
+        assert torch.equal(peek[:n], data)
+        while posted and not via_server.check_exist(key) and time.time() < deadline:
+            time.sleep(0.001)
+        peek.zero_()
+        via_server.read_cache(peek, [(key, 0)], n)
+        via_server.sync()
+        assert torch.equal(peek[:n], data)
+    # a miss is reported by sync(); the connection stays usable
+    with pytest.raises(Exception):
+        conn.read_cache(out, [("db-absent-" + rand_key(), 0)], 4096)
+        conn.sync()
+    key0 = next(iter(want))
+    conn.read_cache(out, [(key0, 0)], want[key0].numel())
+    conn.sync()
+    assert torch.equal(out[:want[key0].numel()], want[key0])
+    # first writer wins: a second write of the key changes nothing
+    buf.fill_(7)
+    torch.cuda.synchronize()
+    conn.rdma_write_cache(buf, [0], want[key0].numel(), conn.allocate_rdma([key0], want[key0].numel()))
+    conn.sync()
+    conn.read_cache(out, [(key0, 0)], want[key0].numel())
+    conn.sync()
+    assert torch.equal(out[:want[key0].numel()], want[key0])
+    assert srv.stats()["inflight"] == 0
+
+
+def test_doorbell_mixes_with_the_ordinary_path(hbm_server):
+    """Larger blocks, batches and busy streams take the ordinary path; it is ordered behind
+    what the worker still has to do (a batch read sees a doorbell write of a moment ago)."""
+    _, port = hbm_server
+    conn = make_conn(port, device_lookup=True, doorbell=True)
+    n, elems = 40, 16384
+    src = torch.randn(n * elems, device="cuda:0")
+    dst = torch.zeros_like(src)
+    conn.register_mr(src)
+    conn.register_mr(dst)
+    keys = [f"dbmix-{i}-{rand_key(5)}" for i in range(n)]
+    blocks = conn.allocate_rdma(keys, elems * 4)
+    # blocks 1.. as one batch (ordinary path), block 0 alone through the worker, no sync between
+    conn.rdma_write_cache(src, [i * elems for i in range(1, n)], elems, blocks[1:])
+    conn.sync()
+    conn.rdma_write_cache(src, [0], elems, blocks[:1])
+    ops = conn.stats()["doorbell_ops"]
+    assert ops == 1
+    conn.read_cache(dst, [(k, i * elems) for i, k in enumerate(keys)], elems)   # batch: ordinary
+    conn.sync()
+    assert torch.equal(src, dst)
+    # 1 MB single block: too large for one CTA, ordinary path
+    big = torch.randn(1 << 18, device="cuda:0")
+    conn.register_mr(big)
+    conn.rdma_write_cache(big, [0], 1 << 18, conn.allocate_rdma(["dbmix-big-" + rand_key()], 1 << 20))
+    conn.sync()
+    assert conn.stats()["doorbell_ops"] == ops
+    # the caller's stream is busy producing the data: ordinary path (ordered behind the stream)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        a = torch.randn(4096, 4096, device="cuda:0")
+        for _ in range(20):
+            a = a @ a * 1e-3
+        page = a.flatten()[:elems].contiguous()
+        conn.register_mr(page)
+        k = "dbmix-stream-" + rand_key()
+        conn.rdma_write_cache(page, [0], elems, conn.allocate_rdma([k], elems * 4))
+    conn.sync()
+    back = torch.zeros(elems, device="cuda:0")
+    conn.register_mr(back)
+    conn.read_cache(back, [(k, 0)], elems)
+    conn.sync()
+    assert torch.equal(back, page)

@@ -924,3 +924,20 @@ def test_posted_commit_skips_the_round_trip_and_still_commits(host_server):
     conn.sync()  # leases held: this sync does the round trip that releases them
     assert torch.equal(src, dst)
     assert srv.stats()["inflight"] == 0
+
+
+def test_doorbell_mode_is_inert_without_a_gpu_pool(host_server):
+    """doorbell=True only changes how single blocks reach an HBM pool from a CUDA tensor; with
+    CPU tensors and the host pool every call takes the ordinary path."""
+    _, port = host_server
+    conn = make_conn(port, doorbell=True, doorbell_idle_us=50)
+    assert conn.config.doorbell and conn.config.doorbell_idle_us == 50
+    src = torch.randn(1024)
+    dst = torch.zeros(1024)
+    conn.register_mr(src)
+    conn.rdma_write_cache(src, [0], 1024, conn.allocate_rdma(["db-cpu"], 4096))
+    conn.sync()
+    conn.read_cache(dst, [("db-cpu", 0)], 1024)
+    conn.sync()
+    assert torch.equal(src, dst)
+    assert conn.stats()["doorbell_ops"] == 0 and conn.stats()["doorbell_launches"] == 0

@@ -46,6 +46,7 @@ CUDA_SOURCES = [
     "kernels/kv_read_fused.cu",
     "kernels/kv_fp8.cu",
     "kernels/kv_fp8_pipe.cu",
+    "kernels/kv_doorbell.cu",
     "kernels/kv_bcast_nvls.cu",
 ]
 BINDING = "pybind.cpp"
