@@ -487,7 +487,7 @@ def main():
     elif a.config == "baselines":
         res = baselines(ctx, 128 << 10)
     else:
-        srv = start_shard_server(ctx.local, ctx.base_port + ctx.rank, 1 << 30, granule_kb=16)
+        srv = start_shard_server(ctx.local, ctx.base_port + ctx.rank, 4 << 30, granule_kb=16)
         ctx.barrier()
         res = latency(ctx, ctx.base_port + (ctx.rank + 1) % ctx.world)
         ctx.barrier()

@@ -38,7 +38,7 @@ namespace {
 
 using namespace dev;
 
-constexpr int kThreads = 512;       // warp 0: control, warps 1..15: copy
+constexpr int kThreads = 1024;      // warp 0: control, warps 1..31: copy (62 KB in flight per round)
 constexpr int kCopyThreads = kThreads - 32;
 constexpr int kBarAll = 2;          // named barrier: control + copy warps
 
