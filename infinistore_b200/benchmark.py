@@ -36,6 +36,9 @@ def parse_args(argv=None):
     p.add_argument("--cpu", action="store_true", help="CPU tensors (needs --rdma)")
     p.add_argument("--device-lookup", action="store_true", help="resolve keys in the HBM index")
     p.add_argument("--variant", default="auto", choices=["auto", "ldst", "tma", "ldst256"])
+    p.add_argument("--posted-commit", action="store_true", help="one-way commit in sync()")
+    p.add_argument("--doorbell", action="store_true",
+                   help="latency mode: single blocks through the persistent worker CTA")
     p.add_argument("--json", action="store_true", help="print one JSON line with the result")
     return p.parse_args(argv)
 
@@ -49,6 +52,8 @@ def run(args):
         link_type=args.link_type,
         log_level="warning",
         device_lookup=args.device_lookup,
+        posted_commit=args.posted_commit,
+        doorbell=args.doorbell,
         copy_variant=args.variant,
     )
     config.connection_type = TYPE_RDMA if args.rdma else TYPE_LOCAL_GPU
