@@ -560,3 +560,46 @@ def test_doorbell_mixes_with_the_ordinary_path(hbm_server):
     conn.read_cache(back, [(k, 0)], elems)
     conn.sync()
     assert torch.equal(back, page)
+
+
+def test_doorbell_worker_follows_a_growing_pool():
+    """--auto-increase adds HBM segments while single blocks flow through the worker: it is
+    stopped and relaunched with the new pool map (its reads resolve segment ids with the view it
+    was launched with), nothing is lost or misread across the switch."""
+    from infinistore_b200 import _infinistore as m
+
+    cfg = m.ServerConfig()
+    cfg.service_port = 0
+    cfg.host = "127.0.0.1"
+    cfg.pool_backend = "hbm"
+    cfg.pool_devices = [0]
+    cfg.prealloc_bytes = 8 * 65536          # 8 blocks per segment
+    cfg.minimal_allocate_size = 64
+    cfg.auto_increase = True
+    srv = m.Server(cfg)
+    port = srv.start()
+    try:
+        conn = make_conn(port, device_lookup=True, doorbell=True, posted_commit=True)
+        n, elems = 40, 16384                 # 64 KB blocks: five segments' worth
+        src = torch.randn(n * elems, device="cuda:0")
+        dst = torch.zeros_like(src)
+        conn.register_mr(src)
+        conn.register_mr(dst)
+        keys = [f"grow-{i}-{rand_key(5)}" for i in range(n)]
+        for i, k in enumerate(keys):
+            conn.rdma_write_cache(src, [i * elems], elems, conn.allocate_rdma([k], elems * 4))
+            conn.sync()
+            if i % 3 == 0:                   # read an OLD block right after the pool grew
+                j = i // 2
+                conn.read_cache(dst, [(keys[j], j * elems)], elems)
+                conn.sync()
+                assert torch.equal(dst[j * elems:(j + 1) * elems], src[j * elems:(j + 1) * elems])
+        assert srv.stats()["segments"] >= 4
+        st = conn.stats()
+        assert st["doorbell_ops"] >= n and st["doorbell_launches"] >= 3
+        for i, k in enumerate(keys):
+            conn.read_cache(dst, [(k, i * elems)], elems)
+        conn.sync()
+        assert torch.equal(src, dst)
+    finally:
+        srv.stop()
