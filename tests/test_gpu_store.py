@@ -603,3 +603,52 @@ def test_doorbell_worker_follows_a_growing_pool():
         assert torch.equal(src, dst)
     finally:
         srv.stop()
+
+
+def test_doorbell_worker_idle_exit_races_and_ring_wrap(hbm_server):
+    """Two connections (two workers on one GPU) with a 30 us idle timeout and random pauses
+    around it, so requests keep arriving while a worker is leaving; bursts of more posts than
+    the ring has slots; every block is verified through the other connection."""
+    import time
+
+    _, port = hbm_server
+    conns = [make_conn(port, device_lookup=True, doorbell=True, doorbell_idle_us=30,
+                       posted_commit=bool(i)) for i in range(2)]
+    rnd = random.Random(11)
+    elems = 2048
+    bufs = [torch.empty(128 * elems, device="cuda:0") for _ in conns]
+    outs = [torch.zeros(128 * elems, device="cuda:0") for _ in conns]
+    for c, b, o in zip(conns, bufs, outs):
+        c.register_mr(b)
+        c.register_mr(o)
+    written = []                                   # (key, tensor copy)
+    for step in range(120):
+        w = step % 2
+        conn, buf = conns[w], bufs[w]
+        burst = rnd.choice([1, 1, 1, 2, 5, 100])   # 100 > 64 ring slots
+        buf.normal_()
+        torch.cuda.synchronize()
+        keys = [f"race-{step}-{i}-{rand_key(4)}" for i in range(burst)]
+        blocks = conn.allocate_rdma(keys, elems * 4)
+        for i in range(burst):                      # single-block calls, no sync in between
+            conn.rdma_write_cache(buf, [i * elems], elems, blocks[i:i + 1])
+        conn.sync()
+        snap = buf[:burst * elems].clone()
+        written.extend((k, snap[i * elems:(i + 1) * elems]) for i, k in enumerate(keys))
+        # the OTHER connection reads a few of everything written so far, one block per call
+        other, out = conns[1 - w], outs[1 - w]
+        picks = [written[rnd.randrange(len(written))] for _ in range(min(burst, 70))]
+        for i, (k, _) in enumerate(picks):
+            other.read_cache(out, [(k, i * elems)], elems)
+        other.sync()
+        for i, (_, data) in enumerate(picks):
+            assert torch.equal(out[i * elems:(i + 1) * elems], data)
+        pause = rnd.choice([0, 0, 10e-6, 25e-6, 30e-6, 35e-6, 60e-6, 2e-3])
+        if pause:
+            t0 = time.perf_counter()
+            while time.perf_counter() - t0 < pause:
+                pass
+    for c in conns:
+        st = c.stats()
+        assert st["doorbell_ops"] > 500 and st["doorbell_launches"] >= 5
+        c.close()
