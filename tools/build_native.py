@@ -38,6 +38,8 @@ HOST_SOURCES = [
     "fabric/fdpass.cpp",
     "ctrl/server.cpp",
     "ctrl/client.cpp",
+    "ctrl/client_data.cpp",
+    "ctrl/client_doorbell.cpp",
 ]
 CUDA_SOURCES = [
     "kernels/kv_copy.cu",
