@@ -9,8 +9,8 @@ batches, one `sync()` after each phase, read-back verified against the source.
 
 One STEP = `--rounds` rounds of (write size-mb -> sync -> read it back -> sync), every round
 with fresh keys (first-writer-wins would turn a re-write into a no-op).  Defaults: 4 GiB per
-phase x 16 rounds = 128 GiB moved per GPU per step, so that K = 20 steps are a timed region
-of ~1 s at N = 1 and ~4 s at N >= 2 (round 1 timed 0.02 s).  The pool cannot hold a whole
+phase x 24 rounds = 192 GiB moved per GPU per step, so that K = 20 steps are a timed region
+of ~1.4 s at N = 1 and ~6 s at N >= 2 (round 1 timed 0.02 s; 16 rounds gave 0.93 s at N = 1).  The pool cannot hold a whole
 run: it is purged and re-reserved between epochs, OUTSIDE the timed regions, whose
 device-measured durations (CUDA events, barrier + synchronize on both sides) are summed.
 
@@ -52,7 +52,7 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--size-mb", type=int, default=4096, help="KV bytes per phase (one round)")
-    p.add_argument("--rounds", type=int, default=16, help="write+read rounds per step")
+    p.add_argument("--rounds", type=int, default=24, help="write+read rounds per step")
     p.add_argument("--block-kb", type=int, default=128)
     p.add_argument("--layers", type=int, default=32, help="batches per phase (reference --steps)")
     p.add_argument("--variant", default="auto", choices=["auto", "ldst", "tma", "ldst256"])
