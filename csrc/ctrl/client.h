@@ -45,6 +45,18 @@ struct KeyOffset {
     uint64_t offset;  // bytes from the tensor base
 };
 
+// The keys of a batch in the layout the lookup kernels read: every key on an 8-byte boundary,
+// zero padded to a multiple of 8 (an empty key occupies 8 zero bytes), offsets and lengths as
+// u32 arrays.  A caller that already holds its keys like this (the Python binding's arena)
+// passes the view along with the KeyOffset list and saves the client a second pass over them.
+struct PackedKeys {
+    const uint8_t* bytes = nullptr;
+    size_t nbytes = 0;
+    const uint32_t* off = nullptr;
+    const uint32_t* len = nullptr;
+    size_t n = 0;
+};
+
 // addr -> key fingerprint of blocks that were allocated but not written yet.
 // Blocks are almost always written in the order they were allocated, so the entries sit in a
 // FIFO and `take` pops the head (a few ns per block on the write hot path); anything out of
@@ -138,7 +150,7 @@ class Connection {
                const RemoteBlock* blocks, size_t nblocks, uint64_t base_ptr, int device,
                uint64_t stream, MoveResult* res = nullptr);
     int r_rdma(const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr, int device,
-               uint64_t stream, MoveResult* res = nullptr);
+               uint64_t stream, MoveResult* res = nullptr, const PackedKeys* packed = nullptr);
     int rw_local(char op, const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr,
                  int device, uint64_t stream);
     // read the same pages into several destination tensors of one device: each pool block
@@ -228,7 +240,7 @@ class Connection {
                                           const std::vector<RemoteBlock>* rb, void* stream);
     int read_via_device_index(const std::vector<KeyOffset>& blocks, int block_size,
                               uint64_t base_ptr, int device, uint64_t stream, int fp8_elems = 0,
-                              MoveResult* res = nullptr);
+                              MoveResult* res = nullptr, const PackedKeys* packed = nullptr);
     int match_via_device_index(const std::vector<std::string_view>& keys, bool exist_only);
     int ensure_host_registered(uint64_t ptr, size_t bytes, int device, bool temporary);
     void release_temporary_host_regs();

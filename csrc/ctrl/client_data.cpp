@@ -477,10 +477,10 @@ int Connection::r_rdma_fp8(const std::vector<KeyOffset>& blocks, int elems, uint
 }
 
 int Connection::r_rdma(const std::vector<KeyOffset>& blocks, int block_size, uint64_t base_ptr,
-                       int device, uint64_t stream, MoveResult* res) {
+                       int device, uint64_t stream, MoveResult* res, const PackedKeys* packed) {
     if (blocks.empty()) return 0;
     if (device_lookup_ && server_hbm_ && device >= 0 && device_index_usable())
-        return read_via_device_index(blocks, block_size, base_ptr, device, stream, 0, res);
+        return read_via_device_index(blocks, block_size, base_ptr, device, stream, 0, res, packed);
     std::vector<RemoteBlock> rb;
     const int r = lookup_blocks(kOpReadLookup, blocks, block_size, rb);
     if (r != 0) return r;
@@ -533,7 +533,7 @@ static size_t pack_keys(const std::string_view* keys, size_t n, uint8_t* bytes, 
 
 int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int block_size,
                                       uint64_t base_ptr, int device, uint64_t stream_in,
-                                      int fp8_elems, MoveResult* res) {
+                                      int fp8_elems, MoveResult* res, const PackedKeys* packed) {
     NvtxRange nvtx("istore.read_via_device_index");
     std::lock_guard<std::mutex> lk(mu_);
     DevCtx* ctx = dev_ctx(device);
@@ -568,19 +568,33 @@ int Connection::read_via_device_index(const std::vector<KeyOffset>& blocks, int 
     for (size_t base = 0; base < blocks.size(); base += kMaxBatch) {
         const uint64_t t_build0 = now_ns();
         const size_t n = std::min(kMaxBatch, blocks.size() - base);
+        // keys into the pinned ring, in the layout the kernels hash them from; three memcpys
+        // when the caller holds them like that already (one batch), a pass over the keys else
+        const bool prepacked = packed && base == 0 && packed->n == blocks.size() && n == blocks.size();
         size_t key_bytes = 0;
-        std::vector<std::string_view> kp(n);
-        for (size_t i = 0; i < n; ++i) {
-            kp[i] = blocks[base + i].key;
-            key_bytes += align_up(std::max<size_t>(kp[i].size(), 1), 8);
+        std::vector<std::string_view> kp;
+        if (prepacked) {
+            key_bytes = packed->nbytes;
+        } else {
+            kp.resize(n);
+            for (size_t i = 0; i < n; ++i) {
+                kp[i] = blocks[base + i].key;
+                key_bytes += align_up(std::max<size_t>(kp[i].size(), 1), 8);
+            }
         }
         const size_t at_bytes = ctx->ring_alloc(key_bytes);
         const size_t at_off = ctx->ring_alloc(n * 4);
         const size_t at_len = ctx->ring_alloc(n * 4);
         const size_t at_dst = ctx->ring_alloc(n * 8);
-        pack_keys(kp.data(), n, ctx->ring_h + at_bytes,
-                  reinterpret_cast<uint32_t*>(ctx->ring_h + at_off),
-                  reinterpret_cast<uint32_t*>(ctx->ring_h + at_len));
+        if (prepacked) {
+            std::memcpy(ctx->ring_h + at_bytes, packed->bytes, key_bytes);
+            std::memcpy(ctx->ring_h + at_off, packed->off, n * 4);
+            std::memcpy(ctx->ring_h + at_len, packed->len, n * 4);
+        } else {
+            pack_keys(kp.data(), n, ctx->ring_h + at_bytes,
+                      reinterpret_cast<uint32_t*>(ctx->ring_h + at_off),
+                      reinterpret_cast<uint32_t*>(ctx->ring_h + at_len));
+        }
         auto* dst = reinterpret_cast<uint64_t*>(ctx->ring_h + at_dst);
         for (size_t i = 0; i < n; ++i) dst[i] = blocks[base + i].offset;
 

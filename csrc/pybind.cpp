@@ -136,11 +136,14 @@ void offsets_from_py(const py::object& obj, OffsetSpan& out) {
 // Keys are copied once into a per-thread arena while the GIL is held; the views stay valid
 // after the GIL is released for the (possibly blocking) native call.
 struct KeyArena {
+    // the layout the lookup kernels read (client.h PackedKeys): keys on 8-byte boundaries,
+    // zero padded - the data plane copies the arena into its pinned ring as it is
     std::vector<char> bytes;
-    std::vector<std::pair<size_t, size_t>> spans;  // offset, length
+    std::vector<uint32_t> off, len;
     void clear() {
         bytes.clear();
-        spans.clear();
+        off.clear();
+        len.clear();
     }
     void add(PyObject* o) {
         const char* p = nullptr;
@@ -154,11 +157,20 @@ struct KeyArena {
         } else {
             throw py::type_error("keys must be str or bytes");
         }
-        spans.emplace_back(bytes.size(), size_t(n));
-        bytes.insert(bytes.end(), p, p + n);
+        if (bytes.size() + size_t(n) + 8 > 0xffffffffull) throw py::value_error("too many key bytes");
+        const size_t at = bytes.size();
+        const size_t padded = (std::max<size_t>(size_t(n), 1) + 7) & ~size_t(7);
+        off.push_back(uint32_t(at));
+        len.push_back(uint32_t(n));
+        bytes.resize(at + padded, 0);
+        std::memcpy(bytes.data() + at, p, size_t(n));
     }
     std::string_view view(size_t i) const {
-        return std::string_view(bytes.data() + spans[i].first, spans[i].second);
+        return std::string_view(bytes.data() + off[i], len[i]);
+    }
+    PackedKeys packed() const {
+        return PackedKeys{reinterpret_cast<const uint8_t*>(bytes.data()), bytes.size(), off.data(),
+                          len.data(), off.size()};
     }
 };
 
@@ -417,8 +429,9 @@ PYBIND11_MODULE(_infinistore, m) {
                int device, uint64_t stream, uint64_t scale) {
                 std::vector<KeyOffset> kb;
                 blocks_list_from_py(blocks, scale, kb);
+                const PackedKeys packed = t_arena.packed();  // this thread's arena: still ours
                 py::gil_scoped_release rel;
-                return c.r_rdma(kb, block_size, base_ptr, device, stream);
+                return c.r_rdma(kb, block_size, base_ptr, device, stream, nullptr, &packed);
             },
             py::arg("blocks"), py::arg("block_size"), py::arg("base_ptr"),
             py::arg("device") = -1, py::arg("stream") = 0, py::arg("scale") = 1)
