@@ -10,7 +10,8 @@ batches, one `sync()` after each phase, read-back verified against the source.
 One STEP = `--rounds` rounds of (write size-mb -> sync -> read it back -> sync), every round
 with fresh keys (first-writer-wins would turn a re-write into a no-op).  Defaults: 4 GiB per
 phase x 24 rounds = 192 GiB moved per GPU per step, so that K = 20 steps are a timed region
-of ~1.4 s at N = 1 and ~6 s at N >= 2 (round 1 timed 0.02 s; 16 rounds gave 0.93 s at N = 1).  The pool cannot hold a whole
+of ~1.4 s at N = 1 and ~6 s at N >= 2 (round 1 timed 0.02 s; 16 rounds gave 0.93 s at
+N = 1).  The pool cannot hold a whole
 run: it is purged and re-reserved between epochs, OUTSIDE the timed regions, whose
 device-measured durations (CUDA events, barrier + synchronize on both sides) are summed.
 
@@ -109,7 +110,8 @@ def reference_arm(args):
         return unavailable("baseline/_ref has no native module: run baseline/build_reference.sh "
                            "(needs uvloop's libuv, flashinfer's spdlog headers, nvcc toolchain)")
     env = dict(os.environ, PYTHONPATH=ref,
-               PATH=os.path.join(ROOT, "baseline", "refshim", "bin") + os.pathsep + os.environ.get("PATH", ""))
+               PATH=os.path.join(ROOT, "baseline", "refshim", "bin") + os.pathsep +
+               os.environ.get("PATH", ""))
     env.pop("PYTHONHOME", None)
     probe = subprocess.run([sys.executable, "-c", "import infinistore._infinistore, torch; "
                             "assert torch.cuda.is_available()"],
@@ -171,7 +173,8 @@ def reference_arm(args):
             m = re.search(r"write cache: ([0-9.]+) MB/s, read cache: ([0-9.]+) MB/s", r.stdout)
             if r.returncode != 0 or not m:
                 raise RuntimeError("reference benchmark failed: " +
-                                   (r.stderr.strip().splitlines() or r.stdout.strip().splitlines() or ["?"])[-1])
+                                   (r.stderr.strip().splitlines() or r.stdout.strip().splitlines()
+                                    or ["?"])[-1])
             return float(m.group(1)), float(m.group(2))
 
         if args.warmup:

@@ -91,7 +91,8 @@ def main():
                 lr.append((t2 - t1) * 1e6)
         srv.purge()
         row = {"block_kb": kb, "blocks_per_call": per,
-               "write_GBps": round(total * a.iters / tw / 1e9, 1), "read_GBps": round(total * a.iters / tr / 1e9, 1),
+               "write_GBps": round(total * a.iters / tw / 1e9, 1),
+               "read_GBps": round(total * a.iters / tr / 1e9, 1),
                "write_sync_us_p50": round(pct(lw, 50), 1), "write_sync_us_p99": round(pct(lw, 99), 1),
                "read_sync_us_p50": round(pct(lr, 50), 1), "read_sync_us_p99": round(pct(lr, 99), 1)}
         rows.append(row)

@@ -45,7 +45,8 @@ def run_memcpy(label, src, pool, dst, nblocks, bs, layers, iters, device):
     torch.cuda.synchronize()
     ok = bool(torch.equal(src.cpu(), dst.cpu()))
     size = nblocks * bs * iters
-    return {"baseline": label, "write_GBps": round(size / tw / 1e9, 2), "read_GBps": round(size / tr / 1e9, 2),
+    return {"baseline": label, "write_GBps": round(size / tw / 1e9, 2),
+            "read_GBps": round(size / tr / 1e9, 2),
             "write_read_GBps": round(2 * size / (tw + tr) / 1e9, 2), "verified": ok,
             "block_kb": bs >> 10, "layers": layers}
 

@@ -58,7 +58,8 @@ for variant, ctas in (("ldst256", 0), ("ldst256", 296), ("tma", 0)):
         uni = timed([0], table, variant, ctas)[0]
         bi = timed([0, 1], table, variant, ctas)
         row = {"op": name, "variant": variant, "ctas": ctas, "uni_GBps": round(total / uni / 1e6, 1),
-               "bidir_GBps_gpu0": round(total / bi[0] / 1e6, 1), "bidir_GBps_gpu1": round(total / bi[1] / 1e6, 1)}
+               "bidir_GBps_gpu0": round(total / bi[0] / 1e6, 1),
+               "bidir_GBps_gpu1": round(total / bi[1] / 1e6, 1)}
         res.append(row)
         print(row, flush=True)
 # mixed: GPU0 pushes while GPU1 pulls (all traffic in ONE direction of the link pair)

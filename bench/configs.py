@@ -475,7 +475,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("config", choices=["fanin", "bcast", "fp8", "latency", "baselines"])
     ap.add_argument("--max-ctas", type=int, default=0, help="fp8: grid cap of the client's kernels")
-    ap.add_argument("--layers", type=int, default=32, help="fp8: calls per phase (pages per call = 16384 / layers)")
+    ap.add_argument("--layers", type=int, default=32,
+                    help="fp8: calls per phase (pages per call = 16384 / layers)")
     a = ap.parse_args()
     ctx = _standalone_ctx()
     if a.config == "fanin":

@@ -69,7 +69,8 @@ def main():
             "python_slice_1024": us(ta, tb), "slice_plus_parse_1024": us(tb, tc),
             "read_issue": us(tc, td), "read_native_build": ns("ns_build", s1, s2),
             "read_native_streams": ns("ns_streams", s1, s2), "read_native_launch": ns("ns_launch", s1, s2)},
-            "phase_ms": {"write_sync_wait": round((t2 - t1) * 1e3, 3), "read_sync_wait": round((te - td) * 1e3, 3)}}
+            "phase_ms": {"write_sync_wait": round((t2 - t1) * 1e3, 3),
+                         "read_sync_wait": round((te - td) * 1e3, 3)}}
         assert torch.equal(src, dst)
     print(json.dumps(out))
     os.makedirs("gpurun_out", exist_ok=True)

@@ -79,7 +79,8 @@ def main():
                    "cxx_launch_us_per_call": st["ns_launch"] / max(st["calls"], 1) / 1e3}
             out[f"lookup={'device' if lookup else 'host'} blocks/call={per_call}"] = {
                 k: round(v, 2) for k, v in row.items()}
-            print(lookup, per_call, out[f"lookup={'device' if lookup else 'host'} blocks/call={per_call}"], flush=True)
+            label = f"lookup={'device' if lookup else 'host'} blocks/call={per_call}"
+            print(lookup, per_call, out[label], flush=True)
             srv.purge()
         conn.close()
     srv.stop()

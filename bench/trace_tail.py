@@ -49,7 +49,8 @@ def run(pool_dev, label, nblk=256, bs=128 << 10, ctas=0, all_local=False, debug=
                "fence_cost_med": np.median(rel[:, 3] - rel[:, 2]),
                "fence_cost_max": (rel[:, 3] - rel[:, 2]).max()}
     out = {k: (round(float(v), 2) if not isinstance(v, int) else v) for k, v in out.items()}
-    print(label, {a: b for a, b in out.items() if a in ("event_us", "fence_done_max", "commit_max", "claim_done_max", "copy_done_max")}, flush=True)
+    shown = ("event_us", "fence_done_max", "commit_max", "claim_done_max", "copy_done_max")
+    print(label, {a: b for a, b in out.items() if a in shown}, flush=True)
     return out
 
 

@@ -21,7 +21,7 @@ from __future__ import annotations
 import asyncio
 import os
 import time
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Tuple
 
 import torch
 

@@ -9,7 +9,6 @@ from __future__ import annotations
 
 from typing import List, Sequence
 
-import numpy as np
 import torch
 
 from .. import _infinistore
@@ -78,7 +77,8 @@ class PrefixBroadcaster:
         mc = self.group.mc_ptr(writer)
         flags_mc = 0
         if flag_ids is not None:
-            assert self.flag_slots and list(flag_ids) == list(range(flag_ids[0], flag_ids[0] + len(flag_ids))), \
+            consecutive = list(range(flag_ids[0], flag_ids[0] + len(flag_ids)))
+            assert self.flag_slots and list(flag_ids) == consecutive, \
                 "flag ids: a contiguous run of slots, one per block"
             flags_mc = mc + self.data_bytes + 4 * flag_ids[0]
             per = _infinistore.kernels.bcast_chunks_per_block(nbytes)

@@ -1,8 +1,6 @@
 """One process per GPU (torchrun): every rank hosts a pool shard and talks to the others."""
 from __future__ import annotations
 
-import os
-from typing import List, Optional
 
 from .. import _infinistore
 from ..lib import ClientConfig, InfinityConnection, TYPE_RDMA

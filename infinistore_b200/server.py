@@ -5,7 +5,8 @@ Flags, defaults and endpoints follow the reference (infinistore/server.py:26-263
 --prealloc-size 16 --dev-name --ib-port --link-type --minimal-allocate-size 64
 --num-stream --warmup`` and ``POST /purge``, ``POST /selftest/{port}``, ``GET /kvmap_len``.
 New: ``--pool-backend``, ``--pool-devices``, ``--extend-size``, ``--replica-size``,
-``--load-from``, ``--evict``, ``--evict-ratio``; ``GET /metrics`` (Prometheus text), ``GET /stats`` (JSON), ``POST /dump`` and
+``--load-from``, ``--evict``, ``--evict-ratio``; ``GET /metrics`` (Prometheus text),
+``GET /stats`` (JSON), ``POST /dump`` and
 ``POST /load`` (checkpoint / resume; bare names inside ``--checkpoint-dir`` only, token or
 loopback callers only).  ``--host`` is honoured (the reference parses
 and ignores it).  The data/control plane runs on a native reactor thread; uvicorn only

@@ -4,7 +4,6 @@ body_size and spins forever on an unknown op byte (Append
 import socket
 import struct
 
-import pytest
 from hypothesis import HealthCheck, given, settings
 from hypothesis import strategies as st
 

@@ -119,5 +119,6 @@ def test_chunk_plan_balances_a_persistent_grid():
         lo = rnd.randint(1, 8)
         chunk, cpb = plan(n, units, lo, 64, ctas)
         assert cpb == -(-units // chunk) and min(lo, units) <= chunk <= max(min(units, 64), min(lo, units))
-        best = min(makespan(n, units, c, ctas) for c in range(min(lo, units), max(min(units, 64), min(lo, units)) + 1))
+        lo_c, hi_c = min(lo, units), max(min(units, 64), min(lo, units))
+        best = min(makespan(n, units, c, ctas) for c in range(lo_c, hi_c + 1))
         assert makespan(n, units, chunk, ctas) * 100 <= best * 104

@@ -2,11 +2,6 @@
 under AddressSanitizer + UBSan (the reference has no sanitizer targets)."""
 import os
 import subprocess
-import sys
-
-import pytest
-
-from conftest import ROOT
 
 
 def test_native_core_unit_tests():
