@@ -369,7 +369,11 @@ __global__ void __launch_bounds__(64)
                         bulk_s2g(reinterpret_cast<uint8_t*>(int64_t(d.dst) + a.delta[rank]) + o,
                                  ring + size_t(s) * a.stage_bytes, plen);
                     } else {
-                        mbar_arrive(&full[s]);  // a miss: complete the phase, keep parities in step
+                        // a miss: complete the phase to keep the parities in step - and wait for
+                        // it like for any other (returns at once; synccheck insists that a
+                        // completed phase has been waited for before the barrier is used again)
+                        mbar_arrive(&full[s]);
+                        mbar_wait(&full[s], ph);
                     }
                     bulk_commit();
                     bulk_wait_read<kStoreLag>();
