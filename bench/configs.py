@@ -96,7 +96,7 @@ def latency(ctx: Ctx, port: int, sizes_kb=(4, 128, 1024), samples=200):
              # stream and an internal one
              "posted_in_stream": {"posted_commit": True, "streams": 0},
              # latency mode: a persistent worker CTA polls a request ring in pinned host memory
-             # (kernels/kv_doorbell.cu; blocks <= 1 MB, above 64 KB shared by 8 CTAs)
+             # (kernels/kv_doorbell.cu; blocks <= 256 KB, larger ones take the ordinary path)
              "doorbell": {"doorbell": True},
              "posted_doorbell": {"posted_commit": True, "doorbell": True}}
     for mode, kw in modes.items():

@@ -62,7 +62,6 @@ struct ClientConfig {
     // a request (a device-wide synchronise waits at most that long for it).
     bool doorbell = false;
     int doorbell_idle_us = 200;
-    int doorbell_ctas = 8;  // leader + helper CTAs; blocks > 64 KB are split over them (1..8)
 };
 
 }  // namespace istore

@@ -86,7 +86,6 @@ struct Connection::DevCtx {
         kernels::DoorbellReq* ring_d = nullptr;
         kernels::DoorbellCtl* ctl_h = nullptr;
         kernels::DoorbellCtl* ctl_d = nullptr;
-        kernels::DoorbellMail* mail_d = nullptr;  // device memory: leader <-> helper CTAs
         cudaStream_t stream = nullptr;
         uint64_t posted = 0;     // last request written to the ring
         uint64_t collected = 0;  // statuses of requests <= collected have been taken
@@ -164,7 +163,6 @@ struct Connection::DevCtx {
             }
             if (db->ring_h) cudaFreeHost(db->ring_h);
             if (db->ctl_h) cudaFreeHost(db->ctl_h);
-            if (db->mail_d) cudaFree(db->mail_d);
         }
         for (int i = 0; i < nstreams; ++i) {
             cudaStreamSynchronize(pool[i]);

@@ -85,11 +85,7 @@ int Connection::doorbell_start(DevCtx* ctx) {
     mix_in(L.shards.n);
     L.epoch = ++db.epoch;
     L.first_seq = db.next_serve;
-    L.ctas = std::max(1, std::min(cfg_.doorbell_ctas, kernels::kDoorbellMaxCtas));
-    L.mail = L.ctas > 1 ? db.mail_d : nullptr;
-    // the mailbox counts arrivals per launch: cleared behind the previous worker, ahead of this one
-    cudaError_t e = cudaMemsetAsync(db.mail_d, 0, sizeof(kernels::DoorbellMail), db.stream);
-    if (e == cudaSuccess) e = kernels::launch_kv_doorbell(L, db.stream);
+    const cudaError_t e = kernels::launch_kv_doorbell(L, db.stream);
     if (e != cudaSuccess) {
         fail(std::string("doorbell worker failed to launch: ") + cudaGetErrorString(e));
         return -1;
@@ -120,12 +116,10 @@ int Connection::doorbell_post(DevCtx* ctx, uint32_t op, const uint64_t (&q)[6]) 
         if (cudaHostAlloc(reinterpret_cast<void**>(&db->ctl_h), sizeof(kernels::DoorbellCtl),
                           cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
             cudaHostGetDevicePointer(&dp, db->ctl_h, 0) != cudaSuccess ||
-            cudaMalloc(reinterpret_cast<void**>(&db->mail_d), sizeof(kernels::DoorbellMail)) != cudaSuccess ||
             cudaStreamCreateWithPriority(&db->stream, cudaStreamNonBlocking, hi) != cudaSuccess) {
             fail(std::string("doorbell control block: ") + cudaGetErrorString(cudaGetLastError()));
             if (db->ring_h) cudaFreeHost(db->ring_h);
             if (db->ctl_h) cudaFreeHost(db->ctl_h);
-            if (db->mail_d) cudaFree(db->mail_d);
             return -1;
         }
         db->ctl_d = static_cast<kernels::DoorbellCtl*>(dp);

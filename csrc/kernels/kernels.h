@@ -337,10 +337,7 @@ cudaError_t launch_kv_read_when_ready(const ReadyLaunch& a, cudaStream_t stream)
 #define ISTORE_KHD
 #endif
 constexpr int kDoorbellMaxSlots = 64;
-constexpr uint32_t kDoorbellMaxBytes = 1u << 20;    // one block per request, at most this
-constexpr uint32_t kDoorbellSoloBytes = 64u << 10;  // up to here the leader CTA copies alone
-constexpr int kDoorbellMaxCtas = 8;                 // leader + helpers
-constexpr uint64_t kDoorbellQuit = ~0ull;
+constexpr uint32_t kDoorbellMaxBytes = 256u << 10;  // larger blocks want more than one CTA
 constexpr uint64_t kDoorbellMagic = 0x646f6f7262656c6cull;
 enum : uint32_t { kDoorbellWrite = 1, kDoorbellRead = 2, kDoorbellStop = 3 };
 enum : uint32_t { kDoorbellOk = 0, kDoorbellMiss = 1, kDoorbellStale = 2, kDoorbellIndexFull = 3 };
@@ -356,15 +353,6 @@ struct DoorbellCtl {
     alignas(64) uint64_t done_seq;  // worker -> host: every request <= done_seq has completed
     alignas(64) uint64_t state;     // worker -> host: doorbell_state(epoch, next request, code)
     alignas(64) uint32_t status[kDoorbellMaxSlots];  // per ring slot, valid once done
-};
-// Device-memory mailbox between the leader CTA and its helpers (zeroed before every launch):
-// for a block larger than kDoorbellSoloBytes the leader publishes the resolved addresses, every
-// CTA copies one slice, helpers count themselves in `arrived` (cumulative over the launch).
-struct DoorbellMail {
-    uint64_t seq;  // request the helpers are to work on; kDoorbellQuit: leave
-    uint64_t src, dst;
-    uint32_t bytes;
-    uint32_t arrived;
 };
 ISTORE_KHD inline uint64_t doorbell_state(uint32_t epoch, uint64_t next, uint32_t code) {
     return (uint64_t(epoch & 0xfffffu) << 44) | ((next & ((1ull << 42) - 1)) << 2) | code;
@@ -383,8 +371,6 @@ struct DoorbellLaunch {
     uint64_t seg_base[kMaxSegs] = {0};
     uint32_t nsegs = 0;
     bool sys = true;
-    DoorbellMail* mail = nullptr;  // device memory; nullptr: a single CTA
-    int ctas = 1;                  // leader + helpers (<= kDoorbellMaxCtas)
 };
 cudaError_t launch_kv_doorbell(const DoorbellLaunch& a, cudaStream_t stream);
 

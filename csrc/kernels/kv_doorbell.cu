@@ -19,15 +19,9 @@
 //                   re-checked after the copy (purge / eviction safe, as on every device path)
 //            both : status word, then st.release.sys of done_seq into host memory
 //
-// Blocks of more than 64 KB are split: the leader CTA (the one that polls) publishes the
-// resolved addresses in a device-memory mailbox, up to seven helper CTAs - parked on that
-// mailbox, one thread each spinning in L2 - copy a slice apiece, fence, and count themselves
-// in; the leader commits / re-checks once everyone has arrived.  One CTA pulls 128 KB over
-// NVLink in ~7 us (62 KB in flight per round trip), eight do it in ~2.
-//
 // The worker leaves when no request arrived for `idle_ns` (so a device-wide synchronise
 // never waits longer than that) and says so in `state`; the host relaunches it with the next
-// request.  One block per request, at most kDoorbellMaxBytes (1 MB); anything else takes the
+// request.  One block per request, at most kDoorbellMaxBytes; anything else takes the
 // ordinary path.  Replaces, for this case, the reference's per-request stream + event +
 // cudaMemcpyAsync + cudaEventSynchronize (src/infinistore.cpp:570-804) and its COMMIT message.
 #include <algorithm>
@@ -74,15 +68,13 @@ __device__ __forceinline__ uint8_t ld_cg_u8(const void* p) {
     return uint8_t(r);
 }
 
-// `len` bytes, src -> dst, by the copy warps (tid = 0 .. kCopyThreads-1): 16-byte vectors
-// over the aligned body, single bytes for a tail (or for everything when a pointer is odd)
+// `len` bytes, src -> dst, by the copy warps (tid = 0 .. kCopyThreads-1)
 __device__ __forceinline__ void copy_block(uint8_t* dst, const uint8_t* src, uint32_t len,
                                            uint32_t tid) {
-    uint32_t body = 0;
-    if (((reinterpret_cast<uint64_t>(dst) | reinterpret_cast<uint64_t>(src)) & 15) == 0) {
+    const uint64_t a = reinterpret_cast<uint64_t>(dst) | reinterpret_cast<uint64_t>(src) | len;
+    if ((a & 15) == 0) {
         constexpr int U = 4;
         const uint32_t nvec = len / 16;
-        body = nvec * 16;
         uint32_t i = tid;
         for (; i + (U - 1) * kCopyThreads < nvec; i += U * kCopyThreads) {
             uint4 v[U];
@@ -92,30 +84,9 @@ __device__ __forceinline__ void copy_block(uint8_t* dst, const uint8_t* src, uin
             for (int u = 0; u < U; ++u) st_v4(dst + size_t(i + u * kCopyThreads) * 16, v[u]);
         }
         for (; i < nvec; i += kCopyThreads) st_v4(dst + size_t(i) * 16, ld_cg_v4(src + size_t(i) * 16));
+    } else {
+        for (uint32_t i = tid; i < len; i += kCopyThreads) dst[i] = ld_cg_u8(src + i);
     }
-    for (uint32_t i = body + tid; i < len; i += kCopyThreads) dst[i] = ld_cg_u8(src + i);
-}
-
-// slice `c` of `n` of a block of `bytes` (16-byte granular): [lo, hi)
-__device__ __forceinline__ void slice_of(uint32_t bytes, uint32_t c, uint32_t n, uint32_t* lo,
-                                         uint32_t* hi) {
-    const uint32_t per = ((bytes + n - 1) / n + 15) & ~15u;
-    *lo = min(bytes, c * per);
-    *hi = min(bytes, *lo + per);
-}
-
-__device__ __forceinline__ uint64_t ld_acquire_gpu_u64(const uint64_t* p) {
-    uint64_t v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu_u64(uint64_t* p, uint64_t v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 struct Shared {
@@ -125,49 +96,10 @@ struct Shared {
     uint32_t slot, tag;  // READ: what the probe resolved (for the re-check)
 };
 
-// A helper CTA: parked on the mailbox, copies its slice of every large block.
-__device__ __forceinline__ void helper_cta(const DoorbellLaunch& a, Shared& sh) {
-    const uint32_t warp = threadIdx.x >> 5;
-    uint64_t seen = 0;
-    for (;;) {
-        if (threadIdx.x == 0) {
-            uint64_t s;
-            while ((s = ld_acquire_gpu_u64(&a.mail->seq)) == seen) __nanosleep(100);
-            sh.q[0] = s;
-            if (s != kDoorbellQuit) {  // ordered behind the acquire
-                sh.q[1] = *reinterpret_cast<volatile uint64_t*>(&a.mail->src);
-                sh.q[2] = *reinterpret_cast<volatile uint64_t*>(&a.mail->dst);
-                sh.q[3] = *reinterpret_cast<volatile uint32_t*>(&a.mail->bytes);
-            }
-        }
-        bar_all();
-        const uint64_t s = sh.q[0];
-        if (s == kDoorbellQuit) return;
-        uint32_t lo, hi;
-        slice_of(uint32_t(sh.q[3]), blockIdx.x, gridDim.x, &lo, &hi);
-        if (warp != 0 && hi > lo)
-            copy_block(reinterpret_cast<uint8_t*>(sh.q[2]) + lo,
-                       reinterpret_cast<const uint8_t*>(sh.q[1]) + lo, hi - lo, threadIdx.x - 32);
-        bar_all();
-        if (threadIdx.x == 0) {
-            fence_sys();  // this CTA's stores are performed (cumulative through the barrier) ...
-            atom_add_acq_rel_gpu(&a.mail->arrived, 1u);  // ... before the leader can count it in
-        }
-        seen = s;
-        bar_all();  // sh is rewritten by the next round
-    }
-}
-
 __global__ void __launch_bounds__(kThreads)
     kv_doorbell_kernel(const __grid_constant__ DoorbellLaunch a) {
     __shared__ Shared sh;
-    if (blockIdx.x != 0) {
-        helper_cta(a, sh);
-        return;
-    }
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t helpers = gridDim.x - 1;
-    uint32_t shared_rounds = 0;  // large blocks so far: helpers have arrived helpers * this often
     uint64_t next = a.first_seq;
     unsigned long long idle_since = globaltimer_ns();
     if (threadIdx.x == 0)
@@ -178,19 +110,6 @@ __global__ void __launch_bounds__(kThreads)
     pub.status = nullptr;
     pub.sys = a.sys;
     pub.shards = a.shards;
-    // large block: hand the addresses to the helpers (thread 0), copy slice 0, wait for them
-    auto publish_to_helpers = [&](uint64_t src, uint64_t dst, uint32_t bytes) {
-        *reinterpret_cast<volatile uint64_t*>(&a.mail->src) = src;
-        *reinterpret_cast<volatile uint64_t*>(&a.mail->dst) = dst;
-        *reinterpret_cast<volatile uint32_t*>(&a.mail->bytes) = bytes;
-        st_release_gpu_u64(&a.mail->seq, next);
-    };
-    auto wait_for_helpers = [&]() {  // thread 0, after the leader's own slice
-        const uint32_t want = helpers * shared_rounds;
-        const unsigned long long t0 = globaltimer_ns();
-        while (ld_acquire_gpu_u32(&a.mail->arrived) != want)
-            if (globaltimer_ns() - t0 > 4000000000ull) __trap();  // a lost helper is a bug
-    };
     for (;;) {
         // ---- poll: one coalesced 64-byte read of the request line over PCIe
         if (warp == 0) {
@@ -213,7 +132,6 @@ __global__ void __launch_bounds__(kThreads)
         const uint32_t have = sh.have;
         if (have == 2 || (have == 1 && (sh.q[0] & 3) == kDoorbellStop)) {
             if (threadIdx.x == 0) {
-                if (helpers) st_release_gpu_u64(&a.mail->seq, kDoorbellQuit);
                 const uint64_t at = have == 1 ? next + 1 : next;  // a STOP request is consumed
                 if (have == 1) {
                     st_relaxed_sys_u32(&a.ctl->status[next % a.slots], kDoorbellOk);
@@ -231,37 +149,27 @@ __global__ void __launch_bounds__(kThreads)
         const uint32_t op = uint32_t(sh.q[0] & 3);
         const uint64_t local = sh.q[1];
         const uint32_t bytes = uint32_t(sh.q[6] >> 32);
-        const bool split = helpers && bytes > kDoorbellSoloBytes;  // uniform over the CTA
-        if (split) ++shared_rounds;
-        uint32_t lo = 0, hi = bytes;
-        if (split) slice_of(bytes, 0, gridDim.x, &lo, &hi);
         uint32_t status = kDoorbellOk;
         if (op == kDoorbellWrite) {
             uint32_t slot = 0;
             const IndexEntry rec{sh.q[3], sh.q[4], sh.q[5], uint32_t(sh.q[6]), bytes};
             if (warp == 0) {
-                if (lane == 0) {
-                    if (split) publish_to_helpers(local, sh.q[2], bytes);
-                    // claim (one CAS round trip) while the copy warps move the block
-                    if (a.table && rec.h1) {
-                        bool full = false;
-                        const idx::TableRef t = idx::select_shard(pub.table, pub.mask, pub.shards, rec.h2);
-                        slot = idx::pack_slot(t.shard, idx::claim(t.table, t.mask, rec, pub.sys, &full));
-                        if (full) status = kDoorbellIndexFull;
-                    }
+                // claim (one CAS round trip) while the copy warps move the block
+                if (lane == 0 && a.table && rec.h1) {
+                    bool full = false;
+                    const idx::TableRef t = idx::select_shard(pub.table, pub.mask, pub.shards, rec.h2);
+                    slot = idx::pack_slot(t.shard, idx::claim(t.table, t.mask, rec, pub.sys, &full));
+                    if (full) status = kDoorbellIndexFull;
                 }
             } else {
-                copy_block(reinterpret_cast<uint8_t*>(sh.q[2]) + lo,
-                           reinterpret_cast<const uint8_t*>(local) + lo, hi - lo, threadIdx.x - 32);
+                copy_block(reinterpret_cast<uint8_t*>(sh.q[2]), reinterpret_cast<const uint8_t*>(local),
+                           bytes, threadIdx.x - 32);
             }
             bar_all();  // the copy warps' stores are ordered before the release below (CTA scope)
             if (threadIdx.x == 0) {
-                // the helpers fenced their slices before they counted themselves in
-                if (split) wait_for_helpers();
                 // In-band commit.  st.release.sys = MEMBAR.SYS + store: cumulative over the
-                // stores of the whole CTA (they happen-before through the barrier) and of the
-                // helpers (through the counter), so a reader on any GPU that observes the tag
-                // observes the block.
+                // stores of the whole CTA (they happen-before through the barrier), so a reader
+                // on any GPU that observes the tag observes the block.
                 if (slot) {
                     IndexBucket* tb = idx::table_of_slot(pub.table, pub.shards, slot);
                     st_release_sys(&idx::way_of(tb, idx::slot_local(slot) - 1)->tag, rec.tag);
@@ -281,9 +189,6 @@ __global__ void __launch_bounds__(kThreads)
                     if (f.size >= bytes && seg < a.nsegs && a.seg_base[seg])
                         src = a.seg_base[seg] + (f.addr & ((1ull << 44) - 1));
                 }
-                // a miss still takes the helpers through a (zero-length) round: the count of
-                // arrivals stays in step with shared_rounds
-                if (split) publish_to_helpers(src, local, src ? bytes : 0);
                 sh.pool_addr = src;
                 sh.slot = src ? f.slot_plus1 : 0;
                 sh.tag = f.tag;
@@ -291,11 +196,10 @@ __global__ void __launch_bounds__(kThreads)
             bar_all();
             const uint64_t src = sh.pool_addr;
             if (warp != 0 && src)
-                copy_block(reinterpret_cast<uint8_t*>(local) + lo,
-                           reinterpret_cast<const uint8_t*>(src) + lo, hi - lo, threadIdx.x - 32);
+                copy_block(reinterpret_cast<uint8_t*>(local), reinterpret_cast<const uint8_t*>(src),
+                           bytes, threadIdx.x - 32);
             bar_all();
             if (threadIdx.x == 0) {
-                if (split) wait_for_helpers();  // every slice has been read from the pool
                 if (!src)
                     status = kDoorbellMiss;
                 else if (!idx::still_valid(idx::table_of_slot(a.table, a.shards, sh.slot),
@@ -320,8 +224,7 @@ __global__ void __launch_bounds__(kThreads)
 cudaError_t launch_kv_doorbell(const DoorbellLaunch& a, cudaStream_t stream) {
     if (!a.ring || !a.ctl || a.slots == 0 || a.slots > uint32_t(kDoorbellMaxSlots))
         return cudaErrorInvalidValue;
-    const int ctas = a.mail ? std::max(1, std::min(a.ctas, kDoorbellMaxCtas)) : 1;
-    kv_doorbell_kernel<<<ctas, kThreads, 0, stream>>>(a);
+    kv_doorbell_kernel<<<1, kThreads, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -319,8 +319,7 @@ PYBIND11_MODULE(_infinistore, m) {
         .def_readwrite("pool_hint", &ClientConfig::pool_hint)
         .def_readwrite("posted_commit", &ClientConfig::posted_commit)
         .def_readwrite("doorbell", &ClientConfig::doorbell)
-        .def_readwrite("doorbell_idle_us", &ClientConfig::doorbell_idle_us)
-        .def_readwrite("doorbell_ctas", &ClientConfig::doorbell_ctas);
+        .def_readwrite("doorbell_idle_us", &ClientConfig::doorbell_idle_us);
 
     py::class_<ServerConfig>(m, "ServerConfig")
         .def(py::init<>())

@@ -57,8 +57,7 @@ class ClientConfig(_infinistore.ClientConfig):
     lookups of OTHER connections follow within the TCP delivery time, as in the reference.
     ``pipe_stage_kb`` / ``pipe_ring_kb``: ring geometry of the TMA pipeline (0 = default).
     ``doorbell`` (default False): latency mode - writes and device-index reads of ONE block of
-    at most 1 MB are handed to a persistent worker (a leader CTA plus ``doorbell_ctas - 1``
-    helpers that share blocks of more than 64 KB) through a request ring in pinned host
+    at most 256 KB are handed to a persistent worker CTA through a request ring in pinned host
     memory instead of launching a kernel (no launch, no event, completion seen by polling host
     memory in ``sync()``); the worker leaves after ``doorbell_idle_us`` (default 200) without
     a request, so a device-wide ``torch.cuda.synchronize()`` waits at most that long for it.
@@ -89,7 +88,6 @@ class ClientConfig(_infinistore.ClientConfig):
         self.pipe_ring_kb = int(kwargs.get("pipe_ring_kb", 0))
         self.doorbell = bool(kwargs.get("doorbell", False))
         self.doorbell_idle_us = int(kwargs.get("doorbell_idle_us", 200))
-        self.doorbell_ctas = int(kwargs.get("doorbell_ctas", 8))
 
     def __repr__(self):
         return (
