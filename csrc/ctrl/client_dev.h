@@ -92,8 +92,7 @@ struct Connection::DevCtx {
         uint32_t epoch = 0;      // launch counter
         bool running = false;    // a launch of `epoch` has not been seen to exit
         uint64_t next_serve = 1;  // first request the next launch serves
-        uint64_t signature = 0;   // pool / index view the running worker was launched with
-        size_t nsegs = 0;         // segments known at that launch
+        size_t nsegs = 0;         // pool segments known when the running worker was launched
         uint32_t misses = 0, stale = 0, publish_failures = 0;  // since the last drain
     };
     std::unique_ptr<Doorbell> db;

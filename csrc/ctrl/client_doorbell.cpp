@@ -67,22 +67,18 @@ int Connection::doorbell_start(DevCtx* ctx) {
     L.slots = uint32_t(kernels::kDoorbellMaxSlots);
     L.idle_ns = uint64_t(std::max(cfg_.doorbell_idle_us, 10)) * 1000;
     L.nsegs = uint32_t(std::min<size_t>(segs_.size(), kernels::DoorbellLaunch::kMaxSegs));
-    uint64_t sig = 1469598103934665603ull;
-    auto mix_in = [&](uint64_t v) { sig = (sig ^ v) * 1099511628211ull; };
     for (uint32_t s = 0; s < L.nsegs; ++s) {
+        // HBM segments and the local replica of an NVLS region; a host-shm tier is not
+        // device-addressable (a block there reads as a miss and the caller falls back)
         uint8_t* base = nullptr;
-        if (segs_[s].kind == kSegDeviceIpc) base = seg_dev_ptr(ctx, s);
+        if (segs_[s].kind != kSegHostShm) base = seg_dev_ptr(ctx, s);
         L.seg_base[s] = reinterpret_cast<uint64_t>(base);
-        mix_in(L.seg_base[s]);
     }
     if (segs_[0].index_slots && L.seg_base[0]) {
         L.table = reinterpret_cast<kernels::IndexBucket*>(L.seg_base[0] + segs_[0].index_off);
         L.table_mask = kernels::index_bucket_mask(segs_[0].index_slots);
         L.shards = index_shards(ctx, nullptr);
     }
-    mix_in(segs_.size());
-    mix_in(reinterpret_cast<uint64_t>(L.table));
-    mix_in(L.shards.n);
     L.epoch = ++db.epoch;
     L.first_seq = db.next_serve;
     const cudaError_t e = kernels::launch_kv_doorbell(L, db.stream);
@@ -90,7 +86,6 @@ int Connection::doorbell_start(DevCtx* ctx) {
         fail(std::string("doorbell worker failed to launch: ") + cudaGetErrorString(e));
         return -1;
     }
-    db.signature = sig;
     db.nsegs = segs_.size();
     db.running = true;
     stats_.doorbell_launches++;
