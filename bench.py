@@ -615,14 +615,32 @@ def main():
         h2d_bytes = size_bytes * rounds
         d2h_bytes = (elems + 1) * 2
 
+        # The inputs of round r+1 stream in over PCIe (their own stream, one event per layer)
+        # while round r is read back: `src` is free as soon as the write phase has been
+        # sync()ed.  Without this the link idles for the whole read phase of every round
+        # (7 ms of 88 at N >= 2: the store's time then shows up 1:1 in the end-to-end number).
+        copy_stream = torch.cuda.Stream(device=dev)
+        layer_ready = [torch.cuda.Event() for _ in range(layers)]
+
+        def h2d_round():
+            copy_stream.wait_stream(stream)      # whatever still reads `src` has been issued
+            with torch.cuda.stream(copy_stream):
+                for l in range(layers):
+                    a, b = l * per_layer, (l + 1) * per_layer
+                    src[a * elems:b * elems].copy_(host_src[a * elems:b * elems], non_blocking=True)
+                    layer_ready[l].record(copy_stream)
+
         def e2e_step(prepared):
             with torch.cuda.stream(stream):
-                for remote, blocks in prepared:
+                h2d_round()
+                for i, (remote, blocks) in enumerate(prepared):
                     for l in range(layers):
                         a, b = l * per_layer, (l + 1) * per_layer
-                        src[a * elems:b * elems].copy_(host_src[a * elems:b * elems], non_blocking=True)
+                        stream.wait_event(layer_ready[l])   # the page mover waits for `stream`
                         conn.rdma_write_cache(src, offsets_np[a:b], elems, remote[a:b])
                     conn.sync()
+                    if i + 1 < len(prepared):
+                        h2d_round()
                     for l in range(layers):
                         a, b = l * per_layer, (l + 1) * per_layer
                         conn.read_cache(dst, blocks[a:b], elems)
@@ -661,7 +679,11 @@ def main():
         e2e = {"value": round(world * bytes_per_step * e2e_steps / dt_max / 1e9, 2), "unit": "GB/s",
                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                "steps": e2e_steps, "ms_per_step": round(dt_max / e2e_steps * 1e3, 3),
-               "pinned_numa_node": numa_node}
+               "pinned_numa_node": numa_node,
+               "how": "per round: pinned host pages -> H2D layer by layer on a copy stream, each "
+                      "layer written as soon as it has landed; sync; read back; sync - the next "
+                      "round's H2D runs under the read phase; D2H of one page + the check flag "
+                      "at the end of the step"}
         del host_src
 
     # ---- extras: latency percentiles, emulated baselines, BASELINE.json configs 3-5
