@@ -941,3 +941,50 @@ def test_doorbell_mode_is_inert_without_a_gpu_pool(host_server):
     conn.sync()
     assert torch.equal(src, dst)
     assert conn.stats()["doorbell_ops"] == 0 and conn.stats()["doorbell_launches"] == 0
+
+
+def test_one_connection_shared_by_four_threads(host_server):
+    """The native connection serialises its control plane (one transaction at a time), its
+    data-plane bookkeeping and sync(); four threads that share ONE InfinityConnection - the
+    GIL is released inside every native call - allocate, write, sync and read their own keys
+    concurrently.  A sync() of one thread may commit the finished writes of another; it must
+    never commit an unfinished one or lose one."""
+    import threading
+
+    srv, port = host_server
+    conn = make_conn(port)
+    errors = []
+
+    def worker(tid):
+        try:
+            rng = np.random.default_rng(100 + tid)
+            src = torch.zeros(8 * 1024)
+            dst = torch.zeros(8 * 1024)
+            conn.register_mr(src)
+            conn.register_mr(dst)
+            for it in range(40):
+                n = int(rng.integers(1, 9))
+                keys = [f"shared-t{tid}-i{it}-b{b}" for b in range(n)]
+                for b in range(n):
+                    src[b * 1024:(b + 1) * 1024] = float(tid * 1000000 + it * 10 + b)
+                blocks = conn.allocate_rdma(keys, 4096)
+                conn.rdma_write_cache(src, [b * 1024 for b in range(n)], 1024, blocks)
+                conn.sync()
+                assert conn.get_match_last_index(keys) == n - 1
+                dst.zero_()
+                conn.read_cache(dst, [(k, b * 1024) for b, k in enumerate(keys)], 1024)
+                conn.sync()
+                if not torch.equal(dst[:n * 1024], src[:n * 1024]):
+                    errors.append(("mismatch", tid, it))
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors, errors[:3]
+    st = srv.stats()
+    assert st["inflight"] == 0 and st["keys"] == srv.kvmap_len()
+    conn.close()
