@@ -652,3 +652,53 @@ def test_doorbell_worker_idle_exit_races_and_ring_wrap(hbm_server):
         st = c.stats()
         assert st["doorbell_ops"] > 500 and st["doorbell_launches"] >= 5
         c.close()
+
+
+@pytest.mark.parametrize("doorbell", [False, True])
+def test_one_connection_shared_by_threads_on_the_gpu_path(hbm_server, doorbell):
+    """Four threads share ONE connection to an HBM pool: launches, the pinned descriptor ring,
+    the doorbell ring and sync() are serialised inside the connection; every thread reads back
+    exactly what it wrote (batches and single blocks mixed)."""
+    import threading
+
+    srv, port = hbm_server
+    conn = make_conn(port, device_lookup=True, doorbell=doorbell)
+    errors = []
+
+    def worker(tid):
+        try:
+            torch.cuda.set_device(0)
+            rng = random.Random(tid)
+            elems = 4096
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                src = torch.zeros(16 * elems, device="cuda:0")
+                dst = torch.zeros(16 * elems, device="cuda:0")
+                conn.register_mr(src)
+                conn.register_mr(dst)
+                for it in range(30):
+                    n = rng.choice([1, 1, 2, 7, 16])
+                    keys = [f"thr-{doorbell}-t{tid}-i{it}-b{b}-{rand_key(4)}" for b in range(n)]
+                    src.copy_(torch.randn(16 * elems, device="cuda:0"))
+                    stream.synchronize()
+                    blocks = conn.allocate_rdma(keys, elems * 4)
+                    conn.rdma_write_cache(src, [b * elems for b in range(n)], elems, blocks)
+                    conn.sync()
+                    dst.zero_()
+                    stream.synchronize()
+                    conn.read_cache(dst, [(k, b * elems) for b, k in enumerate(keys)], elems)
+                    conn.sync()
+                    stream.synchronize()
+                    if not torch.equal(dst[:n * elems], src[:n * elems]):
+                        errors.append(("mismatch", tid, it, n))
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(180)
+    assert not errors, errors[:3]
+    assert srv.stats()["inflight"] == 0
+    conn.close()
