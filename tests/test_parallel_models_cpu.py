@@ -163,3 +163,34 @@ def test_examples_run_on_cpu(host_server, monkeypatch, capsys):
     client_async.main()
     out = capsys.readouterr().out
     assert "fabric cpu->cpu" in out and "iteration 1: ok" in out
+
+
+def test_head_major_cache_geometry_and_shared_key_scheme():
+    """HeadMajorKVCache (decode side) and PagedKVCache (prefill side) must agree on keys - the
+    decode instance fetches what prefill uploaded - and the head-major page is the permuted
+    token-major page."""
+    from infinistore_b200.models import HeadMajorKVCache, layer_keys, read_layer_multi
+
+    layout = KVLayout("geo", layers=3, kv_heads=4, head_dim=8, page_tokens=16, tp=2)
+    a = PagedKVCache(layout, num_pages=5, device="cpu", tp_rank=1)
+    h = HeadMajorKVCache(layout, num_pages=5, device="cpu", tp_rank=1)
+    assert layout.heads_per_rank == 2 and layout.page_elems == 16 * 2 * 8
+    assert h.data.shape == (3, 2, 5, 2, 16, 8) and a.data.shape == (3, 2, 5, 16 * 2 * 8)
+    hashes = chain_hashes(list(range(16 * 3)), 16, salt="geo")
+    for layer in range(3):
+        for kv in (0, 1):
+            assert a.keys(layer, kv, hashes) == h.keys(layer, kv, hashes) == \
+                layer_keys(layout, 1, layer, kv, hashes)
+    assert a.keys(0, 0, hashes)[0] != a.keys(0, 1, hashes)[0] != a.keys(1, 0, hashes)[0]
+    assert "/tp1/" in a.keys(2, 1, hashes)[0] and "/L2/V/" in a.keys(2, 1, hashes)[0]
+    # page_token_major is a VIEW of the head-major page
+    h.data[1, 0, 3].copy_(torch.arange(2 * 16 * 8, dtype=layout.dtype).view(2, 16, 8))
+    tm = h.page_token_major(1, 0, 3)
+    assert tm.shape == (16, 2, 8) and tm[5, 1, 7] == h.data[1, 0, 3, 1, 5, 7]
+    # read_layer_multi insists on caches that really are replicas of one another
+    b = PagedKVCache(layout, num_pages=6, device="cpu", tp_rank=1)
+    with pytest.raises(ValueError):
+        read_layer_multi(None, [a, b], 0, [0], hashes[:1])
+    c = PagedKVCache(layout, num_pages=5, device="cpu", tp_rank=0)
+    with pytest.raises(ValueError):
+        read_layer_multi(None, [a, c], 0, [0], hashes[:1])
