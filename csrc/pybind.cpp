@@ -176,10 +176,44 @@ struct KeyArena {
 
 thread_local KeyArena t_arena;
 
-// [(key, offset), ...] -> KeyOffset views (offset * scale bytes)
+// [(key, offset), ...] -> KeyOffset views (offset * scale bytes).  Also accepted: the pair
+// (keys, offsets) with `keys` a sequence of str / bytes and `offsets` an integer ndarray of the
+// same length - callers that hold their offsets in numpy anyway skip one heap object and one
+// integer conversion per block (the walk below is bound by exactly those cache misses).
 void blocks_list_from_py(const py::object& obj, uint64_t scale, std::vector<KeyOffset>& out) {
     KeyArena& a = t_arena;
     a.clear();
+    if (PyTuple_Check(obj.ptr()) && PyTuple_GET_SIZE(obj.ptr()) == 2 &&
+        py::isinstance<py::array>(py::handle(PyTuple_GET_ITEM(obj.ptr(), 1)))) {
+        auto offs = py::array_t<int64_t, py::array::c_style | py::array::forcecast>::ensure(
+            py::reinterpret_borrow<py::object>(PyTuple_GET_ITEM(obj.ptr(), 1)));
+        if (!offs || offs.ndim() != 1) throw py::type_error("offsets must be a 1-D integer array");
+        PyObject* seq = PySequence_Fast(PyTuple_GET_ITEM(obj.ptr(), 0), "keys must be a sequence of str");
+        if (!seq) throw py::error_already_set();
+        const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);
+        if (n != offs.shape(0)) {
+            Py_DECREF(seq);
+            throw py::value_error("keys and offsets differ in length");
+        }
+        PyObject** items = PySequence_Fast_ITEMS(seq);
+        try {
+            for (Py_ssize_t i = 0; i < n; ++i) {
+                if (i + 8 < n) __builtin_prefetch(items[i + 8]);
+                a.add(items[i]);
+            }
+        } catch (...) {
+            Py_DECREF(seq);
+            throw;
+        }
+        Py_DECREF(seq);
+        const int64_t* o = offs.data();
+        out.resize(size_t(n));
+        for (size_t i = 0; i < size_t(n); ++i) {
+            if (o[i] < 0) throw py::value_error("negative offset");
+            out[i] = KeyOffset{a.view(i), uint64_t(o[i]) * scale};
+        }
+        return;
+    }
     PyObject* seq = PySequence_Fast(obj.ptr(), "blocks must be a sequence of (key, offset)");
     if (!seq) throw py::error_already_set();
     const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);

@@ -524,7 +524,9 @@ class InfinityConnection:
     # ------------------------------------------------------------------ reads
     def read_cache(self, cache: torch.Tensor, blocks: List[Tuple[str, int]], page_size: int,
                    stream="current"):
-        """Read pages into ``cache``.  ``blocks`` = [(key, offset_in_elements)].
+        """Read pages into ``cache``.  ``blocks`` = [(key, offset_in_elements)], or the pair
+        ``(keys, offsets)`` with ``offsets`` an integer ndarray (one heap object less per block
+        for callers that keep offsets in numpy).
 
         Raises if a key is missing or not committed (with ``device_lookup`` the miss is
         detected on the GPU and reported by ``sync()``).

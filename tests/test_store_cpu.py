@@ -988,3 +988,32 @@ def test_one_connection_shared_by_four_threads(host_server):
     st = srv.stats()
     assert st["inflight"] == 0 and st["keys"] == srv.kvmap_len()
     conn.close()
+
+
+def test_blocks_as_keys_plus_offset_array(host_server):
+    """read_cache / local calls also take (keys, offsets) with an integer ndarray of offsets
+    instead of a list of (key, offset) pairs."""
+    _, port = host_server
+    conn = make_conn(port)
+    n, page = 12, 1024
+    src = torch.randn(n * page)
+    dst = torch.zeros_like(src)
+    conn.register_mr(src)
+    conn.register_mr(dst)
+    keys = [f"split-{i}" for i in range(n)]
+    offs = np.arange(n, dtype=np.int64) * page
+    conn.rdma_write_cache(src, offs, page, conn.allocate_rdma(keys, page * 4))
+    conn.sync()
+    conn.read_cache(dst, (keys, offs[::-1].copy()), page)      # reversed placement
+    conn.sync()
+    assert torch.equal(dst.view(n, page), src.view(n, page).flip(0))
+    dst.zero_()
+    conn.read_cache(dst, (keys, offs.astype(np.int32)), page)  # any integer dtype
+    conn.sync()
+    assert torch.equal(dst, src)
+    with pytest.raises(Exception):
+        conn.read_cache(dst, (keys, offs[:-1]), page)           # lengths differ
+    with pytest.raises(Exception):
+        conn.read_cache(dst, (keys, -offs - 1), page)           # negative offset
+    conn.read_cache(dst, [(keys[0], 0), (keys[1], page)], page)  # the pair form is untouched
+    conn.sync()
