@@ -1,46 +1,20 @@
 """infinistore_b200 — a Blackwell-native KV-cache block store with infiniStore's API.
 
-Same public surface as the reference package (infinistore/__init__.py:1-31); see
-``lib.py`` for what changes underneath.
+The package exports the reference's public names (its ``infinistore/__init__.py``) plus the
+additions of this implementation; everything lives in ``lib.py``.
 """
-from .lib import (
-    InfinityConnection,
-    DisableTorchCaching,
-    ClientConfig,
-    ServerConfig,
-    TYPE_RDMA,
-    TYPE_LOCAL_GPU,
-    Logger,
-    check_supported,
-    LINK_ETHERNET,
-    LINK_IB,
-    register_server,
-    stop_server,
-    server_stats,
-    purge_kv_map,
-    get_kvmap_len,
-    dump_kv_map,
-    load_kv_map,
-)
+from . import lib as _lib
 
 __version__ = "0.1.0"
 
-__all__ = [
-    "InfinityConnection",
-    "DisableTorchCaching",
-    "register_server",
-    "stop_server",
-    "server_stats",
-    "ClientConfig",
-    "ServerConfig",
-    "TYPE_RDMA",
-    "TYPE_LOCAL_GPU",
-    "Logger",
-    "check_supported",
-    "LINK_ETHERNET",
-    "LINK_IB",
-    "purge_kv_map",
-    "get_kvmap_len",
-    "dump_kv_map",
-    "load_kv_map",
-]
+# what a program written against the reference imports from the package
+_REFERENCE_SURFACE = (
+    "ClientConfig", "ServerConfig", "InfinityConnection", "DisableTorchCaching", "Logger",
+    "TYPE_RDMA", "TYPE_LOCAL_GPU", "LINK_ETHERNET", "LINK_IB",
+    "register_server", "purge_kv_map", "get_kvmap_len", "check_supported",
+)
+# added here: in-process server control, statistics, checkpoint / resume
+_ADDITIONS = ("stop_server", "server_stats", "dump_kv_map", "load_kv_map")
+
+__all__ = [*_REFERENCE_SURFACE, *_ADDITIONS]
+globals().update({_name: getattr(_lib, _name) for _name in __all__})
