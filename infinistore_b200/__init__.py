@@ -5,7 +5,12 @@ additions of this implementation; everything lives in ``lib.py``.
 """
 from . import lib as _lib
 
-__version__ = "0.1.0"
+try:  # the installed distribution knows its version (setup.py: git describe)
+    from importlib.metadata import PackageNotFoundError as _NotInstalled, version as _version
+
+    __version__ = _version("infinistore-b200")
+except _NotInstalled:  # run from the source tree
+    __version__ = "0.2.0.dev0"
 
 # what a program written against the reference imports from the package
 _REFERENCE_SURFACE = (
