@@ -36,3 +36,16 @@ def test_server_and_client_loopback_under_asan_ubsan():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-6000:]
     assert "0 failed" in r.stdout
     assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr
+
+
+def test_server_and_client_loopback_under_tsan():
+    """The same binary under ThreadSanitizer: the reactor thread, the async completion thread
+    and the client threads of the loop-back scenarios race-free."""
+    from tools import build_native
+
+    exe = build_native.build_loopback_test(sanitize="thread")
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0:second_deadlock_stack=1")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-6000:]
+    assert "0 failed" in r.stdout
+    assert "WARNING: ThreadSanitizer" not in r.stderr
