@@ -1,6 +1,7 @@
 from __future__ import annotations
 
 import os
+import subprocess
 import threading
 from typing import Callable, List, Sequence
 
@@ -32,47 +33,75 @@ def percentile(sorted_values: Sequence[float], q: float) -> float:
 
 
 class ClockSampler(threading.Thread):
-    """SM clock / throttle-reason sampler (NVML in-process) for timed regions."""
+    """Samples SM clocks / throttle reasons of one GPU while the timed region runs.  Uses
+    NVML in-process (a `nvidia-smi` subprocess every 200 ms takes driver-wide locks long
+    enough to perturb a launch-latency-sensitive loop); falls back to nvidia-smi."""
 
-    def __init__(self, index: int, period_s: float = 0.1):
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
         super().__init__(daemon=True)
-        self.period = period_s
-        self.samples: List[int] = []
+        self.index = index
+        self.samples = []
         self.reasons = set()
         self.max_mhz = 0
         self._stop_ev = threading.Event()
-        self._n = None
+        self._nvml = None
         try:
             import pynvml
 
             pynvml.nvmlInit()
+            idx = index
             vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
-            idx = int(vis.split(",")[index]) if vis else index
+            if vis:
+                idx = int(vis.split(",")[index])
             self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            self._n = pynvml
+            self._nvml = pynvml
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
         except Exception:  # noqa: BLE001
-            self._n = None
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        self.samples.append(int(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        for name, bit in (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown),
+                          ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown),
+                          ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(
+            ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+             "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5
+        ).stdout.strip().split(",")
+        if len(out) >= 6:
+            self.samples.append(int(float(out[0])))
+            self.max_mhz = int(float(out[1]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown",
+                                "sw_thermal_slowdown", "sw_power_cap"), out[2:6]):
+                if v.strip().lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
-        n = self._n
-        while n is not None and not self._stop_ev.is_set():
+        while not self._stop_ev.is_set():
             try:
-                self.samples.append(int(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
-                r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
-                for name, bit in (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown),
-                                  ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
-                                  ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown),
-                                  ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap)):
-                    if r & bit:
-                        self.reasons.add(name)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:  # noqa: BLE001
                 pass
-            self._stop_ev.wait(self.period)
+            self._stop_ev.wait(0.1 if self._nvml is not None else 0.5)
 
-    def stop(self) -> dict:
+    def stop(self):
         self._stop_ev.set()
         self.join(timeout=5)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz or None,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+                "reasons": sorted(self.reasons), "samples": len(s),
+                "source": "nvml" if self._nvml is not None else "nvidia-smi"}

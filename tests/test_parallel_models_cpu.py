@@ -194,3 +194,22 @@ def test_head_major_cache_geometry_and_shared_key_scheme():
     c = PagedKVCache(layout, num_pages=5, device="cpu", tp_rank=0)
     with pytest.raises(ValueError):
         read_layer_multi(None, [a, c], 0, [0], hashes[:1])
+
+
+def test_timing_utilities_without_a_gpu():
+    """percentile() and the clock sampler bench.py uses (NVML, falling back to nvidia-smi);
+    on a box with neither the sampler reports nothing rather than failing the run."""
+    import time
+
+    from infinistore_b200.utils import ClockSampler, percentile
+
+    vals = sorted([5.0, 1.0, 3.0, 2.0, 4.0])
+    assert percentile(vals, 0) == 1.0 and percentile(vals, 50) == 3.0 and percentile(vals, 100) == 5.0
+    assert percentile(vals, 99) == 5.0 and percentile([], 50) != percentile([], 50)   # nan
+    s = ClockSampler(0)
+    s.start()
+    time.sleep(0.15)
+    out = s.stop()
+    assert set(out) == {"sm_mhz", "sm_max_mhz", "reasons", "samples", "source"}
+    assert out["source"] in ("nvml", "nvidia-smi") and isinstance(out["reasons"], list)
+    assert (out["samples"] == 0) == (out["sm_mhz"] is None)
